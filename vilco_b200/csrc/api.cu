@@ -1,0 +1,21 @@
+// Error state, launch counter and version of the C-ABI library.
+#include <stdarg.h>
+#include <atomic>
+#include "common.cuh"
+
+namespace vilco {
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+}  // namespace vilco
+
+extern "C" const char* vilco_last_error(void) { return vilco::g_err; }
+extern "C" int vilco_version(void) { return 1; }
+extern "C" uint64_t vilco_launch_count(void) { return vilco::g_launches.load(std::memory_order_relaxed); }

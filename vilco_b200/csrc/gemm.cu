@@ -1,0 +1,488 @@
+// Dense contraction kernel for every GEMM-shaped op on the Moment-Query path (see include/vilco_b200.h).
+//
+// tcgen05 path: one 128 x BN output tile per CTA.  Warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle),
+// warp 1 = TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM),
+// warps 2..5 = epilogue (tcgen05.ld 32x32b, fused bias / row-mask / activation / channel-scale / residual).
+// A k=3 convolution is three row-shifted TMA loads of the same activation tile accumulating into the same
+// TMEM tile; TMA out-of-bounds zero fill implements the conv zero padding and every M/N/K tail.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+#include "common.cuh"
+
+namespace vilco {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;            // 64 bf16 = 128 bytes = one swizzle-128B atom row
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_THREADS = 192;  // 6 warps
+
+struct GemmDev {
+  // coordinate slots: the three outer tensor-map dims are sorted by stride on the host
+  int a_slot_row, a_slot_z1, a_slot_z2;
+  int b_slot_row, b_slot_z1, b_slot_z2;
+  int M, N, K, taps, Z1;
+  int b_major, b_batched;
+  void* D; int d_dtype; long long d_ld, d_s1, d_s2;
+  float alpha;
+  const float* bias;
+  const float* rowmul; long long rowmul_zs;
+  int act;
+  const float* colscale;
+  const float* resid; int resid_masked;
+  int vec_ok;  // 16-byte aligned vector stores allowed
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, 128B swizzle, sm_100 (version = 1)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);             // start address      bits [0,14)
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;    // leading byte off   bits [16,30)
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;    // stride byte off    bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                             // descriptor version bits [46,48)
+  d |= static_cast<uint64_t>(2) << 61;                             // SWIZZLE_128B       bits [61,64)
+  return d;
+}
+
+// instruction descriptor for kind::f16: bf16 x bf16 -> f32, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn_major) {
+  return (1u << 4)                                   // c_format = F32
+         | (1u << 7)                                 // a_format = BF16
+         | (1u << 10)                                // b_format = BF16
+         | (0u << 15)                                // a_major  = K
+         | (static_cast<uint32_t>(b_mn_major) << 16) // b_major
+         | (static_cast<uint32_t>(n >> 3) << 17)     // n_dim
+         | (static_cast<uint32_t>(BM >> 4) << 24);   // m_dim
+}
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+};
+
+// ---------------------------------------------------------------------------------------------
+// epilogue math shared by both implementations
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float epi_value(const GemmDev& p, float acc, int n, float rm, float res) {
+  float v = acc * p.alpha;
+  if (p.bias) v += __ldg(p.bias + n);
+  v *= rm;
+  v = apply_act(v, p.act);
+  if (p.colscale) v *= __ldg(p.colscale + n);
+  return v + res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ GemmDev p) {
+  using L = SmemLayout<BN>;
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int z = blockIdx.z;
+  const int z1 = z % p.Z1, z2 = z / p.Z1;
+
+  const uint32_t full0 = smem_u32(bars);
+  const uint32_t empty0 = smem_u32(bars + STAGES);
+  const uint32_t tfull = smem_u32(bars + 2 * STAGES);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kblocks = (p.K + BK - 1) / BK;
+  const int iters = p.taps * kblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int ca[4], cb[4];
+      ca[p.a_slot_z1] = z1; ca[p.a_slot_z2] = z2;
+      cb[p.b_slot_z2] = p.b_batched ? z2 : 0;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const int tap = it / kblocks;
+        const int kb = it - tap * kblocks;
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+        mbar_expect_tx(full0 + 8 * s, L::STAGE_BYTES);
+        ca[0] = kb * BK;
+        ca[p.a_slot_row] = m0 + tap - (p.taps >> 1);
+        tma_load_4d(sa, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3]);
+        cb[p.b_slot_z1] = p.b_batched ? z1 : tap;
+        if (p.b_major == 0) {
+          cb[0] = kb * BK;
+          cb[p.b_slot_row] = n0;
+        } else {
+          cb[0] = n0;
+          cb[p.b_slot_row] = kb * BK;
+        }
+        tma_load_4d(sb, &tmB, full0 + 8 * s, cb[0], cb[1], cb[2], cb[3]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    const uint32_t idesc = make_idesc(BN, p.b_major);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(full0 + 8 * s, ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major: advance 16 elements = 32 bytes inside the swizzle atom.
+          const uint64_t adesc = make_smem_desc(sa + k * UMMA_K * 2, 16, 1024);
+          // MN-major: advance 16 k-rows of 128 bytes.
+          const uint64_t bdesc = p.b_major == 0 ? make_smem_desc(sb + k * UMMA_K * 2, 16, 1024)
+                                                : make_smem_desc(sb + k * UMMA_K * 128, 16, 1024);
+          tcgen05_mma_f16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tcgen05_commit(empty0 + 8 * s);            // frees the smem stage when these MMAs retire
+        if (it == iters - 1) tcgen05_commit(tfull);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+    const int q = warp & 3;
+    mbar_wait(tfull, 0);
+    tcgen05_fence_after();
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
+    float rm = 1.0f;
+    if (p.rowmul && row_ok) rm = __ldg(p.rowmul + z2 * p.rowmul_zs + m);
+    const float rres = p.resid_masked ? rm : 1.0f;
+    const long long doff = z1 * p.d_s1 + z2 * p.d_s2 + (long long)m * p.d_ld;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      const int nb = n0 + c * 32;
+      if (!row_ok || nb >= p.N) continue;
+      float v[32];
+      const bool full = (nb + 32 <= p.N) && p.vec_ok;
+      if (full) {
+        if (p.resid) {
+          const float4* rp = reinterpret_cast<const float4*>(p.resid + doff + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 t = rp[j];
+            v[4 * j + 0] = t.x * rres; v[4 * j + 1] = t.y * rres; v[4 * j + 2] = t.z * rres; v[4 * j + 3] = t.w * rres;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = epi_value(p, __uint_as_float(r[j]), nb + j, rm, v[j]);
+        if (p.d_dtype == VILCO_F32) {
+          float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.D) + doff + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          uint4* dp = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.D) + doff + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = nb + j;
+          if (n < p.N) {
+            const float res = p.resid ? p.resid[doff + n] * rres : 0.0f;
+            const float o = epi_value(p, __uint_as_float(r[j]), n, rm, res);
+            if (p.d_dtype == VILCO_F32) static_cast<float*>(p.D)[doff + n] = o;
+            else static_cast<__nv_bfloat16*>(p.D)[doff + n] = __float2bfloat16_rn(o);
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT cross-check kernel: same contract, one thread per output element, reads global memory directly.
+// ---------------------------------------------------------------------------------------------
+struct SimtAddr {
+  const __nv_bfloat16* A; long long a_ld, a_s1, a_s2; int a_rows;
+  const __nv_bfloat16* B; long long b_ld, b_s1, b_s2;
+  int Z2;
+};
+
+__global__ void gemm_simt_kernel(const GemmDev p, const SimtAddr q) {
+  const long long total = (long long)p.M * p.N;
+  const int z = blockIdx.y;
+  const int z1 = z % p.Z1, z2 = z / p.Z1;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int m = static_cast<int>(idx / p.N);
+    const int n = static_cast<int>(idx % p.N);
+    float acc = 0.0f;
+    for (int tap = 0; tap < p.taps; ++tap) {
+      const int row = m + tap - (p.taps >> 1);
+      if (row < 0 || row >= q.a_rows) continue;
+      const __nv_bfloat16* a = q.A + z1 * q.a_s1 + z2 * q.a_s2 + (long long)row * q.a_ld;
+      if (p.b_major == 0) {
+        const __nv_bfloat16* b = q.B + (p.b_batched ? z1 * q.b_s1 + z2 * q.b_s2 : tap * q.b_s1) + (long long)n * q.b_ld;
+        for (int k = 0; k < p.K; ++k) acc = fmaf(__bfloat162float(a[k]), __bfloat162float(b[k]), acc);
+      } else {
+        const __nv_bfloat16* b = q.B + (p.b_batched ? z1 * q.b_s1 + z2 * q.b_s2 : tap * q.b_s1) + n;
+        for (int k = 0; k < p.K; ++k) acc = fmaf(__bfloat162float(a[k]), __bfloat162float(b[(long long)k * q.b_ld]), acc);
+      }
+    }
+    float rm = 1.0f;
+    if (p.rowmul) rm = p.rowmul[z2 * p.rowmul_zs + m];
+    const long long doff = z1 * p.d_s1 + z2 * p.d_s2 + (long long)m * p.d_ld + n;
+    const float res = p.resid ? p.resid[doff] * (p.resid_masked ? rm : 1.0f) : 0.0f;
+    const float o = epi_value(p, acc, n, rm, res);
+    if (p.d_dtype == VILCO_F32) static_cast<float*>(p.D)[doff] = o;
+    else static_cast<__nv_bfloat16*>(p.D)[doff] = __float2bfloat16_rn(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// Build a 4-D bf16 tensor map (inner, row, z1, z2); the three outer dims are sorted by stride so the
+// descriptor always sees non-decreasing strides.  slots[] receives the coordinate slot of (row, z1, z2).
+static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, int64_t ld, uint64_t n1,
+                      int64_t s1, uint64_t n2, int64_t s2, uint32_t box_inner, uint32_t box_rows, int slots[3]) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return VILCO_E_CUDA; }
+  struct Dim { uint64_t n; int64_t stride; uint32_t box; int id; };
+  Dim d[3] = {{rows, ld, box_rows, 0}, {n1, s1, 1, 1}, {n2, s2, 1, 2}};
+  // extent-1 dims may carry any stride: give them a harmless large one
+  int64_t big = 16;
+  for (auto& x : d) if (x.n > 1 && x.stride * (int64_t)x.n > big) big = x.stride * (int64_t)x.n;
+  for (auto& x : d) if (x.n <= 1) { x.n = 1; x.stride = (big + 7) / 8 * 8; }
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 3; ++j)
+      if (d[j].stride < d[i].stride) { Dim t = d[i]; d[i] = d[j]; d[j] = t; }
+  cuuint64_t gdim[4] = {inner, d[0].n, d[1].n, d[2].n};
+  cuuint64_t gstr[3] = {(cuuint64_t)d[0].stride * 2, (cuuint64_t)d[1].stride * 2, (cuuint64_t)d[2].stride * 2};
+  cuuint32_t box[4] = {box_inner, d[0].box, d[1].box, d[2].box};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i) {
+    slots[d[i].id] = i + 1;
+    if (gstr[i] % 16 != 0) { set_error("tensor map stride %llu bytes is not a multiple of 16", (unsigned long long)gstr[i]); return VILCO_E_ARG; }
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) { set_error("tensor map base not 16-byte aligned"); return VILCO_E_ARG; }
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu strides %llu %llu %llu box %u %u", (int)r,
+              (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+              (unsigned long long)gdim[3], (unsigned long long)gstr[0], (unsigned long long)gstr[1],
+              (unsigned long long)gstr[2], box[0], box[1]);
+    return VILCO_E_CUDA;
+  }
+  return VILCO_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int Z, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  constexpr int smem = STAGES * L::STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    VILCO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, Z);
+  gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+}  // namespace vilco
+
+using namespace vilco;
+
+extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
+  VILCO_CHECK_ARG(g && g->A && g->B && g->D, "vilco_gemm: null pointer");
+  VILCO_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->Z1 > 0 && g->Z2 > 0, "vilco_gemm: empty problem");
+  VILCO_CHECK_ARG(g->taps == 1 || g->taps == 3, "vilco_gemm: taps must be 1 or 3");
+  VILCO_CHECK_ARG(!(g->b_batched && g->taps != 1), "vilco_gemm: batched B cannot have taps");
+  VILCO_CHECK_ARG(!(g->b_major == 1 && g->N > 64), "vilco_gemm: MN-major B supports N <= 64");
+  VILCO_CHECK_ARG(g->d_dtype == VILCO_F32 || g->d_dtype == VILCO_BF16, "vilco_gemm: bad d_dtype");
+  VILCO_CHECK_ARG(!(g->resid_masked && !g->rowmul), "vilco_gemm: resid_masked needs rowmul");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  GemmDev p{};
+  p.M = g->M; p.N = g->N; p.K = g->K; p.taps = g->taps; p.Z1 = g->Z1;
+  p.b_major = g->b_major; p.b_batched = g->b_batched;
+  p.D = g->D; p.d_dtype = g->d_dtype; p.d_ld = g->d_ld; p.d_s1 = g->d_s1; p.d_s2 = g->d_s2;
+  p.alpha = g->alpha; p.bias = g->bias; p.rowmul = g->rowmul; p.rowmul_zs = g->rowmul_zs;
+  p.act = g->act; p.colscale = g->colscale; p.resid = g->resid; p.resid_masked = g->resid_masked;
+  const int esz = g->d_dtype == VILCO_F32 ? 4 : 2;
+  p.vec_ok = (reinterpret_cast<uintptr_t>(g->D) % 16 == 0) && ((g->d_ld * esz) % 16 == 0) &&
+             ((g->d_s1 * esz) % 16 == 0) && ((g->d_s2 * esz) % 16 == 0) &&
+             (!g->resid || (reinterpret_cast<uintptr_t>(g->resid) % 16 == 0 && (g->d_ld * 4) % 16 == 0 &&
+                            (g->d_s1 * 4) % 16 == 0 && (g->d_s2 * 4) % 16 == 0));
+  const int Z = g->Z1 * g->Z2;
+
+  if (g->impl == 1) {
+    SimtAddr q{};
+    q.A = static_cast<const __nv_bfloat16*>(g->A); q.a_ld = g->a_ld; q.a_s1 = g->a_s1; q.a_s2 = g->a_s2; q.a_rows = g->a_rows;
+    q.B = static_cast<const __nv_bfloat16*>(g->B); q.b_ld = g->b_ld; q.b_s1 = g->b_s1; q.b_s2 = g->b_s2; q.Z2 = g->Z2;
+    const long long total = (long long)g->M * g->N;
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gemm_simt_kernel<<<dim3(blocks, Z), 256, 0, st>>>(p, q);
+    VILCO_LAUNCH_CHECK();
+    return VILCO_OK;
+  }
+
+  // ---- tcgen05 path ----
+  int BN;
+  if (g->b_major == 1) BN = 64;
+  else if (g->N <= 32) BN = 32;
+  else if (g->N <= 64) BN = 64;
+  else BN = 128;
+
+  CUtensorMap tmA, tmB;
+  int sa[3], sb[3];
+  int rc = encode_map(&tmA, g->A, (uint64_t)g->K, (uint64_t)g->a_rows, g->a_ld, (uint64_t)g->Z1, g->a_s1,
+                      (uint64_t)g->Z2, g->a_s2, BK, BM, sa);
+  if (rc) return rc;
+  if (g->b_major == 0) {
+    // (k inner, n rows, z1|tap, z2)
+    const uint64_t n1 = g->b_batched ? (uint64_t)g->Z1 : (uint64_t)g->taps;
+    const uint64_t n2 = g->b_batched ? (uint64_t)g->Z2 : 1;
+    rc = encode_map(&tmB, g->B, (uint64_t)g->K, (uint64_t)g->N, g->b_ld, n1, g->b_s1, n2, g->b_s2, BK, BN, sb);
+  } else {
+    // (n inner, k rows, z1, z2)
+    const uint64_t n1 = g->b_batched ? (uint64_t)g->Z1 : (uint64_t)g->taps;
+    const uint64_t n2 = g->b_batched ? (uint64_t)g->Z2 : 1;
+    rc = encode_map(&tmB, g->B, (uint64_t)g->N, (uint64_t)g->K, g->b_ld, n1, g->b_s1, n2, g->b_s2, 64, BK, sb);
+  }
+  if (rc) return rc;
+  p.a_slot_row = sa[0]; p.a_slot_z1 = sa[1]; p.a_slot_z2 = sa[2];
+  p.b_slot_row = sb[0]; p.b_slot_z1 = sb[1]; p.b_slot_z2 = sb[2];
+
+  switch (BN) {
+    case 32: return launch_tc<32, 6>(tmA, tmB, p, Z, st);
+    case 64: return launch_tc<64, 6>(tmA, tmB, p, Z, st);
+    default: return launch_tc<128, 4>(tmA, tmB, p, Z, st);
+  }
+}

@@ -1,0 +1,105 @@
+"""ctypes binding of the C-ABI library ``libvilco_b200.so`` (declared in ``include/vilco_b200.h``).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+PyTorch is used only for device memory and streams; every compute call goes through the C ABI with
+raw device pointers.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvilco_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+F32, BF16 = 0, 1
+
+
+class VilcoError(RuntimeError):
+    pass
+
+
+class VilcoGemm(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("a_ld", C.c_int64), ("a_s1", C.c_int64), ("a_s2", C.c_int64), ("a_rows", C.c_int32),
+        ("B", C.c_void_p), ("b_ld", C.c_int64), ("b_s1", C.c_int64), ("b_s2", C.c_int64),
+        ("b_major", C.c_int32), ("b_batched", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("taps", C.c_int32), ("Z1", C.c_int32), ("Z2", C.c_int32),
+        ("D", C.c_void_p), ("d_dtype", C.c_int32), ("d_ld", C.c_int64), ("d_s1", C.c_int64), ("d_s2", C.c_int64),
+        ("alpha", C.c_float),
+        ("bias", C.c_void_p),
+        ("rowmul", C.c_void_p), ("rowmul_zs", C.c_int64),
+        ("act", C.c_int32),
+        ("colscale", C.c_void_p),
+        ("resid", C.c_void_p), ("resid_masked", C.c_int32),
+        ("impl", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VilcoError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(vilco_b200 has no CPU / PyTorch fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.vilco_last_error.restype = C.c_char_p
+        _lib.vilco_launch_count.restype = C.c_uint64
+        _lib.vilco_version.restype = C.c_int
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise VilcoError(f"{what} failed (code {rc}): {lib().vilco_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib().vilco_launch_count())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def default_gemm_impl():
+    return 1 if os.environ.get("VILCO_GEMM", "tc") == "simt" else 0
+
+
+def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), d_s=(0, 0), Z=(1, 1), taps=1,
+         b_major=0, b_batched=False, alpha=1.0, bias=None, rowmul=None, rowmul_zs=0, act=ACT_NONE,
+         colscale=None, resid=None, resid_masked=False, impl=None):
+    """Raw descriptor-level call of ``vilco_gemm`` (see include/vilco_b200.h for the contract)."""
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
+    assert D.dtype in (torch.float32, torch.bfloat16)
+    for t in (bias, rowmul, colscale, resid):
+        assert t is None or (t.dtype == torch.float32 and t.is_cuda)
+    g = VilcoGemm()
+    g.A, g.a_ld, g.a_s1, g.a_s2, g.a_rows = A.data_ptr(), a_ld, a_s[0], a_s[1], a_rows
+    g.B, g.b_ld, g.b_s1, g.b_s2 = B.data_ptr(), b_ld, b_s[0], b_s[1]
+    g.b_major, g.b_batched = b_major, int(b_batched)
+    g.M, g.N, g.K, g.taps, g.Z1, g.Z2 = M, N, K, taps, Z[0], Z[1]
+    g.D, g.d_dtype, g.d_ld, g.d_s1, g.d_s2 = D.data_ptr(), (F32 if D.dtype == torch.float32 else BF16), d_ld, d_s[0], d_s[1]
+    g.alpha = alpha
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.rowmul = rowmul.data_ptr() if rowmul is not None else None
+    g.rowmul_zs = rowmul_zs
+    g.act = act
+    g.colscale = colscale.data_ptr() if colscale is not None else None
+    g.resid = resid.data_ptr() if resid is not None else None
+    g.resid_masked = int(resid_masked)
+    g.impl = default_gemm_impl() if impl is None else impl
+    check(lib().vilco_gemm(C.byref(g), stream_ptr()), "vilco_gemm")
+    return D
