@@ -1,0 +1,159 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the REFERENCE ITSELF (imported from
+/root/reference through oracle/ref_shim.py) on seeded inputs and seeded weights.
+
+Run in the authoring container only:   python -m oracle.gen_golden
+The GPU box never runs this (no /root/reference there); it only reads the committed vectors.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import mq_oracle as O
+from . import params as PR
+from . import ref_shim
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def small_cfg():
+    return O.ModelCfg(input_dim=192, embd_dim=256, n_head=4, max_seq_len=128, arch=(2, 2, 4), num_classes=6,
+                      n_txt_in=96, regression_range=[[0, 4], [2, 8], [4, 16], [8, 32], [16, 10000]])
+
+
+def _override(c):
+    def ov(cfg):
+        cfg["dataset"]["input_dim"] = [c.input_dim]
+        cfg["dataset"]["num_classes"] = c.num_classes
+        cfg["dataset"]["max_seq_len"] = c.max_seq_len
+        m = cfg["model"]
+        m["backbone_arch"] = list(c.arch)
+        m["regression_range"] = c.regression_range
+        m["n_head"] = c.n_head
+        m["embd_dim"] = [c.embd_dim]
+        m["fpn_dim"] = c.embd_dim
+        m["head_dim"] = c.embd_dim
+        m["n_txt_in"] = c.n_txt_in
+    return ov
+
+
+def build_reference_model(c, seed=0):
+    """Reference PtTransformer at config `c`, loaded with oracle.params.random_state(seed)."""
+    torch.manual_seed(0)
+    model, cfg = ref_shim.build_model(_override(c))
+    spec = PR.param_spec(c)
+    sd = model.state_dict()
+    for k, shp in spec.items():
+        assert k in sd, f"spec key {k} missing from the reference state_dict"
+        assert tuple(sd[k].shape) == tuple(shp), (k, tuple(sd[k].shape), shp)
+    state = PR.random_state(spec, seed)
+    missing, unexpected = model.load_state_dict(state, strict=False)
+    assert not unexpected, unexpected
+    model.eval()
+    return model, state
+
+
+def run_reference(c, model, videos):
+    """Returns dict of numpy arrays: per-video logits/offsets (concatenated over levels), final detections,
+    and the training losses of the whole batch (model.eval() so dropout/drop-path are identity)."""
+    out = {}
+    with torch.no_grad():
+        for i, v in enumerate(videos):
+            logits, offs, masks = model([v], is_training=False, get_emb=True)
+            out[f"logits_{i}"] = torch.cat(logits, 1)[0].numpy()
+            out[f"offsets_{i}"] = torch.cat(offs, 1)[0].numpy()
+            out[f"masks_{i}"] = torch.cat(masks, 1)[0].numpy()
+            res = model([v], is_training=False)[0]
+            out[f"det_segments_{i}"] = res["segments"].numpy()
+            out[f"det_scores_{i}"] = res["scores"].numpy()
+            out[f"det_labels_{i}"] = res["labels"].numpy()
+    model.loss_normalizer = c.init_loss_norm
+    losses = model(videos, is_training=True)
+    for k, val in losses.items():
+        out["loss_" + k] = np.float32(val.detach().reshape(-1)[0].item())
+    # gradients of final_loss w.r.t. a few probes (used later by the backward parity tests)
+    return out
+
+
+def gen_model_golden():
+    c = small_cfg()
+    model, _ = build_reference_model(c, seed=0)
+    videos = PR.synth_video_list(c, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    out = run_reference(c, model, videos)
+    np.savez_compressed(os.path.join(GOLDEN, "model_small.npz"), **out)
+    print("model_small:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
+def gen_local_attn_golden():
+    """LocalMaskedMHCA standalone (unused by MQ configs, live in NLQ) — MQ/libs/modeling/blocks.py:871-1207."""
+    ns = ref_shim.load()
+    out = {}
+    for name, (C, H, W, T, valid) in {"w9": (128, 2, 9, 64, [64, 41]), "w5": (128, 2, 5, 32, [32, 20])}.items():
+        torch.manual_seed(1)
+        m = ns.blocks.LocalMaskedMHCA(C, H, W).eval()
+        rs = np.random.RandomState(7)
+        sd = {k: torch.from_numpy(rs.standard_normal(tuple(v.shape)).astype(np.float32) * (0.3 if v.dim() == 3 else 0.1) + (1.0 if "norm.weight" in k else 0.0))
+              for k, v in sorted(m.state_dict().items())}
+        m.load_state_dict(sd)
+        x = torch.from_numpy(rs.standard_normal((2, C, T)).astype(np.float32))
+        mask = (torch.arange(T)[None, :] < torch.tensor(valid)[:, None]).unsqueeze(1)
+        with torch.no_grad():
+            y, _ = m(x * mask, mask)
+        out[name + "_x"] = (x * mask).numpy()
+        out[name + "_valid"] = np.asarray(valid)
+        out[name + "_y"] = y.numpy()
+        for k, v in sd.items():
+            out[name + "_p_" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "local_attn.npz"), **out)
+    print("local_attn ok")
+
+
+def gen_nms_golden():
+    """soft-NMS / hard-NMS known answers from the reference's own C++ (MQ/libs/utils/csrc/nms_cpu.cpp)."""
+    ns = ref_shim.load()
+    out = {}
+    rs = np.random.RandomState(3)
+    cases = {"n1": 1, "n17": 17, "n300": 300, "n2000": 2000, "ties": 64}
+    for name, n in cases.items():
+        centre = rs.uniform(0, 1024, n).astype(np.float32)
+        length = np.exp(rs.uniform(np.log(2.0), np.log(400.0), n)).astype(np.float32)
+        segs = np.stack([centre - length / 2, centre + length / 2], 1).astype(np.float32)
+        scores = rs.beta(0.5, 8, n).astype(np.float32)
+        if name == "ties":
+            scores = np.round(scores * 8) / 8 + np.float32(0.01)  # many exactly equal scores
+            scores = scores.astype(np.float32)
+        out[name + "_segs"], out[name + "_scores"] = segs, scores
+        for method, sigma, min_score in ((2, 0.99, 1e-4), (2, 0.5, 0.01), (1, 0.5, 0.001), (0, 0.5, 0.001)):
+            dets = torch.zeros(n, 3)
+            inds = ns.nms_1d_cpu.softnms(torch.from_numpy(segs), torch.from_numpy(scores), dets, iou_threshold=0.1,
+                                         sigma=float(sigma), min_score=float(min_score), method=int(method))
+            tag = f"{name}_m{method}_s{sigma}_t{min_score}"
+            out[tag + "_dets"] = dets[:len(inds)].numpy()
+            out[tag + "_inds"] = inds.numpy()
+        keep = ns.nms_1d_cpu.nms(torch.from_numpy(segs), torch.from_numpy(scores), iou_threshold=0.4)
+        out[name + "_hard_keep"] = keep.numpy()
+    # batched_nms end-to-end (python wrapper + extension), multi-class
+    n, K = 3000, 7
+    centre = rs.uniform(0, 1024, n).astype(np.float32)
+    length = np.exp(rs.uniform(np.log(2.0), np.log(400.0), n)).astype(np.float32)
+    segs = np.stack([centre - length / 2, centre + length / 2], 1).astype(np.float32)
+    scores = rs.beta(0.5, 8, n).astype(np.float32)
+    labels = rs.randint(0, K, n).astype(np.int64)
+    s, sc, lb = ns.nms.batched_nms(torch.from_numpy(segs), torch.from_numpy(scores), torch.from_numpy(labels), 0.1,
+                                   1e-4, 200, use_soft_nms=True, multiclass=True, sigma=0.99, voting_thresh=0.9)
+    out.update(b_segs=segs, b_scores=scores, b_labels=labels, b_out_segs=s.numpy(), b_out_scores=sc.numpy(),
+               b_out_labels=lb.numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "nms.npz"), **out)
+    print("nms ok")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN, exist_ok=True)
+    what = sys.argv[1:] or ["nms", "local", "model"]
+    if "nms" in what:
+        gen_nms_golden()
+    if "local" in what:
+        gen_local_attn_golden()
+    if "model" in what:
+        gen_model_golden()
