@@ -15,6 +15,7 @@
 #ifndef VILCO_B200_H
 #define VILCO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -59,13 +60,16 @@ uint64_t vilco_launch_count(void);
  * epilogue order:  v = alpha*acc + bias[n];  v *= rowmul[z2*rowmul_zs + m];  v = act(v);
  *                  v = v*colscale[n] + resid[z,m,n] * (resid_masked ? rowmul[..] : 1);   store as d_dtype.
  * Any of bias / rowmul / colscale / resid may be NULL.  resid is fp32 with the same strides as D.
+ * Split precision ("bf16x3"): when a_lo and b_lo are non-zero they are the element offsets of a second bf16 plane with
+ * x ~= hi + lo (lo = bf16(x - hi)); the kernel then accumulates hi*hi + hi*lo + lo*hi (three MMAs per k-step), which keeps
+ * ~16 mantissa bits per operand (needed for the 1e-3 parity bar).  d_lo != 0 makes a bf16 output write both planes.
  * impl = 0: tcgen05 + TMA + TMEM kernel;  impl = 1: plain SIMT kernel (debug cross-check of the same math).
  * ------------------------------------------------------------------------------------ */
 typedef struct VilcoGemm {
-  const void* A; int64_t a_ld, a_s1, a_s2; int32_t a_rows;
-  const void* B; int64_t b_ld, b_s1, b_s2; int32_t b_major, b_batched;
+  const void* A; int64_t a_ld, a_s1, a_s2, a_lo; int32_t a_rows;
+  const void* B; int64_t b_ld, b_s1, b_s2, b_lo; int32_t b_major, b_batched;
   int32_t M, N, K, taps, Z1, Z2;
-  void* D; int32_t d_dtype; int64_t d_ld, d_s1, d_s2;
+  void* D; int32_t d_dtype; int64_t d_ld, d_s1, d_s2, d_lo;
   float alpha;
   const float* bias;
   const float* rowmul; int64_t rowmul_zs;
@@ -76,6 +80,89 @@ typedef struct VilcoGemm {
 } VilcoGemm;
 
 int vilco_gemm(const VilcoGemm* g, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Channel LayerNorm over token-major rows (one warp per token, two-pass statistics):
+ *   y = act(LN(x [+ add]) * w + b) [+ pe[t] * rowmul[row]]   (rows flagged in zero_rows are written as 0)
+ * Replaces LayerNorm.forward MQ/libs/modeling/blocks.py:160-175 (eps 1e-5), nn.LayerNorm of ChannelBlock
+ * (blocks.py:449) and of the XLNet layer (eps 1e-12, modeling_xlnet_x.py:330, 489), the `relu(embd_norm(..))`
+ * of the embedding network and the `+ pos_embd * mask` that follows it (MQ/libs/modeling/backbones.py:217-236),
+ * FPNIdentity.forward (MQ/libs/modeling/necks.py:173-198).
+ * Every bf16 OUTPUT of this library takes a `*_lo` element offset: when non-zero a second plane lo = bf16(v - hi) is
+ * written there (split precision, see vilco_gemm); bf16 inputs of the non-GEMM kernels take the same offset.
+ * x is fp32 or bf16 (x_dtype), rows x C contiguous; C % 128 == 0, C <= 1024.  y32 / y16 (either may be NULL) are
+ * written at  batch * y_bs + t * y_ld  with batch = row / rows_per_batch, t = row % rows_per_batch.
+ * ------------------------------------------------------------------------------------ */
+int vilco_layernorm(const void* x, int x_dtype, const float* add, const float* w, const float* b, float eps, int relu,
+                    const float* pe, int pe_T, const float* rowmul, const uint8_t* zero_rows, float* y32, void* y16,
+                    int64_t y16_lo, int64_t y_ld, int64_t y_bs, int rows, int rows_per_batch, int C, void* stream);
+
+/* depthwise conv (k=3, stride 1|2, zero pad 1, no bias) * out_mask -> LayerNorm, for up to three (weight, norm)
+ * sets sharing one input: the q/k/v front of MaskedMHCA / LocalMaskedMHCA (blocks.py:315-345, 364-371; the mask is
+ * nearest-downsampled, blocks.py:117-127).  x (B,T,C) fp32|bf16, mask (B,T) float 1/0, wconv[i] (3,C) tap-major,
+ * out[i] (B,T/stride,C) bf16. */
+int vilco_dwconv_ln(const void* x, int x_dtype, const float* mask, const float* const* wconv, const float* const* lnw,
+                    const float* const* lnb, void* const* out, int64_t out_lo, int n_out, int B, int T, int C, int stride,
+                    float eps, void* stream);
+
+/* nn.MaxPool1d(3, 2, 1) over time (TransformerBlock.pool_skip, blocks.py:519-525) on (B,T,C) fp32 -> (B,T/2,C). */
+int vilco_maxpool3s2(const float* x, float* y, int B, int T, int C, void* stream);
+
+/* o = a*x + b*y (fp32; y may be NULL), optional bf16 copy: the `t_c_alpha` mix (blocks.py:581) and dtype casts. */
+int vilco_axpby(const float* x, const float* y, float a, float b, float* o32, void* o16, int64_t o16_lo, int64_t n,
+                void* stream);
+
+/* layout changes at the boundary: (B,C,T) fp32 reference layout -> (B,T_out,C) bf16 token-major (zero padded), and
+ * (B,T,C) fp32 -> (B,C,T) fp32.  (PtTransformer.preprocessing, MQ/libs/modeling/meta_archs.py:1134-1181) */
+int vilco_pack_feats(const float* x, void* y, int64_t y_lo, int B, int C, int T, int T_out, void* stream);
+int vilco_unpack(const float* x, float* y, int B, int T, int C, void* stream);
+
+/* Row softmax over materialised attention scores S (Z2,Z1,Tq,Tk) fp32 -> P bf16 (row stride p_ld >= Tk, tail zeroed).
+ * mode 0: keys with kmask[z2, j] == 0 get probability 0 (masked_fill(-inf) + softmax, blocks.py:258-260, 388-391).
+ * mode 1: XLNet: (S[i,j] + BD[i, Tk + j - i]) * scale - 1e30 * [key j padded and i != j]
+ *         (rel_shift_bnij + rel_attn_core, modeling_xlnet_x.py:256-304; mask prep :1152-1188); BD is (Z2,Z1,Tq,2Tk). */
+int vilco_softmax_rows(const float* S, const float* BD, const float* kmask, void* P, int64_t p_lo, int Z2, int Z1, int Tq,
+                       int Tk, int64_t p_ld, float scale, int mode, void* stream);
+
+/* LocalMaskedMHCA attention core (blocks.py:1038-1138, 1165-1200): q,k,v (B,T,C) bf16 token-major after the q/k/v
+ * projections, window W (odd), out-of-range keys -inf, padded keys -1e4, padded queries -> 0; rel_pe (H,W) or NULL.
+ * out (B,T,C) bf16 (heads side by side), to be followed by the proj GEMM. */
+int vilco_local_attention(const void* q, const void* k, const void* v, const float* mask, const float* rel_pe, void* out,
+                          int64_t lo, int B, int T, int C, int H, int W, void* stream);
+
+/* ChannelAttention core (blocks.py:423-436): qkv (B,T,3C) bf16 -> y (B,T,C) bf16;  G is a (B,H,64,64) fp32 scratch. */
+int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G, void* y, int64_t y_lo, int B, int T, int C, int H,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Decode of the head outputs into candidate segments — PtTransformer.inference_single_video,
+ * MQ/libs/modeling/meta_archs.py:1594-1692: per pyramid level  prob = sigmoid(logit) * mask;  keep prob > pre_nms_thresh;
+ * sort descending (ties: lower flat index first), keep the first `topk`;  pt = idx / K, cls = idx % K;
+ * seg = (t - off_l * stride, t + off_r * stride) with t = pt * stride;  keep (right - left) > duration_thresh.
+ * logits (B,P,K), offsets (B,P,2), pmask (B,P) fp32 over the concatenated pyramid rows; level l = rows
+ * [lvl_off[l], lvl_off[l] + lvl_len[l]) (host arrays).  Output: per (video, level) a region of `topk` slots in
+ * cand_* (B, n_levels*topk [,2]) holding cand_count[b, l] candidates in sorted order.
+ * ------------------------------------------------------------------------------------ */
+int vilco_decode(const float* logits, const float* offsets, const float* pmask, int B, int P, int K, int n_levels,
+                 const int* lvl_off, const int* lvl_len, const float* lvl_stride, float pre_nms_thresh,
+                 float duration_thresh, int topk, float* cand_segs, float* cand_scores, int* cand_labels, int* cand_count,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * batched_nms — MQ/libs/utils/nms.py:103-190 with its native backend MQ/libs/utils/csrc/nms_cpu.cpp
+ * (softnms_1d_cpu :67-160 for method 0/1/2 = SoftNMSop with method vanilla/linear/gaussian; method 3 = NMSop / nms_1d_cpu
+ * :19-57, i.e. score pre-filter + greedy hard NMS).  Candidates of video b are the first region_count[b, r] entries of each
+ * of its n_regions regions of region_cap slots (decode output layout; a flat array is one region).  Per class (ascending
+ * original order) the reference's array algorithm is reproduced exactly, at most max_seg_num picks are kept per class,
+ * classes are concatenated in ascending id, sorted by score (descending, ties by concatenation order) and cut to
+ * max_seg_num.  multiclass = 0 runs one class-agnostic pass (seg voting is not implemented: the caller must not ask for it).
+ * Outputs (B, max_seg_num [,2]) + out_count (B).  workspace: vilco_nms_workspace_bytes(...) device bytes.
+ * ------------------------------------------------------------------------------------ */
+size_t vilco_nms_workspace_bytes(int B, int n_regions, int region_cap, int num_classes, int det_cap);
+int vilco_batched_nms(const float* segs, const float* scores, const int* labels, const int* region_count, int B,
+                      int n_regions, int region_cap, int num_classes, int multiclass, int method, float iou_threshold,
+                      float sigma, float min_score, int max_seg_num, void* workspace, size_t workspace_bytes,
+                      float* out_segs, float* out_scores, long long* out_labels, int* out_count, void* stream);
 
 #ifdef __cplusplus
 }

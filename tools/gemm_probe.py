@@ -84,6 +84,27 @@ def case_attn(Bsz, H, Tq, Tk, impl):
     report(f"P@V  B{Bsz} H{H} Tq{Tq} Tk{Tk} impl{impl}", O, refo)
 
 
+def split(x):
+    hi = x.bfloat16()
+    return torch.stack([hi, (x - hi.float()).bfloat16()]).contiguous()
+
+
+def case_split(M, N, K, impl):
+    """bf16x3: operands as (hi, lo) planes; result must match the fp32 matmul to ~1e-5."""
+    A32 = torch.randn(M, K, device=dev)
+    W32 = torch.randn(N, K, device=dev) * 0.1
+    A, W = split(A32), split(W32)
+    D = torch.zeros(2, M, N, device=dev, dtype=torch.bfloat16)
+    L.gemm(A, W, D, M=M, N=N, K=K, a_rows=M, a_ld=K, b_ld=K, d_ld=N, impl=impl, a_lo=A.stride(0), b_lo=W.stride(0),
+           d_lo=D.stride(0))
+    D32 = torch.zeros(M, N, device=dev, dtype=torch.float32)
+    L.gemm(A, W, D32, M=M, N=N, K=K, a_rows=M, a_ld=K, b_ld=K, d_ld=N, impl=impl, a_lo=A.stride(0), b_lo=W.stride(0))
+    torch.cuda.synchronize()
+    ref = (A32.double() @ W32.double().t()).float()
+    report(f"split f32-out M{M} N{N} K{K} impl{impl}", D32, ref, tol=2e-5)
+    report(f"split hi+lo-out M{M} N{N} K{K} impl{impl}", D.float().sum(0), ref, tol=3e-5)
+
+
 if __name__ == "__main__":
     impls = [int(a) for a in sys.argv[1:]] or [1, 0]
     for impl in impls:
@@ -99,5 +120,8 @@ if __name__ == "__main__":
         case_attn(2, 2, 128, 128, impl)
         case_attn(1, 16, 512, 57, impl)
         case_attn(2, 4, 1024, 1024, impl)
+        case_split(256, 128, 512, impl)
+        case_split(2048, 1024, 1024, impl)
+        case_split(100, 22, 200, impl)
     print("launches", L.launch_count())
     sys.exit(1 if bad else 0)

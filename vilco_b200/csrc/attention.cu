@@ -1,0 +1,342 @@
+// Attention-side kernels that are not GEMMs:
+//  * masked row softmax over materialised scores (global MaskedMHCA / cross MaskedMHA)        blocks.py:228-269, 351-410
+//  * XLNet relative-attention softmax: (ac + rel_shift(bd)) * scale - 1e30 * mask             modeling_xlnet_x.py:256-320
+//  * LocalMaskedMHCA core: sliding-window attention with the window staged in shared memory   blocks.py:1038-1138
+//  * ChannelAttention core: softmax_d((k*s)^T v) then q A^T                                     blocks.py:423-436
+#include "common.cuh"
+
+namespace vilco {
+
+// ---------------------------------------------------------------------------------------------
+// row softmax.  S: (Z2, Z1, Tq, Tk) fp32 -> P: same shape bf16 with row stride p_ld.
+// mode 0: keys with kmask == 0 get -inf (probability exactly 0).
+// mode 1 (XLNet): score = (S[i,j] + BD[i, Tk + j - i]) * scale; minus 1e30 where key j is padding and i != j.
+// ---------------------------------------------------------------------------------------------
+struct SmParams {
+  const float* S; const float* BD; const float* kmask;  // kmask (Z2, Tk)
+  __nv_bfloat16* P; long long p_lo;
+  int Z1, Tq, Tk; long long p_ld; float scale; int mode;
+  long long rows;
+};
+
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const SmParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int i = static_cast<int>(row % p.Tq);
+  const long long zh = row / p.Tq;
+  const int b = static_cast<int>(zh / p.Z1);
+  const float* s = p.S + row * p.Tk;
+  const float* km = p.kmask ? p.kmask + (long long)b * p.Tk : nullptr;
+  const float* bd = p.mode == 1 ? p.BD + row * (2LL * p.Tk) + (p.Tk - i) : nullptr;
+  __nv_bfloat16* o = p.P + row * p.p_ld;
+
+  auto score = [&](int j) -> float {
+    float v = s[j];
+    if (p.mode == 0) {
+      if (km && km[j] == 0.f) v = -INFINITY;
+    } else {
+      v = (v + bd[j]) * p.scale;
+      if (km && km[j] == 0.f && j != i) v -= 1e30f;
+    }
+    return v;
+  };
+  float mx = -INFINITY;
+  for (int j = lane; j < p.Tk; j += 32) mx = fmaxf(mx, score(j));
+  mx = warp_max(mx);
+  if (mx == -INFINITY) {  // fully masked row (empty clip): the reference would produce NaN; emit zeros
+    for (int j = lane; j < p.p_ld; j += 32) {
+      o[j] = __float2bfloat16_rn(0.f);
+      if (p.p_lo) o[p.p_lo + j] = __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
+  float sum = 0.f;
+  for (int j = lane; j < p.Tk; j += 32) sum += __expf(score(j) - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int j = lane; j < p.p_ld; j += 32) {
+    const float v = j < p.Tk ? __expf(score(j) - mx) * inv : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    o[j] = h;
+    if (p.p_lo) o[p.p_lo + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// local (windowed) attention.  q,k,v: (B, T, C) bf16 token-major, head h = channels [h*d, (h+1)*d).
+// One CTA = (token tile, head, batch); K/V rows [t0-w, t0+TI+w) staged in shared memory once and reused by all
+// queries of the tile; one warp per query, lanes over the head dim, warp-shuffle dot products.
+// ---------------------------------------------------------------------------------------------
+static constexpr int LW_TI = 32;      // queries per CTA
+static constexpr int LW_MAXW = 65;    // max window size
+static constexpr int LW_MAXD = 128;   // max head dim
+
+struct LwParams {
+  const __nv_bfloat16 *q, *k, *v; const float* mask;  // mask (B, T)
+  const float* rel_pe;                                // (H, W) or null
+  __nv_bfloat16* out;
+  long long lo;                                       // lo-plane offset of q/k/v/out (0 = single plane)
+  int B, T, C, H, d, W; float scale;
+};
+
+__device__ __forceinline__ float2 ld2_split(const __nv_bfloat16* p, long long lo) {
+  const uint32_t x = *reinterpret_cast<const uint32_t*>(p);
+  float2 r = make_float2(bf16_lo(x), bf16_hi(x));
+  if (lo) {
+    const uint32_t y = *reinterpret_cast<const uint32_t*>(p + lo);
+    r.x += bf16_lo(y); r.y += bf16_hi(y);
+  }
+  return r;
+}
+__device__ __forceinline__ void st2_split(__nv_bfloat16* p, long long lo, float a, float b) {
+  const uint32_t h = pack_bf16x2(a, b);
+  *reinterpret_cast<uint32_t*>(p) = h;
+  if (lo) *reinterpret_cast<uint32_t*>(p + lo) = pack_bf16x2(a - bf16_lo(h), b - bf16_hi(h));
+}
+
+__global__ void __launch_bounds__(256) local_attn_kernel(const LwParams p) {
+  extern __shared__ float lw_smem[];
+  const int w = p.W / 2;
+  const int t0 = blockIdx.x * LW_TI, h = blockIdx.y, b = blockIdx.z;
+  const int nrows = LW_TI + 2 * w;
+  float* sk = lw_smem;
+  float* sv = lw_smem + (size_t)nrows * p.d;
+  const long long base = (long long)b * p.T * p.C + (long long)h * p.d;
+  // stage the K/V window as fp32 (hi + lo planes summed); rows outside the sequence are never read
+  const int half = p.d / 2;
+  for (int idx = threadIdx.x; idx < nrows * half; idx += blockDim.x) {
+    const int r = idx / half, c = (idx - r * half) * 2;
+    const int t = t0 - w + r;
+    if (t >= 0 && t < p.T) {
+      const float2 kk = ld2_split(p.k + base + (long long)t * p.C + c, p.lo);
+      const float2 vv = ld2_split(p.v + base + (long long)t * p.C + c, p.lo);
+      sk[r * p.d + c] = kk.x; sk[r * p.d + c + 1] = kk.y;
+      sv[r * p.d + c] = vv.x; sv[r * p.d + c + 1] = vv.y;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const float* mk = p.mask + (long long)b * p.T;
+  for (int qi = warp; qi < LW_TI; qi += nwarp) {
+    const int t = t0 + qi;
+    if (t >= p.T) break;
+    __nv_bfloat16* o = p.out + base + (long long)t * p.C;
+    if (mk[t] == 0.f) {  // padded query: probabilities are zeroed (blocks.py:1192-1194)
+      for (int c = lane * 2; c < p.d; c += 64) st2_split(o + c, p.lo, 0.f, 0.f);
+      continue;
+    }
+    float qv[LW_MAXD / 32];
+#pragma unroll
+    for (int u = 0; u < LW_MAXD / 64; ++u) {
+      const int c = lane * 2 + u * 64;
+      if (c < p.d) {
+        const float2 x = ld2_split(p.q + base + (long long)t * p.C + c, p.lo);
+        qv[2 * u] = x.x * p.scale; qv[2 * u + 1] = x.y * p.scale;
+      } else { qv[2 * u] = 0.f; qv[2 * u + 1] = 0.f; }
+    }
+    // scores for j = t-w .. t+w   (lane jj%32 keeps the score of window slot jj)
+    float sc0 = -INFINITY, sc1 = -INFINITY, sc2 = -INFINITY;
+    for (int jj = 0; jj < p.W; ++jj) {
+      const int j = t - w + jj;
+      float part = 0.f;
+      if (j >= 0 && j < p.T) {
+        const float* kr = sk + (qi + jj) * p.d;
+#pragma unroll
+        for (int u = 0; u < LW_MAXD / 64; ++u) {
+          const int c = lane * 2 + u * 64;
+          if (c < p.d) {
+            part = fmaf(qv[2 * u], kr[c], part);
+            part = fmaf(qv[2 * u + 1], kr[c + 1], part);
+          }
+        }
+      }
+      float s = warp_sum(part);
+      if (j < 0 || j >= p.T) s = -INFINITY;
+      else {
+        if (p.rel_pe) s += p.rel_pe[h * p.W + jj];
+        if (mk[j] == 0.f) s += -1e4f;
+      }
+      if ((jj & 31) == lane) { if (jj < 32) sc0 = s; else if (jj < 64) sc1 = s; else sc2 = s; }
+    }
+    float mx = warp_max(fmaxf(fmaxf(sc0, sc1), sc2));
+    float e0 = sc0 == -INFINITY ? 0.f : __expf(sc0 - mx);
+    float e1 = sc1 == -INFINITY ? 0.f : __expf(sc1 - mx);
+    float e2 = sc2 == -INFINITY ? 0.f : __expf(sc2 - mx);
+    const float inv = 1.0f / warp_sum(e0 + e1 + e2);
+    float acc[LW_MAXD / 32];
+#pragma unroll
+    for (int u = 0; u < LW_MAXD / 32; ++u) acc[u] = 0.f;
+    for (int jj = 0; jj < p.W; ++jj) {
+      const int j = t - w + jj;
+      const float pe = __shfl_sync(0xffffffffu, jj < 32 ? e0 : (jj < 64 ? e1 : e2), jj & 31) * inv;
+      if (j < 0 || j >= p.T) continue;
+      const float* vr = sv + (qi + jj) * p.d;
+#pragma unroll
+      for (int u = 0; u < LW_MAXD / 64; ++u) {
+        const int c = lane * 2 + u * 64;
+        if (c < p.d) {
+          acc[2 * u] = fmaf(pe, vr[c], acc[2 * u]);
+          acc[2 * u + 1] = fmaf(pe, vr[c + 1], acc[2 * u + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LW_MAXD / 64; ++u) {
+      const int c = lane * 2 + u * 64;
+      if (c < p.d) st2_split(o + c, p.lo, acc[2 * u], acc[2 * u + 1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel attention.  qkv: (B, T, 3C) bf16 with column = which*C + h*64 + d  (d = 64 fixed).
+// phase 1: G[b,h] (64x64 fp32, zero-initialised by the caller) += sum over a T chunk of (k*scale)^T v
+// phase 2: A = softmax_rows(G[b,h]);  y[t, h*64 + i] = sum_j A[i,j] q[t, j]
+// ---------------------------------------------------------------------------------------------
+static constexpr int CA_D = 64;
+static constexpr int CA_TCHUNK = 64;
+
+__global__ void __launch_bounds__(256) chan_attn_kv_kernel(const __nv_bfloat16* __restrict__ qkv, long long lo,
+                                                           float* __restrict__ G, int T, int C, int H, float scale) {
+  __shared__ float sk[CA_TCHUNK][CA_D + 1];
+  __shared__ float sv[CA_TCHUNK][CA_D + 1];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int t0 = blockIdx.x * CA_TCHUNK;
+  const int nt = min(CA_TCHUNK, T - t0);
+  const long long ld = 3LL * C;
+  const __nv_bfloat16* kb = qkv + ((long long)b * T + t0) * ld + C + h * CA_D;
+  const __nv_bfloat16* vb = kb + C;
+  for (int idx = threadIdx.x; idx < CA_TCHUNK * (CA_D / 2); idx += blockDim.x) {
+    const int r = idx / (CA_D / 2), c = (idx % (CA_D / 2)) * 2;
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    if (r < nt) {
+      const float2 xk = ld2_split(kb + r * ld + c, lo);
+      const float2 xv = ld2_split(vb + r * ld + c, lo);
+      k0 = xk.x * scale; k1 = xk.y * scale; v0 = xv.x; v1 = xv.y;
+    }
+    sk[r][c] = k0; sk[r][c + 1] = k1; sv[r][c] = v0; sv[r][c + 1] = v1;
+  }
+  __syncthreads();
+  // thread (i, j4): 4x4 sub-block of the 64x64 output
+  const int ti = (threadIdx.x / 16) * 4, tj = (threadIdx.x % 16) * 4;
+  float acc[4][4] = {};
+  for (int r = 0; r < CA_TCHUNK; ++r) {
+    float a[4], c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = sk[r][ti + u]; c[u] = sv[r][tj + u]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) acc[u][w] = fmaf(a[u], c[w], acc[u][w]);
+  }
+  float* g = G + ((long long)b * H + h) * CA_D * CA_D;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) atomicAdd(g + (ti + u) * CA_D + tj + w, acc[u][w]);
+}
+
+__global__ void __launch_bounds__(256) chan_attn_apply_kernel(const __nv_bfloat16* __restrict__ qkv, long long lo,
+                                                              const float* __restrict__ G, __nv_bfloat16* __restrict__ y,
+                                                              long long y_lo, int T, int C, int H) {
+  __shared__ float sa[CA_D][CA_D + 1];
+  __shared__ float sq[CA_TCHUNK][CA_D + 1];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int t0 = blockIdx.x * CA_TCHUNK;
+  const int nt = min(CA_TCHUNK, T - t0);
+  const float* g = G + ((long long)b * H + h) * CA_D * CA_D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // softmax of each row i over j (8 warps x 8 rows)
+  for (int i = warp; i < CA_D; i += 8) {
+    const float a0 = g[i * CA_D + lane], a1 = g[i * CA_D + lane + 32];
+    const float mx = warp_max(fmaxf(a0, a1));
+    const float e0 = __expf(a0 - mx), e1 = __expf(a1 - mx);
+    const float inv = 1.0f / warp_sum(e0 + e1);
+    sa[i][lane] = e0 * inv; sa[i][lane + 32] = e1 * inv;
+  }
+  const long long ld = 3LL * C;
+  const __nv_bfloat16* qb = qkv + ((long long)b * T + t0) * ld + h * CA_D;
+  for (int idx = threadIdx.x; idx < CA_TCHUNK * (CA_D / 2); idx += blockDim.x) {
+    const int r = idx / (CA_D / 2), c = (idx % (CA_D / 2)) * 2;
+    float q0 = 0.f, q1 = 0.f;
+    if (r < nt) {
+      const float2 x = ld2_split(qb + r * ld + c, lo);
+      q0 = x.x; q1 = x.y;
+    }
+    sq[r][c] = q0; sq[r][c + 1] = q1;
+  }
+  __syncthreads();
+  // thread: token r = tid / 4 (64 tokens), outputs i in [ (tid%4)*16, +16 )
+  const int r = threadIdx.x / 4, i0 = (threadIdx.x % 4) * 16;
+  if (r < nt) {
+    float acc[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc[u] = 0.f;
+    for (int j = 0; j < CA_D; ++j) {
+      const float qj = sq[r][j];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) acc[u] = fmaf(sa[i0 + u][j], qj, acc[u]);
+    }
+    __nv_bfloat16* o = y + ((long long)b * T + t0 + r) * C + h * CA_D + i0;
+#pragma unroll
+    for (int u = 0; u < 16; u += 2) st2_split(o + u, y_lo, acc[u], acc[u + 1]);
+  }
+}
+
+}  // namespace vilco
+
+using namespace vilco;
+
+extern "C" int vilco_softmax_rows(const float* S, const float* BD, const float* kmask, void* P, int64_t p_lo, int Z2, int Z1,
+                                  int Tq, int Tk, int64_t p_ld, float scale, int mode, void* stream) {
+  VILCO_CHECK_ARG(S && P && Z1 > 0 && Z2 > 0 && Tq > 0 && Tk > 0 && p_ld >= Tk, "vilco_softmax_rows: bad arguments");
+  VILCO_CHECK_ARG(mode == 0 || (mode == 1 && BD && Tq == Tk), "vilco_softmax_rows: mode 1 needs BD and Tq == Tk");
+  SmParams p{};
+  p.S = S; p.BD = BD; p.kmask = kmask; p.P = static_cast<__nv_bfloat16*>(P); p.p_lo = p_lo;
+  p.Z1 = Z1; p.Tq = Tq; p.Tk = Tk; p.p_ld = p_ld; p.scale = scale; p.mode = mode;
+  p.rows = (long long)Z2 * Z1 * Tq;
+  const long long grid = (p.rows + 7) / 8;
+  softmax_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_local_attention(const void* q, const void* k, const void* v, const float* mask, const float* rel_pe,
+                                     void* out, int64_t lo, int B, int T, int C, int H, int W, void* stream) {
+  VILCO_CHECK_ARG(q && k && v && mask && out, "vilco_local_attention: null pointer");
+  VILCO_CHECK_ARG(H > 0 && C % H == 0, "vilco_local_attention: C %% H != 0");
+  const int d = C / H;
+  VILCO_CHECK_ARG(d % 8 == 0 && d <= LW_MAXD, "vilco_local_attention: head dim %d unsupported", d);
+  VILCO_CHECK_ARG(W >= 3 && (W & 1) && W <= LW_MAXW, "vilco_local_attention: window %d unsupported (odd, 3..%d)", W, LW_MAXW);
+  LwParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(q); p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v); p.mask = mask; p.rel_pe = rel_pe;
+  p.out = static_cast<__nv_bfloat16*>(out); p.lo = lo;
+  p.B = B; p.T = T; p.C = C; p.H = H; p.d = d; p.W = W; p.scale = 1.0f / sqrtf(static_cast<float>(d));
+  const size_t smem = (size_t)2 * (LW_TI + 2 * (W / 2)) * d * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    VILCO_CUDA(cudaFuncSetAttribute(local_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    2 * (LW_TI + LW_MAXW) * LW_MAXD * (int)sizeof(float)));
+    configured = true;
+  }
+  dim3 grid((T + LW_TI - 1) / LW_TI, H, B);
+  local_attn_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G, void* y, int64_t y_lo, int B, int T, int C,
+                                       int H, void* stream) {
+  VILCO_CHECK_ARG(qkv && G && y, "vilco_channel_attention: null pointer");
+  VILCO_CHECK_ARG(H > 0 && C == H * CA_D, "vilco_channel_attention: head dim must be 64 (C=%d H=%d)", C, H);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VILCO_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)B * H * CA_D * CA_D, st));
+  dim3 grid((T + CA_TCHUNK - 1) / CA_TCHUNK, H, B);
+  chan_attn_kv_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, T, C, H, 1.0f / sqrtf((float)CA_D));
+  VILCO_LAUNCH_CHECK();
+  chan_attn_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, static_cast<__nv_bfloat16*>(y), y_lo, T, C, H);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}

@@ -1,0 +1,605 @@
+// Post-processing of the Moment-Query head outputs on the GPU:
+//   decode   — PtTransformer.inference_single_video            MQ/libs/modeling/meta_archs.py:1594-1692
+//   soft-NMS — batched_nms / SoftNMSop / softnms_1d_cpu        MQ/libs/utils/nms.py:38-64,103-190, csrc/nms_cpu.cpp:67-160
+//   hard-NMS — NMSop / nms_1d_cpu                              nms.py:8-35, nms_cpu.cpp:19-57
+// The soft-NMS kernel reproduces the reference's sequential array semantics exactly (first-maximum pick, swap into
+// slot i, suppressed entries replaced by the *last* entry) so that kept segments and tie-breaking are identical;
+// the Gaussian weight uses a double-precision restatement of glibc's expf so scores match the CPU bit for bit.
+#include "common.cuh"
+
+namespace vilco {
+
+// ---------------------------------------------------------------------------------------------
+// expf exactly as glibc >= 2.27 computes it (sysdeps/ieee754/flt-32/e_expf.c, FMA variant): table-driven
+// 2^(k/32) * P(r) evaluated in double and rounded once to float.  Valid for |x| < 87 (here x in [-1/sigma, 0]).
+// ---------------------------------------------------------------------------------------------
+__constant__ unsigned long long c_exp2f_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
+};
+
+__device__ __forceinline__ float expf_glibc(float x) {
+  if (!(fabsf(x) < 87.0f)) return expf(x);  // outside the table algorithm's plain range (never hit by soft-NMS)
+  const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
+  const double SHIFT = 0x1.8p+52;
+  const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0;
+  const double C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0;
+  const double C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
+  const double xd = static_cast<double>(x);
+  const double z = __dmul_rn(InvLn2N, xd);
+  double kd = __dadd_rn(z, SHIFT);
+  const unsigned long long ki = static_cast<unsigned long long>(__double_as_longlong(kd));
+  kd = __dsub_rn(kd, SHIFT);
+  const double r = __dsub_rn(z, kd);
+  unsigned long long t = c_exp2f_tab[ki & 31];
+  t += ki << (52 - 5);
+  const double s = __longlong_as_double(static_cast<long long>(t));
+  const double zz = __fma_rn(C0, r, C1);
+  const double r2 = __dmul_rn(r, r);
+  double y = __fma_rn(C2, r, 1.0);
+  y = __fma_rn(zz, r2, y);
+  y = __dmul_rn(y, s);
+  return static_cast<float>(y);
+}
+
+// monotone float -> uint key (larger float <=> larger key)
+__device__ __forceinline__ uint32_t fkey(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide helpers (blockDim.x threads, blockDim.x % 32 == 0, <= 1024)
+// ---------------------------------------------------------------------------------------------
+struct BlockScratch {
+  int warp_tot[32];
+  int bcast[4];
+  unsigned hist[256];
+};
+
+// exclusive prefix sum of one int per thread; returns (exclusive, total)
+__device__ __forceinline__ int block_exscan(int v, BlockScratch& s, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s.warp_tot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nw ? s.warp_tot[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < nw) s.warp_tot[lane] = winc - w;  // exclusive warp offsets
+    if (lane == 31) s.bcast[0] = winc;
+  }
+  __syncthreads();
+  total = s.bcast[0];
+  const int ex = s.warp_tot[warp] + inc - v;
+  __syncthreads();
+  return ex;
+}
+
+// k-th largest (1-based k <= number of valid elements) of keyfn(e), e in [0, n).  keyfn returns (valid, key).
+// Returns the key value; ties_needed = how many elements equal to it belong to the top-k.
+template <typename KeyFn>
+__device__ uint32_t block_kth_largest(int n, int k, KeyFn keyfn, BlockScratch& s, int& ties_needed) {
+  uint32_t prefix = 0, mask = 0;
+  int remaining = k;
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) s.hist[b] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      uint32_t key;
+      if (keyfn(e, key) && (key & mask) == prefix) atomicAdd(&s.hist[(key >> (8 * pass)) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cum = 0, digit = 0;
+      for (int b = 255; b >= 0; --b) {
+        const int h = static_cast<int>(s.hist[b]);
+        if (cum + h >= remaining) { digit = b; break; }
+        cum += h;
+      }
+      s.bcast[1] = digit;
+      s.bcast[2] = remaining - cum;
+    }
+    __syncthreads();
+    prefix |= static_cast<uint32_t>(s.bcast[1]) << (8 * pass);
+    mask |= 0xFFu << (8 * pass);
+    remaining = s.bcast[2];
+    __syncthreads();
+  }
+  ties_needed = remaining;
+  return prefix;
+}
+
+// in-place bitonic sort, descending, of n = power of two 64-bit keys in shared memory
+__device__ void block_bitonic_desc(unsigned long long* a, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = a[i], y = a[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (x < y) : (x > y)) { a[i] = y; a[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode: one CTA per (level, video)
+// ---------------------------------------------------------------------------------------------
+static constexpr int DEC_MAX_LEVELS = 16;
+struct DecodeParams {
+  const float* logits;   // (B, P, K)
+  const float* offsets;  // (B, P, 2)
+  const float* pmask;    // (B, P)
+  int B, P, K, n_levels;
+  int lvl_off[DEC_MAX_LEVELS], lvl_len[DEC_MAX_LEVELS];
+  float lvl_stride[DEC_MAX_LEVELS];
+  float pre_nms_thresh, duration_thresh;
+  int topk;   // <= sort_cap
+  int sort_cap;  // power of two >= topk (shared memory entries)
+  // outputs: candidate regions, one per (video, level), each `topk` entries
+  float* cand_segs;    // (B, n_levels*topk, 2)
+  float* cand_scores;  // (B, n_levels*topk)
+  int* cand_labels;    // (B, n_levels*topk)
+  int* cand_count;     // (B, n_levels)
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(1024) decode_kernel(const DecodeParams p) {
+  extern __shared__ unsigned long long dec_keys[];
+  __shared__ BlockScratch s;
+  const int l = blockIdx.x, b = blockIdx.y;
+  const int Tl = p.lvl_len[l], off = p.lvl_off[l], K = p.K;
+  const int n = Tl * K;
+  const float* lg = p.logits + ((long long)b * p.P + off) * K;
+  const float* mk = p.pmask + (long long)b * p.P + off;
+  const float thr = p.pre_nms_thresh;
+  auto prob_of = [&](int e) -> float { return sigmoidf_(lg[e]) * mk[e / K]; };
+  auto keyfn = [&](int e, uint32_t& key) -> bool {
+    const float pr = prob_of(e);
+    key = __float_as_uint(pr);  // pr > thr > 0: raw bits are monotone
+    return pr > thr;
+  };
+  // 1. how many pass the threshold
+  int cnt = 0;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) cnt += prob_of(e) > thr ? 1 : 0;
+  int total;
+  block_exscan(cnt, s, total);
+  const int M = total;
+  uint32_t kth = 0;
+  int ties = 0;
+  const bool select = M > p.topk;
+  if (select) kth = block_kth_largest(n, p.topk, keyfn, s, ties);
+  const int m_sel = select ? p.topk : M;
+  // 2. ordered gather of the selected entries (index order) into shared memory
+  for (int i = threadIdx.x; i < p.sort_cap; i += blockDim.x) dec_keys[i] = 0ull;
+  __syncthreads();
+  int base_gt = 0, base_eq = 0;  // running counts (uniform across the block)
+  for (int e0 = 0; e0 < n; e0 += blockDim.x) {
+    const int e = e0 + threadIdx.x;
+    uint32_t key = 0;
+    bool valid = false;
+    if (e < n) valid = keyfn(e, key);
+    const int is_gt = valid && (!select || key > kth);
+    const int is_eq = valid && select && key == kth;
+    int tot_gt, tot_eq;
+    const int ex_gt = block_exscan(is_gt, s, tot_gt);
+    const int ex_eq = block_exscan(is_eq, s, tot_eq);
+    const unsigned long long k64 = (static_cast<unsigned long long>(key) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(e));
+    // entries strictly above the k-th value occupy [0, g); the ties quota follows (lowest indices first)
+    const int g_total = select ? (p.topk - ties) : M;
+    if (is_gt) dec_keys[base_gt + ex_gt] = k64;
+    if (is_eq && (base_eq + ex_eq) < ties) dec_keys[g_total + base_eq + ex_eq] = k64;
+    base_gt += tot_gt;
+    base_eq += tot_eq;
+  }
+  __syncthreads();
+  // 3. sort by (score desc, index asc)
+  int sort_n = 32;
+  while (sort_n < m_sel) sort_n <<= 1;
+  block_bitonic_desc(dec_keys, sort_n);
+  // 4. segments, duration filter, ordered write-out
+  const float stride = p.lvl_stride[l];
+  const long long region = ((long long)b * p.n_levels + l) * p.topk;
+  int out_base = 0;
+  for (int r0 = 0; r0 < m_sel; r0 += blockDim.x) {
+    const int r = r0 + threadIdx.x;
+    int keep = 0;
+    float left = 0.f, right = 0.f, score = 0.f;
+    int cls = 0;
+    if (r < m_sel) {
+      const unsigned long long k64 = dec_keys[r];
+      const int e = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(k64 & 0xFFFFFFFFull));
+      score = __uint_as_float(static_cast<uint32_t>(k64 >> 32));
+      const int pt = e / K;
+      cls = e - pt * K;
+      const float tpos = static_cast<float>(pt) * stride;  // arange(0, L, stride)[pt], exact
+      const float ol = p.offsets[((long long)b * p.P + off + pt) * 2 + 0];
+      const float orr = p.offsets[((long long)b * p.P + off + pt) * 2 + 1];
+      left = __fsub_rn(tpos, __fmul_rn(ol, stride));    // separate roundings like the eager reference (no FMA)
+      right = __fadd_rn(tpos, __fmul_rn(orr, stride));
+      keep = __fsub_rn(right, left) > p.duration_thresh;
+    }
+    int tot;
+    const int ex = block_exscan(keep, s, tot);
+    if (keep) {
+      const long long o = region + out_base + ex;
+      p.cand_segs[2 * o] = left; p.cand_segs[2 * o + 1] = right;
+      p.cand_scores[o] = score; p.cand_labels[o] = cls;
+    }
+    out_base += tot;
+  }
+  if (threadIdx.x == 0) p.cand_count[b * p.n_levels + l] = out_base;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS.  Candidates of video b live in `n_regions` regions of `region_cap` entries with `region_count[b][r]` valid ones
+// (decode output), or in one region (public batched_nms API).  One CTA per (class, video).
+// ---------------------------------------------------------------------------------------------
+struct NmsParams {
+  const float* segs; const float* scores; const int* labels;  // (B, n_regions*region_cap [,2])
+  const int* region_count;                                    // (B, n_regions)
+  int B, n_regions, region_cap, num_classes;
+  int multiclass;        // 0: all candidates form one class (class-agnostic)
+  int method;            // soft-NMS method 0 hard-as-soft / 1 linear / 2 gaussian; 3 = NMSop hard NMS (pre-filter by score)
+  float iou_threshold, sigma, min_score;
+  int max_num;           // picks kept per class (<= 0: all)
+  // workspace: 5 arrays of (B, n_regions*region_cap) + hole list, partitioned by class via class_count prefix
+  float* w_x1; float* w_x2; float* w_sc; float* w_ar; int* w_ind; int* w_hole;
+  const int* class_count;  // (B, num_classes) — filled by class_count_kernel
+  // outputs per (video, class): picks in order
+  float* dets;     // (B, num_classes, det_cap, 3)
+  int* det_ind;    // (B, num_classes, det_cap)  original candidate index of each pick
+  int* det_count;  // (B, num_classes)
+  int det_cap;
+};
+
+__global__ void class_count_kernel(const NmsParams p, int* class_count) {
+  const int b = blockIdx.y;
+  for (int r = 0; r < p.n_regions; ++r) {
+    const int cnt = p.region_count[b * p.n_regions + r];
+    const int* lab = p.labels + ((long long)b * p.n_regions + r) * p.region_cap;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
+      const int c = p.multiclass ? lab[e] : 0;
+      if (c >= 0 && c < p.num_classes) {
+        if (p.method == 3 && !(p.scores[((long long)b * p.n_regions + r) * p.region_cap + e] > p.min_score)) continue;
+        atomicAdd(&class_count[b * p.num_classes + c], 1);
+      }
+    }
+  }
+}
+
+struct ArgMax { float v; int pos; };
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {  // first maximum wins (nms_cpu.cpp:95-101)
+  if (b.pos < 0) return a;
+  if (a.pos < 0) return b;
+  if (b.v > a.v || (b.v == a.v && b.pos < a.pos)) return b;
+  return a;
+}
+
+__global__ void __launch_bounds__(256) nms_kernel(const NmsParams p) {
+  __shared__ BlockScratch s;
+  __shared__ ArgMax s_am[32];
+  __shared__ float s_pick[4];
+  __shared__ int s_cnt;
+  const int c = blockIdx.x, b = blockIdx.y;
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int* cc = p.class_count + b * p.num_classes;
+  int my_n = cc[c];
+  if (my_n == 0) {
+    if (tid == 0) p.det_count[b * p.num_classes + c] = 0;
+    return;
+  }
+  int woff = 0;
+  for (int k = 0; k < c; ++k) woff += cc[k];
+  const long long wbase = (long long)b * p.n_regions * p.region_cap + woff;
+  float* x1 = p.w_x1 + wbase; float* x2 = p.w_x2 + wbase; float* sc = p.w_sc + wbase; float* ar = p.w_ar + wbase;
+  int* ind = p.w_ind + wbase; int* hole = p.w_hole + wbase;
+
+  // ---- stable gather of this class (ascending original index) -----------------------------------
+  int filled = 0;
+  for (int r = 0; r < p.n_regions; ++r) {
+    const int cnt = p.region_count[b * p.n_regions + r];
+    const long long rb = ((long long)b * p.n_regions + r) * p.region_cap;
+    for (int e0 = 0; e0 < cnt; e0 += nt) {
+      const int e = e0 + tid;
+      int mine = 0;
+      if (e < cnt) {
+        mine = (!p.multiclass || p.labels[rb + e] == c) ? 1 : 0;
+        if (p.method == 3 && !(p.scores[rb + e] > p.min_score)) mine = 0;
+      }
+      int tot;
+      const int ex = block_exscan(mine, s, tot);
+      if (mine) {
+        const int o = filled + ex;
+        const float a = p.segs[2 * (rb + e)], bb = p.segs[2 * (rb + e) + 1];
+        x1[o] = a; x2[o] = bb; sc[o] = p.scores[rb + e];
+        ar[o] = __fadd_rn(__fsub_rn(bb, a), 1e-6f);
+        ind[o] = r * p.region_cap + e;
+      }
+      filled += tot;
+    }
+  }
+  __syncthreads();
+  int n = filled;
+  const int max_picks = p.max_num > 0 ? min(p.max_num, p.det_cap) : p.det_cap;
+  float* dets = p.dets + ((long long)b * p.num_classes + c) * p.det_cap * 3;
+  int* dind = p.det_ind + ((long long)b * p.num_classes + c) * p.det_cap;
+  const int method = p.method == 3 ? 0 : p.method;
+  // NMSop (method 3) suppresses by iou only; as soft-NMS method 0 the suppressed score becomes 0 and must be dropped
+  const float min_score = p.method == 3 ? 1e-30f : p.min_score;
+
+  int i = 0;
+  for (; i < n && i < max_picks; ++i) {
+    // ---- first maximum over [i, n) ----
+    ArgMax best{0.f, -1};
+    for (int pos = i + tid; pos < n; pos += nt) {
+      const float v = sc[pos];
+      if (best.pos < 0 || v > best.v) { best.v = v; best.pos = pos; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ArgMax other;
+      other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+      other.pos = __shfl_xor_sync(0xffffffffu, best.pos, o);
+      best = better(best, other);
+    }
+    if (lane == 0) s_am[warp] = best;
+    __syncthreads();
+    if (warp == 0) {
+      ArgMax v = lane < nw ? s_am[lane] : ArgMax{0.f, -1};
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ArgMax other;
+        other.v = __shfl_xor_sync(0xffffffffu, v.v, o);
+        other.pos = __shfl_xor_sync(0xffffffffu, v.pos, o);
+        v = better(v, other);
+      }
+      if (lane == 0) {
+        const int mp = v.pos;
+        const float ix1 = x1[mp], ix2 = x2[mp], isc = sc[mp], iar = ar[mp];
+        const int iind = ind[mp];
+        x1[mp] = x1[i]; x2[mp] = x2[i]; sc[mp] = sc[i]; ar[mp] = ar[i]; ind[mp] = ind[i];
+        x1[i] = ix1; x2[i] = ix2; sc[i] = isc; ar[i] = iar; ind[i] = iind;
+        dets[3 * i] = ix1; dets[3 * i + 1] = ix2; dets[3 * i + 2] = isc; dind[i] = iind;
+        s_pick[0] = ix1; s_pick[1] = ix2; s_pick[2] = iar;
+      }
+    }
+    __syncthreads();
+    const float ix1 = s_pick[0], ix2 = s_pick[1], iar = s_pick[2];
+    // ---- decay everything after slot i; contiguous range per thread so order-dependent bookkeeping is a scan ----
+    const int m = n - (i + 1);
+    const int per = (m + nt - 1) / nt;
+    const int lo = min(n, i + 1 + tid * per), hi = min(n, lo + per);
+    int ndel = 0;
+    for (int pos = lo; pos < hi; ++pos) {
+      const float xx1 = fmaxf(ix1, x1[pos]);
+      const float xx2 = fminf(ix2, x2[pos]);
+      const float inter = fmaxf(0.f, __fsub_rn(xx2, xx1));
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iar, ar[pos]), inter));
+      float w = 1.f;
+      if (method == 0) { if (ovr >= p.iou_threshold) w = 0.f; }
+      else if (method == 1) { if (ovr >= p.iou_threshold) w = __fsub_rn(1.f, ovr); }
+      else w = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma));
+      const float ns = __fmul_rn(sc[pos], w);
+      sc[pos] = ns;
+      ndel += ns < min_score ? 1 : 0;
+    }
+    if (!__syncthreads_or(ndel > 0)) continue;
+    // ---- compaction with the reference's order: hole k (ascending) <- k-th survivor from the end ----
+    int dtot;
+    const int dbefore = block_exscan(ndel, s, dtot);
+    const int n_new = n - dtot;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    int d = dbefore, holes_here = 0;
+    for (int pos = lo; pos < hi; ++pos)
+      if (sc[pos] < min_score) {
+        if (pos < n_new) { hole[d] = pos; ++holes_here; }
+        ++d;
+      }
+    if (holes_here) atomicAdd(&s_cnt, holes_here);
+    __syncthreads();
+    const int M = s_cnt;  // holes below n_new == survivors at or above n_new
+    d = dbefore;
+    for (int pos = lo; pos < hi; ++pos) {
+      if (sc[pos] < min_score) { ++d; continue; }
+      if (pos >= n_new) {
+        const int s_before = (pos - n_new) - (d - M);  // survivors in [n_new, pos)
+        const int h = hole[M - 1 - s_before];
+        x1[h] = x1[pos]; x2[h] = x2[pos]; sc[h] = sc[pos]; ar[h] = ar[pos]; ind[h] = ind[pos];
+      }
+    }
+    n = n_new;
+    __syncthreads();
+  }
+  if (tid == 0) p.det_count[b * p.num_classes + c] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// final merge: concat classes ascending, sort by score desc (ties: concat index asc), keep max_seg_num
+// ---------------------------------------------------------------------------------------------
+struct MergeParams {
+  const float* dets; const int* det_ind; const int* det_count; int det_cap, num_classes, B;
+  const int* labels_in;  // original labels (for class-agnostic mode), (B, n_total)
+  int multiclass; long long n_total;
+  int max_seg_num;       // <= 1024
+  float* out_segs; float* out_scores; long long* out_labels; int* out_count;  // (B, max_seg_num ...)
+};
+
+__global__ void __launch_bounds__(1024) merge_kernel(const MergeParams p) {
+  __shared__ BlockScratch s;
+  __shared__ unsigned long long keys[1024];
+  __shared__ int s_off[1025];
+  const int b = blockIdx.x;
+  const int* cnt = p.det_count + b * p.num_classes;
+  // class offsets in the concatenation
+  if (threadIdx.x == 0) {
+    int a = 0;
+    for (int c = 0; c < p.num_classes; ++c) { s_off[c] = a; a += cnt[c]; }
+    s_off[p.num_classes] = a;
+  }
+  __syncthreads();
+  const int total = s_off[p.num_classes];
+  const int nslots = p.num_classes * p.det_cap;
+  const float* dets = p.dets + (long long)b * nslots * 3;
+  auto valid_slot = [&](int e) -> bool { return (e % p.det_cap) < cnt[e / p.det_cap]; };
+  auto keyfn = [&](int e, uint32_t& key) -> bool {
+    if (!valid_slot(e)) return false;
+    key = fkey(dets[3 * e + 2]);
+    return true;
+  };
+  const int k = min(p.max_seg_num, total);
+  if (k == 0) {
+    if (threadIdx.x == 0) p.out_count[b] = 0;
+    return;
+  }
+  int ties = 0;
+  uint32_t kth = 0;
+  const bool select = total > k;
+  if (select) kth = block_kth_largest(nslots, k, keyfn, s, ties);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) keys[i] = 0ull;
+  __syncthreads();
+  const int g_total = select ? (k - ties) : total;
+  int base_gt = 0, base_eq = 0;
+  for (int e0 = 0; e0 < nslots; e0 += blockDim.x) {
+    const int e = e0 + threadIdx.x;
+    uint32_t key = 0;
+    bool valid = false;
+    if (e < nslots) valid = keyfn(e, key);
+    const int is_gt = valid && (!select || key > kth);
+    const int is_eq = valid && select && key == kth;
+    int tg, te;
+    const int xg = block_exscan(is_gt, s, tg);
+    const int xe = block_exscan(is_eq, s, te);
+    // concat position (ascending with e inside a class, classes ascending) breaks ties
+    const uint32_t cpos = valid ? static_cast<uint32_t>(s_off[e / p.det_cap] + e % p.det_cap) : 0u;
+    const unsigned long long k64 = (static_cast<unsigned long long>(key) << 32) | (0xFFFFFFFFu - cpos);
+    if (is_gt) keys[base_gt + xg] = k64;
+    if (is_eq && (base_eq + xe) < ties) keys[g_total + base_eq + xe] = k64;
+    base_gt += tg;
+    base_eq += te;
+  }
+  __syncthreads();
+  int sort_n = 32;
+  while (sort_n < k) sort_n <<= 1;
+  block_bitonic_desc(keys, sort_n);
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+    const uint32_t cpos = 0xFFFFFFFFu - static_cast<uint32_t>(keys[r] & 0xFFFFFFFFull);
+    // locate the class of concat position cpos
+    int c = 0;
+    while (c + 1 < p.num_classes && static_cast<uint32_t>(s_off[c + 1]) <= cpos) ++c;
+    const int e = c * p.det_cap + (static_cast<int>(cpos) - s_off[c]);
+    const long long o = (long long)b * p.max_seg_num + r;
+    p.out_segs[2 * o] = dets[3 * e]; p.out_segs[2 * o + 1] = dets[3 * e + 1];
+    p.out_scores[o] = dets[3 * e + 2];
+    long long lab = c;
+    if (!p.multiclass) lab = p.labels_in[(long long)b * p.n_total + p.det_ind[(long long)b * nslots + e]];
+    p.out_labels[o] = lab;
+  }
+  if (threadIdx.x == 0) p.out_count[b] = k;
+}
+
+}  // namespace vilco
+
+using namespace vilco;
+
+extern "C" int vilco_decode(const float* logits, const float* offsets, const float* pmask, int B, int P, int K,
+                            int n_levels, const int* lvl_off, const int* lvl_len, const float* lvl_stride,
+                            float pre_nms_thresh, float duration_thresh, int topk, float* cand_segs, float* cand_scores,
+                            int* cand_labels, int* cand_count, void* stream) {
+  VILCO_CHECK_ARG(logits && offsets && pmask && cand_segs && cand_scores && cand_labels && cand_count, "vilco_decode: null pointer");
+  VILCO_CHECK_ARG(n_levels > 0 && n_levels <= DEC_MAX_LEVELS, "vilco_decode: n_levels %d unsupported", n_levels);
+  VILCO_CHECK_ARG(topk > 0 && topk <= 8192, "vilco_decode: pre_nms_topk %d unsupported (1..8192)", topk);
+  VILCO_CHECK_ARG(pre_nms_thresh > 0.f, "vilco_decode: pre_nms_thresh must be > 0");
+  DecodeParams p{};
+  p.logits = logits; p.offsets = offsets; p.pmask = pmask; p.B = B; p.P = P; p.K = K; p.n_levels = n_levels;
+  for (int l = 0; l < n_levels; ++l) { p.lvl_off[l] = lvl_off[l]; p.lvl_len[l] = lvl_len[l]; p.lvl_stride[l] = lvl_stride[l]; }
+  p.pre_nms_thresh = pre_nms_thresh; p.duration_thresh = duration_thresh; p.topk = topk;
+  int cap = 32;
+  while (cap < topk) cap <<= 1;
+  p.sort_cap = cap;
+  p.cand_segs = cand_segs; p.cand_scores = cand_scores; p.cand_labels = cand_labels; p.cand_count = cand_count;
+  const size_t smem = (size_t)cap * sizeof(unsigned long long);
+  static bool configured = false;
+  if (!configured) {
+    VILCO_CUDA(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+    configured = true;
+  }
+  decode_kernel<<<dim3(n_levels, B), 1024, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" size_t vilco_nms_workspace_bytes(int B, int n_regions, int region_cap, int num_classes, int det_cap) {
+  const size_t n = (size_t)B * n_regions * region_cap;
+  return n * 6 * 4 + (size_t)B * num_classes * 4 * 2 + (size_t)B * num_classes * det_cap * 4 * 4 + 256;
+}
+
+extern "C" int vilco_batched_nms(const float* segs, const float* scores, const int* labels, const int* region_count,
+                                 int B, int n_regions, int region_cap, int num_classes, int multiclass, int method,
+                                 float iou_threshold, float sigma, float min_score, int max_seg_num, void* workspace,
+                                 size_t workspace_bytes, float* out_segs, float* out_scores, long long* out_labels,
+                                 int* out_count, void* stream) {
+  VILCO_CHECK_ARG(segs && scores && labels && region_count && workspace && out_segs && out_scores && out_labels && out_count,
+                  "vilco_batched_nms: null pointer");
+  VILCO_CHECK_ARG(method >= 0 && method <= 3, "vilco_batched_nms: bad method %d", method);
+  VILCO_CHECK_ARG(max_seg_num > 0 && max_seg_num <= 1024, "vilco_batched_nms: max_seg_num %d unsupported (1..1024)", max_seg_num);
+  VILCO_CHECK_ARG(num_classes > 0 && num_classes <= 1024, "vilco_batched_nms: num_classes %d unsupported", num_classes);
+  const int ncls = multiclass ? num_classes : 1;
+  const int det_cap = max_seg_num;
+  VILCO_CHECK_ARG(workspace_bytes >= vilco_nms_workspace_bytes(B, n_regions, region_cap, ncls, det_cap),
+                  "vilco_batched_nms: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)B * n_regions * region_cap;
+  char* w = static_cast<char*>(workspace);
+  NmsParams p{};
+  p.segs = segs; p.scores = scores; p.labels = labels; p.region_count = region_count;
+  p.B = B; p.n_regions = n_regions; p.region_cap = region_cap; p.num_classes = ncls; p.multiclass = multiclass;
+  p.method = method; p.iou_threshold = iou_threshold; p.sigma = sigma; p.min_score = min_score; p.max_num = max_seg_num;
+  p.w_x1 = reinterpret_cast<float*>(w); w += n * 4;
+  p.w_x2 = reinterpret_cast<float*>(w); w += n * 4;
+  p.w_sc = reinterpret_cast<float*>(w); w += n * 4;
+  p.w_ar = reinterpret_cast<float*>(w); w += n * 4;
+  p.w_ind = reinterpret_cast<int*>(w); w += n * 4;
+  p.w_hole = reinterpret_cast<int*>(w); w += n * 4;
+  int* class_count = reinterpret_cast<int*>(w); w += (size_t)B * ncls * 4;
+  p.det_count = reinterpret_cast<int*>(w); w += (size_t)B * ncls * 4;
+  p.dets = reinterpret_cast<float*>(w); w += (size_t)B * ncls * det_cap * 3 * 4;
+  p.det_ind = reinterpret_cast<int*>(w);
+  p.det_cap = det_cap;
+  p.class_count = class_count;
+  VILCO_CUDA(cudaMemsetAsync(class_count, 0, (size_t)B * ncls * 4, st));
+  class_count_kernel<<<dim3(32, B), 256, 0, st>>>(p, class_count);
+  VILCO_LAUNCH_CHECK();
+  nms_kernel<<<dim3(ncls, B), 256, 0, st>>>(p);
+  VILCO_LAUNCH_CHECK();
+  MergeParams m{};
+  m.dets = p.dets; m.det_ind = p.det_ind; m.det_count = p.det_count; m.det_cap = det_cap; m.num_classes = ncls; m.B = B;
+  m.labels_in = labels; m.multiclass = multiclass; m.n_total = (long long)n_regions * region_cap; m.max_seg_num = max_seg_num;
+  m.out_segs = out_segs; m.out_scores = out_scores; m.out_labels = out_labels; m.out_count = out_count;
+  merge_kernel<<<B, 1024, 0, st>>>(m);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}

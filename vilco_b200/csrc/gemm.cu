@@ -23,7 +23,7 @@ struct GemmDev {
   int b_slot_row, b_slot_z1, b_slot_z2;
   int M, N, K, taps, Z1;
   int b_major, b_batched;
-  void* D; int d_dtype; long long d_ld, d_s1, d_s2;
+  void* D; int d_dtype; long long d_ld, d_s1, d_s2, d_lo;
   float alpha;
   const float* bias;
   const float* rowmul; long long rowmul_zs;
@@ -56,11 +56,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -114,11 +114,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn_major) {
          | (static_cast<uint32_t>(BM >> 4) << 24);   // m_dim
 }
 
-template <int BN>
+// SPLIT: every operand is a (hi, lo) pair of bf16 planes (x ~= hi + lo, lo = bf16(x - hi)); the product is formed as
+// hi*hi + hi*lo + lo*hi (three MMAs into the same accumulator), which recovers ~16 mantissa bits per operand.
+template <int BN, bool SPLIT>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int PLANES = SPLIT ? 2 : 1;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -133,14 +136,20 @@ __device__ __forceinline__ float epi_value(const GemmDev& p, float acc, int n, f
   return v + res;
 }
 
+__device__ __forceinline__ void store_bf16_split(__nv_bfloat16* D, long long off, long long lo_off, float o) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(o);
+  D[off] = h;
+  if (lo_off) D[lo_off + off] = __float2bfloat16_rn(o - __bfloat162float(h));
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmDev p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, SPLIT>;
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
@@ -197,11 +206,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tap = it / kblocks;
         const int kb = it - tap * kblocks;
         const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
+        const uint32_t sb = sa + L::A_BYTES * L::PLANES;
         mbar_expect_tx(full0 + 8 * s, L::STAGE_BYTES);
         ca[0] = kb * BK;
         ca[p.a_slot_row] = m0 + tap - (p.taps >> 1);
-        tma_load_4d(sa, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3]);
         cb[p.b_slot_z1] = p.b_batched ? z1 : tap;
         if (p.b_major == 0) {
           cb[0] = kb * BK;
@@ -210,7 +218,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           cb[0] = n0;
           cb[p.b_slot_row] = kb * BK;
         }
-        tma_load_4d(sb, &tmB, full0 + 8 * s, cb[0], cb[1], cb[2], cb[3]);
+#pragma unroll
+        for (int pl = 0; pl < L::PLANES; ++pl) {
+          tma_load_5d(sa + pl * L::A_BYTES, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3], pl);
+          tma_load_5d(sb + pl * L::B_BYTES, &tmB, full0 + 8 * s, cb[0], cb[1], cb[2], cb[3], pl);
+        }
       }
     }
   } else if (warp == 1) {
@@ -223,15 +235,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tcgen05_fence_after();
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
+        const uint32_t sb = sa + L::A_BYTES * L::PLANES;
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major: advance 16 elements = 32 bytes inside the swizzle atom.
-          const uint64_t adesc = make_smem_desc(sa + k * UMMA_K * 2, 16, 1024);
-          // MN-major: advance 16 k-rows of 128 bytes.
-          const uint64_t bdesc = p.b_major == 0 ? make_smem_desc(sb + k * UMMA_K * 2, 16, 1024)
-                                                : make_smem_desc(sb + k * UMMA_K * 128, 16, 1024);
-          tcgen05_mma_f16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          // K-major: advance 16 elements = 32 bytes inside the swizzle atom; MN-major: 16 k-rows of 128 bytes.
+          const uint32_t aoff = k * UMMA_K * 2;
+          const uint32_t boff = p.b_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
+          const uint64_t a_hi = make_smem_desc(sa + aoff, 16, 1024);
+          const uint64_t b_hi = make_smem_desc(sb + boff, 16, 1024);
+          tcgen05_mma_f16(tmem_base, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (SPLIT) {
+            const uint64_t a_lo = make_smem_desc(sa + L::A_BYTES + aoff, 16, 1024);
+            const uint64_t b_lo = make_smem_desc(sb + L::B_BYTES + boff, 16, 1024);
+            tcgen05_mma_f16(tmem_base, a_hi, b_lo, idesc, 1u);
+            tcgen05_mma_f16(tmem_base, a_lo, b_hi, idesc, 1u);
+          }
         }
         tcgen05_commit(empty0 + 8 * s);            // frees the smem stage when these MMAs retire
         if (it == iters - 1) tcgen05_commit(tfull);  // accumulator complete
@@ -278,10 +296,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 8; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
           uint4* dp = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.D) + doff + nb);
+          uint4* dl = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.D) + p.d_lo + doff + nb);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < 4; ++j) {
+            uint32_t h[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float x0 = v[8 * j + 2 * u], x1 = v[8 * j + 2 * u + 1];
+              h[u] = pack_bf16x2(x0, x1);
+              lo[u] = pack_bf16x2(x0 - bf16_lo(h[u]), x1 - bf16_hi(h[u]));
+            }
+            dp[j] = make_uint4(h[0], h[1], h[2], h[3]);
+            if (p.d_lo) dl[j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
       } else {
 #pragma unroll
@@ -291,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float res = p.resid ? p.resid[doff + n] * rres : 0.0f;
             const float o = epi_value(p, __uint_as_float(r[j]), n, rm, res);
             if (p.d_dtype == VILCO_F32) static_cast<float*>(p.D)[doff + n] = o;
-            else static_cast<__nv_bfloat16*>(p.D)[doff + n] = __float2bfloat16_rn(o);
+            else store_bf16_split(static_cast<__nv_bfloat16*>(p.D), doff + n, p.d_lo, o);
           }
         }
       }
@@ -310,10 +337,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // SIMT cross-check kernel: same contract, one thread per output element, reads global memory directly.
 // ---------------------------------------------------------------------------------------------
 struct SimtAddr {
-  const __nv_bfloat16* A; long long a_ld, a_s1, a_s2; int a_rows;
-  const __nv_bfloat16* B; long long b_ld, b_s1, b_s2;
+  const __nv_bfloat16* A; long long a_ld, a_s1, a_s2, a_lo; int a_rows;
+  const __nv_bfloat16* B; long long b_ld, b_s1, b_s2, b_lo;
   int Z2;
 };
+__device__ __forceinline__ float ld_split(const __nv_bfloat16* p, long long lo) {
+  float v = __bfloat162float(p[0]);
+  if (lo) v += __bfloat162float(p[lo]);
+  return v;
+}
 
 __global__ void gemm_simt_kernel(const GemmDev p, const SimtAddr q) {
   const long long total = (long long)p.M * p.N;
@@ -330,10 +362,10 @@ __global__ void gemm_simt_kernel(const GemmDev p, const SimtAddr q) {
       const __nv_bfloat16* a = q.A + z1 * q.a_s1 + z2 * q.a_s2 + (long long)row * q.a_ld;
       if (p.b_major == 0) {
         const __nv_bfloat16* b = q.B + (p.b_batched ? z1 * q.b_s1 + z2 * q.b_s2 : tap * q.b_s1) + (long long)n * q.b_ld;
-        for (int k = 0; k < p.K; ++k) acc = fmaf(__bfloat162float(a[k]), __bfloat162float(b[k]), acc);
+        for (int k = 0; k < p.K; ++k) acc = fmaf(ld_split(a + k, q.a_lo), ld_split(b + k, q.b_lo), acc);
       } else {
         const __nv_bfloat16* b = q.B + (p.b_batched ? z1 * q.b_s1 + z2 * q.b_s2 : tap * q.b_s1) + n;
-        for (int k = 0; k < p.K; ++k) acc = fmaf(__bfloat162float(a[k]), __bfloat162float(b[(long long)k * q.b_ld]), acc);
+        for (int k = 0; k < p.K; ++k) acc = fmaf(ld_split(a + k, q.a_lo), ld_split(b + (long long)k * q.b_ld, q.b_lo), acc);
       }
     }
     float rm = 1.0f;
@@ -342,7 +374,7 @@ __global__ void gemm_simt_kernel(const GemmDev p, const SimtAddr q) {
     const float res = p.resid ? p.resid[doff] * (p.resid_masked ? rm : 1.0f) : 0.0f;
     const float o = epi_value(p, acc, n, rm, res);
     if (p.d_dtype == VILCO_F32) static_cast<float*>(p.D)[doff] = o;
-    else static_cast<__nv_bfloat16*>(p.D)[doff] = __float2bfloat16_rn(o);
+    else store_bf16_split(static_cast<__nv_bfloat16*>(p.D), doff, p.d_lo, o);
   }
 }
 
@@ -365,7 +397,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 // Build a 4-D bf16 tensor map (inner, row, z1, z2); the three outer dims are sorted by stride so the
 // descriptor always sees non-decreasing strides.  slots[] receives the coordinate slot of (row, z1, z2).
 static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, int64_t ld, uint64_t n1,
-                      int64_t s1, uint64_t n2, int64_t s2, uint32_t box_inner, uint32_t box_rows, int slots[3]) {
+                      int64_t s1, uint64_t n2, int64_t s2, int64_t lo_off, uint32_t box_inner, uint32_t box_rows,
+                      int slots[3]) {
   auto fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return VILCO_E_CUDA; }
   struct Dim { uint64_t n; int64_t stride; uint32_t box; int id; };
@@ -377,16 +410,19 @@ static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   for (int i = 0; i < 3; ++i)
     for (int j = i + 1; j < 3; ++j)
       if (d[j].stride < d[i].stride) { Dim t = d[i]; d[i] = d[j]; d[j] = t; }
-  cuuint64_t gdim[4] = {inner, d[0].n, d[1].n, d[2].n};
-  cuuint64_t gstr[3] = {(cuuint64_t)d[0].stride * 2, (cuuint64_t)d[1].stride * 2, (cuuint64_t)d[2].stride * 2};
-  cuuint32_t box[4] = {box_inner, d[0].box, d[1].box, d[2].box};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  for (int i = 0; i < 3; ++i) {
-    slots[d[i].id] = i + 1;
+  // 5th dim = operand plane (hi, lo); extent 1 when the operand has no lo plane
+  const uint64_t planes = lo_off ? 2 : 1;
+  const int64_t pstride = lo_off ? lo_off : (big + 7) / 8 * 8 * 2;
+  cuuint64_t gdim[5] = {inner, d[0].n, d[1].n, d[2].n, planes};
+  cuuint64_t gstr[4] = {(cuuint64_t)d[0].stride * 2, (cuuint64_t)d[1].stride * 2, (cuuint64_t)d[2].stride * 2,
+                        (cuuint64_t)pstride * 2};
+  cuuint32_t box[5] = {box_inner, d[0].box, d[1].box, d[2].box, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i) slots[d[i].id] = i + 1;
+  for (int i = 0; i < 4; ++i)
     if (gstr[i] % 16 != 0) { set_error("tensor map stride %llu bytes is not a multiple of 16", (unsigned long long)gstr[i]); return VILCO_E_ARG; }
-  }
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) { set_error("tensor map base not 16-byte aligned"); return VILCO_E_ARG; }
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -399,17 +435,17 @@ static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return VILCO_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int Z, cudaStream_t st) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, SPLIT>;
   constexpr int smem = STAGES * L::STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
-    VILCO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VILCO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, Z);
-  gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN, STAGES, SPLIT><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -432,11 +468,12 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   p.M = g->M; p.N = g->N; p.K = g->K; p.taps = g->taps; p.Z1 = g->Z1;
   p.b_major = g->b_major; p.b_batched = g->b_batched;
   p.D = g->D; p.d_dtype = g->d_dtype; p.d_ld = g->d_ld; p.d_s1 = g->d_s1; p.d_s2 = g->d_s2;
+  p.d_lo = g->d_dtype == VILCO_BF16 ? g->d_lo : 0;
   p.alpha = g->alpha; p.bias = g->bias; p.rowmul = g->rowmul; p.rowmul_zs = g->rowmul_zs;
   p.act = g->act; p.colscale = g->colscale; p.resid = g->resid; p.resid_masked = g->resid_masked;
   const int esz = g->d_dtype == VILCO_F32 ? 4 : 2;
   p.vec_ok = (reinterpret_cast<uintptr_t>(g->D) % 16 == 0) && ((g->d_ld * esz) % 16 == 0) &&
-             ((g->d_s1 * esz) % 16 == 0) && ((g->d_s2 * esz) % 16 == 0) &&
+             ((g->d_s1 * esz) % 16 == 0) && ((g->d_s2 * esz) % 16 == 0) && ((p.d_lo * esz) % 16 == 0) &&
              (!g->resid || (reinterpret_cast<uintptr_t>(g->resid) % 16 == 0 && (g->d_ld * 4) % 16 == 0 &&
                             (g->d_s1 * 4) % 16 == 0 && (g->d_s2 * 4) % 16 == 0));
   const int Z = g->Z1 * g->Z2;
@@ -444,6 +481,7 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   if (g->impl == 1) {
     SimtAddr q{};
     q.A = static_cast<const __nv_bfloat16*>(g->A); q.a_ld = g->a_ld; q.a_s1 = g->a_s1; q.a_s2 = g->a_s2; q.a_rows = g->a_rows;
+    q.a_lo = g->a_lo; q.b_lo = g->b_lo;
     q.B = static_cast<const __nv_bfloat16*>(g->B); q.b_ld = g->b_ld; q.b_s1 = g->b_s1; q.b_s2 = g->b_s2; q.Z2 = g->Z2;
     const long long total = (long long)g->M * g->N;
     int blocks = static_cast<int>((total + 255) / 256);
@@ -462,27 +500,35 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
 
   CUtensorMap tmA, tmB;
   int sa[3], sb[3];
+  const bool split = g->a_lo != 0 && g->b_lo != 0;
   int rc = encode_map(&tmA, g->A, (uint64_t)g->K, (uint64_t)g->a_rows, g->a_ld, (uint64_t)g->Z1, g->a_s1,
-                      (uint64_t)g->Z2, g->a_s2, BK, BM, sa);
+                      (uint64_t)g->Z2, g->a_s2, split ? g->a_lo : 0, BK, BM, sa);
   if (rc) return rc;
   if (g->b_major == 0) {
     // (k inner, n rows, z1|tap, z2)
     const uint64_t n1 = g->b_batched ? (uint64_t)g->Z1 : (uint64_t)g->taps;
     const uint64_t n2 = g->b_batched ? (uint64_t)g->Z2 : 1;
-    rc = encode_map(&tmB, g->B, (uint64_t)g->K, (uint64_t)g->N, g->b_ld, n1, g->b_s1, n2, g->b_s2, BK, BN, sb);
+    rc = encode_map(&tmB, g->B, (uint64_t)g->K, (uint64_t)g->N, g->b_ld, n1, g->b_s1, n2, g->b_s2, split ? g->b_lo : 0, BK, BN, sb);
   } else {
     // (n inner, k rows, z1, z2)
     const uint64_t n1 = g->b_batched ? (uint64_t)g->Z1 : (uint64_t)g->taps;
     const uint64_t n2 = g->b_batched ? (uint64_t)g->Z2 : 1;
-    rc = encode_map(&tmB, g->B, (uint64_t)g->N, (uint64_t)g->K, g->b_ld, n1, g->b_s1, n2, g->b_s2, 64, BK, sb);
+    rc = encode_map(&tmB, g->B, (uint64_t)g->N, (uint64_t)g->K, g->b_ld, n1, g->b_s1, n2, g->b_s2, split ? g->b_lo : 0, 64, BK, sb);
   }
   if (rc) return rc;
   p.a_slot_row = sa[0]; p.a_slot_z1 = sa[1]; p.a_slot_z2 = sa[2];
   p.b_slot_row = sb[0]; p.b_slot_z1 = sb[1]; p.b_slot_z2 = sb[2];
 
+  if (split) {
+    switch (BN) {
+      case 32: return launch_tc<32, 4, true>(tmA, tmB, p, Z, st);
+      case 64: return launch_tc<64, 4, true>(tmA, tmB, p, Z, st);
+      default: return launch_tc<128, 3, true>(tmA, tmB, p, Z, st);
+    }
+  }
   switch (BN) {
-    case 32: return launch_tc<32, 6>(tmA, tmB, p, Z, st);
-    case 64: return launch_tc<64, 6>(tmA, tmB, p, Z, st);
-    default: return launch_tc<128, 4>(tmA, tmB, p, Z, st);
+    case 32: return launch_tc<32, 6, false>(tmA, tmB, p, Z, st);
+    case 64: return launch_tc<64, 6, false>(tmA, tmB, p, Z, st);
+    default: return launch_tc<128, 4, false>(tmA, tmB, p, Z, st);
   }
 }

@@ -22,11 +22,11 @@ class VilcoError(RuntimeError):
 
 class VilcoGemm(C.Structure):
     _fields_ = [
-        ("A", C.c_void_p), ("a_ld", C.c_int64), ("a_s1", C.c_int64), ("a_s2", C.c_int64), ("a_rows", C.c_int32),
-        ("B", C.c_void_p), ("b_ld", C.c_int64), ("b_s1", C.c_int64), ("b_s2", C.c_int64),
+        ("A", C.c_void_p), ("a_ld", C.c_int64), ("a_s1", C.c_int64), ("a_s2", C.c_int64), ("a_lo", C.c_int64), ("a_rows", C.c_int32),
+        ("B", C.c_void_p), ("b_ld", C.c_int64), ("b_s1", C.c_int64), ("b_s2", C.c_int64), ("b_lo", C.c_int64),
         ("b_major", C.c_int32), ("b_batched", C.c_int32),
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("taps", C.c_int32), ("Z1", C.c_int32), ("Z2", C.c_int32),
-        ("D", C.c_void_p), ("d_dtype", C.c_int32), ("d_ld", C.c_int64), ("d_s1", C.c_int64), ("d_s2", C.c_int64),
+        ("D", C.c_void_p), ("d_dtype", C.c_int32), ("d_ld", C.c_int64), ("d_s1", C.c_int64), ("d_s2", C.c_int64), ("d_lo", C.c_int64),
         ("alpha", C.c_float),
         ("bias", C.c_void_p),
         ("rowmul", C.c_void_p), ("rowmul_zs", C.c_int64),
@@ -52,6 +52,7 @@ def lib():
         _lib.vilco_last_error.restype = C.c_char_p
         _lib.vilco_launch_count.restype = C.c_uint64
         _lib.vilco_version.restype = C.c_int
+        _lib.vilco_nms_workspace_bytes.restype = C.c_size_t
     return _lib
 
 
@@ -80,7 +81,7 @@ def default_gemm_impl():
 
 def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), d_s=(0, 0), Z=(1, 1), taps=1,
          b_major=0, b_batched=False, alpha=1.0, bias=None, rowmul=None, rowmul_zs=0, act=ACT_NONE,
-         colscale=None, resid=None, resid_masked=False, impl=None):
+         colscale=None, resid=None, resid_masked=False, impl=None, a_lo=0, b_lo=0, d_lo=0):
     """Raw descriptor-level call of ``vilco_gemm`` (see include/vilco_b200.h for the contract)."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
     assert D.dtype in (torch.float32, torch.bfloat16)
@@ -88,6 +89,7 @@ def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), 
         assert t is None or (t.dtype == torch.float32 and t.is_cuda)
     g = VilcoGemm()
     g.A, g.a_ld, g.a_s1, g.a_s2, g.a_rows = A.data_ptr(), a_ld, a_s[0], a_s[1], a_rows
+    g.a_lo, g.b_lo, g.d_lo = a_lo, b_lo, d_lo
     g.B, g.b_ld, g.b_s1, g.b_s2 = B.data_ptr(), b_ld, b_s[0], b_s[1]
     g.b_major, g.b_batched = b_major, int(b_batched)
     g.M, g.N, g.K, g.taps, g.Z1, g.Z2 = M, N, K, taps, Z[0], Z[1]

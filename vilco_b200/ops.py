@@ -1,0 +1,215 @@
+"""Tensor-level wrappers over the C ABI (include/vilco_b200.h).  Token-major layout: (B, T, C), C contiguous.
+
+Every function here launches hand-written sm_100a kernels through ``libvilco_b200.so``; torch only owns the memory.
+
+Operand convention: every bf16 *operand* tensor carries a leading "plane" dimension of size ``PLANES``:
+  PLANES == 1  ("bf16")   : plain bf16 operands, one MMA per k-step (fast; ~3e-3 relative error per GEMM chain)
+  PLANES == 2  ("bf16x3") : x ~= hi + lo with lo = bf16(x - hi); GEMMs accumulate hi*hi + hi*lo + lo*hi in fp32
+                            (~1e-5 relative error) — the mode that meets the 1e-3 parity bar.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import lib as L
+from .lib import ACT_GELU, ACT_NONE, ACT_RELU  # noqa: F401
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+PLANES = 1 if os.environ.get("VILCO_PRECISION", "bf16x3") == "bf16" else 2
+
+
+def set_precision(name):
+    """'bf16x3' (default, parity mode) or 'bf16' (fast mode).  Weights must be re-packed after a change."""
+    global PLANES
+    assert name in ("bf16", "bf16x3")
+    PLANES = 1 if name == "bf16" else 2
+
+
+def precision():
+    return "bf16" if PLANES == 1 else "bf16x3"
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _i64(v):
+    return C.c_int64(int(v))
+
+
+def lo(t):
+    """element offset of the lo plane of an operand tensor (0 when single-plane)."""
+    return t.stride(0) if t.shape[0] == 2 else 0
+
+
+def empty16(*shape, device="cuda"):
+    return torch.empty(PLANES, *shape, device=device, dtype=bf16)
+
+
+def zeros16(*shape, device="cuda"):
+    return torch.zeros(PLANES, *shape, device=device, dtype=bf16)
+
+
+def split16(x):
+    """fp32 tensor -> (PLANES, ...) bf16 operand (used for weights / constants at pack time)."""
+    hi = x.to(bf16)
+    if PLANES == 1:
+        return hi.unsqueeze(0).contiguous()
+    return torch.stack([hi, (x - hi.float()).to(bf16)]).contiguous()
+
+
+def merge16(t):
+    """(PLANES, ...) bf16 operand -> fp32 value (tests / debugging)."""
+    return t.float().sum(0)
+
+
+def linear(x, w, out_dtype=bf16, bias=None, rowmul=None, act=ACT_NONE, colscale=None, resid=None, resid_masked=False,
+           alpha=1.0, out=None):
+    """y[r, n] = epi(sum_k x[r, k] w[n, k]).  x (NP, ..., K) bf16 operand, w (NP, N, K).  rowmul (rows,) fp32,
+    resid (..., N) fp32.  Returns an operand tensor (NP, ..., N) for bf16 output, a plain fp32 tensor otherwise."""
+    K = x.shape[-1]
+    N = w.shape[1]
+    assert w.shape[2] == K and K % 8 == 0
+    rows = x[0].numel() // K
+    if out is None:
+        out = empty16(*x.shape[1:-1], N, device=x.device) if out_dtype == bf16 else \
+            torch.empty(*x.shape[1:-1], N, device=x.device, dtype=f32)
+    L.gemm(x, w, out, M=rows, N=N, K=K, a_rows=rows, a_ld=K, b_ld=K, d_ld=N, a_lo=lo(x), b_lo=lo(w),
+           d_lo=lo(out) if out.dtype == bf16 else 0,
+           bias=bias, rowmul=rowmul, act=act, colscale=colscale, resid=resid, resid_masked=resid_masked, alpha=alpha)
+    return out
+
+
+def conv3(x, w3, out_dtype=bf16, bias=None, rowmul=None, act=ACT_NONE):
+    """k=3 stride-1 zero-padded conv over time.  x (NP, B, T, Cin), w3 (NP, 3, Cout, Cin) tap-major,
+    rowmul (B, T) fp32 -> (B, T, Cout) fp32 or operand (NP, B, T, Cout)."""
+    _, B, T, Cin = x.shape
+    Cout = w3.shape[2]
+    assert w3.shape[1] == 3 and w3.shape[3] == Cin and Cin % 8 == 0
+    out = empty16(B, T, Cout, device=x.device) if out_dtype == bf16 else torch.empty(B, T, Cout, device=x.device, dtype=f32)
+    L.gemm(x, w3, out, M=T, N=Cout, K=Cin, a_rows=T, a_ld=Cin, a_s=(0, T * Cin), Z=(1, B), taps=3, b_ld=Cin,
+           b_s=(Cout * Cin, 0), d_ld=Cout, d_s=(0, T * Cout), a_lo=lo(x), b_lo=lo(w3),
+           d_lo=lo(out) if out.dtype == bf16 else 0, bias=bias, rowmul=rowmul, rowmul_zs=T, act=act)
+    return out
+
+
+def attn_scores(q, k, H, alpha):
+    """S[b,h] = alpha * q_h k_h^T.  q (NP,B,Tq,C), k (NP,B,Tk,C) -> (B,H,Tq,Tk) fp32."""
+    _, B, Tq, Cc = q.shape
+    Tk = k.shape[2]
+    d = Cc // H
+    out = torch.empty(B, H, Tq, Tk, device=q.device, dtype=f32)
+    L.gemm(q, k, out, M=Tq, N=Tk, K=d, a_rows=Tq, a_ld=Cc, a_s=(d, Tq * Cc), Z=(H, B), b_ld=Cc, b_s=(d, Tk * Cc),
+           b_batched=True, d_ld=Tk, d_s=(Tq * Tk, H * Tq * Tk), alpha=alpha, a_lo=lo(q), b_lo=lo(k))
+    return out
+
+
+def attn_pv(P, v, H, Tk):
+    """O[b, :, h*d:(h+1)*d] = P[b,h] v_h.  P (NP,B,H,Tq,ldp), v (NP,B,Tk,C) -> operand (NP,B,Tq,C)."""
+    _, B, _, Tq, ldp = P.shape
+    Cc = v.shape[3]
+    d = Cc // H
+    assert d == 64, "attn_pv: head dim must be 64"
+    out = empty16(B, Tq, Cc, device=v.device)
+    L.gemm(P, v, out, M=Tq, N=d, K=Tk, a_rows=Tq, a_ld=ldp, a_s=(Tq * ldp, H * Tq * ldp), Z=(H, B), b_ld=Cc,
+           b_s=(d, Tk * Cc), b_batched=True, b_major=1, d_ld=Cc, d_s=(d, Tq * Cc), a_lo=lo(P), b_lo=lo(v), d_lo=lo(out))
+    return out
+
+
+def layernorm(x, w, b, eps=1e-5, add=None, relu=False, pe=None, rowmul=None, zero_rows=None, out32=False, out16=True,
+              y16=None, rows_per_batch=None, y_ld=None, y_bs=None, y16_lo=None):
+    """Channel LN over the last dim of token-major fp32 x.  Returns (y32 or None, y16 operand or None).
+    `y16` may be a pre-allocated destination view (then pass y_ld / y_bs / y16_lo / rows_per_batch)."""
+    assert x.dtype == f32 and x.is_contiguous()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    y32 = torch.empty(x.shape, device=x.device, dtype=f32) if out32 else None
+    if out16 and y16 is None:
+        y16 = empty16(*x.shape, device=x.device)
+        y16_lo = lo(y16)
+    rpb = rows if rows_per_batch is None else rows_per_batch
+    L.check(L.lib().vilco_layernorm(
+        _p(x), L.F32, _p(add), _p(w), _p(b), C.c_float(eps), int(relu), _p(pe),
+        0 if pe is None else pe.shape[0], _p(rowmul), _p(zero_rows), _p(y32), _p(y16), _i64(y16_lo or 0),
+        _i64(Cc if y_ld is None else y_ld), _i64(rpb * Cc if y_bs is None else y_bs), rows, rpb, Cc,
+        L.stream_ptr()), "vilco_layernorm")
+    return y32, y16
+
+
+def dwconv_ln(x, mask, wconvs, lnws, lnbs, stride, eps=1e-5):
+    """x (B,T,C) fp32, mask (B,T) fp32 -> list of operands (NP,B,T/stride,C), one per (wconv, ln) set."""
+    assert x.dtype == f32 and x.is_contiguous()
+    B, T, Cc = x.shape
+    n = len(wconvs)
+    outs = [empty16(B, T // stride, Cc, device=x.device) for _ in range(n)]
+    arr = C.c_void_p * n
+    L.check(L.lib().vilco_dwconv_ln(
+        _p(x), L.F32, _p(mask), arr(*[w.data_ptr() for w in wconvs]),
+        arr(*[w.data_ptr() for w in lnws]), arr(*[w.data_ptr() for w in lnbs]), arr(*[o.data_ptr() for o in outs]),
+        _i64(lo(outs[0])), n, B, T, Cc, stride, C.c_float(eps), L.stream_ptr()), "vilco_dwconv_ln")
+    return outs
+
+
+def maxpool3s2(x):
+    B, T, Cc = x.shape
+    y = torch.empty(B, T // 2, Cc, device=x.device, dtype=f32)
+    L.check(L.lib().vilco_maxpool3s2(_p(x), _p(y), B, T, Cc, L.stream_ptr()), "vilco_maxpool3s2")
+    return y
+
+
+def axpby(x, y=None, a=1.0, b=0.0, out32=True, out16=False):
+    """a*x + b*y on fp32 tensors -> (fp32 or None, operand or None)."""
+    o32 = torch.empty_like(x) if out32 else None
+    o16 = empty16(*x.shape, device=x.device) if out16 else None
+    L.check(L.lib().vilco_axpby(_p(x), _p(y), C.c_float(a), C.c_float(b), _p(o32), _p(o16),
+                                _i64(lo(o16) if out16 else 0), _i64(x.numel()), L.stream_ptr()), "vilco_axpby")
+    return o32, o16
+
+
+def pack_feats(x, T_out=None):
+    """(B, C, T) fp32 (reference layout) -> operand (NP, B, T_out, C)."""
+    assert x.dtype == f32 and x.is_contiguous()
+    B, Cc, T = x.shape
+    T_out = T if T_out is None else T_out
+    y = empty16(B, T_out, Cc, device=x.device)
+    L.check(L.lib().vilco_pack_feats(_p(x), _p(y), _i64(lo(y)), B, Cc, T, T_out, L.stream_ptr()), "vilco_pack_feats")
+    return y
+
+
+def unpack(x):
+    """(B, T, C) fp32 -> (B, C, T) fp32."""
+    B, T, Cc = x.shape
+    y = torch.empty(B, Cc, T, device=x.device, dtype=f32)
+    L.check(L.lib().vilco_unpack(_p(x), _p(y), B, T, Cc, L.stream_ptr()), "vilco_unpack")
+    return y
+
+
+def softmax_rows(S, kmask, mode=0, BD=None, scale=1.0):
+    """S (B,H,Tq,Tk) fp32 -> P operand (NP,B,H,Tq,ldp) with ldp = roundup(Tk, 8)."""
+    B, H, Tq, Tk = S.shape
+    ldp = (Tk + 7) // 8 * 8
+    P = empty16(B, H, Tq, ldp, device=S.device)
+    L.check(L.lib().vilco_softmax_rows(_p(S), _p(BD), _p(kmask), _p(P), _i64(lo(P)), B, H, Tq, Tk, _i64(ldp),
+                                       C.c_float(scale), mode, L.stream_ptr()), "vilco_softmax_rows")
+    return P
+
+
+def local_attention(q, k, v, mask, H, W, rel_pe=None):
+    _, B, T, Cc = q.shape
+    out = empty16(B, T, Cc, device=q.device)
+    L.check(L.lib().vilco_local_attention(_p(q), _p(k), _p(v), _p(mask), _p(rel_pe), _p(out), _i64(lo(out)), B, T, Cc, H,
+                                          W, L.stream_ptr()), "vilco_local_attention")
+    return out
+
+
+def channel_attention(qkv, H):
+    _, B, T, C3 = qkv.shape
+    Cc = C3 // 3
+    G = torch.empty(B, H, 64, 64, device=qkv.device, dtype=f32)
+    y = empty16(B, T, Cc, device=qkv.device)
+    L.check(L.lib().vilco_channel_attention(_p(qkv), _i64(lo(qkv)), _p(G), _p(y), _i64(lo(y)), B, T, Cc, H,
+                                            L.stream_ptr()), "vilco_channel_attention")
+    return y
