@@ -164,6 +164,18 @@ int vilco_batched_nms(const float* segs, const float* scores, const int* labels,
                       float sigma, float min_score, int max_seg_num, void* workspace, size_t workspace_bytes,
                       float* out_segs, float* out_scores, long long* out_labels, int* out_count, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Fused forward of the Moment-Query losses — PtTransformer.losses, MQ/libs/modeling/meta_archs.py:1374-1480:
+ * sigmoid focal loss (alpha .25, gamma 2; MQ/libs/modeling/losses.py:5-51) summed over classes and weighted by the
+ * gaussian weight (1 on negatives), DIoU (losses.py:109-168) on positives weighted by (w_l + w_r)/2 * w_cls, the number of
+ * positives, and the label-involved loss  sum_{b,k} BCE(max_t softmax_K(logits)[b,k], present[b,k]).
+ * All tensors over the concatenated pyramid rows (B,P,...); gap (P,) flags layout-only rows.  sums4 (device) receives
+ * [cls_sum, reg_sum, num_pos, al_sum] (un-normalised; the caller divides by the EMA loss normaliser).
+ * ------------------------------------------------------------------------------------ */
+int vilco_mq_losses(const float* logits, const float* offsets, const float* pmask, const uint8_t* gap, const float* gt_cls,
+                    const float* gt_off, const float* w_cls, const float* w_l, const float* w_r, const float* present, int B,
+                    int P, int K, float alpha, float gamma, float* sums4, unsigned int* smax_scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

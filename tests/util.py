@@ -1,0 +1,25 @@
+import numpy as np
+import torch
+
+TOL = 1e-3  # north-star tolerance: logits / offsets / losses within 1e-3 relative (bf16 operands, fp32 accumulate)
+
+
+def rel_max(a, b):
+    """max |a - b| / max |b| — the relative error used throughout the parity tests."""
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def build_pair(cfg, seed=0):
+    """(vilco_b200 model on cuda with seeded weights, the same weights as an oracle params dict)."""
+    from oracle import params as PR
+    from vilco_b200.config import mq_model_kwargs
+    from vilco_b200.modeling import make_meta_arch
+    P = PR.random_state(PR.param_spec(cfg), seed)
+    model = make_meta_arch("LocPointTransformer", **mq_model_kwargs(
+        cfg.input_dim, cfg.embd_dim, cfg.n_head, cfg.max_seq_len, cfg.arch, cfg.num_classes, cfg.n_txt_in,
+        cfg.regression_range))
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected
+    return model.cuda().eval(), P

@@ -1,0 +1,415 @@
+"""`LocPointTransformer` meta-architecture behind the reference's surface
+(MQ/libs/modeling/meta_archs.py:351-1822): same constructor kwargs, same state_dict names, same
+`forward(video_list, task_id, ensemble, hidden_state, is_training, prev_out_cls_logits, get_emb, val_qilDatasetList)`
+contract and the attributes the unchanged CL orchestration touches — computed by the sm_100a kernels
+of libvilco_b200.so.  No PyTorch compute fallback exists: without the CUDA library / a GPU the forward raises.
+"""
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import engine as E
+from .. import lib as L
+from .. import ops
+from ..utils.nms import _run as _nms_run
+from .blocks import LayerNorm, MaskedConv1D, Scale
+from .models import make_backbone, make_generator, make_neck, register_meta_arch
+
+
+class BiasLayer(nn.Module):
+    """BiC bias-correction layer (reference: meta_archs.py:26-36)."""
+
+    def __init__(self):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.ones(1, requires_grad=True))
+        self.beta = nn.Parameter(torch.zeros(1, requires_grad=True))
+
+    def forward(self, x):
+        return self.alpha * x + self.beta
+
+    def printParam(self, i):
+        print(i, self.alpha.item(), self.beta.item())
+
+
+class _Head(nn.Module):
+    def __init__(self, input_dim, feat_dim, num_layers, kernel_size, with_ln):
+        super().__init__()
+        assert with_ln and kernel_size == 3 and num_layers == 3, "MQ configs: 3-layer k=3 heads with LayerNorm"
+        self.head, self.norm = nn.ModuleList(), nn.ModuleList()
+        for idx in range(num_layers - 1):
+            self.head.append(MaskedConv1D(input_dim if idx == 0 else feat_dim, feat_dim, kernel_size, stride=1,
+                                          padding=kernel_size // 2, bias=False))
+            self.norm.append(LayerNorm(feat_dim))
+
+
+class PtTransformerClsHead(_Head):
+    """Shared classification head (reference: meta_archs.py:183-275)."""
+
+    def __init__(self, input_dim, feat_dim, num_classes, prior_prob=0.01, num_layers=3, kernel_size=3,
+                 act_layer=nn.ReLU, with_ln=False, empty_cls=(), detach_feat=False):
+        super().__init__(input_dim, feat_dim, num_layers, kernel_size, with_ln)
+        self.num_classes = num_classes
+        self.cls_head = MaskedConv1D(feat_dim, num_classes, kernel_size, stride=1, padding=kernel_size // 2)
+        torch.nn.init.constant_(self.cls_head.conv.bias, -(math.log((1 - prior_prob) / prior_prob)))
+        for idx in empty_cls:
+            torch.nn.init.constant_(self.cls_head.conv.bias[idx], -(math.log((1 - 1e-6) / 1e-6)))
+        self.reg_params = {}
+
+    def augment_classification(self, num_new_classes, device):
+        self.cls_head.augment_classification(num_new_classes, device)
+        self.num_classes += num_new_classes
+
+
+class PtTransformerRegHead(_Head):
+    """Shared regression head (reference: meta_archs.py:278-349)."""
+
+    def __init__(self, input_dim, feat_dim, fpn_levels, num_layers=3, kernel_size=3, act_layer=nn.ReLU, with_ln=False,
+                 num_bins=16):
+        super().__init__(input_dim, feat_dim, num_layers, kernel_size, with_ln)
+        self.fpn_levels = fpn_levels
+        self.scale = nn.ModuleList([Scale() for _ in range(fpn_levels)])
+        self.offset_head = MaskedConv1D(feat_dim, 2 * (num_bins + 1), kernel_size, stride=1, padding=kernel_size // 2)
+        self.reg_params = {}
+
+
+class _Cfg:
+    """The engine's view of the model configuration."""
+    pass
+
+
+@register_meta_arch("LocPointTransformer")
+class PtTransformer(nn.Module):
+    def __init__(self, backbone_type, fpn_type, use_xl, backbone_arch, scale_factor, input_dim, max_seq_len,
+                 max_buffer_len_factor, n_head, n_mha_win_size, embd_kernel_size, embd_dim, embd_with_ln, fpn_dim,
+                 fpn_with_ln, fpn_start_level, head_dim, regression_range, head_num_layers, head_kernel_size,
+                 head_with_ln, use_abs_pe, use_rel_pe, num_classes, train_cfg, test_cfg, cl_cfg, use_cross_modal,
+                 n_txt_in):
+        super().__init__()
+        self.fpn_strides = [scale_factor ** i for i in range(fpn_start_level, backbone_arch[-1] + 1)]
+        self.reg_range = regression_range
+        assert len(self.fpn_strides) == len(self.reg_range)
+        self.scale_factor, self.num_classes, self.max_seq_len, self.use_xl = scale_factor, num_classes, max_seq_len, use_xl
+        n_levels = 1 + backbone_arch[-1]
+        self.mha_win_size = [n_mha_win_size] * n_levels if isinstance(n_mha_win_size, int) else list(n_mha_win_size)
+        max_div_factor = 1
+        for s, w in zip(self.fpn_strides, self.mha_win_size):  # meta_archs.py:402-415
+            stride = s * (w // 2) * 2 if w > 1 else s
+            assert max_seq_len % stride == 0, "max_seq_len must be divisible by fpn stride and window size"
+            max_div_factor = max(max_div_factor, stride)
+        self.max_div_factor = max_div_factor
+
+        tc = train_cfg
+        self.train_center_sample = tc["center_sample"]
+        assert self.train_center_sample in ["radius", "none"]
+        self.train_center_sample_radius = tc["center_sample_radius"]
+        self.train_loss_weight = tc["loss_weight"]
+        self.train_cls_prior_prob = tc["cls_prior_prob"]
+        self.train_dropout, self.train_droppath = tc["dropout"], tc["droppath"]
+        self.train_label_smoothing = tc["label_smoothing"]
+        self.t_c_alpha, self.al_loss_weight = tc["t_c_alpha"], tc["al_loss_weight"]
+        assert not tc.get("use_dcn", False) and not tc.get("use_us_fpn", False)
+        te = test_cfg
+        self.test_pre_nms_thresh, self.test_pre_nms_topk = te["pre_nms_thresh"], te["pre_nms_topk"]
+        self.test_iou_threshold, self.test_min_score = te["iou_threshold"], te["min_score"]
+        self.test_max_seg_num, self.test_nms_method = te["max_seg_num"], te["nms_method"]
+        assert self.test_nms_method in ["soft", "hard", "none"]
+        self.test_duration_thresh, self.test_multiclass_nms = te["duration_thresh"], te["multiclass_nms"]
+        self.test_nms_sigma, self.test_voting_thresh = te["nms_sigma"], te["voting_thresh"]
+        self.use_cross_modal, self.n_txt_in = use_cross_modal, n_txt_in
+
+        assert backbone_type == "convTransformer", "only the convTransformer backbone is on the MQ path"
+        win = n_mha_win_size if isinstance(n_mha_win_size, int) else -1
+        self.backbone = make_backbone("convTransformer", n_in=input_dim, n_embd=embd_dim, n_head=n_head,
+                                      n_embd_ks=embd_kernel_size, max_len=max_seq_len, use_xl=use_xl, arch=backbone_arch,
+                                      t_c_alpha=self.t_c_alpha, scale_factor=scale_factor, with_ln=embd_with_ln,
+                                      attn_pdrop=0.0, proj_pdrop=self.train_dropout, path_pdrop=self.train_droppath,
+                                      use_abs_pe=use_abs_pe, use_rel_pe=use_rel_pe, use_cross_modal=use_cross_modal,
+                                      n_txt_in=n_txt_in, mha_win_size=-1)  # MQ's TransformerBlock ignores the window (blocks.py:497)
+        del win
+        if isinstance(embd_dim, (list, tuple)):
+            embd_dim = sum(embd_dim)
+        self.embd_dim, self.n_head, self.backbone_arch = embd_dim, n_head, tuple(backbone_arch)
+        self.input_dim = input_dim[0] if isinstance(input_dim, (list, tuple)) else input_dim
+        assert fpn_type == "identity", "fpn_type 'fpn' (FPN1D + DenseAPP) is not selected by any MQ config"
+        assert embd_dim == fpn_dim == head_dim
+        self.neck = make_neck("identity", in_channels=[embd_dim] * n_levels, out_channel=fpn_dim,
+                              scale_factor=scale_factor, start_level=fpn_start_level, with_ln=fpn_with_ln)
+        self.point_generator = make_generator("point", max_seq_len=max_seq_len * max_buffer_len_factor,
+                                              fpn_strides=self.fpn_strides, regression_range=self.reg_range)
+        self.cls_head = PtTransformerClsHead(fpn_dim, head_dim, self.num_classes, kernel_size=head_kernel_size,
+                                             prior_prob=self.train_cls_prior_prob, with_ln=head_with_ln,
+                                             num_layers=head_num_layers, empty_cls=tc["head_empty_cls"])
+        self.reg_head = PtTransformerRegHead(fpn_dim, head_dim, len(self.fpn_strides), kernel_size=head_kernel_size,
+                                             num_layers=head_num_layers, with_ln=head_with_ln, num_bins=0)
+        K = self.num_classes
+        self.mu = nn.Parameter(torch.zeros(K, 1))
+        self.sigma = nn.Parameter(torch.ones(K, 1))
+        self.mu_reg_left = nn.Parameter(-torch.ones(K, 1) * 0.5)
+        self.sigma_reg_left = nn.Parameter(torch.ones(K, 1))
+        self.mu_reg_right = nn.Parameter(torch.ones(K, 1) * 0.5)
+        self.sigma_reg_right = nn.Parameter(torch.ones(K, 1))
+        self.loss_normalizer = tc["init_loss_norm"]
+        self.loss_normalizer_momentum = 0.9
+        self.reg_params = {}
+        # continual-learning bookkeeping touched by the unchanged orchestration (train_cl.py / train_bic.py)
+        self.cl_name = cl_cfg["name"]
+        self.compute_means = self.cl_name == "icarl"
+        self.exemplar_means, self.memory = [], {}
+        self.adv_lambda, self.type_sampling = cl_cfg["adv_lambda"], cl_cfg["type_sampling"]
+        self.n_known = 0
+        self.list_bias_layers, self.list_splits = [], []
+        self.prompt_pool = cl_cfg["prompt_pool"]
+        self.narration_ssl = cl_cfg["narration_ssl"]
+        self.use_adapt = cl_cfg["use_adapt"]
+        if self.prompt_pool or self.narration_ssl or self.use_adapt:
+            raise NotImplementedError("the L2P prompt pool / narration SSL / adapter (mq_vilco.yaml) branches are not "
+                                      "built yet; use the mq_no_cl / icarl / bic / ewc / mas configs")
+        self._packed = None
+        self._packed_key = None
+        self._pe = None
+
+    # ---- small surface used by the orchestration -------------------------------------------------
+    @property
+    def device(self):
+        return list(set(p.device for p in self.parameters()))[0]
+
+    def pre_train_epoch(self, task_id=0, current_epoch=0):
+        pass
+
+    def post_train_step(self):
+        pass
+
+    def augment_classification(self, num_new_classes, device):
+        """Grow the classifier and the per-class gaussian parameters (reference: meta_archs.py:715-751)."""
+        device = self.mu.device
+        self.cls_head.augment_classification(num_new_classes, device)
+        old = self.num_classes
+        self.num_classes += num_new_classes
+        for name, init in (("mu", 0.0), ("sigma", 1.0), ("mu_reg_left", -0.5), ("sigma_reg_left", 1.0),
+                           ("mu_reg_right", 0.5), ("sigma_reg_right", 1.0)):
+            new = nn.Parameter(torch.full((self.num_classes, 1), init, device=device))
+            new.data[:old] = getattr(self, name).data
+            setattr(self, name, new)
+        self._packed = None
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def engine_cfg(self):
+        c = _Cfg()
+        c.embd_dim, c.n_head, c.arch, c.scale_factor = self.embd_dim, self.n_head, self.backbone_arch, self.scale_factor
+        c.use_cross_modal, c.use_xl, c.t_c_alpha, c.max_seq_len = self.use_cross_modal, self.use_xl, self.t_c_alpha, self.max_seq_len
+        c.adapt_blocks = ()
+        return c
+
+    def packed_weights(self):
+        """bf16 operand copies of the parameters, re-packed whenever a parameter changed (optimizer step, load_state_dict,
+        augment_classification) or the precision mode changed."""
+        key = (ops.precision(), tuple(p._version for p in self.parameters()), tuple(id(p) for p in self.parameters()))
+        if self._packed is None or key != self._packed_key:
+            self._packed = E.pack_weights(self.state_dict(), self.device)
+            self._packed_key = key
+            self._pe = E.sinusoid_pe_table(self.max_seq_len, self.embd_dim, self.device)
+        return self._packed
+
+    # ---- preprocessing (reference: meta_archs.py:1134-1221) -------------------------------------------
+    def preprocessing(self, video_list, is_training=True, padding_val=0.0):
+        vl = [x for x in video_list if len(x["labels"]) > 0] if is_training else list(video_list)
+        feats = [x["feats"] for x in vl]
+        lens = [f.shape[-1] for f in feats]
+        max_len = max(lens)
+        if is_training:
+            assert max_len <= self.max_seq_len, "Input length must be smaller than max_seq_len during training"
+            max_len = self.max_seq_len
+        elif max_len <= self.max_seq_len:
+            max_len = self.max_seq_len
+        else:
+            stride = self.max_div_factor
+            max_len = (max_len + (stride - 1)) // stride * stride
+        if max_len != self.max_seq_len:
+            raise NotImplementedError("inputs longer than max_seq_len need the interpolated positional encoding "
+                                      "(backbones.py:229-236): not built yet")
+        dev = self.device
+        B, Cin = len(feats), feats[0].shape[0]
+        if all(f.is_cuda for f in feats):
+            batched = torch.full((B, Cin, max_len), padding_val, device=dev, dtype=torch.float32)
+            for i, f in enumerate(feats):
+                batched[i, :, :lens[i]].copy_(f)
+        else:
+            stage = torch.full((B, Cin, max_len), padding_val, dtype=torch.float32).pin_memory()
+            for i, f in enumerate(feats):
+                stage[i, :, :lens[i]].copy_(f)
+            batched = stage.to(dev, non_blocking=True)
+        lens_t = torch.as_tensor(lens)
+        mask = (torch.arange(max_len)[None, :] < lens_t[:, None]).float().to(dev)
+        return vl, batched, mask
+
+    def query_preprocessing(self, video_list, padding_val=0.0):
+        feats = [x["prompt_feature"] for x in video_list]
+        lens = [f.shape[-1] for f in feats]
+        max_len = max(lens)
+        B, Ct = len(feats), feats[0].shape[0]
+        stage = torch.full((B, Ct, max_len), padding_val, dtype=torch.float32)
+        for i, f in enumerate(feats):
+            stage[i, :, :lens[i]].copy_(f)
+        mask = (torch.arange(max_len)[None, :] < torch.as_tensor(lens)[:, None]).float()
+        return stage.to(self.device), mask.to(self.device)
+
+    # ---- network ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _network(self, video_list, is_training):
+        W = self.packed_weights()
+        cfg = self.engine_cfg()
+        vl, batched, mask = self.preprocessing(video_list, is_training)
+        x16 = ops.pack_feats(batched)
+        t16, tmask = None, None
+        if self.use_cross_modal:
+            text, tmask = self.query_preprocessing(vl if is_training else video_list)
+            t16 = ops.pack_feats(text.contiguous())
+        feats, masks = E.backbone_fwd(W, cfg, x16, mask.contiguous(), t16, tmask, self._pe)
+        logits, offsets, pmask, pyr = E.neck_heads_fwd(W, cfg, feats, masks)
+        return vl, logits, offsets, pmask, pyr
+
+    def forward(self, video_list, task_id=-1, ensemble=False, hidden_state=False, is_training=True,
+                prev_out_cls_logits=None, get_emb=False, val_qilDatasetList=None):
+        if not is_training and not get_emb:
+            assert len(video_list) >= 1
+        vl, logits, offsets, pmask, pyr = self._network(video_list, is_training)
+        if self.n_known > 0 and self.cl_name == "bic":  # BiasLayer on class slices (meta_archs.py:823-836)
+            parts, lo_ = [], 0
+            for i, hi_ in enumerate(self.list_splits):
+                parts.append(self.list_bias_layers[i](logits[:, :, lo_:hi_]))
+                lo_ = hi_
+            logits = torch.cat(parts, dim=2).contiguous()
+        if get_emb:
+            cls_l = [logits[:, o:o + n] for o, n in zip(pyr.off, pyr.lens)]
+            off_l = [offsets[:, o:o + n] for o, n in zip(pyr.off, pyr.lens)]
+            msk_l = [pmask[:, o:o + n].bool() for o, n in zip(pyr.off, pyr.lens)]
+            return cls_l, off_l, msk_l
+        if is_training:
+            return self.losses(vl, logits, offsets, pmask, pyr, prev_out_cls_logits)
+        results = self.inference(video_list, pyr, pmask, logits, offsets)
+        if ensemble:
+            points = self.point_generator(pyr.lens)
+            cls_l = [logits[:, o:o + n] for o, n in zip(pyr.off, pyr.lens)]
+            off_l = [offsets[:, o:o + n] for o, n in zip(pyr.off, pyr.lens)]
+            msk_l = [pmask[:, o:o + n].bool() for o, n in zip(pyr.off, pyr.lens)]
+            return video_list, points, msk_l, cls_l, off_l
+        return results
+
+    # ---- targets + losses (reference: meta_archs.py:1224-1344, 1374-1524) --------------------------------
+    def _label_points(self, pyr, gt_segments, gt_labels):
+        """label_points_single_video on the device, for every video, laid out over the pyramid rows."""
+        dev = self.device
+        pts = torch.zeros(pyr.P, 4, device=dev)
+        for l, (o, n) in enumerate(zip(pyr.off, pyr.lens)):
+            pts[o:o + n] = list(self.point_generator.buffer_points)[l][:n].to(dev)
+        K = self.num_classes
+        cls_t, reg_t, wc, wl, wr = [], [], [], [], []
+        t, stride = pts[:, 0, None], pts[:, 3, None].clamp(min=1e-9)
+        for seg, lab in zip(gt_segments, gt_labels):
+            seg, lab = seg.to(dev).float(), lab.to(dev)
+            lens = (seg[:, 1] - seg[:, 0])[None, :].repeat(pyr.P, 1)
+            left, right = t - seg[None, :, 0], seg[None, :, 1] - t
+            xrel = ((right - left) / 2.0) / (stride * lens)
+            g = lambda m, s: (-(xrel - m[lab].permute(1, 0)) ** 2 / (2 * s[lab].permute(1, 0) ** 2)).exp()  # noqa: E731
+            npc, npl, npr = g(self.mu, self.sigma), g(self.mu_reg_left, self.sigma_reg_left), g(self.mu_reg_right, self.sigma_reg_right)
+            reg = torch.stack((left, right), dim=-1)
+            if self.train_center_sample == "radius":
+                center = 0.5 * (seg[None, :, 0] + seg[None, :, 1])
+                t_mins = center - stride * self.train_center_sample_radius
+                t_maxs = center + stride * self.train_center_sample_radius
+                cb_l = t - torch.maximum(t_mins, seg[None, :, 0])
+                cb_r = torch.minimum(t_maxs, seg[None, :, 1]) - t
+                inside = torch.stack((cb_l, cb_r), -1).min(-1)[0] > 0
+            else:
+                inside = reg.min(-1)[0] > 0
+            maxreg = reg.max(-1)[0]
+            in_range = (maxreg >= pts[:, 1, None]) & (maxreg <= pts[:, 2, None])
+            lens = lens.masked_fill(~inside, float("inf")).masked_fill(~in_range, float("inf"))
+            min_len, min_inds = lens.min(dim=1)
+            mm = ((lens <= (min_len[:, None] + 1e-3)) & (lens < float("inf"))).to(reg.dtype)
+            ct = (mm @ F.one_hot(lab, K).to(reg.dtype)).clamp(min=0.0, max=1.0)
+            r = torch.arange(pyr.P, device=dev)
+            cls_t.append(ct)
+            reg_t.append(reg[r, min_inds] / stride)
+            wc.append(npc[r, min_inds]); wl.append(npl[r, min_inds]); wr.append(npr[r, min_inds])
+        return (torch.stack(cls_t).contiguous(), torch.stack(reg_t).contiguous(), torch.stack(wc).contiguous(),
+                torch.stack(wl).contiguous(), torch.stack(wr).contiguous())
+
+    @torch.no_grad()
+    def losses(self, vl, logits, offsets, pmask, pyr, prev_out_cls_logits=None):
+        """Forward values of cls / reg / al / final loss (reference: meta_archs.py:1374-1524) from the fused loss kernel.
+        The backward pass of the CUDA path is not built yet, so the returned tensors carry no autograd graph."""
+        dev = self.device
+        B, P, K = logits.shape
+        gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
+        if self.train_label_smoothing > 0:
+            gt_cls = gt_cls * (1 - self.train_label_smoothing) + self.train_label_smoothing / (K + 1)
+        present = torch.zeros(B, K, device=dev)
+        for i, x in enumerate(vl):
+            present[i, x["labels"].to(dev)] = 1
+        sums = torch.zeros(4, device=dev)
+        scratch = torch.zeros(B * K, device=dev, dtype=torch.int32)
+        L.check(L.lib().vilco_mq_losses(
+            ops._p(logits), ops._p(offsets), ops._p(pmask), ops._p(pyr.gap_rows), ops._p(gt_cls), ops._p(gt_off),
+            ops._p(wc), ops._p(wl), ops._p(wr), ops._p(present), B, P, K, C.c_float(0.25), C.c_float(2.0), ops._p(sums),
+            ops._p(scratch), L.stream_ptr()), "vilco_mq_losses")
+        s = sums.cpu()
+        num_pos = float(s[2])
+        self.loss_normalizer = self.loss_normalizer_momentum * self.loss_normalizer + \
+            (1 - self.loss_normalizer_momentum) * max(num_pos, 1)
+        cls_loss = sums[0] / self.loss_normalizer
+        reg_loss = sums[1] / self.loss_normalizer
+        al_loss = sums[3] / self.loss_normalizer if K != 1 else torch.zeros((), device=dev)
+        loss_weight = self.train_loss_weight if self.train_loss_weight > 0 else float(cls_loss) / max(float(reg_loss), 0.01)
+        final = cls_loss + reg_loss * loss_weight + al_loss * self.al_loss_weight
+        if self.n_known > 0 and self.cl_name in ("bic", "icarl"):
+            raise NotImplementedError("BiC / iCaRL distillation terms of the training loss are not built yet")
+        return {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final}
+
+    # ---- inference (reference: meta_archs.py:1527-1736) ---------------------------------------------
+    @torch.no_grad()
+    def inference(self, video_list, points_or_pyr, fpn_masks, out_cls_logits, out_offsets, out_lb_logits=None,
+                  out_rb_logits=None, cilsettask=None):
+        """decode (sigmoid / threshold / top-k / segments) + soft-NMS on the GPU, then the conversion to seconds on the
+        host exactly like the reference (meta_archs.py:1723-1727).  Accepts the concatenated-pyramid tensors produced by
+        forward(); returns one dict per video with CPU tensors."""
+        pyr = points_or_pyr
+        assert isinstance(pyr, E.Pyramid), "inference() expects the pyramid layout returned by forward()"
+        assert cilsettask is None or not self.compute_means, "iCaRL nearest-mean re-scoring is not built yet"
+        logits, offsets, pmask = out_cls_logits, out_offsets, fpn_masks
+        B, P, K = logits.shape
+        dev = logits.device
+        nl, topk = len(pyr.lens), int(self.test_pre_nms_topk)
+        cand_segs = torch.empty(B, nl * topk, 2, device=dev)
+        cand_scores = torch.empty(B, nl * topk, device=dev)
+        cand_labels = torch.empty(B, nl * topk, device=dev, dtype=torch.int32)
+        cand_count = torch.zeros(B, nl, device=dev, dtype=torch.int32)
+        IntArr, FltArr = C.c_int * nl, C.c_float * nl
+        L.check(L.lib().vilco_decode(
+            ops._p(logits), ops._p(offsets), ops._p(pmask), B, P, K, nl, IntArr(*pyr.off), IntArr(*pyr.lens),
+            FltArr(*[float(s) for s in self.fpn_strides]), C.c_float(self.test_pre_nms_thresh),
+            C.c_float(self.test_duration_thresh), topk, ops._p(cand_segs), ops._p(cand_scores), ops._p(cand_labels),
+            ops._p(cand_count), L.stream_ptr()), "vilco_decode")
+        if self.test_nms_method != "none":
+            if not self.test_multiclass_nms and self.test_voting_thresh > 0:
+                raise NotImplementedError("class-agnostic NMS with segment voting is not built yet")
+            method = 2 if self.test_nms_method == "soft" else 3
+            segs, scores, labels, count = _nms_run(cand_segs, cand_scores, cand_labels, cand_count, B, nl, topk, K,
+                                                   self.test_multiclass_nms, method, self.test_iou_threshold,
+                                                   self.test_nms_sigma, self.test_min_score, self.test_max_seg_num)
+            segs, scores, labels, count = segs.cpu(), scores.cpu(), labels.cpu(), count.cpu()
+        else:
+            raise NotImplementedError("nms_method 'none' is not built yet")
+        results = []
+        for i, v in enumerate(video_list):
+            k = int(count[i])
+            s, sc, lb = segs[i, :k].clone(), scores[i, :k].clone(), labels[i, :k].clone()
+            if k > 0:  # feature grid -> seconds, clamp to [0, duration]  (meta_archs.py:1723-1727)
+                s = (s * v["feat_stride"] + 0.5 * v["feat_num_frames"]) / v["fps"]
+                s[s <= 0.0] *= 0.0
+                s[s >= v["duration"]] = s[s >= v["duration"]] * 0.0 + v["duration"]
+            results.append({"video_id": v["video_id"], "segments": s, "scores": sc, "labels": lb})
+        return results
