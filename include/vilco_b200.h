@@ -100,8 +100,10 @@ int vilco_layernorm(const void* x, int x_dtype, const float* add, const float* w
 /* depthwise conv (k=3, stride 1|2, zero pad 1, no bias) * out_mask -> LayerNorm, for up to three (weight, norm)
  * sets sharing one input: the q/k/v front of MaskedMHCA / LocalMaskedMHCA (blocks.py:315-345, 364-371; the mask is
  * nearest-downsampled, blocks.py:117-127).  x (B,T,C) fp32|bf16, mask (B,T) float 1/0, wconv[i] (3,C) tap-major,
- * out[i] (B,T/stride,C) bf16. */
-int vilco_dwconv_ln(const void* x, int x_dtype, const float* mask, const float* const* wconv, const float* const* lnw,
+ * out[i] (B,T/stride,C) bf16.  tlen (B,) int or NULL: rows t >= tlen[b] are treated as lying outside the sequence (zero
+ * padding), which makes a batch of differently padded sequences equal to running each one alone. */
+int vilco_dwconv_ln(const void* x, int x_dtype, const float* mask, const int* tlen, const float* const* wconv,
+                    const float* const* lnw,
                     const float* const* lnb, void* const* out, int64_t out_lo, int n_out, int B, int T, int C, int stride,
                     float eps, void* stream);
 
@@ -130,9 +132,10 @@ int vilco_softmax_rows(const float* S, const float* BD, const float* kmask, void
 int vilco_local_attention(const void* q, const void* k, const void* v, const float* mask, const float* rel_pe, void* out,
                           int64_t lo, int B, int T, int C, int H, int W, void* stream);
 
-/* ChannelAttention core (blocks.py:423-436): qkv (B,T,3C) bf16 -> y (B,T,C) bf16;  G is a (B,H,64,64) fp32 scratch. */
-int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G, void* y, int64_t y_lo, int B, int T, int C, int H,
-                            void* stream);
+/* ChannelAttention core (blocks.py:423-436): qkv (B,T,3C) bf16 -> y (B,T,C) bf16;  G is a (B,H,64,64) fp32 scratch.
+ * tlen (B,) or NULL limits the tokens summed in k^T v (the reference sums over every position of its padded batch). */
+int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G, void* y, int64_t y_lo, const int* tlen, int B, int T,
+                            int C, int H, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Decode of the head outputs into candidate segments — PtTransformer.inference_single_video,

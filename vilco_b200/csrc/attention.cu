@@ -198,12 +198,15 @@ static constexpr int CA_D = 64;
 static constexpr int CA_TCHUNK = 64;
 
 __global__ void __launch_bounds__(256) chan_attn_kv_kernel(const __nv_bfloat16* __restrict__ qkv, long long lo,
-                                                           float* __restrict__ G, int T, int C, int H, float scale) {
+                                                           float* __restrict__ G, const int* __restrict__ tlen, int T,
+                                                           int C, int H, float scale) {
   __shared__ float sk[CA_TCHUNK][CA_D + 1];
   __shared__ float sv[CA_TCHUNK][CA_D + 1];
   const int h = blockIdx.y, b = blockIdx.z;
   const int t0 = blockIdx.x * CA_TCHUNK;
-  const int nt = min(CA_TCHUNK, T - t0);
+  const int Tb = tlen ? min(T, tlen[b]) : T;  // tokens that take part in the k^T v sum
+  const int nt = min(CA_TCHUNK, Tb - t0);
+  if (nt <= 0) return;
   const long long ld = 3LL * C;
   const __nv_bfloat16* kb = qkv + ((long long)b * T + t0) * ld + C + h * CA_D;
   const __nv_bfloat16* vb = kb + C;
@@ -327,14 +330,14 @@ extern "C" int vilco_local_attention(const void* q, const void* k, const void* v
   return VILCO_OK;
 }
 
-extern "C" int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G, void* y, int64_t y_lo, int B, int T, int C,
-                                       int H, void* stream) {
+extern "C" int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G, void* y, int64_t y_lo, const int* tlen,
+                                       int B, int T, int C, int H, void* stream) {
   VILCO_CHECK_ARG(qkv && G && y, "vilco_channel_attention: null pointer");
   VILCO_CHECK_ARG(H > 0 && C == H * CA_D, "vilco_channel_attention: head dim must be 64 (C=%d H=%d)", C, H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VILCO_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)B * H * CA_D * CA_D, st));
   dim3 grid((T + CA_TCHUNK - 1) / CA_TCHUNK, H, B);
-  chan_attn_kv_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, T, C, H, 1.0f / sqrtf((float)CA_D));
+  chan_attn_kv_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, tlen, T, C, H, 1.0f / sqrtf((float)CA_D));
   VILCO_LAUNCH_CHECK();
   chan_attn_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, static_cast<__nv_bfloat16*>(y), y_lo, T, C, H);
   VILCO_LAUNCH_CHECK();

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
 struct DwParams {
   const void* x; int x_bf16;          // (B, T, C)
   const float* mask;                  // (B, T) 1/0, input resolution
+  const int* tlen;                    // optional (B,): rows t >= tlen[b] are treated as outside the sequence (zero)
   const float* wconv[3];              // (3 taps, C) each: tap-major
   const float* lnw[3]; const float* lnb[3];
   __nv_bfloat16* out[3];              // (B, T/s, C)
@@ -128,20 +129,24 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const DwParams p) {
   const TIn* xb = static_cast<const TIn*>(p.x) + (long long)bi * p.T * p.C;
   const float m = p.mask[(long long)bi * p.T + tc];
   const float* wc = p.wconv[which];
+  const int Tb = p.tlen ? min(p.T, p.tlen[bi]) : p.T;  // effective sequence end for the zero padding
   float4 v[MAXCH];
 #pragma unroll
   for (int i = 0; i < MAXCH; ++i)
     if (i < nch) {
       const int c = (i * 32 + lane) * 4;
       const float4 w1 = ld4(wc + p.C + c);
-      const float4 x1 = ld4(xb + (long long)tc * p.C + c);
-      float4 a = make_float4(w1.x * x1.x, w1.y * x1.y, w1.z * x1.z, w1.w * x1.w);
-      if (tc > 0) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tc < Tb) {
+        const float4 x1 = ld4(xb + (long long)tc * p.C + c);
+        a = make_float4(w1.x * x1.x, w1.y * x1.y, w1.z * x1.z, w1.w * x1.w);
+      }
+      if (tc > 0 && tc - 1 < Tb) {
         const float4 w0 = ld4(wc + c);
         const float4 x0 = ld4(xb + (long long)(tc - 1) * p.C + c);
         a.x = fmaf(w0.x, x0.x, a.x); a.y = fmaf(w0.y, x0.y, a.y); a.z = fmaf(w0.z, x0.z, a.z); a.w = fmaf(w0.w, x0.w, a.w);
       }
-      if (tc + 1 < p.T) {
+      if (tc + 1 < Tb) {
         const float4 w2 = ld4(wc + 2 * p.C + c);
         const float4 x2 = ld4(xb + (long long)(tc + 1) * p.C + c);
         a.x = fmaf(w2.x, x2.x, a.x); a.y = fmaf(w2.y, x2.y, a.y); a.z = fmaf(w2.z, x2.z, a.z); a.w = fmaf(w2.w, x2.w, a.w);
@@ -275,7 +280,7 @@ extern "C" int vilco_layernorm(const void* x, int x_dtype, const float* add, con
   return VILCO_OK;
 }
 
-extern "C" int vilco_dwconv_ln(const void* x, int x_dtype, const float* mask, const float* const* wconv,
+extern "C" int vilco_dwconv_ln(const void* x, int x_dtype, const float* mask, const int* tlen, const float* const* wconv,
                                const float* const* lnw, const float* const* lnb, void* const* out, int64_t out_lo,
                                int n_out, int B, int T, int C, int stride, float eps, void* stream) {
   VILCO_CHECK_ARG(x && mask && wconv && lnw && lnb && out, "vilco_dwconv_ln: null pointer");
@@ -283,7 +288,7 @@ extern "C" int vilco_dwconv_ln(const void* x, int x_dtype, const float* mask, co
   VILCO_CHECK_ARG(C % 128 == 0 && C <= 128 * MAXCH, "vilco_dwconv_ln: C=%d unsupported", C);
   VILCO_CHECK_ARG((stride == 1 || stride == 2) && T % stride == 0, "vilco_dwconv_ln: stride %d / T %d", stride, T);
   DwParams p{};
-  p.x = x; p.x_bf16 = x_dtype == VILCO_BF16; p.mask = mask;
+  p.x = x; p.x_bf16 = x_dtype == VILCO_BF16; p.mask = mask; p.tlen = tlen;
   for (int i = 0; i < n_out; ++i) {
     p.wconv[i] = wconv[i]; p.lnw[i] = lnw[i]; p.lnb[i] = lnb[i]; p.out[i] = static_cast<__nv_bfloat16*>(out[i]);
   }

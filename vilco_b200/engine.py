@@ -74,14 +74,14 @@ def xlnet_pos_emb(T, C, device):
 # ----------------------------------------------------------------------------------------------------
 # blocks
 # ----------------------------------------------------------------------------------------------------
-def mhca_fwd(W, pre, xin, mask, H, stride, window=-1):
+def mhca_fwd(W, pre, xin, mask, H, stride, window=-1, tlen=None):
     """MaskedMHCA.forward up to (not including) the output projection — blocks.py:351-402; LocalMaskedMHCA when
     window > 1 — blocks.py:1140-1200.  xin = ln1(x) (B,T,C) fp32.  Returns (attn_out bf16 (B,T/s,C), out_mask)."""
     B, T, C = xin.shape
     names = ("query", "key", "value")
     qc, kc, vc = ops.dwconv_ln(xin, mask, [W[pre + f"{n}_conv.conv.weight"] for n in names],
                                [W[pre + f"{n}_norm.weight"] for n in names],
-                               [W[pre + f"{n}_norm.bias"] for n in names], stride)
+                               [W[pre + f"{n}_norm.bias"] for n in names], stride, tlen=tlen)
     omask = mask[:, ::stride].contiguous() if stride > 1 else mask
     q = ops.linear(qc, W[pre + "query.weight"], bf16, bias=W[pre + "query.bias"])
     k = ops.linear(kc, W[pre + "key.weight"], bf16, bias=W[pre + "key.bias"])
@@ -108,10 +108,10 @@ def cross_attn_fwd(W, pre, x16, y16, ymask, H):
     return ops.attn_pv(P, v, H, k.shape[2])
 
 
-def channel_block_fwd(W, pre, ln1_32, ln1_16, H):
+def channel_block_fwd(W, pre, ln1_32, ln1_16, H, tlen=None):
     """ChannelBlock.forward — blocks.py:423-466 on x = ln1(x) (no masking, norm1 unused).  Returns fp32 (B,T,C)."""
     qkv = ops.linear(ln1_16, W[pre + "attn.qkv.weight"], bf16)
-    y = ops.channel_attention(qkv, H)
+    y = ops.channel_attention(qkv, H, tlen)
     x1 = ops.linear(y, W[pre + "attn.proj.weight"], f32, bias=W[pre + "attn.proj.bias"], resid=ln1_32)
     _, n2 = ops.layernorm(x1, W[pre + "norm2.weight"], W[pre + "norm2.bias"], 1e-5)
     h = ops.linear(n2, W[pre + "mlp.0.weight"], bf16, bias=W[pre + "mlp.0.bias"], act=ACT_GELU)
@@ -130,12 +130,12 @@ def adapter_fwd(W, pre, ln1_32):
 
 
 def transformer_block_fwd(W, pre, x32, mask, H, stride, cross=None, t_c_alpha=0.8, window=-1, adapter_pre=None,
-                          want16=False):
+                          want16=False, tlen=None):
     """TransformerBlock.forward — blocks.py:561-593 (eval semantics).  x32 (B,T,C) fp32 residual stream.
     cross = (text32 (B,L,C), text_mask (B,L)) or None.  Returns (out32, out_mask[, out16])."""
     B, T, C = x32.shape
     ln1_32, ln1_16 = ops.layernorm(x32, W[pre + "ln1.weight"], W[pre + "ln1.bias"], out32=True, out16=(stride == 1))
-    o, omask = mhca_fwd(W, pre + "attn.", ln1_32, mask, H, stride, window)
+    o, omask = mhca_fwd(W, pre + "attn.", ln1_32, mask, H, stride, window, tlen)
     om = omask.reshape(-1)
     skip = x32 if stride == 1 else ops.maxpool3s2(x32)
     sa, sm = W.get(pre + "drop_path_attn.scale"), W.get(pre + "drop_path_mlp.scale")
@@ -161,7 +161,7 @@ def transformer_block_fwd(W, pre, x32, mask, H, stride, cross=None, t_c_alpha=0.
     out = ops.linear(m, W[pre + "mlp.3.weight"], f32, bias=W[pre + "mlp.3.bias"], rowmul=om, colscale=sm, resid=h)
     out16 = None
     if stride == 1:
-        out2 = channel_block_fwd(W, pre + "channel_attn.", ln1_32, ln1_16, H)
+        out2 = channel_block_fwd(W, pre + "channel_attn.", ln1_32, ln1_16, H, tlen)
         out, out16 = ops.axpby(out, out2, t_c_alpha, 1.0 - t_c_alpha, out32=True, out16=want16)
     elif want16:
         _, out16 = ops.axpby(out, None, 1.0, 0.0, out32=False, out16=True)
@@ -203,9 +203,11 @@ def xlnet_layer_fwd(W, pre, x32, x16, mask, H, eps=1e-12):
     return h2
 
 
-def backbone_fwd(W, cfg, x16, mask, text16=None, tmask=None, pe=None, pets_prefix="pets."):
+def backbone_fwd(W, cfg, x16, mask, text16=None, tmask=None, pe=None, pets_prefix="pets.", text_lens=None):
     """ConvTransformerBackbone.forward — MQ/libs/modeling/backbones.py:181-289.
-    x16 (B,T,Cin) bf16, mask (B,T) fp32, text16 (B,L,Ct) bf16, tmask (B,L) fp32.  Returns (feats fp32 list, masks)."""
+    x16 (B,T,Cin) bf16, mask (B,T) fp32, text16 (B,L,Ct) bf16, tmask (B,L) fp32.  Returns (feats fp32 list, masks).
+    text_lens (B,) int32 or None: when given, every text sequence is treated as if it had been run alone (un-padded),
+    which is what the reference's batch-1 evaluation does; None reproduces the reference's padded training batch."""
     pre = "backbone."
     _, B, T, _ = x16.shape
     C, H = cfg.embd_dim, cfg.n_head
@@ -230,7 +232,7 @@ def backbone_fwd(W, cfg, x16, mask, text16=None, tmask=None, pe=None, pets_prefi
             t32, t = ops.layernorm(c, W[pre + f"txt_embd_norm.{i}.weight"], W[pre + f"txt_embd_norm.{i}.bias"],
                                    relu=True, out32=last, out16=not last)
         for i in range(cfg.arch[1]):
-            t32, _ = transformer_block_fwd(W, pre + f"txt_stem.{i}.", t32, tmask, H, 1, t_c_alpha=0.8)
+            t32, _ = transformer_block_fwd(W, pre + f"txt_stem.{i}.", t32, tmask, H, 1, t_c_alpha=0.8, tlen=text_lens)
         cross = (t32, tmask)
     x16s = None
     for i in range(cfg.arch[1]):

@@ -236,6 +236,11 @@ class PtTransformer(nn.Module):
             batched = torch.full((B, Cin, max_len), padding_val, device=dev, dtype=torch.float32)
             for i, f in enumerate(feats):
                 batched[i, :, :lens[i]].copy_(f)
+        elif all(f.is_pinned() for f in feats):   # pinned host buffers: straight async H2D into the padded batch
+            batched = torch.full((B, Cin, max_len), padding_val, device=dev, dtype=torch.float32) \
+                if min(lens) < max_len else torch.empty((B, Cin, max_len), device=dev, dtype=torch.float32)
+            for i, f in enumerate(feats):
+                batched[i, :, :lens[i]].copy_(f, non_blocking=True)
         else:
             stage = torch.full((B, Cin, max_len), padding_val, dtype=torch.float32).pin_memory()
             for i, f in enumerate(feats):
@@ -254,22 +259,37 @@ class PtTransformer(nn.Module):
         for i, f in enumerate(feats):
             stage[i, :, :lens[i]].copy_(f)
         mask = (torch.arange(max_len)[None, :] < torch.as_tensor(lens)[:, None]).float()
-        return stage.to(self.device), mask.to(self.device)
+        return stage.to(self.device), mask.to(self.device), torch.as_tensor(lens, dtype=torch.int32).to(self.device)
 
     # ---- network ---------------------------------------------------------------------------------
     @torch.no_grad()
-    def _network(self, video_list, is_training):
+    def _device_forward(self, batched, mask, text, tmask, tlens, is_training):
+        """Everything that runs on the device between the padded input batch and the head outputs."""
         W = self.packed_weights()
         cfg = self.engine_cfg()
-        vl, batched, mask = self.preprocessing(video_list, is_training)
         x16 = ops.pack_feats(batched)
-        t16, tmask = None, None
+        t16 = ops.pack_feats(text) if text is not None else None
+        # evaluation: the reference runs one clip at a time, so its text is never padded; a batched evaluation must
+        # therefore treat every text as un-padded (text_lens).  Training reproduces the reference's padded batch.
+        feats, masks = E.backbone_fwd(W, cfg, x16, mask, t16, tmask, self._pe, text_lens=None if is_training else tlens)
+        return E.neck_heads_fwd(W, cfg, feats, masks)
+
+    @torch.no_grad()
+    def _network(self, video_list, is_training):
+        vl, batched, mask = self.preprocessing(video_list, is_training)
+        text, tmask, tlens = None, None, None
         if self.use_cross_modal:
-            text, tmask = self.query_preprocessing(vl if is_training else video_list)
-            t16 = ops.pack_feats(text.contiguous())
-        feats, masks = E.backbone_fwd(W, cfg, x16, mask.contiguous(), t16, tmask, self._pe)
-        logits, offsets, pmask, pyr = E.neck_heads_fwd(W, cfg, feats, masks)
+            text, tmask, tlens = self.query_preprocessing(vl if is_training else video_list)
+            text = text.contiguous()
+        logits, offsets, pmask, pyr = self._device_forward(batched, mask.contiguous(), text, tmask, tlens, is_training)
         return vl, logits, offsets, pmask, pyr
+
+    # ---- CUDA-graph replay of the whole evaluation step (static shapes: every clip is padded to max_seq_len) --------
+    @torch.no_grad()
+    def make_eval_graph(self, batch_size, text_len=128):
+        """Capture pack -> backbone -> neck -> heads -> decode -> soft-NMS for `batch_size` clips into one CUDA graph.
+        Returns an EvalGraph; .run(video_list) stages inputs, replays, and post-processes like forward()."""
+        return EvalGraph(self, batch_size, text_len)
 
     def forward(self, video_list, task_id=-1, ensemble=False, hidden_state=False, is_training=True,
                 prev_out_cls_logits=None, get_emb=False, val_qilDatasetList=None):
@@ -371,15 +391,8 @@ class PtTransformer(nn.Module):
 
     # ---- inference (reference: meta_archs.py:1527-1736) ---------------------------------------------
     @torch.no_grad()
-    def inference(self, video_list, points_or_pyr, fpn_masks, out_cls_logits, out_offsets, out_lb_logits=None,
-                  out_rb_logits=None, cilsettask=None):
-        """decode (sigmoid / threshold / top-k / segments) + soft-NMS on the GPU, then the conversion to seconds on the
-        host exactly like the reference (meta_archs.py:1723-1727).  Accepts the concatenated-pyramid tensors produced by
-        forward(); returns one dict per video with CPU tensors."""
-        pyr = points_or_pyr
-        assert isinstance(pyr, E.Pyramid), "inference() expects the pyramid layout returned by forward()"
-        assert cilsettask is None or not self.compute_means, "iCaRL nearest-mean re-scoring is not built yet"
-        logits, offsets, pmask = out_cls_logits, out_offsets, fpn_masks
+    def _decode_nms_device(self, pyr, pmask, logits, offsets):
+        """decode + NMS kernels; returns device tensors (segs (B,M,2), scores (B,M), labels (B,M) i64, count (B,) i32)."""
         B, P, K = logits.shape
         dev = logits.device
         nl, topk = len(pyr.lens), int(self.test_pre_nms_topk)
@@ -393,23 +406,110 @@ class PtTransformer(nn.Module):
             FltArr(*[float(s) for s in self.fpn_strides]), C.c_float(self.test_pre_nms_thresh),
             C.c_float(self.test_duration_thresh), topk, ops._p(cand_segs), ops._p(cand_scores), ops._p(cand_labels),
             ops._p(cand_count), L.stream_ptr()), "vilco_decode")
-        if self.test_nms_method != "none":
-            if not self.test_multiclass_nms and self.test_voting_thresh > 0:
-                raise NotImplementedError("class-agnostic NMS with segment voting is not built yet")
-            method = 2 if self.test_nms_method == "soft" else 3
-            segs, scores, labels, count = _nms_run(cand_segs, cand_scores, cand_labels, cand_count, B, nl, topk, K,
-                                                   self.test_multiclass_nms, method, self.test_iou_threshold,
-                                                   self.test_nms_sigma, self.test_min_score, self.test_max_seg_num)
-            segs, scores, labels, count = segs.cpu(), scores.cpu(), labels.cpu(), count.cpu()
-        else:
+        if self.test_nms_method == "none":
             raise NotImplementedError("nms_method 'none' is not built yet")
+        if not self.test_multiclass_nms and self.test_voting_thresh > 0:
+            raise NotImplementedError("class-agnostic NMS with segment voting is not built yet")
+        method = 2 if self.test_nms_method == "soft" else 3
+        return _nms_run(cand_segs, cand_scores, cand_labels, cand_count, B, nl, topk, K, self.test_multiclass_nms, method,
+                        self.test_iou_threshold, self.test_nms_sigma, self.test_min_score, self.test_max_seg_num)
+
+    @staticmethod
+    def _to_results(video_list, segs, scores, labels, count):
+        """device->host results to the reference's output dicts; feature grid -> seconds, clamp to [0, duration]
+        (meta_archs.py:1723-1734)."""
         results = []
         for i, v in enumerate(video_list):
             k = int(count[i])
             s, sc, lb = segs[i, :k].clone(), scores[i, :k].clone(), labels[i, :k].clone()
-            if k > 0:  # feature grid -> seconds, clamp to [0, duration]  (meta_archs.py:1723-1727)
+            if k > 0:
                 s = (s * v["feat_stride"] + 0.5 * v["feat_num_frames"]) / v["fps"]
                 s[s <= 0.0] *= 0.0
                 s[s >= v["duration"]] = s[s >= v["duration"]] * 0.0 + v["duration"]
             results.append({"video_id": v["video_id"], "segments": s, "scores": sc, "labels": lb})
         return results
+
+    @torch.no_grad()
+    def inference(self, video_list, points_or_pyr, fpn_masks, out_cls_logits, out_offsets, out_lb_logits=None,
+                  out_rb_logits=None, cilsettask=None):
+        """decode (sigmoid / threshold / top-k / segments) + soft-NMS on the GPU, then the conversion to seconds on the
+        host exactly like the reference (meta_archs.py:1723-1727).  Accepts the concatenated-pyramid tensors produced by
+        forward(); returns one dict per video with CPU tensors."""
+        pyr = points_or_pyr
+        assert isinstance(pyr, E.Pyramid), "inference() expects the pyramid layout returned by forward()"
+        assert cilsettask is None or not self.compute_means, "iCaRL nearest-mean re-scoring is not built yet"
+        segs, scores, labels, count = self._decode_nms_device(pyr, fpn_masks, out_cls_logits, out_offsets)
+        return self._to_results(video_list, segs.cpu(), scores.cpu(), labels.cpu(), count.cpu())
+
+
+class EvalGraph:
+    """One captured CUDA graph of the evaluation step for a fixed batch size (every clip padded to max_seq_len, every
+    text padded to `text_len` with per-clip lengths, so shapes are static).  Inputs are written into static device
+    buffers; outputs are read from static device buffers."""
+
+    def __init__(self, model, batch_size, text_len=128):
+        self.model, self.B, self.Lt = model, batch_size, text_len
+        dev = model.device
+        T, Cin, Ct = model.max_seq_len, model.input_dim, model.n_txt_in
+        self.feats = torch.zeros(batch_size, Cin, T, device=dev)
+        self.mask = torch.ones(batch_size, T, device=dev)
+        self.text = torch.zeros(batch_size, Ct, text_len, device=dev) if model.use_cross_modal else None
+        self.tmask = torch.ones(batch_size, text_len, device=dev) if model.use_cross_modal else None
+        self.tlens = torch.full((batch_size,), text_len, device=dev, dtype=torch.int32) if model.use_cross_modal else None
+        self.launches = 0
+        model.packed_weights()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # warm-up outside capture (lazy cudaFuncSetAttribute, allocator pools)
+            self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = self._step()
+        self.launches = L.launch_count() - n0
+        self._stage_f = torch.zeros(batch_size, Cin, T).pin_memory()
+        self._stage_t = torch.zeros(batch_size, Ct, text_len).pin_memory() if model.use_cross_modal else None
+
+    def _step(self):
+        m = self.model
+        logits, offsets, pmask, pyr = m._device_forward(self.feats, self.mask, self.text, self.tmask, self.tlens, False)
+        return m._decode_nms_device(pyr, pmask, logits, offsets)
+
+    def load_inputs(self, video_list):
+        """host -> static device buffers (async on the current stream)."""
+        m = self.model
+        assert len(video_list) == self.B
+        T = m.max_seq_len
+        lens = [v["feats"].shape[-1] for v in video_list]
+        assert max(lens) <= T
+        for i, v in enumerate(video_list):
+            f = v["feats"]
+            if f.is_pinned() or f.is_cuda:
+                if lens[i] < T:
+                    self.feats[i, :, lens[i]:].zero_()
+                self.feats[i, :, :lens[i]].copy_(f, non_blocking=True)
+            else:
+                self._stage_f[i].zero_()
+                self._stage_f[i, :, :lens[i]].copy_(f)
+                self.feats[i].copy_(self._stage_f[i], non_blocking=True)
+        self.mask.copy_((torch.arange(T)[None, :] < torch.as_tensor(lens)[:, None]).float(), non_blocking=True)
+        if m.use_cross_modal:
+            tl = [v["prompt_feature"].shape[-1] for v in video_list]
+            assert max(tl) <= self.Lt
+            self._stage_t.zero_()
+            for i, v in enumerate(video_list):
+                self._stage_t[i, :, :tl[i]].copy_(v["prompt_feature"])
+            self.text.copy_(self._stage_t, non_blocking=True)
+            self.tmask.copy_((torch.arange(self.Lt)[None, :] < torch.as_tensor(tl)[:, None]).float(), non_blocking=True)
+            self.tlens.copy_(torch.as_tensor(tl, dtype=torch.int32), non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+
+    def run(self, video_list):
+        self.load_inputs(video_list)
+        self.graph.replay()
+        segs, scores, labels, count = self.out
+        return PtTransformer._to_results(video_list, segs.cpu(), scores.cpu(), labels.cpu(), count.cpu())

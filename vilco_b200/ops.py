@@ -139,7 +139,7 @@ def layernorm(x, w, b, eps=1e-5, add=None, relu=False, pe=None, rowmul=None, zer
     return y32, y16
 
 
-def dwconv_ln(x, mask, wconvs, lnws, lnbs, stride, eps=1e-5):
+def dwconv_ln(x, mask, wconvs, lnws, lnbs, stride, eps=1e-5, tlen=None):
     """x (B,T,C) fp32, mask (B,T) fp32 -> list of operands (NP,B,T/stride,C), one per (wconv, ln) set."""
     assert x.dtype == f32 and x.is_contiguous()
     B, T, Cc = x.shape
@@ -147,7 +147,7 @@ def dwconv_ln(x, mask, wconvs, lnws, lnbs, stride, eps=1e-5):
     outs = [empty16(B, T // stride, Cc, device=x.device) for _ in range(n)]
     arr = C.c_void_p * n
     L.check(L.lib().vilco_dwconv_ln(
-        _p(x), L.F32, _p(mask), arr(*[w.data_ptr() for w in wconvs]),
+        _p(x), L.F32, _p(mask), _p(tlen), arr(*[w.data_ptr() for w in wconvs]),
         arr(*[w.data_ptr() for w in lnws]), arr(*[w.data_ptr() for w in lnbs]), arr(*[o.data_ptr() for o in outs]),
         _i64(lo(outs[0])), n, B, T, Cc, stride, C.c_float(eps), L.stream_ptr()), "vilco_dwconv_ln")
     return outs
@@ -205,11 +205,11 @@ def local_attention(q, k, v, mask, H, W, rel_pe=None):
     return out
 
 
-def channel_attention(qkv, H):
+def channel_attention(qkv, H, tlen=None):
     _, B, T, C3 = qkv.shape
     Cc = C3 // 3
     G = torch.empty(B, H, 64, 64, device=qkv.device, dtype=f32)
     y = empty16(B, T, Cc, device=qkv.device)
-    L.check(L.lib().vilco_channel_attention(_p(qkv), _i64(lo(qkv)), _p(G), _p(y), _i64(lo(y)), B, T, Cc, H,
+    L.check(L.lib().vilco_channel_attention(_p(qkv), _i64(lo(qkv)), _p(G), _p(y), _i64(lo(y)), _p(tlen), B, T, Cc, H,
                                             L.stream_ptr()), "vilco_channel_attention")
     return y
