@@ -1,0 +1,34 @@
+"""Single GEMM shape for ncu captures: python tools/one_gemm.py {qk|mlp1|lin32|conv3} [precision]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vilco_b200 import ops  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "qk"
+ops.set_precision(sys.argv[2] if len(sys.argv) > 2 else "bf16x3")
+dev = "cuda"
+B, T, C, H = 8, 1024, 1024, 16
+x = ops.split16(torch.randn(B, T, C, device=dev))
+if which == "qk":
+    k = ops.split16(torch.randn(B, T, C, device=dev))
+    fn = lambda: ops.attn_scores(x, k, H, 0.125)
+elif which == "mlp1":
+    w4 = ops.split16(torch.randn(4 * C, C, device=dev) * 0.03)
+    b4 = torch.randn(4 * C, device=dev)
+    fn = lambda: ops.linear(x, w4, ops.bf16, bias=b4, act=ops.ACT_GELU)
+elif which == "lin32":
+    w = ops.split16(torch.randn(C, C, device=dev) * 0.03)
+    resid = torch.randn(B, T, C, device=dev)
+    rm = torch.ones(B * T, device=dev)
+    fn = lambda: ops.linear(x, w, ops.f32, rowmul=rm, resid=resid, resid_masked=True)
+else:
+    w3 = ops.split16(torch.randn(3, C, C, device=dev) * 0.03)
+    rm = torch.ones(B, T, device=dev)
+    fn = lambda: ops.conv3(x, w3, ops.f32, rowmul=rm)
+for _ in range(4):
+    fn()
+torch.cuda.synchronize()
+print("ok")

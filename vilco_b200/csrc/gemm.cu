@@ -15,13 +15,15 @@ namespace vilco {
 static constexpr int BM = 128;
 static constexpr int BK = 64;            // 64 bf16 = 128 bytes = one swizzle-128B atom row
 static constexpr int UMMA_K = 16;
-static constexpr int NUM_THREADS = 192;  // 6 warps
+static constexpr int NUM_THREADS = 320;  // 10 warps: TMA, MMA, 8 x epilogue
+static constexpr int EPI_WARPS = 8;
+static constexpr int EPI_SMEM = EPI_WARPS * 32 * 32 * 4;  // one swizzled 32x32 fp32 transpose buffer per epilogue warp
 
 struct GemmDev {
   // coordinate slots: the three outer tensor-map dims are sorted by stride on the host
   int a_slot_row, a_slot_z1, a_slot_z2;
   int b_slot_row, b_slot_z1, b_slot_z2;
-  int M, N, K, taps, Z1;
+  int M, N, K, taps, Z1, Ztot;
   int b_major, b_batched;
   void* D; int d_dtype; long long d_ld, d_s1, d_s2, d_lo;
   float alpha;
@@ -44,6 +46,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -145,28 +150,32 @@ __device__ __forceinline__ void store_bf16_split(__nv_bfloat16* D, long long off
 // ---------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ---------------------------------------------------------------------------------------------
+// Persistent, warp-specialised kernel.  Each CTA loops over output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+//   warp 0      : TMA producer (ring of STAGES smem stages, full/empty mbarriers)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer; two accumulator stages in TMEM so the epilogue
+//                 of tile i overlaps the main loop of tile i+1 (tmem_full / tmem_empty mbarriers)
+//   warps 2..9  : epilogue: tcgen05.ld -> swizzled 32x32 smem transpose -> fused math -> wide coalesced global stores
 template <int BN, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmDev p) {
   using L = SmemLayout<BN, SPLIT>;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int ACC_COLS = BN < 32 ? 32 : BN;       // TMEM columns of one accumulator stage
+  constexpr int TMEM_COLS = 2 * ACC_COLS;           // power of two >= 64
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* stage_buf = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES + EPI_SMEM);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-  const int z = blockIdx.z;
-  const int z1 = z % p.Z1, z2 = z / p.Z1;
 
   const uint32_t full0 = smem_u32(bars);
   const uint32_t empty0 = smem_u32(bars + STAGES);
-  const uint32_t tfull = smem_u32(bars + 2 * STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES);       // [2]
+  const uint32_t tempty0 = smem_u32(bars + 2 * STAGES + 2);  // [2]
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -175,7 +184,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(tfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, EPI_WARPS);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -192,136 +204,215 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int kblocks = (p.K + BK - 1) / BK;
   const int iters = p.taps * kblocks;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int tiles_per_z = n_tiles * m_tiles;
+  const int total_tiles = tiles_per_z * p.Ztot;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       int ca[4], cb[4];
-      ca[p.a_slot_z1] = z1; ca[p.a_slot_z2] = z2;
-      cb[p.b_slot_z2] = p.b_batched ? z2 : 0;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const int tap = it / kblocks;
-        const int kb = it - tap * kblocks;
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES * L::PLANES;
-        mbar_expect_tx(full0 + 8 * s, L::STAGE_BYTES);
-        ca[0] = kb * BK;
-        ca[p.a_slot_row] = m0 + tap - (p.taps >> 1);
-        cb[p.b_slot_z1] = p.b_batched ? z1 : tap;
-        if (p.b_major == 0) {
-          cb[0] = kb * BK;
-          cb[p.b_slot_row] = n0;
-        } else {
-          cb[0] = n0;
-          cb[p.b_slot_row] = kb * BK;
-        }
+      uint32_t it_g = 0;  // global k-iteration counter (continues across tiles)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int z = t / tiles_per_z, r = t - z * tiles_per_z;
+        const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
+        const int z1 = z % p.Z1, z2 = z / p.Z1;
+        ca[p.a_slot_z1] = z1; ca[p.a_slot_z2] = z2;
+        cb[p.b_slot_z2] = p.b_batched ? z2 : 0;
+        for (int it = 0; it < iters; ++it, ++it_g) {
+          const int s = it_g % STAGES;
+          const uint32_t ph = (it_g / STAGES) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const int tap = it / kblocks;
+          const int kb = it - tap * kblocks;
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES * L::PLANES;
+          mbar_expect_tx(full0 + 8 * s, L::STAGE_BYTES);
+          ca[0] = kb * BK;
+          ca[p.a_slot_row] = m0 + tap - (p.taps >> 1);
+          cb[p.b_slot_z1] = p.b_batched ? z1 : tap;
+          if (p.b_major == 0) {
+            cb[0] = kb * BK;
+            cb[p.b_slot_row] = n0;
+          } else {
+            cb[0] = n0;
+            cb[p.b_slot_row] = kb * BK;
+          }
 #pragma unroll
-        for (int pl = 0; pl < L::PLANES; ++pl) {
-          tma_load_5d(sa + pl * L::A_BYTES, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3], pl);
-          tma_load_5d(sb + pl * L::B_BYTES, &tmB, full0 + 8 * s, cb[0], cb[1], cb[2], cb[3], pl);
+          for (int pl = 0; pl < L::PLANES; ++pl) {
+            tma_load_5d(sa + pl * L::A_BYTES, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3], pl);
+            tma_load_5d(sb + pl * L::B_BYTES, &tmB, full0 + 8 * s, cb[0], cb[1], cb[2], cb[3], pl);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
     const uint32_t idesc = make_idesc(BN, p.b_major);
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(full0 + 8 * s, ph);
+    uint32_t it_g = 0, tc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+      const uint32_t acc = tc & 1;
+      mbar_wait(tempty0 + 8 * acc, ((tc >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
       tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES * L::PLANES;
+      const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+      for (int it = 0; it < iters; ++it, ++it_g) {
+        const int s = it_g % STAGES;
+        const uint32_t ph = (it_g / STAGES) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES * L::PLANES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major: advance 16 elements = 32 bytes inside the swizzle atom; MN-major: 16 k-rows of 128 bytes.
-          const uint32_t aoff = k * UMMA_K * 2;
-          const uint32_t boff = p.b_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
-          const uint64_t a_hi = make_smem_desc(sa + aoff, 16, 1024);
-          const uint64_t b_hi = make_smem_desc(sb + boff, 16, 1024);
-          tcgen05_mma_f16(tmem_base, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          if (SPLIT) {
-            const uint64_t a_lo = make_smem_desc(sa + L::A_BYTES + aoff, 16, 1024);
-            const uint64_t b_lo = make_smem_desc(sb + L::B_BYTES + boff, 16, 1024);
-            tcgen05_mma_f16(tmem_base, a_hi, b_lo, idesc, 1u);
-            tcgen05_mma_f16(tmem_base, a_lo, b_hi, idesc, 1u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: advance 16 elements = 32 bytes inside the swizzle atom; MN-major: 16 k-rows of 128 bytes.
+            const uint32_t aoff = k * UMMA_K * 2;
+            const uint32_t boff = p.b_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
+            const uint64_t a_hi = make_smem_desc(sa + aoff, 16, 1024);
+            const uint64_t b_hi = make_smem_desc(sb + boff, 16, 1024);
+            tcgen05_mma_f16(tmem_d, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            if (SPLIT) {
+              const uint64_t a_lo = make_smem_desc(sa + L::A_BYTES + aoff, 16, 1024);
+              const uint64_t b_lo = make_smem_desc(sb + L::B_BYTES + boff, 16, 1024);
+              tcgen05_mma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
+              tcgen05_mma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
+            }
           }
+          tcgen05_commit(empty0 + 8 * s);                        // frees the smem stage when these MMAs retire
+          if (it == iters - 1) tcgen05_commit(tfull0 + 8 * acc);  // accumulator complete
         }
-        tcgen05_commit(empty0 + 8 * s);            // frees the smem stage when these MMAs retire
-        if (it == iters - 1) tcgen05_commit(tfull);  // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+    // ===== 8 epilogue warps: TMEM lane quadrant = warp % 4; the two warps of a quadrant split the 32-column chunks =====
     const int q = warp & 3;
-    mbar_wait(tfull, 0);
-    tcgen05_fence_after();
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < p.M;
-    float rm = 1.0f;
-    if (p.rowmul && row_ok) rm = __ldg(p.rowmul + z2 * p.rowmul_zs + m);
-    const float rres = p.resid_masked ? rm : 1.0f;
-    const long long doff = z1 * p.d_s1 + z2 * p.d_s2 + (long long)m * p.d_ld;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      __syncwarp();
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      const int nb = n0 + c * 32;
-      if (!row_ok || nb >= p.N) continue;
-      float v[32];
-      const bool full = (nb + 32 <= p.N) && p.vec_ok;
-      if (full) {
-        if (p.resid) {
-          const float4* rp = reinterpret_cast<const float4*>(p.resid + doff + nb);
+    const int chalf = (warp - 2) >> 2;
+    float* sbuf = stage_buf + (warp - 2) * (32 * 32);
+    const float alpha = p.alpha;
+    const float* __restrict__ bias = p.bias;
+    const float* __restrict__ colscale = p.colscale;
+    const float* __restrict__ resid = p.resid;
+    const int act = p.act;
+    const bool resid_masked = p.resid_masked != 0;
+    const long long d_ld = p.d_ld, d_lo = p.d_lo;
+    const bool is_f32 = p.d_dtype == VILCO_F32;
+    uint32_t tc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+      const int z = t / tiles_per_z, r = t - z * tiles_per_z;
+      const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
+      const int z1 = z % p.Z1, z2 = z / p.Z1;
+      const uint32_t acc = tc & 1;
+      mbar_wait(tfull0 + 8 * acc, (tc >> 1) & 1);
+      tcgen05_fence_after();
+      const int mrow0 = m0 + q * 32;            // first row of this warp's 32-row slab
+      float rm = 1.0f;                          // row multiplier of the accumulator row this lane owns
+      if (p.rowmul && mrow0 + lane < p.M) rm = __ldg(p.rowmul + z2 * p.rowmul_zs + mrow0 + lane);
+      const long long zoff = z1 * p.d_s1 + z2 * p.d_s2;
+      for (int c = chalf; c < BN / 32; c += 2) {
+        const int nb = n0 + c * 32;
+        if (nb >= p.N) break;  // warp-uniform
+        uint32_t rr[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
+        // stage 1: raw accumulator row -> XOR-swizzled 32x32 transpose buffer (conflict-free 128-bit accesses)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 t = rp[j];
-            v[4 * j + 0] = t.x * rres; v[4 * j + 1] = t.y * rres; v[4 * j + 2] = t.z * rres; v[4 * j + 3] = t.w * rres;
-          }
-        } else {
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<uint4*>(sbuf + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+              make_uint4(rr[4 * j4], rr[4 * j4 + 1], rr[4 * j4 + 2], rr[4 * j4 + 3]);
+        __syncwarp();
+        // stage 2: lanes own columns -> per-column vectors loaded once, wide fully coalesced stores
+        if (is_f32) {
+          // 8 lanes cover one 128-byte row segment, 4 rows per instruction
+          const int rsub = lane >> 3, g = lane & 7;
+          const int n = nb + 4 * g;
+          const bool vec = p.vec_ok && (n + 3 < p.N);
+          float b4[4] = {0.f, 0.f, 0.f, 0.f}, s4[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = epi_value(p, __uint_as_float(r[j]), nb + j, rm, v[j]);
-        if (p.d_dtype == VILCO_F32) {
-          float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.D) + doff + nb);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          uint4* dp = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.D) + doff + nb);
-          uint4* dl = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.D) + p.d_lo + doff + nb);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t h[4], lo[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float x0 = v[8 * j + 2 * u], x1 = v[8 * j + 2 * u + 1];
-              h[u] = pack_bf16x2(x0, x1);
-              lo[u] = pack_bf16x2(x0 - bf16_lo(h[u]), x1 - bf16_hi(h[u]));
+          for (int u = 0; u < 4; ++u)
+            if (n + u < p.N) {
+              if (bias) b4[u] = __ldg(bias + n + u);
+              if (colscale) s4[u] = __ldg(colscale + n + u);
             }
-            dp[j] = make_uint4(h[0], h[1], h[2], h[3]);
-            if (p.d_lo) dl[j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        }
-      } else {
+          float* Df = static_cast<float*>(p.D);
+#pragma unroll 2
+          for (int r0 = 0; r0 < 32; r0 += 4) {
+            const int rloc = r0 + rsub;
+            const int mm = mrow0 + rloc;
+            const float rmr = __shfl_sync(0xffffffffu, rm, rloc);
+            if (mm < p.M && n < p.N) {
+              const float4 a = *reinterpret_cast<const float4*>(sbuf + rloc * 32 + ((g ^ (rloc & 7)) << 2));
+              float v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = nb + j;
-          if (n < p.N) {
-            const float res = p.resid ? p.resid[doff + n] * rres : 0.0f;
-            const float o = epi_value(p, __uint_as_float(r[j]), n, rm, res);
-            if (p.d_dtype == VILCO_F32) static_cast<float*>(p.D)[doff + n] = o;
-            else store_bf16_split(static_cast<__nv_bfloat16*>(p.D), doff + n, p.d_lo, o);
+              for (int u = 0; u < 4; ++u) v[u] = apply_act((v[u] * alpha + b4[u]) * rmr, act) * s4[u];
+              const long long o = zoff + (long long)mm * d_ld + n;
+              const float f = resid_masked ? rmr : 1.0f;
+              if (vec) {
+                if (resid) {
+                  const float4 rs = *reinterpret_cast<const float4*>(resid + o);
+                  v[0] += rs.x * f; v[1] += rs.y * f; v[2] += rs.z * f; v[3] += rs.w * f;
+                }
+                *reinterpret_cast<float4*>(Df + o) = make_float4(v[0], v[1], v[2], v[3]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (n + u < p.N) Df[o + u] = v[u] + (resid ? resid[o + u] * f : 0.0f);
+              }
+            }
+          }
+        } else {
+          // 4 lanes cover one 64-byte row segment (8 columns each), 8 rows per instruction
+          const int rsub = lane >> 2, g2 = (lane & 3) * 2;
+          const int n = nb + 4 * g2;
+          const bool vec = p.vec_ok && (n + 7 < p.N);
+          float b8[8], s8[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            b8[u] = (bias && n + u < p.N) ? __ldg(bias + n + u) : 0.f;
+            s8[u] = (colscale && n + u < p.N) ? __ldg(colscale + n + u) : 1.f;
+          }
+          __nv_bfloat16* Db = static_cast<__nv_bfloat16*>(p.D);
+#pragma unroll 2
+          for (int r0 = 0; r0 < 32; r0 += 8) {
+            const int rloc = r0 + rsub;
+            const int mm = mrow0 + rloc;
+            const float rmr = __shfl_sync(0xffffffffu, rm, rloc);
+            if (mm < p.M && n < p.N) {
+              const float4 a = *reinterpret_cast<const float4*>(sbuf + rloc * 32 + ((g2 ^ (rloc & 7)) << 2));
+              const float4 b = *reinterpret_cast<const float4*>(sbuf + rloc * 32 + (((g2 + 1) ^ (rloc & 7)) << 2));
+              float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = apply_act((v[u] * alpha + b8[u]) * rmr, act) * s8[u];
+              const long long o = zoff + (long long)mm * d_ld + n;
+              if (resid) {
+                const float f = resid_masked ? rmr : 1.0f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (n + u < p.N) v[u] += resid[o + u] * f;
+              }
+              if (vec) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  h[u] = pack_bf16x2(v[2 * u], v[2 * u + 1]);
+                  l[u] = pack_bf16x2(v[2 * u] - bf16_lo(h[u]), v[2 * u + 1] - bf16_hi(h[u]));
+                }
+                *reinterpret_cast<uint4*>(Db + o) = make_uint4(h[0], h[1], h[2], h[3]);
+                if (d_lo) *reinterpret_cast<uint4*>(Db + d_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (n + u < p.N) store_bf16_split(Db, o + u, d_lo, v[u]);
+              }
+            }
           }
         }
       }
+      // this warp is done reading the accumulator stage
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
     }
   }
 
@@ -435,16 +526,28 @@ static int encode_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return VILCO_OK;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, int STAGES, bool SPLIT>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int Z, cudaStream_t st) {
   using L = SmemLayout<BN, SPLIT>;
-  constexpr int smem = STAGES * L::STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * L::STAGE_BYTES + EPI_SMEM + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(smem <= 232448, "dynamic shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
     VILCO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, Z);
+  const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * Z;
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   gemm_tc_kernel<BN, STAGES, SPLIT><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
@@ -465,13 +568,14 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   GemmDev p{};
-  p.M = g->M; p.N = g->N; p.K = g->K; p.taps = g->taps; p.Z1 = g->Z1;
+  p.M = g->M; p.N = g->N; p.K = g->K; p.taps = g->taps; p.Z1 = g->Z1; p.Ztot = g->Z1 * g->Z2;
   p.b_major = g->b_major; p.b_batched = g->b_batched;
   p.D = g->D; p.d_dtype = g->d_dtype; p.d_ld = g->d_ld; p.d_s1 = g->d_s1; p.d_s2 = g->d_s2;
   p.d_lo = g->d_dtype == VILCO_BF16 ? g->d_lo : 0;
   p.alpha = g->alpha; p.bias = g->bias; p.rowmul = g->rowmul; p.rowmul_zs = g->rowmul_zs;
   p.act = g->act; p.colscale = g->colscale; p.resid = g->resid; p.resid_masked = g->resid_masked;
   const int esz = g->d_dtype == VILCO_F32 ? 4 : 2;
+  // 16-byte vector stores / residual loads: every (row, column % vec == 0) element must be 16-byte aligned
   p.vec_ok = (reinterpret_cast<uintptr_t>(g->D) % 16 == 0) && ((g->d_ld * esz) % 16 == 0) &&
              ((g->d_s1 * esz) % 16 == 0) && ((g->d_s2 * esz) % 16 == 0) && ((p.d_lo * esz) % 16 == 0) &&
              (!g->resid || (reinterpret_cast<uintptr_t>(g->resid) % 16 == 0 && (g->d_ld * 4) % 16 == 0 &&
@@ -529,6 +633,6 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   switch (BN) {
     case 32: return launch_tc<32, 6, false>(tmA, tmB, p, Z, st);
     case 64: return launch_tc<64, 6, false>(tmA, tmB, p, Z, st);
-    default: return launch_tc<128, 4, false>(tmA, tmB, p, Z, st);
+    default: return launch_tc<128, 5, false>(tmA, tmB, p, Z, st);
   }
 }

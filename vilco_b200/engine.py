@@ -187,8 +187,14 @@ def xlnet_layer_fwd(W, pre, x32, x16, mask, H, eps=1e-12):
     qr = ops.linear(x16, W[kq], bf16, bias=rr)      # q + r_r_bias
     k = ops.linear(x16, W[kk], bf16)
     v = ops.linear(x16, W[kv], bf16)
-    pos = xlnet_pos_emb(T, C, x32.device)                                   # (2T, C)
-    krel = ops.linear(pos, W[kr], bf16).unsqueeze(1).expand(-1, B, 2 * T, C).contiguous()
+    # k_r = pos_emb @ W_r depends only on the weights and (T, B): cached with the packed weights (also keeps host->device
+    # copies out of CUDA-graph capture)
+    cache = W.setdefault("_cache", {})
+    krel = cache.get(("krel", T, B))
+    if krel is None:
+        pos = xlnet_pos_emb(T, C, x32.device)                               # (2T, C)
+        krel = ops.linear(pos, W[kr], bf16).unsqueeze(1).expand(-1, B, 2 * T, C).contiguous()
+        cache[("krel", T, B)] = krel
     ac = ops.attn_scores(qw, k, H, 1.0)                                     # (B,H,T,T)
     bd = ops.attn_scores(qr, krel, H, 1.0)                                  # (B,H,T,2T)
     P = ops.softmax_rows(ac, mask, mode=1, BD=bd, scale=1.0 / math.sqrt(d))
@@ -284,7 +290,11 @@ def neck_heads_fwd(W, cfg, feats, masks, pyr=None):
     C = cfg.embd_dim
     dev = feats[0].device
     if pyr is None:
-        pyr = Pyramid([f.shape[1] for f in feats], dev)
+        cache = W.setdefault("_cache", {})
+        key = ("pyr",) + tuple(f.shape[1] for f in feats)
+        pyr = cache.get(key)
+        if pyr is None:
+            pyr = cache[key] = Pyramid([f.shape[1] for f in feats], dev)
     P = pyr.P
     fpn = ops.zeros16(B, P, C, device=dev)
     pmask = torch.zeros(B, P, device=dev, dtype=f32)
