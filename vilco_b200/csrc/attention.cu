@@ -63,6 +63,66 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const SmParams p) {
   }
 }
 
+// single-pass variant: the whole row lives in registers (Tk even, Tk <= 64*KMAX); lane l holds columns 2l+64k, 2l+64k+1
+// so loads are 8-byte and bf16 stores 4-byte per lane, fully coalesced; S is read from HBM exactly once.
+template <int KMAX>
+__global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const SmParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int i = static_cast<int>(row % p.Tq);
+  const int b = static_cast<int>((row / p.Tq) / p.Z1);
+  const float* s = p.S + row * p.Tk;
+  const float* km = p.kmask ? p.kmask + (long long)b * p.Tk : nullptr;
+  const float* bd = p.mode == 1 ? p.BD + row * (2LL * p.Tk) + (p.Tk - i) : nullptr;
+  __nv_bfloat16* o = p.P + row * p.p_ld;
+  float v[KMAX][2];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int j = 2 * lane + 64 * k;
+    v[k][0] = -INFINITY; v[k][1] = -INFINITY;
+    if (j < p.Tk) {
+      const float2 x = *reinterpret_cast<const float2*>(s + j);
+      float a0 = x.x, a1 = x.y;
+      float m0 = 1.f, m1 = 1.f;
+      if (km) { const float2 mm = *reinterpret_cast<const float2*>(km + j); m0 = mm.x; m1 = mm.y; }
+      if (p.mode == 0) {
+        if (m0 == 0.f) a0 = -INFINITY;
+        if (m1 == 0.f) a1 = -INFINITY;
+      } else {
+        a0 = (a0 + bd[j]) * p.scale;
+        a1 = (a1 + bd[j + 1]) * p.scale;
+        if (m0 == 0.f && j != i) a0 -= 1e30f;
+        if (m1 == 0.f && j + 1 != i) a1 -= 1e30f;
+      }
+      v[k][0] = a0; v[k][1] = a1;
+      mx = fmaxf(mx, fmaxf(a0, a1));
+    }
+  }
+  mx = warp_max(mx);
+  const bool dead = mx == -INFINITY;  // fully masked row: emit zeros (the reference would produce NaN)
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    v[k][0] = dead ? 0.f : __expf(v[k][0] - mx);
+    v[k][1] = dead ? 0.f : __expf(v[k][1] - mx);
+    sum += v[k][0] + v[k][1];
+  }
+  sum = warp_sum(sum);
+  const float inv = dead ? 0.f : 1.0f / sum;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int j = 2 * lane + 64 * k;
+    if (j < p.p_ld) {
+      const float a0 = v[k][0] * inv, a1 = v[k][1] * inv;
+      const uint32_t h = pack_bf16x2(a0, a1);
+      *reinterpret_cast<uint32_t*>(o + j) = h;
+      if (p.p_lo) *reinterpret_cast<uint32_t*>(o + p.p_lo + j) = pack_bf16x2(a0 - bf16_lo(h), a1 - bf16_hi(h));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // local (windowed) attention.  q,k,v: (B, T, C) bf16 token-major, head h = channels [h*d, (h+1)*d).
 // One CTA = (token tile, head, batch); K/V rows [t0-w, t0+TI+w) staged in shared memory once and reused by all
@@ -300,7 +360,16 @@ extern "C" int vilco_softmax_rows(const float* S, const float* BD, const float* 
   p.Z1 = Z1; p.Tq = Tq; p.Tk = Tk; p.p_ld = p_ld; p.scale = scale; p.mode = mode;
   p.rows = (long long)Z2 * Z1 * Tq;
   const long long grid = (p.rows + 7) / 8;
-  softmax_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const bool reg_ok = (Tk % 2 == 0) && (p_ld % 2 == 0) && Tk <= 2048 && p_ld <= ((Tk + 63) / 64) * 64 &&
+                      (reinterpret_cast<uintptr_t>(S) % 8 == 0) && (!kmask || reinterpret_cast<uintptr_t>(kmask) % 8 == 0);
+  if (reg_ok && Tk <= 512)
+    softmax_rows_reg_kernel<8><<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else if (reg_ok && Tk <= 1024)
+    softmax_rows_reg_kernel<16><<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else if (reg_ok)
+    softmax_rows_reg_kernel<32><<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    softmax_rows_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

@@ -24,7 +24,7 @@ __constant__ unsigned long long c_exp2f_tab[32] = {
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
 };
 
-__device__ __forceinline__ float expf_glibc(float x) {
+__device__ __forceinline__ float expf_glibc(float x, const unsigned long long* __restrict__ tab) {
   if (!(fabsf(x) < 87.0f)) return expf(x);  // outside the table algorithm's plain range (never hit by soft-NMS)
   const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
   const double SHIFT = 0x1.8p+52;
@@ -37,7 +37,7 @@ __device__ __forceinline__ float expf_glibc(float x) {
   const unsigned long long ki = static_cast<unsigned long long>(__double_as_longlong(kd));
   kd = __dsub_rn(kd, SHIFT);
   const double r = __dsub_rn(z, kd);
-  unsigned long long t = c_exp2f_tab[ki & 31];
+  unsigned long long t = tab[ki & 31];  // shared-memory copy: lanes index it divergently
   t += ki << (52 - 5);
   const double s = __longlong_as_double(static_cast<long long>(t));
   const double zz = __fma_rn(C0, r, C1);
@@ -290,6 +290,8 @@ __global__ void class_count_kernel(const NmsParams p, int* class_count) {
   }
 }
 
+static constexpr int NMS_SMEM_CAP = 4096;  // candidates of one class held in shared memory (6 arrays x 16 KB)
+
 struct ArgMax { float v; int pos; };
 __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {  // first maximum wins (nms_cpu.cpp:95-101)
   if (b.pos < 0) return a;
@@ -303,6 +305,8 @@ __global__ void __launch_bounds__(256) nms_kernel(const NmsParams p) {
   __shared__ ArgMax s_am[32];
   __shared__ float s_pick[4];
   __shared__ int s_cnt;
+  __shared__ unsigned long long s_tab[32];
+  if (threadIdx.x < 32) s_tab[threadIdx.x] = c_exp2f_tab[threadIdx.x];
   const int c = blockIdx.x, b = blockIdx.y;
   const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const int* cc = p.class_count + b * p.num_classes;
@@ -316,6 +320,13 @@ __global__ void __launch_bounds__(256) nms_kernel(const NmsParams p) {
   const long long wbase = (long long)b * p.n_regions * p.region_cap + woff;
   float* x1 = p.w_x1 + wbase; float* x2 = p.w_x2 + wbase; float* sc = p.w_sc + wbase; float* ar = p.w_ar + wbase;
   int* ind = p.w_ind + wbase; int* hole = p.w_hole + wbase;
+  // the working set of one class normally fits in shared memory (~30-cycle access instead of an L2 round trip per
+  // dependent step of the 200 sequential picks); the global workspace is the fallback for huge classes
+  extern __shared__ float nms_smem[];
+  if (my_n <= NMS_SMEM_CAP) {
+    x1 = nms_smem; x2 = x1 + NMS_SMEM_CAP; sc = x2 + NMS_SMEM_CAP; ar = sc + NMS_SMEM_CAP;
+    ind = reinterpret_cast<int*>(ar + NMS_SMEM_CAP); hole = ind + NMS_SMEM_CAP;
+  }
 
   // ---- stable gather of this class (ascending original index) -----------------------------------
   int filled = 0;
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(256) nms_kernel(const NmsParams p) {
       float w = 1.f;
       if (method == 0) { if (ovr >= p.iou_threshold) w = 0.f; }
       else if (method == 1) { if (ovr >= p.iou_threshold) w = __fsub_rn(1.f, ovr); }
-      else w = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma));
+      else w = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma), s_tab);
       const float ns = __fmul_rn(sc[pos], w);
       sc[pos] = ns;
       ndel += ns < min_score ? 1 : 0;
@@ -593,7 +604,12 @@ extern "C" int vilco_batched_nms(const float* segs, const float* scores, const i
   VILCO_CUDA(cudaMemsetAsync(class_count, 0, (size_t)B * ncls * 4, st));
   class_count_kernel<<<dim3(32, B), 256, 0, st>>>(p, class_count);
   VILCO_LAUNCH_CHECK();
-  nms_kernel<<<dim3(ncls, B), 256, 0, st>>>(p);
+  static bool nms_configured = false;
+  if (!nms_configured) {
+    VILCO_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * NMS_SMEM_CAP * 4));
+    nms_configured = true;
+  }
+  nms_kernel<<<dim3(ncls, B), 256, 6 * NMS_SMEM_CAP * 4, st>>>(p);
   VILCO_LAUNCH_CHECK();
   MergeParams m{};
   m.dets = p.dets; m.det_ind = p.det_ind; m.det_count = p.det_count; m.det_cap = det_cap; m.num_classes = ncls; m.B = B;

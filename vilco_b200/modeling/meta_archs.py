@@ -508,6 +508,85 @@ class EvalGraph:
     def replay(self):
         self.graph.replay()
 
+    # ---- pipelined evaluation: the H2D copy of batch i+1 overlaps the graph replay of batch i ------------------------
+    def _host_to(self, dst, video_list, stream):
+        """pinned host -> device staging set `dst` on `stream` (async)."""
+        m, T = self.model, self.model.max_seq_len
+        lens = [v["feats"].shape[-1] for v in video_list]
+        with torch.cuda.stream(stream):
+            for i, v in enumerate(video_list):
+                f = v["feats"] if (v["feats"].is_pinned() or v["feats"].is_cuda) else v["feats"].pin_memory()
+                if lens[i] < T:
+                    dst["feats"][i, :, lens[i]:].zero_()
+                dst["feats"][i, :, :lens[i]].copy_(f, non_blocking=True)
+            dst["mask_h"].copy_((torch.arange(T)[None, :] < torch.as_tensor(lens)[:, None]).float())
+            dst["mask"].copy_(dst["mask_h"], non_blocking=True)
+            if m.use_cross_modal:
+                tl = [v["prompt_feature"].shape[-1] for v in video_list]
+                dst["text_h"].zero_()
+                for i, v in enumerate(video_list):
+                    dst["text_h"][i, :, :tl[i]].copy_(v["prompt_feature"])
+                dst["tmask_h"].copy_((torch.arange(self.Lt)[None, :] < torch.as_tensor(tl)[:, None]).float())
+                dst["tlens_h"].copy_(torch.as_tensor(tl, dtype=torch.int32))
+                dst["text"].copy_(dst["text_h"], non_blocking=True)
+                dst["tmask"].copy_(dst["tmask_h"], non_blocking=True)
+                dst["tlens"].copy_(dst["tlens_h"], non_blocking=True)
+
+    def _new_slot(self):
+        m, dev = self.model, self.model.device
+        d = {"feats": torch.empty_like(self.feats), "mask": torch.empty_like(self.mask),
+             "mask_h": torch.empty(self.mask.shape).pin_memory(), "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
+             "done": torch.cuda.Event()}
+        if m.use_cross_modal:
+            d.update(text=torch.empty_like(self.text), tmask=torch.empty_like(self.tmask), tlens=torch.empty_like(self.tlens),
+                     text_h=torch.empty(self.text.shape).pin_memory(), tmask_h=torch.empty(self.tmask.shape).pin_memory(),
+                     tlens_h=torch.empty(self.tlens.shape, dtype=torch.int32).pin_memory())
+        d["out_h"] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self.out]
+        return d
+
+    def infer_stream(self, batches):
+        """Generator over result lists, one per batch of `batches` (an iterable of video_list).  Double-buffered:
+        while the graph of batch i runs, the inputs of batch i+1 are copied host->device on a side stream."""
+        if not hasattr(self, "_slots"):
+            self._slots = [self._new_slot(), self._new_slot()]
+            self._copy_stream = torch.cuda.Stream()
+        comp = torch.cuda.current_stream()
+        pending = []  # (slot, video_list)
+        it = iter(batches)
+        k = 0
+
+        def submit(vl, slot):
+            self._copy_stream.wait_event(slot["free"])
+            self._host_to(slot, vl, self._copy_stream)
+            slot["ready"].record(self._copy_stream)
+            comp.wait_event(slot["ready"])
+            self.feats.copy_(slot["feats"], non_blocking=True)
+            self.mask.copy_(slot["mask"], non_blocking=True)
+            if self.model.use_cross_modal:
+                self.text.copy_(slot["text"], non_blocking=True)
+                self.tmask.copy_(slot["tmask"], non_blocking=True)
+                self.tlens.copy_(slot["tlens"], non_blocking=True)
+            slot["free"].record(comp)
+            self.graph.replay()
+            for h, t in zip(slot["out_h"], self.out):
+                h.copy_(t, non_blocking=True)
+            slot["done"].record(comp)
+
+        for s_ in self._slots:
+            s_["free"].record(comp)
+        for vl in it:
+            slot = self._slots[k % 2]
+            if len(pending) == 2:
+                ps, pvl = pending.pop(0)
+                ps["done"].synchronize()
+                yield PtTransformer._to_results(pvl, *ps["out_h"])
+            submit(vl, slot)
+            pending.append((slot, vl))
+            k += 1
+        for ps, pvl in pending:
+            ps["done"].synchronize()
+            yield PtTransformer._to_results(pvl, *ps["out_h"])
+
     def run(self, video_list):
         self.load_inputs(video_list)
         self.graph.replay()
