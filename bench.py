@@ -236,10 +236,8 @@ def main():
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    if dist is not None:
-        tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    from vilco_b200.dist import max_over_ranks
+    t_dev, t_e2e = max_over_ranks([t_dev, t_e2e], device="cuda")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
