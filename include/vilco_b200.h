@@ -179,6 +179,15 @@ int vilco_mq_losses(const float* logits, const float* offsets, const float* pmas
                     const float* gt_off, const float* w_cls, const float* w_l, const float* w_r, const float* present, int B,
                     int P, int K, float alpha, float gamma, float* sums4, unsigned int* smax_scratch, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Fused masked attention core (head dim 64) — the `att = (q*scale) @ k^T; masked_fill(~kv_mask, -inf); softmax;
+ * att @ v` of MaskedMHCA.forward (MQ/libs/modeling/blocks.py:386-396) and MaskedMHA.forward (blocks.py:255-263):
+ * q (B,Tq,C), k/v (B,Tk,C) bf16 token-major (q_lo / kv_lo = lo-plane offsets, 0 for single plane), kmask (B,Tk) or NULL,
+ * out (B,Tq,C) bf16 (+ lo plane).  Scores stay in TMEM; Tk <= 2048.  Fully masked rows produce zeros.
+ * ------------------------------------------------------------------------------------ */
+int vilco_attention(const void* q, int64_t q_lo, const void* k, const void* v, int64_t kv_lo, const float* kmask, void* out,
+                    int64_t out_lo, int B, int H, int Tq, int Tk, int C, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

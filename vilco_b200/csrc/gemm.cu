@@ -97,6 +97,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // shared-memory matrix descriptor, 128B swizzle, sm_100 (version = 1)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -553,6 +559,293 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmD
   return VILCO_OK;
 }
 
+// =============================================================================================
+// Fused masked attention (global MaskedMHCA core and the MaskedMHA cross attention), head dim 64:
+//   O[b, i, h*64:(h+1)*64] = softmax_j( scale * q_i . k_j  |  keys with kmask == 0 excluded ) @ v
+// One CTA = 128 query rows of one (batch, head).  S = Q K^T lives only in TMEM (two 128-column buffers), never in HBM.
+// Two passes over the key tiles: pass 1 accumulates the row max / sum (online, one thread per row), pass 2 recomputes
+// S, writes P = exp(S - m) / l as bf16 (hi, lo) into 128B-swizzled shared memory and accumulates O += P V in TMEM —
+// recomputing QK^T (K = 64) is cheaper than rescaling O.  warp 0: TMA, warp 1: MMA issuer, warps 2..5: softmax.
+// =============================================================================================
+static constexpr int AT_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps
+static constexpr int AT_BQ = 128, AT_BKV = 128, AT_D = 64;
+static constexpr int AT_MAX_TK = 2048;
+
+struct AttnDev {
+  int q_slot_row, q_slot_z1, q_slot_z2;
+  int k_slot_row, k_slot_z1, k_slot_z2;
+  int v_slot_row, v_slot_z1, v_slot_z2;
+  int Tq, Tk, H;
+  float scale;
+  const float* kmask;  // (B, Tk) or null
+  __nv_bfloat16* O; long long o_lo; long long o_ld, o_sh, o_sb;  // element strides: row, head, batch
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnDev p) {
+  constexpr int PL = SPLIT ? 2 : 1;
+  constexpr int TILE = AT_BQ * AT_D * 2;            // 16 KB: 128 rows x 128 bytes
+  constexpr int Q_BYTES = PL * TILE, K_BYTES = PL * TILE, V_BYTES = PL * TILE;
+  constexpr int P_BYTES = PL * 2 * TILE;            // 128 rows x 128 keys = two 64-key K-major blocks per plane
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;                       // 2 stages
+  uint8_t* sV = sK + 2 * K_BYTES;                   // 1 stage
+  uint8_t* sP = sV + V_BYTES;
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(sP + P_BYTES);      // key validity, one bit per key (AT_MAX_TK / 32 words)
+  float* s_part = reinterpret_cast<float*>(s_bits + AT_MAX_TK / 32);  // (m, l) of 2 halves x 128 rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * 128 * 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t qfull = smem_u32(bars + 0);
+  const uint32_t kfull0 = smem_u32(bars + 1), kempty0 = smem_u32(bars + 3);
+  const uint32_t vfull = smem_u32(bars + 5), vempty = smem_u32(bars + 6);
+  const uint32_t sfull0 = smem_u32(bars + 7), sempty0 = smem_u32(bars + 9);
+  const uint32_t pfull = smem_u32(bars + 11), pempty = smem_u32(bars + 12), ofull = smem_u32(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+  const int nkv = (p.Tk + AT_BKV - 1) / AT_BKV;
+  const int G = 2 * nkv;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    mbar_init(qfull, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(kfull0 + 8 * i, 1); mbar_init(kempty0 + 8 * i, 1);
+      mbar_init(sfull0 + 8 * i, 1); mbar_init(sempty0 + 8 * i, 8);
+    }
+    mbar_init(vfull, 1); mbar_init(vempty, 1);
+    mbar_init(pfull, 8); mbar_init(pempty, 1); mbar_init(ofull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {  // key validity bits of this batch element (tail keys are invalid too)
+    for (int j0 = (warp - 2) * 32; j0 < nkv * AT_BKV; j0 += 8 * 32) {
+      const int j = j0 + lane;
+      const bool ok = j < p.Tk && (!p.kmask || p.kmask[(long long)b * p.Tk + j] != 0.f);
+      const uint32_t w = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) s_bits[j0 >> 5] = w;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int c[4];
+      mbar_expect_tx(qfull, Q_BYTES);
+      c[0] = 0; c[p.q_slot_row] = q0; c[p.q_slot_z1] = h; c[p.q_slot_z2] = b;
+      for (int pl = 0; pl < PL; ++pl) tma_load_5d(smem_u32(sQ) + pl * TILE, &tmQ, qfull, c[0], c[1], c[2], c[3], pl);
+      for (int g = 0; g < G; ++g) {
+        const int st = g & 1, j = g % nkv;
+        mbar_wait(kempty0 + 8 * st, ((g >> 1) & 1) ^ 1);
+        mbar_expect_tx(kfull0 + 8 * st, K_BYTES);
+        c[0] = 0; c[p.k_slot_row] = j * AT_BKV; c[p.k_slot_z1] = h; c[p.k_slot_z2] = b;
+        for (int pl = 0; pl < PL; ++pl)
+          tma_load_5d(smem_u32(sK) + st * K_BYTES + pl * TILE, &tmK, kfull0 + 8 * st, c[0], c[1], c[2], c[3], pl);
+        if (g >= nkv) {
+          mbar_wait(vempty, (j & 1) ^ 1);
+          mbar_expect_tx(vfull, V_BYTES);
+          c[0] = 0; c[p.v_slot_row] = j * AT_BKV; c[p.v_slot_z1] = h; c[p.v_slot_z2] = b;
+          for (int pl = 0; pl < PL; ++pl) tma_load_5d(smem_u32(sV) + pl * TILE, &tmV, vfull, c[0], c[1], c[2], c[3], pl);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = make_idesc(AT_BKV, 0);   // N = 128 keys, B K-major
+    const uint32_t idesc_o = make_idesc(AT_D, 1);     // N = 64, B (V) MN-major
+    mbar_wait(qfull, 0);
+    auto issue_pv = [&](int j) {
+      mbar_wait(pfull, j & 1);
+      mbar_wait(vfull, j & 1);
+      tcgen05_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int ks = 0; ks < AT_BKV / UMMA_K; ++ks) {
+          const uint32_t aoff = (ks >> 2) * TILE + (ks & 3) * 32;  // 64-key block, then 16-key step inside the atom
+          const uint32_t boff = ks * UMMA_K * 128;                 // 16 key rows of 128 bytes
+          const uint64_t a_hi = make_smem_desc(smem_u32(sP) + aoff, 16, 1024);
+          const uint64_t b_hi = make_smem_desc(smem_u32(sV) + boff, 16, 1024);
+          tcgen05_mma_f16(tO, a_hi, b_hi, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          if (SPLIT) {
+            const uint64_t a_lo = make_smem_desc(smem_u32(sP) + 2 * TILE + aoff, 16, 1024);
+            const uint64_t b_lo = make_smem_desc(smem_u32(sV) + TILE + boff, 16, 1024);
+            tcgen05_mma_f16(tO, a_hi, b_lo, idesc_o, 1u);
+            tcgen05_mma_f16(tO, a_lo, b_hi, idesc_o, 1u);
+          }
+        }
+        tcgen05_commit(pempty);
+        tcgen05_commit(vempty);
+      }
+      __syncwarp();
+    };
+    for (int g = 0; g < G; ++g) {
+      const int st = g & 1;
+      const uint32_t ph = (g >> 1) & 1;
+      mbar_wait(kfull0 + 8 * st, ph);
+      mbar_wait(sempty0 + 8 * st, ph ^ 1);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t kb = smem_u32(sK) + st * K_BYTES;
+#pragma unroll
+        for (int k = 0; k < AT_D / UMMA_K; ++k) {
+          const uint64_t a_hi = make_smem_desc(smem_u32(sQ) + k * 32, 16, 1024);
+          const uint64_t b_hi = make_smem_desc(kb + k * 32, 16, 1024);
+          tcgen05_mma_f16(tS0 + st * 128, a_hi, b_hi, idesc_s, k > 0 ? 1u : 0u);
+          if (SPLIT) {
+            const uint64_t a_lo = make_smem_desc(smem_u32(sQ) + TILE + k * 32, 16, 1024);
+            const uint64_t b_lo = make_smem_desc(kb + TILE + k * 32, 16, 1024);
+            tcgen05_mma_f16(tS0 + st * 128, a_hi, b_lo, idesc_s, 1u);
+            tcgen05_mma_f16(tS0 + st * 128, a_lo, b_hi, idesc_s, 1u);
+          }
+        }
+        tcgen05_commit(kempty0 + 8 * st);
+        tcgen05_commit(sfull0 + 8 * st);
+      }
+      __syncwarp();
+      if (g > nkv) issue_pv(g - nkv - 1);  // P V of the previous key tile, after the next S is already in flight
+    }
+    issue_pv(nkv - 1);
+    if (lane == 0) tcgen05_commit(ofull);
+    __syncwarp();
+  } else {
+    // ===== 8 softmax warps: TMEM lane quadrant q = warp % 4 (one thread per query row), column half = (warp-2)/4 =====
+    // everything is kept in the log2 domain: x2 = s * scale * log2(e), p = 2^(x2 - m2l)
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;                 // row inside the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const float sc2 = p.scale * 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f, m2l = 0.f;
+    bool dead = false;
+    for (int g = 0; g < G; ++g) {
+      const int st = g & 1, j = g % nkv;
+      mbar_wait(sfull0 + 8 * st, (g >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t tS = tS0 + st * 128 + lane_addr + half * 64;
+      if (g < nkv) {
+        // pass 1: online row max / sum over this warp's 64 columns of the tile
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t bits = s_bits[j * 4 + half * 2 + c];   // validity of the 32 keys (warp-uniform)
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32(tS + c * 32, r);
+          if (bits == 0u) continue;
+          float x[32];
+          float cmax = -INFINITY;
+          if (bits == 0xFFFFFFFFu) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) { x[u] = __uint_as_float(r[u]) * sc2; cmax = fmaxf(cmax, x[u]); }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+              x[u] = ((bits >> u) & 1u) ? __uint_as_float(r[u]) * sc2 : -INFINITY;
+              cmax = fmaxf(cmax, x[u]);
+            }
+          }
+          const float m_new = fmaxf(m, cmax);      // finite: at least one valid key in this chunk
+          float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+          for (int u = 0; u < 32; u += 2) { sum0 += ex2f(x[u] - m_new); sum1 += ex2f(x[u + 1] - m_new); }
+          l = l * ex2f(m - m_new) + (sum0 + sum1);  // ex2(-inf) = 0 covers the first chunk
+          m = m_new;
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty0 + 8 * st);
+      } else {
+        if (g == nkv) {
+          // combine the two column halves of every row (only cross-warp exchange of the kernel)
+          s_part[(half * 128 + row) * 2] = m;
+          s_part[(half * 128 + row) * 2 + 1] = l;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const float mo = s_part[((half ^ 1) * 128 + row) * 2], lo_ = s_part[((half ^ 1) * 128 + row) * 2 + 1];
+          const float M = fmaxf(m, mo);
+          dead = M == -INFINITY;                    // fully masked row -> zeros
+          const float Lsum = dead ? 1.f : l * ex2f(m - M) + lo_ * ex2f(mo - M);
+          m2l = dead ? 0.f : M + __log2f(Lsum);
+        }
+        mbar_wait(pempty, (j & 1) ^ 1);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t bits = dead ? 0u : s_bits[j * 4 + half * 2 + c];
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld32(tS + c * 32, r);
+          // 32 keys = four 16-byte chunks per plane; 64-key block = half, chunk index inside its 128-byte row
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k0 = ch * 8 + 2 * u;
+              float a = ex2f(__uint_as_float(r[k0]) * sc2 - m2l);
+              float bq = ex2f(__uint_as_float(r[k0 + 1]) * sc2 - m2l);
+              if (bits != 0xFFFFFFFFu) {
+                if (!((bits >> k0) & 1u)) a = 0.f;
+                if (!((bits >> (k0 + 1)) & 1u)) bq = 0.f;
+              }
+              hi[u] = pack_bf16x2(a, bq);
+              lo[u] = pack_bf16x2(a - bf16_lo(hi[u]), bq - bf16_hi(hi[u]));
+            }
+            const int chunk = c * 4 + ch;
+            uint8_t* dst = sP + half * TILE + row * 128 + ((chunk ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (SPLIT) *reinterpret_cast<uint4*>(dst + 2 * TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        tcgen05_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> tensor core reads
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(sempty0 + 8 * st); mbar_arrive(pfull); }
+      }
+    }
+    // ===== output: O (128 x 64 fp32 in TMEM) -> bf16 (hi, lo) rows in global memory; 32 columns per warp =====
+    mbar_wait(ofull, 0);
+    tcgen05_fence_after();
+    const int grow = q0 + row;
+    __nv_bfloat16* orow = p.O + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)grow * p.o_ld + half * 32;
+    {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tO + lane_addr + half * 32, r);
+      if (grow < p.Tq) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float a = __uint_as_float(r[ch * 8 + 2 * u]), bq = __uint_as_float(r[ch * 8 + 2 * u + 1]);
+            hi[u] = pack_bf16x2(a, bq);
+            lo[u] = pack_bf16x2(a - bf16_lo(hi[u]), bq - bf16_hi(hi[u]));
+          }
+          *reinterpret_cast<uint4*>(orow + ch * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (p.o_lo) *reinterpret_cast<uint4*>(orow + p.o_lo + ch * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace vilco
 
 using namespace vilco;
@@ -635,4 +928,46 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
     case 64: return launch_tc<64, 6, false>(tmA, tmB, p, Z, st);
     default: return launch_tc<128, 5, false>(tmA, tmB, p, Z, st);
   }
+}
+
+
+extern "C" int vilco_attention(const void* q, int64_t q_lo, const void* k, const void* v, int64_t kv_lo, const float* kmask,
+                               void* out, int64_t out_lo, int B, int H, int Tq, int Tk, int C, float scale, void* stream) {
+  VILCO_CHECK_ARG(q && k && v && out, "vilco_attention: null pointer");
+  VILCO_CHECK_ARG(H > 0 && C == H * AT_D, "vilco_attention: head dim must be 64 (C=%d, H=%d)", C, H);
+  VILCO_CHECK_ARG(Tq > 0 && Tk > 0 && Tk <= AT_MAX_TK, "vilco_attention: Tk=%d unsupported (1..%d)", Tk, AT_MAX_TK);
+  VILCO_CHECK_ARG(reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_lo % 8 == 0, "vilco_attention: out alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool split = q_lo != 0 && kv_lo != 0;
+  CUtensorMap tmQ, tmK, tmV;
+  int sq[3], sk[3], sv[3];
+  int rc = encode_map(&tmQ, q, AT_D, (uint64_t)Tq, C, (uint64_t)H, AT_D, (uint64_t)B, (int64_t)Tq * C, split ? q_lo : 0,
+                      AT_D, AT_BQ, sq);
+  if (rc) return rc;
+  rc = encode_map(&tmK, k, AT_D, (uint64_t)Tk, C, (uint64_t)H, AT_D, (uint64_t)B, (int64_t)Tk * C, split ? kv_lo : 0, AT_D,
+                  AT_BKV, sk);
+  if (rc) return rc;
+  rc = encode_map(&tmV, v, AT_D, (uint64_t)Tk, C, (uint64_t)H, AT_D, (uint64_t)B, (int64_t)Tk * C, split ? kv_lo : 0, AT_D,
+                  AT_BKV, sv);
+  if (rc) return rc;
+  AttnDev p{};
+  p.q_slot_row = sq[0]; p.q_slot_z1 = sq[1]; p.q_slot_z2 = sq[2];
+  p.k_slot_row = sk[0]; p.k_slot_z1 = sk[1]; p.k_slot_z2 = sk[2];
+  p.v_slot_row = sv[0]; p.v_slot_z1 = sv[1]; p.v_slot_z2 = sv[2];
+  p.Tq = Tq; p.Tk = Tk; p.H = H; p.scale = scale; p.kmask = kmask;
+  p.O = static_cast<__nv_bfloat16*>(out); p.o_lo = out_lo; p.o_ld = C; p.o_sh = AT_D; p.o_sb = (long long)Tq * C;
+  const int PL = split ? 2 : 1;
+  const int smem = PL * 16384 * (1 + 2 + 1 + 2) + AT_MAX_TK / 8 + 2 * 128 * 2 * 4 + 16 * 8 + 16 + 1024;
+  dim3 grid((Tq + AT_BQ - 1) / AT_BQ, H, B);
+  if (split) {
+    static bool cfg = false;
+    if (!cfg) { VILCO_CUDA(cudaFuncSetAttribute(attn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cfg = true; }
+    attn_fused_kernel<true><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { VILCO_CUDA(cudaFuncSetAttribute(attn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cfg = true; }
+    attn_fused_kernel<false><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
+  }
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
 }

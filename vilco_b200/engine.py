@@ -91,6 +91,8 @@ def mhca_fwd(W, pre, xin, mask, H, stride, window=-1, tlen=None):
         return o, omask
     # v * kv_mask (blocks.py:394) fused as the row multiplier of the value projection
     v = ops.linear(vc, W[pre + "value.weight"], bf16, bias=W[pre + "value.bias"], rowmul=omask.reshape(-1))
+    if ops.FUSED_ATTN and C // H == 64 and k.shape[2] <= 2048:
+        return ops.attention(q, k, v, omask, H, 1.0 / math.sqrt(C // H)), omask
     S = ops.attn_scores(q, k, H, 1.0 / math.sqrt(C // H))
     P = ops.softmax_rows(S, omask, mode=0)
     o = ops.attn_pv(P, v, H, k.shape[2])
@@ -103,6 +105,8 @@ def cross_attn_fwd(W, pre, x16, y16, ymask, H):
     q = ops.linear(x16, W[pre + "query.weight"], bf16, bias=W[pre + "query.bias"])
     k = ops.linear(y16, W[pre + "key.weight"], bf16, bias=W[pre + "key.bias"])
     v = ops.linear(y16, W[pre + "value.weight"], bf16, bias=W[pre + "value.bias"], rowmul=ymask.reshape(-1))
+    if ops.FUSED_ATTN and C // H == 64 and k.shape[2] <= 2048:
+        return ops.attention(q, k, v, ymask, H, 1.0 / math.sqrt(C // H))
     S = ops.attn_scores(q, k, H, 1.0 / math.sqrt(C // H))
     P = ops.softmax_rows(S, ymask, mode=0)
     return ops.attn_pv(P, v, H, k.shape[2])

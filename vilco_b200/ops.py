@@ -19,6 +19,7 @@ bf16 = torch.bfloat16
 f32 = torch.float32
 
 PLANES = 1 if os.environ.get("VILCO_PRECISION", "bf16x3") == "bf16" else 2
+FUSED_ATTN = os.environ.get("VILCO_FUSED_ATTN", "1") == "1"  # 0: materialised QK^T -> softmax -> PV kernels
 
 
 def set_precision(name):
@@ -116,6 +117,18 @@ def attn_pv(P, v, H, Tk):
     out = empty16(B, Tq, Cc, device=v.device)
     L.gemm(P, v, out, M=Tq, N=d, K=Tk, a_rows=Tq, a_ld=ldp, a_s=(Tq * ldp, H * Tq * ldp), Z=(H, B), b_ld=Cc,
            b_s=(d, Tk * Cc), b_batched=True, b_major=1, d_ld=Cc, d_s=(d, Tq * Cc), a_lo=lo(P), b_lo=lo(v), d_lo=lo(out))
+    return out
+
+
+def attention(q, k, v, kmask, H, scale):
+    """Fused masked attention core: q (NP,B,Tq,C), k/v (NP,B,Tk,C) operands, kmask (B,Tk) fp32 or None
+    -> operand (NP,B,Tq,C).  Scores never leave TMEM."""
+    _, B, Tq, Cc = q.shape
+    Tk = k.shape[2]
+    assert lo(k) == lo(v)
+    out = empty16(B, Tq, Cc, device=q.device)
+    L.check(L.lib().vilco_attention(_p(q), _i64(lo(q)), _p(k), _p(v), _i64(lo(k)), _p(kmask), _p(out), _i64(lo(out)), B, H,
+                                    Tq, Tk, Cc, C.c_float(scale), L.stream_ptr()), "vilco_attention")
     return out
 
 
