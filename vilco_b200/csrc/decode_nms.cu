@@ -300,7 +300,7 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {  // first maximum
   return a;
 }
 
-__global__ void __launch_bounds__(256) nms_kernel(const NmsParams p) {
+__global__ void __launch_bounds__(1024) nms_kernel(const NmsParams p) {
   __shared__ BlockScratch s;
   __shared__ ArgMax s_am[32];
   __shared__ float s_pick[4];
@@ -363,32 +363,25 @@ __global__ void __launch_bounds__(256) nms_kernel(const NmsParams p) {
 
   int i = 0;
   for (; i < n && i < max_picks; ++i) {
-    // ---- first maximum over [i, n) ----
-    ArgMax best{0.f, -1};
-    for (int pos = i + tid; pos < n; pos += nt) {
-      const float v = sc[pos];
-      if (best.pos < 0 || v > best.v) { best.v = v; best.pos = pos; }
+    // ---- first maximum over [i, n): monotone uint keys + redux.sync (max key, then min position among the maxima) ----
+    uint32_t bkey = 0u;
+    int bpos = 0x7fffffff;
+    for (int pos = i + tid; pos < n; pos += nt) {   // ascending positions per thread: strict '>' keeps the earliest
+      const uint32_t kk = fkey(sc[pos]);
+      if (bpos == 0x7fffffff || kk > bkey) { bkey = kk; bpos = pos; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ArgMax other;
-      other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
-      other.pos = __shfl_xor_sync(0xffffffffu, best.pos, o);
-      best = better(best, other);
+    {
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, bkey);
+      const int wpos = __reduce_min_sync(0xffffffffu, (bkey == wmax) ? bpos : 0x7fffffff);
+      if (lane == 0) { s_am[warp].v = __uint_as_float(wmax); s_am[warp].pos = wpos; }
     }
-    if (lane == 0) s_am[warp] = best;
     __syncthreads();
     if (warp == 0) {
-      ArgMax v = lane < nw ? s_am[lane] : ArgMax{0.f, -1};
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        ArgMax other;
-        other.v = __shfl_xor_sync(0xffffffffu, v.v, o);
-        other.pos = __shfl_xor_sync(0xffffffffu, v.pos, o);
-        v = better(v, other);
-      }
+      const uint32_t kk = lane < nw ? __float_as_uint(s_am[lane].v) : 0u;
+      const int pp = lane < nw ? s_am[lane].pos : 0x7fffffff;
+      const uint32_t bmax = __reduce_max_sync(0xffffffffu, pp == 0x7fffffff ? 0u : kk);
+      const int mp = __reduce_min_sync(0xffffffffu, (kk == bmax) ? pp : 0x7fffffff);
       if (lane == 0) {
-        const int mp = v.pos;
         const float ix1 = x1[mp], ix2 = x2[mp], isc = sc[mp], iar = ar[mp];
         const int iind = ind[mp];
         x1[mp] = x1[i]; x2[mp] = x2[i]; sc[mp] = sc[i]; ar[mp] = ar[i]; ind[mp] = ind[i];
@@ -408,13 +401,18 @@ __global__ void __launch_bounds__(256) nms_kernel(const NmsParams p) {
       const float xx1 = fmaxf(ix1, x1[pos]);
       const float xx2 = fminf(ix2, x2[pos]);
       const float inter = fmaxf(0.f, __fsub_rn(xx2, xx1));
-      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iar, ar[pos]), inter));
-      float w = 1.f;
-      if (method == 0) { if (ovr >= p.iou_threshold) w = 0.f; }
-      else if (method == 1) { if (ovr >= p.iou_threshold) w = __fsub_rn(1.f, ovr); }
-      else w = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma), s_tab);
-      const float ns = __fmul_rn(sc[pos], w);
-      sc[pos] = ns;
+      float ns = sc[pos];
+      // no overlap: ovr = +0 exactly, the weight is exactly 1 (threshold > 0) and the score is unchanged -> skip the
+      // IEEE division and the double-precision exp (bit-identical shortcut); the min_score test still applies
+      if (inter > 0.f || p.iou_threshold <= 0.f) {
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iar, ar[pos]), inter));
+        float w = 1.f;
+        if (method == 0) { if (ovr >= p.iou_threshold) w = 0.f; }
+        else if (method == 1) { if (ovr >= p.iou_threshold) w = __fsub_rn(1.f, ovr); }
+        else w = expf_glibc(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma), s_tab);
+        ns = __fmul_rn(ns, w);
+        sc[pos] = ns;
+      }
       ndel += ns < min_score ? 1 : 0;
     }
     if (!__syncthreads_or(ndel > 0)) continue;
@@ -609,7 +607,7 @@ extern "C" int vilco_batched_nms(const float* segs, const float* scores, const i
     VILCO_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * NMS_SMEM_CAP * 4));
     nms_configured = true;
   }
-  nms_kernel<<<dim3(ncls, B), 256, 6 * NMS_SMEM_CAP * 4, st>>>(p);
+  nms_kernel<<<dim3(ncls, B), 1024, 6 * NMS_SMEM_CAP * 4, st>>>(p);
   VILCO_LAUNCH_CHECK();
   MergeParams m{};
   m.dets = p.dets; m.det_ind = p.det_ind; m.det_count = p.det_count; m.det_cap = det_cap; m.num_classes = ncls; m.B = B;
