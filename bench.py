@@ -150,7 +150,8 @@ def gemm_roofline(graph_runner, model, B):
         r = orig(A, Bm, D, **kw)
         e1.record()
         Z = kw.get("Z", (1, 1))
-        rec.append((e0, e1, 2.0 * kw["M"] * kw["N"] * kw["K"] * kw.get("taps", 1) * Z[0] * Z[1]))
+        rec.append((e0, e1, 2.0 * kw["M"] * kw["N"] * kw["K"] * kw.get("taps", 1) * Z[0] * Z[1],
+                    (kw["M"], kw["N"], kw["K"], kw.get("taps", 1), Z[0] * Z[1], str(D.dtype)[6:])))
         return r
 
     L.gemm = timed
@@ -161,17 +162,24 @@ def gemm_roofline(graph_runner, model, B):
             torch.cuda.synchronize()
     finally:
         L.gemm = orig
-    t = sum(a.elapsed_time(b) for a, b, _ in rec) * 1e-3
-    fl = sum(f for _, _, f in rec)
+    t = sum(a.elapsed_time(b) for a, b, _, _ in rec) * 1e-3
+    fl = sum(f for _, _, f, _ in rec)
+    if os.environ.get("VILCO_GEMM_TABLE"):
+        agg = {}
+        for a, b, f, shape in rec:
+            d = agg.setdefault(shape, [0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b) * 1e3; d[1] += f; d[2] += 1
+        for shape, (us, f, n) in sorted(agg.items(), key=lambda x: -x[1][0]):
+            print(f"  gemm M{shape[0]:6d} N{shape[1]:5d} K{shape[2]:5d} taps{shape[3]} Z{shape[4]:4d} {shape[5]:9s} x{n:3d}  {us:9.1f} us  {f / us / 1e6:7.1f} TFLOP/s", file=sys.stderr)
     return fl, t, len(rec)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8, help="clips per step per GPU")
+    ap.add_argument("--batch", type=int, default=32, help="clips per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "bf16x3"])
     ap.add_argument("--ref-videos", type=int, default=4, help="clips per CPU-baseline sample")

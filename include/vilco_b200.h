@@ -114,6 +114,11 @@ int vilco_maxpool3s2(const float* x, float* y, int B, int T, int C, void* stream
 int vilco_axpby(const float* x, const float* y, float a, float b, float* o32, void* o16, int64_t o16_lo, int64_t n,
                 void* stream);
 
+/* out[r,c] = x[r,c]*rowmul[r] + scale[c]*y[r,c] (fp32): `pool_skip(x)*mask + drop_path_attn(adapter branch)` of a
+ * TransformerBlock that carries a parallel adapter (blocks.py:45-54, 564-567; meta_archs.py:139-148). */
+int vilco_scale_add(const float* x, const float* rowmul, const float* y, const float* scale, float* out, int64_t rows, int C,
+                    void* stream);
+
 /* layout changes at the boundary: (B,C,T) fp32 reference layout -> (B,T_out,C) bf16 token-major (zero padded), and
  * (B,T,C) fp32 -> (B,C,T) fp32.  (PtTransformer.preprocessing, MQ/libs/modeling/meta_archs.py:1134-1181) */
 int vilco_pack_feats(const float* x, void* y, int64_t y_lo, int B, int C, int T, int T_out, void* stream);

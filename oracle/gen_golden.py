@@ -22,6 +22,13 @@ def small_cfg():
                       n_txt_in=96, regression_range=[[0, 4], [2, 8], [4, 16], [8, 32], [16, 10000]])
 
 
+def vilco_cfg():
+    """small mq_vilco.yaml-like config: L2P prompts + temporal adapters (sized for T = 1024 by the reference) + EMA."""
+    return O.ModelCfg(input_dim=192, embd_dim=256, n_head=4, max_seq_len=1024, arch=(2, 2, 5), num_classes=6, n_txt_in=96,
+                      regression_range=[[0, 4], [2, 8], [4, 16], [8, 32], [16, 64], [32, 10000]],
+                      adapt_blocks=(0, 1, 2, 3, 4), n_emas=1, prompt_pool=dict(pool_size=10, top_k=4, length=20))
+
+
 def _override(c):
     def ov(cfg):
         cfg["dataset"]["input_dim"] = [c.input_dim]
@@ -35,13 +42,20 @@ def _override(c):
         m["fpn_dim"] = c.embd_dim
         m["head_dim"] = c.embd_dim
         m["n_txt_in"] = c.n_txt_in
+        if c.prompt_pool:
+            cfg["cl_cfg"].update(prompt_pool=True, pool_size=c.prompt_pool["pool_size"], topk=c.prompt_pool["top_k"],
+                                 length=c.prompt_pool["length"], embed_dim=c.n_txt_in)
+        if c.adapt_blocks:
+            cfg["cl_cfg"].update(use_adapt=True, adapt_blocks=list(c.adapt_blocks))
     return ov
 
 
-def build_reference_model(c, seed=0):
+def build_reference_model(c, seed=0, yaml_name="mq_no_cl.yaml"):
     """Reference PtTransformer at config `c`, loaded with oracle.params.random_state(seed)."""
     torch.manual_seed(0)
-    model, cfg = ref_shim.build_model(_override(c))
+    if yaml_name == "mq_vilco.yaml":
+        torch.Tensor.cuda = lambda self, *a, **k: self   # MemoryBank / contrastive loss call .cuda() (meta_archs.py:42)
+    model, cfg = ref_shim.build_model(_override(c), yaml_name)
     spec = PR.param_spec(c)
     sd = model.state_dict()
     for k, shp in spec.items():
@@ -83,6 +97,26 @@ def gen_model_golden():
     out = run_reference(c, model, videos)
     np.savez_compressed(os.path.join(GOLDEN, "model_small.npz"), **out)
     print("model_small:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
+def gen_vilco_golden():
+    """mq_vilco.yaml branches at inference: prompts prepended to the text, adapters on branch 0-4, EMA-adapter ensemble."""
+    c = vilco_cfg()
+    model, _ = build_reference_model(c, seed=1, yaml_name="mq_vilco.yaml")
+    videos = PR.synth_video_list(c, 1, seed=5, lens=[900], text_lens=[57], n_gt=[3])
+    out = {}
+    with torch.no_grad():
+        logits, offs, masks = model(videos, is_training=False, get_emb=True)
+        out["logits_0"] = torch.cat(logits, 1)[0].numpy()
+        out["offsets_0"] = torch.cat(offs, 1)[0].numpy()
+        # quirk: the EMA-ensemble loop re-binds fpn_masks to the un-squeezed (B,1,T_l) tensors (meta_archs.py:864)
+        out["mask_shape_l0"] = np.asarray(masks[0].shape)
+        out["masks_0"] = torch.cat([m.reshape(m.shape[0], -1) for m in masks], 1)[0].numpy()
+        res = model(videos, is_training=False)[0]
+        out["det_segments_0"], out["det_scores_0"], out["det_labels_0"] = (res[k].numpy() for k in ("segments", "scores", "labels"))
+    out["state_keys"] = np.array(list(model.state_dict().keys()))
+    np.savez_compressed(os.path.join(GOLDEN, "model_vilco.npz"), **out)
+    print("model_vilco:", {k: v.shape for k, v in out.items()})
 
 
 def gen_local_attn_golden():
@@ -157,3 +191,5 @@ if __name__ == "__main__":
         gen_local_attn_golden()
     if "model" in what:
         gen_model_golden()
+    if "vilco" in what:
+        gen_vilco_golden()

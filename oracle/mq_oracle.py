@@ -270,6 +270,8 @@ class ModelCfg:
         self.nms_sigma = 0.99
         self.duration_thresh = 0.01
         self.adapt_blocks = ()  # vilco: (0,1,2,3,4)
+        self.prompt_pool = None  # vilco: dict(pool_size=10, top_k=4, length=20)
+        self.n_emas = 0          # vilco: 1 (EMA copy of the adapters, ensembled at inference)
         for k, v in kw.items():
             assert hasattr(self, k), k
             setattr(self, k, v)
@@ -360,10 +362,39 @@ def points(cfg, lens):
     return out
 
 
+def prompt_prepend(P, cfg, text_bcl):
+    """Prompt.forward with prompt_mask None (evaluation) — MQ/libs/cl_methods/prompt.py:46-137 (embedding_key 'mean',
+    batchwise_prompt).  text (B, Ct, L) -> (B, Ct, top_k*length + L)."""
+    pp = cfg.prompt_pool
+    x = text_bcl.permute(0, 2, 1)
+    nrm = lambda v: v * torch.rsqrt(torch.maximum((v ** 2).sum(1, keepdim=True), torch.tensor(1e-12)))  # noqa: E731
+    sim = nrm(x.mean(dim=1)) @ nrm(P["prompt.prompt_key"]).t()
+    _, idx = torch.topk(sim, k=pp["top_k"], dim=1)
+    pid, cnt = torch.unique(idx, return_counts=True, sorted=True)
+    if pid.shape[0] < pp["pool_size"]:
+        pad = pp["pool_size"] - pid.shape[0]
+        pid = torch.cat([pid, torch.full((pad,), int(idx.min()))])
+        cnt = torch.cat([cnt, torch.zeros(pad, dtype=cnt.dtype)])
+    _, major = torch.topk(cnt, k=pp["top_k"])
+    idx = pid[major].expand(x.shape[0], -1)
+    bp = P["prompt.prompt"][idx].reshape(x.shape[0], -1, x.shape[2])
+    return torch.cat([bp, x], dim=1).permute(0, 2, 1)
+
+
 def forward_heads(P, cfg, feats_bct, mask_b1t, text=None, text_mask=None, training=False):
+    """backbone -> neck -> heads (+ the EMA-adapter ensemble of mq_vilco at inference, meta_archs.py:854-881)."""
+    out = _forward_heads_once(P, cfg, feats_bct, mask_b1t, text, text_mask, training, "pets.")
+    if not training and cfg.adapt_blocks:
+        for e in range(cfg.n_emas):
+            o2 = _forward_heads_once(P, cfg, feats_bct, mask_b1t, text, text_mask, training, f"pets_emas.{e}.module.")
+            out = ([(a + b) / 2 for a, b in zip(out[0], o2[0])], [(a + b) / 2 for a, b in zip(out[1], o2[1])], out[2], out[3])
+    return out
+
+
+def _forward_heads_once(P, cfg, feats_bct, mask_b1t, text=None, text_mask=None, training=False, pets_prefix="pets."):
     """backbone -> neck -> heads; returns lists permuted like meta_archs.py:848-852:
     logits (B,T_l,K), offsets (B,T_l,2), masks (B,T_l)."""
-    feats, masks = backbone(P, cfg, feats_bct, mask_b1t, text, text_mask, training)
+    feats, masks = backbone(P, cfg, feats_bct, mask_b1t, text, text_mask, training, pets_prefix)
     fpn, masks = fpn_identity(P, feats, masks)
     offs = reg_head(P, fpn, masks)
     logits = cls_head(P, fpn, masks)
@@ -663,7 +694,13 @@ def preprocess(cfg, video_list, training):
         for i, v in enumerate(video_list):
             text[i, :, :tl[i]] = v["prompt_feature"]
         tmask = (torch.arange(max(tl))[None, :] < torch.tensor(tl)[:, None]).unsqueeze(1)
+        if cfg.prompt_pool is not None and not training:  # meta_archs.py:759-780 (mask from the PRE-prompt lengths)
+            text = prompt_prepend(P_for_prompt[0], cfg, text)
+            tmask = (torch.arange(text.shape[-1])[None, :] < torch.tensor(tl)[:, None]).unsqueeze(1)
     return x, mask, text, tmask
+
+
+P_for_prompt = [None]  # set by model_infer (keeps preprocess' signature)
 
 
 def model_train_losses(P, cfg, video_list, loss_normalizer=None):
@@ -680,6 +717,7 @@ def model_infer(P, cfg, video_list, softnms_fn=None, return_raw=False):
     """PtTransformer.forward(is_training=False) — meta_archs.py:753-969, 1527-1736, one result dict per video."""
     results = []
     raw = []
+    P_for_prompt[0] = P
     for v in video_list:
         x, mask, text, tmask = preprocess(cfg, [v], False)
         logits, offs, masks, _ = forward_heads(P, cfg, x, mask, text, tmask, training=False)

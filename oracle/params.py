@@ -98,12 +98,18 @@ def param_spec(cfg):
     s["cls_head.cls_head.conv.bias"] = (K,)
     s["reg_head.offset_head.conv.weight"] = (2, C, 3)
     s["reg_head.offset_head.conv.bias"] = (2,)
+    prefixes = ["pets."] + [f"pets_emas.{e}.module." for e in range(getattr(cfg, "n_emas", 0))]
     for j, blk in enumerate(cfg.adapt_blocks):
         T = cfg.max_seq_len >> blk
-        s[f"pets.{j}.layer.0.weight"] = (5 * T, T)
-        s[f"pets.{j}.layer.0.bias"] = (5 * T,)
-        s[f"pets.{j}.layer.2.weight"] = (T // 2, 5 * T)
-        s[f"pets.{j}.layer.2.bias"] = (T // 2,)
+        for pre in prefixes:
+            s[f"{pre}{j}.layer.0.weight"] = (5 * T, T)
+            s[f"{pre}{j}.layer.0.bias"] = (5 * T,)
+            s[f"{pre}{j}.layer.2.weight"] = (T // 2, 5 * T)
+            s[f"{pre}{j}.layer.2.bias"] = (T // 2,)
+    if getattr(cfg, "prompt_pool", None):
+        pp = cfg.prompt_pool
+        s["prompt.prompt"] = (pp["pool_size"], pp["length"], cfg.n_txt_in)
+        s["prompt.prompt_key"] = (pp["pool_size"], cfg.n_txt_in)
     return s
 
 
@@ -137,6 +143,8 @@ def random_state(spec, seed=0):
             v = 1.0 + 0.3 * n
         elif last == "bias" or key.endswith("_bias"):
             v = 0.1 * n
+        elif key.startswith("prompt."):
+            v = 0.5 * n
         elif "rel_attn." in key:  # (C,H,d) einsum weights: fan_in = C
             v = n / np.sqrt(shape[0])
         else:  # conv (out,in,k) / linear (out,in)

@@ -128,3 +128,29 @@ def test_full_size_blocks_vs_oracle():
     assert rel_max(g2.cpu().transpose(1, 2), o2) < TOL
     assert rel_max(g3.cpu().transpose(1, 2), o3) < TOL
     assert (gm.cpu().bool() == m3.squeeze(1)).all()
+
+
+def test_vilco_config_vs_reference_golden():
+    """the flagship mq_vilco.yaml inference path: prompts prepended to the text (mask from pre-prompt lengths), temporal
+    adapters on branch 0-4, EMA-adapter ensemble (shared trunk computed once) — against the reference's own output."""
+    from oracle import params as PR
+    from oracle.gen_golden import vilco_cfg
+    from util import build_vilco_pair
+    g = np.load(os.path.join(GOLDEN, "model_vilco.npz"))
+    cfg = vilco_cfg()
+    model, P = build_vilco_pair(cfg)
+    assert list(model.state_dict().keys()) == list(g["state_keys"])
+    videos = PR.synth_video_list(cfg, 1, seed=5, lens=[900], text_lens=[57], n_gt=[3])
+    cls_l, off_l, msk_l = model(videos, is_training=False, get_emb=True)
+    assert tuple(msk_l[0].shape) == tuple(g["mask_shape_l0"])
+    assert rel_max(torch.cat(cls_l, 1)[0].cpu().numpy(), g["logits_0"]) < TOL
+    assert rel_max(torch.cat(off_l, 1)[0].cpu().numpy(), g["offsets_0"]) < TOL
+    res = model(videos, is_training=False)[0]
+    assert np.abs(res["scores"].numpy() - g["det_scores_0"]).max() < 1e-5
+    # a batch of two clips equals two single-clip runs (prompts are selected per clip in batched evaluation)
+    v2 = PR.synth_video_list(cfg, 2, seed=6, lens=[1024, 700], text_lens=[33, 80], n_gt=[2, 2])
+    a = model(v2, is_training=False, get_emb=True)
+    b0 = model(v2[:1], is_training=False, get_emb=True)
+    b1 = model(v2[1:], is_training=False, get_emb=True)
+    assert rel_max(torch.cat(a[0], 1)[0].cpu(), torch.cat(b0[0], 1)[0].cpu()) < 1e-4
+    assert rel_max(torch.cat(a[0], 1)[1].cpu(), torch.cat(b1[0], 1)[0].cpu()) < 1e-4

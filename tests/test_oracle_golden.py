@@ -113,3 +113,17 @@ def test_batched_nms_restatement():
     assert (s.numpy() == g["b_out_segs"]).all()
     assert (sc.numpy() == g["b_out_scores"]).all()
     assert (lb.numpy() == g["b_out_labels"]).all()
+
+
+def test_vilco_config_oracle_vs_reference_golden():
+    """mq_vilco.yaml branches at inference (L2P prompts, adapters, EMA-adapter ensemble) — golden from the reference."""
+    from oracle.gen_golden import vilco_cfg
+    g = np.load(os.path.join(GOLDEN, "model_vilco.npz"))
+    c = vilco_cfg()
+    P = PR.random_state(PR.param_spec(c), 1)
+    videos = PR.synth_video_list(c, 1, seed=5, lens=[900], text_lens=[57], n_gt=[3])
+    with torch.no_grad():
+        res, raw = O.model_infer(P, c, videos, return_raw=True)
+    assert _rel(torch.cat(raw[0][0], 1)[0].numpy(), g["logits_0"]) < 2e-5
+    assert _rel(torch.cat(raw[0][1], 1)[0].numpy(), g["offsets_0"]) < 2e-5
+    assert np.abs(res[0]["scores"].numpy() - g["det_scores_0"]).max() < 1e-5

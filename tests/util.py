@@ -23,3 +23,20 @@ def build_pair(cfg, seed=0):
     missing, unexpected = model.load_state_dict(P, strict=False)
     assert not unexpected
     return model.cuda().eval(), P
+
+
+def build_vilco_pair(cfg, seed=1):
+    """mq_vilco.yaml-like model (L2P prompts, temporal adapters + EMA copy) with seeded weights."""
+    from oracle import params as PR
+    from vilco_b200.config import mq_model_kwargs
+    from vilco_b200.modeling import make_meta_arch
+    P = PR.random_state(PR.param_spec(cfg), seed)
+    kw = mq_model_kwargs(cfg.input_dim, cfg.embd_dim, cfg.n_head, cfg.max_seq_len, cfg.arch, cfg.num_classes, cfg.n_txt_in,
+                         cfg.regression_range)
+    kw["cl_cfg"].update(name="l2p", memory_size=1010, prompt_pool=True, pool_size=cfg.prompt_pool["pool_size"],
+                        topk=cfg.prompt_pool["top_k"], length=cfg.prompt_pool["length"], embed_dim=cfg.n_txt_in,
+                        narration_ssl=True, use_adapt=True, adapt_blocks=list(cfg.adapt_blocks))
+    model = make_meta_arch("LocPointTransformer", **kw)
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected
+    return model.cuda().eval(), P

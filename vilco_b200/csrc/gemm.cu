@@ -893,7 +893,12 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   if (g->b_major == 1) BN = 64;
   else if (g->N <= 32) BN = 32;
   else if (g->N <= 64) BN = 64;
-  else BN = 128;
+  else {
+    // small problems (text stem, deep pyramid levels): 128x64 tiles double the number of CTAs when 128x128 tiles
+    // would leave most of the 148 SMs idle
+    const long long t128 = (long long)((g->N + 127) / 128) * ((g->M + BM - 1) / BM) * Z;
+    BN = (t128 * 2 <= num_sms()) ? 64 : 128;
+  }
 
   CUtensorMap tmA, tmB;
   int sa[3], sb[3];

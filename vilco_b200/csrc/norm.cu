@@ -209,6 +209,21 @@ __global__ void axpby_kernel(const float* __restrict__ x, const float* __restric
   }
 }
 
+// out[r, c] = x[r, c] * rowmul[r] + scale[c] * y[r, c]   (skip * mask + AffineDropPath-scale * adapter branch)
+__global__ void scale_add_kernel(const float* __restrict__ x, const float* __restrict__ rowmul, const float* __restrict__ y,
+                                 const float* __restrict__ scale, float* __restrict__ out, long long rows, int C) {
+  const long long n4 = rows * (C / 4);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (C / 4);
+    const int c = static_cast<int>(i % (C / 4)) * 4;
+    const float rm = rowmul ? rowmul[r] : 1.0f;
+    const float4 a = ld4(x + 4 * i), b = ld4(y + 4 * i);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (scale) sc = ld4(scale + c);
+    st4(out + 4 * i, make_float4(a.x * rm + sc.x * b.x, a.y * rm + sc.y * b.y, a.z * rm + sc.z * b.z, a.w * rm + sc.w * b.w));
+  }
+}
+
 // (B, C, T) fp32 channel-major (the reference layout) -> (B, T, C) bf16 token-major, zero padded to T_out rows
 __global__ void pack_feats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long y_lo, int C, int T,
                                   int T_out) {
@@ -331,6 +346,14 @@ extern "C" int vilco_unpack(const float* x, float* y, int B, int T, int C, void*
   VILCO_CHECK_ARG(x && y && B > 0 && C > 0 && T > 0, "vilco_unpack: bad arguments");
   dim3 grid((C + 31) / 32, (T + 31) / 32, B);
   unpack_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(x, y, T, C);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_scale_add(const float* x, const float* rowmul, const float* y, const float* scale, float* out,
+                               int64_t rows, int C, void* stream) {
+  VILCO_CHECK_ARG(x && y && out && rows > 0 && C % 4 == 0, "vilco_scale_add: bad arguments");
+  scale_add_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rowmul, y, scale, out, rows, C);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

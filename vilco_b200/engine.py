@@ -29,8 +29,8 @@ def pack_weights(sd, device):
     for k, v in sd.items():
         if not torch.is_floating_point(v):
             continue
-        if k.startswith("backbone.xlnet.word_embedding") or k.startswith("pets_emas."):
-            continue
+        if k.startswith("backbone.xlnet.word_embedding") or ".adapters." in k:
+            continue  # dead embedding table; adapters are packed once under their pets.* / pets_emas.* names
         v = v.detach().to(device=device, dtype=f32)
         last = k.rsplit(".", 1)[-1]
         if ".rel_attn." in k and last in ("q", "k", "v", "r"):
@@ -123,14 +123,14 @@ def channel_block_fwd(W, pre, ln1_32, ln1_16, H, tlen=None):
 
 
 def adapter_fwd(W, pre, ln1_32):
-    """meta_archs.Adapter.layer: Linear over the TIME axis of (B,C,T) — meta_archs.py:105-148.  ln1_32 (B,T,C) fp32
-    -> (B,T/2,C) fp32.  Small (T x 5T x T/2 per channel): expressed as two GEMMs over the transposed activations."""
+    """meta_archs.Adapter.layer: Linear over the TIME axis of (B,C,T): T -> 5T -> T/2 with GELU — meta_archs.py:105-148.
+    ln1_32 (B,T,C) fp32 -> (B,T/2,C) fp32.  Two GEMMs over the transposed activations (rows = B*C, K = T)."""
     B, T, C = ln1_32.shape
-    xt = ops.unpack(ln1_32)  # (B,C,T) fp32
-    x16 = ops.split16(xt)  # dtype cast only (torch used as memory plumbing)
+    xt = ops.unpack(ln1_32)                                         # (B,C,T) fp32
+    _, x16 = ops.axpby(xt, None, 1.0, 0.0, out32=False, out16=True)  # operand planes
     h = ops.linear(x16, W[pre + "layer.0.weight"], bf16, bias=W[pre + "layer.0.bias"], act=ACT_GELU)
     o = ops.linear(h, W[pre + "layer.2.weight"], f32, bias=W[pre + "layer.2.bias"])  # (B,C,T/2)
-    return o.transpose(1, 2).contiguous()
+    return ops.unpack(o)                                            # (B,T/2,C): the same transpose kernel
 
 
 def transformer_block_fwd(W, pre, x32, mask, H, stride, cross=None, t_c_alpha=0.8, window=-1, adapter_pre=None,
@@ -144,11 +144,11 @@ def transformer_block_fwd(W, pre, x32, mask, H, stride, cross=None, t_c_alpha=0.
     skip = x32 if stride == 1 else ops.maxpool3s2(x32)
     sa, sm = W.get(pre + "drop_path_attn.scale"), W.get(pre + "drop_path_mlp.scale")
     if adapter_pre is not None:
-        # out = (attn(ln1 x) + adapter(ln1 x)); adapter output is not masked (meta_archs.py:143-147)
+        # out = attn(ln1 x) + adapter(ln1 x) (adapter output is not masked, meta_archs.py:143-147);
+        # h = skip*mask + sa*out = [skip*mask + sa*adapter] + sa*((proj(o)+b)*mask)
         ad = adapter_fwd(W, adapter_pre, ln1_32)
-        base = ops.linear(o, W[pre + "attn.proj.weight"], f32, bias=W[pre + "attn.proj.bias"], rowmul=om, resid=ad)
-        # h = skip*mask + sa * base
-        h = _scale_add(base, sa, skip, om)
+        r = ops.scale_add(skip, om, ad, sa)
+        h = ops.linear(o, W[pre + "attn.proj.weight"], f32, bias=W[pre + "attn.proj.bias"], rowmul=om, colscale=sa, resid=r)
     else:
         # h = skip*mask + sa * ((proj(o) + b) * mask)      (blocks.py:404-405, 567)
         h = ops.linear(o, W[pre + "attn.proj.weight"], f32, bias=W[pre + "attn.proj.bias"], rowmul=om, colscale=sa,
@@ -170,13 +170,6 @@ def transformer_block_fwd(W, pre, x32, mask, H, stride, cross=None, t_c_alpha=0.
     elif want16:
         _, out16 = ops.axpby(out, None, 1.0, 0.0, out32=False, out16=True)
     return (out, omask, out16) if want16 else (out, omask)
-
-
-def _scale_add(base, scale, skip, om):
-    """h = skip * mask + scale[c] * base  (rare adapter path; composed from the axpby kernel per term)."""
-    B, T, C = base.shape
-    s = base * scale if scale is not None else base  # TODO(kernel): fold into the proj epilogue (second resid)
-    return skip * om.view(B, T, 1) + s
 
 
 def xlnet_layer_fwd(W, pre, x32, x16, mask, H, eps=1e-12):
@@ -213,7 +206,8 @@ def xlnet_layer_fwd(W, pre, x32, x16, mask, H, eps=1e-12):
     return h2
 
 
-def backbone_fwd(W, cfg, x16, mask, text16=None, tmask=None, pe=None, pets_prefix="pets.", text_lens=None):
+def backbone_fwd(W, cfg, x16, mask, text16=None, tmask=None, pe=None, pets_prefix="pets.", text_lens=None,
+                 trunk_only=False):
     """ConvTransformerBackbone.forward — MQ/libs/modeling/backbones.py:181-289.
     x16 (B,T,Cin) bf16, mask (B,T) fp32, text16 (B,L,Ct) bf16, tmask (B,L) fp32.  Returns (feats fp32 list, masks).
     text_lens (B,) int32 or None: when given, every text sequence is treated as if it had been run alone (un-padded),
@@ -251,15 +245,27 @@ def backbone_fwd(W, cfg, x16, mask, text16=None, tmask=None, pe=None, pets_prefi
         x32 = r[0]
         if want16:
             x16s = r[2]
-    feats, masks = [x32], [mask]
+    feat0 = x32
+    if cfg.use_xl and cfg.arch[2] > 0:
+        if x16s is None:
+            _, x16s = ops.axpby(x32, None, 1.0, 0.0, out32=False, out16=True)
+        x32 = xlnet_layer_fwd(W, pre + "xlnet.layer.0.", x32, x16s, mask, H)
+    trunk = (feat0, x32, mask, cross)
+    if trunk_only:
+        return trunk
+    return branch_fwd(W, cfg, trunk, pets_prefix)
+
+
+def branch_fwd(W, cfg, trunk, pets_prefix="pets."):
+    """The strided branch of the backbone (backbones.py:266-286) on top of the shared trunk (embedding, text path, stem,
+    XLNet).  Adapters (`pets_prefix`) only live here, so the EMA-adapter ensemble of mq_vilco re-runs just this part."""
+    pre = "backbone."
+    feat0, x32, mask, cross = trunk
+    feats, masks = [feat0], [mask]
     for i in range(cfg.arch[2]):
-        if cfg.use_xl and i == 0:
-            if x16s is None:
-                _, x16s = ops.axpby(x32, None, 1.0, 0.0, out32=False, out16=True)
-            x32 = xlnet_layer_fwd(W, pre + "xlnet.layer.0.", x32, x16s, mask, H)
         cr = None if i in (1, 2) else cross
-        ad = (pets_prefix + f"{cfg.adapt_blocks.index(i)}.") if i in cfg.adapt_blocks else None
-        x32, mask = transformer_block_fwd(W, pre + f"branch.{i}.", x32, mask, H, cfg.scale_factor, cross=cr,
+        ad = (pets_prefix + f"{list(cfg.adapt_blocks).index(i)}.") if i in cfg.adapt_blocks else None
+        x32, mask = transformer_block_fwd(W, pre + f"branch.{i}.", x32, mask, cfg.n_head, cfg.scale_factor, cross=cr,
                                           t_c_alpha=cfg.t_c_alpha, adapter_pre=ad)
         feats.append(x32)
         masks.append(mask)

@@ -34,6 +34,83 @@ class BiasLayer(nn.Module):
         print(i, self.alpha.item(), self.beta.item())
 
 
+class Adapter(nn.Module):
+    """Temporal adapter ("pet"): Linear over the TIME axis T -> 5T -> T/2 with GELU, run in parallel to the attention of a
+    branch block (reference: meta_archs.py:105-148).  Parameter container; the math runs in engine.adapter_fwd."""
+
+    def __init__(self, embed_dim, down_sample=5, mode="parallel", scale=None, act_layer=nn.GELU, stride=1):
+        super().__init__()
+        assert mode == "parallel"
+        hidden_dim = int(embed_dim * down_sample)
+        self.layer = nn.Sequential(nn.Linear(embed_dim, hidden_dim), act_layer(), nn.Linear(hidden_dim, embed_dim // 2))
+        self.mode = mode
+        nn.init.kaiming_uniform_(self.layer[0].weight, a=math.sqrt(5))
+        nn.init.zeros_(self.layer[0].bias)
+        nn.init.zeros_(self.layer[2].weight)
+        nn.init.zeros_(self.layer[2].bias)
+
+
+class ModelEmaV2(nn.Module):
+    """EMA copy of a module tree over its state_dict (timm.utils.model_ema.ModelEmaV2 semantics, used for the adapter
+    EMA of mq_vilco: meta_archs.py:664-712)."""
+
+    def __init__(self, model, decay=0.9999, device=None):
+        super().__init__()
+        import copy
+        self.module = copy.deepcopy(model)
+        self.module.eval()
+        self.decay = decay
+
+    @torch.no_grad()
+    def update(self, model):
+        for e, m in zip(self.module.state_dict().values(), model.state_dict().values()):
+            e.copy_(self.decay * e + (1.0 - self.decay) * m)
+
+
+class Prompt(nn.Module):
+    """L2P prompt pool (reference: MQ/libs/cl_methods/prompt.py:4-137, the configuration mq_vilco uses: embedding_key
+    'mean', uniform init, learnable keys, batchwise_prompt).  Selection is a handful of tiny host-driven torch ops on
+    (B, 768) tensors — CL-method glue, not a hot kernel."""
+
+    def __init__(self, length=5, embed_dim=768, pool_size=None, top_k=None, batchwise_prompt=True):
+        super().__init__()
+        self.length, self.embed_dim, self.pool_size, self.top_k = length, embed_dim, pool_size, top_k
+        self.batchwise_prompt = batchwise_prompt
+        self.prompt = nn.Parameter(torch.empty(pool_size, length, embed_dim).uniform_(-1, 1))
+        self.prompt_key = nn.Parameter(torch.empty(pool_size, embed_dim).uniform_(-1, 1))
+
+    @staticmethod
+    def l2_normalize(x, dim=None, epsilon=1e-12):
+        sq = torch.sum(x ** 2, dim=dim, keepdim=True)
+        return x * torch.rsqrt(torch.maximum(sq, torch.tensor(epsilon, device=x.device)))
+
+    def forward(self, x_embed, prompt_mask=None, cls_features=None):
+        """x_embed (B, L, C) -> dict with 'prompted_embedding' (B, top_k*length + L, C), 'reduce_sim', ..."""
+        out = {}
+        x_mean = torch.mean(x_embed, dim=1)
+        prompt_norm = self.l2_normalize(self.prompt_key, dim=1)
+        x_norm = self.l2_normalize(x_mean, dim=1)
+        similarity = torch.matmul(x_norm, prompt_norm.t())
+        if prompt_mask is None:
+            _, idx = torch.topk(similarity, k=self.top_k, dim=1)
+            if self.batchwise_prompt:
+                prompt_id, id_counts = torch.unique(idx, return_counts=True, sorted=True)
+                if prompt_id.shape[0] < self.pool_size:
+                    pad = self.pool_size - prompt_id.shape[0]
+                    prompt_id = torch.cat([prompt_id, torch.full((pad,), torch.min(idx.flatten()), device=prompt_id.device)])
+                    id_counts = torch.cat([id_counts, torch.full((pad,), 0, device=id_counts.device)])
+                _, major_idx = torch.topk(id_counts, k=self.top_k)
+                idx = prompt_id[major_idx].expand(x_embed.shape[0], -1)
+        else:
+            idx = prompt_mask
+        batched_prompt = self.prompt[idx].reshape(x_embed.shape[0], -1, x_embed.shape[2])
+        out["prompt_idx"], out["similarity"] = idx, similarity
+        out["reduce_sim"] = torch.sum(prompt_norm[idx] * x_norm.unsqueeze(1)) / x_embed.shape[0]
+        out["total_prompt_len"] = batched_prompt.shape[1]
+        out["prompted_embedding"] = torch.cat([batched_prompt, x_embed], dim=1)
+        return out
+
+
 class _Head(nn.Module):
     def __init__(self, input_dim, feat_dim, num_layers, kernel_size, with_ln):
         super().__init__()
@@ -162,11 +239,29 @@ class PtTransformer(nn.Module):
         self.n_known = 0
         self.list_bias_layers, self.list_splits = [], []
         self.prompt_pool = cl_cfg["prompt_pool"]
+        self.use_prompt_mask = True
+        if cl_cfg["length"] is not None and cl_cfg["pool_size"] is not None and self.prompt_pool:   # meta_archs.py:634-648
+            self.prompt = Prompt(length=cl_cfg["length"], embed_dim=cl_cfg["embed_dim"], pool_size=cl_cfg["pool_size"],
+                                 top_k=cl_cfg["topk"], batchwise_prompt=True)
         self.narration_ssl = cl_cfg["narration_ssl"]
+        self.narration_dim = cl_cfg["narration_dim"]
+        if self.narration_ssl:   # training-only branch; the parameters exist so checkpoints load (meta_archs.py:650-655)
+            self.narration_encoder = nn.Linear(cl_cfg["narration_dim"], 1024)
+        self.ssl_factor = cl_cfg["ssl_factor"]
+        self.num_emas, self.ema_decay = 1, 0.999
         self.use_adapt = cl_cfg["use_adapt"]
-        if self.prompt_pool or self.narration_ssl or self.use_adapt:
-            raise NotImplementedError("the L2P prompt pool / narration SSL / adapter (mq_vilco.yaml) branches are not "
-                                      "built yet; use the mq_no_cl / icarl / bic / ewc / mas configs")
+        self.adapt_blocks = tuple(cl_cfg["adapt_blocks"]) if self.use_adapt else ()
+        if self.use_adapt:       # meta_archs.py:657-700
+            assert max_seq_len == 1024, "the reference sizes the temporal adapters for T = 1024 (meta_archs.py:687)"
+            self.num_freeze_epochs = 10
+            self.pets_emas = nn.ModuleList([])
+            pets, dim = nn.ModuleList([]), 1024
+            for _ in self.adapt_blocks:
+                pets.append(Adapter(embed_dim=dim, down_sample=5, mode="parallel", scale="null"))
+                dim //= 2
+            self.pets = pets
+            self.pets_emas.append(ModelEmaV2(self.pets, decay=self.ema_decay))
+            self.attach_pets(self.pets)
         self._packed = None
         self._packed_key = None
         self._pe = None
@@ -176,11 +271,23 @@ class PtTransformer(nn.Module):
     def device(self):
         return list(set(p.device for p in self.parameters()))[0]
 
+    def attach_pets(self, pets):
+        """register the adapters under backbone.branch.<b>.adapters.attn like AdapterMixin.attach_adapter (blocks.py:28-33)"""
+        for i, b in enumerate(self.adapt_blocks):
+            blk = self.backbone.branch[b]
+            if not isinstance(getattr(blk, "adapters", None), nn.ModuleDict):
+                blk.adapters = nn.ModuleDict()
+            blk.adapters["attn"] = pets[i]
+
     def pre_train_epoch(self, task_id=0, current_epoch=0):
-        pass
+        if self.use_adapt:
+            for prm in self.pets.parameters():
+                prm.requires_grad_(True)
 
     def post_train_step(self):
-        pass
+        if self.use_adapt:   # meta_archs.py:702-707
+            for idx, ema in enumerate(reversed(self.pets_emas)):
+                ema.update(self.pets if idx == 0 else self.pets_emas[idx - 1])
 
     def augment_classification(self, num_new_classes, device):
         """Grow the classifier and the per-class gaussian parameters (reference: meta_archs.py:715-751)."""
@@ -200,7 +307,7 @@ class PtTransformer(nn.Module):
         c = _Cfg()
         c.embd_dim, c.n_head, c.arch, c.scale_factor = self.embd_dim, self.n_head, self.backbone_arch, self.scale_factor
         c.use_cross_modal, c.use_xl, c.t_c_alpha, c.max_seq_len = self.use_cross_modal, self.use_xl, self.t_c_alpha, self.max_seq_len
-        c.adapt_blocks = ()
+        c.adapt_blocks = tuple(self.adapt_blocks)
         return c
 
     def packed_weights(self):
@@ -271,15 +378,62 @@ class PtTransformer(nn.Module):
         t16 = ops.pack_feats(text) if text is not None else None
         # evaluation: the reference runs one clip at a time, so its text is never padded; a batched evaluation must
         # therefore treat every text as un-padded (text_lens).  Training reproduces the reference's padded batch.
-        feats, masks = E.backbone_fwd(W, cfg, x16, mask, t16, tmask, self._pe, text_lens=None if is_training else tlens)
-        return E.neck_heads_fwd(W, cfg, feats, masks)
+        trunk = E.backbone_fwd(W, cfg, x16, mask, t16, tmask, self._pe, text_lens=None if is_training else tlens,
+                               trunk_only=True)
+        feats, masks = E.branch_fwd(W, cfg, trunk, "pets.")
+        logits, offsets, pmask, pyr = E.neck_heads_fwd(W, cfg, feats, masks)
+        if not is_training and self.use_adapt:
+            # EMA-adapter ensemble (meta_archs.py:854-881): the reference re-runs the whole network with the EMA copy
+            # of the adapters and averages logits / offsets; only the strided branch depends on the adapters, so the
+            # shared trunk (embedding, text path, stem, XLNet) is computed once here.
+            for e in range(len(self.pets_emas)):
+                f2, m2 = E.branch_fwd(W, cfg, trunk, f"pets_emas.{e}.module.")
+                l2, o2, _, _ = E.neck_heads_fwd(W, cfg, f2, m2, pyr)
+                logits, _ = ops.axpby(logits, l2, 0.5, 0.5)
+                offsets, _ = ops.axpby(offsets, o2, 0.5, 0.5)
+        return logits, offsets, pmask, pyr
+
+    def _prompted_text(self, text, tlens, is_training, task_id):
+        """L2P prompts prepended to the text tokens (meta_archs.py:759-780).  text (B, Ct, L) on the device.
+        Returns (text', mask', lens', reduce_sim): the mask keeps the reference's quirk of being computed from the
+        PRE-prompt lengths over the prompted sequence."""
+        x = text.permute(0, 2, 1)
+        prompt_mask = None
+        if is_training:
+            start, end = task_id * self.prompt.top_k, (task_id + 1) * self.prompt.top_k
+            if end <= self.prompt.pool_size:
+                prompt_mask = torch.arange(start, end, device=x.device).unsqueeze(0).expand(x.shape[0], -1)
+        res = self.prompt(x, prompt_mask=prompt_mask, cls_features=None)
+        self.total_prompt_len = res["total_prompt_len"]
+        text2 = res["prompted_embedding"].permute(0, 2, 1).contiguous()
+        L2 = text2.shape[-1]
+        mask2 = (torch.arange(L2, device=x.device)[None, :] < tlens[:, None]).float()
+        lens2 = (tlens + self.total_prompt_len).to(torch.int32)   # tensor extent of every prompted text
+        return text2, mask2, lens2, res["reduce_sim"]
 
     @torch.no_grad()
-    def _network(self, video_list, is_training):
+    def _network(self, video_list, is_training, task_id=-1):
         vl, batched, mask = self.preprocessing(video_list, is_training)
         text, tmask, tlens = None, None, None
+        self._reduce_sim = None
         if self.use_cross_modal:
-            text, tmask, tlens = self.query_preprocessing(vl if is_training else video_list)
+            src = vl if is_training else video_list
+            text, tmask, tlens = self.query_preprocessing(src)
+            if hasattr(self, "prompt"):
+                if not is_training and len(src) > 1 and len(set(int(v) for v in tlens.tolist())) > 1:
+                    # batchwise prompt selection + zero-padded means depend on the batch composition: keep the
+                    # reference's one-clip-at-a-time result by selecting prompts per clip
+                    parts = [self._prompted_text(text[i:i + 1, :, :int(tlens[i])], tlens[i:i + 1], False, task_id)
+                             for i in range(len(src))]
+                    L2 = max(p_[0].shape[-1] for p_ in parts)
+                    text = torch.zeros(len(src), text.shape[1], L2, device=text.device)
+                    tmask = torch.zeros(len(src), L2, device=text.device)
+                    for i, p_ in enumerate(parts):
+                        text[i, :, :p_[0].shape[-1]] = p_[0][0]
+                        tmask[i, :p_[1].shape[-1]] = p_[1][0]
+                    tlens = torch.cat([p_[2] for p_ in parts])
+                else:
+                    text, tmask, tlens, self._reduce_sim = self._prompted_text(text, tlens, is_training, task_id)
             text = text.contiguous()
         logits, offsets, pmask, pyr = self._device_forward(batched, mask.contiguous(), text, tmask, tlens, is_training)
         return vl, logits, offsets, pmask, pyr
@@ -295,7 +449,7 @@ class PtTransformer(nn.Module):
                 prev_out_cls_logits=None, get_emb=False, val_qilDatasetList=None):
         if not is_training and not get_emb:
             assert len(video_list) >= 1
-        vl, logits, offsets, pmask, pyr = self._network(video_list, is_training)
+        vl, logits, offsets, pmask, pyr = self._network(video_list, is_training, task_id)
         if self.n_known > 0 and self.cl_name == "bic":  # BiasLayer on class slices (meta_archs.py:823-836)
             parts, lo_ = [], 0
             for i, hi_ in enumerate(self.list_splits):
@@ -306,6 +460,9 @@ class PtTransformer(nn.Module):
             cls_l = [logits[:, o:o + n] for o, n in zip(pyr.off, pyr.lens)]
             off_l = [offsets[:, o:o + n] for o, n in zip(pyr.off, pyr.lens)]
             msk_l = [pmask[:, o:o + n].bool() for o, n in zip(pyr.off, pyr.lens)]
+            if not is_training and self.use_adapt:
+                # reference quirk: its EMA-ensemble loop re-binds fpn_masks to the un-squeezed (B,1,T_l) tensors (:864)
+                msk_l = [m_.unsqueeze(1) for m_ in msk_l]
             return cls_l, off_l, msk_l
         if is_training:
             return self.losses(vl, logits, offsets, pmask, pyr, prev_out_cls_logits)
@@ -406,8 +563,21 @@ class PtTransformer(nn.Module):
             FltArr(*[float(s) for s in self.fpn_strides]), C.c_float(self.test_pre_nms_thresh),
             C.c_float(self.test_duration_thresh), topk, ops._p(cand_segs), ops._p(cand_scores), ops._p(cand_labels),
             ops._p(cand_count), L.stream_ptr()), "vilco_decode")
-        if self.test_nms_method == "none":
-            raise NotImplementedError("nms_method 'none' is not built yet")
+        if self.test_nms_method == "none":   # no NMS: every decoded candidate, level-major (meta_archs.py:1711)
+            cnt = cand_count.cpu()
+            M = int(cnt.sum(1).max())
+            segs = torch.zeros(B, max(M, 1), 2, device=dev)
+            scores = torch.zeros(B, max(M, 1), device=dev)
+            labels = torch.zeros(B, max(M, 1), device=dev, dtype=torch.int64)
+            for b in range(B):
+                o = 0
+                for l in range(nl):
+                    n = int(cnt[b, l])
+                    segs[b, o:o + n] = cand_segs[b, l * topk:l * topk + n]
+                    scores[b, o:o + n] = cand_scores[b, l * topk:l * topk + n]
+                    labels[b, o:o + n] = cand_labels[b, l * topk:l * topk + n].long()
+                    o += n
+            return segs, scores, labels, cnt.sum(1).int().to(dev)
         if not self.test_multiclass_nms and self.test_voting_thresh > 0:
             raise NotImplementedError("class-agnostic NMS with segment voting is not built yet")
         method = 2 if self.test_nms_method == "soft" else 3

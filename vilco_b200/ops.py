@@ -182,6 +182,15 @@ def axpby(x, y=None, a=1.0, b=0.0, out32=True, out16=False):
     return o32, o16
 
 
+def scale_add(x, rowmul, y, scale):
+    """x * rowmul[row] + scale[c] * y on fp32 (B,T,C) tensors."""
+    out = torch.empty_like(x)
+    Cc = x.shape[-1]
+    L.check(L.lib().vilco_scale_add(_p(x), _p(rowmul), _p(y), _p(scale), _p(out), _i64(x.numel() // Cc), Cc,
+                                    L.stream_ptr()), "vilco_scale_add")
+    return out
+
+
 def pack_feats(x, T_out=None):
     """(B, C, T) fp32 (reference layout) -> operand (NP, B, T_out, C)."""
     assert x.dtype == f32 and x.is_contiguous()
