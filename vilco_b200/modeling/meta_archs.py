@@ -87,8 +87,12 @@ class Prompt(nn.Module):
     def forward(self, x_embed, prompt_mask=None, cls_features=None):
         """x_embed (B, L, C) -> dict with 'prompted_embedding' (B, top_k*length + L, C), 'reduce_sim', ..."""
         out = {}
-        x_mean = torch.mean(x_embed, dim=1)
-        prompt_norm = self.l2_normalize(self.prompt_key, dim=1)
+        dev = x_embed.device
+        # the selection runs on the host in fp32: it is a (B, pool) problem whose top-k ties (every id appears once for a
+        # single clip) are broken by the sort implementation — the CPU order is the one the reference's CPU path and the
+        # golden vectors use
+        x_mean = torch.mean(x_embed.detach().float().cpu(), dim=1)
+        prompt_norm = self.l2_normalize(self.prompt_key.detach().float().cpu(), dim=1)
         x_norm = self.l2_normalize(x_mean, dim=1)
         similarity = torch.matmul(x_norm, prompt_norm.t())
         if prompt_mask is None:
@@ -97,12 +101,13 @@ class Prompt(nn.Module):
                 prompt_id, id_counts = torch.unique(idx, return_counts=True, sorted=True)
                 if prompt_id.shape[0] < self.pool_size:
                     pad = self.pool_size - prompt_id.shape[0]
-                    prompt_id = torch.cat([prompt_id, torch.full((pad,), torch.min(idx.flatten()), device=prompt_id.device)])
-                    id_counts = torch.cat([id_counts, torch.full((pad,), 0, device=id_counts.device)])
+                    prompt_id = torch.cat([prompt_id, torch.full((pad,), int(torch.min(idx.flatten())))])
+                    id_counts = torch.cat([id_counts, torch.full((pad,), 0)])
                 _, major_idx = torch.topk(id_counts, k=self.top_k)
                 idx = prompt_id[major_idx].expand(x_embed.shape[0], -1)
         else:
-            idx = prompt_mask
+            idx = prompt_mask.cpu()
+        prompt_norm, x_norm, similarity, idx = prompt_norm.to(dev), x_norm.to(dev), similarity.to(dev), idx.to(dev)
         batched_prompt = self.prompt[idx].reshape(x_embed.shape[0], -1, x_embed.shape[2])
         out["prompt_idx"], out["similarity"] = idx, similarity
         out["reduce_sim"] = torch.sum(prompt_norm[idx] * x_norm.unsqueeze(1)) / x_embed.shape[0]
@@ -619,6 +624,8 @@ class EvalGraph:
 
     def __init__(self, model, batch_size, text_len=128):
         self.model, self.B, self.Lt = model, batch_size, text_len
+        if hasattr(model, "prompt"):
+            raise NotImplementedError("EvalGraph: the host-side L2P prompt selection is not capturable; use model(video_list)")
         dev = model.device
         T, Cin, Ct = model.max_seq_len, model.input_dim, model.n_txt_in
         self.feats = torch.zeros(batch_size, Cin, T, device=dev)
