@@ -77,6 +77,7 @@ typedef struct VilcoGemm {
   const float* colscale;
   const float* resid; int32_t resid_masked;
   int32_t impl;
+  int32_t band_lo, band_hi;   /* band_hi > band_lo: only outputs with band_lo <= m + n < band_hi are computed (others untouched) */
 } VilcoGemm;
 
 int vilco_gemm(const VilcoGemm* g, void* stream);

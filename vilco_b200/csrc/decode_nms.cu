@@ -290,7 +290,7 @@ __global__ void class_count_kernel(const NmsParams p, int* class_count) {
   }
 }
 
-static constexpr int NMS_SMEM_CAP = 4096;  // candidates of one class held in shared memory (6 arrays x 16 KB)
+static constexpr int NMS_SMEM_CAP = 2048;  // candidates of one class held in shared memory (6 arrays x 8 KB -> 4 CTAs/SM)
 
 struct ArgMax { float v; int pos; };
 __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {  // first maximum wins (nms_cpu.cpp:95-101)
@@ -300,7 +300,7 @@ __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {  // first maximum
   return a;
 }
 
-__global__ void __launch_bounds__(1024) nms_kernel(const NmsParams p) {
+__global__ void __launch_bounds__(512) nms_kernel(const NmsParams p) {
   __shared__ BlockScratch s;
   __shared__ ArgMax s_am[32];
   __shared__ float s_pick[4];
@@ -607,7 +607,7 @@ extern "C" int vilco_batched_nms(const float* segs, const float* scores, const i
     VILCO_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * NMS_SMEM_CAP * 4));
     nms_configured = true;
   }
-  nms_kernel<<<dim3(ncls, B), 1024, 6 * NMS_SMEM_CAP * 4, st>>>(p);
+  nms_kernel<<<dim3(ncls, B), 512, 6 * NMS_SMEM_CAP * 4, st>>>(p);
   VILCO_LAUNCH_CHECK();
   MergeParams m{};
   m.dets = p.dets; m.det_ind = p.det_ind; m.det_count = p.det_count; m.det_cap = det_cap; m.num_classes = ncls; m.B = B;

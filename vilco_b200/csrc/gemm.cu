@@ -24,6 +24,7 @@ struct GemmDev {
   int a_slot_row, a_slot_z1, a_slot_z2;
   int b_slot_row, b_slot_z1, b_slot_z2;
   int M, N, K, taps, Z1, Ztot;
+  int band_lo, band_hi;  // when band_hi > band_lo: only elements with band_lo <= m + n < band_hi are needed; tiles outside are skipped
   int b_major, b_batched;
   void* D; int d_dtype; long long d_ld, d_s1, d_s2, d_lo;
   float alpha;
@@ -214,6 +215,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tiles = (p.M + BM - 1) / BM;
   const int tiles_per_z = n_tiles * m_tiles;
   const int total_tiles = tiles_per_z * p.Ztot;
+  // band filter (XLNet relative scores: only bd_raw[i, p] with T <= i + p < 2T is ever read)
+  auto tile_needed = [&](int m0, int n0) -> bool {
+    if (p.band_hi <= p.band_lo) return true;
+    return (m0 + n0 + (BM - 1) + (BN - 1) >= p.band_lo) && (m0 + n0 < p.band_hi);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -224,6 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int z = t / tiles_per_z, r = t - z * tiles_per_z;
         const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
         const int z1 = z % p.Z1, z2 = z / p.Z1;
+        if (!tile_needed(m0, n0)) continue;
         ca[p.a_slot_z1] = z1; ca[p.a_slot_z2] = z2;
         cb[p.b_slot_z2] = p.b_batched ? z2 : 0;
         for (int it = 0; it < iters; ++it, ++it_g) {
@@ -257,9 +264,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== MMA issuer (single thread) =====
     const uint32_t idesc = make_idesc(BN, p.b_major);
     uint32_t it_g = 0, tc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      {
+        const int r = t % tiles_per_z;
+        if (!tile_needed((r / n_tiles) * BM, (r % n_tiles) * BN)) continue;
+      }
       const uint32_t acc = tc & 1;
-      mbar_wait(tempty0 + 8 * acc, ((tc >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
+      const uint32_t tc_cur = tc++;
+      mbar_wait(tempty0 + 8 * acc, ((tc_cur >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
       for (int it = 0; it < iters; ++it, ++it_g) {
@@ -305,12 +317,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const long long d_ld = p.d_ld, d_lo = p.d_lo;
     const bool is_f32 = p.d_dtype == VILCO_F32;
     uint32_t tc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tc) {
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int z = t / tiles_per_z, r = t - z * tiles_per_z;
       const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
+      if (!tile_needed(m0, n0)) continue;
       const int z1 = z % p.Z1, z2 = z / p.Z1;
       const uint32_t acc = tc & 1;
-      mbar_wait(tfull0 + 8 * acc, (tc >> 1) & 1);
+      const uint32_t tc_cur = tc++;
+      mbar_wait(tfull0 + 8 * acc, (tc_cur >> 1) & 1);
       tcgen05_fence_after();
       const int mrow0 = m0 + q * 32;            // first row of this warp's 32-row slab
       float rm = 1.0f;                          // row multiplier of the accumulator row this lane owns
@@ -862,6 +876,7 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
 
   GemmDev p{};
   p.M = g->M; p.N = g->N; p.K = g->K; p.taps = g->taps; p.Z1 = g->Z1; p.Ztot = g->Z1 * g->Z2;
+  p.band_lo = g->band_lo; p.band_hi = g->band_hi;
   p.b_major = g->b_major; p.b_batched = g->b_batched;
   p.D = g->D; p.d_dtype = g->d_dtype; p.d_ld = g->d_ld; p.d_s1 = g->d_s1; p.d_s2 = g->d_s2;
   p.d_lo = g->d_dtype == VILCO_BF16 ? g->d_lo : 0;

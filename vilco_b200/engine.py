@@ -193,7 +193,7 @@ def xlnet_layer_fwd(W, pre, x32, x16, mask, H, eps=1e-12):
         krel = ops.linear(pos, W[kr], bf16).unsqueeze(1).expand(-1, B, 2 * T, C).contiguous()
         cache[("krel", T, B)] = krel
     ac = ops.attn_scores(qw, k, H, 1.0)                                     # (B,H,T,T)
-    bd = ops.attn_scores(qr, krel, H, 1.0)                                  # (B,H,T,2T)
+    bd = ops.attn_scores(qr, krel, H, 1.0, band=(T, 2 * T))                 # (B,H,T,2T); only T <= i + p < 2T is read
     P = ops.softmax_rows(ac, mask, mode=1, BD=bd, scale=1.0 / math.sqrt(d))
     vec = ops.attn_pv(P, v, H, T)
     a = ops.linear(vec, W[ko], f32, resid=x32)                              # attn_out + h

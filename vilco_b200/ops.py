@@ -97,14 +97,15 @@ def conv3(x, w3, out_dtype=bf16, bias=None, rowmul=None, act=ACT_NONE):
     return out
 
 
-def attn_scores(q, k, H, alpha):
-    """S[b,h] = alpha * q_h k_h^T.  q (NP,B,Tq,C), k (NP,B,Tk,C) -> (B,H,Tq,Tk) fp32."""
+def attn_scores(q, k, H, alpha, band=(0, 0)):
+    """S[b,h] = alpha * q_h k_h^T.  q (NP,B,Tq,C), k (NP,B,Tk,C) -> (B,H,Tq,Tk) fp32.  band = (lo, hi): only the
+    entries with lo <= i + j < hi are computed (the rest of the buffer is left untouched)."""
     _, B, Tq, Cc = q.shape
     Tk = k.shape[2]
     d = Cc // H
     out = torch.empty(B, H, Tq, Tk, device=q.device, dtype=f32)
     L.gemm(q, k, out, M=Tq, N=Tk, K=d, a_rows=Tq, a_ld=Cc, a_s=(d, Tq * Cc), Z=(H, B), b_ld=Cc, b_s=(d, Tk * Cc),
-           b_batched=True, d_ld=Tk, d_s=(Tq * Tk, H * Tq * Tk), alpha=alpha, a_lo=lo(q), b_lo=lo(k))
+           b_batched=True, d_ld=Tk, d_s=(Tq * Tk, H * Tq * Tk), alpha=alpha, a_lo=lo(q), b_lo=lo(k), band=band)
     return out
 
 
