@@ -128,9 +128,10 @@ int vilco_unpack(const float* x, float* y, int B, int T, int C, void* stream);
 /* Row softmax over materialised attention scores S (Z2,Z1,Tq,Tk) fp32 -> P bf16 (row stride p_ld >= Tk, tail zeroed).
  * mode 0: keys with kmask[z2, j] == 0 get probability 0 (masked_fill(-inf) + softmax, blocks.py:258-260, 388-391).
  * mode 1: XLNet: (S[i,j] + BD[i, Tk + j - i]) * scale - 1e30 * [key j padded and i != j]
- *         (rel_shift_bnij + rel_attn_core, modeling_xlnet_x.py:256-304; mask prep :1152-1188); BD is (Z2,Z1,Tq,2Tk). */
-int vilco_softmax_rows(const float* S, const float* BD, const float* kmask, void* P, int64_t p_lo, int Z2, int Z1, int Tq,
-                       int Tk, int64_t p_ld, float scale, int mode, void* stream);
+ *         (rel_shift_bnij + rel_attn_core, modeling_xlnet_x.py:256-304; mask prep :1152-1188); BD is (Z2,Z1,Tq,2Tk).
+ * P32 (optional, row stride Tk): fp32 copy of the probabilities kept for the backward pass. */
+int vilco_softmax_rows(const float* S, const float* BD, const float* kmask, void* P, int64_t p_lo, float* P32, int Z2, int Z1,
+                       int Tq, int Tk, int64_t p_ld, float scale, int mode, void* stream);
 
 /* LocalMaskedMHCA attention core (blocks.py:1038-1138, 1165-1200): q,k,v (B,T,C) bf16 token-major after the q/k/v
  * projections, window W (odd), out-of-range keys -inf, padded keys -1e4, padded queries -> 0; rel_pe (H,W) or NULL.
@@ -193,6 +194,38 @@ int vilco_mq_losses(const float* logits, const float* offsets, const float* pmas
  * ------------------------------------------------------------------------------------ */
 int vilco_attention(const void* q, int64_t q_lo, const void* k, const void* v, int64_t kv_lo, const float* kmask, void* out,
                     int64_t out_lo, int B, int H, int Tq, int Tk, int C, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Backward-pass building blocks (training; token-major fp32 gradients).  The GEMM-shaped gradients reuse vilco_gemm:
+ *   dX = dZ W      : A = dZ (K-major over the output channels), B = W as MN-major operand (b_major = 1)
+ *   dW = dZ^T X    : A = dZ^T (vilco_to_planes writes the transposed planes), B = X as MN-major operand
+ * ------------------------------------------------------------------------------------ */
+/* y16[r,c] = x[r,c]*rowmul[r]*colmul[c] as bf16 (hi, lo) planes and / or its transpose yT16[c,r] with row stride ldT
+ * (either output may be NULL). */
+int vilco_to_planes(const float* x, const float* rowmul, const float* colmul, void* y, int64_t y_lo, void* yT, int64_t yT_lo,
+                    int R, int C, int ldT, int Z, void* stream);   /* Z independent (R,C) matrices */
+/* XLNet rel-shift backward: dBD[z,i,T+j-i] = dS[z,i,j] (dBD (Z,T,2T) pre-zeroed) — modeling_xlnet_x.py:256-268 */
+int vilco_relshift_bwd(const float* dS, float* dBD, int64_t Z, int T, void* stream);
+/* y16[b,t,:] = x16[b,t+shift,:] (zero outside the clip) on bf16 planes: shifted operands of the k=3 conv weight gradient */
+int vilco_shift_planes(const void* x, void* y, int64_t lo, int B, int T, int C, int shift, void* stream);
+/* out[c] += sum_r x[r,c] * (y ? y[r,c] : 1) * (rowmul ? rowmul[r] : 1)   (bias / scale / affine gradients; out pre-zeroed) */
+int vilco_colsum(const float* x, const float* y, const float* rowmul, float* out, int R, int C, void* stream);
+/* LayerNorm backward of y = act(LN(x [+ add]) * w + b) (blocks.py:160-175): dx (also the gradient of `add`), dw, db
+ * (accumulated; pre-zeroed by the caller).  y_relu = forward output when the ReLU was fused, else NULL. */
+int vilco_layernorm_bwd(const float* x, const float* add, const float* w, const float* dy, const float* y_relu, float eps,
+                        float* dx, float* dw, float* db, int rows, int C, void* stream);
+/* depthwise k=3 conv * mask backward (MaskedConv1D with groups = C, blocks.py:106-130): dconv (B,T/stride,C) is the
+ * gradient w.r.t. the masked conv output; dx (B,T,C) written or accumulated, dw (3,C) accumulated. */
+int vilco_dwconv_bwd(const float* x, const float* mask, const float* w, const float* dconv, float* dx, float* dw, int B,
+                     int T, int C, int stride, int accumulate_dx, void* stream);
+/* fp32 depthwise k=3 conv * out-mask (the LayerNorm input of vilco_dwconv_ln, recomputed in the backward pass) */
+int vilco_dwconv_fwd32(const float* x, const float* mask, const float* w, float* out, int B, int T, int C, int stride,
+                       void* stream);
+int vilco_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
+/* MaxPool1d(3,2,1) backward (TransformerBlock.pool_skip): dx must be pre-zeroed; gradient goes to the first maximum. */
+int vilco_maxpool3s2_bwd(const float* x, const float* dy, float* dx, int B, int T, int C, void* stream);
+/* dS[r,j] = scale * P[r,j] * (dP[r,j] - sum_k dP[r,k] P[r,k])   (softmax backward over materialised fp32 rows) */
+int vilco_softmax_bwd(const float* P, const float* dP, float* dS, int64_t rows, int Tk, float scale, void* stream);
 
 #ifdef __cplusplus
 }

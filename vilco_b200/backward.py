@@ -1,0 +1,178 @@
+"""Backward primitives of the Moment-Query operators on the sm_100a kernels (training path, work in progress).
+
+Conventions: gradients are fp32 token-major tensors; GEMM-shaped gradients reuse `vilco_gemm`
+(dX = dZ W with W as MN-major B operand, dW = dZ^T X with X as MN-major B operand), everything else is a kernel of
+csrc/bwd.cu.  Each function states the forward it differentiates.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from . import ops
+from .ops import _i64, _p, bf16, f32, lo
+
+
+def to_planes(x, rowmul=None, colmul=None, want=True, want_t=False, batch_dims=0):
+    """x (..., R, C) fp32 -> (y16 (NP,...,R,C) or None, yT16 (NP,...,C,ldT) or None), y = x * rowmul[:,None] * colmul[None,:].
+    The leading `batch_dims` dims index independent matrices (transposed separately); otherwise x is flattened to 2-D."""
+    assert x.dtype == f32 and x.is_contiguous()
+    Cc = x.shape[-1]
+    if batch_dims:
+        lead = tuple(x.shape[:batch_dims])
+        R = x.numel() // Cc
+        for n in lead:
+            R //= n
+        Z = x.numel() // (R * Cc)
+    else:
+        lead, R, Z = (), x.numel() // Cc, 1
+    y = ops.empty16(*lead, R, Cc, device=x.device) if want else None
+    ldT = (R + 7) // 8 * 8
+    yT = ops.zeros16(*lead, Cc, ldT, device=x.device) if want_t else None
+    L.check(L.lib().vilco_to_planes(_p(x), _p(rowmul), _p(colmul), _p(y), _i64(lo(y) if want else 0), _p(yT),
+                                    _i64(lo(yT) if want_t else 0), R, Cc, ldT, Z, L.stream_ptr()), "vilco_to_planes")
+    return y, yT
+
+
+def colsum(x, y=None, rowmul=None, out=None):
+    Cc = x.shape[-1]
+    R = x.numel() // Cc
+    if out is None:
+        out = torch.zeros(Cc, device=x.device, dtype=f32)
+    L.check(L.lib().vilco_colsum(_p(x), _p(y), _p(rowmul), _p(out), R, Cc, L.stream_ptr()), "vilco_colsum")
+    return out
+
+
+def linear_bwd(dy, x16, w16, rowmul=None, alpha=1.0, need_dx=True, need_dw=True, need_db=True):
+    """forward: y = (alpha * x w^T + bias) * rowmul[:, None]   (ops.linear without act / colscale / resid).
+    dy (..., N) fp32, x16 (NP, ..., K), w16 (NP, N, K) -> (dx (..., K) fp32, dw (N, K) fp32, db (N,) fp32)."""
+    N, K = w16.shape[1], w16.shape[2]
+    dy2 = dy.reshape(-1, N)
+    R = dy2.shape[0]
+    dz, dzT = to_planes(dy2, rowmul, None, want=need_dx, want_t=need_dw)
+    dx = dw = db = None
+    if need_dx:
+        dx = torch.empty(*dy.shape[:-1], K, device=dy.device, dtype=f32)
+        L.gemm(dz, w16, dx, M=R, N=K, K=N, a_rows=R, a_ld=N, b_ld=K, d_ld=K, b_major=1, alpha=alpha, a_lo=lo(dz), b_lo=lo(w16))
+    if need_dw:
+        dw = torch.empty(N, K, device=dy.device, dtype=f32)
+        x2 = x16.reshape(x16.shape[0], -1, K)
+        L.gemm(dzT, x2, dw, M=N, N=K, K=R, a_rows=N, a_ld=dzT.shape[2], b_ld=K, d_ld=K, b_major=1, alpha=alpha,
+               a_lo=lo(dzT), b_lo=lo(x2))
+    if need_db:
+        db = colsum(dy2, rowmul=rowmul)
+    return dx, dw, db
+
+
+def shift_planes(x16, shift):
+    """x16 (NP,B,T,C) -> same shape, rows shifted inside every clip: y[b,t] = x[b,t+shift] (zero outside)."""
+    NP, B, T, Cc = x16.shape
+    y = torch.empty_like(x16)
+    L.check(L.lib().vilco_shift_planes(_p(x16), _p(y), _i64(lo(x16)), B, T, Cc, shift, L.stream_ptr()), "vilco_shift_planes")
+    return y
+
+
+def conv3_bwd(dy, x16, w3, w3_flip, rowmul=None, need_dx=True):
+    """forward: y[b,t] = (sum_tap x[b,t+tap-1] w3[tap]^T + bias) * rowmul[b,t]   (ops.conv3).
+    dy (B,T,N) fp32, x16 (NP,B,T,K), w3 / w3_flip (NP,3,N,K) (flip = taps reversed) -> (dx (B,T,K), dw3 (3,N,K), db (N,))."""
+    B, T, N = dy.shape
+    K = w3.shape[3]
+    dz, dzT = to_planes(dy.reshape(-1, N), rowmul.reshape(-1) if rowmul is not None else None, None, want=need_dx, want_t=True)
+    dx = None
+    if need_dx:
+        # dx[b,t] = sum_tap dz[b, t - tap + 1] w3[tap] = sum_tap' dz[b, t + tap' - 1] w3[2 - tap']: the forward conv kernel
+        # on dz with the tap-reversed weights as MN-major B operand
+        dx = torch.empty(B, T, K, device=dy.device, dtype=f32)
+        dz4 = dz.reshape(dz.shape[0], B, T, N)
+        L.gemm(dz4, w3_flip, dx, M=T, N=K, K=N, a_rows=T, a_ld=N, a_s=(0, T * N), Z=(1, B), taps=3, b_ld=K, b_s=(N * K, 0),
+               b_major=1, d_ld=K, d_s=(0, T * K), a_lo=lo(dz4), b_lo=lo(w3_flip))
+    dw = torch.empty(3, N, K, device=dy.device, dtype=f32)
+    R = B * T
+    for tap in range(3):
+        xs = x16 if tap == 1 else shift_planes(x16, tap - 1)
+        x2 = xs.reshape(xs.shape[0], R, K)
+        L.gemm(dzT, x2, dw[tap], M=N, N=K, K=R, a_rows=N, a_ld=dzT.shape[2], b_ld=K, d_ld=K, b_major=1, a_lo=lo(dzT), b_lo=lo(x2))
+    db = colsum(dy.reshape(-1, N), rowmul=rowmul.reshape(-1) if rowmul is not None else None)
+    return dx, dw, db
+
+
+def layernorm_bwd(dy, x, w, eps=1e-5, add=None, y_relu=None, need_dw=True):
+    """forward: y = act(LN(x [+ add]) * w + b)  (ops.layernorm; y_relu = fp32 forward output when relu=True).
+    Returns (dx (also the gradient of `add`), dw, db)."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    dx = torch.empty_like(x)
+    dw = torch.zeros(Cc, device=x.device, dtype=f32) if need_dw else None
+    db = torch.zeros(Cc, device=x.device, dtype=f32) if need_dw else None
+    L.check(L.lib().vilco_layernorm_bwd(_p(x), _p(add), _p(w), _p(dy.contiguous()), _p(y_relu), C.c_float(eps), _p(dx), _p(dw),
+                                        _p(db), rows, Cc, L.stream_ptr()), "vilco_layernorm_bwd")
+    return dx, dw, db
+
+
+def gelu_bwd(dy, x):
+    dx = torch.empty_like(x)
+    L.check(L.lib().vilco_gelu_bwd(_p(x), _p(dy.contiguous()), _p(dx), _i64(x.numel()), L.stream_ptr()), "vilco_gelu_bwd")
+    return dx
+
+
+def maxpool3s2_bwd(dy, x):
+    B, T, Cc = x.shape
+    dx = torch.zeros_like(x)
+    L.check(L.lib().vilco_maxpool3s2_bwd(_p(x), _p(dy.contiguous()), _p(dx), B, T, Cc, L.stream_ptr()), "vilco_maxpool3s2_bwd")
+    return dx
+
+
+def dwconv_ln_bwd(dys, x, mask, wconvs, lnws, stride, eps=1e-5):
+    """forward: out_i = LN_i(dwconv_i(x) * mask_out)  (ops.dwconv_ln), i over (q, k, v).
+    dys: list of (B,T/stride,C) fp32.  Returns (dx (B,T,C), [dwconv_i (3,C)], [dlnw_i], [dlnb_i]).
+    The conv outputs are recomputed from x (cheap, depthwise) instead of being stored."""
+    B, T, Cc = x.shape
+    To = T // stride
+    dx = torch.zeros_like(x)
+    dwc, dlw, dlb = [], [], []
+    om = mask[:, ::stride].contiguous() if stride > 1 else mask
+    for i, dy in enumerate(dys):
+        # recompute conv_i(x) * mask (fp32) with torch-free kernels: depthwise conv = 3 shifted axpby ... kept simple:
+        conv = _dwconv_fwd32(x, mask, wconvs[i], stride)
+        dconv, dw_ln, db_ln = layernorm_bwd(dy, conv, lnws[i], eps)
+        dw = torch.zeros(3, Cc, device=x.device, dtype=f32)
+        L.check(L.lib().vilco_dwconv_bwd(_p(x), _p(mask), _p(wconvs[i]), _p(dconv), _p(dx), _p(dw), B, T, Cc, stride, 1,
+                                         L.stream_ptr()), "vilco_dwconv_bwd")
+        dwc.append(dw); dlw.append(dw_ln); dlb.append(db_ln)
+    return dx, dwc, dlw, dlb
+
+
+def _dwconv_fwd32(x, mask, w3c, stride):
+    """fp32 depthwise conv * out-mask via the existing forward kernel with an identity LayerNorm is not available, so the
+    recomputation uses the dwconv_ln kernel's math through vilco_dwconv_fwd32 (plain fp32 output)."""
+    B, T, Cc = x.shape
+    out = torch.empty(B, T // stride, Cc, device=x.device, dtype=f32)
+    L.check(L.lib().vilco_dwconv_fwd32(_p(x), _p(mask), _p(w3c), _p(out), B, T, Cc, stride, L.stream_ptr()), "vilco_dwconv_fwd32")
+    return out
+
+
+def attention_bwd(dO, q16, k16, v16, kmask, H, scale):
+    """forward: O = softmax_j(scale * q k^T | kmask) v per head (ops.attention / the materialised chain).
+    dO (B,Tq,C) fp32, q16 (NP,B,Tq,C), k16 / v16 (NP,B,Tk,C) -> (dq, dk, dv) fp32 token-major.
+    The probabilities are recomputed (QK^T GEMM + softmax) instead of being stored by the fused forward kernel."""
+    _, B, Tq, Cc = q16.shape
+    Tk = k16.shape[2]
+    S = ops.attn_scores(q16, k16, H, scale)
+    P16, P32 = ops.softmax_rows(S, kmask, mode=0, want32=True)
+    dO16, _ = to_planes(dO.reshape(-1, Cc))
+    dO16 = dO16.reshape(dO16.shape[0], B, Tq, Cc)
+    dP = ops.attn_scores(dO16, v16, H, 1.0)                       # dP[b,h] = dO_h v_h^T
+    dS = torch.empty_like(dP)
+    L.check(L.lib().vilco_softmax_bwd(_p(P32), _p(dP), _p(dS), _i64(B * H * Tq), Tk, C.c_float(scale), L.stream_ptr()),
+            "vilco_softmax_bwd")
+    dS16, dST16 = to_planes(dS, want=True, want_t=True, batch_dims=2)   # (NP,B,H,Tq,Tk) and (NP,B,H,Tk,ldq)
+    if Tk % 8:   # A-operand rows must keep 16-byte strides
+        pad = (Tk + 7) // 8 * 8
+        t2 = ops.zeros16(B, H, Tq, pad, device=dS.device)
+        t2[..., :Tk] = dS16
+        dS16 = t2
+    dq = ops.attn_pv(dS16, k16, H, Tk, out32=True)               # dQ_h = dS K_h
+    dk = ops.attn_pv(dST16, q16, H, Tq, out32=True)              # dK_h = dS^T Q_h
+    _, PT16 = to_planes(P32, want=False, want_t=True, batch_dims=2)
+    dv = ops.attn_pv(PT16, dO16, H, Tq, out32=True)              # dV_h = P^T dO_h
+    return dq, dk, dv

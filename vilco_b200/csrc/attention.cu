@@ -15,6 +15,7 @@ namespace vilco {
 struct SmParams {
   const float* S; const float* BD; const float* kmask;  // kmask (Z2, Tk)
   __nv_bfloat16* P; long long p_lo;
+  float* P32;   // optional fp32 copy of the probabilities (row stride Tk), kept for the backward pass
   int Z1, Tq, Tk; long long p_ld; float scale; int mode;
   long long rows;
 };
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const SmParams p) {
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     o[j] = h;
     if (p.p_lo) o[p.p_lo + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+    if (p.P32 && j < p.Tk) p.P32[row * p.Tk + j] = v;
   }
 }
 
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const SmParams p)
       const uint32_t h = pack_bf16x2(a0, a1);
       *reinterpret_cast<uint32_t*>(o + j) = h;
       if (p.p_lo) *reinterpret_cast<uint32_t*>(o + p.p_lo + j) = pack_bf16x2(a0 - bf16_lo(h), a1 - bf16_hi(h));
+      if (p.P32 && j < p.Tk) *reinterpret_cast<float2*>(p.P32 + row * p.Tk + j) = make_float2(a0, a1);
     }
   }
 }
@@ -351,12 +354,12 @@ __global__ void __launch_bounds__(256) chan_attn_apply_kernel(const __nv_bfloat1
 
 using namespace vilco;
 
-extern "C" int vilco_softmax_rows(const float* S, const float* BD, const float* kmask, void* P, int64_t p_lo, int Z2, int Z1,
-                                  int Tq, int Tk, int64_t p_ld, float scale, int mode, void* stream) {
+extern "C" int vilco_softmax_rows(const float* S, const float* BD, const float* kmask, void* P, int64_t p_lo, float* P32, int Z2,
+                                  int Z1, int Tq, int Tk, int64_t p_ld, float scale, int mode, void* stream) {
   VILCO_CHECK_ARG(S && P && Z1 > 0 && Z2 > 0 && Tq > 0 && Tk > 0 && p_ld >= Tk, "vilco_softmax_rows: bad arguments");
   VILCO_CHECK_ARG(mode == 0 || (mode == 1 && BD && Tq == Tk), "vilco_softmax_rows: mode 1 needs BD and Tq == Tk");
   SmParams p{};
-  p.S = S; p.BD = BD; p.kmask = kmask; p.P = static_cast<__nv_bfloat16*>(P); p.p_lo = p_lo;
+  p.S = S; p.BD = BD; p.kmask = kmask; p.P = static_cast<__nv_bfloat16*>(P); p.p_lo = p_lo; p.P32 = P32;
   p.Z1 = Z1; p.Tq = Tq; p.Tk = Tk; p.p_ld = p_ld; p.scale = scale; p.mode = mode;
   p.rows = (long long)Z2 * Z1 * Tq;
   const long long grid = (p.rows + 7) / 8;

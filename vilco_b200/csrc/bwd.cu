@@ -1,0 +1,386 @@
+// Backward-pass building blocks (token-major fp32 gradients):
+//   rows -> bf16 operand planes with optional row mask / transposition (GEMM dgrad / wgrad operands)
+//   column sums (bias, AffineDropPath-scale and LayerNorm affine gradients)
+//   LayerNorm backward (channel LN of blocks.py:160-175 and nn.LayerNorm), optionally through the fused ReLU
+//   depthwise k=3 conv + mask + LayerNorm backward (q/k/v front of MaskedMHCA)
+//   GELU / max-pool / masked-softmax backward
+#include "common.cuh"
+
+namespace vilco {
+
+__device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4f(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_planes(__nv_bfloat16* p, long long lo, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  p[0] = h;
+  if (lo) p[lo] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// y16[r, c] = x[r, c] * rowmul[r] * colmul[c]  as bf16 planes; optional transposed copy yT16[c, r]
+__global__ void to_planes_kernel(const float* __restrict__ x, const float* __restrict__ rowmul, const float* __restrict__ colmul,
+                                 __nv_bfloat16* __restrict__ y, long long y_lo, __nv_bfloat16* __restrict__ yT, long long yT_lo,
+                                 int R, int C, int ldT) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  x += (long long)blockIdx.z * R * C;
+  if (y) y += (long long)blockIdx.z * R * C;
+  if (yT) yT += (long long)blockIdx.z * C * ldT;
+  if (rowmul) rowmul += (long long)blockIdx.z * R;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = x[(long long)r * C + c];
+      if (rowmul) v *= rowmul[r];
+      if (colmul) v *= colmul[c];
+      if (y) st_planes(y + (long long)r * C + c, y_lo, v);
+    }
+    tile[j][tx] = v;
+  }
+  if (!yT) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (c < C && r < R) st_planes(yT + (long long)c * ldT + r, yT_lo, tile[tx][j]);
+  }
+}
+
+// y16[b, t, :] = x16[b, t + shift, :] (zero outside [0, T)) on bf16 planes: the row-shifted copies the k=3 conv wgrad needs
+__global__ void shift_planes_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long lo16, int planes, int B, int T,
+                                    int C8, int shift) {
+  const long long total = (long long)planes * B * T * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i % C8);
+    long long r = i / C8;
+    const int t = static_cast<int>(r % T); r /= T;
+    const int b = static_cast<int>(r % B);
+    const int pl = static_cast<int>(r / B);
+    const int ts = t + shift;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ts >= 0 && ts < T) v = x[pl * lo16 + ((long long)b * T + ts) * C8 + c];
+    y[pl * lo16 + ((long long)b * T + t) * C8 + c] = v;
+  }
+}
+
+// out[c] (+)= sum_r x[r, c] * (y ? y[r, c] : 1) * (rowmul ? rowmul[r] : 1)
+__global__ void colsum_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ rowmul,
+                              float* __restrict__ out, int R, int C, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    float v = x[(long long)r * C + c];
+    if (y) v *= y[(long long)r * C + c];
+    if (rowmul) v *= rowmul[r];
+    acc += v;
+  }
+  atomicAdd(out + c, acc);
+}
+
+// ---- LayerNorm backward: y = act(LN(x [+ add]) * w + b); one warp per row; dw/db via per-block smem + atomics ----
+static constexpr int BW_MAXCH = 8;
+struct LnBwdParams {
+  const float* x; const float* add; const float* w; const float* dy;
+  const float* y_relu;   // output of the fused ReLU (fp32) or null: gradient passes where y_relu > 0
+  float eps; float* dx; float* dw; float* db; int rows, C;
+};
+
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nch = p.C >> 7;
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float4 dwl[BW_MAXCH], dbl[BW_MAXCH];
+#pragma unroll
+  for (int i = 0; i < BW_MAXCH; ++i) { dwl[i] = make_float4(0, 0, 0, 0); dbl[i] = make_float4(0, 0, 0, 0); }
+  for (int row = blockIdx.x * 8 + warp; row < p.rows; row += gridDim.x * 8) {
+    const float* x = p.x + (long long)row * p.C;
+    float4 v[BW_MAXCH], g[BW_MAXCH];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < BW_MAXCH; ++i)
+      if (i < nch) {
+        const int c = (i * 32 + lane) * 4;
+        v[i] = ld4f(x + c);
+        if (p.add) { const float4 a = ld4f(p.add + (long long)row * p.C + c); v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w; }
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    const float mean = warp_sum(s) / p.C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < BW_MAXCH; ++i)
+      if (i < nch) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / p.C + p.eps);
+    float s1 = 0.f, s2 = 0.f;  // sum(dy*w), sum(dy*w*xhat)
+#pragma unroll
+    for (int i = 0; i < BW_MAXCH; ++i)
+      if (i < nch) {
+        const int c = (i * 32 + lane) * 4;
+        float4 d = ld4f(p.dy + (long long)row * p.C + c);
+        if (p.y_relu) {
+          const float4 yr = ld4f(p.y_relu + (long long)row * p.C + c);
+          if (!(yr.x > 0.f)) d.x = 0.f; if (!(yr.y > 0.f)) d.y = 0.f; if (!(yr.z > 0.f)) d.z = 0.f; if (!(yr.w > 0.f)) d.w = 0.f;
+        }
+        const float4 w = ld4f(p.w + c);
+        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
+        dwl[i].x += d.x * v[i].x; dwl[i].y += d.y * v[i].y; dwl[i].z += d.z * v[i].z; dwl[i].w += d.w * v[i].w;
+        dbl[i].x += d.x; dbl[i].y += d.y; dbl[i].z += d.z; dbl[i].w += d.w;
+        g[i] = make_float4(d.x * w.x, d.y * w.y, d.z * w.z, d.w * w.w);
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+      }
+    s1 = warp_sum(s1) / p.C; s2 = warp_sum(s2) / p.C;
+#pragma unroll
+    for (int i = 0; i < BW_MAXCH; ++i)
+      if (i < nch) {
+        const int c = (i * 32 + lane) * 4;
+        st4f(p.dx + (long long)row * p.C + c,
+             make_float4(rstd * (g[i].x - s1 - v[i].x * s2), rstd * (g[i].y - s1 - v[i].y * s2),
+                         rstd * (g[i].z - s1 - v[i].z * s2), rstd * (g[i].w - s1 - v[i].w * s2)));
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < BW_MAXCH; ++i)
+    if (i < nch) {
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(&s_acc[c], dwl[i].x); atomicAdd(&s_acc[c + 1], dwl[i].y); atomicAdd(&s_acc[c + 2], dwl[i].z); atomicAdd(&s_acc[c + 3], dwl[i].w);
+      atomicAdd(&s_acc[p.C + c], dbl[i].x); atomicAdd(&s_acc[p.C + c + 1], dbl[i].y); atomicAdd(&s_acc[p.C + c + 2], dbl[i].z); atomicAdd(&s_acc[p.C + c + 3], dbl[i].w);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+    if (p.dw) atomicAdd(p.dw + i, s_acc[i]);
+    if (p.db) atomicAdd(p.db + i, s_acc[p.C + i]);
+  }
+}
+
+// ---- depthwise conv k=3 (stride s) * mask backward: given dconv (B, T/s, C) (gradient w.r.t. the masked conv output)
+//      dx[b, t, c] = sum_tap w[tap, c] * dconv[b, to, c] * mask[b, to*s]  over (to, tap) with to*s + tap - 1 == t
+//      dw[tap, c]  = sum_{b,to} dconv * mask * x[b, to*s + tap - 1, c]
+__global__ void dwconv_bwd_kernel(const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ w,
+                                  const float* __restrict__ dconv, float* __restrict__ dx, float* __restrict__ dw, int B, int T,
+                                  int C, int stride, int accumulate_dx) {
+  // one thread per (b, t, c4); dw reduced per block over its rows then atomics
+  extern __shared__ float s_dw[];  // [3][C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_dw[i] = 0.f;
+  __syncthreads();
+  const int To = T / stride;
+  const int c4n = C / 4;
+  const long long total = (long long)B * T * c4n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(idx % c4n) * 4;
+    const long long bt = idx / c4n;
+    const int t = static_cast<int>(bt % T), b = static_cast<int>(bt / T);
+    float4 acc = make_float4(0, 0, 0, 0);
+    // outputs `to` that read input position t: to*s + tap - 1 == t
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      const int num = t - tap + 1;
+      if (num < 0 || num % stride != 0) continue;
+      const int to = num / stride;
+      if (to >= To) continue;
+      const float m = mask[(long long)b * T + to * stride];
+      if (m == 0.f) continue;
+      const float4 d = ld4f(dconv + ((long long)b * To + to) * C + c);
+      const float4 ww = ld4f(w + tap * C + c);
+      acc.x += ww.x * d.x * m; acc.y += ww.y * d.y * m; acc.z += ww.z * d.z * m; acc.w += ww.w * d.w * m;
+      if (dw) {
+        const float4 xv = ld4f(x + ((long long)b * T + t) * C + c);
+        atomicAdd(&s_dw[tap * C + c], d.x * m * xv.x); atomicAdd(&s_dw[tap * C + c + 1], d.y * m * xv.y);
+        atomicAdd(&s_dw[tap * C + c + 2], d.z * m * xv.z); atomicAdd(&s_dw[tap * C + c + 3], d.w * m * xv.w);
+      }
+    }
+    float* o = dx + ((long long)b * T + t) * C + c;
+    if (accumulate_dx) { const float4 p0 = ld4f(o); acc.x += p0.x; acc.y += p0.y; acc.z += p0.z; acc.w += p0.w; }
+    st4f(o, acc);
+  }
+  __syncthreads();
+  if (dw)
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x)
+      if (s_dw[i] != 0.f) atomicAdd(dw + i, s_dw[i]);
+}
+
+// fp32 depthwise k=3 conv * out-mask (recomputation of the LN input in the backward pass)
+__global__ void dwconv_fwd32_kernel(const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ w,
+                                    float* __restrict__ out, int B, int T, int C, int stride) {
+  const int To = T / stride, c4n = C / 4;
+  const long long total = (long long)B * To * c4n;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(idx % c4n) * 4;
+    const long long r = idx / c4n;
+    const int to = static_cast<int>(r % To), b = static_cast<int>(r / To);
+    const int tc = to * stride;
+    const float m = mask[(long long)b * T + tc];
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      const int t = tc + tap - 1;
+      if (t < 0 || t >= T) continue;
+      const float4 xv = ld4f(x + ((long long)b * T + t) * C + c);
+      const float4 ww = ld4f(w + tap * C + c);
+      acc.x = fmaf(ww.x, xv.x, acc.x); acc.y = fmaf(ww.y, xv.y, acc.y); acc.z = fmaf(ww.z, xv.z, acc.z); acc.w = fmaf(ww.w, xv.w, acc.w);
+    }
+    st4f(out + r * C + c, make_float4(acc.x * m, acc.y * m, acc.z * m, acc.w * m));
+  }
+}
+
+// XLNet rel-shift backward: dBD[z, i, T + j - i] = dS[z, i, j]
+__global__ void relshift_bwd_kernel(const float* __restrict__ dS, float* __restrict__ dBD, long long Z, int T) {
+  const long long total = Z * T * T;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = static_cast<int>(idx % T);
+    const long long zi = idx / T;
+    const int i = static_cast<int>(zi % T);
+    dBD[zi * (2LL * T) + (T + j - i)] = dS[idx];
+  }
+}
+
+// dx = dy * gelu'(x)
+__global__ void gelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+    dx[i] = dy[i] * (cdf + v * pdf);
+  }
+}
+
+// MaxPool1d(3, 2, 1) backward on token-major fp32: the gradient goes to the first maximum of the window (ATen semantics)
+__global__ void maxpool3s2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B,
+                                      int T, int C) {
+  const int To = T / 2;
+  const long long total = (long long)B * To * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long r = i / C;
+    const int to = static_cast<int>(r % To), b = static_cast<int>(r / To);
+    const float* xb = x + ((long long)b * T) * C + c;
+    int best = -1;
+    float bv = -INFINITY;
+    for (int tap = 0; tap < 3; ++tap) {
+      const int t = 2 * to + tap - 1;
+      if (t < 0 || t >= T) continue;
+      const float v = xb[(long long)t * C];
+      if (best < 0 || v > bv) { bv = v; best = t; }
+    }
+    atomicAdd(dx + ((long long)b * T + best) * C + c, dy[i]);
+  }
+}
+
+// masked softmax backward over rows: dS[r, j] = scale * P[r, j] * (dP[r, j] - sum_k dP[r, k] P[r, k])
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ P, const float* __restrict__ dP,
+                                                          float* __restrict__ dS, long long rows, int Tk, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* p = P + row * Tk;
+  const float* d = dP + row * Tk;
+  float s = 0.f;
+  for (int j = lane; j < Tk; j += 32) s += p[j] * d[j];
+  s = warp_sum(s);
+  for (int j = lane; j < Tk; j += 32) dS[row * Tk + j] = scale * p[j] * (d[j] - s);
+}
+
+}  // namespace vilco
+
+using namespace vilco;
+
+static inline int bgrid(long long n, int block, int cap = 148 * 8) {
+  long long g = (n + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+extern "C" int vilco_to_planes(const float* x, const float* rowmul, const float* colmul, void* y, int64_t y_lo, void* yT,
+                               int64_t yT_lo, int R, int C, int ldT, int Z, void* stream) {
+  VILCO_CHECK_ARG(x && (y || yT) && R > 0 && C > 0 && Z > 0, "vilco_to_planes: bad arguments");
+  dim3 grid((C + 31) / 32, (R + 31) / 32, Z);
+  to_planes_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, static_cast<__nv_bfloat16*>(yT), yT_lo, R, C, ldT);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_colsum(const float* x, const float* y, const float* rowmul, float* out, int R, int C, void* stream) {
+  VILCO_CHECK_ARG(x && out && R > 0 && C > 0, "vilco_colsum: bad arguments");
+  const int rpb = 256;
+  dim3 grid((C + 127) / 128, (R + rpb - 1) / rpb);
+  colsum_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rowmul, out, R, C, rpb);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_layernorm_bwd(const float* x, const float* add, const float* w, const float* dy, const float* y_relu,
+                                   float eps, float* dx, float* dw, float* db, int rows, int C, void* stream) {
+  VILCO_CHECK_ARG(x && w && dy && dx, "vilco_layernorm_bwd: null pointer");
+  VILCO_CHECK_ARG(C % 128 == 0 && C <= 128 * BW_MAXCH, "vilco_layernorm_bwd: C=%d unsupported", C);
+  LnBwdParams p{x, add, w, dy, y_relu, eps, dx, dw, db, rows, C};
+  int grid = (rows + 7) / 8;
+  if (grid > 148 * 4) grid = 148 * 4;
+  layernorm_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(p);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_dwconv_bwd(const float* x, const float* mask, const float* w, const float* dconv, float* dx, float* dw,
+                                int B, int T, int C, int stride, int accumulate_dx, void* stream) {
+  VILCO_CHECK_ARG(x && mask && w && dconv && dx, "vilco_dwconv_bwd: null pointer");
+  VILCO_CHECK_ARG(C % 4 == 0 && (stride == 1 || stride == 2) && T % stride == 0, "vilco_dwconv_bwd: bad shape");
+  dwconv_bwd_kernel<<<bgrid((long long)B * T * (C / 4), 256, 148 * 4), 256, 3 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      x, mask, w, dconv, dx, dw, B, T, C, stride, accumulate_dx);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream) {
+  VILCO_CHECK_ARG(x && dy && dx && n > 0, "vilco_gelu_bwd: bad arguments");
+  gelu_bwd_kernel<<<bgrid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dx, n);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_maxpool3s2_bwd(const float* x, const float* dy, float* dx, int B, int T, int C, void* stream) {
+  VILCO_CHECK_ARG(x && dy && dx && T % 2 == 0, "vilco_maxpool3s2_bwd: bad arguments");
+  maxpool3s2_bwd_kernel<<<bgrid((long long)B * (T / 2) * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dx, B, T, C);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_softmax_bwd(const float* P, const float* dP, float* dS, int64_t rows, int Tk, float scale, void* stream) {
+  VILCO_CHECK_ARG(P && dP && dS && rows > 0 && Tk > 0, "vilco_softmax_bwd: bad arguments");
+  softmax_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(P, dP, dS, rows, Tk, scale);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_shift_planes(const void* x, void* y, int64_t lo, int B, int T, int C, int shift, void* stream) {
+  VILCO_CHECK_ARG(x && y && C % 8 == 0 && lo % 8 == 0, "vilco_shift_planes: bad arguments");
+  const int planes = lo ? 2 : 1;
+  shift_planes_kernel<<<bgrid((long long)planes * B * T * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), lo / 8, planes, B, T, C / 8, shift);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_dwconv_fwd32(const float* x, const float* mask, const float* w, float* out, int B, int T, int C, int stride,
+                                  void* stream) {
+  VILCO_CHECK_ARG(x && mask && w && out && C % 4 == 0 && (stride == 1 || stride == 2) && T % stride == 0, "vilco_dwconv_fwd32: bad arguments");
+  dwconv_fwd32_kernel<<<bgrid((long long)B * (T / stride) * (C / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, mask, w, out, B, T, C, stride);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_relshift_bwd(const float* dS, float* dBD, int64_t Z, int T, void* stream) {
+  VILCO_CHECK_ARG(dS && dBD && Z > 0 && T > 0, "vilco_relshift_bwd: bad arguments");
+  relshift_bwd_kernel<<<bgrid(Z * T * T, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dS, dBD, Z, T);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}

@@ -869,7 +869,6 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   VILCO_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->Z1 > 0 && g->Z2 > 0, "vilco_gemm: empty problem");
   VILCO_CHECK_ARG(g->taps == 1 || g->taps == 3, "vilco_gemm: taps must be 1 or 3");
   VILCO_CHECK_ARG(!(g->b_batched && g->taps != 1), "vilco_gemm: batched B cannot have taps");
-  VILCO_CHECK_ARG(!(g->b_major == 1 && g->N > 64), "vilco_gemm: MN-major B supports N <= 64");
   VILCO_CHECK_ARG(g->d_dtype == VILCO_F32 || g->d_dtype == VILCO_BF16, "vilco_gemm: bad d_dtype");
   VILCO_CHECK_ARG(!(g->resid_masked && !g->rowmul), "vilco_gemm: resid_masked needs rowmul");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -109,15 +109,16 @@ def attn_scores(q, k, H, alpha, band=(0, 0)):
     return out
 
 
-def attn_pv(P, v, H, Tk):
-    """O[b, :, h*d:(h+1)*d] = P[b,h] v_h.  P (NP,B,H,Tq,ldp), v (NP,B,Tk,C) -> operand (NP,B,Tq,C)."""
+def attn_pv(P, v, H, Tk, out32=False):
+    """O[b, :, h*d:(h+1)*d] = P[b,h] v_h.  P (NP,B,H,Tq,ldp), v (NP,B,Tk,C) -> operand (NP,B,Tq,C) (fp32 (B,Tq,C) if out32)."""
     _, B, _, Tq, ldp = P.shape
     Cc = v.shape[3]
     d = Cc // H
     assert d == 64, "attn_pv: head dim must be 64"
-    out = empty16(B, Tq, Cc, device=v.device)
+    out = torch.empty(B, Tq, Cc, device=v.device, dtype=f32) if out32 else empty16(B, Tq, Cc, device=v.device)
     L.gemm(P, v, out, M=Tq, N=d, K=Tk, a_rows=Tq, a_ld=ldp, a_s=(Tq * ldp, H * Tq * ldp), Z=(H, B), b_ld=Cc,
-           b_s=(d, Tk * Cc), b_batched=True, b_major=1, d_ld=Cc, d_s=(d, Tq * Cc), a_lo=lo(P), b_lo=lo(v), d_lo=lo(out))
+           b_s=(d, Tk * Cc), b_batched=True, b_major=1, d_ld=Cc, d_s=(d, Tq * Cc), a_lo=lo(P), b_lo=lo(v),
+           d_lo=0 if out32 else lo(out))
     return out
 
 
@@ -210,14 +211,15 @@ def unpack(x):
     return y
 
 
-def softmax_rows(S, kmask, mode=0, BD=None, scale=1.0):
-    """S (B,H,Tq,Tk) fp32 -> P operand (NP,B,H,Tq,ldp) with ldp = roundup(Tk, 8)."""
+def softmax_rows(S, kmask, mode=0, BD=None, scale=1.0, want32=False):
+    """S (B,H,Tq,Tk) fp32 -> P operand (NP,B,H,Tq,ldp) with ldp = roundup(Tk, 8) [, fp32 P (B,H,Tq,Tk) when want32]."""
     B, H, Tq, Tk = S.shape
     ldp = (Tk + 7) // 8 * 8
     P = empty16(B, H, Tq, ldp, device=S.device)
-    L.check(L.lib().vilco_softmax_rows(_p(S), _p(BD), _p(kmask), _p(P), _i64(lo(P)), B, H, Tq, Tk, _i64(ldp),
+    P32 = torch.empty(B, H, Tq, Tk, device=S.device, dtype=f32) if want32 else None
+    L.check(L.lib().vilco_softmax_rows(_p(S), _p(BD), _p(kmask), _p(P), _i64(lo(P)), _p(P32), B, H, Tq, Tk, _i64(ldp),
                                        C.c_float(scale), mode, L.stream_ptr()), "vilco_softmax_rows")
-    return P
+    return (P, P32) if want32 else P
 
 
 def local_attention(q, k, v, mask, H, W, rel_pe=None):
