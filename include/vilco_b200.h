@@ -221,11 +221,27 @@ int vilco_dwconv_bwd(const float* x, const float* mask, const float* w, const fl
 /* fp32 depthwise k=3 conv * out-mask (the LayerNorm input of vilco_dwconv_ln, recomputed in the backward pass) */
 int vilco_dwconv_fwd32(const float* x, const float* mask, const float* w, float* out, int B, int T, int C, int stride,
                        void* stream);
+/* fp32 elementwise helper of the training path: op 0: x*rowmul[r]*colmul[c], 1: gelu(x), 2: relu(x), 3: x*(y>0) */
+int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const float* colmul, float* out, int64_t rows,
+             int C, void* stream);
 int vilco_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
 /* MaxPool1d(3,2,1) backward (TransformerBlock.pool_skip): dx must be pre-zeroed; gradient goes to the first maximum. */
 int vilco_maxpool3s2_bwd(const float* x, const float* dy, float* dx, int B, int T, int C, void* stream);
 /* dS[r,j] = scale * P[r,j] * (dP[r,j] - sum_k dP[r,k] P[r,k])   (softmax backward over materialised fp32 rows) */
 int vilco_softmax_bwd(const float* P, const float* dP, float* dS, int64_t rows, int Tk, float scale, void* stream);
+
+/* ChannelAttention core backward (blocks.py:423-436): dy (B,T,C) fp32, qkv planes and G (B,H,64,64) from the forward call
+ * -> dqkv (B,T,3C) fp32; dA_scratch is a (B,H,64,64) fp32 work buffer. */
+int vilco_channel_attention_bwd(const float* dy, const void* qkv, int64_t qkv_lo, const float* G, float* dA_scratch,
+                                float* dqkv, int B, int T, int C, int H, void* stream);
+
+/* Backward of vilco_mq_losses for final = cls + w_reg*reg + w_al*al (each divided by `norm`): gradients w.r.t. the logits,
+ * the offsets and the three gaussian weights (the latter feed torch autograd of the target-assignment glue, which owns
+ * mu / sigma).  smax = the (B,K) scratch filled by the forward call. */
+int vilco_mq_losses_bwd(const float* logits, const float* offsets, const float* pmask, const uint8_t* gap, const float* gt_cls,
+                        const float* gt_off, const float* w_cls, const float* w_l, const float* w_r, const float* present,
+                        const unsigned int* smax, int B, int P, int K, float alpha, float gamma, float norm, float w_reg,
+                        float w_al, float* dlogits, float* doffsets, float* dw_cls, float* dw_l, float* dw_r, void* stream);
 
 #ifdef __cplusplus
 }

@@ -99,6 +99,26 @@ def gen_model_golden():
     print("model_small:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
+def gen_grad_golden():
+    """d final_loss / d parameter from the reference's own autograd (model.eval(): dropout / drop-path identity) on the
+    model_small inputs.  Stored compactly per parameter: L2 norm, sum, and the first 8 entries of the flattened gradient."""
+    c = small_cfg()
+    model, _ = build_reference_model(c, seed=0)
+    videos = PR.synth_video_list(c, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    model.loss_normalizer = c.init_loss_norm
+    model.zero_grad()
+    losses = model(videos, is_training=True)
+    losses["final_loss"].backward()
+    out = {"final_loss": np.float32(losses["final_loss"].item())}
+    spec = PR.param_spec(c)
+    for k, p_ in model.named_parameters():
+        if k in spec and p_.grad is not None:
+            g = p_.grad.detach().reshape(-1).double()
+            out["g:" + k] = np.concatenate([[g.norm().item(), g.sum().item()], g[:8].numpy()]).astype(np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, "grads_small.npz"), **out)
+    print("grads_small:", len(out) - 1, "parameters")
+
+
 def gen_vilco_golden():
     """mq_vilco.yaml branches at inference: prompts prepended to the text, adapters on branch 0-4, EMA-adapter ensemble."""
     c = vilco_cfg()
@@ -193,3 +213,5 @@ if __name__ == "__main__":
         gen_model_golden()
     if "vilco" in what:
         gen_vilco_golden()
+    if "grads" in what:
+        gen_grad_golden()

@@ -127,3 +127,28 @@ def test_vilco_config_oracle_vs_reference_golden():
     assert _rel(torch.cat(raw[0][0], 1)[0].numpy(), g["logits_0"]) < 2e-5
     assert _rel(torch.cat(raw[0][1], 1)[0].numpy(), g["offsets_0"]) < 2e-5
     assert np.abs(res[0]["scores"].numpy() - g["det_scores_0"]).max() < 1e-5
+
+
+def test_oracle_gradients_match_reference_autograd():
+    """d final_loss / d every parameter: torch autograd through the oracle vs the reference's own autograd
+    (tests/golden/grads_small.npz, generated by oracle/gen_golden.py gen_grad_golden)."""
+    import torch
+    from oracle import gen_golden as GG
+    g = np.load(os.path.join(GOLDEN, "grads_small.npz"))
+    cfg = GG.small_cfg()
+    P = {k: v.clone().requires_grad_(True) for k, v in PR.random_state(PR.param_spec(cfg), 0).items()}
+    videos = PR.synth_video_list(cfg, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    lo, _ = O.model_train_losses(P, cfg, videos)
+    lo["final_loss"].backward()
+    assert abs(float(lo["final_loss"]) - float(g["final_loss"])) < 1e-5
+    n = 0
+    for key in g.files:
+        if not key.startswith("g:"):
+            continue
+        ref = g[key]
+        mine = P[key[2:]].grad.reshape(-1).double()
+        got = np.concatenate([[mine.norm().item(), mine.sum().item()], mine[:8].numpy()])
+        scale = max(ref[0], 1e-12)
+        assert np.abs(got - ref).max() <= 2e-4 * scale + 1e-7, (key, got[:3], ref[:3])
+        n += 1
+    assert n == 338

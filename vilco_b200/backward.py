@@ -76,7 +76,7 @@ def conv3_bwd(dy, x16, w3, w3_flip, rowmul=None, need_dx=True):
     """forward: y[b,t] = (sum_tap x[b,t+tap-1] w3[tap]^T + bias) * rowmul[b,t]   (ops.conv3).
     dy (B,T,N) fp32, x16 (NP,B,T,K), w3 / w3_flip (NP,3,N,K) (flip = taps reversed) -> (dx (B,T,K), dw3 (3,N,K), db (N,))."""
     B, T, N = dy.shape
-    K = w3.shape[3]
+    K = w3_flip.shape[3]
     dz, dzT = to_planes(dy.reshape(-1, N), rowmul.reshape(-1) if rowmul is not None else None, None, want=need_dx, want_t=True)
     dx = None
     if need_dx:

@@ -350,6 +350,134 @@ __global__ void __launch_bounds__(256) chan_attn_apply_kernel(const __nv_bfloat1
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// channel attention backward.  y[t,i] = sum_j A[i,j] q[t,j],  A = softmax_j(G),  G[i,j] = sum_t (s k[t,i]) v[t,j]
+//   dA[i,j] = sum_t dy[t,i] q[t,j]           (kernel 1, atomics over T chunks, dA pre-zeroed)
+//   dG = A o (dA - rowsum(dA o A)); dq[t,j] = sum_i dy[t,i] A[i,j]; dk[t,i] = s sum_j dG[i,j] v[t,j];
+//   dv[t,j] = s sum_i dG[i,j] k[t,i]         (kernel 2, per T chunk)
+// ---------------------------------------------------------------------------------------------
+static constexpr int CB_T = 32;
+
+__global__ void __launch_bounds__(256) chan_attn_dA_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ qkv,
+                                                           long long lo, float* __restrict__ dA, int T, int C, int H) {
+  __shared__ float sd[CA_TCHUNK][CA_D + 1];
+  __shared__ float sq[CA_TCHUNK][CA_D + 1];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int t0 = blockIdx.x * CA_TCHUNK;
+  const int nt = min(CA_TCHUNK, T - t0);
+  const long long ld = 3LL * C;
+  const __nv_bfloat16* qb = qkv + ((long long)b * T + t0) * ld + h * CA_D;
+  const float* db = dy + ((long long)b * T + t0) * C + h * CA_D;
+  for (int idx = threadIdx.x; idx < CA_TCHUNK * (CA_D / 2); idx += blockDim.x) {
+    const int r = idx / (CA_D / 2), c = (idx % (CA_D / 2)) * 2;
+    float q0 = 0.f, q1 = 0.f, d0 = 0.f, d1 = 0.f;
+    if (r < nt) {
+      const float2 x = ld2_split(qb + r * ld + c, lo);
+      q0 = x.x; q1 = x.y;
+      d0 = db[(long long)r * C + c]; d1 = db[(long long)r * C + c + 1];
+    }
+    sq[r][c] = q0; sq[r][c + 1] = q1; sd[r][c] = d0; sd[r][c + 1] = d1;
+  }
+  __syncthreads();
+  const int ti = (threadIdx.x / 16) * 4, tj = (threadIdx.x % 16) * 4;
+  float acc[4][4] = {};
+  for (int r = 0; r < CA_TCHUNK; ++r) {
+    float a[4], c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = sd[r][ti + u]; c[u] = sq[r][tj + u]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) acc[u][w] = fmaf(a[u], c[w], acc[u][w]);
+  }
+  float* g = dA + ((long long)b * H + h) * CA_D * CA_D;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) atomicAdd(g + (ti + u) * CA_D + tj + w, acc[u][w]);
+}
+
+__global__ void __launch_bounds__(256) chan_attn_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ qkv,
+                                                            long long lo, const float* __restrict__ G, const float* __restrict__ dA,
+                                                            float* __restrict__ dqkv, int T, int C, int H, float scale) {
+  __shared__ float sA[CA_D][CA_D + 1];
+  __shared__ float sG[CA_D][CA_D + 1];   // dG
+  __shared__ float sx[CB_T][CA_D + 1];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int t0 = blockIdx.x * CB_T;
+  const int nt = min(CB_T, T - t0);
+  const float* g = G + ((long long)b * H + h) * CA_D * CA_D;
+  const float* da = dA + ((long long)b * H + h) * CA_D * CA_D;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < CA_D; i += 8) {
+    const float a0 = g[i * CA_D + lane], a1 = g[i * CA_D + lane + 32];
+    const float mx = warp_max(fmaxf(a0, a1));
+    float e0 = __expf(a0 - mx), e1 = __expf(a1 - mx);
+    const float inv = 1.0f / warp_sum(e0 + e1);
+    e0 *= inv; e1 *= inv;
+    const float d0 = da[i * CA_D + lane], d1 = da[i * CA_D + lane + 32];
+    const float dot = warp_sum(d0 * e0 + d1 * e1);
+    sA[i][lane] = e0; sA[i][lane + 32] = e1;
+    sG[i][lane] = e0 * (d0 - dot); sG[i][lane + 32] = e1 * (d1 - dot);
+  }
+  const long long ld = 3LL * C;
+  const int r = threadIdx.x / 8, c0 = (threadIdx.x % 8) * 8;   // token r of the chunk, 8 outputs
+  float* out = dqkv + ((long long)b * T + t0 + r) * ld + h * CA_D + c0;
+  auto load = [&](int which) {  // 0: dy, 1: v, 2: k  -> sx
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < CB_T * CA_D; idx += blockDim.x) {
+      const int rr = idx / CA_D, cc = idx % CA_D;
+      float v = 0.f;
+      if (rr < nt) {
+        if (which == 0) v = dy[((long long)b * T + t0 + rr) * C + h * CA_D + cc];
+        else {
+          const __nv_bfloat16* p = qkv + ((long long)b * T + t0 + rr) * ld + (which == 1 ? 2 : 1) * C + h * CA_D + cc;
+          v = __bfloat162float(p[0]) + (lo ? __bfloat162float(p[lo]) : 0.f);
+        }
+      }
+      sx[rr][cc] = v;
+    }
+    __syncthreads();
+  };
+  float acc[8];
+  // dq[t, j] = sum_i dy[t, i] A[i, j]
+  load(0);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  for (int i = 0; i < CA_D; ++i) {
+    const float d = sx[r][i];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = fmaf(d, sA[i][c0 + u], acc[u]);
+  }
+  if (r < nt)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) out[u] = acc[u];
+  // dk[t, i] = s * sum_j dG[i, j] v[t, j]
+  load(1);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  for (int j = 0; j < CA_D; ++j) {
+    const float v = sx[r][j];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = fmaf(sG[c0 + u][j], v, acc[u]);
+  }
+  if (r < nt)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) out[C + u] = acc[u] * scale;
+  // dv[t, j] = s * sum_i dG[i, j] k[t, i]
+  load(2);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  for (int i = 0; i < CA_D; ++i) {
+    const float k = sx[r][i];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = fmaf(sG[i][c0 + u], k, acc[u]);
+  }
+  if (r < nt)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) out[2 * C + u] = acc[u] * scale;
+}
+
 }  // namespace vilco
 
 using namespace vilco;
@@ -412,6 +540,21 @@ extern "C" int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G
   chan_attn_kv_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, tlen, T, C, H, 1.0f / sqrtf((float)CA_D));
   VILCO_LAUNCH_CHECK();
   chan_attn_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, static_cast<__nv_bfloat16*>(y), y_lo, T, C, H);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_channel_attention_bwd(const float* dy, const void* qkv, int64_t qkv_lo, const float* G, float* dA_scratch,
+                                           float* dqkv, int B, int T, int C, int H, void* stream) {
+  VILCO_CHECK_ARG(dy && qkv && G && dA_scratch && dqkv, "vilco_channel_attention_bwd: null pointer");
+  VILCO_CHECK_ARG(H > 0 && C == H * CA_D, "vilco_channel_attention_bwd: head dim must be 64");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VILCO_CUDA(cudaMemsetAsync(dA_scratch, 0, sizeof(float) * (size_t)B * H * CA_D * CA_D, st));
+  chan_attn_dA_kernel<<<dim3((T + CA_TCHUNK - 1) / CA_TCHUNK, H, B), 256, 0, st>>>(
+      dy, static_cast<const __nv_bfloat16*>(qkv), qkv_lo, dA_scratch, T, C, H);
+  VILCO_LAUNCH_CHECK();
+  chan_attn_bwd_kernel<<<dim3((T + CB_T - 1) / CB_T, H, B), 256, 0, st>>>(
+      dy, static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, dA_scratch, dqkv, T, C, H, 1.0f / sqrtf((float)CA_D));
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

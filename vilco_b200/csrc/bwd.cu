@@ -241,6 +241,22 @@ __global__ void relshift_bwd_kernel(const float* __restrict__ dS, float* __restr
   }
 }
 
+// generic fp32 elementwise helper: op 0: x*rowmul*colmul, 1: gelu(x), 2: relu(x), 3: x * (y > 0)  (ReLU backward)
+__global__ void ew_kernel(int op, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ rowmul,
+                          const float* __restrict__ colmul, float* __restrict__ out, long long rows, int C) {
+  const long long n = rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (op == 0) {
+      if (rowmul) v *= rowmul[i / C];
+      if (colmul) v *= colmul[i % C];
+    } else if (op == 1) v = gelu_erf(v);
+    else if (op == 2) v = fmaxf(v, 0.f);
+    else if (op == 3) v = y[i] > 0.f ? v : 0.f;
+    out[i] = v;
+  }
+}
+
 // dx = dy * gelu'(x)
 __global__ void gelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -381,6 +397,14 @@ extern "C" int vilco_dwconv_fwd32(const float* x, const float* mask, const float
 extern "C" int vilco_relshift_bwd(const float* dS, float* dBD, int64_t Z, int T, void* stream) {
   VILCO_CHECK_ARG(dS && dBD && Z > 0 && T > 0, "vilco_relshift_bwd: bad arguments");
   relshift_bwd_kernel<<<bgrid(Z * T * T, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dS, dBD, Z, T);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const float* colmul, float* out,
+                        int64_t rows, int C, void* stream) {
+  VILCO_CHECK_ARG(x && out && rows > 0 && C > 0 && op >= 0 && op <= 3 && (op != 3 || y), "vilco_ew: bad arguments");
+  ew_kernel<<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(op, x, y, rowmul, colmul, out, rows, C);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

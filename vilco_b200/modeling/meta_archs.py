@@ -116,6 +116,20 @@ class Prompt(nn.Module):
         return out
 
 
+class _TapeLoss(torch.autograd.Function):
+    """Connects the hand-written backward pass to torch autograd: backward(g) replays the tape scaled by g."""
+
+    @staticmethod
+    def forward(ctx, hook, value, run_backward):
+        ctx.run_backward = run_backward
+        return value.detach().clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.run_backward(float(g))
+        return torch.zeros_like(g), None, None
+
+
 class _Head(nn.Module):
     def __init__(self, input_dim, feat_dim, num_layers, kernel_size, with_ln):
         super().__init__()
@@ -454,6 +468,8 @@ class PtTransformer(nn.Module):
                 prev_out_cls_logits=None, get_emb=False, val_qilDatasetList=None):
         if not is_training and not get_emb:
             assert len(video_list) >= 1
+        if is_training and not get_emb and torch.is_grad_enabled():
+            return self._train_forward(video_list, task_id, prev_out_cls_logits)
         vl, logits, offsets, pmask, pyr = self._network(video_list, is_training, task_id)
         if self.n_known > 0 and self.cl_name == "bic":  # BiasLayer on class slices (meta_archs.py:823-836)
             parts, lo_ = [], 0
@@ -479,6 +495,90 @@ class PtTransformer(nn.Module):
             msk_l = [pmask[:, o:o + n].bool() for o, n in zip(pyr.off, pyr.lens)]
             return video_list, points, msk_l, cls_l, off_l
         return results
+
+    # ---- training step: taped forward on the CUDA kernels + hand-written backward -------------------------------
+    def _train_forward(self, video_list, task_id=-1, prev_out_cls_logits=None):
+        """forward(is_training=True) with gradients: returns the reference's loss dict; `final_loss.backward()` runs the
+        CUDA backward pass (vilco_b200/train_engine.py) and accumulates into every parameter's .grad.  mu / sigma (and
+        the L2P prompt pool) receive their gradients through torch autograd of the small target-assignment glue."""
+        from .. import train_engine as TE
+        if self.n_known > 0 and self.cl_name in ("bic", "icarl"):
+            raise NotImplementedError("BiC / iCaRL distillation terms of the training loss are not built yet")
+        dev = self.device
+        vl, batched, mask = self.preprocessing(video_list, True)
+        text = tmask = None
+        self._reduce_sim = None
+        if self.use_cross_modal:
+            text, tmask, tlens = self.query_preprocessing(vl)
+            if hasattr(self, "prompt"):
+                text, tmask, tlens, self._reduce_sim = self._prompted_text(text, tlens, True, task_id)
+            text = text.contiguous()
+        W = self.packed_weights()
+        cfg = self.engine_cfg()
+        tp = TE.Tape(W)
+        with torch.no_grad():
+            x16 = ops.pack_feats(batched)
+            t16 = ops.pack_feats(text.detach()) if text is not None else None
+            feats, masks, tin = TE.backbone(tp, cfg, x16, mask.contiguous(), t16, tmask, self._pe)
+            if tin is not None and not text.requires_grad:
+                tin.const = True
+            logitsV, offsetsV, pmask, pyr = TE.neck_heads(tp, cfg, feats, masks)
+            logits, offsets = logitsV.v, offsetsV.v
+        B, P, K = logits.shape
+        gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
+        with torch.no_grad():
+            gt_cls, gt_off = gt_cls.detach(), gt_off.detach()
+            if self.train_label_smoothing > 0:
+                gt_cls = gt_cls * (1 - self.train_label_smoothing) + self.train_label_smoothing / (K + 1)
+            present = torch.zeros(B, K, device=dev)
+            for i, x in enumerate(vl):
+                present[i, x["labels"].to(dev)] = 1
+            sums = torch.zeros(4, device=dev)
+            scratch = torch.zeros(B * K, device=dev, dtype=torch.int32)
+            wcd, wld, wrd = wc.detach().contiguous(), wl.detach().contiguous(), wr.detach().contiguous()
+            L.check(L.lib().vilco_mq_losses(
+                ops._p(logits), ops._p(offsets), ops._p(pmask), ops._p(pyr.gap_rows), ops._p(gt_cls), ops._p(gt_off),
+                ops._p(wcd), ops._p(wld), ops._p(wrd), ops._p(present), B, P, K, C.c_float(0.25), C.c_float(2.0), ops._p(sums),
+                ops._p(scratch), L.stream_ptr()), "vilco_mq_losses")
+            s = sums.cpu()
+            self.loss_normalizer = self.loss_normalizer_momentum * self.loss_normalizer + \
+                (1 - self.loss_normalizer_momentum) * max(float(s[2]), 1)
+            norm = float(self.loss_normalizer)
+            cls_loss, reg_loss = sums[0] / norm, sums[1] / norm
+            al_loss = sums[3] / norm if K != 1 else torch.zeros((), device=dev)
+            w_reg = self.train_loss_weight if self.train_loss_weight > 0 else float(s[0] / norm) / max(float(s[1] / norm), 0.01)
+            w_al = self.al_loss_weight if K != 1 else 0.0
+            final = cls_loss + reg_loss * w_reg + al_loss * w_al
+        named = dict(self.named_parameters())
+        model = self
+
+        def run_backward(gscale):
+            with torch.no_grad():
+                dlogits, doffsets = torch.zeros_like(logits), torch.zeros_like(offsets)
+                dwc, dwl, dwr = torch.zeros_like(wcd), torch.zeros_like(wld), torch.zeros_like(wrd)
+                L.check(L.lib().vilco_mq_losses_bwd(
+                    ops._p(logits), ops._p(offsets), ops._p(pmask), ops._p(pyr.gap_rows), ops._p(gt_cls), ops._p(gt_off),
+                    ops._p(wcd), ops._p(wld), ops._p(wrd), ops._p(present), ops._p(scratch), B, P, K, C.c_float(0.25),
+                    C.c_float(2.0), C.c_float(norm / gscale), C.c_float(w_reg), C.c_float(w_al), ops._p(dlogits),
+                    ops._p(doffsets), ops._p(dwc), ops._p(dwl), ops._p(dwr), L.stream_ptr()), "vilco_mq_losses_bwd")
+                logitsV.g, offsetsV.g = dlogits, doffsets
+                model._last_head_grads = (dlogits, doffsets, pyr)   # kept for the gradient parity tests
+                tp.backward()
+                for key, g in tp.G.items():
+                    prm = named.get(key)
+                    if prm is None or not prm.requires_grad:
+                        continue
+                    g = TE.unpack_grad(key, g, prm).to(prm.dtype)
+                    prm.grad = g.clone() if prm.grad is None else prm.grad + g
+            glue = [(t_, g_) for t_, g_ in ((wc, dwc), (wl, dwl), (wr, dwr)) if t_.requires_grad]
+            if tin is not None and text.requires_grad and tin.g is not None:
+                glue.append((text, ops.unpack(tin.g)))
+            if glue:
+                torch.autograd.backward([t_ for t_, _ in glue], [g_ for _, g_ in glue])
+
+        hook = torch.zeros((), device=dev, requires_grad=True)
+        final_t = _TapeLoss.apply(hook, final, run_backward)
+        return {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final_t}
 
     # ---- targets + losses (reference: meta_archs.py:1224-1344, 1374-1524) --------------------------------
     def _label_points(self, pyr, gt_segments, gt_labels):

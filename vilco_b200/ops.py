@@ -230,11 +230,20 @@ def local_attention(q, k, v, mask, H, W, rel_pe=None):
     return out
 
 
-def channel_attention(qkv, H, tlen=None):
+def channel_attention(qkv, H, tlen=None, return_G=False):
     _, B, T, C3 = qkv.shape
     Cc = C3 // 3
     G = torch.empty(B, H, 64, 64, device=qkv.device, dtype=f32)
     y = empty16(B, T, Cc, device=qkv.device)
     L.check(L.lib().vilco_channel_attention(_p(qkv), _i64(lo(qkv)), _p(G), _p(y), _i64(lo(y)), _p(tlen), B, T, Cc, H,
                                             L.stream_ptr()), "vilco_channel_attention")
-    return y
+    return (y, G) if return_G else y
+
+
+def ew(op, x, y=None, rowmul=None, colmul=None):
+    """fp32 elementwise helper (training path): op 0: x*rowmul*colmul, 1: gelu, 2: relu, 3: x*(y>0)."""
+    out = torch.empty_like(x)
+    Cc = x.shape[-1]
+    L.check(L.lib().vilco_ew(op, _p(x), _p(y), _p(rowmul), _p(colmul), _p(out), _i64(x.numel() // Cc), Cc, L.stream_ptr()),
+            "vilco_ew")
+    return out

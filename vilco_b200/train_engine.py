@@ -1,0 +1,445 @@
+"""Training path of the Moment-Query model on the sm_100a kernels: forward with a tape, hand-written backward.
+
+Every operator of vilco_b200/engine.py has a differentiable twin here (`Tape.*`); the forward records a closure per
+operator, `Tape.backward()` replays them in reverse.  Gradients are fp32 token-major tensors; parameter gradients are
+accumulated in the packed-weight layout (`tape.G`) and mapped back to the nn.Parameter shapes by `unpack_grads`.
+Dropout / stochastic depth are not built yet: the training forward uses the evaluation semantics of those layers
+(AffineDropPath = its per-channel scale), which is exactly what the gradient-parity tests compare against.
+"""
+import ctypes as CT
+import math
+
+import torch
+
+from . import backward as BW
+from . import engine as E
+from . import lib as L
+from . import ops
+from .ops import _i64, _p, bf16, f32, lo
+
+
+class V:
+    """value + gradient; `p16` caches the bf16 (hi, lo) operand planes of `v`; const = no gradient wanted."""
+    __slots__ = ("v", "g", "p16", "const")
+
+    def __init__(self, v=None, p16=None, const=False):
+        self.v, self.g, self.p16, self.const = v, None, p16, const
+
+    @property
+    def shape(self):
+        return self.v.shape if self.v is not None else self.p16.shape[1:]
+
+
+def _add(a, b):
+    return ops.axpby(a, b, 1.0, 1.0)[0]
+
+
+class Tape:
+    def __init__(self, W):
+        self.W = W
+        self.G = {}       # packed-layout parameter gradients
+        self.nodes = []
+
+    # ---- plumbing ----
+    def acc(self, x, g):
+        if x is None or g is None or x.const:
+            return
+        g = g.reshape(x.shape)
+        x.g = g.contiguous() if x.g is None else _add(x.g, g.contiguous())
+
+    def accp(self, key, g):
+        if g is None:
+            return
+        self.G[key] = g if key not in self.G else _add(self.G[key], g)
+
+    def planes(self, x):
+        if x.p16 is None:
+            y, _ = BW.to_planes(x.v.reshape(-1, x.v.shape[-1]))
+            x.p16 = y.reshape(y.shape[0], *x.v.shape)
+        return x.p16
+
+    def backward(self):
+        for fn in reversed(self.nodes):
+            fn()
+        self.nodes = []
+
+    # ---- operators ----
+    def linear(self, x, wkey, bkey=None, rowmul=None, bias=None):
+        """y = (x w^T + b) * rowmul.  `bias` overrides W[bkey] (XLNet r_w / r_r)."""
+        W = self.W
+        x16 = self.planes(x)
+        b = bias if bias is not None else (W[bkey] if bkey else None)
+        y = V(ops.linear(x16, W[wkey], f32, bias=b, rowmul=rowmul))
+
+        def bwd():
+            if y.g is None:
+                return
+            dx, dw, db = BW.linear_bwd(y.g, x16, W[wkey], rowmul=rowmul, need_dx=not x.const, need_db=b is not None)
+            self.acc(x, dx)
+            self.accp(wkey, dw)
+            if bkey:
+                self.accp(bkey, db)
+        self.nodes.append(bwd)
+        return y
+
+    def conv3(self, x, wkey, bkey=None, rowmul=None):
+        W = self.W
+        x16 = self.planes(x)
+        y = V(ops.conv3(x16, W[wkey], f32, bias=W[bkey] if bkey else None, rowmul=rowmul))
+        if wkey + ".flip" not in W:
+            W[wkey + ".flip"] = W[wkey].flip(1).contiguous()
+
+        N = W[wkey].shape[2]
+        N8 = (N + 7) // 8 * 8
+        if N8 != N and wkey + ".flip8" not in W:     # dgrad contracts over N: keep 16-byte operand rows
+            wp = torch.zeros(W[wkey].shape[0], 3, N8, W[wkey].shape[3], device=y.v.device, dtype=bf16)
+            wp[:, :, :N] = W[wkey + ".flip"]
+            W[wkey + ".flip8"] = wp
+
+        def bwd():
+            if y.g is None:
+                return
+            if N8 != N:
+                g8 = torch.zeros(*y.g.shape[:-1], N8, device=y.g.device, dtype=f32)
+                g8[..., :N] = y.g
+                dx, dw, db = BW.conv3_bwd(g8, x16, None, W[wkey + ".flip8"], rowmul=rowmul)
+                dw, db = dw[:, :N].contiguous(), db[:N].contiguous()
+            else:
+                dx, dw, db = BW.conv3_bwd(y.g, x16, W[wkey], W[wkey + ".flip"], rowmul=rowmul)
+            self.acc(x, dx)
+            self.accp(wkey, dw)
+            if bkey:
+                self.accp(bkey, db)
+        self.nodes.append(bwd)
+        return y
+
+    def gelu(self, x):
+        y = V(ops.ew(1, x.v))
+        self.nodes.append(lambda: self.acc(x, BW.gelu_bwd(y.g, x.v)) if y.g is not None else None)
+        return y
+
+    def relu(self, x):
+        y = V(ops.ew(2, x.v))
+        self.nodes.append(lambda: self.acc(x, ops.ew(3, y.g, y=y.v)) if y.g is not None else None)
+        return y
+
+    def ln(self, x, wkey, bkey, eps=1e-5, relu=False, pe=None, rowmul=None, zero_rows=None, keep_rows=None):
+        """channel LayerNorm (+ReLU, + pe*rowmul constant, rows flagged in zero_rows forced to 0)."""
+        W = self.W
+        y32, _ = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, out32=True, out16=False, zero_rows=zero_rows)
+        if pe is not None:   # constant positional term, no gradient
+            y32, _ = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, pe=pe, rowmul=rowmul, out32=True, out16=False,
+                                   rows_per_batch=x.v.shape[1])
+            yr, _ = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, out32=True, out16=False)
+        else:
+            yr = y32
+        y = V(y32)
+
+        def bwd():
+            if y.g is None:
+                return
+            g = y.g if keep_rows is None else ops.ew(0, y.g, rowmul=keep_rows)
+            dx, dw, db = BW.layernorm_bwd(g, x.v, W[wkey], eps, y_relu=yr if relu else None)
+            self.acc(x, dx)
+            self.accp(wkey, dw)
+            self.accp(bkey, db)
+        self.nodes.append(bwd)
+        return y
+
+    def dwconv_ln3(self, x, pre, mask, stride):
+        W = self.W
+        names = ("query", "key", "value")
+        wc = [W[pre + f"{n}_conv.conv.weight"] for n in names]
+        lw = [W[pre + f"{n}_norm.weight"] for n in names]
+        lb = [W[pre + f"{n}_norm.bias"] for n in names]
+        outs = [V(p16=o) for o in ops.dwconv_ln(x.v, mask, wc, lw, lb, stride)]
+
+        def bwd():
+            B, T, Cc = x.v.shape
+            dys = [o.g if o.g is not None else torch.zeros(B, T // stride, Cc, device=x.v.device) for o in outs]
+            dx, dwc, dlw, dlb = BW.dwconv_ln_bwd(dys, x.v, mask, wc, lw, stride)
+            self.acc(x, dx)
+            for n, a, b_, c in zip(names, dwc, dlw, dlb):
+                self.accp(pre + f"{n}_conv.conv.weight", a)
+                self.accp(pre + f"{n}_norm.weight", b_)
+                self.accp(pre + f"{n}_norm.bias", c)
+        self.nodes.append(bwd)
+        return outs
+
+    def attention(self, q, k, v, kmask, H, scale):
+        q16, k16, v16 = self.planes(q), self.planes(k), self.planes(v)
+        o = V(p16=ops.attention(q16, k16, v16, kmask, H, scale))
+
+        def bwd():
+            if o.g is None:
+                return
+            dq, dk, dv = BW.attention_bwd(o.g, q16, k16, v16, kmask, H, scale)
+            self.acc(q, dq); self.acc(k, dk); self.acc(v, dv)
+        self.nodes.append(bwd)
+        return o
+
+    def resid_scale(self, resid, rowmul, y, skey):
+        """out = resid * rowmul[row] + scale[c] * y"""
+        s = self.W.get(skey) if skey else None
+        out = V(ops.scale_add(resid.v, rowmul, y.v, s))
+
+        def bwd():
+            if out.g is None:
+                return
+            self.acc(resid, out.g if rowmul is None else ops.ew(0, out.g, rowmul=rowmul))
+            self.acc(y, out.g if s is None else ops.ew(0, out.g, colmul=s))
+            if s is not None:
+                self.accp(skey, BW.colsum(out.g, y=y.v))
+        self.nodes.append(bwd)
+        return out
+
+    def mix(self, a, b, wa=1.0, wb=1.0):
+        out = V(ops.axpby(a.v, b.v, wa, wb)[0])
+
+        def bwd():
+            if out.g is None:
+                return
+            self.acc(a, out.g if wa == 1.0 else ops.axpby(out.g, None, wa, 0.0)[0])
+            self.acc(b, out.g if wb == 1.0 else ops.axpby(out.g, None, wb, 0.0)[0])
+        self.nodes.append(bwd)
+        return out
+
+    def transpose(self, x):
+        """(B,T,C) -> (B,C,T)"""
+        y = V(ops.unpack(x.v))
+        self.nodes.append(lambda: self.acc(x, ops.unpack(y.g)) if y.g is not None else None)
+        return y
+
+    def maxpool(self, x):
+        y = V(ops.maxpool3s2(x.v))
+        self.nodes.append(lambda: self.acc(x, BW.maxpool3s2_bwd(y.g, x.v)) if y.g is not None else None)
+        return y
+
+    def channel_attention(self, qkv, H):
+        q16 = self.planes(qkv)
+        y16, G = ops.channel_attention(q16, H, return_G=True)
+        y = V(p16=y16)
+
+        def bwd():
+            if y.g is None:
+                return
+            _, B, T, C3 = q16.shape
+            dqkv = torch.empty(B, T, C3, device=y.g.device, dtype=f32)
+            dA = torch.empty_like(G)
+            L.check(L.lib().vilco_channel_attention_bwd(_p(y.g.contiguous()), _p(q16), _i64(lo(q16)), _p(G), _p(dA), _p(dqkv),
+                                                        B, T, C3 // 3, H, L.stream_ptr()), "vilco_channel_attention_bwd")
+            self.acc(qkv, dqkv)
+        self.nodes.append(bwd)
+        return y
+
+
+# ----------------------------------------------------------------------------------------------------
+# differentiable blocks (same structure as engine.py; citations there)
+# ----------------------------------------------------------------------------------------------------
+def adapter(tp, pre, ln1):
+    """meta_archs.Adapter.layer over the time axis (meta_archs.py:105-148): (B,T,C) -> (B,T/2,C)."""
+    xt = tp.transpose(ln1)                                              # (B,C,T)
+    h = tp.gelu(tp.linear(xt, pre + "layer.0.weight", pre + "layer.0.bias"))
+    return tp.transpose(tp.linear(h, pre + "layer.2.weight", pre + "layer.2.bias"))
+
+
+def transformer_block(tp, pre, x, mask, H, stride, cross=None, t_c_alpha=0.8, adapter_pre=None):
+    W = tp.W
+    C = x.shape[-1]
+    scale = 1.0 / math.sqrt(C // H)
+    ln1 = tp.ln(x, pre + "ln1.weight", pre + "ln1.bias")
+    qc, kc, vc = tp.dwconv_ln3(ln1, pre + "attn.", mask, stride)
+    om = mask[:, ::stride].contiguous() if stride > 1 else mask
+    omf = om.reshape(-1)
+    q = tp.linear(qc, pre + "attn.query.weight", pre + "attn.query.bias")
+    k = tp.linear(kc, pre + "attn.key.weight", pre + "attn.key.bias")
+    v = tp.linear(vc, pre + "attn.value.weight", pre + "attn.value.bias", rowmul=omf)
+    o = tp.attention(q, k, v, om, H, scale)
+    proj = tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias", rowmul=omf)
+    skip = x if stride == 1 else tp.maxpool(x)
+    sa = pre + "drop_path_attn.scale" if (pre + "drop_path_attn.scale") in W else None
+    sm = pre + "drop_path_mlp.scale" if (pre + "drop_path_mlp.scale") in W else None
+    if adapter_pre is not None:          # out = attn(ln1 x) + adapter(ln1 x), the adapter output is not masked
+        proj = tp.mix(proj, adapter(tp, adapter_pre, ln1))
+    h = tp.resid_scale(skip, omf, proj, sa)
+    if cross is not None and (pre + "cross_attn.query.weight") in W:
+        text, tmask = cross
+        hx = tp.ln(h, pre + "ln3.weight", pre + "ln3.bias")
+        hy = tp.ln(text, pre + "ln3.weight", pre + "ln3.bias")
+        cq = tp.linear(hx, pre + "cross_attn.query.weight", pre + "cross_attn.query.bias")
+        ck = tp.linear(hy, pre + "cross_attn.key.weight", pre + "cross_attn.key.bias")
+        cv = tp.linear(hy, pre + "cross_attn.value.weight", pre + "cross_attn.value.bias", rowmul=tmask.reshape(-1))
+        c = tp.attention(cq, ck, cv, tmask, H, scale)
+        cp = tp.linear(c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias", rowmul=omf)
+        h = tp.resid_scale(h, omf, cp, sa)
+    h2 = tp.ln(h, pre + "ln2.weight", pre + "ln2.bias")
+    m1 = tp.gelu(tp.linear(h2, pre + "mlp.0.weight", pre + "mlp.0.bias"))
+    m2 = tp.linear(m1, pre + "mlp.3.weight", pre + "mlp.3.bias", rowmul=omf)
+    out = tp.resid_scale(h, None, m2, sm)
+    if stride == 1:
+        cpre = pre + "channel_attn."
+        qkv = tp.linear(ln1, cpre + "attn.qkv.weight")
+        y = tp.channel_attention(qkv, H)
+        x1 = tp.mix(ln1, tp.linear(y, cpre + "attn.proj.weight", cpre + "attn.proj.bias"))
+        n2 = tp.ln(x1, cpre + "norm2.weight", cpre + "norm2.bias", 1e-5)
+        hh = tp.linear(tp.gelu(tp.linear(n2, cpre + "mlp.0.weight", cpre + "mlp.0.bias")), cpre + "mlp.2.weight", cpre + "mlp.2.bias")
+        out2 = tp.mix(x1, hh)
+        out = tp.mix(out, out2, t_c_alpha, 1.0 - t_c_alpha)
+    return out, om
+
+
+def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
+    W = tp.W
+    B, T, C = x.shape
+    d = C // H
+    scale = 1.0 / math.sqrt(d)
+    kq, kk, kv, ko, kr = (pre + "rel_attn." + n for n in "qkvor")
+    rw, rr = pre + "rel_attn.r_w_bias", pre + "rel_attn.r_r_bias"
+    qw = tp.linear(x, kq, rw)
+    qr = tp.linear(x, kq, rr)
+    k = tp.linear(x, kk)
+    v = tp.linear(x, kv)
+    pos = V(p16=E.xlnet_pos_emb(T, C, x.v.device))             # constant (2T, C)
+    krel1 = tp.linear(pos, kr)                                 # (2T, C) fp32, depends on W_r only
+    krel = V(krel1.v.unsqueeze(0).expand(B, 2 * T, C).contiguous())
+    qw16, qr16, k16, v16, kr16 = (tp.planes(t) for t in (qw, qr, k, v, krel))
+    ac = ops.attn_scores(qw16, k16, H, 1.0)
+    bd = ops.attn_scores(qr16, kr16, H, 1.0, band=(T, 2 * T))
+    P16, P32 = ops.softmax_rows(ac, mask, mode=1, BD=bd, scale=scale, want32=True)
+    del ac, bd
+    vec = V(ops.attn_pv(P16, v16, H, T, out32=True))
+
+    def bwd():
+        if vec.g is None:
+            return
+        dvec16, _ = BW.to_planes(vec.g.reshape(-1, C))
+        dvec16 = dvec16.reshape(dvec16.shape[0], B, T, C)
+        dP = ops.attn_scores(dvec16, v16, H, 1.0)
+        dS = torch.empty_like(dP)
+        L.check(L.lib().vilco_softmax_bwd(_p(P32), _p(dP), _p(dS), _i64(B * H * T), T, CT.c_float(scale), L.stream_ptr()),
+                "vilco_softmax_bwd")
+        del dP
+        dBD = torch.zeros(B, H, T, 2 * T, device=dS.device, dtype=f32)
+        L.check(L.lib().vilco_relshift_bwd(_p(dS), _p(dBD), _i64(B * H), T, L.stream_ptr()), "vilco_relshift_bwd")
+        dS16, dST16 = BW.to_planes(dS, want=True, want_t=True, batch_dims=2)
+        tp.acc(qw, ops.attn_pv(dS16, k16, H, T, out32=True))
+        tp.acc(k, ops.attn_pv(dST16, qw16, H, T, out32=True))
+        _, PT16 = BW.to_planes(P32, want=False, want_t=True, batch_dims=2)
+        tp.acc(v, ops.attn_pv(PT16, dvec16, H, T, out32=True))
+        dBD16, dBDT16 = BW.to_planes(dBD, want=True, want_t=True, batch_dims=2)
+        tp.acc(qr, ops.attn_pv(dBD16, kr16, H, 2 * T, out32=True))
+        tp.acc(krel, ops.attn_pv(dBDT16, qr16, H, T, out32=True))
+        # krel is the batch broadcast of krel1
+        g1 = krel.g[0]
+        for b in range(1, B):
+            g1 = _add(g1.contiguous(), krel.g[b].contiguous())
+        tp.acc(krel1, g1)
+    tp.nodes.append(bwd)
+    a = tp.mix(tp.linear(vec, ko), x)
+    h1 = tp.ln(a, pre + "rel_attn.layer_norm.weight", pre + "rel_attn.layer_norm.bias", eps)
+    f = tp.linear(tp.gelu(tp.linear(h1, pre + "ff.layer_1.weight", pre + "ff.layer_1.bias")), pre + "ff.layer_2.weight",
+                  pre + "ff.layer_2.bias")
+    return tp.ln(tp.mix(f, h1), pre + "ff.layer_norm.weight", pre + "ff.layer_norm.bias", eps)
+
+
+def backbone(tp, cfg, x16, mask, text16, tmask, pe, pets_prefix="pets."):
+    """ConvTransformerBackbone.forward (backbones.py:181-289), training batch semantics (padded text participates).
+    Returns (feats, masks, text input V or None)."""
+    pre = "backbone."
+    H = cfg.n_head
+    m = mask.reshape(-1)
+    x = tp.linear(V(p16=x16, const=True), pre + "proj.0.conv.weight", pre + "proj.0.conv.bias", rowmul=m)
+    n_embd = cfg.arch[0]
+    for i in range(n_embd):
+        c = tp.conv3(x, pre + f"embd.{i}.conv.weight", None, rowmul=mask)
+        last = i == n_embd - 1
+        x = tp.ln(c, pre + f"embd_norm.{i}.weight", pre + f"embd_norm.{i}.bias", relu=True, pe=pe if last else None,
+                  rowmul=m if last else None)
+    cross, tin = None, None
+    if cfg.use_cross_modal and text16 is not None:
+        tm = tmask.reshape(-1)
+        t = tin = V(p16=text16)
+        for i in range(n_embd):
+            c = tp.linear(t, pre + f"txt_embd.{i}.conv.weight", None, rowmul=tm)
+            t = tp.ln(c, pre + f"txt_embd_norm.{i}.weight", pre + f"txt_embd_norm.{i}.bias", relu=True)
+        for i in range(cfg.arch[1]):
+            t, _ = transformer_block(tp, pre + f"txt_stem.{i}.", t, tmask, H, 1, t_c_alpha=0.8)
+        cross = (t, tmask)
+    for i in range(cfg.arch[1]):
+        x, _ = transformer_block(tp, pre + f"stem.{i}.", x, mask, H, 1, t_c_alpha=cfg.t_c_alpha)
+    feats, masks = [x], [mask]
+    if cfg.use_xl and cfg.arch[2] > 0:
+        x = xlnet_layer(tp, pre + "xlnet.layer.0.", x, mask, H)
+    for i in range(cfg.arch[2]):
+        cr = None if i in (1, 2) else cross
+        ad = (pets_prefix + f"{list(cfg.adapt_blocks).index(i)}.") if i in cfg.adapt_blocks else None
+        x, mask = transformer_block(tp, pre + f"branch.{i}.", x, mask, H, cfg.scale_factor, cross=cr, t_c_alpha=cfg.t_c_alpha,
+                                    adapter_pre=ad)
+        feats.append(x)
+        masks.append(mask)
+    return feats, masks, tin
+
+
+def neck_heads(tp, cfg, feats, masks):
+    W = tp.W
+    B, C = feats[0].shape[0], cfg.embd_dim
+    dev = feats[0].v.device
+    pyr = E.Pyramid([f.shape[1] for f in feats], dev)
+    P = pyr.P
+    lv = [tp.ln(f, f"neck.fpn_norms.{l}.weight", f"neck.fpn_norms.{l}.bias") for l, f in enumerate(feats)]
+    fpn = V(torch.zeros(B, P, C, device=dev, dtype=f32))
+    pmask = torch.zeros(B, P, device=dev, dtype=f32)
+    lvl_of_row = torch.full((P,), -1, device=dev, dtype=torch.long)
+    for l, (f, mk) in enumerate(zip(lv, masks)):
+        o, n = pyr.off[l], pyr.lens[l]
+        fpn.v[:, o:o + n] = f.v
+        pmask[:, o:o + n] = mk
+        lvl_of_row[o:o + n] = l
+
+    def cat_bwd():
+        if fpn.g is None:
+            return
+        for l, f in enumerate(lv):
+            o, n = pyr.off[l], pyr.lens[l]
+            tp.acc(f, fpn.g[:, o:o + n].contiguous())
+    tp.nodes.append(cat_bwd)
+    zero_rows = pyr.gap_rows.repeat(B)
+    keep = (1.0 - pyr.gap_rows.float()).repeat(B).contiguous()
+    outs = []
+    for head in ("cls_head.", "reg_head."):
+        x = fpn
+        for i in range(2):
+            c = tp.conv3(x, head + f"head.{i}.conv.weight", None, rowmul=pmask)
+            x = tp.ln(c, head + f"norm.{i}.weight", head + f"norm.{i}.bias", relu=True, zero_rows=zero_rows, keep_rows=keep)
+        if head == "cls_head.":
+            outs.append(tp.conv3(x, "cls_head.cls_head.conv.weight", "cls_head.cls_head.conv.bias", rowmul=pmask))
+        else:
+            z = tp.conv3(x, "reg_head.offset_head.conv.weight", "reg_head.offset_head.conv.bias", rowmul=pmask)
+            scales = torch.stack([W[f"reg_head.scale.{l}.scale"].reshape(()) for l in range(len(feats))])
+            sv = torch.where(lvl_of_row >= 0, scales[lvl_of_row.clamp(min=0)], torch.zeros((), device=dev)).repeat(B).contiguous()
+            s = V(ops.ew(0, z.v, rowmul=sv))
+
+            def sc_bwd(s=s, z=z, sv=sv):
+                if s.g is None:
+                    return
+                tp.acc(z, ops.ew(0, s.g, rowmul=sv))
+                r = (s.g * z.v).sum(-1).sum(0)            # (P,) tiny glue reduction for the per-level Scale parameters
+                for l in range(len(feats)):
+                    tp.accp(f"reg_head.scale.{l}.scale", r[lvl_of_row == l].sum().reshape(1))
+            tp.nodes.append(sc_bwd)
+            outs.append(tp.relu(s))
+    return outs[0], outs[1], pmask, pyr
+
+
+# ----------------------------------------------------------------------------------------------------
+# packed gradient -> nn.Parameter layout (inverse of engine.pack_weights)
+# ----------------------------------------------------------------------------------------------------
+def unpack_grad(key, g, param):
+    last = key.rsplit(".", 1)[-1]
+    if ".rel_attn." in key and last in ("q", "k", "v", "r"):
+        return g.t().reshape(param.shape)
+    if key.endswith("_conv.conv.weight"):
+        return g.t().reshape(param.shape)
+    if last == "weight" and param.dim() == 3 and param.shape[2] == 3 and param.shape[0] != 1:
+        return g.permute(1, 2, 0).reshape(param.shape)
+    return g.reshape(param.shape)
