@@ -235,6 +235,10 @@ int vilco_softmax_bwd(const float* P, const float* dP, float* dS, int64_t rows, 
 int vilco_channel_attention_bwd(const float* dy, const void* qkv, int64_t qkv_lo, const float* G, float* dA_scratch,
                                 float* dqkv, int B, int T, int C, int H, void* stream);
 
+/* Inverted dropout (nn.Dropout in training mode — blocks.py:222-223, 536-538): out = keep(seed, i) ? x / (1 - p) : 0 with a
+ * counter-based generator; calling it on the gradient with the same seed is the backward pass. */
+int vilco_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream);
+
 /* Backward of vilco_mq_losses for final = cls + w_reg*reg + w_al*al (each divided by `norm`): gradients w.r.t. the logits,
  * the offsets and the three gaussian weights (the latter feed torch autograd of the target-assignment glue, which owns
  * mu / sigma).  smax = the (B,K) scratch filled by the forward call. */

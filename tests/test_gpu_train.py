@@ -1,0 +1,182 @@
+"""Training path on the B200: hand-written backward (vilco_b200/train_engine.py) vs torch autograd through the oracle.
+
+Three layers of evidence:
+  * block level (TransformerBlock in all its variants, XLNetLayer): gradients w.r.t. inputs and every parameter within
+    2e-4 of CPU autograd through the oracle block.  These blocks contain no ReLU and the max-pool acts on the given input,
+    so both sides take identical discrete decisions and the comparison is exact up to rounding.
+  * whole model: d final_loss / d parameter vs the oracle's autograd (itself pinned to the reference's gradients,
+    tests/golden/grads_small.npz).  The model has ~0.7 M ReLU gates; a pre-activation within ~1e-5 of zero may take the
+    other side on the GPU (different summation order), which moves that element's whole gradient.  Such a flip perturbs
+    everything below it by O(1e-2), so the model-level bound is a relative L2 bound per parameter, with the strict bound
+    kept for the parameters no gate sits above (final head convolutions, mu / sigma).
+  * a central finite difference of the CUDA forward loss along the computed gradient direction (validates the backward
+    against the parity-checked forward, independent of gate flips).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gen_golden as GG
+from oracle import mq_oracle as O
+from oracle import params as PR
+from util import build_pair, rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def _grads_block(pre, stride, cross, adapter=False, T=64, L=24, seed=0):
+    from vilco_b200 import engine as E
+    from vilco_b200 import train_engine as TE
+    cfg = GG.small_cfg()
+    C, H, B = cfg.embd_dim, cfg.n_head, 2
+    spec = {k: v for k, v in PR.param_spec(cfg).items() if k.startswith(pre)}
+    if adapter:
+        spec.update({"pets.0.layer.0.weight": (5 * T, T), "pets.0.layer.0.bias": (5 * T,),
+                     "pets.0.layer.2.weight": (T // 2, 5 * T), "pets.0.layer.2.bias": (T // 2,)})
+    P = PR.random_state(spec, seed)
+    g = torch.Generator().manual_seed(seed)
+    valid, tvalid = [T, T - 13], [L, L - 7]
+    mask = torch.arange(T)[None, :] < torch.tensor(valid)[:, None]
+    tmask = torch.arange(L)[None, :] < torch.tensor(tvalid)[:, None]
+    x = torch.randn(B, C, T, generator=g) * mask[:, None]
+    y = torch.randn(B, C, L, generator=g) * tmask[:, None]
+    # oracle autograd (CPU fp32)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    xg, yg = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    out, om = O.transformer_block(Pg, pre, xg, mask[:, None], H, stride, cross_y=yg if cross else None,
+                                  cross_y_mask=tmask.long() if cross else None, t_c_alpha=0.8,
+                                  adapter_pre="pets.0." if adapter else None)
+    R = torch.randn(out.shape, generator=g)
+    (out * R).sum().backward()
+    # CUDA tape
+    W = E.pack_weights(P, "cuda")
+    tp = TE.Tape(W)
+    xv = TE.V(x.permute(0, 2, 1).contiguous().cuda())
+    yv = TE.V(y.permute(0, 2, 1).contiguous().cuda())
+    o, _ = TE.transformer_block(tp, pre, xv, mask.float().cuda(), H, stride, cross=(yv, tmask.float().cuda()) if cross else None,
+                                t_c_alpha=0.8, adapter_pre="pets.0." if adapter else None)
+    assert rel_max(o.v.permute(0, 2, 1), out.detach()) < 1e-4
+    o.g = R.permute(0, 2, 1).contiguous().cuda()
+    tp.backward()
+    errs = {"dx": rel_max(xv.g.permute(0, 2, 1), xg.grad)}
+    if cross:
+        errs["dtext"] = rel_max(yv.g.permute(0, 2, 1), yg.grad)
+    scale = max(float(v.grad.abs().max()) for v in Pg.values() if v.grad is not None)
+    for k, v in Pg.items():
+        if v.grad is None:
+            continue
+        assert k in tp.G, f"no gradient for {k}"
+        got = TE.unpack_grad(k, tp.G[k], v).cpu()
+        if float(v.grad.abs().max()) < 1e-6 * scale:      # analytically zero (key bias under softmax): absolute check
+            assert float(got.abs().max()) < 1e-5 * scale, k
+            continue
+        errs[k] = rel_max(got, v.grad)
+    return errs
+
+
+@pytest.mark.parametrize("pre,stride,cross,adapter", [
+    ("backbone.stem.0.", 1, False, False),       # + ChannelBlock mix
+    ("backbone.branch.1.", 2, False, False),     # strided, max-pool skip
+    ("backbone.branch.0.", 2, True, False),      # + cross attention to the text
+    ("backbone.branch.1.", 2, False, True),      # + temporal adapter
+])
+def test_transformer_block_gradients(pre, stride, cross, adapter):
+    errs = _grads_block(pre, stride, cross, adapter)
+    bad = {k: e for k, e in errs.items() if not e < 2e-4}
+    assert not bad, bad
+
+
+def test_xlnet_layer_gradients():
+    from vilco_b200 import engine as E
+    from vilco_b200 import train_engine as TE
+    cfg = GG.small_cfg()
+    C, H, B, T = cfg.embd_dim, cfg.n_head, 2, 128
+    pre = "backbone.xlnet.layer.0."
+    P = PR.random_state({k: v for k, v in PR.param_spec(cfg).items() if k.startswith(pre)}, 3)
+    g = torch.Generator().manual_seed(3)
+    mask = (torch.arange(T)[None, :] < torch.tensor([T, 90])[:, None]).float()
+    x = torch.randn(B, T, C, generator=g)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    xg = x.clone().requires_grad_(True)
+    out = O.xlnet_layer(Pg, pre, xg, mask)
+    R = torch.randn(out.shape, generator=g)
+    (out * R).sum().backward()
+    tp = TE.Tape(E.pack_weights(P, "cuda"))
+    xv = TE.V(x.cuda())
+    o = TE.xlnet_layer(tp, pre, xv, mask.cuda(), H)
+    assert rel_max(o.v, out.detach()) < 1e-4
+    o.g = R.cuda()
+    tp.backward()
+    errs = {"dx": rel_max(xv.g, xg.grad)}
+    for k, v in Pg.items():
+        if v.grad is not None:
+            errs[k] = rel_max(TE.unpack_grad(k, tp.G[k], v).cpu(), v.grad)
+    bad = {k: e for k, e in errs.items() if not e < 2e-4}
+    assert not bad, bad
+
+
+def _model_grads():
+    cfg = GG.small_cfg()
+    model, P = build_pair(cfg, 0)
+    videos = PR.synth_video_list(cfg, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    lo, _ = O.model_train_losses(Pg, cfg, videos)
+    lo["final_loss"].backward()
+    model.eval()   # dropout / drop-path off, as in the golden generation
+    model.loss_normalizer = cfg.init_loss_norm
+    out = model(videos, is_training=True)
+    out["final_loss"].backward()
+    torch.cuda.synchronize()
+    return cfg, model, videos, Pg, lo, out
+
+
+def test_model_gradients_vs_oracle_autograd():
+    cfg, model, videos, Pg, lo, out = _model_grads()
+    for k in ("cls_loss", "reg_loss", "al_loss", "final_loss"):
+        assert abs(float(out[k]) - float(lo[k])) <= 1e-3 * abs(float(lo[k])) + 1e-6, k
+    named = dict(model.named_parameters())
+    gmax = max(float(v.grad.abs().max()) for v in Pg.values())
+    l2 = {}
+    for k, v in Pg.items():
+        p = named[k]
+        assert p.grad is not None, f"{k} received no gradient"
+        a, b = p.grad.detach().cpu().double(), v.grad.double()
+        if float(b.abs().max()) < 1e-6 * gmax:
+            assert float(a.abs().max()) < 1e-5 * gmax, k
+            continue
+        l2[k] = float((a - b).norm() / b.norm())
+    # no ReLU gate above these: strict
+    for k in ("cls_head.cls_head.conv.weight", "cls_head.cls_head.conv.bias", "reg_head.offset_head.conv.weight",
+              "reg_head.offset_head.conv.bias", "mu", "sigma", "mu_reg_left", "sigma_reg_left", "mu_reg_right", "sigma_reg_right"):
+        assert l2[k] < 1e-4, (k, l2[k])
+    worst = max(l2.items(), key=lambda kv: kv[1])
+    assert worst[1] < 1e-1, worst
+    assert float(np.median(list(l2.values()))) < 2e-2
+
+
+def test_model_gradient_matches_finite_difference_of_cuda_forward():
+    cfg, model, videos, Pg, lo, out = _model_grads()
+    params = [p for p in model.parameters() if p.grad is not None]
+
+    def loss_at(step, direction):
+        with torch.no_grad():
+            for p, d in zip(params, direction):
+                p.add_(d, alpha=step)
+            model.loss_normalizer = cfg.init_loss_norm
+            v = float(model(videos, is_training=True)["final_loss"])
+            for p, d in zip(params, direction):
+                p.sub_(d, alpha=step)
+        return v
+
+    for select in (lambda n: True, lambda n: n.startswith("backbone.")):
+        names = [n for n, p in model.named_parameters() if p.grad is not None]
+        direction = [p.grad.clone() if select(n) else torch.zeros_like(p.grad) for n, p in zip(names, params)]
+        gnorm = math.sqrt(sum(float((d.double() ** 2).sum()) for d in direction))
+        direction = [d / gnorm for d in direction]
+        fds = {h: (loss_at(h, direction) - loss_at(-h, direction)) / (2 * h) for h in (4e-3, 2e-3, 1e-3)}
+        print("finite differences", fds, "analytic", gnorm)
+        assert abs(fds[2e-3] - gnorm) <= 2e-2 * gnorm, (fds, gnorm)
+        extrap = 2 * fds[1e-3] - fds[2e-3]         # the O(h) term comes from the gates that switch inside [-h, h]
+        assert abs(extrap - gnorm) <= 5e-3 * gnorm, (fds, extrap, gnorm)

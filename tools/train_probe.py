@@ -29,7 +29,7 @@ def main():
                      cfg.init_loss_norm)
     lo["final_loss"].backward()
     print("oracle losses", {k: float(v) for k, v in lo.items()}, f"{time.time() - t0:.1f}s")
-    model.train()
+    model.eval()   # dropout / drop-path off, as in the golden generation
     model.loss_normalizer = cfg.init_loss_norm
     out = model(videos, is_training=True)
     print("cuda losses  ", {k: float(v) for k, v in out.items()})

@@ -257,6 +257,20 @@ __global__ void ew_kernel(int op, const float* __restrict__ x, const float* __re
   }
 }
 
+// inverted dropout with a counter-based generator: element i of call `seed` is kept iff mix(seed, i) >= p * 2^32.  The backward
+// pass applies the same kernel to the gradient with the same seed, so no mask is stored.
+__device__ __forceinline__ unsigned int mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return static_cast<unsigned int>((z ^ (z >> 31)) >> 32);
+}
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, unsigned int thr, float inv_keep,
+                               unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = mix64(seed * 0xD1342543DE82EF95ull + static_cast<unsigned long long>(i)) >= thr ? x[i] * inv_keep : 0.f;
+}
+
 // dx = dy * gelu'(x)
 __global__ void gelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -401,7 +415,15 @@ extern "C" int vilco_relshift_bwd(const float* dS, float* dBD, int64_t Z, int T,
   return VILCO_OK;
 }
 
-extern "C" int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const float* colmul, float* out,
+extern "C" int vilco_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream) {
+  VILCO_CHECK_ARG(x && out && n > 0 && p >= 0.f && p < 1.f, "vilco_dropout: bad arguments");
+  const unsigned int thr = static_cast<unsigned int>(static_cast<double>(p) * 4294967296.0);
+  dropout_kernel<<<bgrid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, n, thr, 1.0f / (1.0f - p), seed);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const float* colmul, float* out,
                         int64_t rows, int C, void* stream) {
   VILCO_CHECK_ARG(x && out && rows > 0 && C > 0 && op >= 0 && op <= 3 && (op != 3 || y), "vilco_ew: bad arguments");
   ew_kernel<<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(op, x, y, rowmul, colmul, out, rows, C);

@@ -515,7 +515,14 @@ class PtTransformer(nn.Module):
             text = text.contiguous()
         W = self.packed_weights()
         cfg = self.engine_cfg()
-        tp = TE.Tape(W)
+        # dropout / stochastic depth follow nn.Module.training exactly like the reference's nn.Dropout / AffineDropPath /
+        # XLNet dropout (xlnet_config_*.json: 0.1); model.eval() + is_training=True gives the deterministic losses
+        self._train_calls = getattr(self, "_train_calls", 0) + 1
+        if self.training:
+            tp = TE.Tape(W, dropout=self.train_dropout, droppath=self.train_droppath, xl_dropout=0.1 if self.use_xl else 0.0,
+                         seed=(int(torch.initial_seed()) & 0xFFFFF) * 4096 + self._train_calls)
+        else:
+            tp = TE.Tape(W)
         with torch.no_grad():
             x16 = ops.pack_feats(batched)
             t16 = ops.pack_feats(text.detach()) if text is not None else None
@@ -569,7 +576,10 @@ class PtTransformer(nn.Module):
                     if prm is None or not prm.requires_grad:
                         continue
                     g = TE.unpack_grad(key, g, prm).to(prm.dtype)
-                    prm.grad = g.clone() if prm.grad is None else prm.grad + g
+                    if prm.grad is None:
+                        prm.grad = g.clone()
+                    else:
+                        prm.grad.add_(g)      # in place: .grad may be a view of the trainer's flat all-reduce buffer
             glue = [(t_, g_) for t_, g_ in ((wc, dwc), (wl, dwl), (wr, dwr)) if t_.requires_grad]
             if tin is not None and text.requires_grad and tin.g is not None:
                 glue.append((text, ops.unpack(tin.g)))

@@ -35,10 +35,13 @@ def _add(a, b):
 
 
 class Tape:
-    def __init__(self, W):
+    def __init__(self, W, dropout=0.0, droppath=0.0, xl_dropout=0.0, seed=0):
+        """dropout / droppath > 0 only when the module is in training mode (nn.Dropout / AffineDropPath semantics)."""
         self.W = W
         self.G = {}       # packed-layout parameter gradients
         self.nodes = []
+        self.p_drop, self.p_path, self.p_xl = float(dropout), float(droppath), float(xl_dropout)
+        self.seed = int(seed) << 20
 
     # ---- plumbing ----
     def acc(self, x, g):
@@ -204,6 +207,38 @@ class Tape:
         self.nodes.append(bwd)
         return out
 
+    def dropout(self, x, p=None):
+        """nn.Dropout(p) in training mode (identity when p == 0)."""
+        p = self.p_drop if p is None else p
+        if p <= 0.0:
+            return x
+        self.seed += 1
+        seed = self.seed
+
+        def run(t):
+            out = torch.empty_like(t)
+            L.check(L.lib().vilco_dropout(_p(t), _p(out), _i64(t.numel()), CT.c_float(p), CT.c_uint64(seed), L.stream_ptr()),
+                    "vilco_dropout")
+            return out
+        y = V(run(x.v))
+        self.nodes.append(lambda: self.acc(x, run(y.g.contiguous())) if y.g is not None else None)
+        return y
+
+    def path_rows(self, B, rows_per_sample, device):
+        """per-row multiplier of stochastic depth (drop_path, blocks.py:640-652): one Bernoulli(1 - p) / (1 - p) per sample."""
+        if self.p_path <= 0.0:
+            return None
+        keep = 1.0 - self.p_path
+        m = torch.empty(B, device=device, dtype=f32).bernoulli_(keep) / keep
+        return m.repeat_interleave(rows_per_sample).contiguous()
+
+    def rowscale(self, x, rows):
+        if rows is None:
+            return x
+        y = V(ops.ew(0, x.v, rowmul=rows))
+        self.nodes.append(lambda: self.acc(x, ops.ew(0, y.g.contiguous(), rowmul=rows)) if y.g is not None else None)
+        return y
+
     def transpose(self, x):
         """(B,T,C) -> (B,C,T)"""
         y = V(ops.unpack(x.v))
@@ -255,13 +290,17 @@ def transformer_block(tp, pre, x, mask, H, stride, cross=None, t_c_alpha=0.8, ad
     k = tp.linear(kc, pre + "attn.key.weight", pre + "attn.key.bias")
     v = tp.linear(vc, pre + "attn.value.weight", pre + "attn.value.bias", rowmul=omf)
     o = tp.attention(q, k, v, om, H, scale)
-    proj = tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias", rowmul=omf)
+    B, To = om.shape
+    if tp.p_drop > 0:      # proj_drop sits between the projection and the mask (blocks.py:404-405)
+        proj = tp.rowscale(tp.dropout(tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias")), omf)
+    else:
+        proj = tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias", rowmul=omf)
     skip = x if stride == 1 else tp.maxpool(x)
     sa = pre + "drop_path_attn.scale" if (pre + "drop_path_attn.scale") in W else None
     sm = pre + "drop_path_mlp.scale" if (pre + "drop_path_mlp.scale") in W else None
     if adapter_pre is not None:          # out = attn(ln1 x) + adapter(ln1 x), the adapter output is not masked
         proj = tp.mix(proj, adapter(tp, adapter_pre, ln1))
-    h = tp.resid_scale(skip, omf, proj, sa)
+    h = tp.resid_scale(skip, omf, tp.rowscale(proj, tp.path_rows(B, To, omf.device)), sa)
     if cross is not None and (pre + "cross_attn.query.weight") in W:
         text, tmask = cross
         hx = tp.ln(h, pre + "ln3.weight", pre + "ln3.bias")
@@ -270,43 +309,70 @@ def transformer_block(tp, pre, x, mask, H, stride, cross=None, t_c_alpha=0.8, ad
         ck = tp.linear(hy, pre + "cross_attn.key.weight", pre + "cross_attn.key.bias")
         cv = tp.linear(hy, pre + "cross_attn.value.weight", pre + "cross_attn.value.bias", rowmul=tmask.reshape(-1))
         c = tp.attention(cq, ck, cv, tmask, H, scale)
-        cp = tp.linear(c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias", rowmul=omf)
-        h = tp.resid_scale(h, omf, cp, sa)
+        if tp.p_drop > 0:
+            cp = tp.rowscale(tp.dropout(tp.linear(c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias")), omf)
+        else:
+            cp = tp.linear(c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias", rowmul=omf)
+        h = tp.resid_scale(h, omf, tp.rowscale(cp, tp.path_rows(B, To, omf.device)), sa)
     h2 = tp.ln(h, pre + "ln2.weight", pre + "ln2.bias")
-    m1 = tp.gelu(tp.linear(h2, pre + "mlp.0.weight", pre + "mlp.0.bias"))
-    m2 = tp.linear(m1, pre + "mlp.3.weight", pre + "mlp.3.bias", rowmul=omf)
-    out = tp.resid_scale(h, None, m2, sm)
+    m1 = tp.dropout(tp.gelu(tp.linear(h2, pre + "mlp.0.weight", pre + "mlp.0.bias")))
+    if tp.p_drop > 0:
+        m2 = tp.rowscale(tp.dropout(tp.linear(m1, pre + "mlp.3.weight", pre + "mlp.3.bias")), omf)
+    else:
+        m2 = tp.linear(m1, pre + "mlp.3.weight", pre + "mlp.3.bias", rowmul=omf)
+    out = tp.resid_scale(h, None, tp.rowscale(m2, tp.path_rows(B, To, omf.device)), sm)
     if stride == 1:
         cpre = pre + "channel_attn."
         qkv = tp.linear(ln1, cpre + "attn.qkv.weight")
         y = tp.channel_attention(qkv, H)
-        x1 = tp.mix(ln1, tp.linear(y, cpre + "attn.proj.weight", cpre + "attn.proj.bias"))
+        T_ = ln1.shape[1]        # ChannelBlock: DropPath on both residual branches (blocks.py:448, 462-464)
+        x1 = tp.mix(ln1, tp.rowscale(tp.linear(y, cpre + "attn.proj.weight", cpre + "attn.proj.bias"),
+                                     tp.path_rows(B, T_, omf.device)))
         n2 = tp.ln(x1, cpre + "norm2.weight", cpre + "norm2.bias", 1e-5)
         hh = tp.linear(tp.gelu(tp.linear(n2, cpre + "mlp.0.weight", cpre + "mlp.0.bias")), cpre + "mlp.2.weight", cpre + "mlp.2.bias")
-        out2 = tp.mix(x1, hh)
+        out2 = tp.mix(x1, tp.rowscale(hh, tp.path_rows(B, T_, omf.device)))
         out = tp.mix(out, out2, t_c_alpha, 1.0 - t_c_alpha)
     return out, om
 
 
 def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
+    """XLNetModel.forward with one XLNetLayer on inputs_embeds (modeling_xlnet_x.py:1121-1283, 440-467, 270-332, 482-490),
+    including its dropout sites (input :1201, pos_emb :1228, attn_prob :308, attn_out :327, ff :486-488, output :1280) when
+    tp.p_xl > 0."""
     W = tp.W
     B, T, C = x.shape
     d = C // H
+    pd = tp.p_xl
     scale = 1.0 / math.sqrt(d)
     kq, kk, kv, ko, kr = (pre + "rel_attn." + n for n in "qkvor")
     rw, rr = pre + "rel_attn.r_w_bias", pre + "rel_attn.r_r_bias"
+    x = tp.dropout(x, pd)
     qw = tp.linear(x, kq, rw)
     qr = tp.linear(x, kq, rr)
     k = tp.linear(x, kk)
     v = tp.linear(x, kv)
-    pos = V(p16=E.xlnet_pos_emb(T, C, x.v.device))             # constant (2T, C)
-    krel1 = tp.linear(pos, kr)                                 # (2T, C) fp32, depends on W_r only
-    krel = V(krel1.v.unsqueeze(0).expand(B, 2 * T, C).contiguous())
+    pos16 = E.xlnet_pos_emb(T, C, x.v.device)                  # constant (2T, C)
+    if pd > 0:     # the reference drops the (2T, B, C) expanded table, i.e. an independent mask per clip (:1228)
+        posb = V(ops.merge16(pos16).unsqueeze(0).expand(B, 2 * T, C).contiguous(), const=True)
+        krel1, krel = None, tp.linear(tp.dropout(posb, pd), kr)
+    else:
+        krel1 = tp.linear(V(p16=pos16, const=True), kr)       # (2T, C) fp32, depends on W_r only
+        krel = V(krel1.v.unsqueeze(0).expand(B, 2 * T, C).contiguous())
     qw16, qr16, k16, v16, kr16 = (tp.planes(t) for t in (qw, qr, k, v, krel))
     ac = ops.attn_scores(qw16, k16, H, 1.0)
     bd = ops.attn_scores(qr16, kr16, H, 1.0, band=(T, 2 * T))
     P16, P32 = ops.softmax_rows(ac, mask, mode=1, BD=bd, scale=scale, want32=True)
     del ac, bd
+    seed = None
+    if pd > 0:                                                 # dropout on the attention probabilities
+        tp.seed += 1
+        seed = tp.seed
+        Pd32 = torch.empty_like(P32)
+        L.check(L.lib().vilco_dropout(_p(P32), _p(Pd32), _i64(P32.numel()), CT.c_float(pd), CT.c_uint64(seed), L.stream_ptr()),
+                "vilco_dropout")
+        P16, _ = BW.to_planes(Pd32, want=True, want_t=False, batch_dims=2)
+    else:
+        Pd32 = P32
     vec = V(ops.attn_pv(P16, v16, H, T, out32=True))
 
     def bwd():
@@ -315,6 +381,9 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
         dvec16, _ = BW.to_planes(vec.g.reshape(-1, C))
         dvec16 = dvec16.reshape(dvec16.shape[0], B, T, C)
         dP = ops.attn_scores(dvec16, v16, H, 1.0)
+        if seed is not None:
+            L.check(L.lib().vilco_dropout(_p(dP), _p(dP), _i64(dP.numel()), CT.c_float(pd), CT.c_uint64(seed), L.stream_ptr()),
+                    "vilco_dropout")
         dS = torch.empty_like(dP)
         L.check(L.lib().vilco_softmax_bwd(_p(P32), _p(dP), _p(dS), _i64(B * H * T), T, CT.c_float(scale), L.stream_ptr()),
                 "vilco_softmax_bwd")
@@ -324,22 +393,22 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
         dS16, dST16 = BW.to_planes(dS, want=True, want_t=True, batch_dims=2)
         tp.acc(qw, ops.attn_pv(dS16, k16, H, T, out32=True))
         tp.acc(k, ops.attn_pv(dST16, qw16, H, T, out32=True))
-        _, PT16 = BW.to_planes(P32, want=False, want_t=True, batch_dims=2)
+        _, PT16 = BW.to_planes(Pd32, want=False, want_t=True, batch_dims=2)
         tp.acc(v, ops.attn_pv(PT16, dvec16, H, T, out32=True))
         dBD16, dBDT16 = BW.to_planes(dBD, want=True, want_t=True, batch_dims=2)
         tp.acc(qr, ops.attn_pv(dBD16, kr16, H, 2 * T, out32=True))
         tp.acc(krel, ops.attn_pv(dBDT16, qr16, H, T, out32=True))
-        # krel is the batch broadcast of krel1
-        g1 = krel.g[0]
-        for b in range(1, B):
-            g1 = _add(g1.contiguous(), krel.g[b].contiguous())
-        tp.acc(krel1, g1)
+        if krel1 is not None:                                  # krel is the batch broadcast of krel1
+            g1 = krel.g[0]
+            for b in range(1, B):
+                g1 = _add(g1.contiguous(), krel.g[b].contiguous())
+            tp.acc(krel1, g1)
     tp.nodes.append(bwd)
-    a = tp.mix(tp.linear(vec, ko), x)
+    a = tp.mix(tp.dropout(tp.linear(vec, ko), pd), x)
     h1 = tp.ln(a, pre + "rel_attn.layer_norm.weight", pre + "rel_attn.layer_norm.bias", eps)
-    f = tp.linear(tp.gelu(tp.linear(h1, pre + "ff.layer_1.weight", pre + "ff.layer_1.bias")), pre + "ff.layer_2.weight",
-                  pre + "ff.layer_2.bias")
-    return tp.ln(tp.mix(f, h1), pre + "ff.layer_norm.weight", pre + "ff.layer_norm.bias", eps)
+    f = tp.dropout(tp.gelu(tp.linear(h1, pre + "ff.layer_1.weight", pre + "ff.layer_1.bias")), pd)
+    f = tp.dropout(tp.linear(f, pre + "ff.layer_2.weight", pre + "ff.layer_2.bias"), pd)
+    return tp.dropout(tp.ln(tp.mix(f, h1), pre + "ff.layer_norm.weight", pre + "ff.layer_norm.bias", eps), pd)
 
 
 def backbone(tp, cfg, x16, mask, text16, tmask, pe, pets_prefix="pets."):
