@@ -180,3 +180,66 @@ def test_model_gradient_matches_finite_difference_of_cuda_forward():
         assert abs(fds[2e-3] - gnorm) <= 2e-2 * gnorm, (fds, gnorm)
         extrap = 2 * fds[1e-3] - fds[2e-3]         # the O(h) term comes from the gates that switch inside [-h, h]
         assert abs(extrap - gnorm) <= 5e-3 * gnorm, (fds, extrap, gnorm)
+
+
+def test_flat_adamw_matches_torch_adamw_and_keeps_planes_current():
+    """FlatAdamW (csrc/optim.cu) == clip_grad_norm_ + torch.optim.AdamW on identical gradients; its bf16 planes always equal
+    the hi / lo split of the updated parameters."""
+    from vilco_b200 import ops
+    from vilco_b200.trainer import FlatAdamW
+    torch.manual_seed(0)
+    shapes = [(64, 40, 1), (40,), (3, 17), (1, 24, 1), ()]
+    ref = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    groups = lambda ps: [{"params": ps[:3], "weight_decay": 0.05}, {"params": ps[3:], "weight_decay": 0.0}]  # noqa: E731
+    o_ref = torch.optim.AdamW(groups(ref), lr=1e-2)
+    o_mine = FlatAdamW(groups(mine), lr=1e-2)
+    for it in range(4):
+        gs = [torch.randn(s, device="cuda") * (3.0 if it % 2 else 0.01) for s in shapes]   # clipped and un-clipped steps
+        o_mine.zero_grad()
+        for p, q, g in zip(ref, mine, gs):
+            p.grad = g.clone()
+            q.grad.add_(g)
+        nrm = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        o_ref.step()
+        o_mine.step(clip_grad_l2norm=1.0)
+        assert abs(float(o_mine.grad_norm()) - float(nrm)) <= 1e-5 * float(nrm)
+        for p, q in zip(ref, mine):
+            assert rel_max(q.detach(), p.detach()) < 2e-6
+    for q in mine:
+        pv = o_mine.plane_view(q, (q.numel(),))
+        assert torch.equal(pv, ops.split16(q.detach().reshape(-1)))
+
+
+def test_training_steps_flat_optimizer_equals_torch_optimizer():
+    """Three Trainer.step iterations of the small model: FlatAdamW path (live plane views, no re-pack) vs torch AdamW path
+    (full re-pack each step) end with the same parameters and losses."""
+    from vilco_b200.trainer import Trainer, make_optimizer
+    cfg = GG.small_cfg()
+    videos = PR.synth_video_list(cfg, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    out = []
+    for flat in (False, True):
+        model, P = build_pair(cfg, 0)
+        model.eval()                      # deterministic: no dropout
+        model.loss_normalizer = cfg.init_loss_norm
+        model.loss_normalizer_momentum = 1.0     # frozen normaliser, so that the loss values of successive steps compare
+        opt = make_optimizer(model, {"type": "AdamW", "learning_rate": 1e-3, "weight_decay": 0.05}, flat=flat)
+        tr = Trainer(model, opt, clip_grad_l2norm=1.0)
+        losses = [float(tr.step(videos)["final_loss"]) for _ in range(3)]
+        out.append((losses, {k: v.detach().clone() for k, v in model.named_parameters()}))
+    (l0, p0), (l1, p1) = out
+    assert l0[0] > l0[2], "loss should go down on a repeated batch"
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-4 * abs(a), (l0, l1)
+    # Adam normalises every element's gradient, so elements whose gradient is rounding noise (key biases are analytically
+    # zero, a few weights are numerically ~0) move by +-lr in a direction the last bit decides; compare the UPDATES in L2
+    # (parameters outside the seeded spec are dead weights with a random init per construction)
+    errs = []
+    for k in p0:
+        if k not in P or k.endswith("key.bias") or k.endswith("key_norm.bias"):
+            continue
+        init = P[k].cuda().reshape(p0[k].shape)
+        d0, d1 = (p0[k] - init).double(), (p1[k] - init).double()
+        errs.append((float((d1 - d0).norm() / (d0.norm() + 1e-12)), k))
+    errs.sort(reverse=True)
+    assert errs[0][0] < 5e-2, errs[:8]

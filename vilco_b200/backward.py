@@ -28,7 +28,8 @@ def to_planes(x, rowmul=None, colmul=None, want=True, want_t=False, batch_dims=0
         lead, R, Z = (), x.numel() // Cc, 1
     y = ops.empty16(*lead, R, Cc, device=x.device) if want else None
     ldT = (R + 7) // 8 * 8
-    yT = ops.zeros16(*lead, Cc, ldT, device=x.device) if want_t else None
+    # padding columns (ldT > R) must be zero: they are read as K entries of the weight-gradient GEMMs
+    yT = (ops.zeros16 if ldT != R else ops.empty16)(*lead, Cc, ldT, device=x.device) if want_t else None
     L.check(L.lib().vilco_to_planes(_p(x), _p(rowmul), _p(colmul), _p(y), _i64(lo(y) if want else 0), _p(yT),
                                     _i64(lo(yT) if want_t else 0), R, Cc, ldT, Z, L.stream_ptr()), "vilco_to_planes")
     return y, yT
@@ -43,6 +44,26 @@ def colsum(x, y=None, rowmul=None, out=None):
     return out
 
 
+def wgrad(dzT, x2, Mo, No, R, alpha=1.0):
+    """dW (Mo, No) = dz^T (Mo, R) @ x (R, No): A = transposed gradient planes (row stride ldT), B = activations as MN-major
+    operand.  The reduction runs over all B*T rows while the output has few tiles, so K is split over up to 16 CTAs-worth of
+    batches (split-K) whenever the plain launch would leave most of the 148 SMs idle; partials are summed by vilco_colsum."""
+    ldT = dzT.shape[-1]
+    tiles = ((Mo + 127) // 128) * ((No + 127) // 128)
+    S = min(16, 148 // tiles) if tiles < 100 else 1
+    while S > 1 and (R % (8 * S) != 0 or R // S < 512):
+        S -= 1
+    if S <= 1:
+        dw = torch.empty(Mo, No, device=x2.device, dtype=f32)
+        L.gemm(dzT, x2, dw, M=Mo, N=No, K=R, a_rows=Mo, a_ld=ldT, b_ld=No, d_ld=No, b_major=1, alpha=alpha, a_lo=lo(dzT), b_lo=lo(x2))
+        return dw
+    chunk = R // S
+    part = torch.empty(S, Mo, No, device=x2.device, dtype=f32)
+    L.gemm(dzT, x2, part, M=Mo, N=No, K=chunk, a_rows=Mo, a_ld=ldT, a_s=(chunk, 0), Z=(S, 1), b_ld=No, b_s=(chunk * No, 0),
+           b_batched=True, b_major=1, d_ld=No, d_s=(Mo * No, 0), alpha=alpha, a_lo=lo(dzT), b_lo=lo(x2))
+    return colsum(part.reshape(S, Mo * No)).reshape(Mo, No)
+
+
 def linear_bwd(dy, x16, w16, rowmul=None, alpha=1.0, need_dx=True, need_dw=True, need_db=True):
     """forward: y = (alpha * x w^T + bias) * rowmul[:, None]   (ops.linear without act / colscale / resid).
     dy (..., N) fp32, x16 (NP, ..., K), w16 (NP, N, K) -> (dx (..., K) fp32, dw (N, K) fp32, db (N,) fp32)."""
@@ -55,10 +76,7 @@ def linear_bwd(dy, x16, w16, rowmul=None, alpha=1.0, need_dx=True, need_dw=True,
         dx = torch.empty(*dy.shape[:-1], K, device=dy.device, dtype=f32)
         L.gemm(dz, w16, dx, M=R, N=K, K=N, a_rows=R, a_ld=N, b_ld=K, d_ld=K, b_major=1, alpha=alpha, a_lo=lo(dz), b_lo=lo(w16))
     if need_dw:
-        dw = torch.empty(N, K, device=dy.device, dtype=f32)
-        x2 = x16.reshape(x16.shape[0], -1, K)
-        L.gemm(dzT, x2, dw, M=N, N=K, K=R, a_rows=N, a_ld=dzT.shape[2], b_ld=K, d_ld=K, b_major=1, alpha=alpha,
-               a_lo=lo(dzT), b_lo=lo(x2))
+        dw = wgrad(dzT, x16.reshape(x16.shape[0], -1, K), N, K, R, alpha)
     if need_db:
         db = colsum(dy2, rowmul=rowmul)
     return dx, dw, db
@@ -86,12 +104,12 @@ def conv3_bwd(dy, x16, w3, w3_flip, rowmul=None, need_dx=True):
         dz4 = dz.reshape(dz.shape[0], B, T, N)
         L.gemm(dz4, w3_flip, dx, M=T, N=K, K=N, a_rows=T, a_ld=N, a_s=(0, T * N), Z=(1, B), taps=3, b_ld=K, b_s=(N * K, 0),
                b_major=1, d_ld=K, d_s=(0, T * K), a_lo=lo(dz4), b_lo=lo(w3_flip))
-    dw = torch.empty(3, N, K, device=dy.device, dtype=f32)
     R = B * T
+    taps = []
     for tap in range(3):
         xs = x16 if tap == 1 else shift_planes(x16, tap - 1)
-        x2 = xs.reshape(xs.shape[0], R, K)
-        L.gemm(dzT, x2, dw[tap], M=N, N=K, K=R, a_rows=N, a_ld=dzT.shape[2], b_ld=K, d_ld=K, b_major=1, a_lo=lo(dzT), b_lo=lo(x2))
+        taps.append(wgrad(dzT, xs.reshape(xs.shape[0], R, K), N, K, R))
+    dw = torch.stack(taps)
     db = colsum(dy.reshape(-1, N), rowmul=rowmul.reshape(-1) if rowmul is not None else None)
     return dx, dw, db
 

@@ -63,21 +63,49 @@ __global__ void shift_planes_kernel(const uint4* __restrict__ x, uint4* __restri
   }
 }
 
-// out[c] (+)= sum_r x[r, c] * (y ? y[r, c] : 1) * (rowmul ? rowmul[r] : 1)
-__global__ void colsum_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ rowmul,
-                              float* __restrict__ out, int R, int C, int rows_per_block) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// out[c] += sum_r x[r, c] * (y ? y[r, c] : 1) * (rowmul ? rowmul[r] : 1)
+// block = 32 column groups (float4 when C % 4 == 0) x 8 row lanes over `rows_per_block` rows; smem reduction over the row
+// lanes, one atomicAdd per column and block.
+template <int VEC>
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                     const float* __restrict__ rowmul, float* __restrict__ out, int R, int C,
+                                                     int rows_per_block) {
+  __shared__ float red[8][32 * VEC + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * VEC;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
-  float acc = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    float v = x[(long long)r * C + c];
-    if (y) v *= y[(long long)r * C + c];
-    if (rowmul) v *= rowmul[r];
-    acc += v;
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  if (c < C) {
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const float m = rowmul ? rowmul[r] : 1.f;
+      if (VEC == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(x + (long long)r * C + c);
+        float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (y) w = *reinterpret_cast<const float4*>(y + (long long)r * C + c);
+        acc[0] += v.x * w.x * m; acc[1] += v.y * w.y * m; acc[2] += v.z * w.z * m; acc[3] += v.w * w.w * m;
+      } else {
+        float v = x[(long long)r * C + c];
+        if (y) v *= y[(long long)r * C + c];
+        acc[0] += v * m;
+      }
+    }
   }
-  atomicAdd(out + c, acc);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) red[ty][tx * VEC + i] = acc[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < 32 * VEC; j += 256) {
+    const int cc = blockIdx.x * 32 * VEC + j;
+    if (cc < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][j];
+      atomicAdd(out + cc, t);
+    }
+  }
 }
 
 // ---- LayerNorm backward: y = act(LN(x [+ add]) * w + b); one warp per row; dw/db via per-block smem + atomics ----
@@ -340,9 +368,17 @@ extern "C" int vilco_to_planes(const float* x, const float* rowmul, const float*
 
 extern "C" int vilco_colsum(const float* x, const float* y, const float* rowmul, float* out, int R, int C, void* stream) {
   VILCO_CHECK_ARG(x && out && R > 0 && C > 0, "vilco_colsum: bad arguments");
-  const int rpb = 256;
-  dim3 grid((C + 127) / 128, (R + rpb - 1) / rpb);
-  colsum_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rowmul, out, R, C, rpb);
+  const bool vec = (C % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (!y || reinterpret_cast<uintptr_t>(y) % 16 == 0);
+  const int cols_per_block = vec ? 128 : 32;
+  const int cblocks = (C + cols_per_block - 1) / cols_per_block;
+  // enough row slabs to fill the GPU a few times over, at least 64 rows per slab
+  int slabs = (148 * 4 + cblocks - 1) / cblocks;
+  int rpb = (R + slabs - 1) / slabs;
+  if (rpb < 64) rpb = 64;
+  rpb = (rpb + 7) / 8 * 8;
+  dim3 grid(cblocks, (R + rpb - 1) / rpb);
+  if (vec) colsum_kernel<4><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rowmul, out, R, C, rpb);
+  else colsum_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rowmul, out, R, C, rpb);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

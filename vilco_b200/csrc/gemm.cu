@@ -255,7 +255,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int pl = 0; pl < L::PLANES; ++pl) {
             tma_load_5d(sa + pl * L::A_BYTES, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3], pl);
-            tma_load_5d(sb + pl * L::B_BYTES, &tmB, full0 + 8 * s, cb[0], cb[1], cb[2], cb[3], pl);
+            if (BN <= 64 || p.b_major == 0) {
+              tma_load_5d(sb + pl * L::B_BYTES, &tmB, full0 + 8 * s, cb[0], cb[1], cb[2], cb[3], pl);
+            } else {
+              // MN-major B wider than one 128-byte swizzle atom: one (64 n x BK k) box per 64 columns, BK*128 bytes apart
+#pragma unroll
+              for (int h = 0; h < BN / 64; ++h)
+                tma_load_5d(sb + pl * L::B_BYTES + h * (BK * 128), &tmB, full0 + 8 * s, cb[0] + h * 64, cb[1], cb[2], cb[3], pl);
+            }
           }
         }
       }
@@ -288,11 +295,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t aoff = k * UMMA_K * 2;
             const uint32_t boff = p.b_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
             const uint64_t a_hi = make_smem_desc(sa + aoff, 16, 1024);
-            const uint64_t b_hi = make_smem_desc(sb + boff, 16, 1024);
+            const uint32_t b_lbo = p.b_major == 0 ? 16 : BK * 128;   // MN-major: distance between 64-column swizzle atoms
+            const uint64_t b_hi = make_smem_desc(sb + boff, b_lbo, 1024);
             tcgen05_mma_f16(tmem_d, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
             if (SPLIT) {
               const uint64_t a_lo = make_smem_desc(sa + L::A_BYTES + aoff, 16, 1024);
-              const uint64_t b_lo = make_smem_desc(sb + L::B_BYTES + boff, 16, 1024);
+              const uint64_t b_lo = make_smem_desc(sb + L::B_BYTES + boff, b_lbo, 1024);
               tcgen05_mma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
               tcgen05_mma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
             }
@@ -904,8 +912,10 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
 
   // ---- tcgen05 path ----
   int BN;
-  if (g->b_major == 1) BN = 64;
-  else if (g->N <= 32) BN = 32;
+  if (g->b_major == 1) {
+    const long long t128 = (long long)((g->N + 127) / 128) * ((g->M + BM - 1) / BM) * Z;
+    BN = (g->N <= 64 || t128 * 2 <= num_sms()) ? 64 : 128;
+  } else if (g->N <= 32) BN = 32;
   else if (g->N <= 64) BN = 64;
   else {
     // small problems (text stem, deep pyramid levels): 128x64 tiles double the number of CTAs when 128x128 tiles

@@ -1,0 +1,89 @@
+// Flat-buffer optimizer kernels for the training step: global gradient norm, clip coefficient and a fused AdamW update that
+// also refreshes the bf16 (hi, lo) operand planes the GEMMs read, so the weights never need a separate re-pack pass.
+// Reference semantics: torch.optim.AdamW as built by make_optimizer (MQ/libs/utils/train_utils.py:68-143) preceded by
+// torch.nn.utils.clip_grad_norm_ (train_utils.py:345-349).
+#include "common.cuh"
+
+namespace vilco {
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x, long long n4, const float* __restrict__ tail,
+                                                    int ntail, float* __restrict__ out) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < ntail) acc += tail[threadIdx.x] * tail[threadIdx.x];
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+
+// coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))  (clip_grad_norm_); norm_out = sqrt(sumsq)
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef, float* __restrict__ norm_out) {
+  const float nrm = sqrtf(*sumsq);
+  if (norm_out) *norm_out = nrm;
+  *coef = max_norm > 0.f ? fminf(1.f, max_norm / (nrm + 1e-6f)) : 1.f;
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                    float wd, float bc1, float bc2_sqrt, const float* __restrict__ gscale,
+                                                    __nv_bfloat16* __restrict__ planes, long long planes_lo) {
+  const float gs = gscale ? *gscale : 1.f;
+  const float step = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    pi -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (planes) {
+      const __nv_bfloat16 hi = __float2bfloat16(pi);
+      planes[i] = hi;
+      if (planes_lo) planes[planes_lo + i] = __float2bfloat16(pi - __bfloat162float(hi));
+    }
+  }
+}
+
+}  // namespace vilco
+
+using namespace vilco;
+
+static inline int ogrid(long long n, int block) {
+  long long b = (n + block - 1) / block;
+  const long long cap = 148LL * 8;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" int vilco_grad_clip_coef(const float* g, int64_t n, float max_norm, float* scratch, float* coef, float* norm_out,
+                                    void* stream) {
+  VILCO_CHECK_ARG(g && scratch && coef && n > 0, "vilco_grad_clip_coef: bad arguments");
+  VILCO_CHECK_ARG(reinterpret_cast<uintptr_t>(g) % 16 == 0, "vilco_grad_clip_coef: gradient buffer must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VILCO_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), st));
+  const long long n4 = n / 4;
+  sumsq_kernel<<<ogrid(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(g), n4, g + n4 * 4, static_cast<int>(n - n4 * 4), scratch);
+  VILCO_LAUNCH_CHECK();
+  clip_coef_kernel<<<1, 1, 0, st>>>(scratch, max_norm, coef, norm_out);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, int step, const float* grad_scale, void* planes, int64_t planes_lo, void* stream) {
+  VILCO_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "vilco_adamw: bad arguments");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  adamw_kernel<<<ogrid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, static_cast<__nv_bfloat16*>(planes), planes_lo);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}

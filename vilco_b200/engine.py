@@ -17,39 +17,75 @@ from .ops import ACT_GELU, ACT_NONE, ACT_RELU, bf16, f32
 # ----------------------------------------------------------------------------------------------------
 # weight packing
 # ----------------------------------------------------------------------------------------------------
-def pack_weights(sd, device):
+def _pack_kind(k, v):
+    last = k.rsplit(".", 1)[-1]
+    if ".rel_attn." in k and last in ("q", "k", "v", "r"):
+        return "xl_t"
+    if ".rel_attn." in k and last == "o":
+        return "gemm"
+    if k.endswith("_conv.conv.weight"):
+        return "dw"
+    if last == "weight" and v.dim() == 3 and v.shape[0] == 1 and v.shape[2] == 1:
+        return "vec"
+    if last == "weight" and v.dim() == 3 and v.shape[2] == 3:
+        return "conv3"
+    if last == "weight" and (v.dim() == 2 or (v.dim() == 3 and v.shape[2] == 1)):
+        return "gemm"
+    return "vec"
+
+
+def _pack_one(kind, v):
+    if kind == "xl_t":
+        return ops.split16(v.reshape(v.shape[0], -1).t().contiguous())
+    if kind == "gemm":
+        return ops.split16(v.reshape(v.shape[0], -1).contiguous())
+    if kind == "dw":                                   # depthwise (C,1,3) -> (3,C) fp32
+        return v[:, 0, :].t().contiguous()
+    if kind == "conv3":                                # dense k=3 conv -> tap-major (3, Cout, Cin)
+        return ops.split16(v.permute(2, 0, 1).contiguous())
+    return v.reshape(-1).contiguous() if v.dim() != 2 else v.contiguous()
+
+
+def pack_weights(sd, device, flat=None, params=None):
     """state_dict (reference keys, fp32) -> dict of device tensors in kernel operand formats.
 
     * conv / linear weights feeding a GEMM: bf16, K-major: (Cout, Cin); k=3 convs tap-major (3, Cout, Cin)
     * depthwise k=3 weights: fp32 (3, C) tap-major
     * LayerNorm / AffineDropPath / bias vectors: fp32 flat (C,)
     * XLNet (C, H, d) einsum weights: q,k,v,r transposed to (H*d, C) (K-major B operand), o as (C, H*d)
+
+    flat (a trainer.FlatAdamW) + params (name -> Parameter): parameters owned by the flat optimizer are not copied — vectors
+    are live fp32 views, same-layout GEMM weights are views of the optimizer's bf16 planes (kept current by the fused AdamW
+    kernel); only the permuted layouts (k=3 convs, depthwise, XLNet q/k/v/r) are re-derived by `refresh_packed`.
     """
     W = {}
+    repack = []
     for k, v in sd.items():
         if not torch.is_floating_point(v):
             continue
         if k.startswith("backbone.xlnet.word_embedding") or ".adapters." in k:
             continue  # dead embedding table; adapters are packed once under their pets.* / pets_emas.* names
         v = v.detach().to(device=device, dtype=f32)
-        last = k.rsplit(".", 1)[-1]
-        if ".rel_attn." in k and last in ("q", "k", "v", "r"):
-            W[k] = ops.split16(v.reshape(v.shape[0], -1).t().contiguous())
-        elif ".rel_attn." in k and last == "o":
-            W[k] = ops.split16(v.reshape(v.shape[0], -1).contiguous())
-        elif k.endswith("_conv.conv.weight"):           # depthwise (C,1,3) -> (3,C) fp32
-            W[k] = v[:, 0, :].t().contiguous()
-        elif last == "weight" and v.dim() == 3 and v.shape[0] == 1 and v.shape[2] == 1:  # channel LN weight (1,C,1)
-            W[k] = v.reshape(-1).contiguous()
-        elif last == "weight" and v.dim() == 3 and v.shape[2] == 3:   # dense k=3 conv
-            W[k] = ops.split16(v.permute(2, 0, 1).contiguous())
-        elif last == "weight" and v.dim() == 3 and v.shape[2] == 1:   # 1x1 conv
-            W[k] = ops.split16(v[:, :, 0].contiguous())
-        elif last == "weight" and v.dim() == 2:                        # nn.Linear
-            W[k] = ops.split16(v.contiguous())
-        else:                                                          # biases, scales, LN vectors, mu/sigma ...
-            W[k] = v.reshape(-1).contiguous() if v.dim() != 2 else v.contiguous()
+        kind = _pack_kind(k, v)
+        prm = params.get(k) if (flat is not None and params is not None) else None
+        if prm is not None and id(prm) in flat.slots:
+            if kind == "vec":
+                W[k] = prm.data.reshape(-1) if prm.dim() != 2 else prm.data
+                continue
+            if kind == "gemm":
+                W[k] = flat.plane_view(prm, (prm.shape[0], prm.numel() // prm.shape[0]))
+                continue
+            repack.append((k, kind, prm))
+        W[k] = _pack_one(kind, v)
+    W["_repack"] = repack
     return W
+
+
+def refresh_packed(W):
+    """Re-derive the permuted copies after an in-place parameter update and drop everything cached from the old weights."""
+    for k, kind, prm in W.get("_repack", ()):
+        W[k] = _pack_one(kind, prm.data)
+    W["_cache"] = {}
 
 
 def sinusoid_pe_table(max_len, C, device):

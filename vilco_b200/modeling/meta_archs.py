@@ -288,7 +288,15 @@ class PtTransformer(nn.Module):
     # ---- small surface used by the orchestration -------------------------------------------------
     @property
     def device(self):
-        return list(set(p.device for p in self.parameters()))[0]
+        return next(self.parameters()).device
+
+    def _param_table(self):
+        """(names, parameters) cached: walking the module tree costs ~4 ms and is needed several times per step."""
+        tab = getattr(self, "_ptab", None)
+        if tab is None:      # reset by attach_pets / augment_classification, the only places that add or replace parameters
+            named = list(self.named_parameters())
+            tab = self._ptab = ([k for k, _ in named], [p_ for _, p_ in named], len(named))
+        return tab
 
     def attach_pets(self, pets):
         """register the adapters under backbone.branch.<b>.adapters.attn like AdapterMixin.attach_adapter (blocks.py:28-33)"""
@@ -297,6 +305,7 @@ class PtTransformer(nn.Module):
             if not isinstance(getattr(blk, "adapters", None), nn.ModuleDict):
                 blk.adapters = nn.ModuleDict()
             blk.adapters["attn"] = pets[i]
+        self._ptab = None
 
     def pre_train_epoch(self, task_id=0, current_epoch=0):
         if self.use_adapt:
@@ -320,6 +329,7 @@ class PtTransformer(nn.Module):
             new.data[:old] = getattr(self, name).data
             setattr(self, name, new)
         self._packed = None
+        self._ptab = None
 
     # ---- weights ---------------------------------------------------------------------------------
     def engine_cfg(self):
@@ -329,14 +339,27 @@ class PtTransformer(nn.Module):
         c.adapt_blocks = tuple(self.adapt_blocks)
         return c
 
+    def use_flat_optimizer(self, opt):
+        """Register a trainer.FlatAdamW: its bf16 planes become the GEMM operands of this model (no re-packing per step)."""
+        self._flat = opt
+        self._packed = None
+
     def packed_weights(self):
         """bf16 operand copies of the parameters, re-packed whenever a parameter changed (optimizer step, load_state_dict,
         augment_classification) or the precision mode changed."""
-        key = (ops.precision(), tuple(p._version for p in self.parameters()), tuple(id(p) for p in self.parameters()))
+        flat = getattr(self, "_flat", None)
+        plist = self._param_table()[1]
+        key = (ops.precision(), tuple(p._version for p in plist), tuple(id(p) for p in plist))
         if self._packed is None or key != self._packed_key:
-            self._packed = E.pack_weights(self.state_dict(), self.device)
+            if flat is not None:
+                flat.refresh_planes()
+            self._packed = E.pack_weights(self.state_dict(), self.device, flat, dict(self.named_parameters()) if flat is not None else None)
             self._packed_key = key
+            self._packed_epoch = flat.epoch if flat is not None else 0
             self._pe = E.sinusoid_pe_table(self.max_seq_len, self.embd_dim, self.device)
+        elif flat is not None and self._packed_epoch != flat.epoch:
+            E.refresh_packed(self._packed)
+            self._packed_epoch = flat.epoch
         return self._packed
 
     # ---- preprocessing (reference: meta_archs.py:1134-1221) -------------------------------------------
@@ -556,7 +579,8 @@ class PtTransformer(nn.Module):
             w_reg = self.train_loss_weight if self.train_loss_weight > 0 else float(s[0] / norm) / max(float(s[1] / norm), 0.01)
             w_al = self.al_loss_weight if K != 1 else 0.0
             final = cls_loss + reg_loss * w_reg + al_loss * w_al
-        named = dict(self.named_parameters())
+        names_, plist_, _ = self._param_table()
+        named = dict(zip(names_, plist_))
         model = self
 
         def run_backward(gscale):

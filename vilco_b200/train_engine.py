@@ -89,15 +89,18 @@ class Tape:
         W = self.W
         x16 = self.planes(x)
         y = V(ops.conv3(x16, W[wkey], f32, bias=W[bkey] if bkey else None, rowmul=rowmul))
-        if wkey + ".flip" not in W:
-            W[wkey + ".flip"] = W[wkey].flip(1).contiguous()
-
+        cache = W.setdefault("_cache", {})       # derived from the current weights; dropped when they change
         N = W[wkey].shape[2]
         N8 = (N + 7) // 8 * 8
-        if N8 != N and wkey + ".flip8" not in W:     # dgrad contracts over N: keep 16-byte operand rows
-            wp = torch.zeros(W[wkey].shape[0], 3, N8, W[wkey].shape[3], device=y.v.device, dtype=bf16)
-            wp[:, :, :N] = W[wkey + ".flip"]
-            W[wkey + ".flip8"] = wp
+        fkey = (wkey, "flip", N8)
+        if fkey not in cache:                   # tap-reversed weights; rows padded to 8 so the dgrad K keeps 16-byte rows
+            wf = W[wkey].flip(1)
+            if N8 != N:
+                wp = torch.zeros(wf.shape[0], 3, N8, wf.shape[3], device=wf.device, dtype=bf16)
+                wp[:, :, :N] = wf
+                wf = wp
+            cache[fkey] = wf.contiguous()
+        wflip = cache[fkey]
 
         def bwd():
             if y.g is None:
@@ -105,10 +108,10 @@ class Tape:
             if N8 != N:
                 g8 = torch.zeros(*y.g.shape[:-1], N8, device=y.g.device, dtype=f32)
                 g8[..., :N] = y.g
-                dx, dw, db = BW.conv3_bwd(g8, x16, None, W[wkey + ".flip8"], rowmul=rowmul)
+                dx, dw, db = BW.conv3_bwd(g8, x16, None, wflip, rowmul=rowmul, need_dx=not x.const)
                 dw, db = dw[:, :N].contiguous(), db[:N].contiguous()
             else:
-                dx, dw, db = BW.conv3_bwd(y.g, x16, W[wkey], W[wkey + ".flip"], rowmul=rowmul)
+                dx, dw, db = BW.conv3_bwd(y.g, x16, None, wflip, rowmul=rowmul, need_dx=not x.const)
             self.acc(x, dx)
             self.accp(wkey, dw)
             if bkey:

@@ -45,21 +45,33 @@ class Trainer:
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.clip = float(clip_grad_l2norm)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.grads = FlatGrads(model.parameters())
+        self.flat = isinstance(optimizer, FlatAdamW)
+        if self.flat:
+            model.use_flat_optimizer(optimizer)
+        else:
+            self.grads = FlatGrads(model.parameters())
 
     def step(self, video_list, task_id=0, prev_out_cls_logits=None):
         """video_list = this rank's share of the global batch.  Returns the loss dict of this rank (tensors)."""
-        if not self.grads.attached():
-            self.grads = FlatGrads(self.model.parameters())
-        self.grads.zero()
+        if self.flat:
+            self.optimizer.zero_grad()
+            flat = self.optimizer.flat_grad
+        else:
+            if not self.grads.attached():
+                self.grads = FlatGrads(self.model.parameters())
+            self.grads.zero()
+            flat = self.grads.flat
         losses = self.model(video_list, task_id=task_id, prev_out_cls_logits=prev_out_cls_logits or [])
         losses["final_loss"].backward()
         if self.world > 1:
-            dist.all_reduce(self.grads.flat)
-            self.grads.flat.div_(self.world)
-        if self.clip > 0.0:
-            torch.nn.utils.clip_grad_norm_(self.grads.params, self.clip)
-        self.optimizer.step()
+            dist.all_reduce(flat)
+            flat.div_(self.world)
+        if self.flat:
+            self.optimizer.step(clip_grad_l2norm=self.clip)
+        else:
+            if self.clip > 0.0:
+                torch.nn.utils.clip_grad_norm_(self.grads.params, self.clip)
+            self.optimizer.step()
         if self.scheduler is not None:
             self.scheduler.step()
         if getattr(self.model, "use_adapt", False):
@@ -67,9 +79,10 @@ class Trainer:
         return losses
 
 
-def make_optimizer(model, optimizer_config):
+def make_optimizer(model, optimizer_config, flat=False):
     """Parameter grouping of the reference's make_optimizer (train_utils.py:68-143): biases, LayerNorm weights, Scale /
-    AffineDropPath scales and XLNet norms are not decayed, everything else is."""
+    AffineDropPath scales and XLNet norms are not decayed, everything else is.  flat=True returns the FlatAdamW below
+    (same update rule, hand-written kernels) instead of torch.optim.AdamW."""
     from .modeling.blocks import AffineDropPath, LayerNorm, MaskedConv1D, Scale
     decay, no_decay = set(), set()
     white = (torch.nn.Linear, torch.nn.Conv1d, MaskedConv1D)
@@ -102,5 +115,104 @@ def make_optimizer(model, optimizer_config):
     if optimizer_config["type"] == "SGD":
         return torch.optim.SGD(groups, lr=optimizer_config["learning_rate"], momentum=optimizer_config["momentum"])
     if optimizer_config["type"] == "AdamW":
+        if flat:
+            return FlatAdamW(groups, lr=optimizer_config["learning_rate"])
         return torch.optim.AdamW(groups, lr=optimizer_config["learning_rate"])
     raise TypeError("Unsupported optimizer!")
+
+
+class FlatAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics on flat buffers with hand-written kernels (csrc/optim.cu).
+
+    All trainable parameters, their gradients and both moments live in four contiguous fp32 buffers (parameter groups are
+    contiguous segments, every tensor starts at a multiple of 8 elements); `param.data` / `param.grad` are views, so the
+    model, state_dict and the gradient all-reduce keep working unchanged.  One step = global-norm kernel + clip coefficient
+    + one fused AdamW launch per parameter group, which also rewrites the bf16 (hi, lo) operand planes the GEMM kernels
+    read (`self.planes`), so no per-tensor weight re-packing happens between iterations.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        from . import ops
+        seen, n = set(), 0
+        self.slots = {}          # id(param) -> (offset, numel)
+        self.segments = []       # (start, end, group)
+        for g in self.param_groups:
+            start = n
+            for p in g["params"]:
+                if not p.requires_grad or id(p) in seen:
+                    continue
+                seen.add(id(p))
+                self.slots[id(p)] = (n, p.numel())
+                n = (n + p.numel() + 7) // 8 * 8
+            self.segments.append((start, n, g))
+        dev = next(p for g in self.param_groups for p in g["params"]).device
+        assert dev.type == "cuda", "FlatAdamW runs on the CUDA kernels only"
+        self.n = n
+        self.flat_p = torch.zeros(n, device=dev)
+        self.flat_grad = torch.zeros(n, device=dev)
+        self.exp_avg = torch.zeros(n, device=dev)
+        self.exp_avg_sq = torch.zeros(n, device=dev)
+        self._scal = torch.zeros(3, device=dev)   # sum of squares, clip coefficient, gradient norm
+        self.t = 0
+        self.epoch = 0           # bumped on every update; the model re-derives its permuted weight copies when it changes
+        for g in self.param_groups:
+            for p in g["params"]:
+                if id(p) in self.slots:
+                    o, k = self.slots[id(p)]
+                    self.flat_p[o:o + k].copy_(p.data.reshape(-1))
+                    p.data = self.flat_p[o:o + k].view(p.shape)
+                    p.grad = self.flat_grad[o:o + k].view(p.shape)
+        self.planes = None
+        self._planes_precision = None
+        self.refresh_planes()
+
+    def refresh_planes(self):
+        """(PLANES, n) bf16 hi / lo copies of every parameter (needed after load_state_dict or a precision switch; the
+        optimizer step keeps them current by itself)."""
+        from . import ops
+        with torch.no_grad():
+            hi = self.flat_p.to(torch.bfloat16)
+            self.planes = torch.stack([hi, (self.flat_p - hi.float()).to(torch.bfloat16)]) if ops.PLANES == 2 else hi.unsqueeze(0).clone()
+        self._planes_precision = ops.precision()
+
+    def plane_view(self, p, shape):
+        o, k = self.slots[id(p)]
+        return self.planes[:, o:o + k].view(self.planes.shape[0], *shape)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+        for g in self.param_groups:            # re-attach views something may have replaced
+            for p in g["params"]:
+                if id(p) in self.slots and (p.grad is None or p.grad.untyped_storage().data_ptr() != self.flat_grad.untyped_storage().data_ptr()):
+                    o, k = self.slots[id(p)]
+                    p.grad = self.flat_grad[o:o + k].view(p.shape)
+
+    @torch.no_grad()
+    def step(self, closure=None, clip_grad_l2norm=-1.0):
+        import ctypes as C
+        from . import lib as L
+        from . import ops
+        if ops.precision() != self._planes_precision:
+            self.refresh_planes()
+        self.t += 1
+        st = L.stream_ptr()
+        s = self._scal
+        L.check(L.lib().vilco_grad_clip_coef(ops._p(self.flat_grad), ops._i64(self.n), C.c_float(float(clip_grad_l2norm)),
+                                             C.c_void_p(s.data_ptr()), C.c_void_p(s.data_ptr() + 4), C.c_void_p(s.data_ptr() + 8), st),
+                "vilco_grad_clip_coef")
+        NP = self.planes.shape[0]
+        for a, b, g in self.segments:
+            if b <= a:
+                continue
+            L.check(L.lib().vilco_adamw(
+                C.c_void_p(self.flat_p.data_ptr() + 4 * a), C.c_void_p(self.flat_grad.data_ptr() + 4 * a),
+                C.c_void_p(self.exp_avg.data_ptr() + 4 * a), C.c_void_p(self.exp_avg_sq.data_ptr() + 4 * a), ops._i64(b - a),
+                C.c_float(g["lr"]), C.c_float(g["betas"][0]), C.c_float(g["betas"][1]), C.c_float(g["eps"]),
+                C.c_float(g["weight_decay"]), int(self.t), C.c_void_p(s.data_ptr() + 4),
+                C.c_void_p(self.planes.data_ptr() + 2 * a), ops._i64(self.n if NP == 2 else 0), st), "vilco_adamw")
+        self.epoch += 1
+
+    def grad_norm(self):
+        """global L2 norm of the last step's (un-clipped) gradient — what clip_grad_norm_ returns."""
+        return self._scal[2]
