@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Benchmark of the Moment-Query hot path (BASELINE.json metric: MQ infer videos/s incl. soft-NMS; the training half of
-the metric needs the backward kernels, which are not built yet — see DESIGN.md).
+"""Benchmark of the Moment-Query hot path (BASELINE.json metric: MQ train videos/s & infer videos/s incl. soft-NMS).
+The headline `value` is inference; the training half of the metric is the `train` object of the same JSON line.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation of the same path
@@ -11,6 +11,8 @@ pack -> backbone -> neck -> heads -> decode -> soft-NMS.
   value : videos/s with the inputs already resident in HBM (CUDA-graph replay, CUDA-event timing, max over ranks)
   e2e   : videos/s through the public streaming API `EvalGraph.infer_stream(batches)` with pinned HOST inputs, including
           every step's H2D copies (double-buffered against the previous step's compute) and the D2H read of the detections.
+  train : one iteration of the reference's train_one_epoch loop (zero_grad, forward with dropout / drop-path, loss,
+          backward, NCCL gradient all-reduce for N > 1, clip_grad_norm 1.0, AdamW) on `--train-batch` clips per GPU.
 """
 import argparse
 import json
@@ -112,6 +114,25 @@ def cpu_reference_rate(state_dict, n_videos, seed=7):
     return n_videos / dt, dt
 
 
+def cpu_reference_train_rate(state_dict, n_videos, seed=11):
+    """One optimisation step of the oracle (torch CPU autograd + torch AdamW) on n_videos clips."""
+    from oracle import mq_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.ModelCfg()
+    spec_ok = lambda k, v: torch.is_floating_point(v) and not k.startswith("backbone.xlnet.word_embedding")  # noqa: E731
+    P = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in state_dict.items() if spec_ok(k, v)}
+    opt = torch.optim.AdamW(list(P.values()), lr=1e-4, weight_decay=0.05)
+    vids = synth_videos(n_videos, seed)
+    t0 = time.perf_counter()
+    opt.zero_grad()
+    lo, _ = O.model_train_losses(P, cfg, vids)
+    lo["final_loss"].backward()
+    torch.nn.utils.clip_grad_norm_([p for p in P.values() if p.grad is not None], 1.0)
+    opt.step()
+    dt = time.perf_counter() - t0
+    return n_videos / dt, dt
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,13 +147,16 @@ def run_reference_arm(args):
         vals.append(rate)
     v = float(np.median(vals))
     cores = os.cpu_count() or 1
+    tr_rate, tr_dt = cpu_reference_train_rate(model.state_dict(), 2)
     line = {"impl": "reference", "metric": "mq_infer_videos_per_s", "value": v, "unit": "videos/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "videos_per_step": n},
             "cpu_baseline": {"value": v, "unit": "videos/s", "cores": cores, "kind": "port",
                              "sample": f"{n} clip(s) per step through oracle/mq_oracle.py (torch CPU fp32, {cores} threads) incl. soft-NMS (oracle/softnms.c)"},
-            "e2e": {"value": v, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "train": {"metric": "mq_train_videos_per_s", "value": tr_rate, "unit": "videos/s", "videos_per_step": 2,
+                      "sample": f"1 step (forward, loss, autograd backward, clip, AdamW) of 2 clips through the oracle on {cores} threads, {tr_dt:.1f} s"}}
     print(json.dumps(line), flush=True)
 
 
@@ -177,12 +201,69 @@ def gemm_roofline(graph_runner, model, B):
     return fl, t, len(rec)
 
 
+def run_train_leg(args, model, rank, world, dist, barrier, local):
+    """Training half of the metric: K timed iterations of trainer.Trainer.step (device-resident inputs), then K more with
+    pinned host inputs and a host read of the loss every step (e2e)."""
+    from vilco_b200 import lib as L
+    from vilco_b200.dist import max_over_ranks
+    from vilco_b200.trainer import Trainer, broadcast_parameters, make_optimizer
+    Bt = args.train_batch
+    torch.cuda.empty_cache()
+    model.train()
+    broadcast_parameters(model)
+    opt = make_optimizer(model, {"type": "AdamW", "learning_rate": 1e-4, "weight_decay": 0.05}, flat=True)
+    tr = Trainer(model, opt, clip_grad_l2norm=1.0)
+    host_sets = [synth_videos(Bt, seed=500 + rank * 10 + i, pin=True) for i in range(2)]
+    dev_set = [dict(v) for v in host_sets[0]]
+    for v in dev_set:
+        v["feats"] = v["feats"].cuda()
+    for _ in range(args.warmup):
+        tr.step(dev_set)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = L.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        tr.step(dev_set)
+    e1.record()
+    barrier()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    launches = (L.launch_count() - n0) // args.steps
+    for i in range(args.warmup):
+        float(tr.step(host_sets[i % 2])["final_loss"].detach())
+    barrier()
+    t0 = time.perf_counter()
+    last = 0.0
+    for i in range(args.steps):
+        last = float(tr.step(host_sets[i % 2])["final_loss"].detach())      # D2H read of the loss every step
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t_dev, t_e2e = max_over_ranks([t_dev, t_e2e], device="cuda")
+    mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    model.eval()
+    h2d = sum(v["feats"].numel() * 4 + v["prompt_feature"].numel() * 4 for v in host_sets[0])
+    return {"metric": "mq_train_videos_per_s", "value": world * Bt * args.steps / t_dev, "unit": "videos/s",
+            "ms_per_step": 1e3 * t_dev / args.steps, "videos_per_step_per_gpu": Bt, "gpu_launches_per_step": int(launches),
+            "e2e": {"value": world * Bt * args.steps / t_e2e, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "step": "zero_grad, forward (dropout 0.1, drop-path 0.1, XLNet dropout 0.1), focal + DIoU + label-involved loss, "
+                    "hand-written backward, " + ("NCCL all-reduce of one flat fp32 gradient buffer, " if world > 1 else "") +
+                    "clip_grad_norm 1.0, fused flat AdamW (lr 1e-4, wd 0.05)",
+            "grad_bytes_allreduced_per_step": int(opt.n * 4) if world > 1 else 0, "last_loss": last, "peak_mem_gib": mem,
+            "clocks": sampler.summary()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="clips per step per GPU")
+    ap.add_argument("--train-batch", type=int, default=16, help="clips per training step per GPU (0 = skip the training leg)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "bf16x3"])
     ap.add_argument("--ref-videos", type=int, default=4, help="clips per CPU-baseline sample")
@@ -249,10 +330,6 @@ def main():
     sampler.join(timeout=2)
     from vilco_b200.dist import max_over_ranks
     t_dev, t_e2e = max_over_ranks([t_dev, t_e2e], device="cuda")
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
     h2d = sum(v["feats"].numel() * 4 + v["prompt_feature"].numel() * 4 for v in sets[0]) + B * (1024 + 128 + 1) * 4
     d2h = B * (200 * (2 + 1) * 4 + 200 * 8 + 4)
     hbm, tf_burst, tf_sus, how = peaks()
@@ -285,6 +362,15 @@ def main():
     l1.record()
     torch.cuda.synchronize()
     lat_b1 = l0.elapsed_time(l1) / 10
+    launches_inf = int(g.launches * args.steps)
+    del g, g1          # release the CUDA-graph memory pools before the training leg
+    import gc
+    gc.collect()
+    train = run_train_leg(args, model, rank, world, dist, barrier, local) if args.train_batch > 0 else None
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     line = {
         "metric": "mq_infer_videos_per_s", "value": world * B * args.steps / t_dev, "unit": "videos/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
@@ -293,12 +379,13 @@ def main():
         "config": {"workload": WORKLOAD, "videos_per_step_per_gpu": B,
                    "precision": "bf16x3: bf16 hi+lo operand planes, 3 tcgen05.mma per k-step, fp32 accumulate (parity mode)" if ops.precision() == "bf16x3" else "bf16 single plane (fast mode, ~4e-3 rel. error)",
                    "l2": "working set (packed weights > 0.9 GB per step) exceeds the 126 MB L2; no explicit flush",
-                   "train": "not measured: backward kernels not built yet"},
+                   "train_videos_per_step_per_gpu": args.train_batch},
         "e2e": {"value": world * B * args.steps / t_e2e, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(g.launches * args.steps),
+        "gpu_launches": launches_inf,
         "clocks": sampler.summary(),
         "roofline": roof,
         "latency_b1_ms": lat_b1,
+        "train": train,
     }
     if not args.no_cpu_baseline:
         rate, dt = cpu_reference_rate(model.state_dict(), args.ref_videos)
