@@ -78,6 +78,8 @@ typedef struct VilcoGemm {
   const float* resid; int32_t resid_masked;
   int32_t impl;
   int32_t band_lo, band_hi;   /* band_hi > band_lo: only outputs with band_lo <= m + n < band_hi are computed (others untouched) */
+  int32_t a_major;            /* 0: A is (a_rows, K) K-major (row stride a_ld).  1: A is stored (K, M) MN-major — element (m, k) at
+                                 A[k * a_ld + m] — the natural layout of a gradient matrix used as dZ^T in dW = dZ^T X; taps must be 1 */
 } VilcoGemm;
 
 int vilco_gemm(const VilcoGemm* g, void* stream);

@@ -44,23 +44,24 @@ def colsum(x, y=None, rowmul=None, out=None):
     return out
 
 
-def wgrad(dzT, x2, Mo, No, R, alpha=1.0):
-    """dW (Mo, No) = dz^T (Mo, R) @ x (R, No): A = transposed gradient planes (row stride ldT), B = activations as MN-major
-    operand.  The reduction runs over all B*T rows while the output has few tiles, so K is split over up to 16 CTAs-worth of
-    batches (split-K) whenever the plain launch would leave most of the 148 SMs idle; partials are summed by vilco_colsum."""
-    ldT = dzT.shape[-1]
+def wgrad(dz, x2, Mo, No, R, alpha=1.0):
+    """dW (Mo, No) = dz^T @ x with dz (NP, R, Mo) and x2 (NP, R, No) both in their natural token-major layout: dz is read as
+    an MN-major A operand and x as an MN-major B operand, so no transposed copy is made.  The reduction runs over all B*T
+    rows while the output has few tiles, so K is split over batches (split-K) whenever the plain launch would leave most
+    of the 148 SMs idle; partials are summed by vilco_colsum."""
     tiles = ((Mo + 127) // 128) * ((No + 127) // 128)
     S = min(16, 148 // tiles) if tiles < 100 else 1
     while S > 1 and (R % (8 * S) != 0 or R // S < 512):
         S -= 1
     if S <= 1:
         dw = torch.empty(Mo, No, device=x2.device, dtype=f32)
-        L.gemm(dzT, x2, dw, M=Mo, N=No, K=R, a_rows=Mo, a_ld=ldT, b_ld=No, d_ld=No, b_major=1, alpha=alpha, a_lo=lo(dzT), b_lo=lo(x2))
+        L.gemm(dz, x2, dw, M=Mo, N=No, K=R, a_rows=Mo, a_ld=Mo, a_major=1, b_ld=No, d_ld=No, b_major=1, alpha=alpha,
+               a_lo=lo(dz), b_lo=lo(x2))
         return dw
     chunk = R // S
     part = torch.empty(S, Mo, No, device=x2.device, dtype=f32)
-    L.gemm(dzT, x2, part, M=Mo, N=No, K=chunk, a_rows=Mo, a_ld=ldT, a_s=(chunk, 0), Z=(S, 1), b_ld=No, b_s=(chunk * No, 0),
-           b_batched=True, b_major=1, d_ld=No, d_s=(Mo * No, 0), alpha=alpha, a_lo=lo(dzT), b_lo=lo(x2))
+    L.gemm(dz, x2, part, M=Mo, N=No, K=chunk, a_rows=Mo, a_ld=Mo, a_major=1, a_s=(chunk * Mo, 0), Z=(S, 1), b_ld=No,
+           b_s=(chunk * No, 0), b_batched=True, b_major=1, d_ld=No, d_s=(Mo * No, 0), alpha=alpha, a_lo=lo(dz), b_lo=lo(x2))
     return colsum(part.reshape(S, Mo * No)).reshape(Mo, No)
 
 
@@ -70,13 +71,13 @@ def linear_bwd(dy, x16, w16, rowmul=None, alpha=1.0, need_dx=True, need_dw=True,
     N, K = w16.shape[1], w16.shape[2]
     dy2 = dy.reshape(-1, N)
     R = dy2.shape[0]
-    dz, dzT = to_planes(dy2, rowmul, None, want=need_dx, want_t=need_dw)
+    dz, _ = to_planes(dy2, rowmul, None)
     dx = dw = db = None
     if need_dx:
         dx = torch.empty(*dy.shape[:-1], K, device=dy.device, dtype=f32)
         L.gemm(dz, w16, dx, M=R, N=K, K=N, a_rows=R, a_ld=N, b_ld=K, d_ld=K, b_major=1, alpha=alpha, a_lo=lo(dz), b_lo=lo(w16))
     if need_dw:
-        dw = wgrad(dzT, x16.reshape(x16.shape[0], -1, K), N, K, R, alpha)
+        dw = wgrad(dz, x16.reshape(x16.shape[0], -1, K), N, K, R, alpha)
     if need_db:
         db = colsum(dy2, rowmul=rowmul)
     return dx, dw, db
@@ -95,7 +96,7 @@ def conv3_bwd(dy, x16, w3, w3_flip, rowmul=None, need_dx=True):
     dy (B,T,N) fp32, x16 (NP,B,T,K), w3 / w3_flip (NP,3,N,K) (flip = taps reversed) -> (dx (B,T,K), dw3 (3,N,K), db (N,))."""
     B, T, N = dy.shape
     K = w3_flip.shape[3]
-    dz, dzT = to_planes(dy.reshape(-1, N), rowmul.reshape(-1) if rowmul is not None else None, None, want=need_dx, want_t=True)
+    dz, _ = to_planes(dy.reshape(-1, N), rowmul.reshape(-1) if rowmul is not None else None, None)
     dx = None
     if need_dx:
         # dx[b,t] = sum_tap dz[b, t - tap + 1] w3[tap] = sum_tap' dz[b, t + tap' - 1] w3[2 - tap']: the forward conv kernel
@@ -108,7 +109,7 @@ def conv3_bwd(dy, x16, w3, w3_flip, rowmul=None, need_dx=True):
     taps = []
     for tap in range(3):
         xs = x16 if tap == 1 else shift_planes(x16, tap - 1)
-        taps.append(wgrad(dzT, xs.reshape(xs.shape[0], R, K), N, K, R))
+        taps.append(wgrad(dz, xs.reshape(xs.shape[0], R, K), N, K, R))
     dw = torch.stack(taps)
     db = colsum(dy.reshape(-1, N), rowmul=rowmul.reshape(-1) if rowmul is not None else None)
     return dx, dw, db
@@ -183,14 +184,20 @@ def attention_bwd(dO, q16, k16, v16, kmask, H, scale):
     dS = torch.empty_like(dP)
     L.check(L.lib().vilco_softmax_bwd(_p(P32), _p(dP), _p(dS), _i64(B * H * Tq), Tk, C.c_float(scale), L.stream_ptr()),
             "vilco_softmax_bwd")
+    if Tk % 8 == 0:
+        dS16, _ = to_planes(dS, batch_dims=2)                      # (NP,B,H,Tq,Tk)
+        P16b, _ = to_planes(P32, batch_dims=2)
+        dq = ops.attn_pv(dS16, k16, H, Tk, out32=True)               # dQ_h = dS K_h
+        dk = ops.attn_pv(dS16, q16, H, Tq, out32=True, a_trans=True, M=Tk)   # dK_h = dS^T Q_h  (dS read as MN-major A)
+        dv = ops.attn_pv(P16b, dO16, H, Tq, out32=True, a_trans=True, M=Tk)  # dV_h = P^T dO_h
+        return dq, dk, dv
+    # Tk not a multiple of 8 (text keys): operand rows must keep 16-byte strides -> padded copy / explicit transposes
     dS16, dST16 = to_planes(dS, want=True, want_t=True, batch_dims=2)   # (NP,B,H,Tq,Tk) and (NP,B,H,Tk,ldq)
-    if Tk % 8:   # A-operand rows must keep 16-byte strides
-        pad = (Tk + 7) // 8 * 8
-        t2 = ops.zeros16(B, H, Tq, pad, device=dS.device)
-        t2[..., :Tk] = dS16
-        dS16 = t2
-    dq = ops.attn_pv(dS16, k16, H, Tk, out32=True)               # dQ_h = dS K_h
-    dk = ops.attn_pv(dST16, q16, H, Tq, out32=True)              # dK_h = dS^T Q_h
+    pad = (Tk + 7) // 8 * 8
+    t2 = ops.zeros16(B, H, Tq, pad, device=dS.device)
+    t2[..., :Tk] = dS16
+    dq = ops.attn_pv(t2, k16, H, Tk, out32=True)
+    dk = ops.attn_pv(dST16, q16, H, Tq, out32=True)
     _, PT16 = to_planes(P32, want=False, want_t=True, batch_dims=2)
-    dv = ops.attn_pv(PT16, dO16, H, Tq, out32=True)              # dV_h = P^T dO_h
+    dv = ops.attn_pv(PT16, dO16, H, Tq, out32=True)
     return dq, dk, dv

@@ -24,6 +24,7 @@ struct GemmDev {
   int a_slot_row, a_slot_z1, a_slot_z2;
   int b_slot_row, b_slot_z1, b_slot_z2;
   int M, N, K, taps, Z1, Ztot;
+  int a_major;
   int band_lo, band_hi;  // when band_hi > band_lo: only elements with band_lo <= m + n < band_hi are needed; tiles outside are skipped
   int b_major, b_batched;
   void* D; int d_dtype; long long d_ld, d_s1, d_s2, d_lo;
@@ -116,11 +117,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // instruction descriptor for kind::f16: bf16 x bf16 -> f32, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn_major) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn_major, int a_mn_major = 0) {
   return (1u << 4)                                   // c_format = F32
          | (1u << 7)                                 // a_format = BF16
          | (1u << 10)                                // b_format = BF16
-         | (0u << 15)                                // a_major  = K
+         | (static_cast<uint32_t>(a_mn_major) << 15) // a_major
          | (static_cast<uint32_t>(b_mn_major) << 16) // b_major
          | (static_cast<uint32_t>(n >> 3) << 17)     // n_dim
          | (static_cast<uint32_t>(BM >> 4) << 24);   // m_dim
@@ -242,8 +243,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES * L::PLANES;
           mbar_expect_tx(full0 + 8 * s, L::STAGE_BYTES);
-          ca[0] = kb * BK;
-          ca[p.a_slot_row] = m0 + tap - (p.taps >> 1);
+          if (p.a_major == 0) {
+            ca[0] = kb * BK;
+            ca[p.a_slot_row] = m0 + tap - (p.taps >> 1);
+          } else {
+            ca[0] = m0;
+            ca[p.a_slot_row] = kb * BK;
+          }
           cb[p.b_slot_z1] = p.b_batched ? z1 : tap;
           if (p.b_major == 0) {
             cb[0] = kb * BK;
@@ -254,7 +260,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
 #pragma unroll
           for (int pl = 0; pl < L::PLANES; ++pl) {
-            tma_load_5d(sa + pl * L::A_BYTES, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3], pl);
+            if (p.a_major == 0) {
+              tma_load_5d(sa + pl * L::A_BYTES, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3], pl);
+            } else {   // MN-major A: two (64 m x BK k) boxes, BK*128 bytes apart
+              tma_load_5d(sa + pl * L::A_BYTES, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3], pl);
+              tma_load_5d(sa + pl * L::A_BYTES + BK * 128, &tmA, full0 + 8 * s, ca[0] + 64, ca[1], ca[2], ca[3], pl);
+            }
             if (BN <= 64 || p.b_major == 0) {
               tma_load_5d(sb + pl * L::B_BYTES, &tmB, full0 + 8 * s, cb[0], cb[1], cb[2], cb[3], pl);
             } else {
@@ -269,7 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
-    const uint32_t idesc = make_idesc(BN, p.b_major);
+    const uint32_t idesc = make_idesc(BN, p.b_major, p.a_major);
     uint32_t it_g = 0, tc = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       {
@@ -292,14 +303,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: advance 16 elements = 32 bytes inside the swizzle atom; MN-major: 16 k-rows of 128 bytes.
-            const uint32_t aoff = k * UMMA_K * 2;
+            const uint32_t aoff = p.a_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
+            const uint32_t a_lbo = p.a_major == 0 ? 16 : BK * 128;
             const uint32_t boff = p.b_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
-            const uint64_t a_hi = make_smem_desc(sa + aoff, 16, 1024);
+            const uint64_t a_hi = make_smem_desc(sa + aoff, a_lbo, 1024);
             const uint32_t b_lbo = p.b_major == 0 ? 16 : BK * 128;   // MN-major: distance between 64-column swizzle atoms
             const uint64_t b_hi = make_smem_desc(sb + boff, b_lbo, 1024);
             tcgen05_mma_f16(tmem_d, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
             if (SPLIT) {
-              const uint64_t a_lo = make_smem_desc(sa + L::A_BYTES + aoff, 16, 1024);
+              const uint64_t a_lo = make_smem_desc(sa + L::A_BYTES + aoff, a_lbo, 1024);
               const uint64_t b_lo = make_smem_desc(sb + L::B_BYTES + boff, b_lbo, 1024);
               tcgen05_mma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
               tcgen05_mma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
@@ -478,6 +490,13 @@ __global__ void gemm_simt_kernel(const GemmDev p, const SimtAddr q) {
     for (int tap = 0; tap < p.taps; ++tap) {
       const int row = m + tap - (p.taps >> 1);
       if (row < 0 || row >= q.a_rows) continue;
+      if (p.a_major == 1) {   // A stored (K, M): element (m, k) at k * a_ld + m; B MN-major or K-major
+        const __nv_bfloat16* a = q.A + z1 * q.a_s1 + z2 * q.a_s2 + m;
+        const __nv_bfloat16* b = q.B + (p.b_batched ? z1 * q.b_s1 + z2 * q.b_s2 : 0) + (p.b_major == 0 ? (long long)n * q.b_ld : n);
+        const long long bs = p.b_major == 0 ? 1 : q.b_ld;
+        for (int k = 0; k < p.K; ++k) acc = fmaf(ld_split(a + (long long)k * q.a_ld, q.a_lo), ld_split(b + k * bs, q.b_lo), acc);
+        continue;
+      }
       const __nv_bfloat16* a = q.A + z1 * q.a_s1 + z2 * q.a_s2 + (long long)row * q.a_ld;
       if (p.b_major == 0) {
         const __nv_bfloat16* b = q.B + (p.b_batched ? z1 * q.b_s1 + z2 * q.b_s2 : tap * q.b_s1) + (long long)n * q.b_ld;
@@ -879,11 +898,13 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   VILCO_CHECK_ARG(!(g->b_batched && g->taps != 1), "vilco_gemm: batched B cannot have taps");
   VILCO_CHECK_ARG(g->d_dtype == VILCO_F32 || g->d_dtype == VILCO_BF16, "vilco_gemm: bad d_dtype");
   VILCO_CHECK_ARG(!(g->resid_masked && !g->rowmul), "vilco_gemm: resid_masked needs rowmul");
+  VILCO_CHECK_ARG(g->a_major == 0 || (g->a_major == 1 && g->taps == 1), "vilco_gemm: MN-major A needs taps == 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   GemmDev p{};
   p.M = g->M; p.N = g->N; p.K = g->K; p.taps = g->taps; p.Z1 = g->Z1; p.Ztot = g->Z1 * g->Z2;
   p.band_lo = g->band_lo; p.band_hi = g->band_hi;
+  p.a_major = g->a_major;
   p.b_major = g->b_major; p.b_batched = g->b_batched;
   p.D = g->D; p.d_dtype = g->d_dtype; p.d_ld = g->d_ld; p.d_s1 = g->d_s1; p.d_s2 = g->d_s2;
   p.d_lo = g->d_dtype == VILCO_BF16 ? g->d_lo : 0;
@@ -927,8 +948,13 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   CUtensorMap tmA, tmB;
   int sa[3], sb[3];
   const bool split = g->a_lo != 0 && g->b_lo != 0;
-  int rc = encode_map(&tmA, g->A, (uint64_t)g->K, (uint64_t)g->a_rows, g->a_ld, (uint64_t)g->Z1, g->a_s1,
-                      (uint64_t)g->Z2, g->a_s2, split ? g->a_lo : 0, BK, BM, sa);
+  int rc;
+  if (g->a_major == 0)
+    rc = encode_map(&tmA, g->A, (uint64_t)g->K, (uint64_t)g->a_rows, g->a_ld, (uint64_t)g->Z1, g->a_s1,
+                    (uint64_t)g->Z2, g->a_s2, split ? g->a_lo : 0, BK, BM, sa);
+  else   // (m inner, k rows, z1, z2), one 64-wide swizzle atom per box
+    rc = encode_map(&tmA, g->A, (uint64_t)g->M, (uint64_t)g->K, g->a_ld, (uint64_t)g->Z1, g->a_s1,
+                    (uint64_t)g->Z2, g->a_s2, split ? g->a_lo : 0, 64, BK, sa);
   if (rc) return rc;
   if (g->b_major == 0) {
     // (k inner, n rows, z1|tap, z2)

@@ -34,7 +34,7 @@ class VilcoGemm(C.Structure):
         ("colscale", C.c_void_p),
         ("resid", C.c_void_p), ("resid_masked", C.c_int32),
         ("impl", C.c_int32),
-        ("band_lo", C.c_int32), ("band_hi", C.c_int32),
+        ("band_lo", C.c_int32), ("band_hi", C.c_int32), ("a_major", C.c_int32),
     ]
 
 
@@ -84,7 +84,7 @@ def default_gemm_impl():
 
 def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), d_s=(0, 0), Z=(1, 1), taps=1,
          b_major=0, b_batched=False, alpha=1.0, bias=None, rowmul=None, rowmul_zs=0, act=ACT_NONE,
-         colscale=None, resid=None, resid_masked=False, impl=None, a_lo=0, b_lo=0, d_lo=0, band=(0, 0)):
+         colscale=None, resid=None, resid_masked=False, impl=None, a_lo=0, b_lo=0, d_lo=0, band=(0, 0), a_major=0):
     """Raw descriptor-level call of ``vilco_gemm`` (see include/vilco_b200.h for the contract)."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
     assert D.dtype in (torch.float32, torch.bfloat16)
@@ -107,5 +107,6 @@ def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), 
     g.resid_masked = int(resid_masked)
     g.impl = default_gemm_impl() if impl is None else impl
     g.band_lo, g.band_hi = band
+    g.a_major = a_major
     check(lib().vilco_gemm(C.byref(g), stream_ptr()), "vilco_gemm")
     return D

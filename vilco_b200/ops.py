@@ -109,16 +109,19 @@ def attn_scores(q, k, H, alpha, band=(0, 0)):
     return out
 
 
-def attn_pv(P, v, H, Tk, out32=False):
-    """O[b, :, h*d:(h+1)*d] = P[b,h] v_h.  P (NP,B,H,Tq,ldp), v (NP,B,Tk,C) -> operand (NP,B,Tq,C) (fp32 (B,Tq,C) if out32)."""
-    _, B, _, Tq, ldp = P.shape
+def attn_pv(P, v, H, Tk, out32=False, a_trans=False, M=None):
+    """O[b, :, h*d:(h+1)*d] = P[b,h] v_h.  P (NP,B,H,Tq,ldp), v (NP,B,Tk,C) -> operand (NP,B,Tq,C) (fp32 (B,Tq,C) if out32).
+    a_trans: use P[b,h]^T instead — P is (NP,B,H,Tk,ldp) with M <= ldp valid columns, read as an MN-major A operand (no
+    transposed copy), result (B,M,C)."""
+    _, B, _, R, ldp = P.shape
     Cc = v.shape[3]
     d = Cc // H
     assert d == 64, "attn_pv: head dim must be 64"
+    Tq = (M if M is not None else ldp) if a_trans else R
     out = torch.empty(B, Tq, Cc, device=v.device, dtype=f32) if out32 else empty16(B, Tq, Cc, device=v.device)
-    L.gemm(P, v, out, M=Tq, N=d, K=Tk, a_rows=Tq, a_ld=ldp, a_s=(Tq * ldp, H * Tq * ldp), Z=(H, B), b_ld=Cc,
+    L.gemm(P, v, out, M=Tq, N=d, K=Tk, a_rows=Tq, a_ld=ldp, a_s=(R * ldp, H * R * ldp), Z=(H, B), b_ld=Cc,
            b_s=(d, Tk * Cc), b_batched=True, b_major=1, d_ld=Cc, d_s=(d, Tq * Cc), a_lo=lo(P), b_lo=lo(v),
-           d_lo=0 if out32 else lo(out))
+           d_lo=0 if out32 else lo(out), a_major=1 if a_trans else 0)
     return out
 
 

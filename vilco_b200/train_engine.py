@@ -393,14 +393,16 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
         del dP
         dBD = torch.zeros(B, H, T, 2 * T, device=dS.device, dtype=f32)
         L.check(L.lib().vilco_relshift_bwd(_p(dS), _p(dBD), _i64(B * H), T, L.stream_ptr()), "vilco_relshift_bwd")
-        dS16, dST16 = BW.to_planes(dS, want=True, want_t=True, batch_dims=2)
+        dS16, _ = BW.to_planes(dS, batch_dims=2)
+        del dS
         tp.acc(qw, ops.attn_pv(dS16, k16, H, T, out32=True))
-        tp.acc(k, ops.attn_pv(dST16, qw16, H, T, out32=True))
-        _, PT16 = BW.to_planes(Pd32, want=False, want_t=True, batch_dims=2)
-        tp.acc(v, ops.attn_pv(PT16, dvec16, H, T, out32=True))
-        dBD16, dBDT16 = BW.to_planes(dBD, want=True, want_t=True, batch_dims=2)
+        tp.acc(k, ops.attn_pv(dS16, qw16, H, T, out32=True, a_trans=True))        # dS^T qw: dS read as MN-major A
+        del dS16
+        tp.acc(v, ops.attn_pv(P16, dvec16, H, T, out32=True, a_trans=True))       # P^T dvec
+        dBD16, _ = BW.to_planes(dBD, batch_dims=2)
+        del dBD
         tp.acc(qr, ops.attn_pv(dBD16, kr16, H, 2 * T, out32=True))
-        tp.acc(krel, ops.attn_pv(dBDT16, qr16, H, T, out32=True))
+        tp.acc(krel, ops.attn_pv(dBD16, qr16, H, T, out32=True, a_trans=True))    # dBD^T qr -> (B, 2T, C)
         if krel1 is not None:                                  # krel is the batch broadcast of krel1
             g1 = krel.g[0]
             for b in range(1, B):
