@@ -223,9 +223,10 @@ int vilco_dwconv_bwd(const float* x, const float* mask, const float* w, const fl
 /* fp32 depthwise k=3 conv * out-mask (the LayerNorm input of vilco_dwconv_ln, recomputed in the backward pass) */
 int vilco_dwconv_fwd32(const float* x, const float* mask, const float* w, float* out, int B, int T, int C, int stride,
                        void* stream);
-/* fp32 elementwise helper of the training path: op 0: x*rowmul[r]*colmul[c], 1: gelu(x), 2: relu(x), 3: x*(y>0) */
-int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const float* colmul, float* out, int64_t rows,
-             int C, void* stream);
+/* fp32 elementwise helper of the training path: op 0: x*rowmul[r]*colmul[c], 1: gelu(x), 2: relu(x), 3: x*(y>0).
+ * out (fp32) and / or out16 (bf16 hi plane, lo plane at out16 + out16_lo when out16_lo != 0) receive the result. */
+int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const float* colmul, float* out, void* out16,
+             int64_t out16_lo, int64_t rows, int C, void* stream);
 int vilco_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
 /* MaxPool1d(3,2,1) backward (TransformerBlock.pool_skip): dx must be pre-zeroed; gradient goes to the first maximum. */
 int vilco_maxpool3s2_bwd(const float* x, const float* dy, float* dx, int B, int T, int C, void* stream);
@@ -238,8 +239,8 @@ int vilco_channel_attention_bwd(const float* dy, const void* qkv, int64_t qkv_lo
                                 float* dqkv, int B, int T, int C, int H, void* stream);
 
 /* Inverted dropout (nn.Dropout in training mode — blocks.py:222-223, 536-538): out = keep(seed, i) ? x / (1 - p) : 0 with a
- * counter-based generator; calling it on the gradient with the same seed is the backward pass. */
-int vilco_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream);
+ * counter-based generator; calling it on the gradient with the same seed is the backward pass.  Outputs as in vilco_ew. */
+int vilco_dropout(const float* x, float* out, void* out16, int64_t out16_lo, int64_t n, float p, uint64_t seed, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Optimizer step over flat fp32 buffers (all parameters / gradients / AdamW moments of a parameter group contiguous):

@@ -269,9 +269,11 @@ __global__ void relshift_bwd_kernel(const float* __restrict__ dS, float* __restr
   }
 }
 
-// generic fp32 elementwise helper: op 0: x*rowmul*colmul, 1: gelu(x), 2: relu(x), 3: x * (y > 0)  (ReLU backward)
+// generic fp32 elementwise helper: op 0: x*rowmul*colmul, 1: gelu(x), 2: relu(x), 3: x * (y > 0)  (ReLU backward);
+// optionally also writes the result as bf16 (hi, lo) operand planes for the next GEMM
 __global__ void ew_kernel(int op, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ rowmul,
-                          const float* __restrict__ colmul, float* __restrict__ out, long long rows, int C) {
+                          const float* __restrict__ colmul, float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
+                          long long out16_lo, long long rows, int C) {
   const long long n = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = x[i];
@@ -281,7 +283,8 @@ __global__ void ew_kernel(int op, const float* __restrict__ x, const float* __re
     } else if (op == 1) v = gelu_erf(v);
     else if (op == 2) v = fmaxf(v, 0.f);
     else if (op == 3) v = y[i] > 0.f ? v : 0.f;
-    out[i] = v;
+    if (out) out[i] = v;
+    if (out16) st_planes(out16 + i, out16_lo, v);
   }
 }
 
@@ -293,10 +296,13 @@ __device__ __forceinline__ unsigned int mix64(unsigned long long z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return static_cast<unsigned int>((z ^ (z >> 31)) >> 32);
 }
-__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, unsigned int thr, float inv_keep,
-                               unsigned long long seed) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = mix64(seed * 0xD1342543DE82EF95ull + static_cast<unsigned long long>(i)) >= thr ? x[i] * inv_keep : 0.f;
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
+                               long long out16_lo, long long n, unsigned int thr, float inv_keep, unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = mix64(seed * 0xD1342543DE82EF95ull + static_cast<unsigned long long>(i)) >= thr ? x[i] * inv_keep : 0.f;
+    if (out) out[i] = v;
+    if (out16) st_planes(out16 + i, out16_lo, v);
+  }
 }
 
 // dx = dy * gelu'(x)
@@ -451,18 +457,20 @@ extern "C" int vilco_relshift_bwd(const float* dS, float* dBD, int64_t Z, int T,
   return VILCO_OK;
 }
 
-extern "C" int vilco_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed, void* stream) {
-  VILCO_CHECK_ARG(x && out && n > 0 && p >= 0.f && p < 1.f, "vilco_dropout: bad arguments");
+extern "C" int vilco_dropout(const float* x, float* out, void* out16, int64_t out16_lo, int64_t n, float p, uint64_t seed, void* stream) {
+  VILCO_CHECK_ARG(x && (out || out16) && n > 0 && p >= 0.f && p < 1.f, "vilco_dropout: bad arguments");
   const unsigned int thr = static_cast<unsigned int>(static_cast<double>(p) * 4294967296.0);
-  dropout_kernel<<<bgrid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, n, thr, 1.0f / (1.0f - p), seed);
+  dropout_kernel<<<bgrid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, static_cast<__nv_bfloat16*>(out16), out16_lo, n,
+                                                                             thr, 1.0f / (1.0f - p), seed);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
 
-int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const float* colmul, float* out,
-                        int64_t rows, int C, void* stream) {
-  VILCO_CHECK_ARG(x && out && rows > 0 && C > 0 && op >= 0 && op <= 3 && (op != 3 || y), "vilco_ew: bad arguments");
-  ew_kernel<<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(op, x, y, rowmul, colmul, out, rows, C);
+int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const float* colmul, float* out, void* out16,
+             int64_t out16_lo, int64_t rows, int C, void* stream) {
+  VILCO_CHECK_ARG(x && (out || out16) && rows > 0 && C > 0 && op >= 0 && op <= 3 && (op != 3 || y), "vilco_ew: bad arguments");
+  ew_kernel<<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(op, x, y, rowmul, colmul, out,
+                                                                               static_cast<__nv_bfloat16*>(out16), out16_lo, rows, C);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

@@ -32,23 +32,43 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm
   *coef = max_norm > 0.f ? fminf(1.f, max_norm / (nrm + 1e-6f)) : 1.f;
 }
 
-__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+__device__ __forceinline__ float adamw_one(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps,
+                                           float wd, float step, float bc2_sqrt) {
+  float pi = p * (1.f - lr * wd);
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  pi -= step * m / (sqrtf(v) / bc2_sqrt + eps);
+  p = pi;
+  return pi;
+}
+
+// n is a multiple of 4 and all buffers are 16-byte aligned (FlatAdamW pads every tensor to 8 elements)
+__global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                    float4* __restrict__ v, long long n4, float lr, float b1, float b2, float eps,
                                                     float wd, float bc1, float bc2_sqrt, const float* __restrict__ gscale,
                                                     __nv_bfloat16* __restrict__ planes, long long planes_lo) {
   const float gs = gscale ? *gscale : 1.f;
   const float step = lr / bc1;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * gs;
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    pi -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pi = p[i], mi = m[i], vi = v[i];
+    const float4 gi = g[i];
+    adamw_one(pi.x, gi.x * gs, mi.x, vi.x, lr, b1, b2, eps, wd, step, bc2_sqrt);
+    adamw_one(pi.y, gi.y * gs, mi.y, vi.y, lr, b1, b2, eps, wd, step, bc2_sqrt);
+    adamw_one(pi.z, gi.z * gs, mi.z, vi.z, lr, b1, b2, eps, wd, step, bc2_sqrt);
+    adamw_one(pi.w, gi.w * gs, mi.w, vi.w, lr, b1, b2, eps, wd, step, bc2_sqrt);
     p[i] = pi; m[i] = mi; v[i] = vi;
     if (planes) {
-      const __nv_bfloat16 hi = __float2bfloat16(pi);
-      planes[i] = hi;
-      if (planes_lo) planes[planes_lo + i] = __float2bfloat16(pi - __bfloat162float(hi));
+      const __nv_bfloat16 h0 = __float2bfloat16(pi.x), h1 = __float2bfloat16(pi.y), h2 = __float2bfloat16(pi.z),
+                          h3 = __float2bfloat16(pi.w);
+      uint2 hi;
+      hi.x = pack_bf16x2(h0, h1); hi.y = pack_bf16x2(h2, h3);
+      *reinterpret_cast<uint2*>(planes + 4 * i) = hi;
+      if (planes_lo) {
+        uint2 lo;
+        lo.x = pack_bf16x2(__float2bfloat16(pi.x - __bfloat162float(h0)), __float2bfloat16(pi.y - __bfloat162float(h1)));
+        lo.y = pack_bf16x2(__float2bfloat16(pi.z - __bfloat162float(h2)), __float2bfloat16(pi.w - __bfloat162float(h3)));
+        *reinterpret_cast<uint2*>(planes + planes_lo + 4 * i) = lo;
+      }
     }
   }
 }
@@ -80,10 +100,14 @@ extern "C" int vilco_grad_clip_coef(const float* g, int64_t n, float max_norm, f
 extern "C" int vilco_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                            float weight_decay, int step, const float* grad_scale, void* planes, int64_t planes_lo, void* stream) {
   VILCO_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "vilco_adamw: bad arguments");
+  VILCO_CHECK_ARG(n % 4 == 0 && reinterpret_cast<uintptr_t>(p) % 16 == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(m) % 16 == 0 && reinterpret_cast<uintptr_t>(v) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(planes) % 8 == 0 && planes_lo % 4 == 0,
+                  "vilco_adamw: buffers must be 16-byte aligned and n a multiple of 4");
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
-  adamw_kernel<<<ogrid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, static_cast<__nv_bfloat16*>(planes), planes_lo);
+  adamw_kernel<<<ogrid(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, static_cast<__nv_bfloat16*>(planes), planes_lo);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

@@ -243,10 +243,21 @@ def channel_attention(qkv, H, tlen=None, return_G=False):
     return (y, G) if return_G else y
 
 
-def ew(op, x, y=None, rowmul=None, colmul=None):
-    """fp32 elementwise helper (training path): op 0: x*rowmul*colmul, 1: gelu, 2: relu, 3: x*(y>0)."""
-    out = torch.empty_like(x)
+def ew(op, x, y=None, rowmul=None, colmul=None, out32=True, out16=False):
+    """fp32 elementwise helper (training path): op 0: x*rowmul*colmul, 1: gelu, 2: relu, 3: x*(y>0).
+    Returns the fp32 result, or (fp32 or None, operand planes) when out16 is set."""
+    out = torch.empty_like(x) if out32 else None
+    o16 = empty16(*x.shape, device=x.device) if out16 else None
     Cc = x.shape[-1]
-    L.check(L.lib().vilco_ew(op, _p(x), _p(y), _p(rowmul), _p(colmul), _p(out), _i64(x.numel() // Cc), Cc, L.stream_ptr()),
-            "vilco_ew")
-    return out
+    L.check(L.lib().vilco_ew(op, _p(x), _p(y), _p(rowmul), _p(colmul), _p(out), _p(o16), _i64(lo(o16) if out16 else 0),
+                             _i64(x.numel() // Cc), Cc, L.stream_ptr()), "vilco_ew")
+    return (out, o16) if out16 else out
+
+
+def dropout(x, p, seed, out32=True, out16=False, out=None):
+    """inverted dropout with the counter-based mask of call `seed` (fp32 and / or operand-plane output)."""
+    o32 = (torch.empty_like(x) if out is None else out) if out32 else None
+    o16 = empty16(*x.shape, device=x.device) if out16 else None
+    L.check(L.lib().vilco_dropout(_p(x), _p(o32), _p(o16), _i64(lo(o16) if out16 else 0), _i64(x.numel()), C.c_float(p),
+                                  C.c_uint64(seed), L.stream_ptr()), "vilco_dropout")
+    return (o32, o16) if out16 else o32

@@ -67,12 +67,16 @@ class Tape:
         self.nodes = []
 
     # ---- operators ----
-    def linear(self, x, wkey, bkey=None, rowmul=None, bias=None):
-        """y = (x w^T + b) * rowmul.  `bias` overrides W[bkey] (XLNet r_w / r_r)."""
+    def linear(self, x, wkey, bkey=None, rowmul=None, bias=None, out16=False):
+        """y = (x w^T + b) * rowmul.  `bias` overrides W[bkey] (XLNet r_w / r_r).  out16: the result only feeds tensor-core
+        kernels, so the GEMM epilogue writes the bf16 operand planes directly and no fp32 copy exists."""
         W = self.W
         x16 = self.planes(x)
         b = bias if bias is not None else (W[bkey] if bkey else None)
-        y = V(ops.linear(x16, W[wkey], f32, bias=b, rowmul=rowmul))
+        if out16:
+            y = V(p16=ops.linear(x16, W[wkey], bf16, bias=b, rowmul=rowmul))
+        else:
+            y = V(ops.linear(x16, W[wkey], f32, bias=b, rowmul=rowmul))
 
         def bwd():
             if y.g is None:
@@ -119,8 +123,8 @@ class Tape:
         self.nodes.append(bwd)
         return y
 
-    def gelu(self, x):
-        y = V(ops.ew(1, x.v))
+    def gelu(self, x, want16=True):
+        y = V(*ops.ew(1, x.v, out16=True)) if want16 else V(ops.ew(1, x.v))
         self.nodes.append(lambda: self.acc(x, BW.gelu_bwd(y.g, x.v)) if y.g is not None else None)
         return y
 
@@ -129,17 +133,18 @@ class Tape:
         self.nodes.append(lambda: self.acc(x, ops.ew(3, y.g, y=y.v)) if y.g is not None else None)
         return y
 
-    def ln(self, x, wkey, bkey, eps=1e-5, relu=False, pe=None, rowmul=None, zero_rows=None, keep_rows=None):
-        """channel LayerNorm (+ReLU, + pe*rowmul constant, rows flagged in zero_rows forced to 0)."""
+    def ln(self, x, wkey, bkey, eps=1e-5, relu=False, pe=None, rowmul=None, zero_rows=None, keep_rows=None, want16=True):
+        """channel LayerNorm (+ReLU, + pe*rowmul constant, rows flagged in zero_rows forced to 0).  want16: the kernel also
+        writes the operand planes the next GEMM reads."""
         W = self.W
-        y32, _ = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, out32=True, out16=False, zero_rows=zero_rows)
         if pe is not None:   # constant positional term, no gradient
-            y32, _ = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, pe=pe, rowmul=rowmul, out32=True, out16=False,
-                                   rows_per_batch=x.v.shape[1])
+            y32, y16 = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, pe=pe, rowmul=rowmul, out32=True, out16=want16,
+                                     rows_per_batch=x.v.shape[1])
             yr, _ = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, out32=True, out16=False)
         else:
+            y32, y16 = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, out32=True, out16=want16, zero_rows=zero_rows)
             yr = y32
-        y = V(y32)
+        y = V(y32, p16=y16)
 
         def bwd():
             if y.g is None:
@@ -210,21 +215,15 @@ class Tape:
         self.nodes.append(bwd)
         return out
 
-    def dropout(self, x, p=None):
+    def dropout(self, x, p=None, want16=True):
         """nn.Dropout(p) in training mode (identity when p == 0)."""
         p = self.p_drop if p is None else p
         if p <= 0.0:
             return x
         self.seed += 1
         seed = self.seed
-
-        def run(t):
-            out = torch.empty_like(t)
-            L.check(L.lib().vilco_dropout(_p(t), _p(out), _i64(t.numel()), CT.c_float(p), CT.c_uint64(seed), L.stream_ptr()),
-                    "vilco_dropout")
-            return out
-        y = V(run(x.v))
-        self.nodes.append(lambda: self.acc(x, run(y.g.contiguous())) if y.g is not None else None)
+        y = V(*ops.dropout(x.v, p, seed, out16=True)) if want16 else V(ops.dropout(x.v, p, seed))
+        self.nodes.append(lambda: self.acc(x, ops.dropout(y.g.contiguous(), p, seed)) if y.g is not None else None)
         return y
 
     def path_rows(self, B, rows_per_sample, device):
@@ -285,17 +284,17 @@ def transformer_block(tp, pre, x, mask, H, stride, cross=None, t_c_alpha=0.8, ad
     W = tp.W
     C = x.shape[-1]
     scale = 1.0 / math.sqrt(C // H)
-    ln1 = tp.ln(x, pre + "ln1.weight", pre + "ln1.bias")
+    ln1 = tp.ln(x, pre + "ln1.weight", pre + "ln1.bias", want16=(stride == 1))
     qc, kc, vc = tp.dwconv_ln3(ln1, pre + "attn.", mask, stride)
     om = mask[:, ::stride].contiguous() if stride > 1 else mask
     omf = om.reshape(-1)
-    q = tp.linear(qc, pre + "attn.query.weight", pre + "attn.query.bias")
-    k = tp.linear(kc, pre + "attn.key.weight", pre + "attn.key.bias")
-    v = tp.linear(vc, pre + "attn.value.weight", pre + "attn.value.bias", rowmul=omf)
+    q = tp.linear(qc, pre + "attn.query.weight", pre + "attn.query.bias", out16=True)
+    k = tp.linear(kc, pre + "attn.key.weight", pre + "attn.key.bias", out16=True)
+    v = tp.linear(vc, pre + "attn.value.weight", pre + "attn.value.bias", rowmul=omf, out16=True)
     o = tp.attention(q, k, v, om, H, scale)
     B, To = om.shape
     if tp.p_drop > 0:      # proj_drop sits between the projection and the mask (blocks.py:404-405)
-        proj = tp.rowscale(tp.dropout(tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias")), omf)
+        proj = tp.rowscale(tp.dropout(tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias"), want16=False), omf)
     else:
         proj = tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias", rowmul=omf)
     skip = x if stride == 1 else tp.maxpool(x)
@@ -308,25 +307,25 @@ def transformer_block(tp, pre, x, mask, H, stride, cross=None, t_c_alpha=0.8, ad
         text, tmask = cross
         hx = tp.ln(h, pre + "ln3.weight", pre + "ln3.bias")
         hy = tp.ln(text, pre + "ln3.weight", pre + "ln3.bias")
-        cq = tp.linear(hx, pre + "cross_attn.query.weight", pre + "cross_attn.query.bias")
-        ck = tp.linear(hy, pre + "cross_attn.key.weight", pre + "cross_attn.key.bias")
-        cv = tp.linear(hy, pre + "cross_attn.value.weight", pre + "cross_attn.value.bias", rowmul=tmask.reshape(-1))
+        cq = tp.linear(hx, pre + "cross_attn.query.weight", pre + "cross_attn.query.bias", out16=True)
+        ck = tp.linear(hy, pre + "cross_attn.key.weight", pre + "cross_attn.key.bias", out16=True)
+        cv = tp.linear(hy, pre + "cross_attn.value.weight", pre + "cross_attn.value.bias", rowmul=tmask.reshape(-1), out16=True)
         c = tp.attention(cq, ck, cv, tmask, H, scale)
         if tp.p_drop > 0:
-            cp = tp.rowscale(tp.dropout(tp.linear(c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias")), omf)
+            cp = tp.rowscale(tp.dropout(tp.linear(c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias"), want16=False), omf)
         else:
             cp = tp.linear(c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias", rowmul=omf)
         h = tp.resid_scale(h, omf, tp.rowscale(cp, tp.path_rows(B, To, omf.device)), sa)
     h2 = tp.ln(h, pre + "ln2.weight", pre + "ln2.bias")
-    m1 = tp.dropout(tp.gelu(tp.linear(h2, pre + "mlp.0.weight", pre + "mlp.0.bias")))
+    m1 = tp.dropout(tp.gelu(tp.linear(h2, pre + "mlp.0.weight", pre + "mlp.0.bias"), want16=tp.p_drop <= 0))
     if tp.p_drop > 0:
-        m2 = tp.rowscale(tp.dropout(tp.linear(m1, pre + "mlp.3.weight", pre + "mlp.3.bias")), omf)
+        m2 = tp.rowscale(tp.dropout(tp.linear(m1, pre + "mlp.3.weight", pre + "mlp.3.bias"), want16=False), omf)
     else:
         m2 = tp.linear(m1, pre + "mlp.3.weight", pre + "mlp.3.bias", rowmul=omf)
     out = tp.resid_scale(h, None, tp.rowscale(m2, tp.path_rows(B, To, omf.device)), sm)
     if stride == 1:
         cpre = pre + "channel_attn."
-        qkv = tp.linear(ln1, cpre + "attn.qkv.weight")
+        qkv = tp.linear(ln1, cpre + "attn.qkv.weight", out16=True)
         y = tp.channel_attention(qkv, H)
         T_ = ln1.shape[1]        # ChannelBlock: DropPath on both residual branches (blocks.py:448, 462-464)
         x1 = tp.mix(ln1, tp.rowscale(tp.linear(y, cpre + "attn.proj.weight", cpre + "attn.proj.bias"),
@@ -350,14 +349,14 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
     kq, kk, kv, ko, kr = (pre + "rel_attn." + n for n in "qkvor")
     rw, rr = pre + "rel_attn.r_w_bias", pre + "rel_attn.r_r_bias"
     x = tp.dropout(x, pd)
-    qw = tp.linear(x, kq, rw)
-    qr = tp.linear(x, kq, rr)
-    k = tp.linear(x, kk)
-    v = tp.linear(x, kv)
+    qw = tp.linear(x, kq, rw, out16=True)
+    qr = tp.linear(x, kq, rr, out16=True)
+    k = tp.linear(x, kk, out16=True)
+    v = tp.linear(x, kv, out16=True)
     pos16 = E.xlnet_pos_emb(T, C, x.v.device)                  # constant (2T, C)
     if pd > 0:     # the reference drops the (2T, B, C) expanded table, i.e. an independent mask per clip (:1228)
         posb = V(ops.merge16(pos16).unsqueeze(0).expand(B, 2 * T, C).contiguous(), const=True)
-        krel1, krel = None, tp.linear(tp.dropout(posb, pd), kr)
+        krel1, krel = None, tp.linear(tp.dropout(posb, pd), kr, out16=True)
     else:
         krel1 = tp.linear(V(p16=pos16, const=True), kr)       # (2T, C) fp32, depends on W_r only
         krel = V(krel1.v.unsqueeze(0).expand(B, 2 * T, C).contiguous())
@@ -370,12 +369,7 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
     if pd > 0:                                                 # dropout on the attention probabilities
         tp.seed += 1
         seed = tp.seed
-        Pd32 = torch.empty_like(P32)
-        L.check(L.lib().vilco_dropout(_p(P32), _p(Pd32), _i64(P32.numel()), CT.c_float(pd), CT.c_uint64(seed), L.stream_ptr()),
-                "vilco_dropout")
-        P16, _ = BW.to_planes(Pd32, want=True, want_t=False, batch_dims=2)
-    else:
-        Pd32 = P32
+        P16 = ops.dropout(P32, pd, seed, out32=False, out16=True)[1]
     vec = V(ops.attn_pv(P16, v16, H, T, out32=True))
 
     def bwd():
@@ -385,8 +379,7 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
         dvec16 = dvec16.reshape(dvec16.shape[0], B, T, C)
         dP = ops.attn_scores(dvec16, v16, H, 1.0)
         if seed is not None:
-            L.check(L.lib().vilco_dropout(_p(dP), _p(dP), _i64(dP.numel()), CT.c_float(pd), CT.c_uint64(seed), L.stream_ptr()),
-                    "vilco_dropout")
+            ops.dropout(dP, pd, seed, out=dP)
         dS = torch.empty_like(dP)
         L.check(L.lib().vilco_softmax_bwd(_p(P32), _p(dP), _p(dS), _i64(B * H * T), T, CT.c_float(scale), L.stream_ptr()),
                 "vilco_softmax_bwd")
@@ -409,11 +402,11 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
                 g1 = _add(g1.contiguous(), krel.g[b].contiguous())
             tp.acc(krel1, g1)
     tp.nodes.append(bwd)
-    a = tp.mix(tp.dropout(tp.linear(vec, ko), pd), x)
+    a = tp.mix(tp.dropout(tp.linear(vec, ko), pd, want16=False), x)
     h1 = tp.ln(a, pre + "rel_attn.layer_norm.weight", pre + "rel_attn.layer_norm.bias", eps)
-    f = tp.dropout(tp.gelu(tp.linear(h1, pre + "ff.layer_1.weight", pre + "ff.layer_1.bias")), pd)
-    f = tp.dropout(tp.linear(f, pre + "ff.layer_2.weight", pre + "ff.layer_2.bias"), pd)
-    return tp.dropout(tp.ln(tp.mix(f, h1), pre + "ff.layer_norm.weight", pre + "ff.layer_norm.bias", eps), pd)
+    f = tp.dropout(tp.gelu(tp.linear(h1, pre + "ff.layer_1.weight", pre + "ff.layer_1.bias"), want16=pd <= 0), pd)
+    f = tp.dropout(tp.linear(f, pre + "ff.layer_2.weight", pre + "ff.layer_2.bias"), pd, want16=False)
+    return tp.dropout(tp.ln(tp.mix(f, h1), pre + "ff.layer_norm.weight", pre + "ff.layer_norm.bias", eps, want16=False), pd, want16=False)
 
 
 def backbone(tp, cfg, x16, mask, text16, tmask, pe, pets_prefix="pets."):
@@ -428,7 +421,7 @@ def backbone(tp, cfg, x16, mask, text16, tmask, pe, pets_prefix="pets."):
         c = tp.conv3(x, pre + f"embd.{i}.conv.weight", None, rowmul=mask)
         last = i == n_embd - 1
         x = tp.ln(c, pre + f"embd_norm.{i}.weight", pre + f"embd_norm.{i}.bias", relu=True, pe=pe if last else None,
-                  rowmul=m if last else None)
+                  rowmul=m if last else None, want16=not last)
     cross, tin = None, None
     if cfg.use_cross_modal and text16 is not None:
         tm = tmask.reshape(-1)
@@ -460,7 +453,7 @@ def neck_heads(tp, cfg, feats, masks):
     dev = feats[0].v.device
     pyr = E.Pyramid([f.shape[1] for f in feats], dev)
     P = pyr.P
-    lv = [tp.ln(f, f"neck.fpn_norms.{l}.weight", f"neck.fpn_norms.{l}.bias") for l, f in enumerate(feats)]
+    lv = [tp.ln(f, f"neck.fpn_norms.{l}.weight", f"neck.fpn_norms.{l}.bias", want16=False) for l, f in enumerate(feats)]
     fpn = V(torch.zeros(B, P, C, device=dev, dtype=f32))
     pmask = torch.zeros(B, P, device=dev, dtype=f32)
     lvl_of_row = torch.full((P,), -1, device=dev, dtype=torch.long)
