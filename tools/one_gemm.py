@@ -1,4 +1,4 @@
-"""Single GEMM shape for ncu captures: python tools/one_gemm.py {qk|mlp1|lin32|conv3} [precision]"""
+"""Single GEMM shape for ncu captures: python tools/one_gemm.py {qk|mlp1|lin32|conv3|heads|wgrad} [precision]"""
 import os
 import sys
 
@@ -24,6 +24,16 @@ elif which == "lin32":
     resid = torch.randn(B, T, C, device=dev)
     rm = torch.ones(B * T, device=dev)
     fn = lambda: ops.linear(x, w, ops.f32, rowmul=rm, resid=resid, resid_masked=True)
+elif which == "heads":   # the dominant GEMM of bench.py's default step: head tower conv over the (32, 2056, 1024) pyramid
+    xh = ops.split16(torch.randn(32, 2056, C, device=dev))
+    w3 = ops.split16(torch.randn(3, C, C, device=dev) * 0.03)
+    rm = torch.ones(32, 2056, device=dev)
+    fn = lambda: ops.conv3(xh, w3, ops.f32, rowmul=rm)
+elif which == "wgrad":   # weight gradient dW = dZ^T X, both operands MN-major, split-K 2 (training step, 16 clips)
+    from vilco_b200 import backward as BW
+    dz = ops.split16(torch.randn(16 * T, C, device=dev))
+    xa = ops.split16(torch.randn(16 * T, C, device=dev))
+    fn = lambda: BW.wgrad(dz, xa, C, C, 16 * T)
 else:
     w3 = ops.split16(torch.randn(3, C, C, device=dev) * 0.03)
     rm = torch.ones(B, T, device=dev)

@@ -44,30 +44,32 @@ def colsum(x, y=None, rowmul=None, out=None):
     return out
 
 
-def wgrad(dz, x2, Mo, No, R, alpha=1.0):
+def wgrad(dz, x2, Mo, No, R, alpha=1.0, out=None):
     """dW (Mo, No) = dz^T @ x with dz (NP, R, Mo) and x2 (NP, R, No) both in their natural token-major layout: dz is read as
     an MN-major A operand and x as an MN-major B operand, so no transposed copy is made.  The reduction runs over all B*T
     rows while the output has few tiles, so K is split over batches (split-K) whenever the plain launch would leave most
-    of the 148 SMs idle; partials are summed by vilco_colsum."""
+    of the 148 SMs idle; partials are summed by vilco_colsum.  out: fp32 (Mo, No) buffer to ACCUMULATE into (the
+    parameter's .grad view)."""
     tiles = ((Mo + 127) // 128) * ((No + 127) // 128)
     S = min(16, 148 // tiles) if tiles < 100 else 1
     while S > 1 and (R % (8 * S) != 0 or R // S < 512):
         S -= 1
     if S <= 1:
-        dw = torch.empty(Mo, No, device=x2.device, dtype=f32)
+        dw = torch.empty(Mo, No, device=x2.device, dtype=f32) if out is None else out
         L.gemm(dz, x2, dw, M=Mo, N=No, K=R, a_rows=Mo, a_ld=Mo, a_major=1, b_ld=No, d_ld=No, b_major=1, alpha=alpha,
-               a_lo=lo(dz), b_lo=lo(x2))
+               a_lo=lo(dz), b_lo=lo(x2), resid=out)
         return dw
     chunk = R // S
     part = torch.empty(S, Mo, No, device=x2.device, dtype=f32)
     L.gemm(dz, x2, part, M=Mo, N=No, K=chunk, a_rows=Mo, a_ld=Mo, a_major=1, a_s=(chunk * Mo, 0), Z=(S, 1), b_ld=No,
            b_s=(chunk * No, 0), b_batched=True, b_major=1, d_ld=No, d_s=(Mo * No, 0), alpha=alpha, a_lo=lo(dz), b_lo=lo(x2))
-    return colsum(part.reshape(S, Mo * No)).reshape(Mo, No)
+    return colsum(part.reshape(S, Mo * No), out=None if out is None else out.reshape(-1)).reshape(Mo, No)
 
 
-def linear_bwd(dy, x16, w16, rowmul=None, alpha=1.0, need_dx=True, need_dw=True, need_db=True):
+def linear_bwd(dy, x16, w16, rowmul=None, alpha=1.0, need_dx=True, need_dw=True, need_db=True, dw_out=None, db_out=None):
     """forward: y = (alpha * x w^T + bias) * rowmul[:, None]   (ops.linear without act / colscale / resid).
-    dy (..., N) fp32, x16 (NP, ..., K), w16 (NP, N, K) -> (dx (..., K) fp32, dw (N, K) fp32, db (N,) fp32)."""
+    dy (..., N) fp32, x16 (NP, ..., K), w16 (NP, N, K) -> (dx (..., K) fp32, dw (N, K) fp32, db (N,) fp32).
+    dw_out / db_out: fp32 buffers the parameter gradients are accumulated into instead of fresh tensors."""
     N, K = w16.shape[1], w16.shape[2]
     dy2 = dy.reshape(-1, N)
     R = dy2.shape[0]
@@ -77,9 +79,9 @@ def linear_bwd(dy, x16, w16, rowmul=None, alpha=1.0, need_dx=True, need_dw=True,
         dx = torch.empty(*dy.shape[:-1], K, device=dy.device, dtype=f32)
         L.gemm(dz, w16, dx, M=R, N=K, K=N, a_rows=R, a_ld=N, b_ld=K, d_ld=K, b_major=1, alpha=alpha, a_lo=lo(dz), b_lo=lo(w16))
     if need_dw:
-        dw = wgrad(dz, x16.reshape(x16.shape[0], -1, K), N, K, R, alpha)
+        dw = wgrad(dz, x16.reshape(x16.shape[0], -1, K), N, K, R, alpha, out=dw_out)
     if need_db:
-        db = colsum(dy2, rowmul=rowmul)
+        db = colsum(dy2, rowmul=rowmul, out=db_out)
     return dx, dw, db
 
 
@@ -115,14 +117,14 @@ def conv3_bwd(dy, x16, w3, w3_flip, rowmul=None, need_dx=True):
     return dx, dw, db
 
 
-def layernorm_bwd(dy, x, w, eps=1e-5, add=None, y_relu=None, need_dw=True):
+def layernorm_bwd(dy, x, w, eps=1e-5, add=None, y_relu=None, need_dw=True, dw_out=None, db_out=None):
     """forward: y = act(LN(x [+ add]) * w + b)  (ops.layernorm; y_relu = fp32 forward output when relu=True).
     Returns (dx (also the gradient of `add`), dw, db)."""
     Cc = x.shape[-1]
     rows = x.numel() // Cc
     dx = torch.empty_like(x)
-    dw = torch.zeros(Cc, device=x.device, dtype=f32) if need_dw else None
-    db = torch.zeros(Cc, device=x.device, dtype=f32) if need_dw else None
+    dw = (torch.zeros(Cc, device=x.device, dtype=f32) if dw_out is None else dw_out) if need_dw else None
+    db = (torch.zeros(Cc, device=x.device, dtype=f32) if db_out is None else db_out) if need_dw else None
     L.check(L.lib().vilco_layernorm_bwd(_p(x), _p(add), _p(w), _p(dy.contiguous()), _p(y_relu), C.c_float(eps), _p(dx), _p(dw),
                                         _p(db), rows, Cc, L.stream_ptr()), "vilco_layernorm_bwd")
     return dx, dw, db

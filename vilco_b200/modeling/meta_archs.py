@@ -519,6 +519,26 @@ class PtTransformer(nn.Module):
             return video_list, points, msk_l, cls_l, off_l
         return results
 
+    def _grad_sinks(self):
+        """key -> fp32 view of the parameter's existing .grad in the kernels' packed layout, for the parameters whose
+        packed layout equals the parameter layout (vectors, 1x1 convs, nn.Linear, XLNet o).  With a trainer the .grad
+        tensors are persistent views of one flat buffer, so the table is rebuilt only when a .grad pointer changes."""
+        names, plist, _ = self._param_table()
+        sig = tuple(p.grad.data_ptr() if (p.grad is not None and p.requires_grad) else 0 for p in plist)
+        if getattr(self, "_sinks_sig", None) != sig:
+            sinks = {}
+            for k, p in zip(names, plist):
+                if p.grad is None or not p.requires_grad or not p.grad.is_contiguous() or p.grad.dtype != torch.float32 \
+                        or ".adapters." in k:
+                    continue
+                kind = E._pack_kind(k, p)
+                if kind == "vec" and p.dim() != 2:
+                    sinks[k] = p.grad.view(-1)
+                elif kind == "gemm":
+                    sinks[k] = p.grad.view(p.shape[0], -1)
+            self._sinks, self._sinks_sig = sinks, sig
+        return self._sinks
+
     # ---- training step: taped forward on the CUDA kernels + hand-written backward -------------------------------
     def _train_forward(self, video_list, task_id=-1, prev_out_cls_logits=None):
         """forward(is_training=True) with gradients: returns the reference's loss dict; `final_loss.backward()` runs the
@@ -541,11 +561,12 @@ class PtTransformer(nn.Module):
         # dropout / stochastic depth follow nn.Module.training exactly like the reference's nn.Dropout / AffineDropPath /
         # XLNet dropout (xlnet_config_*.json: 0.1); model.eval() + is_training=True gives the deterministic losses
         self._train_calls = getattr(self, "_train_calls", 0) + 1
+        sinks = self._grad_sinks()
         if self.training:
             tp = TE.Tape(W, dropout=self.train_dropout, droppath=self.train_droppath, xl_dropout=0.1 if self.use_xl else 0.0,
-                         seed=(int(torch.initial_seed()) & 0xFFFFF) * 4096 + self._train_calls)
+                         seed=(int(torch.initial_seed()) & 0xFFFFF) * 4096 + self._train_calls, sinks=sinks)
         else:
-            tp = TE.Tape(W)
+            tp = TE.Tape(W, sinks=sinks)
         with torch.no_grad():
             x16 = ops.pack_feats(batched)
             t16 = ops.pack_feats(text.detach()) if text is not None else None

@@ -35,10 +35,13 @@ def _add(a, b):
 
 
 class Tape:
-    def __init__(self, W, dropout=0.0, droppath=0.0, xl_dropout=0.0, seed=0):
+    def __init__(self, W, dropout=0.0, droppath=0.0, xl_dropout=0.0, seed=0, sinks=None):
         """dropout / droppath > 0 only when the module is in training mode (nn.Dropout / AffineDropPath semantics)."""
         self.W = W
         self.G = {}       # packed-layout parameter gradients
+        # key -> fp32 buffer in the packed layout that IS the parameter's .grad (zeroed by the trainer): kernels accumulate
+        # straight into it, no temporary and no add per parameter
+        self.sinks = sinks or {}
         self.nodes = []
         self.p_drop, self.p_path, self.p_xl = float(dropout), float(droppath), float(xl_dropout)
         self.seed = int(seed) << 20
@@ -81,10 +84,13 @@ class Tape:
         def bwd():
             if y.g is None:
                 return
-            dx, dw, db = BW.linear_bwd(y.g, x16, W[wkey], rowmul=rowmul, need_dx=not x.const, need_db=b is not None)
+            sw, sb = self.sinks.get(wkey), self.sinks.get(bkey) if bkey else None
+            dx, dw, db = BW.linear_bwd(y.g, x16, W[wkey], rowmul=rowmul, need_dx=not x.const, need_db=b is not None,
+                                       dw_out=sw, db_out=sb)
             self.acc(x, dx)
-            self.accp(wkey, dw)
-            if bkey:
+            if sw is None:
+                self.accp(wkey, dw)
+            if bkey and sb is None:
                 self.accp(bkey, db)
         self.nodes.append(bwd)
         return y
@@ -150,10 +156,14 @@ class Tape:
             if y.g is None:
                 return
             g = y.g if keep_rows is None else ops.ew(0, y.g, rowmul=keep_rows)
-            dx, dw, db = BW.layernorm_bwd(g, x.v, W[wkey], eps, y_relu=yr if relu else None)
+            sw, sb = self.sinks.get(wkey), self.sinks.get(bkey)
+            if (sw is None) != (sb is None):
+                sw = sb = None
+            dx, dw, db = BW.layernorm_bwd(g, x.v, W[wkey], eps, y_relu=yr if relu else None, dw_out=sw, db_out=sb)
             self.acc(x, dx)
-            self.accp(wkey, dw)
-            self.accp(bkey, db)
+            if sw is None:
+                self.accp(wkey, dw)
+                self.accp(bkey, db)
         self.nodes.append(bwd)
         return y
 
@@ -200,7 +210,11 @@ class Tape:
             self.acc(resid, out.g if rowmul is None else ops.ew(0, out.g, rowmul=rowmul))
             self.acc(y, out.g if s is None else ops.ew(0, out.g, colmul=s))
             if s is not None:
-                self.accp(skey, BW.colsum(out.g, y=y.v))
+                sk = self.sinks.get(skey)
+                if sk is None:
+                    self.accp(skey, BW.colsum(out.g, y=y.v))
+                else:
+                    BW.colsum(out.g, y=y.v, out=sk)
         self.nodes.append(bwd)
         return out
 
