@@ -8,7 +8,8 @@ from collections import defaultdict
 path = sys.argv[1]
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 rows = []
-with open(path) as f:
+import gzip
+with (gzip.open(path, "rt") if path.endswith(".gz") else open(path)) as f:
     lines = [l for l in f if not l.startswith("==")]
 rd = csv.DictReader(lines)
 for r in rd:
