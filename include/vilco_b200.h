@@ -206,8 +206,9 @@ int vilco_attention(const void* q, int64_t q_lo, const void* k, const void* v, i
  * (either output may be NULL). */
 int vilco_to_planes(const float* x, const float* rowmul, const float* colmul, void* y, int64_t y_lo, void* yT, int64_t yT_lo,
                     int R, int C, int ldT, int Z, void* stream);   /* Z independent (R,C) matrices */
-/* XLNet rel-shift backward: dBD[z,i,T+j-i] = dS[z,i,j] (dBD (Z,T,2T) pre-zeroed) — modeling_xlnet_x.py:256-268 */
-int vilco_relshift_bwd(const float* dS, float* dBD, int64_t Z, int T, void* stream);
+/* XLNet rel-shift backward (modeling_xlnet_x.py:256-268): dBD[z,i,p] = dS[z,i,p-T+i] inside the band, 0 elsewhere; every
+ * element of the (Z,T,2T) output is written, as fp32 (dBD) and / or as bf16 operand planes (dBD16, lo plane at + dbd_lo). */
+int vilco_relshift_bwd(const float* dS, float* dBD, void* dBD16, int64_t dbd_lo, int64_t Z, int T, void* stream);
 /* y16[b,t,:] = x16[b,t+shift,:] (zero outside the clip) on bf16 planes: shifted operands of the k=3 conv weight gradient */
 int vilco_shift_planes(const void* x, void* y, int64_t lo, int B, int T, int C, int shift, void* stream);
 /* out[c] += sum_r x[r,c] * (y ? y[r,c] : 1) * (rowmul ? rowmul[r] : 1)   (bias / scale / affine gradients; out pre-zeroed) */
@@ -230,8 +231,11 @@ int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const 
 int vilco_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
 /* MaxPool1d(3,2,1) backward (TransformerBlock.pool_skip): dx must be pre-zeroed; gradient goes to the first maximum. */
 int vilco_maxpool3s2_bwd(const float* x, const float* dy, float* dx, int B, int T, int C, void* stream);
-/* dS[r,j] = scale * P[r,j] * (dP[r,j] - sum_k dP[r,k] P[r,k])   (softmax backward over materialised fp32 rows) */
-int vilco_softmax_bwd(const float* P, const float* dP, float* dS, int64_t rows, int Tk, float scale, void* stream);
+/* dS[r,j] = scale * P[r,j] * (dP[r,j] - sum_k dP[r,k] P[r,k]).  P: fp32 rows (P32) or, when P32 is NULL, the bf16 hi/lo planes
+ * of the forward softmax (P16, lo plane at + p_lo, row stride p_ld).  dS: fp32 (row stride Tk) and / or operand planes
+ * (dS16, lo plane at + ds_lo, row stride ds_ld). */
+int vilco_softmax_bwd(const float* P32, const void* P16, int64_t p_lo, int64_t p_ld, const float* dP, float* dS, void* dS16,
+                      int64_t ds_lo, int64_t ds_ld, int64_t rows, int Tk, float scale, void* stream);
 
 /* ChannelAttention core backward (blocks.py:423-436): dy (B,T,C) fp32, qkv planes and G (B,H,64,64) from the forward call
  * -> dqkv (B,T,3C) fp32; dA_scratch is a (B,H,64,64) fp32 work buffer. */

@@ -172,34 +172,36 @@ def _dwconv_fwd32(x, mask, w3c, stride):
     return out
 
 
+def softmax_bwd(dP, scale, P32=None, P16=None, want32=False, want16=True):
+    """dS = scale * P * (dP - rowsum(dP * P)) over the last dim of (B,H,Tq,Tk).  P from fp32 rows or from the operand planes
+    of the forward softmax; returns (dS fp32 or None, dS operand planes (NP,B,H,Tq,ldp) or None)."""
+    B, H, Tq, Tk = dP.shape
+    ldp = (Tk + 7) // 8 * 8
+    dS = torch.empty_like(dP) if want32 else None
+    dS16 = ops.empty16(B, H, Tq, ldp, device=dP.device) if want16 else None
+    L.check(L.lib().vilco_softmax_bwd(_p(P32), _p(P16), _i64(lo(P16) if P16 is not None else 0),
+                                      _i64(P16.shape[-1] if P16 is not None else 0), _p(dP), _p(dS), _p(dS16),
+                                      _i64(lo(dS16) if want16 else 0), _i64(ldp), _i64(B * H * Tq), Tk, C.c_float(scale),
+                                      L.stream_ptr()), "vilco_softmax_bwd")
+    return dS, dS16
+
+
 def attention_bwd(dO, q16, k16, v16, kmask, H, scale):
     """forward: O = softmax_j(scale * q k^T | kmask) v per head (ops.attention / the materialised chain).
     dO (B,Tq,C) fp32, q16 (NP,B,Tq,C), k16 / v16 (NP,B,Tk,C) -> (dq, dk, dv) fp32 token-major.
-    The probabilities are recomputed (QK^T GEMM + softmax) instead of being stored by the fused forward kernel."""
+    The probabilities are recomputed (QK^T GEMM + softmax) instead of being stored by the fused forward kernel; P and dS
+    only ever exist as operand planes, and their transposes are never formed (MN-major A operands)."""
     _, B, Tq, Cc = q16.shape
     Tk = k16.shape[2]
     S = ops.attn_scores(q16, k16, H, scale)
-    P16, P32 = ops.softmax_rows(S, kmask, mode=0, want32=True)
+    P16 = ops.softmax_rows(S, kmask, mode=0)                        # (NP,B,H,Tq,ldp)
+    del S
     dO16, _ = to_planes(dO.reshape(-1, Cc))
     dO16 = dO16.reshape(dO16.shape[0], B, Tq, Cc)
-    dP = ops.attn_scores(dO16, v16, H, 1.0)                       # dP[b,h] = dO_h v_h^T
-    dS = torch.empty_like(dP)
-    L.check(L.lib().vilco_softmax_bwd(_p(P32), _p(dP), _p(dS), _i64(B * H * Tq), Tk, C.c_float(scale), L.stream_ptr()),
-            "vilco_softmax_bwd")
-    if Tk % 8 == 0:
-        dS16, _ = to_planes(dS, batch_dims=2)                      # (NP,B,H,Tq,Tk)
-        P16b, _ = to_planes(P32, batch_dims=2)
-        dq = ops.attn_pv(dS16, k16, H, Tk, out32=True)               # dQ_h = dS K_h
-        dk = ops.attn_pv(dS16, q16, H, Tq, out32=True, a_trans=True, M=Tk)   # dK_h = dS^T Q_h  (dS read as MN-major A)
-        dv = ops.attn_pv(P16b, dO16, H, Tq, out32=True, a_trans=True, M=Tk)  # dV_h = P^T dO_h
-        return dq, dk, dv
-    # Tk not a multiple of 8 (text keys): operand rows must keep 16-byte strides -> padded copy / explicit transposes
-    dS16, dST16 = to_planes(dS, want=True, want_t=True, batch_dims=2)   # (NP,B,H,Tq,Tk) and (NP,B,H,Tk,ldq)
-    pad = (Tk + 7) // 8 * 8
-    t2 = ops.zeros16(B, H, Tq, pad, device=dS.device)
-    t2[..., :Tk] = dS16
-    dq = ops.attn_pv(t2, k16, H, Tk, out32=True)
-    dk = ops.attn_pv(dST16, q16, H, Tq, out32=True)
-    _, PT16 = to_planes(P32, want=False, want_t=True, batch_dims=2)
-    dv = ops.attn_pv(PT16, dO16, H, Tq, out32=True)
+    dP = ops.attn_scores(dO16, v16, H, 1.0)                          # dP[b,h] = dO_h v_h^T
+    _, dS16 = softmax_bwd(dP, scale, P16=P16)
+    del dP
+    dq = ops.attn_pv(dS16, k16, H, Tk, out32=True)                   # dQ_h = dS K_h
+    dk = ops.attn_pv(dS16, q16, H, Tq, out32=True, a_trans=True, M=Tk)   # dK_h = dS^T Q_h
+    dv = ops.attn_pv(P16, dO16, H, Tq, out32=True, a_trans=True, M=Tk)   # dV_h = P^T dO_h
     return dq, dk, dv

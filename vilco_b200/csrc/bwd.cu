@@ -258,14 +258,19 @@ __global__ void dwconv_fwd32_kernel(const float* __restrict__ x, const float* __
   }
 }
 
-// XLNet rel-shift backward: dBD[z, i, T + j - i] = dS[z, i, j]
-__global__ void relshift_bwd_kernel(const float* __restrict__ dS, float* __restrict__ dBD, long long Z, int T) {
-  const long long total = Z * T * T;
+// XLNet rel-shift backward: dBD[z, i, p] = dS[z, i, p - T + i] where that index is inside [0, T), else 0 (gather form: every
+// output element is written once, fp32 and / or operand planes)
+__global__ void relshift_bwd_kernel(const float* __restrict__ dS, float* __restrict__ dBD, __nv_bfloat16* __restrict__ dBD16,
+                                    long long dbd_lo, long long Z, int T) {
+  const long long total = Z * T * 2LL * T;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int j = static_cast<int>(idx % T);
-    const long long zi = idx / T;
+    const int pp = static_cast<int>(idx % (2 * T));
+    const long long zi = idx / (2 * T);
     const int i = static_cast<int>(zi % T);
-    dBD[zi * (2LL * T) + (T + j - i)] = dS[idx];
+    const int j = pp - T + i;
+    const float v = (j >= 0 && j < T) ? dS[zi * T + j] : 0.f;
+    if (dBD) dBD[idx] = v;
+    if (dBD16) st_planes(dBD16 + idx, dbd_lo, v);
   }
 }
 
@@ -337,18 +342,33 @@ __global__ void maxpool3s2_bwd_kernel(const float* __restrict__ x, const float* 
   }
 }
 
-// masked softmax backward over rows: dS[r, j] = scale * P[r, j] * (dP[r, j] - sum_k dP[r, k] P[r, k])
-__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ P, const float* __restrict__ dP,
-                                                          float* __restrict__ dS, long long rows, int Tk, float scale) {
+// masked softmax backward over rows: dS[r, j] = scale * P[r, j] * (dP[r, j] - sum_k dP[r, k] P[r, k]).  P comes from the fp32
+// copy when given, else from the (hi, lo) operand planes the forward softmax wrote (row stride p_ld); dS goes out as fp32
+// and / or as operand planes (row stride ds_ld) for the dQ / dK GEMMs.
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ P32, const __nv_bfloat16* __restrict__ P16,
+                                                          long long p_lo, long long p_ld, const float* __restrict__ dP,
+                                                          float* __restrict__ dS, __nv_bfloat16* __restrict__ dS16, long long ds_lo,
+                                                          long long ds_ld, long long rows, int Tk, float scale) {
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const float* p = P + row * Tk;
   const float* d = dP + row * Tk;
+  const float* p32 = P32 ? P32 + row * Tk : nullptr;
+  const __nv_bfloat16* p16 = P16 ? P16 + row * p_ld : nullptr;
+  auto prob = [&](int j) -> float {
+    if (p32) return p32[j];
+    float v = __bfloat162float(p16[j]);
+    if (p_lo) v += __bfloat162float(p16[p_lo + j]);
+    return v;
+  };
   float s = 0.f;
-  for (int j = lane; j < Tk; j += 32) s += p[j] * d[j];
+  for (int j = lane; j < Tk; j += 32) s += prob(j) * d[j];
   s = warp_sum(s);
-  for (int j = lane; j < Tk; j += 32) dS[row * Tk + j] = scale * p[j] * (d[j] - s);
+  for (int j = lane; j < Tk; j += 32) {
+    const float v = scale * prob(j) * (d[j] - s);
+    if (dS) dS[row * Tk + j] = v;
+    if (dS16) st_planes(dS16 + row * ds_ld + j, ds_lo, v);
+  }
 }
 
 }  // namespace vilco
@@ -425,9 +445,11 @@ extern "C" int vilco_maxpool3s2_bwd(const float* x, const float* dy, float* dx, 
   return VILCO_OK;
 }
 
-extern "C" int vilco_softmax_bwd(const float* P, const float* dP, float* dS, int64_t rows, int Tk, float scale, void* stream) {
-  VILCO_CHECK_ARG(P && dP && dS && rows > 0 && Tk > 0, "vilco_softmax_bwd: bad arguments");
-  softmax_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(P, dP, dS, rows, Tk, scale);
+extern "C" int vilco_softmax_bwd(const float* P32, const void* P16, int64_t p_lo, int64_t p_ld, const float* dP, float* dS,
+                                 void* dS16, int64_t ds_lo, int64_t ds_ld, int64_t rows, int Tk, float scale, void* stream) {
+  VILCO_CHECK_ARG((P32 || P16) && dP && (dS || dS16) && rows > 0 && Tk > 0, "vilco_softmax_bwd: bad arguments");
+  softmax_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      P32, static_cast<const __nv_bfloat16*>(P16), p_lo, p_ld, dP, dS, static_cast<__nv_bfloat16*>(dS16), ds_lo, ds_ld, rows, Tk, scale);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -450,9 +472,10 @@ extern "C" int vilco_dwconv_fwd32(const float* x, const float* mask, const float
   return VILCO_OK;
 }
 
-extern "C" int vilco_relshift_bwd(const float* dS, float* dBD, int64_t Z, int T, void* stream) {
-  VILCO_CHECK_ARG(dS && dBD && Z > 0 && T > 0, "vilco_relshift_bwd: bad arguments");
-  relshift_bwd_kernel<<<bgrid(Z * T * T, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dS, dBD, Z, T);
+extern "C" int vilco_relshift_bwd(const float* dS, float* dBD, void* dBD16, int64_t dbd_lo, int64_t Z, int T, void* stream) {
+  VILCO_CHECK_ARG(dS && (dBD || dBD16) && Z > 0 && T > 0, "vilco_relshift_bwd: bad arguments");
+  relshift_bwd_kernel<<<bgrid(Z * T * 2LL * T, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dS, dBD, static_cast<__nv_bfloat16*>(dBD16), dbd_lo, Z, T);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

@@ -394,20 +394,16 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
         dP = ops.attn_scores(dvec16, v16, H, 1.0)
         if seed is not None:
             ops.dropout(dP, pd, seed, out=dP)
-        dS = torch.empty_like(dP)
-        L.check(L.lib().vilco_softmax_bwd(_p(P32), _p(dP), _p(dS), _i64(B * H * T), T, CT.c_float(scale), L.stream_ptr()),
-                "vilco_softmax_bwd")
+        dS, dS16 = BW.softmax_bwd(dP, scale, P32=P32, want32=True)
         del dP
-        dBD = torch.zeros(B, H, T, 2 * T, device=dS.device, dtype=f32)
-        L.check(L.lib().vilco_relshift_bwd(_p(dS), _p(dBD), _i64(B * H), T, L.stream_ptr()), "vilco_relshift_bwd")
-        dS16, _ = BW.to_planes(dS, batch_dims=2)
+        dBD16 = ops.empty16(B, H, T, 2 * T, device=dS.device)
+        L.check(L.lib().vilco_relshift_bwd(_p(dS), None, _p(dBD16), _i64(lo(dBD16)), _i64(B * H), T, L.stream_ptr()),
+                "vilco_relshift_bwd")
         del dS
         tp.acc(qw, ops.attn_pv(dS16, k16, H, T, out32=True))
         tp.acc(k, ops.attn_pv(dS16, qw16, H, T, out32=True, a_trans=True))        # dS^T qw: dS read as MN-major A
         del dS16
         tp.acc(v, ops.attn_pv(P16, dvec16, H, T, out32=True, a_trans=True))       # P^T dvec
-        dBD16, _ = BW.to_planes(dBD, batch_dims=2)
-        del dBD
         tp.acc(qr, ops.attn_pv(dBD16, kr16, H, 2 * T, out32=True))
         tp.acc(krel, ops.attn_pv(dBD16, qr16, H, T, out32=True, a_trans=True))    # dBD^T qr -> (B, 2T, C)
         if krel1 is not None:                                  # krel is the batch broadcast of krel1
