@@ -260,6 +260,18 @@ int vilco_grad_clip_coef(const float* g, int64_t n, float max_norm, float* scrat
 int vilco_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 float weight_decay, int step, const float* grad_scale, void* planes, int64_t planes_lo, void* stream);
 
+/* Residual branch of a TransformerBlock in training mode, fused (blocks.py:404-405, 567-585, drop_path :640-652):
+ *   out[r,c] = resid[r,c]*rm[r] + scale[c] * dropout_p(y[r,c] + bias[c]) * ymul[r]
+ * with y the raw projection GEMM output, ymul[r] = out-mask * stochastic-depth factor of the row's sample, dropout from the
+ * counter-based generator of vilco_dropout (p = 0: none).  rm / bias / scale / ymul may be NULL (= 1 / 0 / 1 / 1).
+ * The backward writes d resid = g*rm (optional), dy as bf16 operand planes (the dZ of the projection's gradient GEMMs) and
+ * accumulates dbias[c] += sum_r dy, dscale[c] += sum_r (d out * ymul * keep) * (y + bias)  (either may be NULL). */
+int vilco_resid_branch_fwd(const float* resid, const float* rm, const float* y, const float* bias, const float* scale,
+                           const float* ymul, float* out, int64_t rows, int C, float p, uint64_t seed, void* stream);
+int vilco_resid_branch_bwd(const float* g, const float* rm, const float* y, const float* bias, const float* scale,
+                           const float* ymul, float* dresid, void* dy16, int64_t dy_lo, float* dbias, float* dscale, int R, int C,
+                           float p, uint64_t seed, void* stream);
+
 /* Backward of vilco_mq_losses for final = cls + w_reg*reg + w_al*al (each divided by `norm`): gradients w.r.t. the logits,
  * the offsets and the three gaussian weights (the latter feed torch autograd of the target-assignment glue, which owns
  * mu / sigma).  smax = the (B,K) scratch filled by the forward call. */

@@ -243,3 +243,69 @@ def test_training_steps_flat_optimizer_equals_torch_optimizer():
         errs.append((float((d1 - d0).norm() / (d0.norm() + 1e-12)), k))
     errs.sort(reverse=True)
     assert errs[0][0] < 5e-2, errs[:8]
+
+
+def test_dropout_mask_statistics_and_fused_residual_branch():
+    """vilco_dropout: inverted dropout with a reproducible counter-based mask; vilco_resid_branch_fwd / _bwd (the fused
+    `resid*mask + scale * dropout(proj + b) * mask * drop_path` of a TransformerBlock in training mode) against the same
+    expression in torch using the mask that vilco_dropout produces for the same seed."""
+    import ctypes as C
+    from vilco_b200 import lib as L
+    from vilco_b200 import ops
+    torch.manual_seed(0)
+    R, Cc, p, seed = 777, 256, 0.1, 12345
+    ones = torch.ones(R, Cc, device="cuda")
+    keep = ops.dropout(ones, p, seed)                       # 0 or 1 / (1 - p)
+    vals = torch.unique(keep)
+    assert vals.numel() == 2 and vals[0] == 0 and abs(float(vals[1]) - 1 / (1 - p)) < 1e-6
+    frac = float((keep == 0).float().mean())
+    assert abs(frac - p) < 4 * math.sqrt(p * (1 - p) / (R * Cc))
+    assert torch.equal(keep, ops.dropout(ones, p, seed))    # same seed -> same mask (this is how the backward re-derives it)
+    assert not torch.equal(keep, ops.dropout(ones, p, seed + 1))
+    x = torch.randn(R, Cc, device="cuda")
+    y32, y16 = ops.dropout(x, p, seed, out16=True)
+    assert torch.equal(y32, x * keep) and rel_max(ops.merge16(y16), y32) < 2e-5
+
+    resid, y, g = (torch.randn(R, Cc, device="cuda") for _ in range(3))
+    rm = (torch.rand(R, device="cuda") > 0.2).float()
+    ymul = rm * torch.tensor([0.0, 1 / 0.9], device="cuda")[torch.randint(0, 2, (R,), device="cuda")]
+    bias, scale = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    out = torch.empty_like(y)
+    st = L.stream_ptr()
+    L.check(L.lib().vilco_resid_branch_fwd(ops._p(resid), ops._p(rm), ops._p(y), ops._p(bias), ops._p(scale), ops._p(ymul),
+                                           ops._p(out), ops._i64(R), Cc, C.c_float(p), C.c_uint64(seed), st))
+    ref = resid * rm[:, None] + scale * ((y + bias) * keep) * ymul[:, None]
+    assert rel_max(out, ref) < 1e-6
+    dres = torch.empty_like(g)
+    dz = ops.empty16(R, Cc, device="cuda")
+    db, ds = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+    L.check(L.lib().vilco_resid_branch_bwd(ops._p(g), ops._p(rm), ops._p(y), ops._p(bias), ops._p(scale), ops._p(ymul), ops._p(dres),
+                                           ops._p(dz), ops._i64(ops.lo(dz)), ops._p(db), ops._p(ds), R, Cc, C.c_float(p),
+                                           C.c_uint64(seed), st))
+    t = g * ymul[:, None] * keep
+    assert rel_max(dres, g * rm[:, None]) < 1e-6
+    assert rel_max(ops.merge16(dz), t * scale) < 2e-5
+    assert rel_max(db, (t * scale).sum(0)) < 1e-5
+    assert rel_max(ds, (t * (y + bias)).sum(0)) < 1e-5
+
+
+def test_training_mode_step_runs_with_dropout_and_changes_with_the_seed():
+    """model.train(): dropout / stochastic depth / XLNet dropout active.  Two calls draw different masks (different losses),
+    every parameter still receives a finite gradient."""
+    cfg = GG.small_cfg()
+    model, P = build_pair(cfg, 0)
+    videos = PR.synth_video_list(cfg, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    model.train()
+    vals = []
+    for _ in range(2):
+        model.zero_grad()
+        model.loss_normalizer = cfg.init_loss_norm
+        out = model(videos, is_training=True)
+        out["final_loss"].backward()
+        vals.append(float(out["final_loss"].detach()))
+    assert vals[0] != vals[1]
+    det = 0.4416                                           # the deterministic (eval-mode) loss of this batch
+    assert all(abs(v - det) < 0.5 * det for v in vals)
+    for k, prm in model.named_parameters():
+        if k in P:
+            assert prm.grad is not None and torch.isfinite(prm.grad).all(), k

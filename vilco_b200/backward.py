@@ -85,6 +85,18 @@ def linear_bwd(dy, x16, w16, rowmul=None, alpha=1.0, need_dx=True, need_dw=True,
     return dx, dw, db
 
 
+def linear_bwd16(dz, x16, w16, need_dx=True, dw_out=None):
+    """linear_bwd for a gradient that already exists as operand planes dz (NP, R, N) (bias gradient done by the producer)."""
+    N, K = w16.shape[1], w16.shape[2]
+    R = dz.shape[1]
+    dx = None
+    if need_dx:
+        dx = torch.empty(R, K, device=dz.device, dtype=f32)
+        L.gemm(dz, w16, dx, M=R, N=K, K=N, a_rows=R, a_ld=N, b_ld=K, d_ld=K, b_major=1, a_lo=lo(dz), b_lo=lo(w16))
+    dw = wgrad(dz, x16.reshape(x16.shape[0], -1, K), N, K, R, out=dw_out)
+    return dx, dw
+
+
 def shift_planes(x16, shift):
     """x16 (NP,B,T,C) -> same shape, rows shifted inside every clip: y[b,t] = x[b,t+shift] (zero outside)."""
     NP, B, T, Cc = x16.shape

@@ -310,6 +310,68 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
   }
 }
 
+// ---- residual branch of a TransformerBlock in training mode, fused (blocks.py:404-405, 567-585, 640-670):
+//   out[r,c] = resid[r,c] * rm[r] + scale[c] * (y[r,c] + bias[c]) * ymul[r] * keep(seed, r*C+c)
+// y = raw GEMM output of the projection, bias its bias (added here so that dropout sees proj(x)+b like the reference),
+// ymul[r] = out-mask[r] * stochastic-depth factor of the row's sample, keep = inverted dropout factor (1 when p == 0).
+__global__ void __launch_bounds__(256) resid_branch_fwd_kernel(const float* __restrict__ resid, const float* __restrict__ rm,
+                                                               const float* __restrict__ y, const float* __restrict__ bias,
+                                                               const float* __restrict__ scale, const float* __restrict__ ymul,
+                                                               float* __restrict__ out, long long rows, int C, unsigned int thr,
+                                                               float inv_keep, unsigned long long seed) {
+  const long long n = rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = static_cast<int>(i - r * C);
+    float v = y[i] + (bias ? bias[c] : 0.f);
+    if (thr) v = mix64(seed * 0xD1342543DE82EF95ull + static_cast<unsigned long long>(i)) >= thr ? v * inv_keep : 0.f;
+    v *= (ymul ? ymul[r] : 1.f) * (scale ? scale[c] : 1.f);
+    out[i] = resid[i] * (rm ? rm[r] : 1.f) + v;
+  }
+}
+
+// backward of the above for one (128-column, row-slab) block: d resid (optional), dy as operand planes (the dZ of the
+// projection's weight / data gradient GEMMs), and the column sums dbias[c] += sum_r dy, dscale[c] += sum_r t * (y + bias).
+__global__ void __launch_bounds__(256) resid_branch_bwd_kernel(const float* __restrict__ g, const float* __restrict__ rm,
+                                                               const float* __restrict__ y, const float* __restrict__ bias,
+                                                               const float* __restrict__ scale, const float* __restrict__ ymul,
+                                                               float* __restrict__ dresid, __nv_bfloat16* __restrict__ dy16,
+                                                               long long dy_lo, float* __restrict__ dbias, float* __restrict__ dscale,
+                                                               int R, int C, int rows_per_block, unsigned int thr, float inv_keep,
+                                                               unsigned long long seed) {
+  __shared__ float red[2][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(R, r0 + rows_per_block);
+  float sb = 0.f, ss = 0.f;
+  if (c < C) {
+    const float sc = scale ? scale[c] : 1.f;
+    const float bc = bias ? bias[c] : 0.f;
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const long long i = (long long)r * C + c;
+      const float gi = g[i];
+      if (dresid) dresid[i] = gi * (rm ? rm[r] : 1.f);
+      float t = gi * (ymul ? ymul[r] : 1.f);
+      if (thr) t = mix64(seed * 0xD1342543DE82EF95ull + static_cast<unsigned long long>(i)) >= thr ? t * inv_keep : 0.f;
+      const float dyi = t * sc;
+      st_planes(dy16 + i, dy_lo, dyi);
+      sb += dyi;
+      ss += t * (y[i] + bc);
+    }
+  }
+  red[0][ty][tx] = sb;
+  red[1][ty][tx] = ss;
+  __syncthreads();
+  if (ty < 2 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[ty][k][tx];
+    float* dst = ty == 0 ? dbias : dscale;
+    if (dst) atomicAdd(dst + c, t);
+  }
+}
+
 // dx = dy * gelu'(x)
 __global__ void gelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -494,6 +556,34 @@ int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const 
   VILCO_CHECK_ARG(x && (out || out16) && rows > 0 && C > 0 && op >= 0 && op <= 3 && (op != 3 || y), "vilco_ew: bad arguments");
   ew_kernel<<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(op, x, y, rowmul, colmul, out,
                                                                                static_cast<__nv_bfloat16*>(out16), out16_lo, rows, C);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_resid_branch_fwd(const float* resid, const float* rm, const float* y, const float* bias, const float* scale,
+                                      const float* ymul, float* out, int64_t rows, int C, float p, uint64_t seed, void* stream) {
+  VILCO_CHECK_ARG(resid && y && out && rows > 0 && C > 0 && p >= 0.f && p < 1.f, "vilco_resid_branch_fwd: bad arguments");
+  const unsigned int thr = static_cast<unsigned int>(static_cast<double>(p) * 4294967296.0);
+  resid_branch_fwd_kernel<<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(resid, rm, y, bias, scale, ymul, out, rows,
+                                                                                        C, thr, 1.0f / (1.0f - p), seed);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_resid_branch_bwd(const float* g, const float* rm, const float* y, const float* bias, const float* scale,
+                                      const float* ymul, float* dresid, void* dy16, int64_t dy_lo, float* dbias, float* dscale,
+                                      int R, int C, float p, uint64_t seed, void* stream) {
+  VILCO_CHECK_ARG(g && y && dy16 && R > 0 && C > 0 && p >= 0.f && p < 1.f, "vilco_resid_branch_bwd: bad arguments");
+  const unsigned int thr = static_cast<unsigned int>(static_cast<double>(p) * 4294967296.0);
+  const int cblocks = (C + 31) / 32;
+  int slabs = (148 * 8 + cblocks - 1) / cblocks;
+  int rpb = (R + slabs - 1) / slabs;
+  if (rpb < 32) rpb = 32;
+  rpb = (rpb + 7) / 8 * 8;
+  dim3 grid(cblocks, (R + rpb - 1) / rpb);
+  resid_branch_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, rm, y, bias, scale, ymul, dresid,
+                                                                             static_cast<__nv_bfloat16*>(dy16), dy_lo, dbias, dscale, R,
+                                                                             C, rpb, thr, 1.0f / (1.0f - p), seed);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

@@ -199,6 +199,56 @@ class Tape:
         self.nodes.append(bwd)
         return o
 
+    def proj_branch(self, resid, rm, x, wkey, bkey, skey, mask_rows, B, rows_per_sample, p=None, path=True):
+        """One fused residual branch: out = resid * rm + scale * dropout(x W^T + b) * mask * drop_path  (training semantics of
+        `pool_skip(x)*mask + drop_path_attn(attn(...))` / `out + drop_path_mlp(mlp(...)*mask)`, blocks.py:567-585).
+        Forward = GEMM + vilco_resid_branch_fwd; backward = vilco_resid_branch_bwd (d resid, dZ planes, d bias, d scale in one
+        pass) + the two gradient GEMMs."""
+        W = self.W
+        x16 = self.planes(x)
+        y = ops.linear(x16, W[wkey], f32)
+        b = W[bkey] if bkey else None
+        sc = W.get(skey) if skey else None
+        path = self.path_rows(B, rows_per_sample, y.device) if path else None
+        ymul = mask_rows if path is None else (mask_rows * path if mask_rows is not None else path)
+        p = self.p_drop if p is None else p
+        seed = 0
+        if p > 0:
+            self.seed += 1
+            seed = self.seed
+        N = y.shape[-1]
+        rows = y.numel() // N
+        outv = torch.empty_like(y)
+        L.check(L.lib().vilco_resid_branch_fwd(_p(resid.v), _p(rm), _p(y), _p(b), _p(sc), _p(ymul), _p(outv), _i64(rows), N,
+                                               CT.c_float(p), CT.c_uint64(seed), L.stream_ptr()), "vilco_resid_branch_fwd")
+        out = V(outv)
+
+        def bwd():
+            if out.g is None:
+                return
+            g = out.g.contiguous()
+            dz = ops.empty16(rows, N, device=g.device)
+            dres = torch.empty_like(g) if rm is not None else None
+            sb = self.sinks.get(bkey) if bkey else None
+            ss = self.sinks.get(skey) if sc is not None else None
+            db = sb if sb is not None else (torch.zeros(N, device=g.device, dtype=f32) if bkey else None)
+            ds = ss if ss is not None else (torch.zeros(N, device=g.device, dtype=f32) if sc is not None else None)
+            L.check(L.lib().vilco_resid_branch_bwd(_p(g), _p(rm), _p(y), _p(b), _p(sc), _p(ymul), _p(dres), _p(dz), _i64(lo(dz)),
+                                                   _p(db), _p(ds), rows, N, CT.c_float(p), CT.c_uint64(seed), L.stream_ptr()),
+                    "vilco_resid_branch_bwd")
+            self.acc(resid, dres if rm is not None else g)
+            if bkey and sb is None:
+                self.accp(bkey, db)
+            if sc is not None and ss is None:
+                self.accp(skey, ds)
+            sw = self.sinks.get(wkey)
+            dx, dw = BW.linear_bwd16(dz, x16, W[wkey], need_dx=not x.const, dw_out=sw)
+            self.acc(x, dx)
+            if sw is None:
+                self.accp(wkey, dw)
+        self.nodes.append(bwd)
+        return out
+
     def resid_scale(self, resid, rowmul, y, skey):
         """out = resid * rowmul[row] + scale[c] * y"""
         s = self.W.get(skey) if skey else None
@@ -307,16 +357,18 @@ def transformer_block(tp, pre, x, mask, H, stride, cross=None, t_c_alpha=0.8, ad
     v = tp.linear(vc, pre + "attn.value.weight", pre + "attn.value.bias", rowmul=omf, out16=True)
     o = tp.attention(q, k, v, om, H, scale)
     B, To = om.shape
-    if tp.p_drop > 0:      # proj_drop sits between the projection and the mask (blocks.py:404-405)
-        proj = tp.rowscale(tp.dropout(tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias"), want16=False), omf)
-    else:
-        proj = tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias", rowmul=omf)
     skip = x if stride == 1 else tp.maxpool(x)
     sa = pre + "drop_path_attn.scale" if (pre + "drop_path_attn.scale") in W else None
     sm = pre + "drop_path_mlp.scale" if (pre + "drop_path_mlp.scale") in W else None
-    if adapter_pre is not None:          # out = attn(ln1 x) + adapter(ln1 x), the adapter output is not masked
+    if adapter_pre is not None:          # out = attn(ln1 x) + adapter(ln1 x), the adapter output is not masked nor dropped
+        if tp.p_drop > 0:                # proj_drop sits between the projection and the mask (blocks.py:404-405)
+            proj = tp.rowscale(tp.dropout(tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias"), want16=False), omf)
+        else:
+            proj = tp.linear(o, pre + "attn.proj.weight", pre + "attn.proj.bias", rowmul=omf)
         proj = tp.mix(proj, adapter(tp, adapter_pre, ln1))
-    h = tp.resid_scale(skip, omf, tp.rowscale(proj, tp.path_rows(B, To, omf.device)), sa)
+        h = tp.resid_scale(skip, omf, tp.rowscale(proj, tp.path_rows(B, To, omf.device)), sa)
+    else:
+        h = tp.proj_branch(skip, omf, o, pre + "attn.proj.weight", pre + "attn.proj.bias", sa, omf, B, To)
     if cross is not None and (pre + "cross_attn.query.weight") in W:
         text, tmask = cross
         hx = tp.ln(h, pre + "ln3.weight", pre + "ln3.bias")
@@ -325,28 +377,19 @@ def transformer_block(tp, pre, x, mask, H, stride, cross=None, t_c_alpha=0.8, ad
         ck = tp.linear(hy, pre + "cross_attn.key.weight", pre + "cross_attn.key.bias", out16=True)
         cv = tp.linear(hy, pre + "cross_attn.value.weight", pre + "cross_attn.value.bias", rowmul=tmask.reshape(-1), out16=True)
         c = tp.attention(cq, ck, cv, tmask, H, scale)
-        if tp.p_drop > 0:
-            cp = tp.rowscale(tp.dropout(tp.linear(c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias"), want16=False), omf)
-        else:
-            cp = tp.linear(c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias", rowmul=omf)
-        h = tp.resid_scale(h, omf, tp.rowscale(cp, tp.path_rows(B, To, omf.device)), sa)
+        h = tp.proj_branch(h, omf, c, pre + "cross_attn.proj.weight", pre + "cross_attn.proj.bias", sa, omf, B, To)
     h2 = tp.ln(h, pre + "ln2.weight", pre + "ln2.bias")
     m1 = tp.dropout(tp.gelu(tp.linear(h2, pre + "mlp.0.weight", pre + "mlp.0.bias"), want16=tp.p_drop <= 0))
-    if tp.p_drop > 0:
-        m2 = tp.rowscale(tp.dropout(tp.linear(m1, pre + "mlp.3.weight", pre + "mlp.3.bias"), want16=False), omf)
-    else:
-        m2 = tp.linear(m1, pre + "mlp.3.weight", pre + "mlp.3.bias", rowmul=omf)
-    out = tp.resid_scale(h, None, tp.rowscale(m2, tp.path_rows(B, To, omf.device)), sm)
+    out = tp.proj_branch(h, None, m1, pre + "mlp.3.weight", pre + "mlp.3.bias", sm, omf, B, To)
     if stride == 1:
         cpre = pre + "channel_attn."
         qkv = tp.linear(ln1, cpre + "attn.qkv.weight", out16=True)
         y = tp.channel_attention(qkv, H)
         T_ = ln1.shape[1]        # ChannelBlock: DropPath on both residual branches (blocks.py:448, 462-464)
-        x1 = tp.mix(ln1, tp.rowscale(tp.linear(y, cpre + "attn.proj.weight", cpre + "attn.proj.bias"),
-                                     tp.path_rows(B, T_, omf.device)))
+        x1 = tp.proj_branch(ln1, None, y, cpre + "attn.proj.weight", cpre + "attn.proj.bias", None, None, B, T_, p=0.0)
         n2 = tp.ln(x1, cpre + "norm2.weight", cpre + "norm2.bias", 1e-5)
-        hh = tp.linear(tp.gelu(tp.linear(n2, cpre + "mlp.0.weight", cpre + "mlp.0.bias")), cpre + "mlp.2.weight", cpre + "mlp.2.bias")
-        out2 = tp.mix(x1, tp.rowscale(hh, tp.path_rows(B, T_, omf.device)))
+        out2 = tp.proj_branch(x1, None, tp.gelu(tp.linear(n2, cpre + "mlp.0.weight", cpre + "mlp.0.bias")),
+                              cpre + "mlp.2.weight", cpre + "mlp.2.bias", None, None, B, T_, p=0.0)
         out = tp.mix(out, out2, t_c_alpha, 1.0 - t_c_alpha)
     return out, om
 
@@ -412,11 +455,11 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
                 g1 = _add(g1.contiguous(), krel.g[b].contiguous())
             tp.acc(krel1, g1)
     tp.nodes.append(bwd)
-    a = tp.mix(tp.dropout(tp.linear(vec, ko), pd, want16=False), x)
+    a = tp.proj_branch(x, None, vec, ko, None, None, None, B, T, p=pd, path=False)          # dropout(attn_out) + h
     h1 = tp.ln(a, pre + "rel_attn.layer_norm.weight", pre + "rel_attn.layer_norm.bias", eps)
     f = tp.dropout(tp.gelu(tp.linear(h1, pre + "ff.layer_1.weight", pre + "ff.layer_1.bias"), want16=pd <= 0), pd)
-    f = tp.dropout(tp.linear(f, pre + "ff.layer_2.weight", pre + "ff.layer_2.bias"), pd, want16=False)
-    return tp.dropout(tp.ln(tp.mix(f, h1), pre + "ff.layer_norm.weight", pre + "ff.layer_norm.bias", eps, want16=False), pd, want16=False)
+    f = tp.proj_branch(h1, None, f, pre + "ff.layer_2.weight", pre + "ff.layer_2.bias", None, None, B, T, p=pd, path=False)
+    return tp.dropout(tp.ln(f, pre + "ff.layer_norm.weight", pre + "ff.layer_norm.bias", eps, want16=False), pd, want16=False)
 
 
 def backbone(tp, cfg, x16, mask, text16, tmask, pe, pets_prefix="pets."):
