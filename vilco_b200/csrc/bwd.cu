@@ -16,6 +16,45 @@ __device__ __forceinline__ void st_planes(__nv_bfloat16* p, long long lo, float 
   if (lo) p[lo] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// four consecutive values -> hi plane (and lo plane) with one 8-byte store each; p must be 8-byte aligned, lo % 4 == 0
+__device__ __forceinline__ void st_planes4(__nv_bfloat16* p, long long lo, float4 v) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                      h3 = __float2bfloat16_rn(v.w);
+  __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+  if (lo) {
+    uint2 w;
+    w.x = pack_bf16x2(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+    w.y = pack_bf16x2(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+    *reinterpret_cast<uint2*>(p + lo) = w;
+  }
+}
+__device__ __forceinline__ float4 ld_planes4(const __nv_bfloat16* p, long long lo) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  float4 v = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  if (lo) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p + lo);
+    v.x += bf16_lo(w.x); v.y += bf16_hi(w.x); v.z += bf16_lo(w.y); v.w += bf16_hi(w.y);
+  }
+  return v;
+}
+
+// plain (no transpose) fp32 -> planes, 4 elements per thread; C % 4 == 0
+__global__ void __launch_bounds__(256) to_planes_vec_kernel(const float* __restrict__ x, const float* __restrict__ rowmul,
+                                                            const float* __restrict__ colmul, __nv_bfloat16* __restrict__ y,
+                                                            long long y_lo, long long rows, int C) {
+  const int C4 = C >> 2;
+  const long long n4 = rows * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = ld4f(x + 4 * i);
+    if (rowmul) { const float m = rowmul[i / C4]; v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
+    if (colmul) { const float4 m = ld4f(colmul + 4 * (i % C4)); v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w; }
+    st_planes4(y + 4 * i, y_lo, v);
+  }
+}
+
 // y16[r, c] = x[r, c] * rowmul[r] * colmul[c]  as bf16 planes; optional transposed copy yT16[c, r]
 __global__ void to_planes_kernel(const float* __restrict__ x, const float* __restrict__ rowmul, const float* __restrict__ colmul,
                                  __nv_bfloat16* __restrict__ y, long long y_lo, __nv_bfloat16* __restrict__ yT, long long yT_lo,
@@ -260,36 +299,67 @@ __global__ void dwconv_fwd32_kernel(const float* __restrict__ x, const float* __
 
 // XLNet rel-shift backward: dBD[z, i, p] = dS[z, i, p - T + i] where that index is inside [0, T), else 0 (gather form: every
 // output element is written once, fp32 and / or operand planes)
-__global__ void relshift_bwd_kernel(const float* __restrict__ dS, float* __restrict__ dBD, __nv_bfloat16* __restrict__ dBD16,
-                                    long long dbd_lo, long long Z, int T) {
-  const long long total = Z * T * 2LL * T;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int pp = static_cast<int>(idx % (2 * T));
-    const long long zi = idx / (2 * T);
+__global__ void __launch_bounds__(256) relshift_bwd_kernel(const float* __restrict__ dS, float* __restrict__ dBD,
+                                                           __nv_bfloat16* __restrict__ dBD16, long long dbd_lo, long long Z, int T) {
+  const int W4 = (2 * T) >> 2;   // T % 2 == 0 is checked by the host
+  const long long total4 = Z * T * W4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
+    const int p0 = static_cast<int>(idx % W4) * 4;
+    const long long zi = idx / W4;
     const int i = static_cast<int>(zi % T);
-    const int j = pp - T + i;
-    const float v = (j >= 0 && j < T) ? dS[zi * T + j] : 0.f;
-    if (dBD) dBD[idx] = v;
-    if (dBD16) st_planes(dBD16 + idx, dbd_lo, v);
+    const float* src = dS + zi * T;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = p0 + k - T + i;
+      v[k] = (j >= 0 && j < T) ? src[j] : 0.f;
+    }
+    const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    if (dBD) st4f(dBD + 4 * idx, o);
+    if (dBD16) st_planes4(dBD16 + 4 * idx, dbd_lo, o);
   }
 }
 
 // generic fp32 elementwise helper: op 0: x*rowmul*colmul, 1: gelu(x), 2: relu(x), 3: x * (y > 0)  (ReLU backward);
 // optionally also writes the result as bf16 (hi, lo) operand planes for the next GEMM
-__global__ void ew_kernel(int op, const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ rowmul,
-                          const float* __restrict__ colmul, float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
-                          long long out16_lo, long long rows, int C) {
-  const long long n = rows * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float v = x[i];
-    if (op == 0) {
-      if (rowmul) v *= rowmul[i / C];
-      if (colmul) v *= colmul[i % C];
-    } else if (op == 1) v = gelu_erf(v);
-    else if (op == 2) v = fmaxf(v, 0.f);
-    else if (op == 3) v = y[i] > 0.f ? v : 0.f;
-    if (out) out[i] = v;
-    if (out16) st_planes(out16 + i, out16_lo, v);
+__device__ __forceinline__ float ew_apply(int op, float v, float y) {
+  if (op == 1) return gelu_erf(v);
+  if (op == 2) return fmaxf(v, 0.f);
+  if (op == 3) return y > 0.f ? v : 0.f;
+  return v;
+}
+template <bool VEC>
+__global__ void __launch_bounds__(256) ew_kernel(int op, const float* __restrict__ x, const float* __restrict__ y,
+                                                 const float* __restrict__ rowmul, const float* __restrict__ colmul,
+                                                 float* __restrict__ out, __nv_bfloat16* __restrict__ out16, long long out16_lo,
+                                                 long long rows, int C) {
+  if (VEC) {
+    const int C4 = C >> 2;
+    const long long n4 = rows * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      float4 v = ld4f(x + 4 * i);
+      float4 yy = make_float4(0, 0, 0, 0);
+      if (op == 3) yy = ld4f(y + 4 * i);
+      if (op == 0) {
+        if (rowmul) { const float m = rowmul[i / C4]; v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
+        if (colmul) { const float4 m = ld4f(colmul + 4 * (i % C4)); v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w; }
+      } else {
+        v.x = ew_apply(op, v.x, yy.x); v.y = ew_apply(op, v.y, yy.y); v.z = ew_apply(op, v.z, yy.z); v.w = ew_apply(op, v.w, yy.w);
+      }
+      if (out) st4f(out + 4 * i, v);
+      if (out16) st_planes4(out16 + 4 * i, out16_lo, v);
+    }
+  } else {
+    const long long n = rows * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      float v = x[i];
+      if (op == 0) {
+        if (rowmul) v *= rowmul[i / C];
+        if (colmul) v *= colmul[i % C];
+      } else v = ew_apply(op, v, op == 3 ? y[i] : 0.f);
+      if (out) out[i] = v;
+      if (out16) st_planes(out16 + i, out16_lo, v);
+    }
   }
 }
 
@@ -301,10 +371,25 @@ __device__ __forceinline__ unsigned int mix64(unsigned long long z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return static_cast<unsigned int>((z ^ (z >> 31)) >> 32);
 }
-__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, __nv_bfloat16* __restrict__ out16,
-                               long long out16_lo, long long n, unsigned int thr, float inv_keep, unsigned long long seed) {
+__device__ __forceinline__ float keep_factor(unsigned long long seed, unsigned long long i, unsigned int thr, float inv_keep) {
+  return mix64(seed * 0xD1342543DE82EF95ull + i) >= thr ? inv_keep : 0.f;
+}
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                      __nv_bfloat16* __restrict__ out16, long long out16_lo, long long n,
+                                                      unsigned int thr, float inv_keep, unsigned long long seed, int vec) {
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      float4 v = ld4f(x + 4 * i);
+      v.x *= keep_factor(seed, 4 * i, thr, inv_keep); v.y *= keep_factor(seed, 4 * i + 1, thr, inv_keep);
+      v.z *= keep_factor(seed, 4 * i + 2, thr, inv_keep); v.w *= keep_factor(seed, 4 * i + 3, thr, inv_keep);
+      if (out) st4f(out + 4 * i, v);
+      if (out16) st_planes4(out16 + 4 * i, out16_lo, v);
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = mix64(seed * 0xD1342543DE82EF95ull + static_cast<unsigned long long>(i)) >= thr ? x[i] * inv_keep : 0.f;
+    const float v = x[i] * keep_factor(seed, i, thr, inv_keep);
     if (out) out[i] = v;
     if (out16) st_planes(out16 + i, out16_lo, v);
   }
@@ -319,14 +404,24 @@ __global__ void __launch_bounds__(256) resid_branch_fwd_kernel(const float* __re
                                                                const float* __restrict__ scale, const float* __restrict__ ymul,
                                                                float* __restrict__ out, long long rows, int C, unsigned int thr,
                                                                float inv_keep, unsigned long long seed) {
-  const long long n = rows * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / C;
-    const int c = static_cast<int>(i - r * C);
-    float v = y[i] + (bias ? bias[c] : 0.f);
-    if (thr) v = mix64(seed * 0xD1342543DE82EF95ull + static_cast<unsigned long long>(i)) >= thr ? v * inv_keep : 0.f;
-    v *= (ymul ? ymul[r] : 1.f) * (scale ? scale[c] : 1.f);
-    out[i] = resid[i] * (rm ? rm[r] : 1.f) + v;
+  const int C4 = C >> 2;   // C % 4 == 0 (host check)
+  const long long n4 = rows * C4;
+  for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * blockDim.x) {
+    const long long r = i4 / C4;
+    const int c = static_cast<int>(i4 - r * C4) * 4;
+    float4 v = ld4f(y + 4 * i4);
+    if (bias) { const float4 b = ld4f(bias + c); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+    if (thr) {
+      const unsigned long long i = 4ull * static_cast<unsigned long long>(i4);
+      v.x *= keep_factor(seed, i, thr, inv_keep); v.y *= keep_factor(seed, i + 1, thr, inv_keep);
+      v.z *= keep_factor(seed, i + 2, thr, inv_keep); v.w *= keep_factor(seed, i + 3, thr, inv_keep);
+    }
+    const float ym = ymul ? ymul[r] : 1.f;
+    float4 sc = make_float4(ym, ym, ym, ym);
+    if (scale) { const float4 t = ld4f(scale + c); sc.x *= t.x; sc.y *= t.y; sc.z *= t.z; sc.w *= t.w; }
+    const float4 a = ld4f(resid + 4 * i4);
+    const float m = rm ? rm[r] : 1.f;
+    st4f(out + 4 * i4, make_float4(a.x * m + v.x * sc.x, a.y * m + v.y * sc.y, a.z * m + v.z * sc.z, a.w * m + v.w * sc.w));
   }
 }
 
@@ -339,47 +434,64 @@ __global__ void __launch_bounds__(256) resid_branch_bwd_kernel(const float* __re
                                                                long long dy_lo, float* __restrict__ dbias, float* __restrict__ dscale,
                                                                int R, int C, int rows_per_block, unsigned int thr, float inv_keep,
                                                                unsigned long long seed) {
-  __shared__ float red[2][8][33];
+  __shared__ float red[2][8][129];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
+  const int c = (blockIdx.x * 32 + tx) * 4;   // C % 4 == 0 (host check)
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(R, r0 + rows_per_block);
-  float sb = 0.f, ss = 0.f;
+  float4 sb = make_float4(0, 0, 0, 0), ss = make_float4(0, 0, 0, 0);
   if (c < C) {
-    const float sc = scale ? scale[c] : 1.f;
-    const float bc = bias ? bias[c] : 0.f;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bc = make_float4(0, 0, 0, 0);
+    if (scale) sc = ld4f(scale + c);
+    if (bias) bc = ld4f(bias + c);
     for (int r = r0 + ty; r < r1; r += 8) {
       const long long i = (long long)r * C + c;
-      const float gi = g[i];
-      if (dresid) dresid[i] = gi * (rm ? rm[r] : 1.f);
-      float t = gi * (ymul ? ymul[r] : 1.f);
-      if (thr) t = mix64(seed * 0xD1342543DE82EF95ull + static_cast<unsigned long long>(i)) >= thr ? t * inv_keep : 0.f;
-      const float dyi = t * sc;
-      st_planes(dy16 + i, dy_lo, dyi);
-      sb += dyi;
-      ss += t * (y[i] + bc);
+      const float4 gi = ld4f(g + i);
+      if (dresid) { const float m = rm ? rm[r] : 1.f; st4f(dresid + i, make_float4(gi.x * m, gi.y * m, gi.z * m, gi.w * m)); }
+      const float ym = ymul ? ymul[r] : 1.f;
+      float4 t = make_float4(gi.x * ym, gi.y * ym, gi.z * ym, gi.w * ym);
+      if (thr) {
+        t.x *= keep_factor(seed, i, thr, inv_keep); t.y *= keep_factor(seed, i + 1, thr, inv_keep);
+        t.z *= keep_factor(seed, i + 2, thr, inv_keep); t.w *= keep_factor(seed, i + 3, thr, inv_keep);
+      }
+      const float4 dyi = make_float4(t.x * sc.x, t.y * sc.y, t.z * sc.z, t.w * sc.w);
+      st_planes4(dy16 + i, dy_lo, dyi);
+      sb.x += dyi.x; sb.y += dyi.y; sb.z += dyi.z; sb.w += dyi.w;
+      const float4 yi = ld4f(y + i);
+      ss.x += t.x * (yi.x + bc.x); ss.y += t.y * (yi.y + bc.y); ss.z += t.z * (yi.z + bc.z); ss.w += t.w * (yi.w + bc.w);
     }
   }
-  red[0][ty][tx] = sb;
-  red[1][ty][tx] = ss;
+  red[0][ty][tx * 4] = sb.x; red[0][ty][tx * 4 + 1] = sb.y; red[0][ty][tx * 4 + 2] = sb.z; red[0][ty][tx * 4 + 3] = sb.w;
+  red[1][ty][tx * 4] = ss.x; red[1][ty][tx * 4 + 1] = ss.y; red[1][ty][tx * 4 + 2] = ss.z; red[1][ty][tx * 4 + 3] = ss.w;
   __syncthreads();
-  if (ty < 2 && c < C) {
-    float t = 0.f;
+  {
+    const int which = threadIdx.x >> 7, j = threadIdx.x & 127;   // 128 threads per sum
+    const int cc = blockIdx.x * 128 + j;
+    float* dst = which == 0 ? dbias : dscale;
+    if (cc < C && dst) {
+      float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[ty][k][tx];
-    float* dst = ty == 0 ? dbias : dscale;
-    if (dst) atomicAdd(dst + c, t);
+      for (int k = 0; k < 8; ++k) t += red[which][k][j];
+      atomicAdd(dst + cc, t);
+    }
   }
 }
 
 // dx = dy * gelu'(x)
-__global__ void gelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = x[i];
-    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
-    const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
-    dx[i] = dy[i] * (cdf + v * pdf);
+__device__ __forceinline__ float gelu_grad(float v) {
+  const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+  return cdf + v * pdf;
+}
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                       float* __restrict__ dx, long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ld4f(x + 4 * i), d = ld4f(dy + 4 * i);
+    st4f(dx + 4 * i, make_float4(d.x * gelu_grad(v.x), d.y * gelu_grad(v.y), d.z * gelu_grad(v.z), d.w * gelu_grad(v.w)));
   }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * gelu_grad(x[i]);
 }
 
 // MaxPool1d(3, 2, 1) backward on token-major fp32: the gradient goes to the first maximum of the window (ATen semantics)
@@ -423,7 +535,21 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     if (p_lo) v += __bfloat162float(p16[p_lo + j]);
     return v;
   };
+  const bool vec = !p32 && (Tk % 4 == 0) && (p_ld % 4 == 0) && (p_lo % 4 == 0) && (ds_ld % 4 == 0) && (ds_lo % 4 == 0) && dS16 && !dS;
   float s = 0.f;
+  if (vec) {   // planes in, planes out: 4 elements per lane and iteration
+    for (int j = lane * 4; j < Tk; j += 128) {
+      const float4 pv = ld_planes4(p16 + j, p_lo), dv = ld4f(d + j);
+      s += (pv.x * dv.x + pv.y * dv.y) + (pv.z * dv.z + pv.w * dv.w);
+    }
+    s = warp_sum(s);
+    for (int j = lane * 4; j < Tk; j += 128) {
+      const float4 pv = ld_planes4(p16 + j, p_lo), dv = ld4f(d + j);
+      st_planes4(dS16 + row * ds_ld + j, ds_lo, make_float4(scale * pv.x * (dv.x - s), scale * pv.y * (dv.y - s),
+                                                            scale * pv.z * (dv.z - s), scale * pv.w * (dv.w - s)));
+    }
+    return;
+  }
   for (int j = lane; j < Tk; j += 32) s += prob(j) * d[j];
   s = warp_sum(s);
   for (int j = lane; j < Tk; j += 32) {
@@ -447,6 +573,17 @@ static inline int bgrid(long long n, int block, int cap = 148 * 8) {
 extern "C" int vilco_to_planes(const float* x, const float* rowmul, const float* colmul, void* y, int64_t y_lo, void* yT,
                                int64_t yT_lo, int R, int C, int ldT, int Z, void* stream) {
   VILCO_CHECK_ARG(x && (y || yT) && R > 0 && C > 0 && Z > 0, "vilco_to_planes: bad arguments");
+  if (!yT && C % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 && y_lo % 4 == 0 &&
+      (!colmul || reinterpret_cast<uintptr_t>(colmul) % 16 == 0)) {
+    // Z independent matrices are contiguous: one flat pass (rowmul, when given, indexes z * R + r as well)
+    const long long rows = (long long)Z * R;
+    long long g = (rows * (C / 4) + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    to_planes_vec_kernel<<<static_cast<unsigned>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, rows, C);
+    VILCO_LAUNCH_CHECK();
+    return VILCO_OK;
+  }
   dim3 grid((C + 31) / 32, (R + 31) / 32, Z);
   to_planes_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
       x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, static_cast<__nv_bfloat16*>(yT), yT_lo, R, C, ldT);
@@ -495,7 +632,9 @@ extern "C" int vilco_dwconv_bwd(const float* x, const float* mask, const float* 
 
 extern "C" int vilco_gelu_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream) {
   VILCO_CHECK_ARG(x && dy && dx && n > 0, "vilco_gelu_bwd: bad arguments");
-  gelu_bwd_kernel<<<bgrid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dx, n);
+  VILCO_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(dy) % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(dx) % 16 == 0, "vilco_gelu_bwd: buffers must be 16-byte aligned");
+  gelu_bwd_kernel<<<bgrid((n + 3) / 4, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dx, n);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -535,8 +674,8 @@ extern "C" int vilco_dwconv_fwd32(const float* x, const float* mask, const float
 }
 
 extern "C" int vilco_relshift_bwd(const float* dS, float* dBD, void* dBD16, int64_t dbd_lo, int64_t Z, int T, void* stream) {
-  VILCO_CHECK_ARG(dS && (dBD || dBD16) && Z > 0 && T > 0, "vilco_relshift_bwd: bad arguments");
-  relshift_bwd_kernel<<<bgrid(Z * T * 2LL * T, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  VILCO_CHECK_ARG(dS && (dBD || dBD16) && Z > 0 && T > 0 && T % 2 == 0 && dbd_lo % 4 == 0, "vilco_relshift_bwd: bad arguments");
+  relshift_bwd_kernel<<<bgrid(Z * T * (T / 2LL), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       dS, dBD, static_cast<__nv_bfloat16*>(dBD16), dbd_lo, Z, T);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
@@ -545,8 +684,10 @@ extern "C" int vilco_relshift_bwd(const float* dS, float* dBD, void* dBD16, int6
 extern "C" int vilco_dropout(const float* x, float* out, void* out16, int64_t out16_lo, int64_t n, float p, uint64_t seed, void* stream) {
   VILCO_CHECK_ARG(x && (out || out16) && n > 0 && p >= 0.f && p < 1.f, "vilco_dropout: bad arguments");
   const unsigned int thr = static_cast<unsigned int>(static_cast<double>(p) * 4294967296.0);
-  dropout_kernel<<<bgrid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, static_cast<__nv_bfloat16*>(out16), out16_lo, n,
-                                                                             thr, 1.0f / (1.0f - p), seed);
+  auto al = [](const void* q, int a) { return !q || reinterpret_cast<uintptr_t>(q) % a == 0; };
+  const int vec = (n % 4 == 0 && al(x, 16) && al(out, 16) && al(out16, 8) && out16_lo % 4 == 0) ? 1 : 0;
+  dropout_kernel<<<bgrid(vec ? n / 4 : n, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, out, static_cast<__nv_bfloat16*>(out16), out16_lo, n, thr, 1.0f / (1.0f - p), seed, vec);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -554,17 +695,23 @@ extern "C" int vilco_dropout(const float* x, float* out, void* out16, int64_t ou
 int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const float* colmul, float* out, void* out16,
              int64_t out16_lo, int64_t rows, int C, void* stream) {
   VILCO_CHECK_ARG(x && (out || out16) && rows > 0 && C > 0 && op >= 0 && op <= 3 && (op != 3 || y), "vilco_ew: bad arguments");
-  ew_kernel<<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(op, x, y, rowmul, colmul, out,
-                                                                               static_cast<__nv_bfloat16*>(out16), out16_lo, rows, C);
+  auto al = [](const void* q, int a) { return !q || reinterpret_cast<uintptr_t>(q) % a == 0; };
+  const bool vec = C % 4 == 0 && al(x, 16) && al(y, 16) && al(colmul, 16) && al(out, 16) && al(out16, 8) && out16_lo % 4 == 0;
+  if (vec)
+    ew_kernel<true><<<bgrid(rows * (C / 4), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        op, x, y, rowmul, colmul, out, static_cast<__nv_bfloat16*>(out16), out16_lo, rows, C);
+  else
+    ew_kernel<false><<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        op, x, y, rowmul, colmul, out, static_cast<__nv_bfloat16*>(out16), out16_lo, rows, C);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
 
 extern "C" int vilco_resid_branch_fwd(const float* resid, const float* rm, const float* y, const float* bias, const float* scale,
                                       const float* ymul, float* out, int64_t rows, int C, float p, uint64_t seed, void* stream) {
-  VILCO_CHECK_ARG(resid && y && out && rows > 0 && C > 0 && p >= 0.f && p < 1.f, "vilco_resid_branch_fwd: bad arguments");
+  VILCO_CHECK_ARG(resid && y && out && rows > 0 && C > 0 && C % 4 == 0 && p >= 0.f && p < 1.f, "vilco_resid_branch_fwd: bad arguments");
   const unsigned int thr = static_cast<unsigned int>(static_cast<double>(p) * 4294967296.0);
-  resid_branch_fwd_kernel<<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(resid, rm, y, bias, scale, ymul, out, rows,
+  resid_branch_fwd_kernel<<<bgrid(rows * (C / 4), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(resid, rm, y, bias, scale, ymul, out, rows,
                                                                                         C, thr, 1.0f / (1.0f - p), seed);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
@@ -573,9 +720,10 @@ extern "C" int vilco_resid_branch_fwd(const float* resid, const float* rm, const
 extern "C" int vilco_resid_branch_bwd(const float* g, const float* rm, const float* y, const float* bias, const float* scale,
                                       const float* ymul, float* dresid, void* dy16, int64_t dy_lo, float* dbias, float* dscale,
                                       int R, int C, float p, uint64_t seed, void* stream) {
-  VILCO_CHECK_ARG(g && y && dy16 && R > 0 && C > 0 && p >= 0.f && p < 1.f, "vilco_resid_branch_bwd: bad arguments");
+  VILCO_CHECK_ARG(g && y && dy16 && R > 0 && C > 0 && C % 4 == 0 && dy_lo % 4 == 0 && p >= 0.f && p < 1.f,
+                  "vilco_resid_branch_bwd: bad arguments");
   const unsigned int thr = static_cast<unsigned int>(static_cast<double>(p) * 4294967296.0);
-  const int cblocks = (C + 31) / 32;
+  const int cblocks = (C + 127) / 128;
   int slabs = (148 * 8 + cblocks - 1) / cblocks;
   int rpb = (R + slabs - 1) / slabs;
   if (rpb < 32) rpb = 32;
