@@ -155,15 +155,13 @@ struct LnBwdParams {
   float eps; float* dx; float* dw; float* db; int rows, C;
 };
 
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p) {
-  extern __shared__ float s_acc[];  // [2][C]
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams p) {
+  extern __shared__ float s_acc[];  // [2][C]: per-block partial dw / db, accumulated with shared-memory atomics
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nch = p.C >> 7;
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  float4 dwl[BW_MAXCH], dbl[BW_MAXCH];
-#pragma unroll
-  for (int i = 0; i < BW_MAXCH; ++i) { dwl[i] = make_float4(0, 0, 0, 0); dbl[i] = make_float4(0, 0, 0, 0); }
+  const bool want_wb = p.dw != nullptr;
   for (int row = blockIdx.x * 8 + warp; row < p.rows; row += gridDim.x * 8) {
     const float* x = p.x + (long long)row * p.C;
     float4 v[BW_MAXCH], g[BW_MAXCH];
@@ -175,6 +173,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
         v[i] = ld4f(x + c);
         if (p.add) { const float4 a = ld4f(p.add + (long long)row * p.C + c); v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w; }
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    // issue the gradient loads before the reductions so that they overlap the shuffle chains
+#pragma unroll
+    for (int i = 0; i < BW_MAXCH; ++i)
+      if (i < nch) {
+        const int c = (i * 32 + lane) * 4;
+        g[i] = ld4f(p.dy + (long long)row * p.C + c);
+        if (p.y_relu) {
+          const float4 yr = ld4f(p.y_relu + (long long)row * p.C + c);
+          if (!(yr.x > 0.f)) g[i].x = 0.f; if (!(yr.y > 0.f)) g[i].y = 0.f; if (!(yr.z > 0.f)) g[i].z = 0.f; if (!(yr.w > 0.f)) g[i].w = 0.f;
+        }
       }
     const float mean = warp_sum(s) / p.C;
     float q = 0.f;
@@ -190,15 +199,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
     for (int i = 0; i < BW_MAXCH; ++i)
       if (i < nch) {
         const int c = (i * 32 + lane) * 4;
-        float4 d = ld4f(p.dy + (long long)row * p.C + c);
-        if (p.y_relu) {
-          const float4 yr = ld4f(p.y_relu + (long long)row * p.C + c);
-          if (!(yr.x > 0.f)) d.x = 0.f; if (!(yr.y > 0.f)) d.y = 0.f; if (!(yr.z > 0.f)) d.z = 0.f; if (!(yr.w > 0.f)) d.w = 0.f;
-        }
+        const float4 d = g[i];
         const float4 w = ld4f(p.w + c);
         v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
-        dwl[i].x += d.x * v[i].x; dwl[i].y += d.y * v[i].y; dwl[i].z += d.z * v[i].z; dwl[i].w += d.w * v[i].w;
-        dbl[i].x += d.x; dbl[i].y += d.y; dbl[i].z += d.z; dbl[i].w += d.w;
+        if (want_wb) {
+          atomicAdd(&s_acc[c], d.x * v[i].x); atomicAdd(&s_acc[c + 1], d.y * v[i].y);
+          atomicAdd(&s_acc[c + 2], d.z * v[i].z); atomicAdd(&s_acc[c + 3], d.w * v[i].w);
+          atomicAdd(&s_acc[p.C + c], d.x); atomicAdd(&s_acc[p.C + c + 1], d.y);
+          atomicAdd(&s_acc[p.C + c + 2], d.z); atomicAdd(&s_acc[p.C + c + 3], d.w);
+        }
         g[i] = make_float4(d.x * w.x, d.y * w.y, d.z * w.z, d.w * w.w);
         s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
         s2 += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
@@ -213,18 +222,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
                          rstd * (g[i].z - s1 - v[i].z * s2), rstd * (g[i].w - s1 - v[i].w * s2)));
       }
   }
-#pragma unroll
-  for (int i = 0; i < BW_MAXCH; ++i)
-    if (i < nch) {
-      const int c = (i * 32 + lane) * 4;
-      atomicAdd(&s_acc[c], dwl[i].x); atomicAdd(&s_acc[c + 1], dwl[i].y); atomicAdd(&s_acc[c + 2], dwl[i].z); atomicAdd(&s_acc[c + 3], dwl[i].w);
-      atomicAdd(&s_acc[p.C + c], dbl[i].x); atomicAdd(&s_acc[p.C + c + 1], dbl[i].y); atomicAdd(&s_acc[p.C + c + 2], dbl[i].z); atomicAdd(&s_acc[p.C + c + 3], dbl[i].w);
-    }
   __syncthreads();
-  for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
-    if (p.dw) atomicAdd(p.dw + i, s_acc[i]);
-    if (p.db) atomicAdd(p.db + i, s_acc[p.C + i]);
-  }
+  if (want_wb)
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+      atomicAdd(p.dw + i, s_acc[i]);
+      if (p.db) atomicAdd(p.db + i, s_acc[p.C + i]);
+    }
 }
 
 // ---- depthwise conv k=3 (stride s) * mask backward: given dconv (B, T/s, C) (gradient w.r.t. the masked conv output)
@@ -614,7 +617,7 @@ extern "C" int vilco_layernorm_bwd(const float* x, const float* add, const float
   VILCO_CHECK_ARG(C % 128 == 0 && C <= 128 * BW_MAXCH, "vilco_layernorm_bwd: C=%d unsupported", C);
   LnBwdParams p{x, add, w, dy, y_relu, eps, dx, dw, db, rows, C};
   int grid = (rows + 7) / 8;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148 * 2 * 4) grid = 148 * 2 * 4;   // 2 resident CTAs per SM, ~4 rows per warp
   layernorm_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(p);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
