@@ -4,6 +4,7 @@
 //   LayerNorm backward (channel LN of blocks.py:160-175 and nn.LayerNorm), optionally through the fused ReLU
 //   depthwise k=3 conv + mask + LayerNorm backward (q/k/v front of MaskedMHCA)
 //   GELU / max-pool / masked-softmax backward
+#include <cstdlib>
 #include "common.cuh"
 
 namespace vilco {
@@ -156,12 +157,13 @@ struct LnBwdParams {
 };
 
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams p) {
-  extern __shared__ float s_acc[];  // [2][C]: per-block partial dw / db, accumulated with shared-memory atomics
+  extern __shared__ float s_acc[];  // [8 warps][2][C]: warp-private partial dw / db (each lane owns its columns: plain RMW)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nch = p.C >> 7;
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 16 * p.C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const bool want_wb = p.dw != nullptr;
+  float* my = s_acc + warp * 2 * p.C;
   for (int row = blockIdx.x * 8 + warp; row < p.rows; row += gridDim.x * 8) {
     const float* x = p.x + (long long)row * p.C;
     float4 v[BW_MAXCH], g[BW_MAXCH];
@@ -203,10 +205,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
         const float4 w = ld4f(p.w + c);
         v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;   // xhat
         if (want_wb) {
-          atomicAdd(&s_acc[c], d.x * v[i].x); atomicAdd(&s_acc[c + 1], d.y * v[i].y);
-          atomicAdd(&s_acc[c + 2], d.z * v[i].z); atomicAdd(&s_acc[c + 3], d.w * v[i].w);
-          atomicAdd(&s_acc[p.C + c], d.x); atomicAdd(&s_acc[p.C + c + 1], d.y);
-          atomicAdd(&s_acc[p.C + c + 2], d.z); atomicAdd(&s_acc[p.C + c + 3], d.w);
+          float4 aw = ld4f(my + c), ab = ld4f(my + p.C + c);
+          aw.x += d.x * v[i].x; aw.y += d.y * v[i].y; aw.z += d.z * v[i].z; aw.w += d.w * v[i].w;
+          ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+          st4f(my + c, aw); st4f(my + p.C + c, ab);
         }
         g[i] = make_float4(d.x * w.x, d.y * w.y, d.z * w.z, d.w * w.w);
         s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
@@ -224,9 +226,12 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
   }
   __syncthreads();
   if (want_wb)
-    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
-      atomicAdd(p.dw + i, s_acc[i]);
-      if (p.db) atomicAdd(p.db + i, s_acc[p.C + i]);
+    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_acc[w * 2 * p.C + i];
+      float* dst = i < p.C ? p.dw + i : (p.db ? p.db + (i - p.C) : nullptr);
+      if (dst) atomicAdd(dst, t);
     }
 }
 
@@ -617,8 +622,15 @@ extern "C" int vilco_layernorm_bwd(const float* x, const float* add, const float
   VILCO_CHECK_ARG(C % 128 == 0 && C <= 128 * BW_MAXCH, "vilco_layernorm_bwd: C=%d unsupported", C);
   LnBwdParams p{x, add, w, dy, y_relu, eps, dx, dw, db, rows, C};
   int grid = (rows + 7) / 8;
-  if (grid > 148 * 2 * 4) grid = 148 * 2 * 4;   // 2 resident CTAs per SM, ~4 rows per warp
-  layernorm_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(p);
+  static int cap = [] { const char* e = getenv("VILCO_LNB_GRID"); return e ? atoi(e) : 148 * 2; }();
+  if (grid > cap) grid = cap;   // 2 resident CTAs per SM (64 KB of warp-private accumulators each)
+  const int smem = 16 * C * static_cast<int>(sizeof(float));
+  static int configured = 0;
+  if (smem > configured) {
+    VILCO_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  layernorm_bwd_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
