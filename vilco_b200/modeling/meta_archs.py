@@ -581,9 +581,10 @@ class PtTransformer(nn.Module):
             gt_cls, gt_off = gt_cls.detach(), gt_off.detach()
             if self.train_label_smoothing > 0:
                 gt_cls = gt_cls * (1 - self.train_label_smoothing) + self.train_label_smoothing / (K + 1)
-            present = torch.zeros(B, K, device=dev)
+            present = torch.zeros(B, K)
             for i, x in enumerate(vl):
-                present[i, x["labels"].to(dev)] = 1
+                present[i, x["labels"].cpu()] = 1
+            present = present.to(dev)
             sums = torch.zeros(4, device=dev)
             scratch = torch.zeros(B * K, device=dev, dtype=torch.int32)
             wcd, wld, wrd = wc.detach().contiguous(), wl.detach().contiguous(), wr.detach().contiguous()
@@ -637,43 +638,53 @@ class PtTransformer(nn.Module):
 
     # ---- targets + losses (reference: meta_archs.py:1224-1344, 1374-1524) --------------------------------
     def _label_points(self, pyr, gt_segments, gt_labels):
-        """label_points_single_video on the device, for every video, laid out over the pyramid rows."""
+        """label_points / label_points_single_video (meta_archs.py:1224-1344) for the whole batch at once, laid out over the
+        pyramid rows: the ground truths of every video are padded to the batch maximum (padding can never be selected) so
+        the assignment is ~30 batched device ops instead of a Python loop per video.  Returns gt_cls (B,P,K), gt_off (B,P,2),
+        and the three Gaussian weights (B,P), which carry autograd to mu / sigma."""
         dev = self.device
-        pts = torch.zeros(pyr.P, 4, device=dev)
-        for l, (o, n) in enumerate(zip(pyr.off, pyr.lens)):
-            pts[o:o + n] = list(self.point_generator.buffer_points)[l][:n].to(dev)
         K = self.num_classes
-        cls_t, reg_t, wc, wl, wr = [], [], [], [], []
-        t, stride = pts[:, 0, None], pts[:, 3, None].clamp(min=1e-9)
-        for seg, lab in zip(gt_segments, gt_labels):
-            seg, lab = seg.to(dev).float(), lab.to(dev)
-            lens = (seg[:, 1] - seg[:, 0])[None, :].repeat(pyr.P, 1)
-            left, right = t - seg[None, :, 0], seg[None, :, 1] - t
-            xrel = ((right - left) / 2.0) / (stride * lens)
-            g = lambda m, s: (-(xrel - m[lab].permute(1, 0)) ** 2 / (2 * s[lab].permute(1, 0) ** 2)).exp()  # noqa: E731
-            npc, npl, npr = g(self.mu, self.sigma), g(self.mu_reg_left, self.sigma_reg_left), g(self.mu_reg_right, self.sigma_reg_right)
-            reg = torch.stack((left, right), dim=-1)
-            if self.train_center_sample == "radius":
-                center = 0.5 * (seg[None, :, 0] + seg[None, :, 1])
-                t_mins = center - stride * self.train_center_sample_radius
-                t_maxs = center + stride * self.train_center_sample_radius
-                cb_l = t - torch.maximum(t_mins, seg[None, :, 0])
-                cb_r = torch.minimum(t_maxs, seg[None, :, 1]) - t
-                inside = torch.stack((cb_l, cb_r), -1).min(-1)[0] > 0
-            else:
-                inside = reg.min(-1)[0] > 0
-            maxreg = reg.max(-1)[0]
-            in_range = (maxreg >= pts[:, 1, None]) & (maxreg <= pts[:, 2, None])
-            lens = lens.masked_fill(~inside, float("inf")).masked_fill(~in_range, float("inf"))
-            min_len, min_inds = lens.min(dim=1)
-            mm = ((lens <= (min_len[:, None] + 1e-3)) & (lens < float("inf"))).to(reg.dtype)
-            ct = (mm @ F.one_hot(lab, K).to(reg.dtype)).clamp(min=0.0, max=1.0)
-            r = torch.arange(pyr.P, device=dev)
-            cls_t.append(ct)
-            reg_t.append(reg[r, min_inds] / stride)
-            wc.append(npc[r, min_inds]); wl.append(npl[r, min_inds]); wr.append(npr[r, min_inds])
-        return (torch.stack(cls_t).contiguous(), torch.stack(reg_t).contiguous(), torch.stack(wc).contiguous(),
-                torch.stack(wl).contiguous(), torch.stack(wr).contiguous())
+        pts = getattr(pyr, "pts", None)
+        if pts is None or pts.device != dev:
+            pts = torch.zeros(pyr.P, 4)
+            for l, (o, n) in enumerate(zip(pyr.off, pyr.lens)):
+                pts[o:o + n] = list(self.point_generator.buffer_points)[l][:n].cpu()
+            pts = pyr.pts = pts.to(dev)
+        B, G = len(gt_segments), max(int(s.shape[0]) for s in gt_segments)
+        seg_h, lab_h, val_h = torch.zeros(B, G, 2), torch.zeros(B, G, dtype=torch.long), torch.zeros(B, G, dtype=torch.bool)
+        for i, (sg, lb) in enumerate(zip(gt_segments, gt_labels)):
+            n = sg.shape[0]
+            seg_h[i, :n], lab_h[i, :n], val_h[i, :n] = sg.float().cpu(), lb.cpu(), True
+            seg_h[i, n:, 1] = 1.0                      # padded segments get length 1 (never selected; avoids 0/0)
+        seg, lab, valid = seg_h.to(dev), lab_h.to(dev), val_h.to(dev)
+        t, stride = pts[None, :, 0, None], pts[None, :, 3, None].clamp(min=1e-9)          # (1,P,1)
+        s0, s1 = seg[:, None, :, 0], seg[:, None, :, 1]                                    # (B,1,G)
+        lens = (s1 - s0).expand(B, pyr.P, G)
+        left, right = t - s0, s1 - t                                                       # (B,P,G)
+        xrel = ((right - left) / 2.0) / (stride * lens)
+        if self.train_center_sample == "radius":
+            center = 0.5 * (s0 + s1)
+            t_mins = center - stride * self.train_center_sample_radius
+            t_maxs = center + stride * self.train_center_sample_radius
+            inside = torch.minimum(t - torch.maximum(t_mins, s0), torch.minimum(t_maxs, s1) - t) > 0
+        else:
+            inside = torch.minimum(left, right) > 0
+        maxreg = torch.maximum(left, right)
+        in_range = (maxreg >= pts[None, :, 1, None]) & (maxreg <= pts[None, :, 2, None])
+        lens = lens.masked_fill(~(inside & in_range & valid[:, None, :]), float("inf"))
+        min_len, min_inds = lens.min(dim=2)                                                # (B,P)
+        mm = ((lens <= (min_len[..., None] + 1e-3)) & (lens < float("inf"))).to(left.dtype)
+        gt_cls = torch.bmm(mm, F.one_hot(lab, K).to(left.dtype)).clamp(min=0.0, max=1.0)   # (B,P,K)
+        idx = min_inds[..., None]
+        gt_off = torch.cat((left.gather(2, idx), right.gather(2, idx)), dim=-1) / stride   # (B,P,2)
+        xs = xrel.gather(2, idx).squeeze(-1)                                               # (B,P)
+        ls = lab.gather(1, min_inds)                                                       # (B,P) label of the selected gt
+
+        def gauss(m, s):
+            return (-(xs - m[ls, 0]) ** 2 / (2 * s[ls, 0] ** 2)).exp()
+        return (gt_cls.contiguous(), gt_off.contiguous(), gauss(self.mu, self.sigma).contiguous(),
+                gauss(self.mu_reg_left, self.sigma_reg_left).contiguous(),
+                gauss(self.mu_reg_right, self.sigma_reg_right).contiguous())
 
     @torch.no_grad()
     def losses(self, vl, logits, offsets, pmask, pyr, prev_out_cls_logits=None):
@@ -684,9 +695,10 @@ class PtTransformer(nn.Module):
         gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
         if self.train_label_smoothing > 0:
             gt_cls = gt_cls * (1 - self.train_label_smoothing) + self.train_label_smoothing / (K + 1)
-        present = torch.zeros(B, K, device=dev)
+        present = torch.zeros(B, K)
         for i, x in enumerate(vl):
-            present[i, x["labels"].to(dev)] = 1
+            present[i, x["labels"].cpu()] = 1
+        present = present.to(dev)
         sums = torch.zeros(4, device=dev)
         scratch = torch.zeros(B * K, device=dev, dtype=torch.int32)
         L.check(L.lib().vilco_mq_losses(
