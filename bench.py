@@ -133,6 +133,64 @@ def cpu_reference_train_rate(state_dict, n_videos, seed=11):
     return n_videos / dt, dt
 
 
+def eager_gpu_rates(state_dict, tf32, n_inf=8, n_train=2):
+    """The same restatement run as eager PyTorch fp32 ON THE B200 (what running the reference's own modules on the GPU
+    amounts to: cuDNN / cuBLAS kernels behind torch ops, batch-1 evaluation, soft-NMS on the host like nms_cpu.cpp).
+    A reported baseline like cpu_baseline; the oracle is only executed here as the thing compared against."""
+    from oracle import mq_oracle as O
+    from oracle import nms_c
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+    cfg = O.ModelCfg()
+    ok = lambda k, v: torch.is_floating_point(v) and not k.startswith("backbone.xlnet.word_embedding")  # noqa: E731
+    P = {k: v.detach().float().cuda().clone() for k, v in state_dict.items() if ok(k, v)}
+    orig_pe = O.sinusoid_pe
+    O.sinusoid_pe = lambda *a: orig_pe(*a).cuda()
+    try:
+        with torch.device("cuda"):
+            def infer(v):
+                x, mask, text, tmask = O.preprocess(cfg, [v], False)
+                with torch.no_grad():
+                    logits, offs, masks, _ = O.forward_heads(P, cfg, x, mask, text, tmask, training=False)
+                    pts = O.points(cfg, [m.shape[1] for m in masks])
+                    segs, scores, labels = O.decode_single_video(cfg, pts, [m[0] for m in masks], [l[0] for l in logits],
+                                                                 [o[0] for o in offs])
+                return O.postprocess(cfg, segs.cpu(), scores.cpu(), labels.cpu(), v["fps"], v["duration"], v["feat_stride"],
+                                     v["feat_num_frames"], nms_c.softnms_1d)
+            vids = synth_videos(n_inf + 1, 21)
+            infer(vids[0])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for v in vids[1:]:
+                infer(v)
+            torch.cuda.synchronize()
+            inf_rate = n_inf / (time.perf_counter() - t0)
+            for q in P.values():
+                q.requires_grad_(True)
+            opt = torch.optim.AdamW(list(P.values()), lr=1e-4, weight_decay=0.05)
+            tv = synth_videos(n_train, 22)
+            for v in tv:
+                v["segments"], v["labels"] = v["segments"].cuda(), v["labels"].cuda()
+
+            def train_step():
+                opt.zero_grad()
+                lo, _ = O.model_train_losses(P, cfg, tv)
+                lo["final_loss"].backward()
+                torch.nn.utils.clip_grad_norm_([q for q in P.values() if q.grad is not None], 1.0)
+                opt.step()
+            train_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                train_step()
+            torch.cuda.synchronize()
+            tr_rate = 3 * n_train / (time.perf_counter() - t0)
+    finally:
+        O.sinusoid_pe = orig_pe
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return inf_rate, tr_rate
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -388,6 +446,17 @@ def main():
         "train": train,
     }
     if not args.no_cpu_baseline:
+        try:
+            eg = {}
+            for tf32 in (False, True):
+                i_r, t_r = eager_gpu_rates(model.state_dict(), tf32)
+                eg["tf32" if tf32 else "fp32"] = {"infer_videos_per_s": i_r, "train_videos_per_s": t_r}
+            eg["what"] = ("oracle/mq_oracle.py as eager PyTorch on this B200 (torch ops -> cuDNN/cuBLAS), evaluation one clip per "
+                          "call + host soft-NMS, training batch 2 with torch autograd + AdamW, no dropout")
+            line["eager_gpu_baseline"] = eg
+        except Exception as e:  # a baseline must never take the bench down
+            line["eager_gpu_baseline"] = {"unavailable": repr(e)[:300]}
+        torch.cuda.empty_cache()
         rate, dt = cpu_reference_rate(model.state_dict(), args.ref_videos)
         cores = os.cpu_count() or 1
         line["cpu_baseline"] = {"value": rate, "unit": "videos/s", "cores": cores, "kind": "port",
