@@ -250,12 +250,14 @@ int vilco_dropout(const float* x, float* out, void* out16, int64_t out16_lo, int
  * Optimizer step over flat fp32 buffers (all parameters / gradients / AdamW moments of a parameter group contiguous):
  *   vilco_grad_clip_coef : coef = min(1, max_norm / (||g||_2 + 1e-6))   — torch.nn.utils.clip_grad_norm_ as called by
  *                          train_one_epoch (MQ/libs/utils/train_utils.py:345-349); max_norm <= 0 gives coef = 1.
- *                          scratch / coef / norm_out are single device floats.
+ *                          Deterministic (no floating-point atomics: data-parallel replicas get bit-identical
+ *                          coefficients).  scratch: VILCO_CLIP_SCRATCH device floats; coef / norm_out: single device floats.
  *   vilco_adamw          : torch.optim.AdamW update (decoupled weight decay, bias correction; make_optimizer,
  *                          train_utils.py:124-140) with the gradient scaled by *grad_scale (device scalar or NULL).  When
  *                          `planes` is given the updated parameter is also written as bf16 hi (planes[i]) and lo
  *                          (planes[planes_lo + i], skipped when planes_lo == 0) operand planes for the GEMM kernels.
  * ------------------------------------------------------------------------------------ */
+#define VILCO_CLIP_SCRATCH 1184
 int vilco_grad_clip_coef(const float* g, int64_t n, float max_norm, float* scratch, float* coef, float* norm_out, void* stream);
 int vilco_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 float weight_decay, int step, const float* grad_scale, void* planes, int64_t planes_lo, void* stream);

@@ -6,8 +6,10 @@
 
 namespace vilco {
 
+// deterministic two-stage sum of squares (data-parallel replicas must compute bit-identical clip coefficients, so no
+// floating-point atomics): stage 1 writes one partial per block, stage 2 reduces the partials in a fixed order.
 __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x, long long n4, const float* __restrict__ tail,
-                                                    int ntail, float* __restrict__ out) {
+                                                    int ntail, float* __restrict__ partial) {
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = x[i];
@@ -21,15 +23,27 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += red[i];
-    atomicAdd(out, t);
+    partial[blockIdx.x] = t;
   }
 }
 
-// coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))  (clip_grad_norm_); norm_out = sqrt(sumsq)
-__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef, float* __restrict__ norm_out) {
-  const float nrm = sqrtf(*sumsq);
-  if (norm_out) *norm_out = nrm;
-  *coef = max_norm > 0.f ? fminf(1.f, max_norm / (nrm + 1e-6f)) : 1.f;
+// coef = min(1, max_norm / (sqrt(sumsq) + 1e-6))  (clip_grad_norm_); norm_out = sqrt(sumsq).  One block of 256 threads.
+__global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict__ partial, int nparts, float max_norm,
+                                                        float* __restrict__ coef, float* __restrict__ norm_out) {
+  __shared__ float red[256];
+  float t = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 256) t += partial[i];
+  red[threadIdx.x] = t;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float nrm = sqrtf(red[0]);
+    if (norm_out) *norm_out = nrm;
+    *coef = max_norm > 0.f ? fminf(1.f, max_norm / (nrm + 1e-6f)) : 1.f;
+  }
 }
 
 __device__ __forceinline__ float adamw_one(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps,
@@ -88,11 +102,11 @@ extern "C" int vilco_grad_clip_coef(const float* g, int64_t n, float max_norm, f
   VILCO_CHECK_ARG(g && scratch && coef && n > 0, "vilco_grad_clip_coef: bad arguments");
   VILCO_CHECK_ARG(reinterpret_cast<uintptr_t>(g) % 16 == 0, "vilco_grad_clip_coef: gradient buffer must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  VILCO_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), st));
   const long long n4 = n / 4;
-  sumsq_kernel<<<ogrid(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(g), n4, g + n4 * 4, static_cast<int>(n - n4 * 4), scratch);
+  const int grid = ogrid(n4, 256);   // <= 148 * 8 partials; scratch must hold VILCO_CLIP_SCRATCH floats
+  sumsq_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(g), n4, g + n4 * 4, static_cast<int>(n - n4 * 4), scratch);
   VILCO_LAUNCH_CHECK();
-  clip_coef_kernel<<<1, 1, 0, st>>>(scratch, max_norm, coef, norm_out);
+  clip_coef_kernel<<<1, 256, 0, st>>>(scratch, grid, max_norm, coef, norm_out);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

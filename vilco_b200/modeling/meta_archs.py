@@ -567,6 +567,7 @@ class PtTransformer(nn.Module):
                          seed=(int(torch.initial_seed()) & 0xFFFFF) * 4096 + self._train_calls, sinks=sinks)
         else:
             tp = TE.Tape(W, sinks=sinks)
+        tp.after_node = getattr(self, "_after_backward_node", None)     # set by trainer.Trainer (bucketed all-reduce)
         with torch.no_grad():
             x16 = ops.pack_feats(batched)
             t16 = ops.pack_feats(text.detach()) if text is not None else None
@@ -617,6 +618,7 @@ class PtTransformer(nn.Module):
                 logitsV.g, offsetsV.g = dlogits, doffsets
                 model._last_head_grads = (dlogits, doffsets, pyr)   # kept for the gradient parity tests
                 tp.backward()
+                model._last_touch = (tp.n_nodes, dict(tp.touch), set(tp.G.keys()))
                 for key, g in tp.G.items():
                     prm = named.get(key)
                     if prm is None or not prm.requires_grad:

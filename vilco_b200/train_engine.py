@@ -42,6 +42,9 @@ class Tape:
         # key -> fp32 buffer in the packed layout that IS the parameter's .grad (zeroed by the trainer): kernels accumulate
         # straight into it, no temporary and no add per parameter
         self.sinks = sinks or {}
+        self.touch = {}          # sink key -> index (in backward execution order) of the last node that accumulated into it
+        self.cur = -1
+        self.after_node = None   # optional callback(i) after backward node i (the trainer's bucketed all-reduce)
         self.nodes = []
         self.p_drop, self.p_path, self.p_xl = float(dropout), float(droppath), float(xl_dropout)
         self.seed = int(seed) << 20
@@ -64,9 +67,22 @@ class Tape:
             x.p16 = y.reshape(y.shape[0], *x.v.shape)
         return x.p16
 
+    def sink(self, key):
+        """the .grad view to accumulate parameter `key` into (or None), remembering which backward node used it last"""
+        if key is None:
+            return None
+        t = self.sinks.get(key)
+        if t is not None:
+            self.touch[key] = self.cur
+        return t
+
     def backward(self):
-        for fn in reversed(self.nodes):
+        self.n_nodes = len(self.nodes)
+        for i, fn in enumerate(reversed(self.nodes)):
+            self.cur = i
             fn()
+            if self.after_node is not None:
+                self.after_node(i)
         self.nodes = []
 
     # ---- operators ----
@@ -84,7 +100,7 @@ class Tape:
         def bwd():
             if y.g is None:
                 return
-            sw, sb = self.sinks.get(wkey), self.sinks.get(bkey) if bkey else None
+            sw, sb = self.sink(wkey), self.sink(bkey) if bkey else None
             dx, dw, db = BW.linear_bwd(y.g, x16, W[wkey], rowmul=rowmul, need_dx=not x.const, need_db=b is not None,
                                        dw_out=sw, db_out=sb)
             self.acc(x, dx)
@@ -156,7 +172,7 @@ class Tape:
             if y.g is None:
                 return
             g = y.g if keep_rows is None else ops.ew(0, y.g, rowmul=keep_rows)
-            sw, sb = self.sinks.get(wkey), self.sinks.get(bkey)
+            sw, sb = self.sink(wkey), self.sink(bkey)
             if (sw is None) != (sb is None):
                 sw = sb = None
             dx, dw, db = BW.layernorm_bwd(g, x.v, W[wkey], eps, y_relu=yr if relu else None, dw_out=sw, db_out=sb)
@@ -229,8 +245,8 @@ class Tape:
             g = out.g.contiguous()
             dz = ops.empty16(rows, N, device=g.device)
             dres = torch.empty_like(g) if rm is not None else None
-            sb = self.sinks.get(bkey) if bkey else None
-            ss = self.sinks.get(skey) if sc is not None else None
+            sb = self.sink(bkey) if bkey else None
+            ss = self.sink(skey) if sc is not None else None
             db = sb if sb is not None else (torch.zeros(N, device=g.device, dtype=f32) if bkey else None)
             ds = ss if ss is not None else (torch.zeros(N, device=g.device, dtype=f32) if sc is not None else None)
             L.check(L.lib().vilco_resid_branch_bwd(_p(g), _p(rm), _p(y), _p(b), _p(sc), _p(ymul), _p(dres), _p(dz), _i64(lo(dz)),
@@ -241,7 +257,7 @@ class Tape:
                 self.accp(bkey, db)
             if sc is not None and ss is None:
                 self.accp(skey, ds)
-            sw = self.sinks.get(wkey)
+            sw = self.sink(wkey)
             dx, dw = BW.linear_bwd16(dz, x16, W[wkey], need_dx=not x.const, dw_out=sw)
             self.acc(x, dx)
             if sw is None:
@@ -260,7 +276,7 @@ class Tape:
             self.acc(resid, out.g if rowmul is None else ops.ew(0, out.g, rowmul=rowmul))
             self.acc(y, out.g if s is None else ops.ew(0, out.g, colmul=s))
             if s is not None:
-                sk = self.sinks.get(skey)
+                sk = self.sink(skey)
                 if sk is None:
                     self.accp(skey, BW.colsum(out.g, y=y.v))
                 else:

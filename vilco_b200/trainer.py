@@ -41,15 +41,69 @@ def broadcast_parameters(model, src=0):
 
 
 class Trainer:
-    def __init__(self, model, optimizer, clip_grad_l2norm=-1.0, scheduler=None):
+    """One iteration of train_one_epoch, data-parallel.  With a FlatAdamW optimizer and world_size > 1 the gradient
+    all-reduce is bucketed and overlapped with the backward pass: the flat buffer is laid out in (approximately) reverse
+    execution order, the first step records after which backward node each bucket is complete, and from the second step on
+    every finished bucket is all-reduced asynchronously (NCCL stream) while the remaining backward kernels run."""
+    BUCKET = 32 * 1024 * 1024      # elements (128 MB of fp32) per all-reduce bucket
+
+    def __init__(self, model, optimizer, clip_grad_l2norm=-1.0, scheduler=None, overlap=True):
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.clip = float(clip_grad_l2norm)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.flat = isinstance(optimizer, FlatAdamW)
+        self.overlap = bool(overlap) and self.flat and self.world > 1
+        self.plan = None           # (n_nodes, {node index: [(a, b), ...]}, [(a, b) launched after the last node])
+        self._work = []
         if self.flat:
             model.use_flat_optimizer(optimizer)
         else:
             self.grads = FlatGrads(model.parameters())
+
+    # ---- bucketed all-reduce -------------------------------------------------------------------------------------
+    def _build_plan(self):
+        """From the last backward's record: bucket [a, b) of the flat gradient buffer is final after node max(last touch of
+        the parameters inside it); parameters that took the fallback path (permuted layouts, glue) are final at the end."""
+        last = getattr(self.model, "_last_touch", None)
+        if last is None:
+            return None
+        n_nodes, touch, fallback = last
+        opt = self.optimizer
+        names = {id(p): k for k, p in self.model.named_parameters()}
+        ready = []                                     # (offset, end, node index; None = only final after the whole backward)
+        for g in opt.param_groups:
+            for p in g["params"]:
+                if id(p) in opt.slots:
+                    o, k = opt.slots[id(p)]
+                    key = names.get(id(p))
+                    if key in fallback:
+                        r = None
+                    elif key in touch:
+                        r = touch[key]
+                    elif bool((opt.flat_grad[o:o + k] != 0).any()):
+                        r = None                       # written by torch autograd of the glue (mu / sigma, prompts)
+                    else:
+                        r = -1                         # dead parameter: its gradient is the zero it was reset to
+                    ready.append((o, o + k, r))
+        ready.sort()
+        per_node, tail = {}, []
+        a = 0
+        while a < opt.n:
+            b = min(opt.n, a + self.BUCKET)
+            rs = [r for (o, e, r) in ready if o < b and e > a]
+            if rs and all(r is not None for r in rs):
+                per_node.setdefault(max(max(rs), 0), []).append((a, b))
+            else:
+                tail.append((a, b))
+            a = b
+        return n_nodes, per_node, tail
+
+    def _launch(self, a, b):
+        self._work.append(dist.all_reduce(self.optimizer.flat_grad[a:b], async_op=True))
+
+    def _after_node(self, i):
+        for a, b in self.plan[1].get(i, ()):
+            self._launch(a, b)
 
     def step(self, video_list, task_id=0, prev_out_cls_logits=None):
         """video_list = this rank's share of the global batch.  Returns the loss dict of this rank (tensors)."""
@@ -61,11 +115,33 @@ class Trainer:
                 self.grads = FlatGrads(self.model.parameters())
             self.grads.zero()
             flat = self.grads.flat
+        use_plan = self.overlap and self.plan is not None
+        self.model._after_backward_node = self._after_node if use_plan else None
+        self._work = []
         losses = self.model(video_list, task_id=task_id, prev_out_cls_logits=prev_out_cls_logits or [])
-        losses["final_loss"].backward()
+        final = losses["final_loss"]
         if self.world > 1:
-            dist.all_reduce(flat)
-            flat.div_(self.world)
+            # d(mean over ranks) : scale this rank's gradient by 1 / world, the all-reduce then only sums
+            final.backward(torch.full_like(final, 1.0 / self.world))
+            if use_plan and getattr(self.model, "_last_touch", (None,))[0] == self.plan[0]:
+                for a, b in self.plan[2]:
+                    self._launch(a, b)
+                for w in self._work:
+                    w.wait()
+            else:
+                if self._work:     # the tape changed shape under an old plan: finish what was launched, redo everything
+                    for w in self._work:
+                        w.wait()
+                    raise RuntimeError("backward structure changed while a bucket plan was active; recreate the Trainer")
+                dist.all_reduce(flat)
+            if getattr(self, "keep_grad", False):
+                torch.cuda.synchronize()
+                self.last_grad = flat.clone()
+            if self.overlap and (self.plan is None or self.plan[0] != self.model._last_touch[0]):
+                self.plan = self._build_plan()
+        else:
+            final.backward()
+        self.model._after_backward_node = None
         if self.flat:
             self.optimizer.step(clip_grad_l2norm=self.clip)
         else:
@@ -108,9 +184,18 @@ def make_optimizer(model, optimizer_config, flat=False):
     decay, no_decay = decay & pd.keys(), (no_decay & pd.keys()) - decay
     remain = pd.keys() - (decay | no_decay)
     wd = optimizer_config["weight_decay"]
-    groups = [{"params": [pd[n] for n in sorted(decay)], "weight_decay": wd},
-              {"params": [pd[n] for n in sorted(no_decay)], "weight_decay": 0.0},
-              {"params": [pd[n] for n in sorted(remain)], "weight_decay": wd}]
+    # torch path: alphabetical like the reference.  flat path: reverse definition order ~ the order in which the backward
+    # pass completes the gradients, so that the trainer's all-reduce buckets become ready early (the update rule does not
+    # depend on the order)
+    pos = {n: i for i, n in enumerate(pd)}
+    from .engine import _pack_kind
+    late = lambda n: _pack_kind(n, pd[n]) in ("conv3", "dw", "xl_t") or pd[n].dim() == 0 or pd[n].dim() == 2 and pd[n].shape[1] == 1  # noqa: E731
+    # (permuted layouts, Scale scalars and mu / sigma get their gradients at the very end of the backward pass: keep them
+    # together behind the parameters whose gradients the kernels write in place)
+    order = (lambda names: sorted(names, key=lambda n: (late(n), -pos[n]))) if flat else sorted
+    groups = [{"params": [pd[n] for n in order(decay)], "weight_decay": wd},
+              {"params": [pd[n] for n in order(no_decay)], "weight_decay": 0.0},
+              {"params": [pd[n] for n in order(remain)], "weight_decay": wd}]
     groups = [g for g in groups if g["params"]]
     if optimizer_config["type"] == "SGD":
         return torch.optim.SGD(groups, lr=optimizer_config["learning_rate"], momentum=optimizer_config["momentum"])
@@ -153,7 +238,8 @@ class FlatAdamW(torch.optim.Optimizer):
         self.flat_grad = torch.zeros(n, device=dev)
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
-        self._scal = torch.zeros(3, device=dev)   # sum of squares, clip coefficient, gradient norm
+        self._scal = torch.zeros(3, device=dev)   # (unused), clip coefficient, gradient norm
+        self._partials = torch.zeros(1184, device=dev)   # VILCO_CLIP_SCRATCH per-block partial sums of squares
         self.t = 0
         self.epoch = 0           # bumped on every update; the model re-derives its permuted weight copies when it changes
         for g in self.param_groups:
@@ -199,7 +285,8 @@ class FlatAdamW(torch.optim.Optimizer):
         st = L.stream_ptr()
         s = self._scal
         L.check(L.lib().vilco_grad_clip_coef(ops._p(self.flat_grad), ops._i64(self.n), C.c_float(float(clip_grad_l2norm)),
-                                             C.c_void_p(s.data_ptr()), C.c_void_p(s.data_ptr() + 4), C.c_void_p(s.data_ptr() + 8), st),
+                                             C.c_void_p(self._partials.data_ptr()), C.c_void_p(s.data_ptr() + 4),
+                                             C.c_void_p(s.data_ptr() + 8), st),
                 "vilco_grad_clip_coef")
         NP = self.planes.shape[0]
         for a, b, g in self.segments:
