@@ -270,7 +270,7 @@ def run_train_leg(args, model, rank, world, dist, barrier, local):
     model.train()
     broadcast_parameters(model)
     opt = make_optimizer(model, {"type": "AdamW", "learning_rate": 1e-4, "weight_decay": 0.05}, flat=True)
-    tr = Trainer(model, opt, clip_grad_l2norm=1.0)
+    tr = Trainer(model, opt, clip_grad_l2norm=1.0, overlap=os.environ.get("VILCO_OVERLAP", "1") == "1")
     host_sets = [synth_videos(Bt, seed=500 + rank * 10 + i, pin=True) for i in range(2)]
     dev_set = [dict(v) for v in host_sets[0]]
     for v in dev_set:

@@ -309,3 +309,31 @@ def test_training_mode_step_runs_with_dropout_and_changes_with_the_seed():
     for k, prm in model.named_parameters():
         if k in P:
             assert prm.grad is not None and torch.isfinite(prm.grad).all(), k
+
+
+def test_flat_adamw_compaction_parks_dead_parameters():
+    """Parameters the backward never writes are moved behind the live region: like torch.optim.AdamW with .grad = None they
+    are neither updated nor decayed, and the values / moments of the live ones survive the re-layout."""
+    from vilco_b200.trainer import FlatAdamW
+    torch.manual_seed(1)
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in [(16, 8), (5,), (7, 3), (11,)]]
+    before = [p.detach().clone() for p in ps]
+    opt = FlatAdamW([{"params": ps[:3], "weight_decay": 0.1}, {"params": ps[3:], "weight_decay": 0.0}], lr=1e-2)
+    for p in ps:
+        p.grad.add_(torch.randn_like(p))
+    opt.step()
+    m_before = [opt.exp_avg[opt.slots[id(p)][0]:opt.slots[id(p)][0] + p.numel()].clone() for p in ps]
+    after1 = [p.detach().clone() for p in ps]
+    opt.compact({id(ps[1])})
+    assert opt.live_ranges()[0][1] - opt.live_ranges()[0][0] < opt.segments[0][2] - opt.segments[0][0]
+    for p, a, m in zip(ps, after1, m_before):
+        o, k = opt.slots[id(p)]
+        assert torch.equal(p.detach(), a) and torch.equal(opt.exp_avg[o:o + k], m)
+        assert p.grad.data_ptr() == opt.flat_grad[o:o + k].data_ptr()
+    opt.zero_grad()
+    for p in ps:
+        p.grad.add_(torch.randn_like(p))
+    opt.step()
+    assert torch.equal(ps[1].detach(), after1[1])                      # parked: untouched (no update, no weight decay)
+    assert all(not torch.equal(p.detach(), a) for p, a in zip([ps[0], ps[2], ps[3]], [after1[0], after1[2], after1[3]]))
+    assert all(not torch.equal(a, b) for a, b in zip(after1, before))

@@ -349,7 +349,8 @@ class PtTransformer(nn.Module):
         augment_classification) or the precision mode changed."""
         flat = getattr(self, "_flat", None)
         plist = self._param_table()[1]
-        key = (ops.precision(), tuple(p._version for p in plist), tuple(id(p) for p in plist))
+        key = (ops.precision(), tuple(p._version for p in plist), tuple(id(p) for p in plist),
+               flat.layout_version if flat is not None else 0)
         if self._packed is None or key != self._packed_key:
             if flat is not None:
                 flat.refresh_planes()

@@ -44,7 +44,7 @@ class Tape:
         self.sinks = sinks or {}
         self.touch = {}          # sink key -> index (in backward execution order) of the last node that accumulated into it
         self.cur = -1
-        self.after_node = None   # optional callback(i) after backward node i (the trainer's bucketed all-reduce)
+        self.after_node = None   # optional callback(i, n_nodes) after backward node i (the trainer's bucketed all-reduce)
         self.nodes = []
         self.p_drop, self.p_path, self.p_xl = float(dropout), float(droppath), float(xl_dropout)
         self.seed = int(seed) << 20
@@ -82,7 +82,7 @@ class Tape:
             self.cur = i
             fn()
             if self.after_node is not None:
-                self.after_node(i)
+                self.after_node(i, self.n_nodes)
         self.nodes = []
 
     # ---- operators ----

@@ -54,6 +54,7 @@ class Trainer:
         self.flat = isinstance(optimizer, FlatAdamW)
         self.overlap = bool(overlap) and self.flat and self.world > 1
         self.plan = None           # (n_nodes, {node index: [(a, b), ...]}, [(a, b) launched after the last node])
+        self._plan_nodes = None
         self._work = []
         if self.flat:
             model.use_flat_optimizer(optimizer)
@@ -61,47 +62,59 @@ class Trainer:
             self.grads = FlatGrads(model.parameters())
 
     # ---- bucketed all-reduce -------------------------------------------------------------------------------------
-    def _build_plan(self):
-        """From the last backward's record: bucket [a, b) of the flat gradient buffer is final after node max(last touch of
-        the parameters inside it); parameters that took the fallback path (permuted layouts, glue) are final at the end."""
-        last = getattr(self.model, "_last_touch", None)
-        if last is None:
-            return None
-        n_nodes, touch, fallback = last
+    def _readiness(self):
+        """{id(param): node index after which its gradient is final | None (only at the very end) | -1 (dead: never written)}
+        from the record of the last backward pass."""
+        n_nodes, touch, fallback = self.model._last_touch
         opt = self.optimizer
         names = {id(p): k for k, p in self.model.named_parameters()}
-        ready = []                                     # (offset, end, node index; None = only final after the whole backward)
+        out = {}
         for g in opt.param_groups:
             for p in g["params"]:
                 if id(p) in opt.slots:
                     o, k = opt.slots[id(p)]
                     key = names.get(id(p))
                     if key in fallback:
-                        r = None
+                        out[id(p)] = None
                     elif key in touch:
-                        r = touch[key]
+                        out[id(p)] = touch[key]
                     elif bool((opt.flat_grad[o:o + k] != 0).any()):
-                        r = None                       # written by torch autograd of the glue (mu / sigma, prompts)
+                        out[id(p)] = None              # written by torch autograd of the glue (mu / sigma, prompts)
                     else:
-                        r = -1                         # dead parameter: its gradient is the zero it was reset to
-                    ready.append((o, o + k, r))
-        ready.sort()
+                        out[id(p)] = -1
+        return out
+
+    def _build_plan(self, ready):
+        """Bucket [a, b) of the live part of the flat gradient buffer is final after node max(last touch of the parameters
+        inside it); parameters that took the fallback path (permuted layouts, glue) are final at the end."""
+        opt = self.optimizer
+        spans = sorted((opt.slots[i][0], opt.slots[i][0] + opt.slots[i][1], r) for i, r in ready.items())
         per_node, tail = {}, []
-        a = 0
-        while a < opt.n:
-            b = min(opt.n, a + self.BUCKET)
-            rs = [r for (o, e, r) in ready if o < b and e > a]
-            if rs and all(r is not None for r in rs):
-                per_node.setdefault(max(max(rs), 0), []).append((a, b))
-            else:
-                tail.append((a, b))
-            a = b
-        return n_nodes, per_node, tail
+        for lo_, hi_ in opt.live_ranges():
+            a = lo_
+            while a < hi_:
+                b = min(hi_, a + self.BUCKET)
+                rs = [r for (o, e, r) in spans if o < b and e > a]
+                if rs and all(r is not None for r in rs):
+                    per_node.setdefault(max(max(rs), 0), []).append((a, b))
+                else:
+                    tail.append((a, b))
+                a = b
+        return self.model._last_touch[0], per_node, tail
+
+    def _named(self):
+        tab = getattr(self.model, "_param_table", None)
+        if tab is not None:
+            names, plist, _ = tab()
+            return zip(names, plist)
+        return self.model.named_parameters()
 
     def _launch(self, a, b):
         self._work.append(dist.all_reduce(self.optimizer.flat_grad[a:b], async_op=True))
 
-    def _after_node(self, i):
+    def _after_node(self, i, n_nodes):
+        if n_nodes != self.plan[0]:      # the tape changed shape (e.g. model.train() <-> eval()): fall back for this step
+            return
         for a, b in self.plan[1].get(i, ()):
             self._launch(a, b)
 
@@ -123,24 +136,34 @@ class Trainer:
         if self.world > 1:
             # d(mean over ranks) : scale this rank's gradient by 1 / world, the all-reduce then only sums
             final.backward(torch.full_like(final, 1.0 / self.world))
-            if use_plan and getattr(self.model, "_last_touch", (None,))[0] == self.plan[0]:
+        else:
+            final.backward()
+        touched_dead = self.flat and self.optimizer.dead and any(
+            id(p) in self.optimizer.dead for k, p in self._named() if k in self.model._last_touch[1])
+        if self.world > 1:
+            if use_plan and self.model._last_touch[0] == self.plan[0]:
                 for a, b in self.plan[2]:
                     self._launch(a, b)
+                if touched_dead:         # a parameter parked as dead received a gradient: reduce the parked regions too
+                    for _, le, e, _ in self.optimizer.segments:
+                        if e > le:
+                            self._launch(le, e)
                 for w in self._work:
                     w.wait()
             else:
-                if self._work:     # the tape changed shape under an old plan: finish what was launched, redo everything
-                    for w in self._work:
-                        w.wait()
-                    raise RuntimeError("backward structure changed while a bucket plan was active; recreate the Trainer")
+                assert not self._work
                 dist.all_reduce(flat)
             if getattr(self, "keep_grad", False):
                 torch.cuda.synchronize()
                 self.last_grad = flat.clone()
-            if self.overlap and (self.plan is None or self.plan[0] != self.model._last_touch[0]):
-                self.plan = self._build_plan()
-        else:
-            final.backward()
+        if self.flat and hasattr(self.model, "_last_touch") and \
+                (self._plan_nodes != self.model._last_touch[0] or touched_dead):
+            # first step (or the tape changed): find the parameters the backward never writes, move them out of the updated /
+            # all-reduced region, and plan the buckets over the new layout
+            ready = self._readiness()
+            self.optimizer.compact({i for i, r in ready.items() if r == -1})
+            self._plan_nodes = self.model._last_touch[0]
+            self.plan = self._build_plan(ready) if self.overlap else None
         self.model._after_backward_node = None
         if self.flat:
             self.optimizer.step(clip_grad_l2norm=self.clip)
@@ -218,40 +241,72 @@ class FlatAdamW(torch.optim.Optimizer):
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        from . import ops
-        seen, n = set(), 0
-        self.slots = {}          # id(param) -> (offset, numel)
-        self.segments = []       # (start, end, group)
-        for g in self.param_groups:
-            start = n
-            for p in g["params"]:
-                if not p.requires_grad or id(p) in seen:
-                    continue
-                seen.add(id(p))
-                self.slots[id(p)] = (n, p.numel())
-                n = (n + p.numel() + 7) // 8 * 8
-            self.segments.append((start, n, g))
         dev = next(p for g in self.param_groups for p in g["params"]).device
         assert dev.type == "cuda", "FlatAdamW runs on the CUDA kernels only"
-        self.n = n
-        self.flat_p = torch.zeros(n, device=dev)
-        self.flat_grad = torch.zeros(n, device=dev)
-        self.exp_avg = torch.zeros(n, device=dev)
-        self.exp_avg_sq = torch.zeros(n, device=dev)
+        self.device = dev
+        self.slots = None        # id(param) -> (offset, numel)
+        self.segments = []       # (start, live_end, end, group): [start, live_end) is updated, [live_end, end) holds dead parameters
+        self.dead = set()
+        self.layout_version = 0
         self._scal = torch.zeros(3, device=dev)   # (unused), clip coefficient, gradient norm
         self._partials = torch.zeros(1184, device=dev)   # VILCO_CLIP_SCRATCH per-block partial sums of squares
         self.t = 0
         self.epoch = 0           # bumped on every update; the model re-derives its permuted weight copies when it changes
-        for g in self.param_groups:
-            for p in g["params"]:
-                if id(p) in self.slots:
-                    o, k = self.slots[id(p)]
-                    self.flat_p[o:o + k].copy_(p.data.reshape(-1))
-                    p.data = self.flat_p[o:o + k].view(p.shape)
-                    p.grad = self.flat_grad[o:o + k].view(p.shape)
         self.planes = None
         self._planes_precision = None
+        self._layout(set())
+
+    def _layout(self, dead):
+        """(Re)build the flat buffers: per parameter group the live parameters first, then the dead ones (parameters the
+        backward pass never writes — torch.optim.AdamW skips those because their .grad stays None; here they sit behind
+        `live_end` and are neither updated, decayed nor all-reduced).  Existing values / moments are carried over."""
+        old_slots = self.slots
+        old = (self.flat_p, self.flat_grad, self.exp_avg, self.exp_avg_sq) if old_slots is not None else None
+        seen, n, slots, segments = set(), 0, {}, []
+        for g in self.param_groups:
+            start = n
+            ps = []
+            for p in g["params"]:
+                if p.requires_grad and id(p) not in seen:
+                    seen.add(id(p))
+                    ps.append(p)
+            for p in ps:
+                if id(p) not in dead:
+                    slots[id(p)] = (n, p.numel())
+                    n = (n + p.numel() + 7) // 8 * 8
+            live_end = n
+            for p in ps:
+                if id(p) in dead:
+                    slots[id(p)] = (n, p.numel())
+                    n = (n + p.numel() + 7) // 8 * 8
+            segments.append((start, live_end, n, g))
+        new = [torch.zeros(n, device=self.device) for _ in range(4)]
+        with torch.no_grad():
+            for g in self.param_groups:
+                for p in g["params"]:
+                    if id(p) not in slots:
+                        continue
+                    o, k = slots[id(p)]
+                    if old is None:
+                        new[0][o:o + k].copy_(p.data.reshape(-1))
+                    else:
+                        oo, _ = old_slots[id(p)]
+                        for dst, src in zip(new, old):
+                            dst[o:o + k].copy_(src[oo:oo + k])
+                    p.data = new[0][o:o + k].view(p.shape)
+                    p.grad = new[1][o:o + k].view(p.shape)
+        self.flat_p, self.flat_grad, self.exp_avg, self.exp_avg_sq = new
+        self.n, self.slots, self.segments, self.dead = n, slots, segments, set(dead)
+        self.layout_version += 1
         self.refresh_planes()
+
+    def compact(self, dead_ids):
+        """Move the given parameters (ids) behind the live region of their group."""
+        if set(dead_ids) != self.dead:
+            self._layout(set(dead_ids))
+
+    def live_ranges(self):
+        return [(a, le) for a, le, _, _ in self.segments if le > a]
 
     def refresh_planes(self):
         """(PLANES, n) bf16 hi / lo copies of every parameter (needed after load_state_dict or a precision switch; the
@@ -289,7 +344,7 @@ class FlatAdamW(torch.optim.Optimizer):
                                              C.c_void_p(s.data_ptr() + 8), st),
                 "vilco_grad_clip_coef")
         NP = self.planes.shape[0]
-        for a, b, g in self.segments:
+        for a, b, _, g in self.segments:
             if b <= a:
                 continue
             L.check(L.lib().vilco_adamw(
