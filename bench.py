@@ -311,7 +311,9 @@ def run_train_leg(args, model, rank, world, dist, barrier, local):
             "step": "zero_grad, forward (dropout 0.1, drop-path 0.1, XLNet dropout 0.1), focal + DIoU + label-involved loss, "
                     "hand-written backward, " + ("NCCL all-reduce of one flat fp32 gradient buffer, " if world > 1 else "") +
                     "clip_grad_norm 1.0, fused flat AdamW (lr 1e-4, wd 0.05)",
-            "grad_bytes_allreduced_per_step": int(opt.n * 4) if world > 1 else 0, "last_loss": last, "peak_mem_gib": mem,
+            "grad_bytes_allreduced_per_step": int(4 * sum(b - a for a, b in opt.live_ranges())) if world > 1 else 0,
+            "allreduce": ("bucketed (128 MB), launched as the backward completes each bucket" if tr.overlap else "one call after the backward") if world > 1 else None,
+            "live_parameters": int(sum(b - a for a, b in opt.live_ranges())), "all_parameters": int(opt.n), "last_loss": last, "peak_mem_gib": mem,
             "clocks": sampler.summary()}
 
 
