@@ -337,3 +337,28 @@ def test_flat_adamw_compaction_parks_dead_parameters():
     assert torch.equal(ps[1].detach(), after1[1])                      # parked: untouched (no update, no weight decay)
     assert all(not torch.equal(p.detach(), a) for p, a in zip([ps[0], ps[2], ps[3]], [after1[0], after1[2], after1[3]]))
     assert all(not torch.equal(a, b) for a, b in zip(after1, before))
+
+
+def test_fast_bf16_backward_mode_is_bounded():
+    """VILCO_BWD_PRECISION=bf16: backward GEMMs read one bf16 plane per operand.  Forward / losses are unchanged;
+    gradients stay within a few 1e-3 (relative L2) of the split-precision ones."""
+    from vilco_b200 import ops
+    cfg, model, videos, Pg, lo_, out = _model_grads()
+    ref = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    ref_loss = float(out["final_loss"].detach())
+    old = ops.BWD_PRECISION
+    ops.BWD_PRECISION = "bf16"
+    try:
+        model.zero_grad()
+        model.loss_normalizer = cfg.init_loss_norm
+        out2 = model(videos, is_training=True)
+        out2["final_loss"].backward()
+    finally:
+        ops.BWD_PRECISION = old
+    assert abs(float(out2["final_loss"].detach()) - ref_loss) <= 1e-6 * ref_loss     # same forward (sums use float atomics)
+    gmax = max(float(g.abs().max()) for g in ref.values())
+    errs = []
+    for k, p in model.named_parameters():
+        if k in ref and float(ref[k].abs().max()) > 1e-6 * gmax:
+            errs.append(float((p.grad - ref[k]).norm() / ref[k].norm()))
+    assert max(errs) < 5e-2 and float(np.median(errs)) < 1e-2, (max(errs), float(np.median(errs)))

@@ -41,9 +41,28 @@ def _i64(v):
     return C.c_int64(int(v))
 
 
+# Optional fast training mode: the backward GEMMs read only the hi plane of every operand (one tcgen05.mma per k-step instead of
+# three).  Gradients then carry plain-bf16 operand rounding (~3e-3 relative, what bf16 autocast training has); the forward
+# pass, the losses and therefore every parity statement about outputs are unaffected.  Default: full split precision.
+BWD_PRECISION = os.environ.get("VILCO_BWD_PRECISION", "bf16x3")
+_single = False
+
+
+class single_plane:
+    """context: operand tensors are treated as single-plane (lo() == 0) for everything launched inside"""
+
+    def __enter__(self):
+        global _single
+        self.prev, _single = _single, True
+
+    def __exit__(self, *a):
+        global _single
+        _single = self.prev
+
+
 def lo(t):
     """element offset of the lo plane of an operand tensor (0 when single-plane)."""
-    return t.stride(0) if t.shape[0] == 2 else 0
+    return t.stride(0) if (t.shape[0] == 2 and not _single) else 0
 
 
 def empty16(*shape, device="cuda"):

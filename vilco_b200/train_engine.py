@@ -77,6 +77,9 @@ class Tape:
         return t
 
     def backward(self):
+        if ops.BWD_PRECISION == "bf16" and not ops._single:
+            with ops.single_plane():
+                return self.backward()
         self.n_nodes = len(self.nodes)
         for i, fn in enumerate(reversed(self.nodes)):
             self.cur = i
