@@ -29,6 +29,15 @@ def vilco_cfg():
                       adapt_blocks=(0, 1, 2, 3, 4), n_emas=1, prompt_pool=dict(pool_size=10, top_k=4, length=20))
 
 
+def vilco_train_cfg():
+    """mq_vilco.yaml training at reduced depth: prompts + adapters + narration SSL need C = 1024 (narration_encoder output,
+    meta_archs.py:650) and T = 1024 (adapter sizes, :687)."""
+    return O.ModelCfg(input_dim=64, embd_dim=1024, n_head=16, max_seq_len=1024, arch=(2, 1, 5), num_classes=6, n_txt_in=96,
+                      regression_range=[[0, 4], [2, 8], [4, 16], [8, 32], [16, 64], [32, 10000]],
+                      adapt_blocks=(0, 1, 2, 3, 4), n_emas=1, prompt_pool=dict(pool_size=10, top_k=4, length=20),
+                      narration_dim=32)
+
+
 def _override(c):
     def ov(cfg):
         cfg["dataset"]["input_dim"] = [c.input_dim]
@@ -47,6 +56,11 @@ def _override(c):
                                  length=c.prompt_pool["length"], embed_dim=c.n_txt_in)
         if c.adapt_blocks:
             cfg["cl_cfg"].update(use_adapt=True, adapt_blocks=list(c.adapt_blocks))
+        if getattr(c, "narration_dim", 0):
+            cfg["cl_cfg"].update(narration_ssl=True, narration_dim=c.narration_dim, memory_size=48, ssl_factor=0.01)
+            cfg["train_cfg"].update(dropout=0.0, droppath=1e-12)   # deterministic (keep_prob rounds to 1.0) but keeps AffineDropPath; the SSL branch needs model.train()
+        else:
+            cfg["cl_cfg"].update(narration_ssl=False)
     return ov
 
 
@@ -117,6 +131,51 @@ def gen_grad_golden():
             out["g:" + k] = np.concatenate([[g.norm().item(), g.sum().item()], g[:8].numpy()]).astype(np.float64)
     np.savez_compressed(os.path.join(GOLDEN, "grads_small.npz"), **out)
     print("grads_small:", len(out) - 1, "parameters")
+
+
+def narration_inputs(c, videos, seed=9):
+    """narration_feats (narration_dim, Ln) / narration_mask per video (schema ego4d.py:820-837), seeded."""
+    rs = np.random.RandomState(seed)
+    for i, v in enumerate(videos):
+        ln = int(rs.randint(2, 9))
+        v["narration_feats"] = torch.from_numpy(rs.standard_normal((c.narration_dim, ln)).astype(np.float32))
+        v["narration_mask"] = 1.0 if i != 1 else 0.0        # one clip without narration
+    return videos
+
+
+def seeded_memory_bank(size, dim, seed=17):
+    m = np.random.RandomState(seed).standard_normal((size, dim)).astype(np.float32)
+    return torch.from_numpy(m / np.linalg.norm(m, axis=1, keepdims=True))
+
+
+def gen_vilco_train_golden():
+    """One training forward / backward of the mq_vilco branches in the REFERENCE (model.train(), every dropout p = 0): L2P
+    prompts selected by task id + pull constraint (n_known > 0), temporal adapters, narration SSL with a seeded memory
+    bank.  Stored: the losses and, per parameter, L2 norm / sum / first 8 entries of d final_loss / d parameter."""
+    c = vilco_train_cfg()
+    model, _ = build_reference_model(c, seed=2, yaml_name="mq_vilco.yaml")
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model.train()
+    model.n_known = 1
+    model.memory_bank.memory = seeded_memory_bank(48, 1024)
+    model.memory_bank.ptr = 0
+    videos = narration_inputs(c, PR.synth_video_list(c, 3, seed=6, lens=[1024, 900, 700], text_lens=[40, 57, 33], n_gt=[3, 2, 4]))
+    model.loss_normalizer = c.init_loss_norm
+    model.zero_grad()
+    losses = model(videos, task_id=1, is_training=True)
+    losses["final_loss"].backward()
+    out = {"loss_" + k: np.float32(v.detach().reshape(-1)[0].item()) for k, v in losses.items()}
+    n = 0
+    for k, p_ in model.named_parameters():
+        if p_.grad is not None and ".adapters." not in k:
+            g = p_.grad.detach().reshape(-1).double()
+            out["g:" + k] = np.concatenate([[g.norm().item(), g.sum().item()], g[:8].numpy()]).astype(np.float64)
+            n += 1
+    out["memory_after"] = model.memory_bank.memory[:4].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "train_vilco.npz"), **out)
+    print("train_vilco:", {k: float(v) for k, v in out.items() if k.startswith("loss_")}, n, "parameter gradients")
 
 
 def gen_vilco_golden():
@@ -215,3 +274,5 @@ if __name__ == "__main__":
         gen_vilco_golden()
     if "grads" in what:
         gen_grad_golden()
+    if "vilco_train" in what:
+        gen_vilco_train_golden()

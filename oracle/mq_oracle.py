@@ -272,6 +272,7 @@ class ModelCfg:
         self.adapt_blocks = ()  # vilco: (0,1,2,3,4)
         self.prompt_pool = None  # vilco: dict(pool_size=10, top_k=4, length=20)
         self.n_emas = 0          # vilco: 1 (EMA copy of the adapters, ensembled at inference)
+        self.narration_dim = 0   # vilco training: 512 (narration SSL branch; only the parameter spec uses it here)
         for k, v in kw.items():
             assert hasattr(self, k), k
             setattr(self, k, v)

@@ -106,6 +106,9 @@ def param_spec(cfg):
             s[f"{pre}{j}.layer.0.bias"] = (5 * T,)
             s[f"{pre}{j}.layer.2.weight"] = (T // 2, 5 * T)
             s[f"{pre}{j}.layer.2.bias"] = (T // 2,)
+    if getattr(cfg, "narration_dim", 0):      # narration SSL branch (meta_archs.py:650-652): Linear(narration_dim, 1024)
+        s["narration_encoder.weight"] = (1024, cfg.narration_dim)
+        s["narration_encoder.bias"] = (1024,)
     if getattr(cfg, "prompt_pool", None):
         pp = cfg.prompt_pool
         s["prompt.prompt"] = (pp["pool_size"], pp["length"], cfg.n_txt_in)

@@ -362,3 +362,46 @@ def test_fast_bf16_backward_mode_is_bounded():
         if k in ref and float(ref[k].abs().max()) > 1e-6 * gmax:
             errs.append(float((p.grad - ref[k]).norm() / ref[k].norm()))
     assert max(errs) < 5e-2 and float(np.median(errs)) < 1e-2, (max(errs), float(np.median(errs)))
+
+
+def test_vilco_training_step_matches_reference_golden():
+    """mq_vilco.yaml training branches — L2P prompts chosen by task id + pull constraint, temporal adapters, narration SSL
+    with a memory bank — against losses and gradients produced by the REFERENCE itself (tests/golden/train_vilco.npz)."""
+    import os
+    from conftest import GOLDEN
+    from util import build_vilco_train_pair
+    g = np.load(os.path.join(GOLDEN, "train_vilco.npz"))
+    cfg = GG.vilco_train_cfg()
+    model, P = build_vilco_train_pair(cfg)
+    model.train()
+    model.n_known = 1
+    model.memory_bank.memory = GG.seeded_memory_bank(48, 1024).cuda()
+    model.memory_bank.ptr = 0
+    videos = GG.narration_inputs(cfg, PR.synth_video_list(cfg, 3, seed=6, lens=[1024, 900, 700], text_lens=[40, 57, 33],
+                                                           n_gt=[3, 2, 4]))
+    model.loss_normalizer = cfg.init_loss_norm
+    out = model(videos, task_id=1, is_training=True)
+    out["final_loss"].backward()
+    for k in ("cls_loss", "reg_loss", "al_loss", "ssl_loss", "final_loss"):
+        ref = float(g["loss_" + k])
+        assert abs(float(out[k].detach()) - ref) <= 1e-3 * abs(ref) + 1e-6, (k, float(out[k].detach()), ref)
+    assert rel_max(model.memory_bank.memory[:4], g["memory_after"]) < 1e-4
+    named = dict(model.named_parameters())
+    gmax = max(float(g[k][0]) for k in g.files if k.startswith("g:"))
+    strict = ("cls_head.cls_head", "reg_head.offset_head", "mu", "sigma", "narration_encoder", "prompt.")
+    n = 0
+    for key in g.files:
+        if not key.startswith("g:"):
+            continue
+        ref = g[key]
+        p = named[key[2:]]
+        if ref[0] < 1e-6 * gmax:
+            continue
+        assert p.grad is not None, key
+        mine = p.grad.detach().reshape(-1).double().cpu()
+        got = np.concatenate([[mine.norm().item(), mine.sum().item()], mine[:8].numpy()])
+        tol = 1e-3 if key[2:].startswith(strict) else 5e-2     # (ReLU gate flips perturb everything below them, see above)
+        assert abs(got[0] - ref[0]) <= tol * ref[0], (key, got[0], ref[0])
+        assert np.abs(got[2:] - ref[2:]).max() <= tol * ref[0] + 1e-7, (key, got[2:4], ref[2:4])
+        n += 1
+    assert n > 250

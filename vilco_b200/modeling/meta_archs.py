@@ -107,13 +107,43 @@ class Prompt(nn.Module):
                 idx = prompt_id[major_idx].expand(x_embed.shape[0], -1)
         else:
             idx = prompt_mask.cpu()
-        prompt_norm, x_norm, similarity, idx = prompt_norm.to(dev), x_norm.to(dev), similarity.to(dev), idx.to(dev)
+        similarity, idx = similarity.to(dev), idx.to(dev)
         batched_prompt = self.prompt[idx].reshape(x_embed.shape[0], -1, x_embed.shape[2])
         out["prompt_idx"], out["similarity"] = idx, similarity
-        out["reduce_sim"] = torch.sum(prompt_norm[idx] * x_norm.unsqueeze(1)) / x_embed.shape[0]
+        # the pull-constraint term is differentiable w.r.t. the prompt keys: recomputed on the device with autograd
+        pn = self.l2_normalize(self.prompt_key, dim=1)
+        xn = self.l2_normalize(torch.mean(x_embed, dim=1), dim=1)
+        out["reduce_sim"] = torch.sum(pn[idx] * xn.unsqueeze(1)) / x_embed.shape[0]
         out["total_prompt_len"] = batched_prompt.shape[1]
         out["prompted_embedding"] = torch.cat([batched_prompt, x_embed], dim=1)
         return out
+
+
+class MemoryBank:
+    """FIFO of normalised narration embeddings used as negatives by the narration SSL term (meta_archs.py:38-60); lives on
+    the device of the features it is first updated with."""
+
+    def __init__(self, size, feature_dim):
+        self.size, self.feature_dim = size, feature_dim
+        self.memory = torch.randn(size, feature_dim)
+        self.ptr = 0
+
+    @torch.no_grad()
+    def update(self, features):
+        self.memory = self.memory.to(features.device)
+        n = features.size(0)
+        assert n <= self.size, "Batch size must be less than or equal to memory bank size"
+        if self.ptr + n <= self.size:
+            self.memory[self.ptr:self.ptr + n] = features
+            self.ptr += n
+        else:
+            overflow = (self.ptr + n) - self.size
+            self.memory[self.ptr:] = features[:self.size - self.ptr]
+            self.memory[:overflow] = features[self.size - self.ptr:]
+            self.ptr = overflow
+
+    def get_all(self):
+        return self.memory
 
 
 class _TapeLoss(torch.autograd.Function):
@@ -266,6 +296,7 @@ class PtTransformer(nn.Module):
         self.narration_dim = cl_cfg["narration_dim"]
         if self.narration_ssl:   # training-only branch; the parameters exist so checkpoints load (meta_archs.py:650-655)
             self.narration_encoder = nn.Linear(cl_cfg["narration_dim"], 1024)
+            self.memory_bank = MemoryBank(cl_cfg["memory_size"], 1024)
         self.ssl_factor = cl_cfg["ssl_factor"]
         self.num_emas, self.ema_decay = 1, 0.999
         self.use_adapt = cl_cfg["use_adapt"]
@@ -564,7 +595,8 @@ class PtTransformer(nn.Module):
         self._train_calls = getattr(self, "_train_calls", 0) + 1
         sinks = self._grad_sinks()
         if self.training:
-            tp = TE.Tape(W, dropout=self.train_dropout, droppath=self.train_droppath, xl_dropout=0.1 if self.use_xl else 0.0,
+            tp = TE.Tape(W, dropout=self.train_dropout, droppath=self.train_droppath,
+                         xl_dropout=getattr(self, "xl_dropout", 0.1) if self.use_xl else 0.0,   # xlnet_config_*.json: 0.1
                          seed=(int(torch.initial_seed()) & 0xFFFFF) * 4096 + self._train_calls, sinks=sinks)
         else:
             tp = TE.Tape(W, sinks=sinks)
@@ -575,8 +607,17 @@ class PtTransformer(nn.Module):
             feats, masks, tin = TE.backbone(tp, cfg, x16, mask.contiguous(), t16, tmask, self._pe)
             if tin is not None and not text.requires_grad:
                 tin.const = True
-            logitsV, offsetsV, pmask, pyr = TE.neck_heads(tp, cfg, feats, masks)
+            logitsV, offsetsV, pmask, pyr, fpn_lv = TE.neck_heads(tp, cfg, feats, masks)
             logits, offsets = logitsV.v, offsetsV.v
+        # torch-side loss terms of the mq_vilco branches (tiny; their autograd runs inside run_backward):
+        extra, extra_named, ssl_leaves = [], {}, None
+        if self.training and self.narration_ssl and self.use_cross_modal:
+            ssl_term, ssl_leaves = self._narration_ssl(vl, fpn_lv, masks)
+            if ssl_term is not None:
+                extra.append(ssl_term)
+                extra_named["ssl_loss"] = ssl_term.detach()
+        if self.n_known > 0 and self.cl_name == "l2p" and self._reduce_sim is not None:
+            extra.append(-0.1 * self._reduce_sim)         # pull constraint of L2P (meta_archs.py:1478-1480)
         B, P, K = logits.shape
         gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
         with torch.no_grad():
@@ -603,6 +644,8 @@ class PtTransformer(nn.Module):
             w_reg = self.train_loss_weight if self.train_loss_weight > 0 else float(s[0] / norm) / max(float(s[1] / norm), 0.01)
             w_al = self.al_loss_weight if K != 1 else 0.0
             final = cls_loss + reg_loss * w_reg + al_loss * w_al
+            for t_ in extra:
+                final = final + t_.detach()
         names_, plist_, _ = self._param_table()
         named = dict(zip(names_, plist_))
         model = self
@@ -618,6 +661,13 @@ class PtTransformer(nn.Module):
                     ops._p(doffsets), ops._p(dwc), ops._p(dwl), ops._p(dwr), L.stream_ptr()), "vilco_mq_losses_bwd")
                 logitsV.g, offsetsV.g = dlogits, doffsets
                 model._last_head_grads = (dlogits, doffsets, pyr)   # kept for the gradient parity tests
+            if extra:
+                torch.autograd.backward(extra, [torch.full_like(t_, gscale) for t_ in extra])
+                if ssl_leaves is not None:
+                    for f_, leaf in zip(fpn_lv, ssl_leaves):
+                        if leaf.grad is not None:
+                            tp.acc(f_, leaf.grad)
+            with torch.no_grad():
                 tp.backward()
                 model._last_touch = (tp.n_nodes, dict(tp.touch), set(tp.G.keys()))
                 for key, g in tp.G.items():
@@ -637,7 +687,46 @@ class PtTransformer(nn.Module):
 
         hook = torch.zeros((), device=dev, requires_grad=True)
         final_t = _TapeLoss.apply(hook, final, run_backward)
-        return {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final_t}
+        out = {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final_t}
+        out.update(extra_named)
+        return out
+
+    def _narration_ssl(self, vl, fpn_lv, masks):
+        """Narration self-supervision of mq_vilco (meta_archs.py:794-811, 939-945, 1351-1372): masked-mean narration
+        embedding vs the masked-mean video embedding averaged over the pyramid levels, InfoNCE against a memory bank.
+        Small torch expressions on leaves cut from the tape; returns (ssl_factor * loss or None, leaves)."""
+        dev = self.device
+        nf = [x["narration_feats"] for x in vl]
+        lens = torch.as_tensor([f.shape[-1] for f in nf])
+        nb = torch.zeros(len(nf), nf[0].shape[0], int(lens.max()))
+        for i, f in enumerate(nf):
+            nb[i, :, :f.shape[-1]].copy_(f)
+        m0 = torch.tensor([float(x["narration_mask"]) for x in vl]).to(dev)
+        m1 = (torch.arange(int(lens.max()))[None, :] < lens[:, None]).unsqueeze(1).to(dev)
+        leaves = [f.v.detach().requires_grad_(True) for f in fpn_lv]
+        if not bool(m0.sum() > 0):
+            return None, leaves
+        with torch.enable_grad():
+            n = self.narration_encoder(nb.to(dev).permute(0, 2, 1)).permute(0, 2, 1) * m1          # (B,1024,Ln)
+            cnt = m1.sum(dim=2, dtype=torch.float)
+            cnt[cnt == 0.] = 1.
+            n = F.normalize(n.sum(dim=2) / cnt, dim=1)
+            vfs = []
+            for leaf, mk in zip(leaves, masks):                                                      # leaf (B,T_l,C), mk (B,T_l)
+                c_ = mk.sum(dim=1, keepdim=True)
+                c_ = torch.where(c_ == 0, torch.ones_like(c_), c_)
+                vfs.append((leaf * mk[:, :, None]).sum(dim=1) / c_)
+            v = F.normalize(torch.stack(vfs).mean(dim=0), dim=1)
+            sel = m0.to(torch.bool)
+            self.memory_bank.update(n[sel])
+            t_, v_ = n[sel], v[sel]
+            pos = torch.einsum("nc,nc->n", [t_, v_]).unsqueeze(-1)
+            mem = self.memory_bank.get_all()
+            lt = torch.cat([pos, t_ @ mem.T], dim=1) / 0.07
+            lv_ = torch.cat([pos, v_ @ mem.T], dim=1) / 0.07
+            lab = torch.zeros(t_.size(0), dtype=torch.long, device=dev)
+            ssl = (F.cross_entropy(lt, lab) + F.cross_entropy(lv_, lab)) / 2
+        return self.ssl_factor * ssl, leaves
 
     # ---- targets + losses (reference: meta_archs.py:1224-1344, 1374-1524) --------------------------------
     def _label_points(self, pyr, gt_segments, gt_labels):

@@ -567,7 +567,7 @@ def neck_heads(tp, cfg, feats, masks):
                     tp.accp(f"reg_head.scale.{l}.scale", r[lvl_of_row == l].sum().reshape(1))
             tp.nodes.append(sc_bwd)
             outs.append(tp.relu(s))
-    return outs[0], outs[1], pmask, pyr
+    return outs[0], outs[1], pmask, pyr, lv
 
 
 # ----------------------------------------------------------------------------------------------------
