@@ -15,12 +15,26 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     prof = os.environ.get("TRAIN_PROF")
-    model = bench.build_model().cuda().train()
+    if os.environ.get("VILCO_CFG") == "vilco":      # mq_vilco.yaml: L2P prompts + temporal adapters (+EMA) + narration SSL
+        import numpy as np
+        from vilco_b200.config import mq_model_kwargs
+        from vilco_b200.modeling import make_meta_arch
+        kw = mq_model_kwargs(num_classes=22)
+        kw["cl_cfg"].update(name="l2p", memory_size=1010, prompt_pool=True, pool_size=10, topk=4, length=20, embed_dim=768,
+                            narration_ssl=True, narration_dim=512, ssl_factor=0.01, use_adapt=True, adapt_blocks=[0, 1, 2, 3, 4])
+        torch.manual_seed(0)
+        model = make_meta_arch("LocPointTransformer", **kw).cuda().train()
+    else:
+        model = bench.build_model().cuda().train()
     opt = make_optimizer(model, {"type": "AdamW", "learning_rate": 1e-4, "weight_decay": 0.05}, flat=os.environ.get("FLAT", "1") == "1")
     tr = Trainer(model, opt, clip_grad_l2norm=1.0)
     vids = bench.synth_videos(B, seed=0)
-    for v in vids:
+    for i, v in enumerate(vids):
         v["feats"] = v["feats"].cuda()
+        if os.environ.get("VILCO_CFG") == "vilco":
+            rs = np.random.RandomState(i)
+            v["narration_feats"] = torch.from_numpy(rs.standard_normal((512, int(rs.randint(1, 17)))).astype(np.float32))
+            v["narration_mask"] = float(rs.rand() < 0.7)
     for i in range(2):
         lo = tr.step(vids)
     torch.cuda.synchronize()

@@ -377,21 +377,35 @@ class PtTransformer(nn.Module):
 
     def packed_weights(self):
         """bf16 operand copies of the parameters, re-packed whenever a parameter changed (optimizer step, load_state_dict,
-        augment_classification) or the precision mode changed."""
+        augment_classification) or the precision mode changed.  The EMA copies of the adapters change after every training
+        step (`post_train_step`) but are small: they are re-packed on their own."""
         flat = getattr(self, "_flat", None)
-        plist = self._param_table()[1]
-        key = (ops.precision(), tuple(p._version for p in plist), tuple(id(p) for p in plist),
+        names, plist, _ = self._param_table()
+        ema = getattr(self, "_ema_idx", None)
+        if ema is None or len(ema[0]) + len(ema[1]) != len(names):
+            ema = self._ema_idx = ([i for i, k in enumerate(names) if not k.startswith("pets_emas.")],
+                                   [i for i, k in enumerate(names) if k.startswith("pets_emas.")])
+        key = (ops.precision(), tuple(plist[i]._version for i in ema[0]), tuple(id(p) for p in plist),
                flat.layout_version if flat is not None else 0)
+        ema_key = tuple(plist[i]._version for i in ema[1])
         if self._packed is None or key != self._packed_key:
             if flat is not None:
                 flat.refresh_planes()
-            self._packed = E.pack_weights(self.state_dict(), self.device, flat, dict(self.named_parameters()) if flat is not None else None)
+            self._packed = E.pack_weights(self.state_dict(), self.device, flat, dict(zip(names, plist)) if flat is not None else None)
             self._packed_key = key
+            self._packed_ema_key = ema_key
             self._packed_epoch = flat.epoch if flat is not None else 0
             self._pe = E.sinusoid_pe_table(self.max_seq_len, self.embd_dim, self.device)
-        elif flat is not None and self._packed_epoch != flat.epoch:
-            E.refresh_packed(self._packed)
-            self._packed_epoch = flat.epoch
+        else:
+            if flat is not None and self._packed_epoch != flat.epoch:
+                E.refresh_packed(self._packed)
+                self._packed_epoch = flat.epoch
+            if ema_key != self._packed_ema_key:
+                for i in ema[1]:
+                    k, p = names[i], plist[i]
+                    self._packed[k] = E._pack_one(E._pack_kind(k, p), p.detach().to(dtype=torch.float32))
+                self._packed["_cache"] = {}
+                self._packed_ema_key = ema_key
         return self._packed
 
     # ---- preprocessing (reference: meta_archs.py:1134-1221) -------------------------------------------
