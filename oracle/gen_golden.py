@@ -178,6 +178,50 @@ def gen_vilco_train_golden():
     print("train_vilco:", {k: float(v) for k, v in out.items() if k.startswith("loss_")}, n, "parameter gradients")
 
 
+def prev_logits(c, seed=4, probs=False):
+    """per-level (T_l, K) arrays standing in for the previous task's recorded classification outputs"""
+    rs = np.random.RandomState(seed)
+    out = []
+    for l in range(c.n_levels):
+        a = rs.standard_normal((c.max_seq_len >> l, c.num_classes)).astype(np.float32)
+        out.append(1.0 / (1.0 + np.exp(-a)) if probs else a)
+    return out
+
+
+def gen_distill_golden():
+    """BiC (bias layers on the class slices + soft-target distillation) and iCaRL (BCE distillation) terms of the training
+    loss (meta_archs.py:823-836, 1482-1519) from the REFERENCE: losses and gradient summaries, model.eval() (no dropout)."""
+    c = small_cfg()
+    out = {}
+    for name, yaml_name in (("bic", "mq_bic_all.yaml"), ("icarl", "mq_icarl_all.yaml")):
+        model, _ = build_reference_model(c, seed=0, yaml_name=yaml_name)
+        ns = ref_shim.load()
+        model.n_known = 3
+        if name == "bic":
+            model.list_splits = [3, 6]
+            model.list_bias_layers = [ns.meta_archs.BiasLayer(), ns.meta_archs.BiasLayer()]
+            for bl, (a, b) in zip(model.list_bias_layers, ((1.1, 0.05), (0.9, -0.02))):
+                bl.alpha.data.fill_(a)
+                bl.beta.data.fill_(b)
+        videos = PR.synth_video_list(c, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+        prev = prev_logits(c, probs=True)
+        model.loss_normalizer = c.init_loss_norm
+        model.zero_grad()
+        losses = model(videos, is_training=True, prev_out_cls_logits=prev if name == "bic" else [prev])
+        losses["final_loss"].backward()
+        for k, v in losses.items():
+            out[f"{name}_loss_{k}"] = np.float32(torch.as_tensor(v).detach().reshape(-1)[0].item())
+        spec = PR.param_spec(c)
+        for k, p_ in model.named_parameters():
+            if k in spec and p_.grad is not None:
+                g = p_.grad.detach().reshape(-1).double()
+                out[f"{name}_g:{k}"] = np.concatenate([[g.norm().item(), g.sum().item()], g[:8].numpy()]).astype(np.float64)
+        if name == "bic":
+            out["bic_bias_grads"] = np.array([[bl.alpha.grad.item(), bl.beta.grad.item()] for bl in model.list_bias_layers])
+    np.savez_compressed(os.path.join(GOLDEN, "distill_small.npz"), **out)
+    print("distill_small:", {k: float(v) for k, v in out.items() if "_loss_" in k})
+
+
 def gen_vilco_golden():
     """mq_vilco.yaml branches at inference: prompts prepended to the text, adapters on branch 0-4, EMA-adapter ensemble."""
     c = vilco_cfg()
@@ -276,3 +320,5 @@ if __name__ == "__main__":
         gen_grad_golden()
     if "vilco_train" in what:
         gen_vilco_train_golden()
+    if "distill" in what:
+        gen_distill_golden()

@@ -405,3 +405,40 @@ def test_vilco_training_step_matches_reference_golden():
         assert np.abs(got[2:] - ref[2:]).max() <= tol * ref[0] + 1e-7, (key, got[2:4], ref[2:4])
         n += 1
     assert n > 250
+
+
+@pytest.mark.parametrize("name", ["bic", "icarl"])
+def test_distillation_terms_match_reference_golden(name):
+    """n_known > 0: BiC bias layers + soft-target distillation / iCaRL BCE distillation (meta_archs.py:823-836, 1482-1519)
+    against losses and gradients produced by the reference (tests/golden/distill_small.npz)."""
+    import os
+    from conftest import GOLDEN
+    from vilco_b200.modeling.meta_archs import BiasLayer
+    g = np.load(os.path.join(GOLDEN, "distill_small.npz"))
+    cfg = GG.small_cfg()
+    model, P = build_pair(cfg, 0)
+    model.eval()
+    model.cl_name, model.n_known = name, 3
+    if name == "bic":
+        model.list_splits = [3, 6]
+        model.list_bias_layers = [BiasLayer().cuda(), BiasLayer().cuda()]
+        for bl, (a, b) in zip(model.list_bias_layers, ((1.1, 0.05), (0.9, -0.02))):
+            bl.alpha.data.fill_(a)
+            bl.beta.data.fill_(b)
+    videos = PR.synth_video_list(cfg, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    prev = GG.prev_logits(cfg, probs=True)
+    model.loss_normalizer = cfg.init_loss_norm
+    out = model(videos, is_training=True, prev_out_cls_logits=prev if name == "bic" else [prev])
+    out["final_loss"].backward()
+    for k in ("cls_loss", "reg_loss", "al_loss", "dist_loss", "final_loss"):
+        ref = float(g[f"{name}_loss_{k}"])
+        assert abs(float(out[k].detach()) - ref) <= 1e-3 * abs(ref) + 1e-6, (k, float(out[k].detach()), ref)
+    if name == "bic":
+        got = np.array([[bl.alpha.grad.item(), bl.beta.grad.item()] for bl in model.list_bias_layers])
+        assert np.abs(got - g["bic_bias_grads"]).max() <= 1e-3 * np.abs(g["bic_bias_grads"]).max()
+    named = dict(model.named_parameters())
+    for key in ("cls_head.cls_head.conv.weight", "cls_head.cls_head.conv.bias", "cls_head.norm.1.weight", "mu"):
+        ref = g[f"{name}_g:{key}"]
+        mine = named[key].grad.detach().reshape(-1).double().cpu()
+        got = np.concatenate([[mine.norm().item(), mine.sum().item()], mine[:8].numpy()])
+        assert np.abs(got - ref).max() <= 2e-3 * ref[0] + 1e-8, (key, got[:3], ref[:3])

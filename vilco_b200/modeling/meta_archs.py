@@ -591,8 +591,6 @@ class PtTransformer(nn.Module):
         CUDA backward pass (vilco_b200/train_engine.py) and accumulates into every parameter's .grad.  mu / sigma (and
         the L2P prompt pool) receive their gradients through torch autograd of the small target-assignment glue."""
         from .. import train_engine as TE
-        if self.n_known > 0 and self.cl_name in ("bic", "icarl"):
-            raise NotImplementedError("BiC / iCaRL distillation terms of the training loss are not built yet")
         dev = self.device
         vl, batched, mask = self.preprocessing(video_list, True)
         text = tmask = None
@@ -633,6 +631,23 @@ class PtTransformer(nn.Module):
         if self.n_known > 0 and self.cl_name == "l2p" and self._reduce_sim is not None:
             extra.append(-0.1 * self._reduce_sim)         # pull constraint of L2P (meta_archs.py:1478-1480)
         B, P, K = logits.shape
+        # BiC / iCaRL (n_known > 0): bias layers on the class slices of the logits and the distillation term are torch
+        # expressions on a leaf cut at the logits (meta_archs.py:823-836, 1482-1519)
+        lg_leaf = lg_biased = None
+        if self.n_known > 0 and self.cl_name in ("bic", "icarl"):
+            lg_leaf = logits.detach().requires_grad_(True)
+            with torch.enable_grad():
+                lg_biased = lg_leaf
+                if self.cl_name == "bic" and len(self.list_splits) > 0:
+                    parts, lo_ = [], 0
+                    for i, hi_ in enumerate(self.list_splits):
+                        parts.append(self.list_bias_layers[i](lg_leaf[:, :, lo_:hi_]))
+                        lo_ = hi_
+                    lg_biased = torch.cat(parts, dim=2)
+                dist = self._distill_term(lg_biased, pyr, prev_out_cls_logits)
+            logits = lg_biased.detach().contiguous()
+            extra.append(dist)
+            extra_named["dist_loss"] = dist.detach()
         gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
         with torch.no_grad():
             gt_cls, gt_off = gt_cls.detach(), gt_off.detach()
@@ -675,12 +690,21 @@ class PtTransformer(nn.Module):
                     ops._p(doffsets), ops._p(dwc), ops._p(dwl), ops._p(dwr), L.stream_ptr()), "vilco_mq_losses_bwd")
                 logitsV.g, offsetsV.g = dlogits, doffsets
                 model._last_head_grads = (dlogits, doffsets, pyr)   # kept for the gradient parity tests
-            if extra:
-                torch.autograd.backward(extra, [torch.full_like(t_, gscale) for t_ in extra])
-                if ssl_leaves is not None:
-                    for f_, leaf in zip(fpn_lv, ssl_leaves):
-                        if leaf.grad is not None:
-                            tp.acc(f_, leaf.grad)
+            tensors, grads = list(extra), [torch.full_like(t_, gscale) for t_ in extra]
+            if lg_leaf is not None and lg_biased is not lg_leaf:
+                tensors.append(lg_biased)        # through the bias layers (their alpha / beta get .grad here) to the raw logits
+                grads.append(dlogits)
+            if tensors:
+                torch.autograd.backward(tensors, grads)
+            if lg_leaf is not None:
+                if lg_biased is not lg_leaf:
+                    logitsV.g = lg_leaf.grad
+                elif lg_leaf.grad is not None:
+                    logitsV.g = dlogits + lg_leaf.grad
+            if ssl_leaves is not None:
+                for f_, leaf in zip(fpn_lv, ssl_leaves):
+                    if leaf.grad is not None:
+                        tp.acc(f_, leaf.grad)
             with torch.no_grad():
                 tp.backward()
                 model._last_touch = (tp.n_nodes, dict(tp.touch), set(tp.G.keys()))
@@ -704,6 +728,28 @@ class PtTransformer(nn.Module):
         out = {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final_t}
         out.update(extra_named)
         return out
+
+    def _distill_term(self, lg, pyr, prev_out_cls_logits):
+        """Distillation against the previous task's recorded classification outputs (per level (T_l, K_prev) numpy arrays),
+        only batch element 0, as the reference computes it — BiC: soft targets at temperature 2 weighted n_known / K
+        (meta_archs.py:1482-1499); iCaRL: per-class BCE-with-logits (:1501-1519)."""
+        prev = prev_out_cls_logits
+        nl = len(pyr.lens)
+        dist = 0
+        if self.cl_name == "bic":
+            alpha = self.n_known / self.cls_head.cls_head.conv.out_channels
+            for i, (o, n) in enumerate(zip(pyr.off, pyr.lens)):
+                p_i = torch.as_tensor(prev[i]).to(lg.device)
+                logp = F.log_softmax(lg[0, o:o + n, :self.n_known] / 2, dim=1)
+                dist = dist + 0.01 * alpha * (-torch.mean(torch.sum(p_i[:, :self.n_known] * logp, dim=1)))
+            return dist
+        bce = nn.BCEWithLogitsLoss()
+        for i, (o, n) in enumerate(zip(pyr.off, pyr.lens)):
+            if len(prev) != nl or len(prev) == 1:
+                prev = prev[0]
+            p_i = torch.as_tensor(prev[i]).to(lg.device)
+            dist = dist + 0.01 * sum(bce(lg[0, o:o + n, y], p_i[:, y]) for y in range(self.n_known))
+        return dist
 
     def _narration_ssl(self, vl, fpn_lv, masks):
         """Narration self-supervision of mq_vilco (meta_archs.py:794-811, 939-945, 1351-1372): masked-mean narration
