@@ -167,7 +167,7 @@ int vilco_decode(const float* logits, const float* offsets, const float* pmask, 
  * of its n_regions regions of region_cap slots (decode output layout; a flat array is one region).  Per class (ascending
  * original order) the reference's array algorithm is reproduced exactly, at most max_seg_num picks are kept per class,
  * classes are concatenated in ascending id, sorted by score (descending, ties by concatenation order) and cut to
- * max_seg_num.  multiclass = 0 runs one class-agnostic pass (seg voting is not implemented: the caller must not ask for it).
+ * max_seg_num.  multiclass = 0 runs one class-agnostic pass (follow it with vilco_seg_voting when voting_thresh > 0).
  * Outputs (B, max_seg_num [,2]) + out_count (B).  workspace: vilco_nms_workspace_bytes(...) device bytes.
  * ------------------------------------------------------------------------------------ */
 size_t vilco_nms_workspace_bytes(int B, int n_regions, int region_cap, int num_classes, int det_cap);
@@ -175,6 +175,12 @@ int vilco_batched_nms(const float* segs, const float* scores, const int* labels,
                       int n_regions, int region_cap, int num_classes, int multiclass, int method, float iou_threshold,
                       float sigma, float min_score, int max_seg_num, void* workspace, size_t workspace_bytes,
                       float* out_segs, float* out_scores, long long* out_labels, int* out_count, void* stream);
+
+/* Segment voting of the class-agnostic branch of batched_nms (MQ/libs/utils/nms.py:66-101, 174-181): every kept segment
+ * (out_segs (B, max_seg_num, 2), first out_count[b] rows) is replaced in place by the score*IoU-weighted mean of all
+ * candidates of its clip (same layout as vilco_batched_nms' inputs) with IoU >= voting_thresh. */
+int vilco_seg_voting(float* out_segs, const int* out_count, const float* segs, const float* scores, const int* region_count,
+                     int B, int n_regions, int region_cap, int max_seg_num, float voting_thresh, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused forward of the Moment-Query losses — PtTransformer.losses, MQ/libs/modeling/meta_archs.py:1374-1480:

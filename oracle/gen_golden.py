@@ -222,6 +222,27 @@ def gen_distill_golden():
     print("distill_small:", {k: float(v) for k, v in out.items() if "_loss_" in k})
 
 
+def gen_nms_voting_golden():
+    """class-agnostic batched_nms with segment voting (nms.py:159-181) from the reference python wrapper + C++ extension."""
+    ns = ref_shim.load()
+    rs = np.random.RandomState(11)
+    out = {}
+    for name, n in (("a", 500), ("b", 4000)):
+        centre = rs.uniform(0, 1024, n).astype(np.float32)
+        length = np.exp(rs.uniform(np.log(2.0), np.log(400.0), n)).astype(np.float32)
+        segs = np.stack([centre - length / 2, centre + length / 2], 1).astype(np.float32)
+        scores = rs.beta(0.5, 8, n).astype(np.float32) + np.float32(1e-3)
+        labels = rs.randint(0, 5, n).astype(np.int64)
+        for soft in (True, False):
+            s, sc, lb = ns.nms.batched_nms(torch.from_numpy(segs), torch.from_numpy(scores), torch.from_numpy(labels), 0.3,
+                                           1e-3, 100, use_soft_nms=soft, multiclass=False, sigma=0.75, voting_thresh=0.75)
+            tag = f"{name}_{'soft' if soft else 'hard'}"
+            out[tag + "_segs"], out[tag + "_scores"], out[tag + "_labels"] = s.numpy(), sc.numpy(), lb.numpy()
+        out[name + "_in_segs"], out[name + "_in_scores"], out[name + "_in_labels"] = segs, scores, labels
+    np.savez_compressed(os.path.join(GOLDEN, "nms_voting.npz"), **out)
+    print("nms_voting ok", {k: v.shape for k, v in out.items() if k.endswith("_segs") and "_in_" not in k})
+
+
 def gen_vilco_golden():
     """mq_vilco.yaml branches at inference: prompts prepended to the text, adapters on branch 0-4, EMA-adapter ensemble."""
     c = vilco_cfg()
@@ -322,3 +343,5 @@ if __name__ == "__main__":
         gen_vilco_train_golden()
     if "distill" in what:
         gen_distill_golden()
+    if "voting" in what:
+        gen_nms_voting_golden()

@@ -118,3 +118,18 @@ def test_decode_vs_oracle():
         same = sum(1 for x, y in zip(ka, kb) if x == y)
         assert same >= 0.999 * len(ka)
         assert abs(float(scores.sum()) - float(got_sc.sum())) < 1e-3 * float(scores.sum())
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+@pytest.mark.parametrize("soft", [True, False])
+def test_class_agnostic_nms_with_segment_voting(name, soft):
+    """multiclass=False + voting_thresh > 0 (nms.py:159-181): scores / labels / order identical to the reference, voted
+    segments within fp32 rounding of its normalise-then-matmul formulation."""
+    from vilco_b200.utils import batched_nms
+    g = np.load(os.path.join(GOLDEN, "nms_voting.npz"))
+    s, sc, lb = batched_nms(torch.from_numpy(g[name + "_in_segs"]), torch.from_numpy(g[name + "_in_scores"]),
+                            torch.from_numpy(g[name + "_in_labels"]), 0.3, 1e-3, 100, use_soft_nms=soft, multiclass=False,
+                            sigma=0.75, voting_thresh=0.75)
+    tag = f"{name}_{'soft' if soft else 'hard'}"
+    assert (sc.numpy() == g[tag + "_scores"]).all() and (lb.numpy() == g[tag + "_labels"]).all()
+    assert np.abs(s.numpy() - g[tag + "_segs"]).max() <= 1e-5 * np.abs(g[tag + "_segs"]).max()

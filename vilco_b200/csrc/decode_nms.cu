@@ -566,6 +566,57 @@ extern "C" size_t vilco_nms_workspace_bytes(int B, int n_regions, int region_cap
   return n * 6 * 4 + (size_t)B * num_classes * 4 * 2 + (size_t)B * num_classes * det_cap * 4 * 4 + 256;
 }
 
+// Segment voting (MQ/libs/utils/nms.py:66-101): every kept segment becomes the average of ALL candidates of its clip that
+// overlap it with IoU >= thr, weighted by score * IoU.  One block per kept segment, candidates streamed once.
+__global__ void __launch_bounds__(256) seg_voting_kernel(float* __restrict__ out_segs, const int* __restrict__ out_count,
+                                                         const float* __restrict__ segs, const float* __restrict__ scores,
+                                                         const int* __restrict__ region_count, int n_regions, int region_cap,
+                                                         int M, float thr) {
+  const int m = blockIdx.x, b = blockIdx.y;
+  if (m >= out_count[b]) return;
+  const float a0 = out_segs[((long long)b * M + m) * 2], a1 = out_segs[((long long)b * M + m) * 2 + 1];
+  const float la = a1 - a0;
+  double sw = 0.0, s0 = 0.0, s1 = 0.0;
+  for (int r = 0; r < n_regions; ++r) {
+    const int cnt = region_count[b * n_regions + r];
+    const long long base = ((long long)b * n_regions + r) * region_cap;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const float x0 = segs[(base + i) * 2], x1 = segs[(base + i) * 2 + 1];
+      const float inter = fmaxf(fminf(a1, x1) - fmaxf(a0, x0), 0.f);
+      const float iou = inter / (la + (x1 - x0) - inter);
+      if (iou >= thr) {
+        const double w = static_cast<double>(scores[base + i] * iou);
+        sw += w; s0 += w * x0; s1 += w * x1;
+      }
+    }
+  }
+  __shared__ double red[3][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sw; red[1][threadIdx.x >> 5] = s0; red[2][threadIdx.x >> 5] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tw = 0.0, t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < 8; ++k) { tw += red[0][k]; t0 += red[1][k]; t1 += red[2][k]; }
+    out_segs[((long long)b * M + m) * 2] = static_cast<float>(t0 / tw);
+    out_segs[((long long)b * M + m) * 2 + 1] = static_cast<float>(t1 / tw);
+  }
+}
+
+extern "C" int vilco_seg_voting(float* out_segs, const int* out_count, const float* segs, const float* scores,
+                                const int* region_count, int B, int n_regions, int region_cap, int max_seg_num,
+                                float voting_thresh, void* stream) {
+  VILCO_CHECK_ARG(out_segs && out_count && segs && scores && region_count && B > 0 && max_seg_num > 0,
+                  "vilco_seg_voting: bad arguments");
+  seg_voting_kernel<<<dim3(max_seg_num, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out_segs, out_count, segs, scores, region_count, n_regions, region_cap, max_seg_num, voting_thresh);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
 extern "C" int vilco_batched_nms(const float* segs, const float* scores, const int* labels, const int* region_count,
                                  int B, int n_regions, int region_cap, int num_classes, int multiclass, int method,
                                  float iou_threshold, float sigma, float min_score, int max_seg_num, void* workspace,

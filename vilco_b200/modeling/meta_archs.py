@@ -902,11 +902,14 @@ class PtTransformer(nn.Module):
                     labels[b, o:o + n] = cand_labels[b, l * topk:l * topk + n].long()
                     o += n
             return segs, scores, labels, cnt.sum(1).int().to(dev)
-        if not self.test_multiclass_nms and self.test_voting_thresh > 0:
-            raise NotImplementedError("class-agnostic NMS with segment voting is not built yet")
         method = 2 if self.test_nms_method == "soft" else 3
-        return _nms_run(cand_segs, cand_scores, cand_labels, cand_count, B, nl, topk, K, self.test_multiclass_nms, method,
-                        self.test_iou_threshold, self.test_nms_sigma, self.test_min_score, self.test_max_seg_num)
+        res = _nms_run(cand_segs, cand_scores, cand_labels, cand_count, B, nl, topk, K, self.test_multiclass_nms, method,
+                       self.test_iou_threshold, self.test_nms_sigma, self.test_min_score, self.test_max_seg_num)
+        if not self.test_multiclass_nms and self.test_voting_thresh > 0:      # class-agnostic: segment voting (nms.py:174-181)
+            from ..utils.nms import seg_voting
+            seg_voting(res[0], res[3], cand_segs, cand_scores, cand_count, B, nl, topk, self.test_max_seg_num,
+                       self.test_voting_thresh)
+        return res
 
     @staticmethod
     def _to_results(video_list, segs, scores, labels, count):

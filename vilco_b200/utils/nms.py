@@ -35,8 +35,6 @@ def batched_nms(segs, scores, cls_idxs, iou_threshold, min_score, max_seg_num, u
     n = segs.shape[0]
     if n == 0:  # nms.py:118-121
         return torch.zeros([0, 2]), torch.zeros([0]), torch.zeros([0], dtype=cls_idxs.dtype)
-    if not multiclass and voting_thresh > 0:
-        raise L.VilcoError("batched_nms: class-agnostic NMS with segment voting is not implemented on the GPU path")
     L.lib().vilco_nms_workspace_bytes.restype = C.c_size_t
     dev = segs.device if segs.is_cuda else torch.device("cuda", torch.cuda.current_device())
     s = segs.to(dev, torch.float32).contiguous()
@@ -46,5 +44,15 @@ def batched_nms(segs, scores, cls_idxs, iou_threshold, min_score, max_seg_num, u
     cnt = torch.tensor([n], device=dev, dtype=torch.int32)
     os_, osc, ol, oc = _run(s, sc, lb, cnt, 1, 1, n, num_classes, multiclass, 2 if use_soft_nms else 3, iou_threshold,
                             sigma, min_score, max_seg_num)
+    if not multiclass and voting_thresh > 0:      # nms.py:174-181
+        seg_voting(os_, oc, s, sc, cnt, 1, 1, n, max_seg_num, voting_thresh)
     k = int(oc.item())
     return os_[0, :k].cpu(), osc[0, :k].cpu(), ol[0, :k].cpu().to(cls_idxs.dtype)
+
+
+def seg_voting(out_segs, out_count, segs, scores, region_count, B, n_regions, region_cap, max_seg_num, voting_thresh):
+    """in-place segment voting of the kept segments against all candidates (device tensors, see vilco_seg_voting)"""
+    L.check(L.lib().vilco_seg_voting(
+        C.c_void_p(out_segs.data_ptr()), C.c_void_p(out_count.data_ptr()), C.c_void_p(segs.data_ptr()),
+        C.c_void_p(scores.data_ptr()), C.c_void_p(region_count.data_ptr()), B, n_regions, region_cap, int(max_seg_num),
+        C.c_float(voting_thresh), L.stream_ptr()), "vilco_seg_voting")
