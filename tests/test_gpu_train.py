@@ -442,3 +442,22 @@ def test_distillation_terms_match_reference_golden(name):
         mine = named[key].grad.detach().reshape(-1).double().cpu()
         got = np.concatenate([[mine.norm().item(), mine.sum().item()], mine[:8].numpy()])
         assert np.abs(got - ref).max() <= 2e-3 * ref[0] + 1e-8, (key, got[:3], ref[:3])
+
+
+def test_ragged_training_batch_matches_oracle():
+    """clips and texts of very different lengths, 1 / 8 / 3 ground truths per clip: losses vs the oracle, and a backward
+    pass that leaves finite gradients.  (A clip without labels cannot be part of a cross-modal training batch in the
+    reference either: it drops the clip's features but not its text, meta_archs.py:1138 vs :1188.)"""
+    cfg = GG.small_cfg()
+    model, P = build_pair(cfg, 0)
+    model.eval()
+    videos = PR.synth_video_list(cfg, 3, seed=4, lens=[128, 64, 37], text_lens=[20, 128, 77], n_gt=[1, 8, 3])
+    lo, _ = O.model_train_losses(P, cfg, videos)
+    model.loss_normalizer = cfg.init_loss_norm
+    out = model(videos, is_training=True)
+    for k in ("cls_loss", "reg_loss", "al_loss", "final_loss"):
+        assert abs(float(out[k].detach()) - float(lo[k])) <= 1e-3 * abs(float(lo[k])) + 1e-6, (k, float(out[k].detach()), float(lo[k]))
+    out["final_loss"].backward()
+    for k, prm in model.named_parameters():
+        if k in P:
+            assert prm.grad is not None and torch.isfinite(prm.grad).all(), k
