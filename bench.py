@@ -406,6 +406,8 @@ def main():
             "achieved": top["tflops"], "peak": tf_sus, "unit": "TFLOP/s", "frac": top["tflops"] / tf_sus,
             "traffic": traffic, "peak_source": f"bf16_tflops_sustained of {how}",
             "algorithmic_flop_per_launch": top["flop_per_launch"],
+            "mma_per_algorithmic_mac": 3 if ops.precision() == "bf16x3" else 1,
+            "tensor_pipe_frac": top["tflops"] * (3 if ops.precision() == "bf16x3" else 1) / tf_sus,
             "all_gemm_launches": {"launches": nl, "achieved": fl / tg / 1e12, "share_of_step": tg / (t_dev / args.steps)},
             "note": "algorithmic FLOPs (2*M*N*K*taps*Z); bf16x3 executes 3 tcgen05.mma per algorithmic MAC, so 1/3 of the "
                     "tensor peak is the ceiling of this figure in the default precision"}
