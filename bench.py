@@ -54,11 +54,13 @@ def synth_videos(n, seed, T=1024, Cin=4096, Ct=768, K=22, pin=False):
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
-    def __init__(self, gpu):
+    def __init__(self, gpu, enabled=True):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.stop_flag, self.enabled = gpu, [], False, enabled
 
     def run(self):
+        if not self.enabled:     # only rank 0 polls nvidia-smi: N pollers per node perturb the ranks they are supposed to observe
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
@@ -69,7 +71,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.2)
 
     def summary(self):
         if not self.rows:
@@ -278,7 +280,7 @@ def run_train_leg(args, model, rank, world, dist, barrier, local):
     for _ in range(args.warmup):
         tr.step(dev_set)
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=rank == 0)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = L.launch_count()
@@ -360,7 +362,7 @@ def main():
     for _ in range(args.warmup):
         g.replay()
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=rank == 0)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = L.launch_count()
