@@ -13,6 +13,7 @@ def timeit(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 
+print("peak HBM (MEASURED_PEAKS.json): see repo root; fp32 token-major (16384, 1024) tensors unless noted")
 R, C = 16384, 1024
 x, dy = torch.randn(R, C, device="cuda"), torch.randn(R, C, device="cuda")
 w = torch.randn(C, device="cuda")
@@ -29,6 +30,20 @@ us = timeit(lambda: ops.ew(1, x, out16=True))
 print(f"gelu fwd+planes {R}x{C}: {us:.1f} us  {R * C * 12 / us / 1e6:.2f} TB/s")
 us = timeit(lambda: ops.dropout(x, 0.1, 7))
 print(f"dropout       {R}x{C}: {us:.1f} us  {R * C * 8 / us / 1e6:.2f} TB/s")
+lw, lb = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+us = timeit(lambda: ops.layernorm(x, lw, lb, out32=True, out16=True))
+print(f"layernorm fwd (fp32 + planes) {R}x{C}: {us:.1f} us  {R * C * 12 / us / 1e6:.2f} TB/s (4 B in, 4 + 4 B out)")
+res, y = torch.randn(R, C, device="cuda"), torch.randn(R, C, device="cuda")
+import ctypes as CT
+from vilco_b200 import lib as L
+out = torch.empty_like(y)
+rm = torch.ones(R, device="cuda")
+us = timeit(lambda: L.check(L.lib().vilco_resid_branch_fwd(ops._p(res), ops._p(rm), ops._p(y), ops._p(lb), ops._p(lw), ops._p(rm), ops._p(out), ops._i64(R), C, CT.c_float(0.1), CT.c_uint64(5), L.stream_ptr())))
+print(f"resid_branch_fwd (dropout) {R}x{C}: {us:.1f} us  {R * C * 12 / us / 1e6:.2f} TB/s (8 B in, 4 B out)")
+dz = ops.empty16(R, C, device="cuda")
+dbb, dss = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+us = timeit(lambda: L.check(L.lib().vilco_resid_branch_bwd(ops._p(dy), ops._p(rm), ops._p(y), ops._p(lb), ops._p(lw), ops._p(rm), ops._p(out), ops._p(dz), ops._i64(ops.lo(dz)), ops._p(dbb), ops._p(dss), R, C, CT.c_float(0.1), CT.c_uint64(5), L.stream_ptr())))
+print(f"resid_branch_bwd (dropout) {R}x{C}: {us:.1f} us  {R * C * 16 / us / 1e6:.2f} TB/s (8 B in, 4 + 4 B out)")
 B, H, T = 4, 16, 1024
 P = torch.softmax(torch.randn(B, H, T, T, device="cuda"), -1)
 P16 = ops.split16(P)

@@ -832,8 +832,10 @@ class PtTransformer(nn.Module):
         xs = xrel.gather(2, idx).squeeze(-1)                                               # (B,P)
         ls = lab.gather(1, min_inds)                                                       # (B,P) label of the selected gt
 
+        oh = F.one_hot(ls, K).to(xs.dtype)        # (B,P,K): the per-point parameter lookup as a matmul (its autograd is a
+                                                  # matmul too; fancy-index backward is a sort + serial accumulate per call)
         def gauss(m, s):
-            return (-(xs - m[ls, 0]) ** 2 / (2 * s[ls, 0] ** 2)).exp()
+            return (-(xs - (oh @ m).squeeze(-1)) ** 2 / (2 * (oh @ s).squeeze(-1) ** 2)).exp()
         return (gt_cls.contiguous(), gt_off.contiguous(), gauss(self.mu, self.sigma).contiguous(),
                 gauss(self.mu_reg_left, self.sigma_reg_left).contiguous(),
                 gauss(self.mu_reg_right, self.sigma_reg_right).contiguous())
