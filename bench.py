@@ -59,8 +59,23 @@ class ClockSampler(threading.Thread):
         self.gpu, self.rows, self.stop_flag, self.enabled = gpu, [], False, enabled
 
     def run(self):
-        if not self.enabled:     # only rank 0 polls nvidia-smi: N pollers per node perturb the ranks they are supposed to observe
+        if not self.enabled:     # only rank 0 polls: N pollers per node perturb the ranks they are supposed to observe
             return
+        try:                     # NVML in-process (nvidia_ml_py): far lighter than spawning nvidia-smi several times a second
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+            while not self.stop_flag:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] +
+                                 ["Active" if r & bit else "Not Active" for _, bit in bits])
+                time.sleep(0.1)
+            return
+        except Exception:
+            pass
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
@@ -71,7 +86,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.3)
 
     def summary(self):
         if not self.rows:
