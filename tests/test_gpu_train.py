@@ -461,3 +461,44 @@ def test_ragged_training_batch_matches_oracle():
     for k, prm in model.named_parameters():
         if k in P:
             assert prm.grad is not None and torch.isfinite(prm.grad).all(), k
+
+
+def test_flat_adamw_checkpoint_round_trip_and_torch_compatibility():
+    """FlatAdamW.state_dict() has torch.optim.AdamW's structure: resuming from it (in a new FlatAdamW or in torch's AdamW)
+    continues with identical updates."""
+    from vilco_b200.trainer import FlatAdamW
+    torch.manual_seed(3)
+    shapes = [(32, 16), (16,), (8, 4, 1)]
+    base = [torch.randn(s, device="cuda") for s in shapes]
+    grads = [[torch.randn(s, device="cuda") for s in shapes] for _ in range(4)]
+
+    def mk(cls):
+        ps = [torch.nn.Parameter(b.clone()) for b in base]
+        return ps, cls([{"params": ps[:2], "weight_decay": 0.05}, {"params": ps[2:], "weight_decay": 0.0}], lr=1e-2)
+
+    def run(ps, opt, gs):
+        for g in gs:
+            opt.zero_grad()
+            for p, gi in zip(ps, g):
+                if p.grad is None:
+                    p.grad = gi.clone()
+                else:
+                    p.grad.add_(gi)
+            opt.step()
+
+    ps_a, opt_a = mk(FlatAdamW)
+    run(ps_a, opt_a, grads[:2])
+    sd = opt_a.state_dict()
+    assert set(sd["state"].keys()) == {0, 1, 2} and float(sd["state"][0]["step"]) == 2.0
+    run(ps_a, opt_a, grads[2:])                                  # uninterrupted run = the reference trajectory
+    for cls in (FlatAdamW, torch.optim.AdamW):
+        ps_b, opt_b = mk(cls)
+        ps_c, opt_c = mk(FlatAdamW)
+        run(ps_c, opt_c, grads[:2])                              # parameters after two steps ...
+        with torch.no_grad():
+            for p, q in zip(ps_b, ps_c):
+                p.copy_(q)
+        opt_b.load_state_dict(sd)                                # ... plus the checkpointed moments
+        run(ps_b, opt_b, grads[2:])
+        for p, q in zip(ps_b, ps_a):
+            assert rel_max(p.detach(), q.detach()) < 5e-6, cls

@@ -10,7 +10,7 @@ import torch
 
 from . import lib as L
 from . import ops
-from .ops import _i64, _p, bf16, f32, lo
+from .ops import _i64, _p, f32, lo
 
 
 def to_planes(x, rowmul=None, colmul=None, want=True, want_t=False, batch_dims=0):

@@ -93,7 +93,7 @@ using namespace vilco;
 
 static inline int ogrid(long long n, int block) {
   long long b = (n + block - 1) / block;
-  const long long cap = 148LL * 8;
+  const long long cap = 148LL * 8;   // also bounds the number of sum-of-squares partials (VILCO_CLIP_SCRATCH)
   return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -120,7 +120,9 @@ extern "C" int vilco_adamw(float* p, const float* g, float* m, float* v, int64_t
                   "vilco_adamw: buffers must be 16-byte aligned and n a multiple of 4");
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
-  adamw_kernel<<<ogrid(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;   // seven 16-byte streams per thread: keep many warps in flight
+  adamw_kernel<<<static_cast<unsigned>(blocks < 1 ? 1 : blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, static_cast<__nv_bfloat16*>(planes), planes_lo);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;

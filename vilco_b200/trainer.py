@@ -355,6 +355,42 @@ class FlatAdamW(torch.optim.Optimizer):
                 C.c_void_p(self.planes.data_ptr() + 2 * a), ops._i64(self.n if NP == 2 else 0), st), "vilco_adamw")
         self.epoch += 1
 
+    # ---- checkpointing in torch.optim.AdamW's own format (train_utils.save_checkpoint stores optimizer.state_dict()) ------
+    def state_dict(self):
+        """Same structure as torch.optim.AdamW.state_dict(): per-parameter 'step', 'exp_avg', 'exp_avg_sq' (clones of the
+        flat slices) indexed by the position of the parameter in the groups, so a checkpoint written here resumes with
+        torch.optim.AdamW and vice versa.  Parked (dead) parameters have no state, like parameters without a gradient."""
+        state, groups, idx = {}, [], 0
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                if id(p) in self.slots and id(p) not in self.dead and self.t > 0:
+                    o, k = self.slots[id(p)]
+                    state[idx] = {"step": torch.tensor(float(self.t)), "exp_avg": self.exp_avg[o:o + k].view(p.shape).clone(),
+                                  "exp_avg_sq": self.exp_avg_sq[o:o + k].view(p.shape).clone()}
+                ids.append(idx)
+                idx += 1
+            groups.append({**{k_: v for k_, v in g.items() if k_ != "params"}, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        idx = 0
+        steps = []
+        with torch.no_grad():
+            for g, sg in zip(self.param_groups, sd["param_groups"]):
+                for k_, v in sg.items():
+                    if k_ != "params":
+                        g[k_] = v
+                for p in g["params"]:
+                    st = sd["state"].get(idx)
+                    if st is not None and id(p) in self.slots:
+                        o, k = self.slots[id(p)]
+                        self.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                        self.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                        steps.append(int(float(st["step"])))
+                    idx += 1
+        self.t = max(steps) if steps else 0
+
     def grad_norm(self):
         """global L2 norm of the last step's (un-clipped) gradient — what clip_grad_norm_ returns."""
         return self._scal[2]
