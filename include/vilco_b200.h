@@ -143,6 +143,7 @@ int vilco_local_attention(const void* q, const void* k, const void* v, const flo
 
 /* ChannelAttention core (blocks.py:423-436): qkv (B,T,3C) bf16 -> y (B,T,C) bf16;  G is a (B,H,64,64) fp32 scratch.
  * tlen (B,) or NULL limits the tokens summed in k^T v (the reference sums over every position of its padded batch). */
+/* (y may be NULL: only G is computed) */
 int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G, void* y, int64_t y_lo, const int* tlen, int B, int T,
                             int C, int H, void* stream);
 

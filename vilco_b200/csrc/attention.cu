@@ -532,13 +532,14 @@ extern "C" int vilco_local_attention(const void* q, const void* k, const void* v
 
 extern "C" int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G, void* y, int64_t y_lo, const int* tlen,
                                        int B, int T, int C, int H, void* stream) {
-  VILCO_CHECK_ARG(qkv && G && y, "vilco_channel_attention: null pointer");
+  VILCO_CHECK_ARG(qkv && G, "vilco_channel_attention: null pointer");   // y == NULL: only G = (k / 8)^T v is wanted
   VILCO_CHECK_ARG(H > 0 && C == H * CA_D, "vilco_channel_attention: head dim must be 64 (C=%d H=%d)", C, H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VILCO_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)B * H * CA_D * CA_D, st));
   dim3 grid((T + CA_TCHUNK - 1) / CA_TCHUNK, H, B);
   chan_attn_kv_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, tlen, T, C, H, 1.0f / sqrtf((float)CA_D));
   VILCO_LAUNCH_CHECK();
+  if (!y) return VILCO_OK;
   chan_attn_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, static_cast<__nv_bfloat16*>(y), y_lo, T, C, H);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;

@@ -252,14 +252,65 @@ def local_attention(q, k, v, mask, H, W, rel_pe=None):
     return out
 
 
-def channel_attention(qkv, H, tlen=None, return_G=False):
+CHAN_TC = os.environ.get("VILCO_CHAN_TC", "1") == "1"   # 0: the SIMT channel-attention kernels
+
+
+def channel_attention(qkv, H, tlen=None, return_A=False):
+    """ChannelAttention core (blocks.py:423-436): per head A = softmax_rows((k / 8)^T v) over ALL T rows, y = (A q^T)^T.
+    qkv operand (NP,B,T,3C) -> y operand (NP,B,T,C) [, A operand (NP,B,H,64,64)].
+    Default: G = k^T v on the SIMT kernel (exact fp32 products), the row softmax, and y = q A^T on the tensor-core GEMM kernel.
+    With per-sequence lengths (`tlen`, batched text evaluation) or VILCO_CHAN_TC=0 the SIMT apply kernel is used too."""
     _, B, T, C3 = qkv.shape
     Cc = C3 // 3
+    if tlen is not None or not CHAN_TC or Cc // H != 64:
+        G = torch.empty(B, H, 64, 64, device=qkv.device, dtype=f32)
+        y = empty16(B, T, Cc, device=qkv.device)
+        L.check(L.lib().vilco_channel_attention(_p(qkv), _i64(lo(qkv)), _p(G), _p(y), _i64(lo(y)), _p(tlen), B, T, Cc, H,
+                                                L.stream_ptr()), "vilco_channel_attention")
+        if not return_A:
+            return y
+        return y, softmax_rows(G.reshape(B, H, 64, 64), None, mode=0)
+    q = qkv[..., :Cc]
     G = torch.empty(B, H, 64, 64, device=qkv.device, dtype=f32)
+    # G[i, j] = (1/8) sum_t k[t, i] v[t, j]: sums of T products feed a softmax, so this stays on the SIMT kernel, which forms
+    # the full (hi + lo) x (hi + lo) products in fp32 (the three-MMA split drops lo x lo, visible in the detection scores)
+    L.check(L.lib().vilco_channel_attention(_p(qkv), _i64(lo(qkv)), _p(G), None, _i64(0), None, B, T, Cc, H, L.stream_ptr()),
+            "vilco_channel_attention")
+    A16 = softmax_rows(G, None, mode=0)                                   # (NP,B,H,64,64)
     y = empty16(B, T, Cc, device=qkv.device)
-    L.check(L.lib().vilco_channel_attention(_p(qkv), _i64(lo(qkv)), _p(G), _p(y), _i64(lo(y)), _p(tlen), B, T, Cc, H,
-                                            L.stream_ptr()), "vilco_channel_attention")
-    return (y, G) if return_G else y
+    # y[t, i] = sum_j q[t, j] A[i, j]
+    L.gemm(q, A16, y, M=T, N=64, K=64, a_rows=T, a_ld=C3, a_s=(64, T * C3), Z=(H, B), b_ld=64, b_s=(64 * 64, H * 64 * 64),
+           b_batched=True, d_ld=Cc, d_s=(64, T * Cc), a_lo=lo(qkv), b_lo=lo(A16), d_lo=lo(y))
+    return (y, A16) if return_A else y
+
+
+def channel_attention_bwd(dy, qkv, A16, H):
+    """backward of channel_attention: dy (B,T,C) fp32, qkv operand (NP,B,T,3C), A operand (NP,B,H,64,64) -> dqkv (B,T,3C) fp32.
+    Six launches of existing kernels: dy -> planes, dA = dy^T q, dq = dy A, softmax backward (dG as planes),
+    dk = (1/8) v dG^T, dv = (1/8) k dG."""
+    from . import backward as BW
+    _, B, T, C3 = qkv.shape
+    Cc = C3 // 3
+    q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+    dy16, _ = BW.to_planes(dy.reshape(-1, Cc))
+    dy16 = dy16.reshape(dy16.shape[0], B, T, Cc)
+    dqkv = torch.empty(B, T, C3, device=dy.device, dtype=f32)
+    dA = torch.empty(B, H, 64, 64, device=dy.device, dtype=f32)
+    # dA[i, j] = sum_t dy[t, i] q[t, j]
+    L.gemm(dy16, q, dA, M=64, N=64, K=T, a_rows=64, a_ld=Cc, a_s=(64, T * Cc), a_major=1, Z=(H, B), b_ld=C3, b_s=(64, T * C3),
+           b_batched=True, b_major=1, d_ld=64, d_s=(64 * 64, H * 64 * 64), a_lo=lo(dy16), b_lo=lo(qkv))
+    # dq[t, j] = sum_i dy[t, i] A[i, j]
+    L.gemm(dy16, A16, dqkv, M=T, N=64, K=64, a_rows=T, a_ld=Cc, a_s=(64, T * Cc), Z=(H, B), b_ld=64, b_s=(64 * 64, H * 64 * 64),
+           b_batched=True, b_major=1, d_ld=C3, d_s=(64, T * C3), a_lo=lo(dy16), b_lo=lo(A16))
+    _, dG16 = BW.softmax_bwd(dA, 1.0, P16=A16)                            # dG = A * (dA - rowsum(dA * A)) as planes
+    # dk[t, i] = (1/8) sum_j v[t, j] dG[i, j]
+    L.gemm(v, dG16, dqkv[..., Cc:2 * Cc], M=T, N=64, K=64, a_rows=T, a_ld=C3, a_s=(64, T * C3), Z=(H, B), b_ld=64,
+           b_s=(64 * 64, H * 64 * 64), b_batched=True, d_ld=C3, d_s=(64, T * C3), alpha=0.125, a_lo=lo(qkv), b_lo=lo(dG16))
+    # dv[t, j] = (1/8) sum_i k[t, i] dG[i, j]
+    L.gemm(k, dG16, dqkv[..., 2 * Cc:], M=T, N=64, K=64, a_rows=T, a_ld=C3, a_s=(64, T * C3), Z=(H, B), b_ld=64,
+           b_s=(64 * 64, H * 64 * 64), b_batched=True, b_major=1, d_ld=C3, d_s=(64, T * C3), alpha=0.125, a_lo=lo(qkv),
+           b_lo=lo(dG16))
+    return dqkv
 
 
 def ew(op, x, y=None, rowmul=None, colmul=None, out32=True, out16=False):

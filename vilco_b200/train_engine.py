@@ -337,18 +337,12 @@ class Tape:
 
     def channel_attention(self, qkv, H):
         q16 = self.planes(qkv)
-        y16, G = ops.channel_attention(q16, H, return_G=True)
+        y16, A16 = ops.channel_attention(q16, H, return_A=True)
         y = V(p16=y16)
 
         def bwd():
-            if y.g is None:
-                return
-            _, B, T, C3 = q16.shape
-            dqkv = torch.empty(B, T, C3, device=y.g.device, dtype=f32)
-            dA = torch.empty_like(G)
-            L.check(L.lib().vilco_channel_attention_bwd(_p(y.g.contiguous()), _p(q16), _i64(lo(q16)), _p(G), _p(dA), _p(dqkv),
-                                                        B, T, C3 // 3, H, L.stream_ptr()), "vilco_channel_attention_bwd")
-            self.acc(qkv, dqkv)
+            if y.g is not None:
+                self.acc(qkv, ops.channel_attention_bwd(y.g.contiguous(), q16, A16, H))
         self.nodes.append(bwd)
         return y
 
