@@ -502,3 +502,18 @@ def test_flat_adamw_checkpoint_round_trip_and_torch_compatibility():
         run(ps_b, opt_b, grads[2:])
         for p, q in zip(ps_b, ps_a):
             assert rel_max(p.detach(), q.detach()) < 5e-6, cls
+
+
+def test_training_loop_drives_the_loss_down():
+    """25 optimisation steps of trainer.Trainer (FlatAdamW, clip 1.0, dropout / drop-path ON) on one fixed batch."""
+    from vilco_b200.trainer import Trainer, make_optimizer
+    cfg = GG.small_cfg()
+    model, P = build_pair(cfg, 0)
+    model.train()
+    model.loss_normalizer_momentum = 1.0
+    videos = PR.synth_video_list(cfg, 4, seed=3, lens=[128, 100, 90, 128], text_lens=[40, 57, 33, 64], n_gt=[3, 2, 4, 1])
+    tr = Trainer(model, make_optimizer(model, {"type": "AdamW", "learning_rate": 3e-4, "weight_decay": 0.05}, flat=True),
+                 clip_grad_l2norm=1.0)
+    hist = [float(tr.step(videos)["final_loss"].detach()) for _ in range(25)]
+    assert all(np.isfinite(hist))
+    assert np.mean(hist[-3:]) < 0.4 * np.mean(hist[:3]), hist
