@@ -54,9 +54,9 @@ def synth_videos(n, seed, T=1024, Cin=4096, Ct=768, K=22, pin=False):
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
-    def __init__(self, gpu, enabled=True):
+    def __init__(self, gpu, enabled=True, period=0.1):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag, self.enabled = gpu, [], False, enabled
+        self.gpu, self.rows, self.stop_flag, self.enabled, self.period = gpu, [], False, enabled, period
 
     def run(self):
         if not self.enabled:     # only rank 0 polls: N pollers per node perturb the ranks they are supposed to observe
@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] +
                                  ["Active" if r & bit else "Not Active" for _, bit in bits])
-                time.sleep(0.1)
+                time.sleep(self.period)
             return
         except Exception:
             pass
@@ -295,7 +295,8 @@ def run_train_leg(args, model, rank, world, dist, barrier, local):
     for _ in range(args.warmup):
         tr.step(dev_set)
     barrier()
-    sampler = ClockSampler(local, enabled=rank == 0)
+    # (NVML queries contend with the ~2500 kernel launches of a training step for the driver: poll slowly here)
+    sampler = ClockSampler(local, enabled=rank == 0, period=0.4)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = L.launch_count()
