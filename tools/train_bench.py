@@ -70,7 +70,7 @@ def main():
         tr.step(vids)
         torch.cuda.synchronize()
         pr.disable()
-        pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+        pstats.Stats(pr).sort_stats(os.environ.get("CPROF_SORT", "cumulative")).print_stats(45)
         return
     n0 = L.launch_count()
     t0 = time.perf_counter()

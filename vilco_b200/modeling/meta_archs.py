@@ -147,17 +147,28 @@ class MemoryBank:
 
 
 class _TapeLoss(torch.autograd.Function):
-    """Connects the hand-written backward pass to torch autograd: backward(g) replays the tape scaled by g."""
+    """Connects the hand-written backward pass to torch autograd.  backward(g) replays the tape scaled by g.
+
+    Two modes: with a trainer (`model._direct_grads`) the kernels accumulate straight into the existing `.grad` buffers and
+    nothing is returned.  Otherwise — the reference's own loop, possibly under DistributedDataParallel — the parameters the
+    tape writes are inputs of this Function and their gradients are RETURNED, so torch's AccumulateGrad nodes (and with
+    them DDP's reducer hooks, GradScaler, hooks of the EWC / MAS code, ...) see them exactly as for the reference model."""
 
     @staticmethod
-    def forward(ctx, hook, value, run_backward):
-        ctx.run_backward = run_backward
+    def forward(ctx, hook, value, run_backward, keys, *params):
+        ctx.run_backward, ctx.keys, ctx.shapes = run_backward, keys, [(p.shape, p.dtype, p.device) for p in params]
         return value.detach().clone()
 
     @staticmethod
     def backward(ctx, g):
-        ctx.run_backward(float(g))
-        return torch.zeros_like(g), None, None
+        grads = ctx.run_backward(float(g)) or {}
+        outs = []
+        for k, (shape, dtype, dev) in zip(ctx.keys, ctx.shapes):
+            gk = grads.get(k)
+            # a listed parameter the tape did not reach (only possible in the very first step, before the set of live
+            # parameters is known) gets zeros: every input of a DDP-wrapped Function must receive a gradient
+            outs.append(gk if gk is not None else torch.zeros(shape, dtype=dtype, device=dev))
+        return (torch.zeros_like(g), None, None, None, *outs)
 
 
 class _Head(nn.Module):
@@ -374,6 +385,7 @@ class PtTransformer(nn.Module):
         """Register a trainer.FlatAdamW: its bf16 planes become the GEMM operands of this model (no re-packing per step)."""
         self._flat = opt
         self._packed = None
+        self._direct_grads = True
 
     def packed_weights(self):
         """bf16 operand copies of the parameters, re-packed whenever a parameter changed (optimizer step, load_state_dict,
@@ -605,7 +617,7 @@ class PtTransformer(nn.Module):
         # dropout / stochastic depth follow nn.Module.training exactly like the reference's nn.Dropout / AffineDropPath /
         # XLNet dropout (xlnet_config_*.json: 0.1); model.eval() + is_training=True gives the deterministic losses
         self._train_calls = getattr(self, "_train_calls", 0) + 1
-        sinks = self._grad_sinks()
+        sinks = self._grad_sinks() if getattr(self, "_direct_grads", False) else {}
         if self.training:
             tp = TE.Tape(W, dropout=self.train_dropout, droppath=self.train_droppath,
                          xl_dropout=getattr(self, "xl_dropout", 0.1) if self.use_xl else 0.0,   # xlnet_config_*.json: 0.1
@@ -678,6 +690,26 @@ class PtTransformer(nn.Module):
         names_, plist_, _ = self._param_table()
         named = dict(zip(names_, plist_))
         model = self
+        direct = bool(getattr(self, "_direct_grads", False))
+        # parameters only the torch-side glue reaches (target-assignment Gaussians, prompt pool, narration encoder): their
+        # gradients are computed inside run_backward with torch.autograd.grad — never by a nested .backward(), whose
+        # AccumulateGrad hooks would fire a second time under DistributedDataParallel — and delivered like the tape's
+        owned = [(k_, p_) for k_, p_ in zip(names_, plist_) if p_.requires_grad and (
+            k_ in ("mu", "sigma", "mu_reg_left", "sigma_reg_left", "mu_reg_right", "sigma_reg_right")
+            or k_.startswith(("prompt.", "narration_encoder.")))]
+        bias_params = [q_ for bl in self.list_bias_layers for q_ in bl.parameters()] if lg_leaf is not None else []
+        live = []
+        if not direct:
+            # autograd mode: every parameter whose gradient this Function will return (all trainable ones until the first
+            # backward has shown which ones the tape reaches)
+            known = getattr(self, "_live_keys", None)
+            owned_names = {k_ for k_, _ in owned}
+            for k_, p_ in zip(names_, plist_):
+                if not p_.requires_grad or k_.startswith("pets_emas.") or ".adapters." in k_:
+                    continue
+                if k_ in owned_names or known is None or k_ in known:
+                    live.append((k_, p_))
+        passed = {k_ for k_, _ in live}
 
         def run_backward(gscale):
             with torch.no_grad():
@@ -690,21 +722,41 @@ class PtTransformer(nn.Module):
                     ops._p(doffsets), ops._p(dwc), ops._p(dwl), ops._p(dwr), L.stream_ptr()), "vilco_mq_losses_bwd")
                 logitsV.g, offsetsV.g = dlogits, doffsets
                 model._last_head_grads = (dlogits, doffsets, pyr)   # kept for the gradient parity tests
+            owned_p = [p_ for _, p_ in owned]
+            owned_g = [None] * len(owned_p)
+
+            def glue_grads(tensors, grads, leaves):
+                """d(sum grads . tensors) / d(leaves + owned parameters + bias-layer parameters) without touching any .grad"""
+                ins = list(leaves) + owned_p + bias_params
+                out = torch.autograd.grad(tensors, ins, grads, allow_unused=True)
+                for i in range(len(owned_p)):
+                    g_ = out[len(leaves) + i]
+                    if g_ is not None:
+                        owned_g[i] = g_ if owned_g[i] is None else owned_g[i] + g_
+                for q_, g_ in zip(bias_params, out[len(leaves) + len(owned_p):]):
+                    if g_ is not None:       # BiC bias layers live in a plain python list outside the module tree
+                        q_.grad = g_.clone() if q_.grad is None else q_.grad + g_
+                return out[:len(leaves)]
+
             tensors, grads = list(extra), [torch.full_like(t_, gscale) for t_ in extra]
             if lg_leaf is not None and lg_biased is not lg_leaf:
-                tensors.append(lg_biased)        # through the bias layers (their alpha / beta get .grad here) to the raw logits
+                tensors.append(lg_biased)        # through the bias layers back to the raw logits
                 grads.append(dlogits)
             if tensors:
-                torch.autograd.backward(tensors, grads)
-            if lg_leaf is not None:
-                if lg_biased is not lg_leaf:
-                    logitsV.g = lg_leaf.grad
-                elif lg_leaf.grad is not None:
-                    logitsV.g = dlogits + lg_leaf.grad
-            if ssl_leaves is not None:
-                for f_, leaf in zip(fpn_lv, ssl_leaves):
-                    if leaf.grad is not None:
-                        tp.acc(f_, leaf.grad)
+                leaves = ([lg_leaf] if lg_leaf is not None else []) + (list(ssl_leaves) if ssl_leaves is not None else [])
+                lgr = glue_grads(tensors, grads, leaves)
+                if lg_leaf is not None:
+                    g_lg = lgr[0]
+                    if lg_biased is not lg_leaf:
+                        logitsV.g = g_lg
+                    elif g_lg is not None:
+                        logitsV.g = dlogits + g_lg
+                    lgr = lgr[1:]
+                if ssl_leaves is not None:
+                    for f_, g_ in zip(fpn_lv, lgr):
+                        if g_ is not None:
+                            tp.acc(f_, g_)
+            returned = {}
             with torch.no_grad():
                 tp.backward()
                 model._last_touch = (tp.n_nodes, dict(tp.touch), set(tp.G.keys()))
@@ -713,18 +765,38 @@ class PtTransformer(nn.Module):
                     if prm is None or not prm.requires_grad:
                         continue
                     g = TE.unpack_grad(key, g, prm).to(prm.dtype)
-                    if prm.grad is None:
+                    if direct:
+                        if prm.grad is None:
+                            prm.grad = g.clone()
+                        else:
+                            prm.grad.add_(g)  # in place: .grad is a view of the trainer's flat all-reduce buffer
+                    elif key in passed:
+                        returned[key] = g.contiguous()
+                    elif prm.grad is None:    # reached for the first time after the live set was recorded: assign directly
                         prm.grad = g.clone()
                     else:
-                        prm.grad.add_(g)      # in place: .grad may be a view of the trainer's flat all-reduce buffer
+                        prm.grad.add_(g)
+                model._live_keys = set(tp.G.keys())
             glue = [(t_, g_) for t_, g_ in ((wc, dwc), (wl, dwl), (wr, dwr)) if t_.requires_grad]
             if tin is not None and text.requires_grad and tin.g is not None:
                 glue.append((text, ops.unpack(tin.g)))
             if glue:
-                torch.autograd.backward([t_ for t_, _ in glue], [g_ for _, g_ in glue])
+                glue_grads([t_ for t_, _ in glue], [g_ for _, g_ in glue], [])
+            with torch.no_grad():
+                for (k_, p_), g_ in zip(owned, owned_g):
+                    if g_ is None:
+                        continue
+                    if direct or k_ not in passed:
+                        if p_.grad is None:
+                            p_.grad = g_.clone()
+                        else:
+                            p_.grad.add_(g_)
+                    else:
+                        returned[k_] = g_.contiguous()
+            return returned
 
         hook = torch.zeros((), device=dev, requires_grad=True)
-        final_t = _TapeLoss.apply(hook, final, run_backward)
+        final_t = _TapeLoss.apply(hook, final, run_backward, [k for k, _ in live], *[p_ for _, p_ in live])
         out = {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final_t}
         out.update(extra_named)
         return out

@@ -60,6 +60,8 @@ class Trainer:
             model.use_flat_optimizer(optimizer)
         else:
             self.grads = FlatGrads(model.parameters())
+            if hasattr(model, "_train_forward"):
+                model._direct_grads = True     # the backward kernels accumulate straight into the flat .grad views
 
     # ---- bucketed all-reduce -------------------------------------------------------------------------------------
     def _readiness(self):
