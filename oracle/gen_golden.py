@@ -243,6 +243,24 @@ def gen_nms_voting_golden():
     print("nms_voting ok", {k: v.shape for k, v in out.items() if k.endswith("_segs") and "_in_" not in k})
 
 
+def gen_optimizer_groups_golden():
+    """parameter grouping of the reference's make_optimizer (train_utils.py:68-143) on the small and the vilco model:
+    names per group (decay / no_decay / remain) — pins trainer.make_optimizer."""
+    import json
+    ref_shim.load()
+    import libs.utils.train_utils as TU
+    out = {}
+    for tag, c, yaml_name in (("small", small_cfg(), "mq_no_cl.yaml"), ("vilco", vilco_cfg(), "mq_vilco.yaml")):
+        model, _ = build_reference_model(c, seed=0 if tag == "small" else 1, yaml_name=yaml_name)
+        opt = TU.make_optimizer(model, {"type": "AdamW", "learning_rate": 1e-4, "weight_decay": 0.05, "momentum": 0.9})
+        names = {id(p): k for k, p in model.named_parameters()}
+        out[tag] = [{"weight_decay": g["weight_decay"], "params": sorted(names[id(p)] for p in g["params"])}
+                    for g in opt.param_groups]
+    with open(os.path.join(GOLDEN, "optimizer_groups.json"), "w") as f:
+        json.dump(out, f)
+    print("optimizer_groups:", {k: [len(g["params"]) for g in v] for k, v in out.items()})
+
+
 def gen_vilco_golden():
     """mq_vilco.yaml branches at inference: prompts prepended to the text, adapters on branch 0-4, EMA-adapter ensemble."""
     c = vilco_cfg()
@@ -345,3 +363,5 @@ if __name__ == "__main__":
         gen_distill_golden()
     if "voting" in what:
         gen_nms_voting_golden()
+    if "optimizer" in what:
+        gen_optimizer_groups_golden()

@@ -63,3 +63,37 @@ def test_no_fallback_without_gpu():
     from vilco_b200.utils import batched_nms
     with pytest.raises(Exception):
         batched_nms(torch.rand(8, 2), torch.rand(8), torch.zeros(8, dtype=torch.int64), 0.1, 1e-4, 200)
+
+
+def test_make_optimizer_groups_match_reference():
+    """trainer.make_optimizer puts every parameter into the same weight-decay group as the reference's make_optimizer
+    (MQ/libs/utils/train_utils.py:68-143; golden from the reference itself, oracle/gen_golden.py gen_optimizer_groups_golden)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from oracle import gen_golden as GG
+    from vilco_b200.config import mq_model_kwargs
+    from vilco_b200.modeling import make_meta_arch
+    from vilco_b200.trainer import make_optimizer
+    g = json.load(open(os.path.join(GOLDEN, "optimizer_groups.json")))
+    for tag, cfg in (("small", GG.small_cfg()), ("vilco", GG.vilco_cfg())):
+        kw = mq_model_kwargs(cfg.input_dim, cfg.embd_dim, cfg.n_head, cfg.max_seq_len, cfg.arch, cfg.num_classes, cfg.n_txt_in,
+                             cfg.regression_range)
+        if tag == "vilco":
+            kw["cl_cfg"].update(name="l2p", memory_size=1010, prompt_pool=True, pool_size=cfg.prompt_pool["pool_size"],
+                                topk=cfg.prompt_pool["top_k"], length=cfg.prompt_pool["length"], embed_dim=cfg.n_txt_in,
+                                narration_ssl=False, use_adapt=True, adapt_blocks=list(cfg.adapt_blocks))
+        model = make_meta_arch("LocPointTransformer", **kw)
+        opt = make_optimizer(model, {"type": "AdamW", "learning_rate": 1e-4, "weight_decay": 0.05})
+        names = {id(p): k for k, p in model.named_parameters()}
+        mine = {}
+        for gr in opt.param_groups:
+            for p in gr["params"]:
+                mine[names[id(p)]] = gr["weight_decay"]
+        ref = {}
+        for gr in g[tag]:
+            for k in gr["params"]:
+                ref.setdefault(k, gr["weight_decay"])
+        assert set(mine) == set(ref), (tag, sorted(set(mine) ^ set(ref))[:8])
+        wrong = [k for k in ref if mine[k] != ref[k]]
+        assert not wrong, (tag, wrong[:8])
