@@ -517,3 +517,24 @@ def test_training_loop_drives_the_loss_down():
     hist = [float(tr.step(videos)["final_loss"].detach()) for _ in range(25)]
     assert all(np.isfinite(hist))
     assert np.mean(hist[-3:]) < 0.4 * np.mean(hist[:3]), hist
+
+
+def test_eval_graph_follows_weight_updates():
+    """An EvalGraph captured before training must not keep reading the old packed weights: after optimizer steps its
+    results equal the eager evaluation of the updated model."""
+    from vilco_b200.trainer import Trainer, make_optimizer
+    cfg = GG.small_cfg()
+    model, P = build_pair(cfg, 0)
+    videos = PR.synth_video_list(cfg, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    model.eval()
+    g = model.make_eval_graph(2, text_len=64)
+    before = g.run(videos)
+    model.loss_normalizer = cfg.init_loss_norm
+    tr = Trainer(model, make_optimizer(model, {"type": "AdamW", "learning_rate": 1e-2, "weight_decay": 0.05}, flat=True), 1.0)
+    for _ in range(3):
+        tr.step(videos)
+    with torch.no_grad():
+        eager = model(videos, is_training=False)
+    after = g.run(videos)
+    assert rel_max(after[0]["scores"], eager[0]["scores"]) < 1e-4
+    assert rel_max(after[0]["scores"], before[0]["scores"]) > 1e-3      # the update is visible

@@ -1030,7 +1030,18 @@ class EvalGraph:
         self.tmask = torch.ones(batch_size, text_len, device=dev) if model.use_cross_modal else None
         self.tlens = torch.full((batch_size,), text_len, device=dev, dtype=torch.int32) if model.use_cross_modal else None
         self.launches = 0
-        model.packed_weights()
+        self._capture()
+        self._stage_f = torch.zeros(batch_size, Cin, T).pin_memory()
+        self._stage_t = torch.zeros(batch_size, Ct, text_len).pin_memory() if model.use_cross_modal else None
+
+    def _weights_sig(self):
+        m = self.model
+        W = m.packed_weights()
+        return (id(W), m._packed_key, getattr(m, "_packed_epoch", 0), getattr(m, "_packed_ema_key", None))
+
+    def _capture(self):
+        """(Re)capture the graph against the model's current packed weights."""
+        self._sig = self._weights_sig()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):   # warm-up outside capture (lazy cudaFuncSetAttribute, allocator pools)
@@ -1042,8 +1053,12 @@ class EvalGraph:
         with torch.cuda.graph(self.graph):
             self.out = self._step()
         self.launches = L.launch_count() - n0
-        self._stage_f = torch.zeros(batch_size, Cin, T).pin_memory()
-        self._stage_t = torch.zeros(batch_size, Ct, text_len).pin_memory() if model.use_cross_modal else None
+
+    def refresh(self):
+        """The captured graph reads the packed weight tensors that existed at capture time: after an optimizer step,
+        load_state_dict or a precision switch some of them are new tensors, so the graph is captured again."""
+        if self._weights_sig() != self._sig:
+            self._capture()
 
     def _step(self):
         m = self.model
@@ -1120,6 +1135,7 @@ class EvalGraph:
     def infer_stream(self, batches):
         """Generator over result lists, one per batch of `batches` (an iterable of video_list).  Double-buffered:
         while the graph of batch i runs, the inputs of batch i+1 are copied host->device on a side stream."""
+        self.refresh()
         if not hasattr(self, "_slots"):
             self._slots = [self._new_slot(), self._new_slot()]
             self._copy_stream = torch.cuda.Stream()
@@ -1161,6 +1177,7 @@ class EvalGraph:
             yield PtTransformer._to_results(pvl, *ps["out_h"])
 
     def run(self, video_list):
+        self.refresh()
         self.load_inputs(video_list)
         self.graph.replay()
         segs, scores, labels, count = self.out
