@@ -341,7 +341,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="clips per step per GPU")
-    ap.add_argument("--train-batch", type=int, default=16, help="clips per training step per GPU (0 = skip the training leg)")
+    ap.add_argument("--train-batch", type=int, default=32, help="clips per training step per GPU (0 = skip the training leg)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "bf16x3"])
     ap.add_argument("--ref-videos", type=int, default=4, help="clips per CPU-baseline sample")
