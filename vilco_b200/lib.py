@@ -66,10 +66,16 @@ def launch_count():
     return int(lib().vilco_launch_count())
 
 
+_dev_index = None
+
+
 def stream_ptr():
-    """raw handle of torch's current CUDA stream on the current device (the cheap private accessor: this is called once per
-    kernel launch, ~2000 times per training step)."""
-    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    """raw handle of torch's current CUDA stream (the cheap private accessor: this is called once per kernel launch, ~1500
+    times per training step).  One process drives one GPU, so the device index is looked up once."""
+    global _dev_index
+    if _dev_index is None:
+        _dev_index = torch.cuda.current_device()
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(_dev_index))
 
 
 def ptr(t):
@@ -82,31 +88,45 @@ def default_gemm_impl():
     return 1 if os.environ.get("VILCO_GEMM", "tc") == "simt" else 0
 
 
+_gemm_cache = {}     # descriptor without the pointers -> prepared VilcoGemm (a training step issues ~570 GEMMs from ~60 shapes)
+_gemm_fn = None
+
+
 def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), d_s=(0, 0), Z=(1, 1), taps=1,
          b_major=0, b_batched=False, alpha=1.0, bias=None, rowmul=None, rowmul_zs=0, act=ACT_NONE,
          colscale=None, resid=None, resid_masked=False, impl=None, a_lo=0, b_lo=0, d_lo=0, band=(0, 0), a_major=0):
     """Raw descriptor-level call of ``vilco_gemm`` (see include/vilco_b200.h for the contract)."""
-    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
-    assert D.dtype in (torch.float32, torch.bfloat16)
-    for t in (bias, rowmul, colscale, resid):
-        assert t is None or (t.dtype == torch.float32 and t.is_cuda)
-    g = VilcoGemm()
-    g.A, g.a_ld, g.a_s1, g.a_s2, g.a_rows = A.data_ptr(), a_ld, a_s[0], a_s[1], a_rows
-    g.a_lo, g.b_lo, g.d_lo = a_lo, b_lo, d_lo
-    g.B, g.b_ld, g.b_s1, g.b_s2 = B.data_ptr(), b_ld, b_s[0], b_s[1]
-    g.b_major, g.b_batched = b_major, int(b_batched)
-    g.M, g.N, g.K, g.taps, g.Z1, g.Z2 = M, N, K, taps, Z[0], Z[1]
-    g.D, g.d_dtype, g.d_ld, g.d_s1, g.d_s2 = D.data_ptr(), (F32 if D.dtype == torch.float32 else BF16), d_ld, d_s[0], d_s[1]
-    g.alpha = alpha
+    global _gemm_fn
+    d32 = D.dtype == torch.float32
+    key = (M, N, K, a_rows, a_ld, b_ld, d_ld, a_s, b_s, d_s, Z, taps, b_major, b_batched, alpha, rowmul_zs, act, resid_masked,
+           impl, a_lo, b_lo, d_lo, band, a_major, d32)
+    g = _gemm_cache.get(key)
+    if g is None:
+        assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
+        assert D.dtype in (torch.float32, torch.bfloat16)
+        g = VilcoGemm()
+        g.a_ld, g.a_s1, g.a_s2, g.a_rows = a_ld, a_s[0], a_s[1], a_rows
+        g.a_lo, g.b_lo, g.d_lo = a_lo, b_lo, d_lo
+        g.b_ld, g.b_s1, g.b_s2 = b_ld, b_s[0], b_s[1]
+        g.b_major, g.b_batched = b_major, int(b_batched)
+        g.M, g.N, g.K, g.taps, g.Z1, g.Z2 = M, N, K, taps, Z[0], Z[1]
+        g.d_dtype, g.d_ld, g.d_s1, g.d_s2 = (F32 if d32 else BF16), d_ld, d_s[0], d_s[1]
+        g.alpha = alpha
+        g.rowmul_zs = rowmul_zs
+        g.act = act
+        g.resid_masked = int(resid_masked)
+        g.impl = default_gemm_impl() if impl is None else impl
+        g.band_lo, g.band_hi = band
+        g.a_major = a_major
+        _gemm_cache[key] = g
+        if _gemm_fn is None:
+            _gemm_fn = lib().vilco_gemm
+    g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
     g.bias = bias.data_ptr() if bias is not None else None
     g.rowmul = rowmul.data_ptr() if rowmul is not None else None
-    g.rowmul_zs = rowmul_zs
-    g.act = act
     g.colscale = colscale.data_ptr() if colscale is not None else None
     g.resid = resid.data_ptr() if resid is not None else None
-    g.resid_masked = int(resid_masked)
-    g.impl = default_gemm_impl() if impl is None else impl
-    g.band_lo, g.band_hi = band
-    g.a_major = a_major
-    check(lib().vilco_gemm(C.byref(g), stream_ptr()), "vilco_gemm")
+    rc = _gemm_fn(C.byref(g), stream_ptr())
+    if rc != 0:
+        check(rc, "vilco_gemm")
     return D
