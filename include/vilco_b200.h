@@ -141,6 +141,13 @@ int vilco_softmax_rows(const float* S, const float* BD, const float* kmask, void
 int vilco_local_attention(const void* q, const void* k, const void* v, const float* mask, const float* rel_pe, void* out,
                           int64_t lo, int B, int T, int C, int H, int W, void* stream);
 
+/* Backward of vilco_local_attention (LocalMaskedMHCA core, blocks.py:1140-1200): dO (B,T,C) fp32 -> dq, dk, dv (B,T,C) fp32.
+ * The probabilities are recomputed; scratch_p / scratch_ds are (B, H, T, W) fp32 work buffers (P and dS rows). The gradient
+ * of rel_pe is not produced (use_rel_pe is off in every reference config). */
+int vilco_local_attention_bwd(const float* dO, const void* q, const void* k, const void* v, int64_t lo, const float* mask,
+                              const float* rel_pe, float* scratch_p, float* scratch_ds, float* dq, float* dk, float* dv,
+                              int B, int T, int C, int H, int W, void* stream);
+
 /* ChannelAttention core (blocks.py:423-436): qkv (B,T,3C) bf16 -> y (B,T,C) bf16;  G is a (B,H,64,64) fp32 scratch.
  * tlen (B,) or NULL limits the tokens summed in k^T v (the reference sums over every position of its padded batch). */
 /* (y may be NULL: only G is computed) */

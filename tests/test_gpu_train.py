@@ -538,3 +538,32 @@ def test_eval_graph_follows_weight_updates():
     after = g.run(videos)
     assert rel_max(after[0]["scores"], eager[0]["scores"]) < 1e-4
     assert rel_max(after[0]["scores"], before[0]["scores"]) > 1e-3      # the update is visible
+
+
+@pytest.mark.parametrize("B,H,T,d,W,valid", [(2, 2, 64, 64, 9, [64, 41]), (1, 4, 200, 96, 19, [173]), (2, 2, 37, 32, 5, [37, 20])])
+def test_local_attention_backward(B, H, T, d, W, valid):
+    """LocalMaskedMHCA core (window W): dq / dk / dv of vilco_local_attention_bwd vs torch autograd through the same banded
+    attention written densely (scale 1/sqrt(d), -1e4 on padded keys, -inf outside the band / sequence, padded query rows
+    zeroed — blocks.py:1140-1200); head dim 96 = the NLQ configuration."""
+    from vilco_b200 import backward as BW
+    from vilco_b200 import ops
+    torch.manual_seed(0)
+    C, w = H * d, W // 2
+    mask = (torch.arange(T, device="cuda")[None, :] < torch.tensor(valid, device="cuda")[:, None]).float().contiguous()
+    q, k, v = (ops.merge16(ops.split16(torch.randn(B, T, C, device="cuda"))).requires_grad_(True) for _ in range(3))
+    qh, kh, vh = (t.view(B, T, H, d).permute(0, 2, 1, 3) for t in (q, k, v))
+    S = (qh / math.sqrt(d)) @ kh.transpose(-1, -2)
+    i = torch.arange(T, device="cuda")
+    band = (i[:, None] - i[None, :]).abs() <= w
+    S = S + (-1e4) * (1 - mask)[:, None, None, :]
+    S = S.masked_fill(~band[None, None], float("-inf"))
+    P = torch.softmax(S, -1) * mask[:, None, :, None]
+    O = (P @ vh).permute(0, 2, 1, 3).reshape(B, T, C)
+    q16, k16, v16 = (ops.split16(t.detach()) for t in (q, k, v))
+    out = ops.merge16(ops.local_attention(q16, k16, v16, mask, H, W))
+    assert rel_max(out, O.detach()) < 2e-5
+    dO = torch.randn(B, T, C, device="cuda")
+    O.backward(dO)
+    dq, dk, dv = BW.local_attention_bwd(dO, q16, k16, v16, mask, H, W)
+    for name, got, ref in (("dq", dq, q.grad), ("dk", dk, k.grad), ("dv", dv, v.grad)):
+        assert rel_max(got, ref) < 2e-5, name

@@ -217,3 +217,15 @@ def attention_bwd(dO, q16, k16, v16, kmask, H, scale):
     dk = ops.attn_pv(dS16, q16, H, Tq, out32=True, a_trans=True, M=Tk)   # dK_h = dS^T Q_h
     dv = ops.attn_pv(P16, dO16, H, Tq, out32=True, a_trans=True, M=Tk)   # dV_h = P^T dO_h
     return dq, dk, dv
+
+
+def local_attention_bwd(dO, q16, k16, v16, mask, H, W, rel_pe=None):
+    """forward: ops.local_attention (LocalMaskedMHCA core).  dO (B,T,C) fp32, q16 / k16 / v16 (NP,B,T,C) -> (dq, dk, dv) fp32."""
+    _, B, T, Cc = q16.shape
+    dq, dk, dv = (torch.empty(B, T, Cc, device=dO.device, dtype=f32) for _ in range(3))
+    sp = torch.empty(B, H, T, W, device=dO.device, dtype=f32)
+    sds = torch.empty(B, H, T, W, device=dO.device, dtype=f32)
+    L.check(L.lib().vilco_local_attention_bwd(_p(dO.contiguous()), _p(q16), _p(k16), _p(v16), _i64(lo(q16)), _p(mask), _p(rel_pe),
+                                              _p(sp), _p(sds), _p(dq), _p(dk), _p(dv), B, T, Cc, H, W, L.stream_ptr()),
+            "vilco_local_attention_bwd")
+    return dq, dk, dv

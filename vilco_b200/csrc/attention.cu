@@ -253,6 +253,177 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LwParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// local (windowed) attention, backward.  Two passes with the staging scheme of the forward kernel:
+//   pass Q (one warp per query t): recompute the W probabilities, dP[jj] = dO[t] . v[j], dS = P * (dP - sum P dP),
+//          dq[t] = scale * sum_jj dS[jj] k[j]; P and dS rows go to a (B, H, T, W) fp32 scratch
+//   pass KV (one warp per key j): dk[j] = scale * sum_jj dS[t, jj] q[t], dv[j] = sum_jj P[t, jj] dO[t] with t = j + w - jj
+//          (the window is symmetric, so the queries that see key j are t in [j - w, j + w]); no atomics.
+// ---------------------------------------------------------------------------------------------
+struct LwBwdParams {
+  const __nv_bfloat16 *q, *k, *v; const float* mask; const float* rel_pe; const float* dO;
+  float *sP, *sdS;               // scratch (B, H, T, W)
+  float *dq, *dk, *dv;           // (B, T, C) fp32
+  long long lo;
+  int B, T, C, H, d, W; float scale;
+};
+
+__global__ void __launch_bounds__(256) local_attn_bwd_q_kernel(const LwBwdParams p) {
+  extern __shared__ float lw_smem[];
+  const int w = p.W / 2;
+  const int t0 = blockIdx.x * LW_TI, h = blockIdx.y, b = blockIdx.z;
+  const int nrows = LW_TI + 2 * w;
+  float* sk = lw_smem;
+  float* sv = lw_smem + (size_t)nrows * p.d;
+  const long long base = (long long)b * p.T * p.C + (long long)h * p.d;
+  const int half = p.d / 2;
+  for (int idx = threadIdx.x; idx < nrows * half; idx += blockDim.x) {
+    const int r = idx / half, c = (idx - r * half) * 2;
+    const int t = t0 - w + r;
+    if (t >= 0 && t < p.T) {
+      const float2 kk = ld2_split(p.k + base + (long long)t * p.C + c, p.lo);
+      const float2 vv = ld2_split(p.v + base + (long long)t * p.C + c, p.lo);
+      sk[r * p.d + c] = kk.x; sk[r * p.d + c + 1] = kk.y;
+      sv[r * p.d + c] = vv.x; sv[r * p.d + c + 1] = vv.y;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const float* mk = p.mask + (long long)b * p.T;
+  for (int qi = warp; qi < LW_TI; qi += nwarp) {
+    const int t = t0 + qi;
+    if (t >= p.T) break;
+    float* rowP = p.sP + (((long long)b * p.H + h) * p.T + t) * p.W;
+    float* rowS = p.sdS + (((long long)b * p.H + h) * p.T + t) * p.W;
+    float* dqo = p.dq + base + (long long)t * p.C;
+    if (mk[t] == 0.f) {      // padded query: its probabilities were zeroed in the forward pass
+      for (int jj = lane; jj < p.W; jj += 32) { rowP[jj] = 0.f; rowS[jj] = 0.f; }
+      for (int c = lane * 2; c < p.d; c += 64) { dqo[c] = 0.f; dqo[c + 1] = 0.f; }
+      continue;
+    }
+    float qv[LW_MAXD / 32], gv[LW_MAXD / 32];
+#pragma unroll
+    for (int u = 0; u < LW_MAXD / 64; ++u) {
+      const int c = lane * 2 + u * 64;
+      if (c < p.d) {
+        const float2 x = ld2_split(p.q + base + (long long)t * p.C + c, p.lo);
+        qv[2 * u] = x.x * p.scale; qv[2 * u + 1] = x.y * p.scale;
+        gv[2 * u] = p.dO[base + (long long)t * p.C + c]; gv[2 * u + 1] = p.dO[base + (long long)t * p.C + c + 1];
+      } else { qv[2 * u] = qv[2 * u + 1] = gv[2 * u] = gv[2 * u + 1] = 0.f; }
+    }
+    float sc0 = -INFINITY, sc1 = -INFINITY, sc2 = -INFINITY, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+    for (int jj = 0; jj < p.W; ++jj) {
+      const int j = t - w + jj;
+      float part = 0.f, dpart = 0.f;
+      if (j >= 0 && j < p.T) {
+        const float* kr = sk + (qi + jj) * p.d;
+        const float* vr = sv + (qi + jj) * p.d;
+#pragma unroll
+        for (int u = 0; u < LW_MAXD / 64; ++u) {
+          const int c = lane * 2 + u * 64;
+          if (c < p.d) {
+            part = fmaf(qv[2 * u], kr[c], part); part = fmaf(qv[2 * u + 1], kr[c + 1], part);
+            dpart = fmaf(gv[2 * u], vr[c], dpart); dpart = fmaf(gv[2 * u + 1], vr[c + 1], dpart);
+          }
+        }
+      }
+      float s = warp_sum(part);
+      const float dpv = warp_sum(dpart);
+      if (j < 0 || j >= p.T) s = -INFINITY;
+      else {
+        if (p.rel_pe) s += p.rel_pe[h * p.W + jj];
+        if (mk[j] == 0.f) s += -1e4f;
+      }
+      if ((jj & 31) == lane) {
+        if (jj < 32) { sc0 = s; dp0 = dpv; } else if (jj < 64) { sc1 = s; dp1 = dpv; } else { sc2 = s; dp2 = dpv; }
+      }
+    }
+    const float mx = warp_max(fmaxf(fmaxf(sc0, sc1), sc2));
+    float e0 = sc0 == -INFINITY ? 0.f : __expf(sc0 - mx);
+    float e1 = sc1 == -INFINITY ? 0.f : __expf(sc1 - mx);
+    float e2 = sc2 == -INFINITY ? 0.f : __expf(sc2 - mx);
+    const float inv = 1.0f / warp_sum(e0 + e1 + e2);
+    e0 *= inv; e1 *= inv; e2 *= inv;
+    const float delta = warp_sum(e0 * dp0 + e1 * dp1 + e2 * dp2);
+    const float ds0 = e0 * (dp0 - delta), ds1 = e1 * (dp1 - delta), ds2 = e2 * (dp2 - delta);
+    if (lane < p.W) { rowP[lane] = e0; rowS[lane] = ds0; }
+    if (lane + 32 < p.W) { rowP[lane + 32] = e1; rowS[lane + 32] = ds1; }
+    if (lane + 64 < p.W) { rowP[lane + 64] = e2; rowS[lane + 64] = ds2; }
+    float acc[LW_MAXD / 32];
+#pragma unroll
+    for (int u = 0; u < LW_MAXD / 32; ++u) acc[u] = 0.f;
+    for (int jj = 0; jj < p.W; ++jj) {
+      const int j = t - w + jj;
+      const float ds = __shfl_sync(0xffffffffu, jj < 32 ? ds0 : (jj < 64 ? ds1 : ds2), jj & 31);
+      if (j < 0 || j >= p.T) continue;
+      const float* kr = sk + (qi + jj) * p.d;
+#pragma unroll
+      for (int u = 0; u < LW_MAXD / 64; ++u) {
+        const int c = lane * 2 + u * 64;
+        if (c < p.d) { acc[2 * u] = fmaf(ds, kr[c], acc[2 * u]); acc[2 * u + 1] = fmaf(ds, kr[c + 1], acc[2 * u + 1]); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LW_MAXD / 64; ++u) {
+      const int c = lane * 2 + u * 64;
+      if (c < p.d) { dqo[c] = acc[2 * u] * p.scale; dqo[c + 1] = acc[2 * u + 1] * p.scale; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) local_attn_bwd_kv_kernel(const LwBwdParams p) {
+  extern __shared__ float lw_smem[];
+  const int w = p.W / 2;
+  const int t0 = blockIdx.x * LW_TI, h = blockIdx.y, b = blockIdx.z;
+  const int nrows = LW_TI + 2 * w;
+  float* sq = lw_smem;                              // queries  t0 - w .. t0 + TI + w
+  float* sg = lw_smem + (size_t)nrows * p.d;        // dO rows of the same queries
+  const long long base = (long long)b * p.T * p.C + (long long)h * p.d;
+  const int half = p.d / 2;
+  for (int idx = threadIdx.x; idx < nrows * half; idx += blockDim.x) {
+    const int r = idx / half, c = (idx - r * half) * 2;
+    const int t = t0 - w + r;
+    if (t >= 0 && t < p.T) {
+      const float2 qq = ld2_split(p.q + base + (long long)t * p.C + c, p.lo);
+      sq[r * p.d + c] = qq.x; sq[r * p.d + c + 1] = qq.y;
+      sg[r * p.d + c] = p.dO[base + (long long)t * p.C + c]; sg[r * p.d + c + 1] = p.dO[base + (long long)t * p.C + c + 1];
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int ki = warp; ki < LW_TI; ki += nwarp) {
+    const int j = t0 + ki;
+    if (j >= p.T) break;
+    float ak[LW_MAXD / 32], av[LW_MAXD / 32];
+#pragma unroll
+    for (int u = 0; u < LW_MAXD / 32; ++u) { ak[u] = 0.f; av[u] = 0.f; }
+    for (int jj = 0; jj < p.W; ++jj) {
+      const int t = j + w - jj;                     // the query for which key j sits in window slot jj
+      if (t < 0 || t >= p.T) continue;
+      const long long so = (((long long)b * p.H + h) * p.T + t) * p.W + jj;
+      const float ds = p.sdS[so], pp = p.sP[so];
+      const float* qr = sq + (t - (t0 - w)) * p.d;
+      const float* gr = sg + (t - (t0 - w)) * p.d;
+#pragma unroll
+      for (int u = 0; u < LW_MAXD / 64; ++u) {
+        const int c = lane * 2 + u * 64;
+        if (c < p.d) {
+          ak[2 * u] = fmaf(ds, qr[c], ak[2 * u]); ak[2 * u + 1] = fmaf(ds, qr[c + 1], ak[2 * u + 1]);
+          av[2 * u] = fmaf(pp, gr[c], av[2 * u]); av[2 * u + 1] = fmaf(pp, gr[c + 1], av[2 * u + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LW_MAXD / 64; ++u) {
+      const int c = lane * 2 + u * 64;
+      if (c < p.d) {
+        p.dk[base + (long long)j * p.C + c] = ak[2 * u] * p.scale; p.dk[base + (long long)j * p.C + c + 1] = ak[2 * u + 1] * p.scale;
+        p.dv[base + (long long)j * p.C + c] = av[2 * u]; p.dv[base + (long long)j * p.C + c + 1] = av[2 * u + 1];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // channel attention.  qkv: (B, T, 3C) bf16 with column = which*C + h*64 + d  (d = 64 fixed).
 // phase 1: G[b,h] (64x64 fp32, zero-initialised by the caller) += sum over a T chunk of (k*scale)^T v
 // phase 2: A = softmax_rows(G[b,h]);  y[t, h*64 + i] = sum_j A[i,j] q[t, j]
@@ -526,6 +697,36 @@ extern "C" int vilco_local_attention(const void* q, const void* k, const void* v
   }
   dim3 grid((T + LW_TI - 1) / LW_TI, H, B);
   local_attn_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_local_attention_bwd(const float* dO, const void* q, const void* k, const void* v, int64_t lo,
+                                         const float* mask, const float* rel_pe, float* scratch_p, float* scratch_ds, float* dq,
+                                         float* dk, float* dv, int B, int T, int C, int H, int W, void* stream) {
+  VILCO_CHECK_ARG(dO && q && k && v && mask && scratch_p && scratch_ds && dq && dk && dv, "vilco_local_attention_bwd: null pointer");
+  VILCO_CHECK_ARG(H > 0 && C % H == 0, "vilco_local_attention_bwd: C %% H != 0");
+  const int d = C / H;
+  VILCO_CHECK_ARG(d % 8 == 0 && d <= LW_MAXD, "vilco_local_attention_bwd: head dim %d unsupported", d);
+  VILCO_CHECK_ARG(W >= 3 && (W & 1) && W <= LW_MAXW, "vilco_local_attention_bwd: window %d unsupported (odd, 3..%d)", W, LW_MAXW);
+  LwBwdParams p{};
+  p.q = static_cast<const __nv_bfloat16*>(q); p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v); p.mask = mask; p.rel_pe = rel_pe; p.dO = dO;
+  p.sP = scratch_p; p.sdS = scratch_ds; p.dq = dq; p.dk = dk; p.dv = dv; p.lo = lo;
+  p.B = B; p.T = T; p.C = C; p.H = H; p.d = d; p.W = W; p.scale = 1.0f / sqrtf(static_cast<float>(d));
+  const size_t smem = (size_t)2 * (LW_TI + 2 * (W / 2)) * d * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    const int mx = 2 * (LW_TI + LW_MAXW) * LW_MAXD * (int)sizeof(float);
+    VILCO_CUDA(cudaFuncSetAttribute(local_attn_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    VILCO_CUDA(cudaFuncSetAttribute(local_attn_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    configured = true;
+  }
+  dim3 grid((T + LW_TI - 1) / LW_TI, H, B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  local_attn_bwd_q_kernel<<<grid, 256, smem, st>>>(p);
+  VILCO_LAUNCH_CHECK();
+  local_attn_bwd_kv_kernel<<<grid, 256, smem, st>>>(p);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
