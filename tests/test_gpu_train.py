@@ -567,3 +567,41 @@ def test_local_attention_backward(B, H, T, d, W, valid):
     dq, dk, dv = BW.local_attention_bwd(dO, q16, k16, v16, mask, H, W)
     for name, got, ref in (("dq", dq, q.grad), ("dk", dk, k.grad), ("dv", dv, v.grad)):
         assert rel_max(got, ref) < 2e-5, name
+
+
+def test_class_incremental_flow():
+    """The query-incremental loop in miniature (what train_cl.py does between sub-tasks): train on 3 classes, evaluate,
+    augment_classification(+3), new optimizer, train on all 6 classes, evaluate.  Checks that the grown classifier / the
+    grown mu, sigma are live in the CUDA path, that old-class weights are carried over, and that inference follows."""
+    from vilco_b200.config import mq_model_kwargs
+    from vilco_b200.modeling import make_meta_arch
+    from vilco_b200.trainer import Trainer, make_optimizer
+    cfg = GG.small_cfg()
+    torch.manual_seed(0)
+    model = make_meta_arch("LocPointTransformer", **mq_model_kwargs(cfg.input_dim, cfg.embd_dim, cfg.n_head, cfg.max_seq_len,
+                                                                    cfg.arch, 3, cfg.n_txt_in, cfg.regression_range)).cuda()
+    videos = PR.synth_video_list(cfg, 4, seed=8, lens=[128, 100, 90, 128], text_lens=[40, 57, 33, 64], n_gt=[3, 2, 4, 1])
+    task0 = [dict(v, labels=v["labels"] % 3) for v in videos]
+    model.train()
+    tr = Trainer(model, make_optimizer(model, {"type": "AdamW", "learning_rate": 3e-4, "weight_decay": 0.05}, flat=True), 1.0)
+    l0 = [float(tr.step(task0)["final_loss"].detach()) for _ in range(6)]
+    model.eval()
+    with torch.no_grad():
+        r0 = model(task0[:1], is_training=False)
+    assert int(r0[0]["labels"].max()) <= 2
+    w_old = model.cls_head.cls_head.conv.weight.detach().clone()
+    mu_old = model.mu.detach().clone()
+    model.augment_classification(3, "cuda")
+    model.n_known = 3
+    assert model.num_classes == 6 and model.cls_head.cls_head.conv.weight.shape[0] == 6 and model.mu.shape[0] == 6
+    assert torch.equal(model.cls_head.cls_head.conv.weight[:3].detach(), w_old) and torch.equal(model.mu[:3].detach(), mu_old)
+    model.train()
+    tr = Trainer(model, make_optimizer(model, {"type": "AdamW", "learning_rate": 3e-4, "weight_decay": 0.05}, flat=True), 1.0)
+    l1 = [float(tr.step(videos)["final_loss"].detach()) for _ in range(6)]
+    assert all(np.isfinite(l0 + l1)) and l1[-1] < l1[0]
+    assert not torch.equal(model.cls_head.cls_head.conv.weight[3:].detach(), torch.zeros_like(model.cls_head.cls_head.conv.weight[3:]))
+    model.eval()
+    with torch.no_grad():
+        logits, _, _ = model(videos[:1], is_training=False, get_emb=True)
+        r1 = model(videos[:1], is_training=False)
+    assert logits[0].shape[-1] == 6 and len(r1[0]["scores"]) > 0
