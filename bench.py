@@ -319,7 +319,19 @@ def run_train_leg(args, model, rank, world, dist, barrier, local):
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    t_dev, t_e2e = max_over_ranks([t_dev, t_e2e], device="cuda")
+    # the reference's own batch size (train_cfg.batch_size 2 per GPU): launch-bound, reported for context
+    small = dev_set[:2]
+    for _ in range(2):
+        tr.step(small)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(5):
+        tr.step(small)
+    s1.record()
+    barrier()
+    t_small = s0.elapsed_time(s1) * 1e-3
+    t_dev, t_e2e, t_small = max_over_ranks([t_dev, t_e2e, t_small], device="cuda")
     mem = torch.cuda.max_memory_allocated() / 2 ** 30
     model.eval()
     h2d = sum(v["feats"].numel() * 4 + v["prompt_feature"].numel() * 4 for v in host_sets[0])
@@ -332,6 +344,8 @@ def run_train_leg(args, model, rank, world, dist, barrier, local):
             "grad_bytes_allreduced_per_step": int(4 * sum(b - a for a, b in opt.live_ranges())) if world > 1 else 0,
             "allreduce": ("bucketed (128 MB), launched as the backward completes each bucket" if tr.overlap else "one call after the backward") if world > 1 else None,
             "live_parameters": int(sum(b - a for a, b in opt.live_ranges())), "all_parameters": int(opt.n), "last_loss": last, "peak_mem_gib": mem,
+            "batch2": {"value": world * 2 * 5 / t_small, "unit": "videos/s", "ms_per_step": 1e3 * t_small / 5,
+                       "note": "same step at the reference's 2 clips per GPU: bound by the ~1500 kernel launches issued from Python"},
             "clocks": sampler.summary()}
 
 
