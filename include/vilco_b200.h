@@ -296,6 +296,18 @@ int vilco_mq_losses_bwd(const float* logits, const float* offsets, const float* 
                         const unsigned int* smax, int B, int P, int K, float alpha, float gamma, float norm, float w_reg,
                         float w_al, float* dlogits, float* doffsets, float* dw_cls, float* dw_l, float* dw_r, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Evaluation tail (host function, no kernel launch; all pointers are HOST pointers): the greedy matching loop of
+ * compute_average_precision_detection, MQ/libs/utils/metrics.py:277-346 (tIoU = segment_iou :348-372, float64) for the
+ * predictions and ground truths of ONE label.  pred_seg (n_pred, 2) sorted by descending score; pred_vid[i] = dense index
+ * of the prediction's video among the videos that own ground truth of this label, -1 if it has none (false positive at
+ * every threshold, :308-312); ground-truth rows are grouped by video in their original order: video v owns rows
+ * gt_start[v] .. gt_start[v+1]-1 of gt_seg (n_gt, 2).  Output tp (n_thr, n_pred) bytes: 1 = true positive; every other
+ * prediction is a false positive (fp = 1 - tp).
+ * ------------------------------------------------------------------------------------ */
+int vilco_ap_match(const double* pred_seg, const int64_t* pred_vid, int64_t n_pred, const double* gt_seg,
+                   const int64_t* gt_start, int64_t n_vid, const double* tiou_thr, int n_thr, uint8_t* tp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,8 +20,11 @@ def test_install_makes_the_reference_callers_use_vilco_b200():
     import libs.utils as lu
     import libs.utils.train_utils as tu
     ref_make, ref_nms = lm.make_meta_arch, lu.batched_nms
-    saved = {(m, n): getattr(m, n) for m in (lm, lu, tu, lm.meta_archs if hasattr(lm, "meta_archs") else lm)
-             for n in dir(m) if n in ("make_meta_arch", "make_backbone", "make_neck", "make_generator", "MaskedConv1D",
+    import libs.utils.metrics as lmet
+    import libs.utils.get_retrieval_performance as lret
+    saved = {(m, n): getattr(m, n) for m in (lm, lu, tu, lmet, lret, lm.meta_archs if hasattr(lm, "meta_archs") else lm)
+             for n in dir(m) if n in ("ANETdetection", "evaluation_retrieval", "Moment_Retrieval",
+                                      "compute_average_precision_detection","make_meta_arch", "make_backbone", "make_neck", "make_generator", "MaskedConv1D",
                                       "MaskedMHCA", "MaskedMHA", "LayerNorm", "TransformerBlock", "Scale", "AffineDropPath",
                                       "BiasLayer", "batched_nms", "XLNetModel", "XLNetLMHeadModel")}
     import vilco_b200.compat as compat
@@ -31,6 +34,9 @@ def test_install_makes_the_reference_callers_use_vilco_b200():
         assert ("libs.modeling", "make_meta_arch") in patched and ("libs.utils", "batched_nms") in patched
         assert lm.make_meta_arch is M.make_meta_arch and lm.make_meta_arch is not ref_make
         assert lu.batched_nms is not ref_nms and tu.MaskedConv1D is M.MaskedConv1D and tu.LayerNorm is M.LayerNorm
+        import vilco_b200.utils.metrics as E
+        assert lu.ANETdetection is E.ANETdetection and tu.ANETdetection is E.ANETdetection
+        assert tu.evaluation_retrieval.__module__ == "vilco_b200.utils.get_retrieval_performance"
         # the reference's config loader + OUR factory, the reference's make_optimizer on OUR model
         c = GG.small_cfg()
         cwd = os.getcwd()

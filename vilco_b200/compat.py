@@ -7,10 +7,11 @@
 `install()` rebinds, in the already imported reference modules, exactly the names of the drop-in boundary:
 `libs.modeling.{make_meta_arch, make_backbone, make_neck, make_generator, MaskedConv1D, MaskedMHCA, MaskedMHA, LayerNorm,
 TransformerBlock, Scale, AffineDropPath, BiasLayer}`, `libs.modeling.modeling_xlnet_x.{XLNetModel, XLNetLMHeadModel}`,
-`libs.utils.batched_nms` / `libs.utils.nms.batched_nms`, and the copies of those names that `libs.utils.train_utils` and
+`libs.utils.batched_nms` / `libs.utils.nms.batched_nms`, the evaluation tail `libs.utils.ANETdetection` /
+`libs.utils.get_retrieval_performance.evaluation_retrieval`, and the copies of those names that `libs.utils.train_utils` and
 `libs.modeling.meta_archs` took at import time (`from ..modeling import MaskedConv1D, ...` — the isinstance keys of
 `make_optimizer`, train_utils.py:19-20, 29, 76-77, 96).  Everything else of the reference (config loader, datasets,
-schedulers, the CL orchestration, evaluation) stays in place and runs unchanged.
+schedulers, the CL orchestration, the validation loops) stays in place and runs unchanged.
 """
 import sys
 
@@ -52,4 +53,15 @@ def install(libs_modeling=None, libs_utils=None):
     for name in ("XLNetModel", "XLNetLMHeadModel"):
         if hasattr(X, name):
             put(tu, name, getattr(X, name))
+    # evaluation tail: the detection-mAP evaluator eval.py / train_cl.py construct and the recall metric
+    # valid_one_epoch* calls — same signatures and bit-identical results (tests/test_metrics.py), without the per-row pandas
+    # walk.  The reference's metrics.py uses np.float (numpy < 1.24), so on a current numpy this is also what makes it run.
+    from .utils import metrics as E
+    from .utils import get_retrieval_performance as G
+    for mod in (lu, sys.modules.get("libs.utils.metrics"), tu):
+        put(mod, "ANETdetection", E.ANETdetection)
+    put(sys.modules.get("libs.utils.metrics"), "compute_average_precision_detection", E.compute_average_precision_detection)
+    for mod in (sys.modules.get("libs.utils.get_retrieval_performance"), tu):
+        put(mod, "evaluation_retrieval", G.evaluation_retrieval)
+    put(sys.modules.get("libs.utils.get_retrieval_performance"), "Moment_Retrieval", G.Moment_Retrieval)
     return patched

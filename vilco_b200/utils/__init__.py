@@ -1,1 +1,3 @@
 from .nms import batched_nms  # noqa: F401
+from .metrics import ANETdetection, remove_duplicate_annotations  # noqa: F401
+from .get_retrieval_performance import evaluation_retrieval  # noqa: F401
