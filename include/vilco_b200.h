@@ -127,6 +127,16 @@ int vilco_scale_add(const float* x, const float* rowmul, const float* y, const f
 int vilco_pack_feats(const float* x, void* y, int64_t y_lo, int B, int C, int T, int T_out, void* stream);
 int vilco_unpack(const float* x, float* y, int B, int T, int C, void* stream);
 
+/* Data path in front of the model: the `force_upsampling` resize of Ego4dCLDataset.__getitem__,
+ * MQ/libs/datasets/ego4d.py:644-651 — F.interpolate(feats.permute(1,0)[None], size=max_seq_len, mode='linear',
+ * align_corners=False) — on the features as stored on disk.  x: rows of C floats (token-major, the `.pt` layout of
+ * ego4d.py:612); clip b owns rows row_start[b] .. row_start[b+1]-1 (device int64, B+1 entries, every clip >= 1 row).
+ * Outputs, either may be NULL: out32 (B, T_out, C) fp32 and out16 (B, T_out, C) bf16 operand planes (lo plane at element
+ * offset out16_lo, 0 = none) — the layout vilco_pack_feats produces, so the resized clip never exists in the reference's
+ * (C, T) layout unless the caller asks for it (vilco_unpack). */
+int vilco_resize_feats(const float* x, const int64_t* row_start, int B, int C, int T_out, float* out32, void* out16,
+                       int64_t out16_lo, void* stream);
+
 /* Row softmax over materialised attention scores S (Z2,Z1,Tq,Tk) fp32 -> P bf16 (row stride p_ld >= Tk, tail zeroed).
  * mode 0: keys with kmask[z2, j] == 0 get probability 0 (masked_fill(-inf) + softmax, blocks.py:258-260, 388-391).
  * mode 1: XLNet: (S[i,j] + BD[i, Tk + j - i]) * scale - 1e30 * [key j padded and i != j]

@@ -97,3 +97,21 @@ def test_make_optimizer_groups_match_reference():
         assert set(mine) == set(ref), (tag, sorted(set(mine) ^ set(ref))[:8])
         wrong = [k for k in ref if mine[k] != ref[k]]
         assert not wrong, (tag, wrong[:8])
+
+
+def test_data_path_argument_checks_need_no_gpu():
+    """vilco_b200.data validates the clip list on the host before anything touches the device."""
+    import pytest
+    import torch
+    from vilco_b200 import data
+    with pytest.raises(ValueError, match="no clips"):
+        data.resize_feats([], 1024)
+    with pytest.raises(ValueError, match="every clip must be"):
+        data.resize_feats([torch.zeros(3, 8), torch.zeros(3, 12)], 16)
+    with pytest.raises(ValueError, match="every clip must be"):
+        data.resize_feats(torch.zeros(0, 8), 16)
+    with pytest.raises(TypeError, match="fp32"):
+        data.resize_feats(torch.zeros(3, 8, dtype=torch.float64), 16)
+    with pytest.raises(ValueError, match="multiple of 4"):
+        data.resize_feats(torch.zeros(3, 6), 16)
+    assert data.feat_stride_after_resize(480.0, 30.0, 1024) == (480.0 * 30.0 / 1024, 480.0 * 30.0 / 1024)

@@ -248,6 +248,43 @@ __global__ void pack_feats_kernel(const float* __restrict__ x, __nv_bfloat16* __
   }
 }
 
+// Data path in front of the model: raw clip features as stored on disk — (T_in, C) fp32 rows, clip b owns
+// rows row_start[b] .. row_start[b+1]-1 of x — resized along time to T_out rows like
+// F.interpolate(feats.permute(1,0)[None], size=max_seq_len, mode='linear', align_corners=False) (MQ/libs/datasets/ego4d.py:644-651;
+// ATen's area_pixel_compute_source_index / guard_index_and_lambda in float), written token-major as fp32 and/or bf16 operand
+// planes.  One thread per 4 channels of an output row: both source rows are read with 16-byte loads that are contiguous
+// across the warp, every input byte is needed by at most ceil(T_out/T_in)+1 neighbouring output rows (L2 hits).
+__global__ void resize_feats_kernel(const float* __restrict__ x, const long long* __restrict__ row_start, float* __restrict__ o32,
+                                    __nv_bfloat16* __restrict__ o16, long long o16_lo, int C4, int T_out) {
+  const int b = blockIdx.y;
+  const long long r0 = row_start[b];
+  const int T_in = static_cast<int>(row_start[b + 1] - r0);
+  if (T_in <= 0) return;
+  const float scale = static_cast<float>(T_in) / static_cast<float>(T_out);
+  const long long n = static_cast<long long>(T_out) * C4;
+  const long long C = 4ll * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i / C4);
+    const long long c = (i - static_cast<long long>(t) * C4) * 4;
+    float src = __fadd_rn(__fmul_rn(scale, static_cast<float>(t) + 0.5f), -0.5f);
+    if (src < 0.f) src = 0.f;
+    int i0 = static_cast<int>(src);
+    if (i0 > T_in - 1) i0 = T_in - 1;
+    const int i1 = i0 + (i0 < T_in - 1 ? 1 : 0);
+    float l1 = src - static_cast<float>(i0);
+    l1 = fminf(fmaxf(l1, 0.f), 1.f);
+    const float l0 = 1.f - l1;
+    const float4 a = ld4(x + (r0 + i0) * C + c), d = ld4(x + (r0 + i1) * C + c);
+    // separate multiplies and add (no FMA contraction), like the scalar expression w0*x0 + w1*x1 of the CPU kernel
+    const float4 v = make_float4(__fadd_rn(__fmul_rn(l0, a.x), __fmul_rn(l1, d.x)), __fadd_rn(__fmul_rn(l0, a.y), __fmul_rn(l1, d.y)),
+                                 __fadd_rn(__fmul_rn(l0, a.z), __fmul_rn(l1, d.z)), __fadd_rn(__fmul_rn(l0, a.w), __fmul_rn(l1, d.w)));
+    const long long o = (static_cast<long long>(b) * T_out + t) * C + c;
+    if (o32) st4(o32 + o, v);
+    if (o16) st4s(o16 + o, o16_lo, v);
+  }
+}
+
 // (B, T, C) fp32 token-major -> (B, C, T) fp32 channel-major (outputs handed back in the reference layout)
 __global__ void unpack_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int C) {
   __shared__ float tile[32][33];
@@ -338,6 +375,19 @@ extern "C" int vilco_pack_feats(const float* x, void* y, int64_t y_lo, int B, in
   VILCO_CHECK_ARG(x && y && B > 0 && C > 0 && T > 0 && T_out >= T, "vilco_pack_feats: bad arguments");
   dim3 grid((T_out + 31) / 32, (C + 31) / 32, B);
   pack_feats_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y), y_lo, C, T, T_out);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+extern "C" int vilco_resize_feats(const float* x, const int64_t* row_start, int B, int C, int T_out, float* out32, void* out16,
+                                  int64_t out16_lo, void* stream) {
+  VILCO_CHECK_ARG(x && row_start && (out32 || out16) && B > 0 && T_out > 0, "vilco_resize_feats: bad arguments");
+  VILCO_CHECK_ARG(C > 0 && C % 4 == 0, "vilco_resize_feats: C = %d must be a multiple of 4", C);
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t row offsets");
+  const long long n = static_cast<long long>(T_out) * (C / 4);
+  dim3 grid(grid_for(n, 256, 148 * 8 / (B < 8 ? B : 8)), B);
+  resize_feats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<const long long*>(row_start), out32, static_cast<__nv_bfloat16*>(out16), out16_lo, C / 4, T_out);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
