@@ -62,3 +62,31 @@ def test_model_accepts_device_feats_from_the_data_path():
         lb, ob, _ = model([b], is_training=False, get_emb=True)
     assert rel_max(torch.cat(lb, 1), torch.cat(la, 1)) < 1e-5
     assert rel_max(torch.cat(ob, 1), torch.cat(oa, 1)) < 1e-5
+
+
+def test_eval_graph_takes_raw_clips():
+    """EvalGraph.run / infer_stream with `feats_raw` (features as stored, resized on the device) == the same clips resized
+    on the CPU like the dataset does and passed as `feats`; a batch mixing both forms is refused."""
+    from oracle import params as PR
+    from oracle.gen_golden import small_cfg
+    from util import build_pair, rel_max
+    cfg = small_cfg()
+    model, _ = build_pair(cfg)
+    T = cfg.max_seq_len
+    vids = PR.synth_video_list(cfg, 2, seed=6, lens=[T, T], text_lens=[21, 50], n_gt=[2, 3])
+    gen = torch.Generator().manual_seed(8)
+    raws = [torch.randn(t, cfg.input_dim, generator=gen) for t in (T - 29, T // 3)]
+    cpu = [dict(v, feats=_ref(r, T)) for v, r in zip(vids, raws)]
+    raw = [dict({k: x for k, x in v.items() if k != "feats"}, feats_raw=r) for v, r in zip(vids, raws)]
+    g = model.make_eval_graph(2, text_len=64)
+    want = g.run(cpu)
+    got = g.run(raw)
+    streamed = [r for res in g.infer_stream([raw, raw, raw]) for r in res]
+    assert len(streamed) == 6
+    for res in (got, streamed[:2], streamed[4:]):
+        for a, b in zip(res, want):
+            assert a["video_id"] == b["video_id"] and a["segments"].shape == b["segments"].shape
+            assert rel_max(a["scores"], b["scores"]) < 1e-5
+            assert (a["labels"] == b["labels"]).float().mean().item() > 0.98
+    with pytest.raises(ValueError, match="feats_raw"):
+        g.run([raw[0], cpu[1]])

@@ -67,6 +67,14 @@ def resize_feats(clips, max_seq_len):
     return out[0] if single else list(out.unbind(0))
 
 
+def resize_feats_into(clips, out):
+    """list of B raw (T_in, C) clips -> `out` (B, C, max_seq_len), a preallocated device buffer in the reference layout (the
+    static input buffer of an `EvalGraph`): upload of the raw blocks, one resize launch, one transpose launch."""
+    o32, _ = _launch(clips, out.shape[2], True, False)
+    ops.unpack(o32, out=out)
+    return out
+
+
 def resize_pack(clips, max_seq_len):
     """list of (T_in, C) clips -> operand planes (NP, B, max_seq_len, C): what `ops.pack_feats` returns for the resized,
     transposed batch, without either intermediate."""

@@ -1065,14 +1065,30 @@ class EvalGraph:
         logits, offsets, pmask, pyr = m._device_forward(self.feats, self.mask, self.text, self.tmask, self.tlens, False)
         return m._decode_nms_device(pyr, pmask, logits, offsets)
 
+    @staticmethod
+    def _raw_clips(video_list):
+        """the clips' features as stored on disk — `feats_raw` (T_in, C), SURVEY.md §8f-2 — when every clip carries them:
+        the force_upsampling resize of the dataset (ego4d.py:644-651) then runs on the device (vilco_b200/data.py) and
+        `feats` is not needed."""
+        raw = [v.get("feats_raw") for v in video_list]
+        if all(r is None for r in raw):
+            return None
+        if any(r is None for r in raw):
+            raise ValueError("EvalGraph: either every clip of a batch carries 'feats_raw' or none does")
+        return [r if (r.is_pinned() or r.is_cuda) else r.pin_memory() for r in raw]
+
     def load_inputs(self, video_list):
         """host -> static device buffers (async on the current stream)."""
         m = self.model
         assert len(video_list) == self.B
         T = m.max_seq_len
-        lens = [v["feats"].shape[-1] for v in video_list]
+        raw = self._raw_clips(video_list)
+        lens = [T] * self.B if raw is not None else [v["feats"].shape[-1] for v in video_list]
         assert max(lens) <= T
-        for i, v in enumerate(video_list):
+        if raw is not None:
+            from .. import data
+            data.resize_feats_into(raw, self.feats)
+        for i, v in enumerate(video_list if raw is None else ()):
             f = v["feats"]
             if f.is_pinned() or f.is_cuda:
                 if lens[i] < T:
@@ -1100,9 +1116,13 @@ class EvalGraph:
     def _host_to(self, dst, video_list, stream):
         """pinned host -> device staging set `dst` on `stream` (async)."""
         m, T = self.model, self.model.max_seq_len
-        lens = [v["feats"].shape[-1] for v in video_list]
+        raw = self._raw_clips(video_list)
+        lens = [T] * self.B if raw is not None else [v["feats"].shape[-1] for v in video_list]
         with torch.cuda.stream(stream):
-            for i, v in enumerate(video_list):
+            if raw is not None:
+                from .. import data
+                data.resize_feats_into(raw, dst["feats"])
+            for i, v in enumerate(video_list if raw is None else ()):
                 f = v["feats"] if (v["feats"].is_pinned() or v["feats"].is_cuda) else v["feats"].pin_memory()
                 if lens[i] < T:
                     dst["feats"][i, :, lens[i]:].zero_()
