@@ -229,7 +229,8 @@ def unpack(x, out=None):
     """(B, T, C) fp32 -> (B, C, T) fp32 (into `out` when given)."""
     B, T, Cc = x.shape
     y = torch.empty(B, Cc, T, device=x.device, dtype=f32) if out is None else out
-    assert y.shape == (B, Cc, T) and y.dtype == f32 and y.is_contiguous() and x.is_contiguous()
+    if out is not None:
+        assert y.shape == (B, Cc, T) and y.dtype == f32 and y.is_contiguous() and x.is_contiguous()
     L.check(L.lib().vilco_unpack(_p(x), _p(y), B, T, Cc, L.stream_ptr()), "vilco_unpack")
     return y
 
