@@ -90,3 +90,35 @@ def test_eval_graph_takes_raw_clips():
             assert (a["labels"] == b["labels"]).float().mean().item() > 0.98
     with pytest.raises(ValueError, match="feats_raw"):
         g.run([raw[0], cpu[1]])
+
+
+def test_validation_pass_equals_clip_by_clip_evaluation():
+    """vilco_b200.utils.validate.valid_one_epoch (regrouped static batches, padded last batch, streaming graph, in-memory
+    evaluator) gives the result table of the reference-style loop `for clip: model([clip])`."""
+    import numpy as np
+    import pandas as pd
+    from oracle import params as PR
+    from oracle.gen_golden import small_cfg
+    from util import build_pair
+    from vilco_b200.utils.metrics import ANETdetection
+    from vilco_b200.utils.validate import results_table, valid_one_epoch
+    cfg = small_cfg()
+    model, _ = build_pair(cfg)
+    T = cfg.max_seq_len
+    vids = PR.synth_video_list(cfg, 5, seed=9, lens=[T, T - 20, 64, T, 90], text_lens=[21, 50, 33, 12, 60], n_gt=[2, 3, 1, 2, 2])
+    for i, v in enumerate(vids):
+        v["video_id"] = f"clip{i}"
+    gt = pd.DataFrame({"video-id": [v["video_id"] for v in vids for _ in range(len(v["labels"]))],
+                       "t-start": [float(s[0]) for v in vids for s in v["segments"]],
+                       "t-end": [float(s[1]) for v in vids for s in v["segments"]],
+                       "label": [int(l) for v in vids for l in v["labels"]]})
+    index = {j: i for i, j in enumerate(sorted(gt["label"].unique()))}
+    gt["label"] = gt["label"].map(index)
+    ev = ANETdetection((gt, index), tiou_thresholds=np.linspace(0.1, 0.5, 5))
+    mAP, avg, thr, rec = valid_one_epoch([[v] for v in vids], model, 0, evaluator=ev, batch_size=2, text_len=64)
+    assert rec is None and mAP.shape == (5,) and 0.0 <= avg <= 1.0
+    with torch.no_grad():
+        want = results_table([model([v], is_training=False)[0] for v in vids])
+    mAP2, avg2, _ = ANETdetection((gt, index), tiou_thresholds=np.linspace(0.1, 0.5, 5)).evaluate(want, verbose=False)
+    # the batched graph and the single-clip call agree to the last bits of the scores; the mAP of both tables must agree
+    assert abs(avg - avg2) < 1e-3, (avg, avg2)
