@@ -86,3 +86,43 @@ def feat_stride_after_resize(duration, fps, max_seq_len):
     """`feat_stride` / `num_frames` the dataset reports for a force-upsampled fixed-length clip (ego4d.py:631-640)."""
     stride = duration * fps / max_seq_len
     return stride, stride
+
+
+def truncate_feats(data_dict, max_seq_len, trunc_thresh, crop_ratio=None, max_num_trials=200, has_action=True, no_trunc=False):
+    """Training-time random crop of a clip — same contract, same consumption of Python's `random` stream and same result as
+    `truncate_feats` of MQ/libs/datasets/data_utils.py:24-112 (so a seeded run draws the identical windows), with two
+    differences in how it is done: `feats` may live on the device (the crop is a device slice, e.g. of `resize_feats`
+    output), and only the entries that change are copied — the reference deep-copies the whole dict, 16 MiB of features
+    included, before it knows the window.
+
+    Window search: up to `max_num_trials` uniform windows of the target length; accepted when (has_action) at least one
+    segment keeps >= trunc_thresh of its length inside, or (no_trunc) additionally no segment is cut; the last trial is
+    used if none qualifies.  Segments are clipped to the window, filtered by the threshold and shifted to its origin."""
+    import random
+    feat_len = data_dict['feats'].shape[1]
+    if feat_len <= max_seq_len:
+        if crop_ratio is None:
+            return data_dict
+        max_seq_len = random.randint(max(round(crop_ratio[0] * feat_len), 1), min(round(crop_ratio[1] * feat_len), feat_len))
+        if feat_len == max_seq_len:
+            return data_dict
+    segs = data_dict['segments']
+    length = torch.abs(segs[:, 1] - segs[:, 0])
+    for _ in range(max_num_trials):
+        st = random.randint(0, feat_len - max_seq_len)
+        ed = st + max_seq_len
+        left = segs[:, 0].clamp(min=float(st))
+        right = segs[:, 1].clamp(max=float(ed))
+        ratio = (right - left).clamp(min=0) / length
+        keep = ratio >= trunc_thresh
+        if no_trunc:
+            if bool(keep.any()) and not bool(((ratio > 0.0) & (ratio < 1.0)).any()):
+                break
+        elif not has_action or bool(keep.any()):
+            break
+    out = dict(data_dict)                       # shallow: untouched entries (ids, text features, ...) are shared
+    out['feats'] = data_dict['feats'][:, st:ed].clone()
+    out['segmentation_labels'] = data_dict['segmentation_labels'][st:ed, :].clone()
+    out['segments'] = torch.stack((left[keep], right[keep]), dim=1) - st
+    out['labels'] = data_dict['labels'][keep].clone()
+    return out
