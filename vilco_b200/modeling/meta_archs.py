@@ -568,7 +568,7 @@ class PtTransformer(nn.Module):
             return cls_l, off_l, msk_l
         if is_training:
             return self.losses(vl, logits, offsets, pmask, pyr, prev_out_cls_logits)
-        results = self.inference(video_list, pyr, pmask, logits, offsets)
+        results = self.inference(video_list, pyr, pmask, logits, offsets, cilsettask=val_qilDatasetList)
         if ensemble:
             points = self.point_generator(pyr.lens)
             cls_l = [logits[:, o:o + n] for o, n in zip(pyr.off, pyr.lens)]
@@ -1008,9 +1008,81 @@ class PtTransformer(nn.Module):
         forward(); returns one dict per video with CPU tensors."""
         pyr = points_or_pyr
         assert isinstance(pyr, E.Pyramid), "inference() expects the pyramid layout returned by forward()"
-        assert cilsettask is None or not self.compute_means, "iCaRL nearest-mean re-scoring is not built yet"
         segs, scores, labels, count = self._decode_nms_device(pyr, fpn_masks, out_cls_logits, out_offsets)
-        return self._to_results(video_list, segs.cpu(), scores.cpu(), labels.cpu(), count.cpu())
+        results = self._to_results(video_list, segs.cpu(), scores.cpu(), labels.cpu(), count.cpu())
+        # iCaRL (meta_archs.py:1559-1562): while `compute_means` is set and the validation passes its task object, a clip is
+        # re-scored by the nearest exemplar mean.  classify() clears the flag itself, so like in the reference this happens
+        # for the first clip after the flag was raised (train_utils.py:305) and the kernel path above serves all others.
+        for idx, v in enumerate(video_list):
+            if cilsettask is not None and self.compute_means:
+                results[idx] = self._rescored_result(v, idx, self.classify(v, cilsettask), pyr, fpn_masks, out_cls_logits,
+                                                     out_offsets)
+        return results
+
+    def _fpn_features(self, video_list):
+        """FPN outputs of `neck(backbone(...))` per level in the reference layout (B, C, T_l), fp32 — the quantity
+        `classify` works on (meta_archs.py:1073-1079, 1110-1118: no prompts, no EMA ensemble)."""
+        _, batched, mask = self.preprocessing(video_list, is_training=False)
+        text = tmask = tlens = t16 = None
+        if self.use_cross_modal:
+            text, tmask, tlens = self.query_preprocessing(video_list)
+            t16 = ops.pack_feats(text.contiguous())
+        W, cfg = self.packed_weights(), self.engine_cfg()
+        trunk = E.backbone_fwd(W, cfg, ops.pack_feats(batched), mask.contiguous(), t16, tmask, self._pe, text_lens=tlens,
+                               trunk_only=True)
+        feats, _ = E.branch_fwd(W, cfg, trunk, "pets.")
+        out = []
+        for l, f in enumerate(feats):
+            y32, _ = ops.layernorm(f, W[f"neck.fpn_norms.{l}.weight"], W[f"neck.fpn_norms.{l}.bias"], out32=True, out16=False)
+            out.append(y32.permute(0, 2, 1))
+        return out
+
+    @torch.no_grad()
+    def classify(self, x, cilsettask):
+        """iCaRL nearest-mean-of-exemplars distances of one clip — meta_archs.py:1061-1131.  Returns, per pyramid level, the
+        (1, T_l, n_classes) squared distances between the clip's normalised FPN features and the class means of the exemplar
+        memory; the means are (re)computed from `self.memory` through `cilsettask.get_dataloader` while `compute_means` is
+        set.  The network passes run on the CUDA path, the reductions are `modeling/icarl.py`."""
+        from . import icarl
+        if self.compute_means:
+            print("Computing mean of exemplars...")
+            exemplar_means = [[] for _ in range(icarl.FPN_LEVELS)]
+            for class_id, videos in self.memory.items():
+                per_level = None
+                for video_list in cilsettask.get_dataloader({class_id: videos}, sample_frame=True):
+                    lv = [icarl.normalize_level(f) for f in self._fpn_features(video_list)]
+                    if per_level is None:
+                        per_level = [[f] for f in lv]
+                    else:
+                        for i, f in enumerate(lv):
+                            per_level[i].append(f)
+                for i, fs in enumerate(per_level):
+                    exemplar_means[i].append(icarl.exemplar_mean(fs))
+            self.exemplar_means = exemplar_means
+            self.compute_means = False
+        feats = self._fpn_features([x])
+        return [icarl.nme_dists(feats[i], self.exemplar_means[i]) for i in range(icarl.FPN_LEVELS)]
+
+    def _rescored_result(self, v, idx, dists, pyr, pmask, logits, offsets):
+        """`inference_single_video` with `cls_preds_per_vid` (meta_archs.py:1625-1682) + `postprocessing` (:1695-1736) for
+        one clip: candidate selection by exemplar distance (torch glue on the device), soft-NMS on the GPU kernel."""
+        from . import icarl
+        from ..utils.nms import batched_nms
+        points = self.point_generator(pyr.lens)
+        segs, scores, labels = [], [], []
+        for l, (o, n) in enumerate(zip(pyr.off, pyr.lens)):
+            s, sc, lb = icarl.select_candidates(logits[idx, o:o + n], offsets[idx, o:o + n], points[l].to(logits.device),
+                                                pmask[idx, o:o + n], dists[l], self.num_classes, int(self.test_pre_nms_topk),
+                                                self.test_duration_thresh)
+            segs.append(s), scores.append(sc), labels.append(lb)
+        segs, scores, labels = torch.cat(segs), torch.cat(scores), torch.cat(labels)
+        if self.test_nms_method != "none":
+            segs, scores, labels = batched_nms(segs, scores, labels, self.test_iou_threshold, self.test_min_score,
+                                               self.test_max_seg_num, use_soft_nms=(self.test_nms_method == "soft"),
+                                               multiclass=self.test_multiclass_nms, sigma=self.test_nms_sigma,
+                                               voting_thresh=self.test_voting_thresh)
+        n = segs.shape[0]
+        return self._to_results([v], segs.cpu()[None], scores.cpu()[None], labels.cpu()[None], torch.tensor([n]))[0]
 
 
 class EvalGraph:
