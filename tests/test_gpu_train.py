@@ -428,11 +428,16 @@ def test_distillation_terms_match_reference_golden(name):
     videos = PR.synth_video_list(cfg, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
     prev = GG.prev_logits(cfg, probs=True)
     model.loss_normalizer = cfg.init_loss_norm
+    with torch.no_grad():                       # validate_loss path (train_utils.py:584-655): same values, no graph
+        model.loss_normalizer = cfg.init_loss_norm
+        quiet = model(videos, is_training=True, prev_out_cls_logits=prev if name == "bic" else [prev])
+    model.loss_normalizer = cfg.init_loss_norm
     out = model(videos, is_training=True, prev_out_cls_logits=prev if name == "bic" else [prev])
     out["final_loss"].backward()
     for k in ("cls_loss", "reg_loss", "al_loss", "dist_loss", "final_loss"):
         ref = float(g[f"{name}_loss_{k}"])
         assert abs(float(out[k].detach()) - ref) <= 1e-3 * abs(ref) + 1e-6, (k, float(out[k].detach()), ref)
+        assert abs(float(quiet[k]) - ref) <= 1e-3 * abs(ref) + 1e-6, ("no_grad", k, float(quiet[k]), ref)
     if name == "bic":
         got = np.array([[bl.alpha.grad.item(), bl.beta.grad.item()] for bl in model.list_bias_layers])
         assert np.abs(got - g["bic_bias_grads"]).max() <= 1e-3 * np.abs(g["bic_bias_grads"]).max()

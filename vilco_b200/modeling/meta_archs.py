@@ -914,8 +914,9 @@ class PtTransformer(nn.Module):
 
     @torch.no_grad()
     def losses(self, vl, logits, offsets, pmask, pyr, prev_out_cls_logits=None):
-        """Forward values of cls / reg / al / final loss (reference: meta_archs.py:1374-1524) from the fused loss kernel.
-        The backward pass of the CUDA path is not built yet, so the returned tensors carry no autograd graph."""
+        """Forward values of cls / reg / al / final loss (reference: meta_archs.py:1374-1524) from the fused loss kernel, for
+        calls under `torch.no_grad()` (`validate_loss`, train_utils.py:584-655); with gradients enabled forward() takes
+        `_train_forward`, whose result carries the hand-written backward."""
         dev = self.device
         B, P, K = logits.shape
         gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
@@ -940,9 +941,13 @@ class PtTransformer(nn.Module):
         al_loss = sums[3] / self.loss_normalizer if K != 1 else torch.zeros((), device=dev)
         loss_weight = self.train_loss_weight if self.train_loss_weight > 0 else float(cls_loss) / max(float(reg_loss), 0.01)
         final = cls_loss + reg_loss * loss_weight + al_loss * self.al_loss_weight
+        out = {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final}
         if self.n_known > 0 and self.cl_name in ("bic", "icarl"):
-            raise NotImplementedError("BiC / iCaRL distillation terms of the training loss are not built yet")
-        return {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final}
+            # distillation against the previous task's outputs (meta_archs.py:1482-1519); forward() already applied the BiC
+            # bias layers to `logits`
+            out["dist_loss"] = self._distill_term(logits, pyr, prev_out_cls_logits)
+            out["final_loss"] = final + out["dist_loss"]
+        return out
 
     # ---- inference (reference: meta_archs.py:1527-1736) ---------------------------------------------
     @torch.no_grad()
