@@ -60,3 +60,44 @@ def test_install_makes_the_reference_callers_use_vilco_b200():
     finally:
         for (m, n), v in saved.items():
             setattr(m, n, v)
+
+
+def test_launcher_runs_an_unmodified_style_script_on_the_mirrors(tmp_path, capsys):
+    """python -m vilco_b200.run <script>: a script written like the reference's entry points (module-level
+    `from libs.modeling import make_meta_arch`, `from libs.utils import ...`, argv of its own) sees the rebound names."""
+    import sys
+    from oracle import ref_shim
+    import vilco_b200.run as launcher
+    ns = ref_shim.load()                                   # this container's missing-dependency stubs (timm, turtle, ...)
+    script = tmp_path / "entry_like_eval.py"
+    script.write_text(
+        "import sys\n"
+        "from libs.modeling import make_meta_arch\n"
+        "from libs.utils import batched_nms, ANETdetection\n"
+        "import libs.utils.train_utils as tu\n"
+        "print('ARGV', sys.argv[1:])\n"
+        "print('BOUND', make_meta_arch.__module__, batched_nms.__module__, ANETdetection.__module__, tu.LayerNorm.__module__)\n"
+        "print('MAIN', __name__)\n")
+    import libs.modeling as lm
+    import libs.utils as lu
+    import libs.utils.train_utils as tu
+    import libs.utils.metrics as lmet
+    import libs.utils.get_retrieval_performance as lret
+    mods = [m for m in (lm, lu, tu, lmet, lret, sys.modules.get("libs.modeling.models"), sys.modules.get("libs.modeling.meta_archs"),
+                        sys.modules.get("libs.utils.nms"), sys.modules.get("libs.modeling.modeling_xlnet_x")) if m is not None]
+    saved = [(m, dict(vars(m))) for m in mods]
+    cwd, argv, path = os.getcwd(), list(sys.argv), list(sys.path)
+    try:
+        launcher.main(["--mq-root", ns.REF_MQ, str(script), "configs/mq_vilco.yaml", "--topk", "5"])
+        out = capsys.readouterr().out
+        assert "ARGV ['configs/mq_vilco.yaml', '--topk', '5']" in out and "MAIN __main__" in out
+        assert "BOUND vilco_b200.modeling.models vilco_b200.utils.nms vilco_b200.utils.metrics vilco_b200.modeling.blocks" in out
+        assert os.getcwd() == ns.REF_MQ
+        with pytest.raises(SystemExit, match="not a ViLCo/MQ checkout"):
+            launcher.main(["--mq-root", str(tmp_path), "eval.py"])
+    finally:
+        os.chdir(cwd)
+        sys.argv[:], sys.path[:] = argv, path
+        for m, d in saved:                                 # undo compat.install() for the other tests of this process
+            for k, v in d.items():
+                setattr(m, k, v)
