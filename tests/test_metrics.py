@@ -172,6 +172,13 @@ def test_matcher_edge_cases_and_random_agreement():
     # zero-length prediction and ground truth anywhere: tIoU = 0/0 = NaN, which the reference counts as a match
     tp = M.ap_match(np.array([[5., 5.]]), np.array([0]), np.array([[9., 9.]]), np.array([0, 1]), thr)
     assert tp.sum() == 5
+    # tied tIoUs (the same moment annotated three times): each repeat of the prediction takes one of them, the fourth is a
+    # false positive; among equal tIoUs the higher ground-truth row is taken first (argsort()[::-1] of <= 16 rows)
+    gt3 = np.array([[0., 10.], [0., 10.], [0., 10.], [50., 60.]])
+    pr4 = np.array([[0., 10.]] * 4)
+    tp = M.ap_match(pr4, np.zeros(4, np.int64), gt3, np.array([0, 4]), np.array([0.5]))
+    assert tp.tolist() == [[1, 1, 1, 0]]
+    assert np.array_equal(tp, _python_matcher(pr4, np.zeros(4, np.int64), gt3, np.array([0, 4]), np.array([0.5])))
     # bad arguments are reported through the error code, not a crash
     with pytest.raises(Exception, match="out of range"):
         M.ap_match(np.array([[0., 1.]]), np.array([3]), np.array([[0., 1.]]), np.array([0, 1]), thr)

@@ -49,9 +49,8 @@ def _run(n, batch_size, loader=None):
         pass
     g = FakeGraph(batch_size)
     ev = ANETdetection(_ground_truth(n), tiou_thresholds=np.linspace(0.1, 0.5, 5))
-    # recall table: ground truth of the clips that have detections (the reference's evaluate() needs a prediction entry for
-    # every ground-truth clip, get_retrieval_performance.py:133-136)
-    ret_gt = {f"v{k}": {k % 3: [[10.0 * k + j, 10.0 * k + j + 5.0] for j in range(k % 4)]} for k in range(n) if k % 4}
+    # recall table over every clip: clips 0, 4, ... have a ground truth but no detections -> counted as not retrieved
+    ret_gt = {f"v{k}": {k % 3: [[10.0 * k + j, 10.0 * k + j + 5.0] for j in range(max(1, k % 4))]} for k in range(n)}
     res = valid_one_epoch(loader if loader is not None else _loader(n), M(), 0, evaluator=ev, graph=g, batch_size=batch_size,
                           retrieval_gt=ret_gt, print_freq=2)
     return res, g, ev
@@ -64,7 +63,8 @@ def test_single_process_pass_pads_the_last_batch_and_evaluates():
     # every detection coincides with a ground truth of its clip and label; clips 0 and 4 have no detections but one
     # ground truth each -> recall of their labels is below 1, precision stays 1
     assert avg > 0.5 and np.all(mAP <= 1.0)
-    assert rec.shape == (5, 2) and np.all(rec == 1.0)
+    n_gt = sum(max(1, k % 4) for k in range(7))
+    assert rec.shape == (5, 2) and np.allclose(rec, (n_gt - 2) / n_gt)     # all but the two detection-less clips' moments
     # same pass with another batch size and another loader grouping gives identical numbers
     (mAP2, avg2, _, rec2), g2, _ = _run(7, 32, loader=[[{"video_id": f"v{i}"} for i in range(j, min(7, j + 3))] for j in (0, 3, 6)])
     assert g2.calls == 1 and np.array_equal(mAP, mAP2) and avg == avg2 and np.array_equal(rec, rec2)

@@ -106,6 +106,8 @@ def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluato
     eval_result = None
     if retrieval_gt is not None:
         pred = R.predictions_from_results(results, idx_classes)
+        for o in outputs:                       # a clip without detections retrieves nothing (the reference's evaluate()
+            pred.setdefault(o['video_id'], {})  # stops in pdb when a ground-truth clip has no prediction entry, :133-136)
         eval_result = R.evaluation_retrieval(gt=retrieval_gt, pred=pred, subset="val", tiou=list(R.TIOUS), use_cl=use_cl,
                                              current_task_id=current_task_id)
         for i, t in enumerate(R.TIOUS):
