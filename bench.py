@@ -208,6 +208,74 @@ def eager_gpu_rates(state_dict, tf32, n_inf=8, n_train=2):
     return inf_rate, tr_rate
 
 
+def next_rows():
+    """The rows either side of the hot path timed beside it, each next to the reference's CPU way of doing the
+    same thing: the dataset's linear time-resize of a stored clip (vilco_resize_feats vs F.interpolate on the host) and the
+    evaluation tail (ANETdetection mirror on 200 clips x 200 detections; the reference's pandas walk takes ~55 s for that
+    table, tools/metrics_bench.py --reference).  Reported extras: a failure here never takes the bench line down."""
+    out = {}
+    try:
+        import torch.nn.functional as F
+        from vilco_b200 import lib as L
+        from vilco_b200 import ops
+        Bc, T_in, C, T = 32, 512, 4096, 1024
+        x = torch.randn(Bc * T_in, C, device="cuda")
+        row_start = torch.arange(0, (Bc + 1) * T_in, T_in, dtype=torch.int64, device="cuda")
+        o16 = ops.empty16(Bc, T, C)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for i in range(13):                      # 3 warm-ups; input 268 MB + output 537 MB per launch exceed the L2
+            if i == 3:
+                ev[0].record()
+            L.check(L.lib().vilco_resize_feats(ops._p(x), ops._p(row_start), Bc, C, T, None, ops._p(o16), ops._i64(ops.lo(o16)),
+                                               L.stream_ptr()), "vilco_resize_feats")
+        ev[1].record()
+        torch.cuda.synchronize()
+        sec = ev[0].elapsed_time(ev[1]) / 10 * 1e-3
+        nbytes = x.numel() * 4 + o16.numel() * 2
+        xc = x[:T_in].cpu()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            F.interpolate(xc.permute(1, 0).unsqueeze(0), size=T, mode="linear", align_corners=False)
+        cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+        hbm = peaks()[0]
+        out["data_path"] = {"kernel": "vilco::resize_feats_kernel", "workload": "32 stored clips 512x4096 fp32 -> 1024 rows, bf16 hi/lo planes",
+                            "us_per_launch": sec * 1e6, "bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": hbm, "unit": "GB/s",
+                            "frac": nbytes / sec / 1e9 / hbm, "clips_per_s": Bc / sec, "cpu_interpolate_ms_per_clip": cpu_ms}
+        del x, o16
+    except Exception as e:
+        out["data_path"] = {"unavailable": repr(e)[:200]}
+    try:
+        import pandas as pd
+        from vilco_b200.utils.metrics import ANETdetection
+        rs = np.random.RandomState(5)
+        gv, g0, g1, gl, pv, p0, p1, pl, ps = [], [], [], [], [], [], [], [], []
+        for v in range(200):
+            n = int(rs.randint(1, 9))
+            c, ln = rs.uniform(0, 480, n), np.exp(rs.uniform(0, np.log(120), n))
+            lab = rs.randint(0, 22, n)
+            gv += [f"clip{v}"] * n
+            g0 += list(np.maximum(c - ln / 2, 0)); g1 += list(c + ln / 2); gl += list(lab)
+            k = rs.randint(0, n, 200)
+            j0 = np.maximum(c[k] - ln[k] / 2 + rs.normal(0, 0.2, 200) * ln[k], 0)
+            pv += [f"clip{v}"] * 200
+            p0 += list(j0); p1 += list(j0 + ln[k] * np.exp(rs.normal(0, 0.2, 200)))
+            pl += list(np.where(rs.rand(200) < 0.7, lab[k], rs.randint(0, 22, 200))); ps += list(rs.beta(0.5, 4.0, 200))
+        gt = pd.DataFrame({"video-id": gv, "t-start": g0, "t-end": g1, "label": gl})
+        index = {j: i for i, j in enumerate(sorted(gt["label"].unique()))}
+        gt["label"] = gt["label"].map(index)
+        evl = ANETdetection((gt, index), tiou_thresholds=np.linspace(0.1, 0.5, 5))
+        preds = {"video-id": pv, "t-start": np.float32(p0), "t-end": np.float32(p1), "label": np.int64(pl), "score": np.float32(ps)}
+        t0 = time.perf_counter()
+        _, avg, _ = evl.evaluate(preds, verbose=False)
+        dt = time.perf_counter() - t0
+        out["evaluation_tail"] = {"workload": "detection mAP@0.1:0.5 of 200 clips x 200 detections, 22 labels (host code, vilco_ap_match)",
+                                  "seconds": dt, "detections_per_s": len(ps) / dt, "avg_mAP": float(avg),
+                                  "reference": "the reference's evaluator on a table of this size: ~55 s in one process (tools/metrics_bench.py --reference)"}
+    except Exception as e:
+        out["evaluation_tail"] = {"unavailable": repr(e)[:200]}
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -493,6 +561,12 @@ def main():
         except Exception as e:  # a baseline must never take the bench down
             line["eager_gpu_baseline"] = {"unavailable": repr(e)[:300]}
         torch.cuda.empty_cache()
+        if world == 1:
+            try:
+                line["next_rows"] = next_rows()
+                torch.cuda.empty_cache()
+            except Exception as e:  # extras must never take the bench line down
+                line["next_rows"] = {"unavailable": repr(e)[:200]}
         rate, dt = cpu_reference_rate(model.state_dict(), args.ref_videos)
         cores = os.cpu_count() or 1
         line["cpu_baseline"] = {"value": rate, "unit": "videos/s", "cores": cores, "kind": "port",
