@@ -1,0 +1,60 @@
+"""First pin of the NLQ row (not built yet — docs/NEXT_NLQ.md): the committed fixtures produced by the
+reference's own NLQ model (oracle/gen_golden_nlq.py) are well-formed, the seeded weight recipe is a pure function of
+(name, shape, seed), and — in the authoring container, in a subprocess because NLQ's package is also called `libs` — the
+reference still reproduces the committed vectors."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def test_state_spec_and_golden_are_well_formed():
+    spec = json.load(open(os.path.join(GOLDEN, "nlq_state_spec.json")))
+    sd = spec["state_dict"]
+    assert len(sd) == 467 and spec["n_parameters"] == 30168202
+    assert sd["backbone.vid_embd.0.conv.weight"] == [384, 256, 3]                      # video 256-d -> C = 384, k = 3
+    assert sd["backbone.vid_stem.0.attn.query.weight"][:2] == [384, 384]                # 4 heads of 96
+    assert any(k.startswith("backbone.vid_stem.3.cross_attn.") for k in sd)              # text cross-attention in the video stem
+    g = np.load(os.path.join(GOLDEN, "nlq_small.npz"))
+    lens = [512 >> l for l in range(7)]
+    for i in range(2):
+        for l, n in enumerate(lens):
+            assert g[f"logits_{i}_{l}"].shape == (n, 1) and g[f"offsets_{i}_{l}"].shape == (n, 2) and g[f"mask_{i}_{l}"].shape == (n,)
+            assert np.isfinite(g[f"logits_{i}_{l}"]).all() and (g[f"offsets_{i}_{l}"] >= 0).all()
+        assert g[f"det_segments_{i}"].shape == (5, 2) and (np.diff(g[f"det_scores_{i}"]) <= 0).all()     # max_seg_num 5, sorted
+    assert g["mask_1_0"].sum() == 512 - 37                                                 # the second clip is 37 features shorter
+
+
+def test_seeded_weights_are_a_pure_function_of_name_shape_seed():
+    from oracle.gen_golden_nlq import nlq_random_state
+    shapes = {"a.conv.weight": (4, 3, 3), "a.norm.weight": (4,), "a.norm.bias": (4,), "s.scale": (1, 4, 1), "b.bias": (4,)}
+    a, b = nlq_random_state(shapes, 3), nlq_random_state(shapes, 3)
+    assert all(torch.equal(a[k], b[k]) for k in shapes)
+    assert not torch.equal(a["a.conv.weight"], nlq_random_state(shapes, 4)["a.conv.weight"])
+    assert abs(float(a["a.norm.weight"].mean()) - 1.0) < 0.3 and abs(float(a["s.scale"].mean()) - 1.0) < 0.3
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/NLQ/libs/modeling"), reason="NLQ reference not present (GPU box)")
+def test_reference_reproduces_the_committed_vectors():
+    code = (
+        "import numpy as np, torch, os\n"
+        "from oracle import nlq_shim\n"
+        "from oracle.gen_golden_nlq import nlq_random_state, small, synth_clips, GOLDEN\n"
+        "m, cfg = nlq_shim.build_model(small)\n"
+        "shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if torch.is_floating_point(v)}\n"
+        "m.load_state_dict(nlq_random_state(shapes, 0), strict=False); m.eval()\n"
+        "g = np.load(os.path.join(GOLDEN, 'nlq_small.npz'))\n"
+        "with torch.no_grad():\n"
+        "    lg, of, mk = m([synth_clips(cfg, 2, 0)[1]], is_training=False, get_emb=True)\n"
+        "err = max(float(np.abs(lg[l][0].numpy() - g[f'logits_1_{l}']).max()) for l in range(7))\n"
+        "print('MAXERR', err)\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    err = float([ln for ln in out.stdout.splitlines() if ln.startswith("MAXERR")][-1].split()[1])
+    assert err < 1e-5, err
