@@ -11,6 +11,7 @@ Writes
 """
 import json
 import os
+import zlib
 
 import numpy as np
 import torch
@@ -25,8 +26,8 @@ def nlq_random_state(shapes, seed=0):
     norm weights and per-channel scales around 1 (this also lifts the AffineDropPath scales from their 1e-4 init, which
     would hide every residual branch), biases small, everything else N(0, 1/sqrt(fan_in))."""
     out = {}
-    for i, (name, shape) in enumerate(shapes.items()):
-        g = torch.Generator().manual_seed(seed * 100003 + i)
+    for name, shape in shapes.items():
+        g = torch.Generator().manual_seed(seed * 100003 + zlib.crc32(name.encode()))
         leaf = name.rsplit(".", 1)[-1]
         if len(shape) == 0:
             out[name] = torch.tensor(1.0)

@@ -157,7 +157,7 @@ def adapter_time(P, pre, x):
 
 
 def transformer_block(P, pre, x, mask, n_head, stride, cross_y=None, cross_y_mask=None, t_c_alpha=0.8,
-                      window=-1, adapter_pre=None):
+                      window=-1, adapter_pre=None, channel_mix=True):
     """TransformerBlock.forward — blocks.py:561-593 (eval: AffineDropPath == per-channel scale, blocks.py:655-670)."""
     ln1 = channel_layernorm(x, P[pre + "ln1.weight"], P[pre + "ln1.bias"])
     if window > 1:
@@ -181,7 +181,7 @@ def transformer_block(P, pre, x, mask, n_head, stride, cross_y=None, cross_y_mas
     h = F.conv1d(F.gelu(F.conv1d(h, P[pre + "mlp.0.weight"], P[pre + "mlp.0.bias"])),
                  P[pre + "mlp.3.weight"], P[pre + "mlp.3.bias"]) * mf
     out = out + (h if sm is None else sm * h)
-    if stride == 1:
+    if stride == 1 and channel_mix:   # MQ only; the NLQ block (NLQ/libs/modeling/blocks.py:840-874) has no channel mix
         out2 = channel_block(P, pre + "channel_attn.", ln1, n_head)
         out = t_c_alpha * out + (1 - t_c_alpha) * out2
     return out, out_mask

@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement (torch fp32) of the NLQ model's forward pass, SURVEY.md §8f-1, composed from the
+operator restatements of oracle/mq_oracle.py (the NLQ blocks are the MQ blocks without the channel mix and with the windowed
+attention live).  Pinned against the reference's own NLQ model: tests/golden/nlq_small.npz (oracle/gen_golden_nlq.py),
+tests/test_nlq_pin.py.  The product does not import this.
+
+Follows NLQ/libs/modeling/backbones.py:546-615 (ConvTransformerBackbone.forward), blocks.py:840-874 (TransformerBlock.forward),
+necks.py (FPNIdentity), meta_archs.py:182-338 (heads), :614-748 (PtTransformer.forward, evaluation branch).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import mq_oracle as O
+
+
+class NlqCfg:
+    """ego4d_nlq_v2_egovlp_1e-4.yaml"""
+
+    def __init__(self, **kw):
+        self.input_vid_dim, self.input_txt_dim, self.embd_dim, self.n_head = 256, 512, 384, 4
+        self.max_seq_len, self.arch, self.window, self.scale_factor, self.num_classes = 2560, (2, 4, 4, 0, 6), 9, 2, 1
+        for k, v in kw.items():
+            assert hasattr(self, k), k
+            setattr(self, k, v)
+
+
+def backbone(P, cfg, vid, vid_mask, txt, txt_mask):
+    """vid (B, Cv, T), vid_mask (B, 1, T) bool, txt (B, Ct, L), txt_mask (B, 1, L) bool -> per-level features and masks."""
+    pre = "backbone."
+    x, m = vid, vid_mask
+    for i in range(cfg.arch[0]):                                                    # backbones.py:552-554
+        x, m = O.masked_conv1d(x, m, P[pre + f"vid_embd.{i}.conv.weight"], None)
+        x = F.relu(O.channel_layernorm(x, P[pre + f"vid_embd_norm.{i}.weight"], P[pre + f"vid_embd_norm.{i}.bias"]))
+    T = x.shape[-1]
+    pe = O.sinusoid_pe(cfg.max_seq_len, cfg.embd_dim) / (cfg.embd_dim ** 0.5)       # :446-448, evaluation branch :564-572
+    if T >= cfg.max_seq_len:
+        pe = F.interpolate(pe, T, mode="linear", align_corners=False)
+    x = x + pe[:, :, :T] * m.to(x.dtype)
+    q, qm = txt, txt_mask
+    for i in range(cfg.arch[0]):                                                    # :577-579 (k = 1 convolutions)
+        q, qm = O.masked_conv1d(q, qm, P[pre + f"txt_embd.{i}.conv.weight"], None)
+        q = F.relu(O.channel_layernorm(q, P[pre + f"txt_embd_norm.{i}.weight"], P[pre + f"txt_embd_norm.{i}.bias"]))
+    for i in range(cfg.arch[1]):                                                    # :585-586 global self-attention on the text
+        q, qm = O.transformer_block(P, pre + f"txt_stem.{i}.", q, qm, cfg.n_head, 1, channel_mix=False)
+    qml = qm.squeeze(1).long()
+    for i in range(cfg.arch[2]):                                                    # :589-590 window attention + cross attention
+        x, m = O.transformer_block(P, pre + f"vid_stem.{i}.", x, m, cfg.n_head, 1, q, qml, window=cfg.window,
+                                   channel_mix=False)
+    feats, masks = [x], [m]
+    for i in range(cfg.arch[3] + cfg.arch[4]):                                      # :601-604; the first arch[3] blocks cross-attend
+        cy, cm = (q, qml) if i < cfg.arch[3] else (None, None)
+        x, m = O.transformer_block(P, pre + f"branch.{i}.", x, m, cfg.n_head, cfg.scale_factor, cy, cm, window=cfg.window,
+                                   channel_mix=False)
+        feats.append(x)
+        masks.append(m)
+    return feats, masks
+
+
+def forward_heads(P, cfg, vid, vid_mask, txt, txt_mask):
+    """-> (list of (B, T_l, K) logits, list of (B, T_l, 2) offsets, list of (B, T_l) masks), the `get_emb=True` return of
+    PtTransformer.forward (meta_archs.py:744-745)."""
+    feats, masks = backbone(P, cfg, vid, vid_mask, txt, txt_mask)
+    fpn, masks = O.fpn_identity(P, feats, masks)
+    logits = [t.permute(0, 2, 1) for t in O.cls_head(P, fpn, masks)]
+    offsets = [t.permute(0, 2, 1) for t in O.reg_head(P, fpn, masks)]
+    return logits, offsets, [m.squeeze(1) for m in masks]
+
+
+def preprocess_eval(cfg, clip):
+    """PtTransformer.preprocessing / query_preprocessing for one evaluation clip (meta_archs.py:918-957): pad to max_seq_len."""
+    f = clip["feats"]
+    T = cfg.max_seq_len
+    assert f.shape[-1] <= T
+    vid = F.pad(f, [0, T - f.shape[-1]]).unsqueeze(0)
+    vmask = (torch.arange(T)[None, :] < f.shape[-1]).unsqueeze(1)
+    txt = clip["query_feats"].unsqueeze(0)
+    tmask = torch.ones(1, 1, txt.shape[-1], dtype=torch.bool)
+    return vid, vmask, txt, tmask

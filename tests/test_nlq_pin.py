@@ -58,3 +58,25 @@ def test_reference_reproduces_the_committed_vectors():
     assert out.returncode == 0, out.stderr[-2000:]
     err = float([ln for ln in out.stdout.splitlines() if ln.startswith("MAXERR")][-1].split()[1])
     assert err < 1e-5, err
+
+
+def test_nlq_oracle_matches_reference_golden():
+    """oracle/nlq_oracle.py (the MQ operator restatements re-composed for NLQ: window-9 attention live, head dim 96, text
+    cross-attention in the video stem) against the reference's own NLQ forward — logits / offsets within 2e-5, masks equal."""
+    from oracle import nlq_oracle as N
+    from oracle.gen_golden_nlq import nlq_random_state, synth_clips
+    spec = json.load(open(os.path.join(GOLDEN, "nlq_state_spec.json")))["state_dict"]
+    shapes = {k: tuple(v) for k, v in spec.items() if not k.endswith("num_batches_tracked")}
+    g = np.load(os.path.join(GOLDEN, "nlq_small.npz"))
+    cfg = N.NlqCfg(max_seq_len=512)
+    # the small golden model differs from the full-size spec only in buffers that depend on T (none are parameters)
+    P = nlq_random_state({k: v for k, v in shapes.items()}, 0)
+    clips = synth_clips({"dataset": {"max_seq_len": 512, "input_vid_dim": 256, "input_txt_dim": 512}}, 2, 0)
+    with torch.no_grad():
+        for i, clip in enumerate(clips):
+            logits, offsets, masks = N.forward_heads(P, cfg, *N.preprocess_eval(cfg, clip))
+            assert len(logits) == 7
+            for l in range(7):
+                assert np.array_equal(masks[l][0].numpy(), g[f"mask_{i}_{l}"])
+                assert np.abs(logits[l][0].numpy() - g[f"logits_{i}_{l}"]).max() < 2e-5, (i, l)
+                assert np.abs(offsets[l][0].numpy() - g[f"offsets_{i}_{l}"]).max() < 2e-5 * max(1.0, np.abs(g[f"offsets_{i}_{l}"]).max()), (i, l)
