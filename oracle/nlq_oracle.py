@@ -75,3 +75,27 @@ def preprocess_eval(cfg, clip):
     txt = clip["query_feats"].unsqueeze(0)
     tmask = torch.ones(1, 1, txt.shape[-1], dtype=torch.bool)
     return vid, vmask, txt, tmask
+
+
+class NlqTestCfg:
+    """test_cfg of ego4d_nlq_v2_egovlp_1e-4.yaml in the field names oracle/mq_oracle.py's decode / NMS restatements read."""
+
+    def __init__(self, cfg):
+        self.pre_nms_thresh, self.pre_nms_topk, self.duration_thresh = 0.001, 2000, 0.001
+        self.iou_threshold, self.min_score, self.max_seg_num, self.nms_sigma = 0.1, 0.001, 5, 0.75
+        self.max_seq_len = cfg.max_seq_len
+        n_levels = 1 + cfg.arch[3] + cfg.arch[4]
+        self.strides = [cfg.scale_factor ** l for l in range(n_levels)]
+        self.regression_range = [[0, 4], [2, 8], [4, 16], [8, 32], [16, 64], [32, 128], [64, 10000]]
+
+
+def infer(P, cfg, clip, softnms_fn=None):
+    """PtTransformer.forward(is_training=False) for one clip -> (segments (n, 2) seconds, scores, labels): the decode and
+    soft-NMS restatements of the MQ oracle apply unchanged (NLQ/libs/modeling/meta_archs.py inference / postprocessing)."""
+    tc = NlqTestCfg(cfg)
+    logits, offsets, masks = forward_heads(P, cfg, *preprocess_eval(cfg, clip))
+    lens = [t.shape[1] for t in logits]
+    segs, scores, labels = O.decode_single_video(tc, O.points(tc, lens), [m[0] for m in masks], [t[0] for t in logits],
+                                                 [t[0] for t in offsets])
+    return O.postprocess(tc, segs, scores, labels, clip["fps"], clip["duration"], clip["feat_stride"],
+                         clip["feat_num_frames"], softnms_fn=softnms_fn)

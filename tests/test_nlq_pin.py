@@ -80,3 +80,21 @@ def test_nlq_oracle_matches_reference_golden():
                 assert np.array_equal(masks[l][0].numpy(), g[f"mask_{i}_{l}"])
                 assert np.abs(logits[l][0].numpy() - g[f"logits_{i}_{l}"]).max() < 2e-5, (i, l)
                 assert np.abs(offsets[l][0].numpy() - g[f"offsets_{i}_{l}"]).max() < 2e-5 * max(1.0, np.abs(g[f"offsets_{i}_{l}"]).max()), (i, l)
+
+
+def test_nlq_oracle_detections_match_reference_golden():
+    """decode + soft-NMS (sigma 0.75, 5 segments per query) of the oracle on its own logits == the reference's detections."""
+    from oracle import nlq_oracle as N
+    from oracle import nms_c
+    from oracle.gen_golden_nlq import nlq_random_state, synth_clips
+    spec = json.load(open(os.path.join(GOLDEN, "nlq_state_spec.json")))["state_dict"]
+    P = nlq_random_state({k: tuple(v) for k, v in spec.items()}, 0)
+    g = np.load(os.path.join(GOLDEN, "nlq_small.npz"))
+    cfg = N.NlqCfg(max_seq_len=512)
+    clips = synth_clips({"dataset": {"max_seq_len": 512, "input_vid_dim": 256, "input_txt_dim": 512}}, 2, 0)
+    with torch.no_grad():
+        for i, clip in enumerate(clips):
+            s, sc, lb = N.infer(P, cfg, clip, softnms_fn=nms_c.softnms_1d)
+            assert s.shape == (5, 2) and np.array_equal(lb.numpy(), g[f"det_labels_{i}"])
+            assert np.abs(sc.numpy() - g[f"det_scores_{i}"]).max() < 1e-5
+            assert np.abs(s.numpy() - g[f"det_segments_{i}"]).max() < 1e-3
