@@ -84,6 +84,20 @@ def main():
             res = model([clip], is_training=False)[0]
             for k in ("segments", "scores", "labels"):
                 out[f"det_{k}_{i}"] = res[k].numpy()
+    # training losses (meta_archs.py:746-776, 1094-1155) of the two clips as one batch: train mode with every dropout /
+    # drop-path probability set to 0 (the scales of AffineDropPath stay), so that the pass is deterministic
+    model.train()
+    for m in model.modules():
+        if hasattr(m, "drop_prob"):
+            m.drop_prob = 0.0
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    out["loss_normalizer_before"] = np.float32(model.loss_normalizer)
+    losses = model(synth_clips(cfg, 2, 0), is_training=True)
+    for k, v in losses.items():
+        out["loss_" + k] = np.float32(v.detach().item())
+    out["loss_normalizer_after"] = np.float32(model.loss_normalizer)
+    print({k: float(v) for k, v in out.items() if k.startswith("loss_")})
     np.savez_compressed(os.path.join(GOLDEN, "nlq_small.npz"), **out)
     print({k: v.shape for k, v in out.items() if k.endswith(("_0_0", "_0_6")) or k.startswith("det_")})
     print("logit range", float(out["logits_0_0"].min()), float(out["logits_0_0"].max()),

@@ -99,3 +99,57 @@ def infer(P, cfg, clip, softnms_fn=None):
                                                  [t[0] for t in offsets])
     return O.postprocess(tc, segs, scores, labels, clip["fps"], clip["duration"], clip["feat_stride"],
                          clip["feat_num_frames"], softnms_fn=softnms_fn)
+
+
+def label_points(points, gt_segments, gt_onehot, radius=1.5):
+    """Classification / regression targets of one clip, the classic ActionFormer assignment the NLQ model keeps
+    (NLQ/libs/modeling/meta_archs.py:980-1072, `center_sample: radius`): a point is positive for a moment when it lies within
+    `radius` strides of the moment's centre (clipped to the moment) and the farther boundary falls into the level's regression
+    range; among several candidates the shortest moment wins.  points (P, 4) = [t, lo, hi, stride]; returns (P, K), (P, 2)."""
+    n_pts, n_gt = points.shape[0], gt_segments.shape[0]
+    if n_gt == 0:
+        return gt_segments.new_zeros((n_pts, gt_onehot.shape[1])), gt_segments.new_zeros((n_pts, 2))
+    t, lo, hi, stride = (points[:, j, None] for j in range(4))
+    s0, s1 = gt_segments[None, :, 0], gt_segments[None, :, 1]
+    reg = torch.stack((t - s0, s1 - t), dim=-1)                                     # (P, N, 2)
+    centre = 0.5 * (s0 + s1)
+    inside = torch.minimum(t - torch.maximum(centre - stride * radius, s0), torch.minimum(centre + stride * radius, s1) - t) > 0
+    far = reg.max(-1)[0]
+    in_range = (far >= lo) & (far <= hi)
+    length = (s1 - s0).repeat(n_pts, 1).masked_fill(~(inside & in_range), float("inf"))
+    shortest, idx = length.min(dim=1)
+    pick = ((length <= shortest[:, None] + 1e-3) & (length < float("inf"))).to(reg.dtype)
+    cls_t = (pick @ gt_onehot.to(reg.dtype)).clamp(0.0, 1.0)
+    reg_t = reg[torch.arange(n_pts), idx] / stride
+    return cls_t, reg_t
+
+
+def train_losses(P, cfg, clips, loss_normalizer=200.0, momentum=0.9, label_smoothing=0.1, loss_weight=1.0):
+    """PtTransformer.forward in training mode with every dropout / drop-path probability at 0 (meta_archs.py:746-776) and
+    `losses` (:1094-1155): focal loss over valid points (label smoothing s: y(1-s) + s/(K+1)), DIoU on positives, both divided
+    by the EMA of the number of positives.  Returns the dict of the reference and the updated normaliser."""
+    T = cfg.max_seq_len
+    B = len(clips)
+    vid = torch.zeros(B, cfg.input_vid_dim, T)
+    L = max(c["query_feats"].shape[-1] for c in clips)
+    txt = torch.zeros(B, cfg.input_txt_dim, L)
+    for i, c in enumerate(clips):
+        vid[i, :, :c["feats"].shape[-1]] = c["feats"]
+        txt[i, :, :c["query_feats"].shape[-1]] = c["query_feats"]
+    vmask = (torch.arange(T)[None, :] < torch.tensor([c["feats"].shape[-1] for c in clips])[:, None]).unsqueeze(1)
+    tmask = (torch.arange(L)[None, :] < torch.tensor([c["query_feats"].shape[-1] for c in clips])[:, None]).unsqueeze(1)
+    logits, offsets, masks = forward_heads(P, cfg, vid, vmask, txt, tmask)
+    tc = NlqTestCfg(cfg)
+    pts = torch.cat(O.points(tc, [t.shape[1] for t in logits]), dim=0)
+    targets = [label_points(pts, c["segments"], c["one_hot_labels"]) for c in clips]
+    gt_cls, gt_off = torch.stack([t[0] for t in targets]), torch.stack([t[1] for t in targets])
+    valid = torch.cat(masks, dim=1)
+    pos = (gt_cls.sum(-1) > 0) & valid
+    num_pos = int(pos.sum())
+    norm = momentum * loss_normalizer + (1 - momentum) * max(num_pos, 1)
+    K = gt_cls.shape[-1]
+    target = gt_cls[valid] * (1 - label_smoothing) + label_smoothing / (K + 1)
+    cls_loss = O.sigmoid_focal_loss(torch.cat(logits, dim=1)[valid], target).sum() / norm
+    pred = torch.cat(offsets, dim=1)[pos]
+    reg_loss = O.ctr_diou_loss_1d(pred, gt_off[pos]).sum() / norm if num_pos else 0 * pred.sum()
+    return {"cls_loss": cls_loss, "reg_loss": reg_loss, "final_loss": cls_loss + reg_loss * loss_weight}, norm

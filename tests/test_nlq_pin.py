@@ -98,3 +98,21 @@ def test_nlq_oracle_detections_match_reference_golden():
             assert s.shape == (5, 2) and np.array_equal(lb.numpy(), g[f"det_labels_{i}"])
             assert np.abs(sc.numpy() - g[f"det_scores_{i}"]).max() < 1e-5
             assert np.abs(s.numpy() - g[f"det_segments_{i}"]).max() < 1e-3
+
+
+def test_nlq_oracle_training_losses_match_reference_golden():
+    """label assignment (centre sampling, radius 1.5) + focal (label smoothing 0.1) + DIoU of a two-clip batch with ragged
+    video and text lengths, deterministic train mode — against the reference's own losses."""
+    from oracle import nlq_oracle as N
+    from oracle.gen_golden_nlq import nlq_random_state, synth_clips
+    spec = json.load(open(os.path.join(GOLDEN, "nlq_state_spec.json")))["state_dict"]
+    P = nlq_random_state({k: tuple(v) for k, v in spec.items()}, 0)
+    g = np.load(os.path.join(GOLDEN, "nlq_small.npz"))
+    cfg = N.NlqCfg(max_seq_len=512)
+    clips = synth_clips({"dataset": {"max_seq_len": 512, "input_vid_dim": 256, "input_txt_dim": 512}}, 2, 0)
+    with torch.no_grad():
+        losses, norm = N.train_losses(P, cfg, clips, loss_normalizer=float(g["loss_normalizer_before"]))
+    assert abs(norm - float(g["loss_normalizer_after"])) < 1e-3
+    for k in ("cls_loss", "reg_loss", "final_loss"):
+        ref = float(g["loss_" + k])
+        assert abs(float(losses[k]) - ref) <= 2e-5 * max(1.0, abs(ref)), (k, float(losses[k]), ref)
