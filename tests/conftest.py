@@ -26,3 +26,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_library():
+    """libvilco_b200.so is a build artefact (git-ignored): build it once per session when it is missing, so that any subset of
+    the tests can be run from a fresh checkout.  (The product itself never builds on demand: vilco_b200.lib raises.)"""
+    from vilco_b200 import lib
+    if not os.path.exists(lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    yield
