@@ -105,3 +105,28 @@ def test_two_ranks_shard_by_clip_and_agree_with_one_process():
     assert out[0][1] == 3 and out[1][1] == 2                # rank 0: clips 0,2,4,6,8 -> 3 batches; rank 1: 1,3,5,7 -> 2
     for _, _, m, a, r in out:
         assert m == mAP.tolist() and a == float(avg) and r == rec.tolist()
+
+
+def test_prompt_models_are_evaluated_eagerly_in_the_same_batches():
+    """a model with an L2P prompt pool cannot be graph-captured: the pass calls model(batch, is_training=False, task_id=...)
+    on the regrouped batches instead and gives the same table."""
+    from vilco_b200.utils.metrics import ANETdetection
+    from vilco_b200.utils.validate import valid_one_epoch
+    calls = []
+
+    class PromptModel(torch.nn.Module):
+        prompt = object()
+
+        def forward(self, video_list, task_id=-1, is_training=True):
+            assert not is_training
+            calls.append((len(video_list), task_id))
+            return next(FakeGraph(len(video_list)).infer_stream([video_list]))
+
+        def make_eval_graph(self, *a, **k):
+            raise AssertionError("a prompt model must not be graph-captured")
+
+    ev = ANETdetection(_ground_truth(7), tiou_thresholds=np.linspace(0.1, 0.5, 5))
+    mAP, avg, _, rec = valid_one_epoch(_loader(7), PromptModel(), 0, evaluator=ev, batch_size=3, task_id=2)
+    assert calls == [(3, 2), (3, 2), (3, 2)] and rec is None
+    (mAP2, avg2, _, _), _, _ = _run(7, 3)
+    assert np.array_equal(mAP, mAP2) and avg == avg2

@@ -67,13 +67,28 @@ def results_table(outputs):
             'score': cat(sc, np.float32)}
 
 
+class _EagerStream:
+    """`infer_stream` for models whose evaluation step cannot be captured in a CUDA graph — the L2P prompt pool of
+    `mq_vilco.yaml` selects its prompts on the host (`EvalGraph` refuses such a model): the same batches go through
+    `model(batch, is_training=False, task_id=...)`, i.e. the same kernels launched eagerly."""
+
+    def __init__(self, model, task_id=-1):
+        self.model, self.task_id = model, task_id
+
+    def infer_stream(self, batches):
+        for batch in batches:
+            yield self.model(batch, task_id=self.task_id, is_training=False)
+
+
 def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluator=None, output_file=None, tb_writer=None,
                     print_freq=20, logger=None, dataset_name=None, *, batch_size=32, text_len=128, graph=None,
-                    sharded_loader=False, current_task_id=None, retrieval_gt=None, idx_classes=None, use_cl=False):
+                    sharded_loader=False, current_task_id=None, retrieval_gt=None, idx_classes=None, use_cl=False,
+                    task_id=-1):
     """Drop-in for `valid_one_epoch(val_loader, model, curr_epoch, ...)`; keyword-only extensions after `*`:
     batch_size / text_len of the captured graph, `graph` (an existing `EvalGraph`), `sharded_loader`, `current_task_id` +
     `use_cl` for the query-incremental evaluator, `retrieval_gt` (annotation file or loaded object) + `idx_classes`
-    (integer label → ground-truth label key) to get the recall table without the json round trip."""
+    (integer label → ground-truth label key) to get the recall table without the json round trip, `task_id` for models
+    with a prompt pool (evaluated eagerly, see `_EagerStream`)."""
     assert (evaluator is not None) or (output_file is not None)
     if ext_score_file is not None:
         raise NotImplementedError("valid_one_epoch: external classification scores (postprocess_results) are not part of "
@@ -83,7 +98,12 @@ def valid_one_epoch(val_loader, model, curr_epoch, ext_score_file=None, evaluato
     rank, world = 0, 1
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-    g = graph if graph is not None else model.make_eval_graph(batch_size, text_len=text_len)
+    if graph is not None:
+        g = graph
+    elif hasattr(model, "prompt"):
+        g = _EagerStream(model, task_id)
+    else:
+        g = model.make_eval_graph(batch_size, text_len=text_len)
     real = []
     start = time.time()
 
