@@ -115,3 +115,24 @@ def test_data_path_argument_checks_need_no_gpu():
     with pytest.raises(ValueError, match="multiple of 4"):
         data.resize_feats(torch.zeros(3, 6), 16)
     assert data.feat_stride_after_resize(480.0, 30.0, 1024) == (480.0 * 30.0 / 1024, 480.0 * 30.0 / 1024)
+
+
+def test_reference_style_inference_lists_pack_into_the_pyramid_layout():
+    """model.inference(video_list, points, fpn_masks, cls_list, off_list, None, None) as infer_one_epoch_ensemble calls it
+    (train_utils.py:957-961): the per-level lists are packed into the concatenated layout (host/torch glue, CPU-checkable)."""
+    from vilco_b200.modeling.meta_archs import PtTransformer
+    torch.manual_seed(0)
+    lens, B, K = [8, 4, 2], 2, 3
+    cls_l = [torch.randn(B, n, K) for n in lens]
+    off_l = [torch.rand(B, n, 2) for n in lens]
+    msk_l = [torch.rand(B, n) > 0.3 for n in lens]
+    pyr, pmask, logits, offsets = PtTransformer._lists_to_pyramid(msk_l, cls_l, off_l)
+    assert pyr.lens == lens and pyr.off == [0, 9, 14] and pyr.P == 24 and logits.shape == (B, 24, K)
+    for o, n, lg, of, mk in zip(pyr.off, pyr.lens, cls_l, off_l, msk_l):
+        assert torch.equal(logits[:, o:o + n], lg) and torch.equal(offsets[:, o:o + n], of)
+        assert torch.equal(pmask[:, o:o + n], mk.float())
+    gap = pyr.gap_rows.bool()
+    assert float(logits[:, gap].abs().sum()) == 0 and float(pmask[:, gap].sum()) == 0
+    # the (B, 1, T_l) masks the EMA-ensemble quirk of get_emb returns are accepted too
+    pyr2, pmask2, _, _ = PtTransformer._lists_to_pyramid([m.unsqueeze(1) for m in msk_l], cls_l, off_l)
+    assert torch.equal(pmask2, pmask)

@@ -48,3 +48,26 @@ def test_icarl_rescoring_vs_reference_golden():
             ok = (lb == gl[j]) & (np.abs(sc - gsc[j]) < 1e-5) & (np.abs(s - gs[j]).max(1) < 5e-2)
             hit += bool(ok.any())
         assert hit / len(gsc) > 0.75, (i, hit, len(gsc))
+
+
+def test_reference_style_ensemble_inference_call():
+    """infer_one_epoch_ensemble's calling form (train_utils.py:945-961): forward(ensemble=True) returns the per-level lists,
+    the caller averages them over models and hands them to model.inference(video_list, points, masks, cls, offs, None, None).
+    Averaging two copies of the same outputs is the identity, so the detections must equal the plain evaluation call."""
+    from oracle import params as PR
+    from oracle.gen_golden import small_cfg
+    cfg = small_cfg()
+    model, _ = build_pair(cfg)
+    videos = PR.synth_video_list(cfg, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    with torch.no_grad():
+        want = model(videos, is_training=False)
+        vl, points, masks, cls_l, off_l = model(videos, ensemble=True, is_training=False)
+        assert len(points) == len(cls_l) == len(off_l) == len(masks) and cls_l[0].shape[:2] == (2, 128)
+        cls_avg = [(a + a) / 2.0 for a in cls_l]
+        off_avg = [(a + a) / 2.0 for a in off_l]
+        got = model.inference(vl, points, masks, cls_avg, off_avg, None, None)
+    assert len(got) == len(want) == 2
+    for a, b in zip(got, want):
+        assert a["video_id"] == b["video_id"]
+        assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["labels"], b["labels"])
+        assert torch.equal(a["segments"], b["segments"])

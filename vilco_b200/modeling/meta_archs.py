@@ -1012,7 +1012,11 @@ class PtTransformer(nn.Module):
         host exactly like the reference (meta_archs.py:1723-1727).  Accepts the concatenated-pyramid tensors produced by
         forward(); returns one dict per video with CPU tensors."""
         pyr = points_or_pyr
-        assert isinstance(pyr, E.Pyramid), "inference() expects the pyramid layout returned by forward()"
+        if not isinstance(pyr, E.Pyramid):
+            # the reference's calling form (infer_one_epoch_ensemble, train_utils.py:957-961): per-level lists as returned by
+            # forward(ensemble=True) — points [T_l, 4], masks (B, T_l), logits (B, T_l, K), offsets (B, T_l, 2), e.g. averaged
+            # over several models — packed back into the concatenated pyramid layout the decode kernel reads
+            pyr, fpn_masks, out_cls_logits, out_offsets = self._lists_to_pyramid(fpn_masks, out_cls_logits, out_offsets)
         segs, scores, labels, count = self._decode_nms_device(pyr, fpn_masks, out_cls_logits, out_offsets)
         results = self._to_results(video_list, segs.cpu(), scores.cpu(), labels.cpu(), count.cpu())
         # iCaRL (meta_archs.py:1559-1562): while `compute_means` is set and the validation passes its task object, a clip is
@@ -1023,6 +1027,22 @@ class PtTransformer(nn.Module):
                 results[idx] = self._rescored_result(v, idx, self.classify(v, cilsettask), pyr, fpn_masks, out_cls_logits,
                                                      out_offsets)
         return results
+
+    @staticmethod
+    def _lists_to_pyramid(fpn_masks, out_cls_logits, out_offsets):
+        """per-level lists -> (Pyramid, pmask (B, P) fp32, logits (B, P, K) fp32, offsets (B, P, 2) fp32); gap rows stay zero
+        (mask 0: never a candidate)."""
+        dev = out_cls_logits[0].device
+        B, K = out_cls_logits[0].shape[0], out_cls_logits[0].shape[2]
+        pyr = E.Pyramid([t.shape[1] for t in out_cls_logits], dev)
+        logits = torch.zeros(B, pyr.P, K, device=dev, dtype=torch.float32)
+        offsets = torch.zeros(B, pyr.P, 2, device=dev, dtype=torch.float32)
+        pmask = torch.zeros(B, pyr.P, device=dev, dtype=torch.float32)
+        for o, n, lg, of, mk in zip(pyr.off, pyr.lens, out_cls_logits, out_offsets, fpn_masks):
+            logits[:, o:o + n] = lg
+            offsets[:, o:o + n] = of
+            pmask[:, o:o + n] = mk.reshape(B, n).to(torch.float32)
+        return pyr, pmask, logits, offsets
 
     def _fpn_features(self, video_list):
         """FPN outputs of `neck(backbone(...))` per level in the reference layout (B, C, T_l), fp32 — the quantity
