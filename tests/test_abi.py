@@ -136,3 +136,21 @@ def test_reference_style_inference_lists_pack_into_the_pyramid_layout():
     # the (B, 1, T_l) masks the EMA-ensemble quirk of get_emb returns are accepted too
     pyr2, pmask2, _, _ = PtTransformer._lists_to_pyramid([m.unsqueeze(1) for m in msk_l], cls_l, off_l)
     assert torch.equal(pmask2, pmask)
+
+
+def test_orchestration_facing_attributes_exist():
+    """every attribute / method train.py, train_cl.py, train_bic.py, eval.py, train_utils.py and the EWC / MAS helpers touch
+    on the model (enumerated from the reference with grep) exists on the mirror."""
+    from oracle.gen_golden import small_cfg
+    from vilco_b200.config import mq_model_kwargs
+    from vilco_b200.modeling import make_meta_arch
+    c = small_cfg()
+    m = make_meta_arch("LocPointTransformer", **mq_model_kwargs(c.input_dim, c.embd_dim, c.n_head, c.max_seq_len, c.arch,
+                                                                 c.num_classes, c.n_txt_in, c.regression_range))
+    for name in ("use_adapt", "pre_train_epoch", "post_train_step", "cl_name", "compute_means", "type_sampling", "n_known",
+                 "memory", "add_samples_to_mem", "reg_params", "num_classes", "device", "augment_classification",
+                 "list_bias_layers", "list_splits", "inference", "classify", "exemplar_means", "loss_normalizer",
+                 "state_dict", "load_state_dict", "named_parameters", "named_modules"):
+        assert hasattr(m, name), name
+    assert m.cls_head.cls_head.conv.out_channels == c.num_classes
+    assert isinstance(m.memory, dict) and isinstance(m.reg_params, dict) and m.list_bias_layers is not None

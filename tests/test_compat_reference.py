@@ -101,3 +101,27 @@ def test_launcher_runs_an_unmodified_style_script_on_the_mirrors(tmp_path, capsy
         for m, d in saved:                                 # undo compat.install() for the other tests of this process
             for k, v in d.items():
                 setattr(m, k, v)
+
+
+def test_replay_memory_update_matches_the_reference_under_the_same_seed(capsys):
+    """model.add_samples_to_mem(cilsettask, data, m) (train_cl.py:353): same exemplars as the reference's method for the same
+    `random` seed, for a numeric budget and for 'ALL'."""
+    import copy
+    import random
+    import types
+    from oracle import ref_shim
+    from vilco_b200.modeling.meta_archs import PtTransformer
+    ns = ref_shim.load()
+    ref_fn = ns.meta_archs.PtTransformer.add_samples_to_mem
+    old = {3: [f"old3_{i}" for i in range(7)], 5: [f"old5_{i}" for i in range(4)]}
+    new = {5: [f"new5_{i}" for i in range(6)], 8: [f"new8_{i}" for i in range(9)], 9: ["only"]}
+    for m in (4, 'ALL'):
+        a, b = types.SimpleNamespace(memory=copy.deepcopy(old)), types.SimpleNamespace(memory=copy.deepcopy(old))
+        random.seed(11)
+        ref_fn(a, None, copy.deepcopy(new), m)
+        state = random.getstate()
+        random.seed(11)
+        PtTransformer.add_samples_to_mem(b, None, copy.deepcopy(new), m)
+        assert random.getstate() == state and a.memory == b.memory, m
+        assert list(b.memory) == [3, 5, 8, 9] and (m == 'ALL' or all(len(v) <= m for v in b.memory.values()))
+    assert "Memory... Class: 8, num videos: 4" in capsys.readouterr().out

@@ -359,6 +359,19 @@ class PtTransformer(nn.Module):
             for idx, ema in enumerate(reversed(self.pets_emas)):
                 ema.update(self.pets if idx == 0 else self.pets_emas[idx - 1])
 
+    def add_samples_to_mem(self, cilsettask, data, m):
+        """Replay memory update after a task (train_cl.py:353; reference: meta_archs.py:972, active part :1043-1055): the new
+        classes' clips are merged into `self.memory` (same class id: replaced), every class list is shuffled in place with
+        Python's `random` — one shuffle per class in dictionary order, so a seeded run keeps the reference's exemplars — and
+        cut to `m` clips (`'ALL'` keeps everything).  `cilsettask` is unused, as in the reference's random sampling."""
+        import random
+        self.memory = {**self.memory, **data}
+        for class_id, videos in self.memory.items():
+            random.shuffle(videos)
+            self.memory[class_id] = videos if m == 'ALL' else videos[:m]
+        for class_id, videos in self.memory.items():
+            print('Memory... Class: {}, num videos: {}'.format(class_id, len(videos)))
+
     def augment_classification(self, num_new_classes, device):
         """Grow the classifier and the per-class gaussian parameters (reference: meta_archs.py:715-751)."""
         device = self.mu.device
