@@ -104,6 +104,32 @@ def run_reference(c, model, videos):
     return out
 
 
+def full_cfg(num_classes=22):
+    """mq_no_cl.yaml at full size (C=1024, T=1024, input 4096, 10 levels); num_classes=110 = after augment_classification
+    over the 5 sub-tasks (train_cl.py:378)."""
+    return O.ModelCfg(num_classes=num_classes)
+
+
+FULL_VIDEOS = dict(seed=8, lens=[1024, 700], text_lens=[57, 33], n_gt=[4, 3])
+
+
+def gen_full_golden():
+    """The north-star configuration itself: the REFERENCE at mq_no_cl.yaml full size on 2 clips (T = 1024 and a ragged 700),
+    K = 22 and K = 110 -> tests/golden/model_full.npz: per clip the logits / offsets / masks over all 2046 pyramid points, the
+    final detections (decode + soft-NMS, 200 kept segments), and the training losses of the 2-clip batch."""
+    out = {}
+    for K in (22, 110):
+        c = full_cfg(K)
+        model, _ = build_reference_model(c, seed=4)
+        videos = PR.synth_video_list(c, 2, **FULL_VIDEOS)
+        r = run_reference(c, model, videos)
+        for k, v in r.items():
+            out[f"k{K}_{k}"] = v
+        del model
+    np.savez_compressed(os.path.join(GOLDEN, "model_full.npz"), **out)
+    print("model_full:", {k: (v.shape if hasattr(v, "shape") and v.shape else float(v)) for k, v in out.items()})
+
+
 def gen_model_golden():
     c = small_cfg()
     model, _ = build_reference_model(c, seed=0)
@@ -365,3 +391,5 @@ if __name__ == "__main__":
         gen_nms_voting_golden()
     if "optimizer" in what:
         gen_optimizer_groups_golden()
+    if "full" in what:
+        gen_full_golden()
