@@ -425,7 +425,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="clips per step per GPU")
     ap.add_argument("--train-batch", type=int, default=32, help="clips per training step per GPU (0 = skip the training leg)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=None, choices=[None, "bf16", "bf16x3"])
+    ap.add_argument("--precision", default=None, choices=[None, "mixed", "fp16x3", "fp16", "bf16x3", "bf16"])
     ap.add_argument("--ref-videos", type=int, default=24, help="clips per CPU-baseline sample (about 10 s on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

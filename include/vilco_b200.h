@@ -35,6 +35,17 @@ extern "C" {
 /* dtype codes */
 #define VILCO_F32 0
 #define VILCO_BF16 1
+#define VILCO_F16 2
+
+/* Element format of the 16-bit ACTIVATION / WEIGHT operand planes every kernel of this library reads and writes
+ * (VILCO_BF16, the initial value, or VILCO_F16).  It is process-wide state read at launch time (and therefore baked
+ * into a captured CUDA graph): set it once per precision mode, before packing weights.  fp16 planes carry 11
+ * significant bits (8x tighter than bf16) at the same tensor-core rate; the 16-bit GRADIENT planes the backward
+ * kernels emit (vilco_to_planes with grad = 1, vilco_resid_branch_bwd, vilco_softmax_bwd, vilco_relshift_bwd) are
+ * always bf16 because gradient magnitudes do not fit the fp16 range.  vilco_gemm takes the format of each operand
+ * explicitly (a_fmt / b_fmt / d_dtype) since it mixes the two. */
+int vilco_set_plane_format(int fmt);
+int vilco_get_plane_format(void);
 
 const char* vilco_last_error(void);
 int vilco_version(void);
@@ -60,10 +71,14 @@ uint64_t vilco_launch_count(void);
  * epilogue order:  v = alpha*acc + bias[n];  v *= rowmul[z2*rowmul_zs + m];  v = act(v);
  *                  v = v*colscale[n] + resid[z,m,n] * (resid_masked ? rowmul[..] : 1);   store as d_dtype.
  * Any of bias / rowmul / colscale / resid may be NULL.  resid is fp32 with the same strides as D.
- * Split precision ("bf16x3"): when a_lo and b_lo are non-zero they are the element offsets of a second bf16 plane with
- * x ~= hi + lo (lo = bf16(x - hi)); the kernel then accumulates hi*hi + hi*lo + lo*hi (three MMAs per k-step), which keeps
- * ~16 mantissa bits per operand (needed for the 1e-3 parity bar).  d_lo != 0 makes a bf16 output write both planes.
- * impl = 0: tcgen05 + TMA + TMEM kernel;  impl = 1: plain SIMT kernel (debug cross-check of the same math).
+ * A and B are 16-bit operands (a_fmt / b_fmt: fp16 or bf16, independently) in one or two planes: a non-zero a_lo / b_lo is
+ * the element offset of a second plane with x ~= hi + lo (lo = round16(x - hi)).  Per k-step the kernel issues hi*hi, plus
+ * hi*lo when B has a lo plane, plus lo*hi when A has one (1, 2 or 3 tcgen05.mma into the same fp32 accumulator): single
+ * planes for the contractions whose operand rounding the 1e-3 parity bar tolerates, split operands where it does not
+ * (DESIGN.md section 2).  d_dtype VILCO_BF16 / VILCO_F16 with d_lo != 0 writes both planes of the output.
+ * impl = 0: tcgen05 + TMA + TMEM kernel, tile shape chosen automatically (128 x {32,64,128} tiles on one CTA, 256 x {128,256}
+ * tiles on a CTA pair with cta_group::2 for large K-major problems);  impl = 1: plain SIMT kernel (debug cross-check of the
+ * same math);  impl = 2 / 3: tcgen05 kernel forced to one CTA / a CTA pair per tile (probes).
  * ------------------------------------------------------------------------------------ */
 typedef struct VilcoGemm {
   const void* A; int64_t a_ld, a_s1, a_s2, a_lo; int32_t a_rows;
@@ -80,6 +95,7 @@ typedef struct VilcoGemm {
   int32_t band_lo, band_hi;   /* band_hi > band_lo: only outputs with band_lo <= m + n < band_hi are computed (others untouched) */
   int32_t a_major;            /* 0: A is (a_rows, K) K-major (row stride a_ld).  1: A is stored (K, M) MN-major — element (m, k) at
                                  A[k * a_ld + m] — the natural layout of a gradient matrix used as dZ^T in dW = dZ^T X; taps must be 1 */
+  int32_t a_fmt, b_fmt;       /* element format of A / B: VILCO_BF16 or VILCO_F16 (0 = VILCO_BF16); may differ (gradient x activation) */
 } VilcoGemm;
 
 int vilco_gemm(const VilcoGemm* g, void* stream);
@@ -226,10 +242,11 @@ int vilco_attention(const void* q, int64_t q_lo, const void* k, const void* v, i
  *   dX = dZ W      : A = dZ (K-major over the output channels), B = W as MN-major operand (b_major = 1)
  *   dW = dZ^T X    : A = dZ^T (vilco_to_planes writes the transposed planes), B = X as MN-major operand
  * ------------------------------------------------------------------------------------ */
-/* y16[r,c] = x[r,c]*rowmul[r]*colmul[c] as bf16 (hi, lo) planes and / or its transpose yT16[c,r] with row stride ldT
- * (either output may be NULL). */
+/* y16[r,c] = x[r,c]*rowmul[r]*colmul[c] as 16-bit (hi, lo) planes and / or its transpose yT16[c,r] with row stride ldT
+ * (either output may be NULL).  grad != 0: x is a gradient, the planes are bf16; grad == 0: an activation, the planes use
+ * the format of vilco_set_plane_format. */
 int vilco_to_planes(const float* x, const float* rowmul, const float* colmul, void* y, int64_t y_lo, void* yT, int64_t yT_lo,
-                    int R, int C, int ldT, int Z, void* stream);   /* Z independent (R,C) matrices */
+                    int R, int C, int ldT, int Z, int grad, void* stream);   /* Z independent (R,C) matrices */
 /* XLNet rel-shift backward (modeling_xlnet_x.py:256-268): dBD[z,i,p] = dS[z,i,p-T+i] inside the band, 0 elsewhere; every
  * element of the (Z,T,2T) output is written, as fp32 (dBD) and / or as bf16 operand planes (dBD16, lo plane at + dbd_lo). */
 int vilco_relshift_bwd(const float* dS, float* dBD, void* dBD16, int64_t dbd_lo, int64_t Z, int T, void* stream);

@@ -10,6 +10,7 @@ import runpy
 import pytest
 
 pytestmark = pytest.mark.gpu
+PRECISION = "fp16x3"   # the tolerances below state the exact (split-operand) arithmetic; see conftest._precision_mode
 
 
 def test_backward_primitives_match_torch_autograd():

@@ -12,6 +12,7 @@ from conftest import GOLDEN
 from util import build_pair, rel_max
 
 pytestmark = pytest.mark.gpu
+PRECISION = "fp16x3"   # the tolerances below state the exact (split-operand) arithmetic; see conftest._precision_mode
 
 
 def test_icarl_rescoring_vs_reference_golden():

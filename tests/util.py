@@ -1,3 +1,5 @@
+import contextlib
+
 import numpy as np
 import torch
 
@@ -61,3 +63,45 @@ def build_vilco_train_pair(cfg, seed=2):
     assert not unexpected
     model.xl_dropout = 0.0
     return model.cuda(), P
+
+
+@contextlib.contextmanager
+def precision(name):
+    """run a block in another operand-format policy (vilco_b200.ops.set_precision)"""
+    from vilco_b200 import ops
+    prev = ops.precision()
+    ops.set_precision(name)
+    try:
+        yield
+    finally:
+        ops.set_precision(prev)
+
+
+def oracle_detections(cfg, video, cls_l, off_l, msk_l):
+    """The REFERENCE ALGORITHM's decode + soft-NMS + post-processing (oracle restatement, pinned bit-exactly to the
+    reference's own extension) applied to GIVEN head outputs (per-level lists, batch 1).  Comparing it with the CUDA path's
+    detections isolates the decode / NMS kernels from the rounding of the network in front of them."""
+    from oracle import mq_oracle as O
+    from oracle import nms_c
+    pts = O.points(cfg, [m.shape[1] for m in msk_l])
+    segs, scores, labels = O.decode_single_video(cfg, pts, [m[0].cpu().bool() for m in msk_l], [l[0].cpu() for l in cls_l],
+                                                 [o[0].cpu() for o in off_l])
+    return O.postprocess(cfg, segs, scores, labels, video["fps"], video["duration"], video["feat_stride"],
+                         video["feat_num_frames"], nms_c.softnms_1d)
+
+
+def match_detections(res, g_segs, g_scores, g_labels, seg_tol=2e-3):
+    """-> (max score diff by rank, number of ranks whose label differs, max |segment diff| over same-label ranks,
+    number of our detections with no (label, segment) partner anywhere in the reference list)."""
+    segs, scores, labels = (np.asarray(res[k]) for k in ("segments", "scores", "labels"))
+    g_segs, g_scores, g_labels = np.asarray(g_segs), np.asarray(g_scores), np.asarray(g_labels)
+    assert segs.shape == g_segs.shape, (segs.shape, g_segs.shape)
+    ds = float(np.abs(scores - g_scores).max()) if len(scores) else 0.0
+    same = labels == g_labels
+    dseg = float(np.abs(segs[same] - g_segs[same]).max()) if same.any() else 0.0
+    orphans = 0
+    for s, lb in zip(segs, labels):
+        cand = g_segs[g_labels == lb]
+        if cand.size == 0 or np.abs(cand - s[None]).max(1).min() > seg_tol:
+            orphans += 1
+    return ds, int((~same).sum()), dseg, orphans

@@ -1,0 +1,139 @@
+"""GPU probe of the unified tcgen05 GEMM: operand formats (fp16 / bf16, mixed), 1 or 2 planes per operand, one CTA or a CTA
+pair (cta_group::2) per tile, k=3 taps, ragged M / N, every output type — against torch float64 matmuls of the same rounded
+operands — then CUDA-event timings of the Moment-Query shapes at 32 clips.
+
+    python tools/gemm2_probe.py            # correctness + timing        python tools/gemm2_probe.py check | time
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vilco_b200 import lib as L  # noqa: E402
+
+torch.manual_seed(0)
+dev = "cuda"
+bad = 0
+F16, BF16 = torch.float16, torch.bfloat16
+
+
+def planes(x, dtype, n):
+    hi = x.to(dtype)
+    if n == 1:
+        return hi.unsqueeze(0).contiguous()
+    return torch.stack([hi, (x - hi.float()).to(dtype)]).contiguous()
+
+
+def lo(t):
+    return t.stride(0) if t.shape[0] == 2 else 0
+
+
+def report(name, got, ref, tol):
+    global bad
+    got = got.double()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-9
+    ok = err <= tol * scale and torch.isfinite(got).all().item()
+    bad += 0 if ok else 1
+    print(f"{'OK ' if ok else 'BAD'} {name:78s} rel_err {err / scale:.2e} (tol {tol:.0e})", flush=True)
+
+
+def case(M, N, K, fa, fb, pa, pb, impl, out=torch.float32, taps=1, epi=False, dplanes=1):
+    """D = A W^T (taps: k=3 conv over rows) with operands rounded to their planes; reference = float64 on the SAME rounded
+    operands, so the tolerance only covers fp32 accumulation (+ the dropped lo*lo term and the output rounding)."""
+    A32 = torch.randn(M, K, device=dev)
+    W32 = torch.randn(taps, N, K, device=dev) * 0.1
+    A, W = planes(A32, fa, pa), planes(W32, fb, pb)
+    Ar, Wr = A.double().sum(0), W.double().sum(0)
+    if taps == 1:
+        ref = Ar @ Wr[0].t()
+    else:
+        Ap = torch.nn.functional.pad(Ar, (0, 0, 1, 1))
+        ref = sum(Ap[t:t + M] @ Wr[t].t() for t in range(3))
+    D = torch.zeros(dplanes if out != torch.float32 else 1, M, N, device=dev, dtype=out)
+    kw = {}
+    if epi:
+        bias = torch.randn(N, device=dev)
+        rowmul = (torch.rand(M, device=dev) > 0.3).float() * 1.5
+        colscale = torch.randn(N, device=dev)
+        kw = dict(bias=bias, rowmul=rowmul, colscale=colscale, act=L.ACT_RELU, alpha=0.5)
+        ref = torch.relu((ref * 0.5 + bias.double()) * rowmul.double()[:, None]) * colscale.double()
+        if out == torch.float32:
+            resid = torch.randn(M, N, device=dev)
+            kw.update(resid=resid, resid_masked=True)
+            ref = ref + resid.double() * rowmul.double()[:, None]
+    L.gemm(A, W, D[0] if out == torch.float32 else D, M=M, N=N, K=K, a_rows=M, a_ld=K, b_ld=K, b_s=(N * K, 0), d_ld=N, taps=taps,
+           impl=impl, a_lo=lo(A), b_lo=lo(W), d_lo=lo(D) if out != torch.float32 else 0, **kw)
+    torch.cuda.synchronize()
+    got = D.double().sum(0)
+    # dropped lo*lo term: 2^-2p of the product magnitude; output rounding when the result is a single 16-bit plane
+    eps = {F16: 2.0 ** -11, BF16: 2.0 ** -8}
+    tol = 3e-6 + (eps[fa] * eps[fb] * 4 if pa == 2 and pb == 2 else 0)
+    if out != torch.float32:
+        tol += eps[out] if dplanes == 1 else eps[out] ** 2 * 4
+    name = (f"M{M} N{N} K{K} taps{taps} A:{str(fa)[6:]}x{pa} B:{str(fb)[6:]}x{pb} impl{impl} out:{str(out)[6:]}x{dplanes} epi{int(epi)}")
+    report(name, got, ref, tol)
+
+
+def check():
+    for impl in (1, 2, 3):   # SIMT, one CTA per tile, CTA pair per tile
+        for fa, fb in ((F16, F16), (BF16, BF16), (BF16, F16)):
+            for pa, pb in ((1, 1), (2, 2), (2, 1), (1, 2)):
+                case(512, 256, 256, fa, fb, pa, pb, impl)
+        case(1000, 520, 328, F16, F16, 1, 1, impl, epi=True)                        # ragged M / N / K tails + epilogue
+        case(2056 * 2, 1024, 1024, F16, F16, 1, 1, impl, taps=3, epi=True)           # head-conv shape (flat pyramid rows)
+        case(1030, 256, 512, F16, F16, 2, 2, impl, taps=3)
+        case(2048, 1024, 1024, F16, F16, 1, 1, impl, out=F16, epi=True)              # 16-bit output, one plane
+        case(2048, 1024, 1024, F16, F16, 2, 2, impl, out=F16, dplanes=2, epi=True)   # 16-bit output, two planes
+        case(2048, 3072, 1024, BF16, BF16, 2, 2, impl, out=BF16, dplanes=2)
+        case(777, 110, 1024, F16, F16, 1, 1, impl, taps=3, epi=True)                 # N % 8 != 0 (K = 110 classes)
+        case(4096, 4096, 1024, F16, F16, 1, 1, impl, out=F16, epi=True)
+    print("launches", L.launch_count(), "bad", bad)
+
+
+def timeit(fn, flops, name, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n
+    print(f"{name:70s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s", flush=True)
+
+
+def timing():
+    Bc = int(os.environ.get("CLIPS", 32))
+    shapes = [("heads conv3 flat", Bc * 2056, 1024, 1024, 3, torch.float32),
+              ("C x C -> planes", Bc * 1024, 1024, 1024, 1, F16),
+              ("C x C -> f32 + resid", Bc * 1024, 1024, 1024, 1, torch.float32),
+              ("mlp up (gelu) -> planes", Bc * 1024, 4096, 1024, 1, F16),
+              ("mlp down -> f32", Bc * 1024, 1024, 4096, 1, torch.float32),
+              ("proj 4096 -> planes", Bc * 1024, 1024, 4096, 1, F16),
+              ("branch level 2 C x C", Bc * 256, 1024, 1024, 1, torch.float32),
+              ("branch level 4 C x C", Bc * 64, 1024, 1024, 1, torch.float32)]
+    for name, M, N, K, taps, out in shapes:
+        for (pa, pb, impls) in ((1, 1, (2, 3)), (2, 2, (2, 3))):
+            A = planes(torch.randn(M, K, device=dev), F16, pa)
+            W = planes(torch.randn(taps, N, K, device=dev) * 0.05, F16, pb)
+            D = torch.empty(M, N, device=dev, dtype=out) if out == torch.float32 else torch.empty(1, M, N, device=dev, dtype=out)
+            resid = torch.randn(M, N, device=dev) if out == torch.float32 else None
+            bias = torch.randn(N, device=dev)
+            for impl in impls + (0,):
+                fn = lambda: L.gemm(A, W, D, M=M, N=N, K=K, a_rows=M, a_ld=K, b_ld=K, b_s=(N * K, 0), d_ld=N, taps=taps, impl=impl,  # noqa: E731
+                                    a_lo=lo(A), b_lo=lo(W), bias=bias, resid=resid, act=L.ACT_GELU if out != torch.float32 else L.ACT_NONE)
+                timeit(fn, 2.0 * M * N * K * taps, f"{name} M{M} N{N} K{K} t{taps} planes {pa}/{pb} impl{impl}")
+            del A, W, D
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["check", "time"]
+    if "check" in what:
+        check()
+    if "time" in what:
+        timing()
+    sys.exit(1 if bad else 0)

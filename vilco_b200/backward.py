@@ -13,9 +13,11 @@ from . import ops
 from .ops import _i64, _p, f32, lo
 
 
-def to_planes(x, rowmul=None, colmul=None, want=True, want_t=False, batch_dims=0):
+def to_planes(x, rowmul=None, colmul=None, want=True, want_t=False, batch_dims=0, grad=True, planes=None):
     """x (..., R, C) fp32 -> (y16 (NP,...,R,C) or None, yT16 (NP,...,C,ldT) or None), y = x * rowmul[:,None] * colmul[None,:].
-    The leading `batch_dims` dims index independent matrices (transposed separately); otherwise x is flattened to 2-D."""
+    The leading `batch_dims` dims index independent matrices (transposed separately); otherwise x is flattened to 2-D.
+    grad=True (the default here: this module handles gradients): bf16 planes; grad=False: an activation, planes in the
+    activation format."""
     assert x.dtype == f32 and x.is_contiguous()
     Cc = x.shape[-1]
     if batch_dims:
@@ -26,12 +28,13 @@ def to_planes(x, rowmul=None, colmul=None, want=True, want_t=False, batch_dims=0
         Z = x.numel() // (R * Cc)
     else:
         lead, R, Z = (), x.numel() // Cc, 1
-    y = ops.empty16(*lead, R, Cc, device=x.device) if want else None
+    y = ops.empty16(*lead, R, Cc, device=x.device, grad=grad, planes=planes) if want else None
     ldT = (R + 7) // 8 * 8
     # padding columns (ldT > R) must be zero: they are read as K entries of the weight-gradient GEMMs
-    yT = (ops.zeros16 if ldT != R else ops.empty16)(*lead, Cc, ldT, device=x.device) if want_t else None
+    yT = (ops.zeros16 if ldT != R else ops.empty16)(*lead, Cc, ldT, device=x.device, grad=grad, planes=planes) if want_t else None
     L.check(L.lib().vilco_to_planes(_p(x), _p(rowmul), _p(colmul), _p(y), _i64(lo(y) if want else 0), _p(yT),
-                                    _i64(lo(yT) if want_t else 0), R, Cc, ldT, Z, L.stream_ptr()), "vilco_to_planes")
+                                    _i64(lo(yT) if want_t else 0), R, Cc, ldT, Z, int(bool(grad)), L.stream_ptr()),
+            "vilco_to_planes")
     return y, yT
 
 
@@ -190,7 +193,7 @@ def softmax_bwd(dP, scale, P32=None, P16=None, want32=False, want16=True):
     B, H, Tq, Tk = dP.shape
     ldp = (Tk + 7) // 8 * 8
     dS = torch.empty_like(dP) if want32 else None
-    dS16 = ops.empty16(B, H, Tq, ldp, device=dP.device) if want16 else None
+    dS16 = ops.empty16(B, H, Tq, ldp, device=dP.device, grad=True) if want16 else None
     L.check(L.lib().vilco_softmax_bwd(_p(P32), _p(P16), _i64(lo(P16) if P16 is not None else 0),
                                       _i64(P16.shape[-1] if P16 is not None else 0), _p(dP), _p(dS), _p(dS16),
                                       _i64(lo(dS16) if want16 else 0), _i64(ldp), _i64(B * H * Tq), Tk, C.c_float(scale),

@@ -13,9 +13,20 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<int> g_act_fmt{VILCO_BF16};
+int act_fmt() { return g_act_fmt.load(std::memory_order_relaxed); }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
 }  // namespace vilco
 
 extern "C" const char* vilco_last_error(void) { return vilco::g_err; }
-extern "C" int vilco_version(void) { return 1; }
+extern "C" int vilco_version(void) { return 2; }
 extern "C" uint64_t vilco_launch_count(void) { return vilco::g_launches.load(std::memory_order_relaxed); }
+extern "C" int vilco_set_plane_format(int fmt) {
+  if (fmt != VILCO_BF16 && fmt != VILCO_F16) {
+    vilco::set_error("vilco_set_plane_format: fmt must be VILCO_BF16 or VILCO_F16");
+    return VILCO_E_ARG;
+  }
+  vilco::g_act_fmt.store(fmt, std::memory_order_relaxed);
+  return VILCO_OK;
+}
+extern "C" int vilco_get_plane_format(void) { return vilco::act_fmt(); }

@@ -18,6 +18,7 @@ struct SmParams {
   float* P32;   // optional fp32 copy of the probabilities (row stride Tk), kept for the backward pass
   int Z1, Tq, Tk; long long p_ld; float scale; int mode;
   long long rows;
+  int fmt;      // element format of P
 };
 
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const SmParams p) {
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const SmParams p) {
   mx = warp_max(mx);
   if (mx == -INFINITY) {  // fully masked row (empty clip): the reference would produce NaN; emit zeros
     for (int j = lane; j < p.p_ld; j += 32) {
-      o[j] = __float2bfloat16_rn(0.f);
+      o[j] = __float2bfloat16_rn(0.f);              // 0x0000 in both formats
       if (p.p_lo) o[p.p_lo + j] = __float2bfloat16_rn(0.f);
     }
     return;
@@ -58,9 +59,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const SmParams p) {
   const float inv = 1.0f / sum;
   for (int j = lane; j < p.p_ld; j += 32) {
     const float v = j < p.Tk ? __expf(score(j) - mx) * inv : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    o[j] = h;
-    if (p.p_lo) o[p.p_lo + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+    store16_split(reinterpret_cast<uint16_t*>(o), j, p.p_lo, v, p.fmt);
     if (p.P32 && j < p.Tk) p.P32[row * p.Tk + j] = v;
   }
 }
@@ -118,9 +117,14 @@ __global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const SmParams p)
     const int j = 2 * lane + 64 * k;
     if (j < p.p_ld) {
       const float a0 = v[k][0] * inv, a1 = v[k][1] * inv;
-      const uint32_t h = pack_bf16x2(a0, a1);
-      *reinterpret_cast<uint32_t*>(o + j) = h;
-      if (p.p_lo) *reinterpret_cast<uint32_t*>(o + p.p_lo + j) = pack_bf16x2(a0 - bf16_lo(h), a1 - bf16_hi(h));
+      if (p.p_lo) {
+        uint32_t h, l;
+        split16x2(a0, a1, p.fmt, h, l);
+        *reinterpret_cast<uint32_t*>(o + j) = h;
+        *reinterpret_cast<uint32_t*>(o + p.p_lo + j) = l;
+      } else {
+        *reinterpret_cast<uint32_t*>(o + j) = pack16x2(a0, a1, p.fmt);
+      }
       if (p.P32 && j < p.Tk) *reinterpret_cast<float2*>(p.P32 + row * p.Tk + j) = make_float2(a0, a1);
     }
   }
@@ -141,21 +145,22 @@ struct LwParams {
   __nv_bfloat16* out;
   long long lo;                                       // lo-plane offset of q/k/v/out (0 = single plane)
   int B, T, C, H, d, W; float scale;
+  int fmt;
 };
 
-__device__ __forceinline__ float2 ld2_split(const __nv_bfloat16* p, long long lo) {
-  const uint32_t x = *reinterpret_cast<const uint32_t*>(p);
-  float2 r = make_float2(bf16_lo(x), bf16_hi(x));
+__device__ __forceinline__ float2 ld2_split(const __nv_bfloat16* p, long long lo, int fmt) {
+  float2 r = unpack16x2(*reinterpret_cast<const uint32_t*>(p), fmt);
   if (lo) {
-    const uint32_t y = *reinterpret_cast<const uint32_t*>(p + lo);
-    r.x += bf16_lo(y); r.y += bf16_hi(y);
+    const float2 y = unpack16x2(*reinterpret_cast<const uint32_t*>(p + lo), fmt);
+    r.x += y.x; r.y += y.y;
   }
   return r;
 }
-__device__ __forceinline__ void st2_split(__nv_bfloat16* p, long long lo, float a, float b) {
-  const uint32_t h = pack_bf16x2(a, b);
+__device__ __forceinline__ void st2_split(__nv_bfloat16* p, long long lo, float a, float b, int fmt) {
+  uint32_t h, l;
+  split16x2(a, b, fmt, h, l);
   *reinterpret_cast<uint32_t*>(p) = h;
-  if (lo) *reinterpret_cast<uint32_t*>(p + lo) = pack_bf16x2(a - bf16_lo(h), b - bf16_hi(h));
+  if (lo) *reinterpret_cast<uint32_t*>(p + lo) = l;
 }
 
 __global__ void __launch_bounds__(256) local_attn_kernel(const LwParams p) {
@@ -172,8 +177,8 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LwParams p) {
     const int r = idx / half, c = (idx - r * half) * 2;
     const int t = t0 - w + r;
     if (t >= 0 && t < p.T) {
-      const float2 kk = ld2_split(p.k + base + (long long)t * p.C + c, p.lo);
-      const float2 vv = ld2_split(p.v + base + (long long)t * p.C + c, p.lo);
+      const float2 kk = ld2_split(p.k + base + (long long)t * p.C + c, p.lo, p.fmt);
+      const float2 vv = ld2_split(p.v + base + (long long)t * p.C + c, p.lo, p.fmt);
       sk[r * p.d + c] = kk.x; sk[r * p.d + c + 1] = kk.y;
       sv[r * p.d + c] = vv.x; sv[r * p.d + c + 1] = vv.y;
     }
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LwParams p) {
     if (t >= p.T) break;
     __nv_bfloat16* o = p.out + base + (long long)t * p.C;
     if (mk[t] == 0.f) {  // padded query: probabilities are zeroed (blocks.py:1192-1194)
-      for (int c = lane * 2; c < p.d; c += 64) st2_split(o + c, p.lo, 0.f, 0.f);
+      for (int c = lane * 2; c < p.d; c += 64) st2_split(o + c, p.lo, 0.f, 0.f, p.fmt);
       continue;
     }
     float qv[LW_MAXD / 32];
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LwParams p) {
     for (int u = 0; u < LW_MAXD / 64; ++u) {
       const int c = lane * 2 + u * 64;
       if (c < p.d) {
-        const float2 x = ld2_split(p.q + base + (long long)t * p.C + c, p.lo);
+        const float2 x = ld2_split(p.q + base + (long long)t * p.C + c, p.lo, p.fmt);
         qv[2 * u] = x.x * p.scale; qv[2 * u + 1] = x.y * p.scale;
       } else { qv[2 * u] = 0.f; qv[2 * u + 1] = 0.f; }
     }
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(256) local_attn_kernel(const LwParams p) {
 #pragma unroll
     for (int u = 0; u < LW_MAXD / 64; ++u) {
       const int c = lane * 2 + u * 64;
-      if (c < p.d) st2_split(o + c, p.lo, acc[2 * u], acc[2 * u + 1]);
+      if (c < p.d) st2_split(o + c, p.lo, acc[2 * u], acc[2 * u + 1], p.fmt);
     }
   }
 }
@@ -265,6 +270,7 @@ struct LwBwdParams {
   float *dq, *dk, *dv;           // (B, T, C) fp32
   long long lo;
   int B, T, C, H, d, W; float scale;
+  int fmt;
 };
 
 __global__ void __launch_bounds__(256) local_attn_bwd_q_kernel(const LwBwdParams p) {
@@ -280,8 +286,8 @@ __global__ void __launch_bounds__(256) local_attn_bwd_q_kernel(const LwBwdParams
     const int r = idx / half, c = (idx - r * half) * 2;
     const int t = t0 - w + r;
     if (t >= 0 && t < p.T) {
-      const float2 kk = ld2_split(p.k + base + (long long)t * p.C + c, p.lo);
-      const float2 vv = ld2_split(p.v + base + (long long)t * p.C + c, p.lo);
+      const float2 kk = ld2_split(p.k + base + (long long)t * p.C + c, p.lo, p.fmt);
+      const float2 vv = ld2_split(p.v + base + (long long)t * p.C + c, p.lo, p.fmt);
       sk[r * p.d + c] = kk.x; sk[r * p.d + c + 1] = kk.y;
       sv[r * p.d + c] = vv.x; sv[r * p.d + c + 1] = vv.y;
     }
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(256) local_attn_bwd_q_kernel(const LwBwdParams
     for (int u = 0; u < LW_MAXD / 64; ++u) {
       const int c = lane * 2 + u * 64;
       if (c < p.d) {
-        const float2 x = ld2_split(p.q + base + (long long)t * p.C + c, p.lo);
+        const float2 x = ld2_split(p.q + base + (long long)t * p.C + c, p.lo, p.fmt);
         qv[2 * u] = x.x * p.scale; qv[2 * u + 1] = x.y * p.scale;
         gv[2 * u] = p.dO[base + (long long)t * p.C + c]; gv[2 * u + 1] = p.dO[base + (long long)t * p.C + c + 1];
       } else { qv[2 * u] = qv[2 * u + 1] = gv[2 * u] = gv[2 * u + 1] = 0.f; }
@@ -383,7 +389,7 @@ __global__ void __launch_bounds__(256) local_attn_bwd_kv_kernel(const LwBwdParam
     const int r = idx / half, c = (idx - r * half) * 2;
     const int t = t0 - w + r;
     if (t >= 0 && t < p.T) {
-      const float2 qq = ld2_split(p.q + base + (long long)t * p.C + c, p.lo);
+      const float2 qq = ld2_split(p.q + base + (long long)t * p.C + c, p.lo, p.fmt);
       sq[r * p.d + c] = qq.x; sq[r * p.d + c + 1] = qq.y;
       sg[r * p.d + c] = p.dO[base + (long long)t * p.C + c]; sg[r * p.d + c + 1] = p.dO[base + (long long)t * p.C + c + 1];
     }
@@ -433,7 +439,7 @@ static constexpr int CA_TCHUNK = 64;
 
 __global__ void __launch_bounds__(256) chan_attn_kv_kernel(const __nv_bfloat16* __restrict__ qkv, long long lo,
                                                            float* __restrict__ G, const int* __restrict__ tlen, int T,
-                                                           int C, int H, float scale) {
+                                                           int C, int H, float scale, int fmt) {
   __shared__ float sk[CA_TCHUNK][CA_D + 1];
   __shared__ float sv[CA_TCHUNK][CA_D + 1];
   const int h = blockIdx.y, b = blockIdx.z;
@@ -448,8 +454,8 @@ __global__ void __launch_bounds__(256) chan_attn_kv_kernel(const __nv_bfloat16* 
     const int r = idx / (CA_D / 2), c = (idx % (CA_D / 2)) * 2;
     float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
     if (r < nt) {
-      const float2 xk = ld2_split(kb + r * ld + c, lo);
-      const float2 xv = ld2_split(vb + r * ld + c, lo);
+      const float2 xk = ld2_split(kb + r * ld + c, lo, fmt);
+      const float2 xv = ld2_split(vb + r * ld + c, lo, fmt);
       k0 = xk.x * scale; k1 = xk.y * scale; v0 = xv.x; v1 = xv.y;
     }
     sk[r][c] = k0; sk[r][c + 1] = k1; sv[r][c] = v0; sv[r][c + 1] = v1;
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(256) chan_attn_kv_kernel(const __nv_bfloat16* 
 
 __global__ void __launch_bounds__(256) chan_attn_apply_kernel(const __nv_bfloat16* __restrict__ qkv, long long lo,
                                                               const float* __restrict__ G, __nv_bfloat16* __restrict__ y,
-                                                              long long y_lo, int T, int C, int H) {
+                                                              long long y_lo, int T, int C, int H, int fmt) {
   __shared__ float sa[CA_D][CA_D + 1];
   __shared__ float sq[CA_TCHUNK][CA_D + 1];
   const int h = blockIdx.y, b = blockIdx.z;
@@ -498,7 +504,7 @@ __global__ void __launch_bounds__(256) chan_attn_apply_kernel(const __nv_bfloat1
     const int r = idx / (CA_D / 2), c = (idx % (CA_D / 2)) * 2;
     float q0 = 0.f, q1 = 0.f;
     if (r < nt) {
-      const float2 x = ld2_split(qb + r * ld + c, lo);
+      const float2 x = ld2_split(qb + r * ld + c, lo, fmt);
       q0 = x.x; q1 = x.y;
     }
     sq[r][c] = q0; sq[r][c + 1] = q1;
@@ -517,7 +523,7 @@ __global__ void __launch_bounds__(256) chan_attn_apply_kernel(const __nv_bfloat1
     }
     __nv_bfloat16* o = y + ((long long)b * T + t0 + r) * C + h * CA_D + i0;
 #pragma unroll
-    for (int u = 0; u < 16; u += 2) st2_split(o + u, y_lo, acc[u], acc[u + 1]);
+    for (int u = 0; u < 16; u += 2) st2_split(o + u, y_lo, acc[u], acc[u + 1], fmt);
   }
 }
 
@@ -530,7 +536,7 @@ __global__ void __launch_bounds__(256) chan_attn_apply_kernel(const __nv_bfloat1
 static constexpr int CB_T = 32;
 
 __global__ void __launch_bounds__(256) chan_attn_dA_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ qkv,
-                                                           long long lo, float* __restrict__ dA, int T, int C, int H) {
+                                                           long long lo, float* __restrict__ dA, int T, int C, int H, int fmt) {
   __shared__ float sd[CA_TCHUNK][CA_D + 1];
   __shared__ float sq[CA_TCHUNK][CA_D + 1];
   const int h = blockIdx.y, b = blockIdx.z;
@@ -543,7 +549,7 @@ __global__ void __launch_bounds__(256) chan_attn_dA_kernel(const float* __restri
     const int r = idx / (CA_D / 2), c = (idx % (CA_D / 2)) * 2;
     float q0 = 0.f, q1 = 0.f, d0 = 0.f, d1 = 0.f;
     if (r < nt) {
-      const float2 x = ld2_split(qb + r * ld + c, lo);
+      const float2 x = ld2_split(qb + r * ld + c, lo, fmt);
       q0 = x.x; q1 = x.y;
       d0 = db[(long long)r * C + c]; d1 = db[(long long)r * C + c + 1];
     }
@@ -570,7 +576,7 @@ __global__ void __launch_bounds__(256) chan_attn_dA_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) chan_attn_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ qkv,
                                                             long long lo, const float* __restrict__ G, const float* __restrict__ dA,
-                                                            float* __restrict__ dqkv, int T, int C, int H, float scale) {
+                                                            float* __restrict__ dqkv, int T, int C, int H, float scale, int fmt) {
   __shared__ float sA[CA_D][CA_D + 1];
   __shared__ float sG[CA_D][CA_D + 1];   // dG
   __shared__ float sx[CB_T][CA_D + 1];
@@ -603,7 +609,7 @@ __global__ void __launch_bounds__(256) chan_attn_bwd_kernel(const float* __restr
         if (which == 0) v = dy[((long long)b * T + t0 + rr) * C + h * CA_D + cc];
         else {
           const __nv_bfloat16* p = qkv + ((long long)b * T + t0 + rr) * ld + (which == 1 ? 2 : 1) * C + h * CA_D + cc;
-          v = __bfloat162float(p[0]) + (lo ? __bfloat162float(p[lo]) : 0.f);
+          v = load16_split(reinterpret_cast<const uint16_t*>(p), lo, fmt);
         }
       }
       sx[rr][cc] = v;
@@ -661,6 +667,7 @@ extern "C" int vilco_softmax_rows(const float* S, const float* BD, const float* 
   p.S = S; p.BD = BD; p.kmask = kmask; p.P = static_cast<__nv_bfloat16*>(P); p.p_lo = p_lo; p.P32 = P32;
   p.Z1 = Z1; p.Tq = Tq; p.Tk = Tk; p.p_ld = p_ld; p.scale = scale; p.mode = mode;
   p.rows = (long long)Z2 * Z1 * Tq;
+  p.fmt = act_fmt();
   const long long grid = (p.rows + 7) / 8;
   const bool reg_ok = (Tk % 2 == 0) && (p_ld % 2 == 0) && Tk <= 2048 && p_ld <= ((Tk + 63) / 64) * 64 &&
                       (reinterpret_cast<uintptr_t>(S) % 8 == 0) && (!kmask || reinterpret_cast<uintptr_t>(kmask) % 8 == 0);
@@ -688,6 +695,7 @@ extern "C" int vilco_local_attention(const void* q, const void* k, const void* v
   p.v = static_cast<const __nv_bfloat16*>(v); p.mask = mask; p.rel_pe = rel_pe;
   p.out = static_cast<__nv_bfloat16*>(out); p.lo = lo;
   p.B = B; p.T = T; p.C = C; p.H = H; p.d = d; p.W = W; p.scale = 1.0f / sqrtf(static_cast<float>(d));
+  p.fmt = act_fmt();
   const size_t smem = (size_t)2 * (LW_TI + 2 * (W / 2)) * d * sizeof(float);
   static bool configured = false;
   if (!configured) {
@@ -714,6 +722,7 @@ extern "C" int vilco_local_attention_bwd(const float* dO, const void* q, const v
   p.v = static_cast<const __nv_bfloat16*>(v); p.mask = mask; p.rel_pe = rel_pe; p.dO = dO;
   p.sP = scratch_p; p.sdS = scratch_ds; p.dq = dq; p.dk = dk; p.dv = dv; p.lo = lo;
   p.B = B; p.T = T; p.C = C; p.H = H; p.d = d; p.W = W; p.scale = 1.0f / sqrtf(static_cast<float>(d));
+  p.fmt = act_fmt();
   const size_t smem = (size_t)2 * (LW_TI + 2 * (W / 2)) * d * sizeof(float);
   static bool configured = false;
   if (!configured) {
@@ -738,10 +747,12 @@ extern "C" int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VILCO_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)B * H * CA_D * CA_D, st));
   dim3 grid((T + CA_TCHUNK - 1) / CA_TCHUNK, H, B);
-  chan_attn_kv_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, tlen, T, C, H, 1.0f / sqrtf((float)CA_D));
+  chan_attn_kv_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, tlen, T, C, H, 1.0f / sqrtf((float)CA_D),
+                                            act_fmt());
   VILCO_LAUNCH_CHECK();
   if (!y) return VILCO_OK;
-  chan_attn_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, static_cast<__nv_bfloat16*>(y), y_lo, T, C, H);
+  chan_attn_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, static_cast<__nv_bfloat16*>(y), y_lo, T, C, H,
+                                               act_fmt());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -753,10 +764,10 @@ extern "C" int vilco_channel_attention_bwd(const float* dy, const void* qkv, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VILCO_CUDA(cudaMemsetAsync(dA_scratch, 0, sizeof(float) * (size_t)B * H * CA_D * CA_D, st));
   chan_attn_dA_kernel<<<dim3((T + CA_TCHUNK - 1) / CA_TCHUNK, H, B), 256, 0, st>>>(
-      dy, static_cast<const __nv_bfloat16*>(qkv), qkv_lo, dA_scratch, T, C, H);
+      dy, static_cast<const __nv_bfloat16*>(qkv), qkv_lo, dA_scratch, T, C, H, act_fmt());
   VILCO_LAUNCH_CHECK();
   chan_attn_bwd_kernel<<<dim3((T + CB_T - 1) / CB_T, H, B), 256, 0, st>>>(
-      dy, static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, dA_scratch, dqkv, T, C, H, 1.0f / sqrtf((float)CA_D));
+      dy, static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, dA_scratch, dqkv, T, C, H, 1.0f / sqrtf((float)CA_D), act_fmt());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

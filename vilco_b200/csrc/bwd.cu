@@ -11,33 +11,30 @@ namespace vilco {
 
 __device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4f(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ void st_planes(__nv_bfloat16* p, long long lo, float v) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  p[0] = h;
-  if (lo) p[lo] = __float2bfloat16_rn(v - __bfloat162float(h));
+__device__ __forceinline__ void st_planes(__nv_bfloat16* p, long long lo, float v, int fmt) {
+  store16_split(reinterpret_cast<uint16_t*>(p), 0, lo, v, fmt);
 }
 
 // four consecutive values -> hi plane (and lo plane) with one 8-byte store each; p must be 8-byte aligned, lo % 4 == 0
-__device__ __forceinline__ void st_planes4(__nv_bfloat16* p, long long lo, float4 v) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                      h3 = __float2bfloat16_rn(v.w);
-  __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
-  *reinterpret_cast<uint2*>(p) = u;
+__device__ __forceinline__ void st_planes4(__nv_bfloat16* p, long long lo, float4 v, int fmt) {
   if (lo) {
-    uint2 w;
-    w.x = pack_bf16x2(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
-    w.y = pack_bf16x2(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
-    *reinterpret_cast<uint2*>(p + lo) = w;
+    uint32_t h0, h1, l0, l1;
+    split16x2(v.x, v.y, fmt, h0, l0);
+    split16x2(v.z, v.w, fmt, h1, l1);
+    *reinterpret_cast<uint2*>(p) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(p + lo) = make_uint2(l0, l1);
+  } else {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack16x2(v.x, v.y, fmt), pack16x2(v.z, v.w, fmt));
   }
 }
-__device__ __forceinline__ float4 ld_planes4(const __nv_bfloat16* p, long long lo) {
+__device__ __forceinline__ float4 ld_planes4(const __nv_bfloat16* p, long long lo, int fmt) {
   const uint2 u = *reinterpret_cast<const uint2*>(p);
-  float4 v = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+  const float2 a = unpack16x2(u.x, fmt), b = unpack16x2(u.y, fmt);
+  float4 v = make_float4(a.x, a.y, b.x, b.y);
   if (lo) {
     const uint2 w = *reinterpret_cast<const uint2*>(p + lo);
-    v.x += bf16_lo(w.x); v.y += bf16_hi(w.x); v.z += bf16_lo(w.y); v.w += bf16_hi(w.y);
+    const float2 c = unpack16x2(w.x, fmt), d = unpack16x2(w.y, fmt);
+    v.x += c.x; v.y += c.y; v.z += d.x; v.w += d.y;
   }
   return v;
 }
@@ -45,21 +42,21 @@ __device__ __forceinline__ float4 ld_planes4(const __nv_bfloat16* p, long long l
 // plain (no transpose) fp32 -> planes, 4 elements per thread; C % 4 == 0
 __global__ void __launch_bounds__(256) to_planes_vec_kernel(const float* __restrict__ x, const float* __restrict__ rowmul,
                                                             const float* __restrict__ colmul, __nv_bfloat16* __restrict__ y,
-                                                            long long y_lo, long long rows, int C) {
+                                                            long long y_lo, long long rows, int C, int fmt) {
   const int C4 = C >> 2;
   const long long n4 = rows * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = ld4f(x + 4 * i);
     if (rowmul) { const float m = rowmul[i / C4]; v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
     if (colmul) { const float4 m = ld4f(colmul + 4 * (i % C4)); v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w; }
-    st_planes4(y + 4 * i, y_lo, v);
+    st_planes4(y + 4 * i, y_lo, v, fmt);
   }
 }
 
 // y16[r, c] = x[r, c] * rowmul[r] * colmul[c]  as bf16 planes; optional transposed copy yT16[c, r]
 __global__ void to_planes_kernel(const float* __restrict__ x, const float* __restrict__ rowmul, const float* __restrict__ colmul,
                                  __nv_bfloat16* __restrict__ y, long long y_lo, __nv_bfloat16* __restrict__ yT, long long yT_lo,
-                                 int R, int C, int ldT) {
+                                 int R, int C, int ldT, int fmt) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -74,7 +71,7 @@ __global__ void to_planes_kernel(const float* __restrict__ x, const float* __res
       v = x[(long long)r * C + c];
       if (rowmul) v *= rowmul[r];
       if (colmul) v *= colmul[c];
-      if (y) st_planes(y + (long long)r * C + c, y_lo, v);
+      if (y) st_planes(y + (long long)r * C + c, y_lo, v, fmt);
     }
     tile[j][tx] = v;
   }
@@ -82,7 +79,7 @@ __global__ void to_planes_kernel(const float* __restrict__ x, const float* __res
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
     const int c = c0 + j, r = r0 + tx;
-    if (c < C && r < R) st_planes(yT + (long long)c * ldT + r, yT_lo, tile[tx][j]);
+    if (c < C && r < R) st_planes(yT + (long long)c * ldT + r, yT_lo, tile[tx][j], fmt);
   }
 }
 
@@ -324,7 +321,7 @@ __global__ void __launch_bounds__(256) relshift_bwd_kernel(const float* __restri
     }
     const float4 o = make_float4(v[0], v[1], v[2], v[3]);
     if (dBD) st4f(dBD + 4 * idx, o);
-    if (dBD16) st_planes4(dBD16 + 4 * idx, dbd_lo, o);
+    if (dBD16) st_planes4(dBD16 + 4 * idx, dbd_lo, o, VILCO_BF16);   // gradient planes are bf16
   }
 }
 
@@ -340,7 +337,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) ew_kernel(int op, const float* __restrict__ x, const float* __restrict__ y,
                                                  const float* __restrict__ rowmul, const float* __restrict__ colmul,
                                                  float* __restrict__ out, __nv_bfloat16* __restrict__ out16, long long out16_lo,
-                                                 long long rows, int C) {
+                                                 long long rows, int C, int fmt) {
   if (VEC) {
     const int C4 = C >> 2;
     const long long n4 = rows * C4;
@@ -355,7 +352,7 @@ __global__ void __launch_bounds__(256) ew_kernel(int op, const float* __restrict
         v.x = ew_apply(op, v.x, yy.x); v.y = ew_apply(op, v.y, yy.y); v.z = ew_apply(op, v.z, yy.z); v.w = ew_apply(op, v.w, yy.w);
       }
       if (out) st4f(out + 4 * i, v);
-      if (out16) st_planes4(out16 + 4 * i, out16_lo, v);
+      if (out16) st_planes4(out16 + 4 * i, out16_lo, v, fmt);
     }
   } else {
     const long long n = rows * C;
@@ -366,7 +363,7 @@ __global__ void __launch_bounds__(256) ew_kernel(int op, const float* __restrict
         if (colmul) v *= colmul[i % C];
       } else v = ew_apply(op, v, op == 3 ? y[i] : 0.f);
       if (out) out[i] = v;
-      if (out16) st_planes(out16 + i, out16_lo, v);
+      if (out16) st_planes(out16 + i, out16_lo, v, fmt);
     }
   }
 }
@@ -384,7 +381,7 @@ __device__ __forceinline__ float keep_factor(unsigned long long seed, unsigned l
 }
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                       __nv_bfloat16* __restrict__ out16, long long out16_lo, long long n,
-                                                      unsigned int thr, float inv_keep, unsigned long long seed, int vec) {
+                                                      unsigned int thr, float inv_keep, unsigned long long seed, int vec, int fmt) {
   if (vec) {
     const long long n4 = n >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -392,14 +389,14 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
       v.x *= keep_factor(seed, 4 * i, thr, inv_keep); v.y *= keep_factor(seed, 4 * i + 1, thr, inv_keep);
       v.z *= keep_factor(seed, 4 * i + 2, thr, inv_keep); v.w *= keep_factor(seed, 4 * i + 3, thr, inv_keep);
       if (out) st4f(out + 4 * i, v);
-      if (out16) st_planes4(out16 + 4 * i, out16_lo, v);
+      if (out16) st_planes4(out16 + 4 * i, out16_lo, v, fmt);
     }
     return;
   }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i] * keep_factor(seed, i, thr, inv_keep);
     if (out) out[i] = v;
-    if (out16) st_planes(out16 + i, out16_lo, v);
+    if (out16) st_planes(out16 + i, out16_lo, v, fmt);
   }
 }
 
@@ -463,7 +460,7 @@ __global__ void __launch_bounds__(256) resid_branch_bwd_kernel(const float* __re
         t.z *= keep_factor(seed, i + 2, thr, inv_keep); t.w *= keep_factor(seed, i + 3, thr, inv_keep);
       }
       const float4 dyi = make_float4(t.x * sc.x, t.y * sc.y, t.z * sc.z, t.w * sc.w);
-      st_planes4(dy16 + i, dy_lo, dyi);
+      st_planes4(dy16 + i, dy_lo, dyi, VILCO_BF16);   // gradient planes are bf16
       sb.x += dyi.x; sb.y += dyi.y; sb.z += dyi.z; sb.w += dyi.w;
       const float4 yi = ld4f(y + i);
       ss.x += t.x * (yi.x + bc.x); ss.y += t.y * (yi.y + bc.y); ss.z += t.z * (yi.z + bc.z); ss.w += t.w * (yi.w + bc.w);
@@ -530,7 +527,8 @@ __global__ void maxpool3s2_bwd_kernel(const float* __restrict__ x, const float* 
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ P32, const __nv_bfloat16* __restrict__ P16,
                                                           long long p_lo, long long p_ld, const float* __restrict__ dP,
                                                           float* __restrict__ dS, __nv_bfloat16* __restrict__ dS16, long long ds_lo,
-                                                          long long ds_ld, long long rows, int Tk, float scale) {
+                                                          long long ds_ld, long long rows, int Tk, float scale, int pfmt) {
+  // P16 (forward probabilities) is in the activation format pfmt; the gradient planes dS16 are bf16
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -539,22 +537,21 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   const __nv_bfloat16* p16 = P16 ? P16 + row * p_ld : nullptr;
   auto prob = [&](int j) -> float {
     if (p32) return p32[j];
-    float v = __bfloat162float(p16[j]);
-    if (p_lo) v += __bfloat162float(p16[p_lo + j]);
-    return v;
+    return load16_split(reinterpret_cast<const uint16_t*>(p16) + j, p_lo, pfmt);
   };
   const bool vec = !p32 && (Tk % 4 == 0) && (p_ld % 4 == 0) && (p_lo % 4 == 0) && (ds_ld % 4 == 0) && (ds_lo % 4 == 0) && dS16 && !dS;
   float s = 0.f;
   if (vec) {   // planes in, planes out: 4 elements per lane and iteration
     for (int j = lane * 4; j < Tk; j += 128) {
-      const float4 pv = ld_planes4(p16 + j, p_lo), dv = ld4f(d + j);
+      const float4 pv = ld_planes4(p16 + j, p_lo, pfmt), dv = ld4f(d + j);
       s += (pv.x * dv.x + pv.y * dv.y) + (pv.z * dv.z + pv.w * dv.w);
     }
     s = warp_sum(s);
     for (int j = lane * 4; j < Tk; j += 128) {
-      const float4 pv = ld_planes4(p16 + j, p_lo), dv = ld4f(d + j);
+      const float4 pv = ld_planes4(p16 + j, p_lo, pfmt), dv = ld4f(d + j);
       st_planes4(dS16 + row * ds_ld + j, ds_lo, make_float4(scale * pv.x * (dv.x - s), scale * pv.y * (dv.y - s),
-                                                            scale * pv.z * (dv.z - s), scale * pv.w * (dv.w - s)));
+                                                            scale * pv.z * (dv.z - s), scale * pv.w * (dv.w - s)),
+                 VILCO_BF16);
     }
     return;
   }
@@ -563,7 +560,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   for (int j = lane; j < Tk; j += 32) {
     const float v = scale * prob(j) * (d[j] - s);
     if (dS) dS[row * Tk + j] = v;
-    if (dS16) st_planes(dS16 + row * ds_ld + j, ds_lo, v);
+    if (dS16) st_planes(dS16 + row * ds_ld + j, ds_lo, v, VILCO_BF16);
   }
 }
 
@@ -579,8 +576,9 @@ static inline int bgrid(long long n, int block, int cap = 148 * 8) {
 }
 
 extern "C" int vilco_to_planes(const float* x, const float* rowmul, const float* colmul, void* y, int64_t y_lo, void* yT,
-                               int64_t yT_lo, int R, int C, int ldT, int Z, void* stream) {
+                               int64_t yT_lo, int R, int C, int ldT, int Z, int grad, void* stream) {
   VILCO_CHECK_ARG(x && (y || yT) && R > 0 && C > 0 && Z > 0, "vilco_to_planes: bad arguments");
+  const int fmt = grad ? VILCO_BF16 : act_fmt();
   if (!yT && C % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 && y_lo % 4 == 0 &&
       (!colmul || reinterpret_cast<uintptr_t>(colmul) % 16 == 0)) {
     // Z independent matrices are contiguous: one flat pass (rowmul, when given, indexes z * R + r as well)
@@ -588,13 +586,13 @@ extern "C" int vilco_to_planes(const float* x, const float* rowmul, const float*
     long long g = (rows * (C / 4) + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
     to_planes_vec_kernel<<<static_cast<unsigned>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, rows, C);
+        x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, rows, C, fmt);
     VILCO_LAUNCH_CHECK();
     return VILCO_OK;
   }
   dim3 grid((C + 31) / 32, (R + 31) / 32, Z);
   to_planes_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, static_cast<__nv_bfloat16*>(yT), yT_lo, R, C, ldT);
+      x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, static_cast<__nv_bfloat16*>(yT), yT_lo, R, C, ldT, fmt);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -665,7 +663,8 @@ extern "C" int vilco_softmax_bwd(const float* P32, const void* P16, int64_t p_lo
                                  void* dS16, int64_t ds_lo, int64_t ds_ld, int64_t rows, int Tk, float scale, void* stream) {
   VILCO_CHECK_ARG((P32 || P16) && dP && (dS || dS16) && rows > 0 && Tk > 0, "vilco_softmax_bwd: bad arguments");
   softmax_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      P32, static_cast<const __nv_bfloat16*>(P16), p_lo, p_ld, dP, dS, static_cast<__nv_bfloat16*>(dS16), ds_lo, ds_ld, rows, Tk, scale);
+      P32, static_cast<const __nv_bfloat16*>(P16), p_lo, p_ld, dP, dS, static_cast<__nv_bfloat16*>(dS16), ds_lo, ds_ld, rows, Tk, scale,
+      act_fmt());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -702,7 +701,7 @@ extern "C" int vilco_dropout(const float* x, float* out, void* out16, int64_t ou
   auto al = [](const void* q, int a) { return !q || reinterpret_cast<uintptr_t>(q) % a == 0; };
   const int vec = (n % 4 == 0 && al(x, 16) && al(out, 16) && al(out16, 8) && out16_lo % 4 == 0) ? 1 : 0;
   dropout_kernel<<<bgrid(vec ? n / 4 : n, 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, out, static_cast<__nv_bfloat16*>(out16), out16_lo, n, thr, 1.0f / (1.0f - p), seed, vec);
+      x, out, static_cast<__nv_bfloat16*>(out16), out16_lo, n, thr, 1.0f / (1.0f - p), seed, vec, act_fmt());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -714,10 +713,10 @@ int vilco_ew(int op, const float* x, const float* y, const float* rowmul, const 
   const bool vec = C % 4 == 0 && al(x, 16) && al(y, 16) && al(colmul, 16) && al(out, 16) && al(out16, 8) && out16_lo % 4 == 0;
   if (vec)
     ew_kernel<true><<<bgrid(rows * (C / 4), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        op, x, y, rowmul, colmul, out, static_cast<__nv_bfloat16*>(out16), out16_lo, rows, C);
+        op, x, y, rowmul, colmul, out, static_cast<__nv_bfloat16*>(out16), out16_lo, rows, C, act_fmt());
   else
     ew_kernel<false><<<bgrid(rows * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        op, x, y, rowmul, colmul, out, static_cast<__nv_bfloat16*>(out16), out16_lo, rows, C);
+        op, x, y, rowmul, colmul, out, static_cast<__nv_bfloat16*>(out16), out16_lo, rows, C, act_fmt());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
@@ -12,6 +13,9 @@ namespace vilco {
 // ---- host-side error plumbing -------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// element format of the ACTIVATION / WEIGHT operand planes (VILCO_BF16 or VILCO_F16; vilco_set_plane_format).  Gradient
+// planes (the backward kernels' 16-bit outputs) are always bf16: their range does not fit fp16.
+int act_fmt();
 
 #define VILCO_CHECK_ARG(cond, ...)                         \
   do {                                                     \
@@ -70,5 +74,43 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// ---- 16-bit operand planes in either format (fmt is warp-uniform: VILCO_BF16 or VILCO_F16) -------------------------------
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fmt) {
+  if (fmt == VILCO_F16) {   // saturate instead of producing inf (fp16 max = 65504)
+    __half2 h = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, int fmt) {
+  if (fmt == VILCO_F16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return make_float2(bf16_lo(u), bf16_hi(u));
+}
+__device__ __forceinline__ uint16_t pack16(float v, int fmt) {
+  if (fmt == VILCO_F16) return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float unpack16(uint16_t u, int fmt) {
+  if (fmt == VILCO_F16) return __half2float(__ushort_as_half(u));
+  return __uint_as_float(static_cast<uint32_t>(u) << 16);
+}
+// hi plane word + the residual (lo) plane word of two values
+__device__ __forceinline__ void split16x2(float a, float b, int fmt, uint32_t& hi, uint32_t& lo) {
+  hi = pack16x2(a, b, fmt);
+  const float2 h = unpack16x2(hi, fmt);
+  lo = pack16x2(a - h.x, b - h.y, fmt);
+}
+// scalar store of one value into the hi (and, when lo != 0, the lo) plane
+__device__ __forceinline__ void store16_split(uint16_t* D, long long off, long long lo_off, float o, int fmt) {
+  const uint16_t h = pack16(o, fmt);
+  D[off] = h;
+  if (lo_off) D[lo_off + off] = pack16(o - unpack16(h, fmt), fmt);
+}
+__device__ __forceinline__ float load16_split(const uint16_t* p, long long lo, int fmt) {
+  float v = unpack16(p[0], fmt);
+  if (lo) v += unpack16(p[lo], fmt);
+  return v;
+}
 
 }  // namespace vilco

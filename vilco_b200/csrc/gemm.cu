@@ -1,10 +1,14 @@
 // Dense contraction kernel for every GEMM-shaped op on the Moment-Query path (see include/vilco_b200.h).
 //
-// tcgen05 path: one 128 x BN output tile per CTA.  Warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle),
-// warp 1 = TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM),
-// warps 2..5 = epilogue (tcgen05.ld 32x32b, fused bias / row-mask / activation / channel-scale / residual).
-// A k=3 convolution is three row-shifted TMA loads of the same activation tile accumulating into the same
-// TMEM tile; TMA out-of-bounds zero fill implements the conv zero padding and every M/N/K tail.
+// tcgen05 path, persistent and warp-specialised.  One output tile is (128 * CG) x BN, CG = 1 or 2 CTAs (cta_group::2: the two
+// CTAs of a cluster pair share one 256-row MMA; each loads its own 128 A rows and HALF of the B tile, so the operand bytes
+// every SM pulls from L2 per MMA are halved).  Warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle), warp 1 = TMEM
+// allocator + single-thread tcgen05.mma issuer (kind::f16: fp16 / bf16 operands, mixed per operand, fp32 accumulate in TMEM;
+// leader CTA only when CG = 2), warps 2..9 = epilogue (tcgen05.ld 32x32b -> swizzled smem transpose -> fused bias / row-mask /
+// activation / channel-scale / residual -> 16-byte coalesced stores).  A k=3 convolution is three row-shifted TMA loads of the
+// same activation tile accumulating into the same TMEM tile; TMA out-of-bounds zero fill implements the conv zero padding and
+// every M/N/K tail.  Operands come as 1 or 2 planes each (x ~= hi + lo): the MMAs issued per k-step are hi*hi, plus hi*lo when
+// B has a lo plane, plus lo*hi when A has one.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -12,12 +16,15 @@
 
 namespace vilco {
 
-static constexpr int BM = 128;
-static constexpr int BK = 64;            // 64 bf16 = 128 bytes = one swizzle-128B atom row
+static constexpr int BM = 128;           // rows per CTA
+static constexpr int BK = 64;            // 64 16-bit elements = 128 bytes = one swizzle-128B atom row
 static constexpr int UMMA_K = 16;
 static constexpr int NUM_THREADS = 320;  // 10 warps: TMA, MMA, 8 x epilogue
 static constexpr int EPI_WARPS = 8;
 static constexpr int EPI_SMEM = EPI_WARPS * 32 * 32 * 4;  // one swizzled 32x32 fp32 transpose buffer per epilogue warp
+static constexpr int MAX_STAGES = 8;
+static constexpr int BAR_BYTES = 1024;   // barriers + TMEM slot live in the first KB of the (1024-aligned) dynamic smem
+static constexpr int SMEM_LIMIT = 232448;
 
 struct GemmDev {
   // coordinate slots: the three outer tensor-map dims are sorted by stride on the host
@@ -27,6 +34,8 @@ struct GemmDev {
   int a_major;
   int band_lo, band_hi;  // when band_hi > band_lo: only elements with band_lo <= m + n < band_hi are needed; tiles outside are skipped
   int b_major, b_batched;
+  int pa, pb, stages;    // operand planes (1 or 2) and smem ring depth
+  int a_fmt, b_fmt;      // VILCO_BF16 / VILCO_F16 per operand
   void* D; int d_dtype; long long d_ld, d_s1, d_s2, d_lo;
   float alpha;
   const float* bias;
@@ -52,6 +61,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive on a barrier addressed in the cluster window (own CTA or the pair's leader)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -70,10 +83,25 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// cta_group::2 form: the data lands in the executing CTA's shared memory, the transaction bytes are signalled on `bar`, which
+// may live in the peer CTA of the pair (the leader's full barrier)
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                                int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// commit of a cta_group::2 MMA sequence: arrives on the barrier at the same shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void tcgen05_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
 }
 __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                 uint32_t accumulate) {
@@ -85,6 +113,25 @@ __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc,
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tcgen05_mma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+static constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: the pair's leader
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -116,26 +163,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-// instruction descriptor for kind::f16: bf16 x bf16 -> f32, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn_major, int a_mn_major = 0) {
-  return (1u << 4)                                   // c_format = F32
-         | (1u << 7)                                 // a_format = BF16
-         | (1u << 10)                                // b_format = BF16
-         | (static_cast<uint32_t>(a_mn_major) << 15) // a_major
-         | (static_cast<uint32_t>(b_mn_major) << 16) // b_major
-         | (static_cast<uint32_t>(n >> 3) << 17)     // n_dim
-         | (static_cast<uint32_t>(BM >> 4) << 24);   // m_dim
+// instruction descriptor for kind::f16: (fp16 | bf16) x (fp16 | bf16) -> f32; m = 128 (cta_group::1) or 256 (cta_group::2)
+__host__ __device__ constexpr uint32_t make_idesc(int n, int b_mn_major, int a_mn_major = 0, int a_fmt = VILCO_BF16,
+                                                  int b_fmt = VILCO_BF16, int m = BM) {
+  return (1u << 4)                                             // c_format = F32
+         | ((a_fmt == VILCO_BF16 ? 1u : 0u) << 7)              // a_format: 0 = F16, 1 = BF16
+         | ((b_fmt == VILCO_BF16 ? 1u : 0u) << 10)             // b_format
+         | (static_cast<uint32_t>(a_mn_major) << 15)           // a_major
+         | (static_cast<uint32_t>(b_mn_major) << 16)           // b_major
+         | (static_cast<uint32_t>(n >> 3) << 17)               // n_dim
+         | (static_cast<uint32_t>(m >> 4) << 24);              // m_dim
 }
-
-// SPLIT: every operand is a (hi, lo) pair of bf16 planes (x ~= hi + lo, lo = bf16(x - hi)); the product is formed as
-// hi*hi + hi*lo + lo*hi (three MMAs into the same accumulator), which recovers ~16 mantissa bits per operand.
-template <int BN, bool SPLIT>
-struct SmemLayout {
-  static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int PLANES = SPLIT ? 2 : 1;
-  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
-};
 
 // ---------------------------------------------------------------------------------------------
 // epilogue math shared by both implementations
@@ -149,41 +187,43 @@ __device__ __forceinline__ float epi_value(const GemmDev& p, float acc, int n, f
   return v + res;
 }
 
-__device__ __forceinline__ void store_bf16_split(__nv_bfloat16* D, long long off, long long lo_off, float o) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(o);
-  D[off] = h;
-  if (lo_off) D[lo_off + off] = __float2bfloat16_rn(o - __bfloat162float(h));
-}
-
 // ---------------------------------------------------------------------------------------------
 // tcgen05 kernel
 // ---------------------------------------------------------------------------------------------
-// Persistent, warp-specialised kernel.  Each CTA loops over output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
-//   warp 0      : TMA producer (ring of STAGES smem stages, full/empty mbarriers)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer; two accumulator stages in TMEM so the epilogue
-//                 of tile i overlaps the main loop of tile i+1 (tmem_full / tmem_empty mbarriers)
-//   warps 2..9  : epilogue: tcgen05.ld -> swizzled 32x32 smem transpose -> fused math -> wide coalesced global stores
-template <int BN, int STAGES, bool SPLIT>
+// Persistent: each CTA pair (CG = 2) or CTA (CG = 1) loops over output tiles t = id, id + n_workers, ...
+//   warp 0      : TMA producer (ring of p.stages smem stages, full/empty mbarriers).  CG = 2: both CTAs load their own A rows
+//                 and their half of B; all transaction bytes of a stage are signalled on the LEADER's full barrier.
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (leader CTA only); two accumulator stages in TMEM so the
+//                 epilogue of tile i overlaps the main loop of tile i+1 (tmem_full / tmem_empty mbarriers; tmem_empty lives in
+//                 the leader and counts the epilogue warps of both CTAs)
+//   warps 2..9  : epilogue of this CTA's 128 rows
+template <int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmDev p) {
-  using L = SmemLayout<BN, SPLIT>;
+  constexpr int BNH = BN / CG;                      // B rows (output columns) this CTA stages
   constexpr int ACC_COLS = BN < 32 ? 32 : BN;       // TMEM columns of one accumulator stage
   constexpr int TMEM_COLS = 2 * ACC_COLS;           // power of two >= 64
+  constexpr uint32_t A_BYTES = BM * BK * 2;         // 16 KB per plane
+  constexpr uint32_t B_BYTES = BNH * BK * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stage_buf = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES + EPI_SMEM);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  float* stage_buf = reinterpret_cast<float*>(smem + BAR_BYTES);
+  uint8_t* ring = smem + BAR_BYTES + EPI_SMEM;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int PA = p.pa, PB = p.pb, STAGES = p.stages;
+  const uint32_t stage_bytes = PA * A_BYTES + PB * B_BYTES;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
   const uint32_t full0 = smem_u32(bars);
-  const uint32_t empty0 = smem_u32(bars + STAGES);
-  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES);       // [2]
-  const uint32_t tempty0 = smem_u32(bars + 2 * STAGES + 2);  // [2]
+  const uint32_t empty0 = smem_u32(bars + MAX_STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * MAX_STAGES);       // [2]
+  const uint32_t tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);  // [2]
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -194,32 +234,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(tempty0 + 8 * a, EPI_WARPS * CG);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int kblocks = (p.K + BK - 1) / BK;
   const int iters = p.taps * kblocks;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_tiles = (p.M + BM * CG - 1) / (BM * CG);
   const int tiles_per_z = n_tiles * m_tiles;
   const int total_tiles = tiles_per_z * p.Ztot;
+  const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
   // band filter (XLNet relative scores: only bd_raw[i, p] with T <= i + p < 2T is ever read)
   auto tile_needed = [&](int m0, int n0) -> bool {
     if (p.band_hi <= p.band_lo) return true;
-    return (m0 + n0 + (BM - 1) + (BN - 1) >= p.band_lo) && (m0 + n0 < p.band_hi);
+    return (m0 + n0 + (BM * CG - 1) + (BN - 1) >= p.band_lo) && (m0 + n0 < p.band_hi);
   };
 
   if (warp == 0) {
@@ -227,11 +275,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== TMA producer =====
       int ca[4], cb[4];
       uint32_t it_g = 0;  // global k-iteration counter (continues across tiles)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = worker; t < total_tiles; t += n_workers) {
         const int z = t / tiles_per_z, r = t - z * tiles_per_z;
-        const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
+        const int mt0 = (r / n_tiles) * BM * CG, n0 = (r % n_tiles) * BN;
         const int z1 = z % p.Z1, z2 = z / p.Z1;
-        if (!tile_needed(m0, n0)) continue;
+        if (!tile_needed(mt0, n0)) continue;
+        const int m0 = mt0 + static_cast<int>(rank) * BM;     // this CTA's A rows
+        const int nb0 = n0 + static_cast<int>(rank) * BNH;    // this CTA's share of the B tile
         ca[p.a_slot_z1] = z1; ca[p.a_slot_z2] = z2;
         cb[p.b_slot_z2] = p.b_batched ? z2 : 0;
         for (int it = 0; it < iters; ++it, ++it_g) {
@@ -240,9 +290,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const int tap = it / kblocks;
           const int kb = it - tap * kblocks;
-          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES * L::PLANES;
-          mbar_expect_tx(full0 + 8 * s, L::STAGE_BYTES);
+          const uint32_t sa = smem_u32(ring + s * stage_bytes);
+          const uint32_t sb = sa + A_BYTES * PA;
+          uint32_t fb = full0 + 8 * s;
+          if (CG == 2) {
+            if (rank == 0) mbar_expect_tx(fb, stage_bytes * 2);   // the bytes of both CTAs land on the leader's barrier
+            fb &= PEER_BIT_MASK;
+          } else {
+            mbar_expect_tx(fb, stage_bytes);
+          }
           if (p.a_major == 0) {
             ca[0] = kb * BK;
             ca[p.a_slot_row] = m0 + tap - (p.taps >> 1);
@@ -253,74 +309,88 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           cb[p.b_slot_z1] = p.b_batched ? z1 : tap;
           if (p.b_major == 0) {
             cb[0] = kb * BK;
-            cb[p.b_slot_row] = n0;
+            cb[p.b_slot_row] = nb0;
           } else {
-            cb[0] = n0;
+            cb[0] = nb0;
             cb[p.b_slot_row] = kb * BK;
           }
-#pragma unroll
-          for (int pl = 0; pl < L::PLANES; ++pl) {
-            if (p.a_major == 0) {
-              tma_load_5d(sa + pl * L::A_BYTES, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3], pl);
-            } else {   // MN-major A: two (64 m x BK k) boxes, BK*128 bytes apart
-              tma_load_5d(sa + pl * L::A_BYTES, &tmA, full0 + 8 * s, ca[0], ca[1], ca[2], ca[3], pl);
-              tma_load_5d(sa + pl * L::A_BYTES + BK * 128, &tmA, full0 + 8 * s, ca[0] + 64, ca[1], ca[2], ca[3], pl);
-            }
-            if (BN <= 64 || p.b_major == 0) {
-              tma_load_5d(sb + pl * L::B_BYTES, &tmB, full0 + 8 * s, cb[0], cb[1], cb[2], cb[3], pl);
+          auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4) {
+            if (CG == 2) tma_load_5d_2sm(dst, tm, fb, c0, c1, c2, c3, c4);
+            else tma_load_5d(dst, tm, fb, c0, c1, c2, c3, c4);
+          };
+          for (int pl = 0; pl < PA; ++pl) {
+            load(sa + pl * A_BYTES, &tmA, ca[0], ca[1], ca[2], ca[3], pl);
+            if (p.a_major != 0)   // MN-major A: two (64 m x BK k) boxes, BK*128 bytes apart
+              load(sa + pl * A_BYTES + BK * 128, &tmA, ca[0] + 64, ca[1], ca[2], ca[3], pl);
+          }
+          for (int pl = 0; pl < PB; ++pl) {
+            if (BNH <= 64 || p.b_major == 0) {
+              load(sb + pl * B_BYTES, &tmB, cb[0], cb[1], cb[2], cb[3], pl);
             } else {
               // MN-major B wider than one 128-byte swizzle atom: one (64 n x BK k) box per 64 columns, BK*128 bytes apart
 #pragma unroll
-              for (int h = 0; h < BN / 64; ++h)
-                tma_load_5d(sb + pl * L::B_BYTES + h * (BK * 128), &tmB, full0 + 8 * s, cb[0] + h * 64, cb[1], cb[2], cb[3], pl);
+              for (int h = 0; h < BNH / 64; ++h)
+                load(sb + pl * B_BYTES + h * (BK * 128), &tmB, cb[0] + h * 64, cb[1], cb[2], cb[3], pl);
             }
           }
         }
+      }
+      // tail: wait until the MMAs have released every stage this CTA filled (no arrival may target an exited CTA)
+      for (int k = 0; k < STAGES; ++k, ++it_g) {
+        if (it_g < static_cast<uint32_t>(STAGES)) continue;   // stage never used
+        mbar_wait(empty0 + 8 * (it_g % STAGES), ((it_g / STAGES) & 1) ^ 1);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    const uint32_t idesc = make_idesc(BN, p.b_major, p.a_major);
-    uint32_t it_g = 0, tc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      {
-        const int r = t % tiles_per_z;
-        if (!tile_needed((r / n_tiles) * BM, (r % n_tiles) * BN)) continue;
-      }
-      const uint32_t acc = tc & 1;
-      const uint32_t tc_cur = tc++;
-      mbar_wait(tempty0 + 8 * acc, ((tc_cur >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
-      tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-      for (int it = 0; it < iters; ++it, ++it_g) {
-        const int s = it_g % STAGES;
-        const uint32_t ph = (it_g / STAGES) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+    // ===== MMA issuer (single thread of the leader CTA) =====
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc(BN, p.b_major, p.a_major, p.a_fmt, p.b_fmt, BM * CG);
+      uint32_t it_g = 0, tc = 0;
+      for (int t = worker; t < total_tiles; t += n_workers) {
+        {
+          const int r = t % tiles_per_z;
+          if (!tile_needed((r / n_tiles) * BM * CG, (r % n_tiles) * BN)) continue;
+        }
+        const uint32_t acc = tc & 1;
+        const uint32_t tc_cur = tc++;
+        mbar_wait(tempty0 + 8 * acc, ((tc_cur >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES * L::PLANES;
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+        for (int it = 0; it < iters; ++it, ++it_g) {
+          const int s = it_g % STAGES;
+          const uint32_t ph = (it_g / STAGES) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tcgen05_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(ring + s * stage_bytes);
+            const uint32_t sb = sa + A_BYTES * PA;
+            auto mma = [&](uint64_t ad, uint64_t bd, uint32_t accum) {
+              if (CG == 2) tcgen05_mma_f16_2sm(tmem_d, ad, bd, idesc, accum);
+              else tcgen05_mma_f16(tmem_d, ad, bd, idesc, accum);
+            };
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: advance 16 elements = 32 bytes inside the swizzle atom; MN-major: 16 k-rows of 128 bytes.
-            const uint32_t aoff = p.a_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
-            const uint32_t a_lbo = p.a_major == 0 ? 16 : BK * 128;
-            const uint32_t boff = p.b_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
-            const uint64_t a_hi = make_smem_desc(sa + aoff, a_lbo, 1024);
-            const uint32_t b_lbo = p.b_major == 0 ? 16 : BK * 128;   // MN-major: distance between 64-column swizzle atoms
-            const uint64_t b_hi = make_smem_desc(sb + boff, b_lbo, 1024);
-            tcgen05_mma_f16(tmem_d, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            if (SPLIT) {
-              const uint64_t a_lo = make_smem_desc(sa + L::A_BYTES + aoff, a_lbo, 1024);
-              const uint64_t b_lo = make_smem_desc(sb + L::B_BYTES + boff, b_lbo, 1024);
-              tcgen05_mma_f16(tmem_d, a_hi, b_lo, idesc, 1u);
-              tcgen05_mma_f16(tmem_d, a_lo, b_hi, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // K-major: advance 16 elements = 32 bytes inside the swizzle atom; MN-major: 16 k-rows of 128 bytes.
+              const uint32_t aoff = p.a_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
+              const uint32_t a_lbo = p.a_major == 0 ? 16 : BK * 128;
+              const uint32_t boff = p.b_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
+              const uint64_t a_hi = make_smem_desc(sa + aoff, a_lbo, 1024);
+              const uint32_t b_lbo = p.b_major == 0 ? 16 : BK * 128;   // MN-major: distance between 64-column swizzle atoms
+              const uint64_t b_hi = make_smem_desc(sb + boff, b_lbo, 1024);
+              mma(a_hi, b_hi, (it > 0 || k > 0) ? 1u : 0u);
+              if (PB == 2) mma(a_hi, make_smem_desc(sb + B_BYTES + boff, b_lbo, 1024), 1u);
+              if (PA == 2) mma(make_smem_desc(sa + A_BYTES + aoff, a_lbo, 1024), b_hi, 1u);
+            }
+            if (CG == 2) {
+              tcgen05_commit_2sm(empty0 + 8 * s);                        // frees the stage in both CTAs when these MMAs retire
+              if (it == iters - 1) tcgen05_commit_2sm(tfull0 + 8 * acc);  // accumulator complete (both CTAs' epilogues)
+            } else {
+              tcgen05_commit(empty0 + 8 * s);
+              if (it == iters - 1) tcgen05_commit(tfull0 + 8 * acc);
             }
           }
-          tcgen05_commit(empty0 + 8 * s);                        // frees the smem stage when these MMAs retire
-          if (it == iters - 1) tcgen05_commit(tfull0 + 8 * acc);  // accumulator complete
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
@@ -336,11 +406,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool resid_masked = p.resid_masked != 0;
     const long long d_ld = p.d_ld, d_lo = p.d_lo;
     const bool is_f32 = p.d_dtype == VILCO_F32;
+    const int d_fmt = p.d_dtype;
     uint32_t tc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = worker; t < total_tiles; t += n_workers) {
       const int z = t / tiles_per_z, r = t - z * tiles_per_z;
-      const int m0 = (r / n_tiles) * BM, n0 = (r % n_tiles) * BN;
-      if (!tile_needed(m0, n0)) continue;
+      const int mt0 = (r / n_tiles) * BM * CG, n0 = (r % n_tiles) * BN;
+      if (!tile_needed(mt0, n0)) continue;
+      const int m0 = mt0 + static_cast<int>(rank) * BM;
       const int z1 = z % p.Z1, z2 = z / p.Z1;
       const uint32_t acc = tc & 1;
       const uint32_t tc_cur = tc++;
@@ -352,7 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long zoff = z1 * p.d_s1 + z2 * p.d_s2;
       for (int c = chalf; c < BN / 32; c += 2) {
         const int nb = n0 + c * 32;
-        if (nb >= p.N) break;  // warp-uniform
+        if (nb >= p.N || mrow0 >= p.M) break;  // warp-uniform
         uint32_t rr[32];
         __syncwarp();
         tmem_ld32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
@@ -412,7 +484,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             b8[u] = (bias && n + u < p.N) ? __ldg(bias + n + u) : 0.f;
             s8[u] = (colscale && n + u < p.N) ? __ldg(colscale + n + u) : 1.f;
           }
-          __nv_bfloat16* Db = static_cast<__nv_bfloat16*>(p.D);
+          uint16_t* Db = static_cast<uint16_t*>(p.D);
 #pragma unroll 2
           for (int r0 = 0; r0 < 32; r0 += 8) {
             const int rloc = r0 + rsub;
@@ -433,17 +505,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               if (vec) {
                 uint32_t h[4], l[4];
+                if (d_lo) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  h[u] = pack_bf16x2(v[2 * u], v[2 * u + 1]);
-                  l[u] = pack_bf16x2(v[2 * u] - bf16_lo(h[u]), v[2 * u + 1] - bf16_hi(h[u]));
+                  for (int u = 0; u < 4; ++u) split16x2(v[2 * u], v[2 * u + 1], d_fmt, h[u], l[u]);
+                  *reinterpret_cast<uint4*>(Db + o) = make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(Db + d_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+                } else {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) h[u] = pack16x2(v[2 * u], v[2 * u + 1], d_fmt);
+                  *reinterpret_cast<uint4*>(Db + o) = make_uint4(h[0], h[1], h[2], h[3]);
                 }
-                *reinterpret_cast<uint4*>(Db + o) = make_uint4(h[0], h[1], h[2], h[3]);
-                if (d_lo) *reinterpret_cast<uint4*>(Db + d_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
               } else {
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
-                  if (n + u < p.N) store_bf16_split(Db, o + u, d_lo, v[u]);
+                  if (n + u < p.N) store16_split(Db, o + u, d_lo, v[u], d_fmt);
               }
             }
           }
@@ -452,15 +527,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // this warp is done reading the accumulator stage
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster((tempty0 + 8 * acc) & PEER_BIT_MASK);   // the leader's barrier
+        else mbar_arrive(tempty0 + 8 * acc);
+      }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -472,10 +553,8 @@ struct SimtAddr {
   const __nv_bfloat16* B; long long b_ld, b_s1, b_s2, b_lo;
   int Z2;
 };
-__device__ __forceinline__ float ld_split(const __nv_bfloat16* p, long long lo) {
-  float v = __bfloat162float(p[0]);
-  if (lo) v += __bfloat162float(p[lo]);
-  return v;
+__device__ __forceinline__ float ld_split(const __nv_bfloat16* p, long long lo, int fmt) {
+  return load16_split(reinterpret_cast<const uint16_t*>(p), lo, fmt);
 }
 
 __global__ void gemm_simt_kernel(const GemmDev p, const SimtAddr q) {
@@ -494,16 +573,16 @@ __global__ void gemm_simt_kernel(const GemmDev p, const SimtAddr q) {
         const __nv_bfloat16* a = q.A + z1 * q.a_s1 + z2 * q.a_s2 + m;
         const __nv_bfloat16* b = q.B + (p.b_batched ? z1 * q.b_s1 + z2 * q.b_s2 : 0) + (p.b_major == 0 ? (long long)n * q.b_ld : n);
         const long long bs = p.b_major == 0 ? 1 : q.b_ld;
-        for (int k = 0; k < p.K; ++k) acc = fmaf(ld_split(a + (long long)k * q.a_ld, q.a_lo), ld_split(b + k * bs, q.b_lo), acc);
+        for (int k = 0; k < p.K; ++k) acc = fmaf(ld_split(a + (long long)k * q.a_ld, q.a_lo, p.a_fmt), ld_split(b + k * bs, q.b_lo, p.b_fmt), acc);
         continue;
       }
       const __nv_bfloat16* a = q.A + z1 * q.a_s1 + z2 * q.a_s2 + (long long)row * q.a_ld;
       if (p.b_major == 0) {
         const __nv_bfloat16* b = q.B + (p.b_batched ? z1 * q.b_s1 + z2 * q.b_s2 : tap * q.b_s1) + (long long)n * q.b_ld;
-        for (int k = 0; k < p.K; ++k) acc = fmaf(ld_split(a + k, q.a_lo), ld_split(b + k, q.b_lo), acc);
+        for (int k = 0; k < p.K; ++k) acc = fmaf(ld_split(a + k, q.a_lo, p.a_fmt), ld_split(b + k, q.b_lo, p.b_fmt), acc);
       } else {
         const __nv_bfloat16* b = q.B + (p.b_batched ? z1 * q.b_s1 + z2 * q.b_s2 : tap * q.b_s1) + n;
-        for (int k = 0; k < p.K; ++k) acc = fmaf(ld_split(a + k, q.a_lo), ld_split(b + (long long)k * q.b_ld, q.b_lo), acc);
+        for (int k = 0; k < p.K; ++k) acc = fmaf(ld_split(a + k, q.a_lo, p.a_fmt), ld_split(b + (long long)k * q.b_ld, q.b_lo, p.b_fmt), acc);
       }
     }
     float rm = 1.0f;
@@ -512,7 +591,7 @@ __global__ void gemm_simt_kernel(const GemmDev p, const SimtAddr q) {
     const float res = p.resid ? p.resid[doff] * (p.resid_masked ? rm : 1.0f) : 0.0f;
     const float o = epi_value(p, acc, n, rm, res);
     if (p.d_dtype == VILCO_F32) static_cast<float*>(p.D)[doff] = o;
-    else store_bf16_split(static_cast<__nv_bfloat16*>(p.D), doff, p.d_lo, o);
+    else store16_split(static_cast<uint16_t*>(p.D), doff, p.d_lo, o, p.d_dtype);
   }
 }
 
@@ -583,19 +662,33 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, bool SPLIT>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int Z, cudaStream_t st) {
-  using L = SmemLayout<BN, SPLIT>;
-  constexpr int smem = STAGES * L::STAGE_BYTES + EPI_SMEM + (2 * STAGES + 4) * 8 + 16 + 1024;
-  static_assert(smem <= 232448, "dynamic shared memory budget exceeded");
+template <int BN, int CG>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p, int Z, cudaStream_t st) {
+  const int stage_bytes = p.pa * (BM * BK * 2) + p.pb * ((BN / CG) * BK * 2);
+  int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_SMEM) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) { set_error("vilco_gemm: tile does not fit shared memory"); return VILCO_E_UNSUPPORTED; }
+  p.stages = stages;
+  const int smem = 1024 + BAR_BYTES + EPI_SMEM + stages * stage_bytes;
   static bool configured = false;
   if (!configured) {
-    VILCO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VILCO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
-  const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * Z;
-  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  gemm_tc_kernel<BN, STAGES, SPLIT><<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
+  const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM * CG - 1) / (BM * CG)) * Z;
+  const int workers = num_sms() / CG;
+  const int grid = static_cast<int>(tiles < workers ? tiles : workers) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  VILCO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, tmA, tmB, p));
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -620,6 +713,7 @@ struct AttnDev {
   float scale;
   const float* kmask;  // (B, Tk) or null
   __nv_bfloat16* O; long long o_lo; long long o_ld, o_sh, o_sb;  // element strides: row, head, batch
+  int fmt;             // element format of q / k / v / P / O (activation planes)
 };
 
 template <bool SPLIT>
@@ -706,8 +800,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc_s = make_idesc(AT_BKV, 0);   // N = 128 keys, B K-major
-    const uint32_t idesc_o = make_idesc(AT_D, 1);     // N = 64, B (V) MN-major
+    const uint32_t idesc_s = make_idesc(AT_BKV, 0, 0, p.fmt, p.fmt);   // N = 128 keys, B K-major
+    const uint32_t idesc_o = make_idesc(AT_D, 1, 0, p.fmt, p.fmt);     // N = 64, B (V) MN-major
     mbar_wait(qfull, 0);
     auto issue_pv = [&](int j) {
       mbar_wait(pfull, j & 1);
@@ -839,8 +933,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 if (!((bits >> k0) & 1u)) a = 0.f;
                 if (!((bits >> (k0 + 1)) & 1u)) bq = 0.f;
               }
-              hi[u] = pack_bf16x2(a, bq);
-              lo[u] = pack_bf16x2(a - bf16_lo(hi[u]), bq - bf16_hi(hi[u]));
+              if (SPLIT) split16x2(a, bq, p.fmt, hi[u], lo[u]);
+              else hi[u] = pack16x2(a, bq, p.fmt);
             }
             const int chunk = c * 4 + ch;
             uint8_t* dst = sP + half * TILE + row * 128 + ((chunk ^ (row & 7)) << 4);
@@ -870,8 +964,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float a = __uint_as_float(r[ch * 8 + 2 * u]), bq = __uint_as_float(r[ch * 8 + 2 * u + 1]);
-            hi[u] = pack_bf16x2(a, bq);
-            lo[u] = pack_bf16x2(a - bf16_lo(hi[u]), bq - bf16_hi(hi[u]));
+            split16x2(a, bq, p.fmt, hi[u], lo[u]);
           }
           *reinterpret_cast<uint4*>(orow + ch * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           if (p.o_lo) *reinterpret_cast<uint4*>(orow + p.o_lo + ch * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -896,9 +989,12 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   VILCO_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0 && g->Z1 > 0 && g->Z2 > 0, "vilco_gemm: empty problem");
   VILCO_CHECK_ARG(g->taps == 1 || g->taps == 3, "vilco_gemm: taps must be 1 or 3");
   VILCO_CHECK_ARG(!(g->b_batched && g->taps != 1), "vilco_gemm: batched B cannot have taps");
-  VILCO_CHECK_ARG(g->d_dtype == VILCO_F32 || g->d_dtype == VILCO_BF16, "vilco_gemm: bad d_dtype");
+  VILCO_CHECK_ARG(g->d_dtype == VILCO_F32 || g->d_dtype == VILCO_BF16 || g->d_dtype == VILCO_F16, "vilco_gemm: bad d_dtype");
   VILCO_CHECK_ARG(!(g->resid_masked && !g->rowmul), "vilco_gemm: resid_masked needs rowmul");
   VILCO_CHECK_ARG(g->a_major == 0 || (g->a_major == 1 && g->taps == 1), "vilco_gemm: MN-major A needs taps == 1");
+  const int a_fmt = g->a_fmt ? g->a_fmt : VILCO_BF16, b_fmt = g->b_fmt ? g->b_fmt : VILCO_BF16;   // 0 = legacy callers: bf16
+  VILCO_CHECK_ARG((a_fmt == VILCO_BF16 || a_fmt == VILCO_F16) && (b_fmt == VILCO_BF16 || b_fmt == VILCO_F16),
+                  "vilco_gemm: operand formats must be VILCO_BF16 or VILCO_F16");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   GemmDev p{};
@@ -906,8 +1002,10 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   p.band_lo = g->band_lo; p.band_hi = g->band_hi;
   p.a_major = g->a_major;
   p.b_major = g->b_major; p.b_batched = g->b_batched;
+  p.pa = g->a_lo ? 2 : 1; p.pb = g->b_lo ? 2 : 1;
+  p.a_fmt = a_fmt; p.b_fmt = b_fmt;
   p.D = g->D; p.d_dtype = g->d_dtype; p.d_ld = g->d_ld; p.d_s1 = g->d_s1; p.d_s2 = g->d_s2;
-  p.d_lo = g->d_dtype == VILCO_BF16 ? g->d_lo : 0;
+  p.d_lo = g->d_dtype != VILCO_F32 ? g->d_lo : 0;
   p.alpha = g->alpha; p.bias = g->bias; p.rowmul = g->rowmul; p.rowmul_zs = g->rowmul_zs;
   p.act = g->act; p.colscale = g->colscale; p.resid = g->resid; p.resid_masked = g->resid_masked;
   const int esz = g->d_dtype == VILCO_F32 ? 4 : 2;
@@ -931,57 +1029,51 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
     return VILCO_OK;
   }
 
-  // ---- tcgen05 path ----
-  int BN;
+  // ---- tcgen05 path: tile shape ----
+  int BN, CG = 1;
+  const long long t128 = (long long)((g->N + 127) / 128) * ((g->M + BM - 1) / BM) * Z;   // 128 x 128 tiles
+  const int force_cg = g->impl >= 2 ? g->impl - 1 : 0;    // impl 2 / 3: force cta_group 1 / 2 (probes); 0: automatic
   if (g->b_major == 1) {
-    const long long t128 = (long long)((g->N + 127) / 128) * ((g->M + BM - 1) / BM) * Z;
     BN = (g->N <= 64 || t128 * 2 <= num_sms()) ? 64 : 128;
   } else if (g->N <= 32) BN = 32;
   else if (g->N <= 64) BN = 64;
   else {
     // small problems (text stem, deep pyramid levels): 128x64 tiles double the number of CTAs when 128x128 tiles
     // would leave most of the 148 SMs idle
-    const long long t128 = (long long)((g->N + 127) / 128) * ((g->M + BM - 1) / BM) * Z;
     BN = (t128 * 2 <= num_sms()) ? 64 : 128;
+  }
+  // CTA pairs (cta_group::2, 256 x 256 or 256 x 128 tiles) for the big K-major problems: at least ~2 waves of 256 x 256 tiles
+  if (g->a_major == 0 && g->b_major == 0 && g->band_hi <= g->band_lo && force_cg != 1 && g->N >= 128) {
+    const long long t256 = (long long)((g->N + 255) / 256) * ((g->M + 255) / 256) * Z;
+    if (g->N >= 256 && (t256 >= 2 * (num_sms() / 2) || force_cg == 2)) { BN = 256; CG = 2; }
+    else if (t128 / 2 >= 2 * (num_sms() / 2) || force_cg == 2) { BN = 128; CG = 2; }
   }
 
   CUtensorMap tmA, tmB;
   int sa[3], sb[3];
-  const bool split = g->a_lo != 0 && g->b_lo != 0;
   int rc;
   if (g->a_major == 0)
     rc = encode_map(&tmA, g->A, (uint64_t)g->K, (uint64_t)g->a_rows, g->a_ld, (uint64_t)g->Z1, g->a_s1,
-                    (uint64_t)g->Z2, g->a_s2, split ? g->a_lo : 0, BK, BM, sa);
+                    (uint64_t)g->Z2, g->a_s2, g->a_lo, BK, BM, sa);
   else   // (m inner, k rows, z1, z2), one 64-wide swizzle atom per box
     rc = encode_map(&tmA, g->A, (uint64_t)g->M, (uint64_t)g->K, g->a_ld, (uint64_t)g->Z1, g->a_s1,
-                    (uint64_t)g->Z2, g->a_s2, split ? g->a_lo : 0, 64, BK, sa);
+                    (uint64_t)g->Z2, g->a_s2, g->a_lo, 64, BK, sa);
   if (rc) return rc;
-  if (g->b_major == 0) {
-    // (k inner, n rows, z1|tap, z2)
-    const uint64_t n1 = g->b_batched ? (uint64_t)g->Z1 : (uint64_t)g->taps;
-    const uint64_t n2 = g->b_batched ? (uint64_t)g->Z2 : 1;
-    rc = encode_map(&tmB, g->B, (uint64_t)g->K, (uint64_t)g->N, g->b_ld, n1, g->b_s1, n2, g->b_s2, split ? g->b_lo : 0, BK, BN, sb);
-  } else {
-    // (n inner, k rows, z1, z2)
-    const uint64_t n1 = g->b_batched ? (uint64_t)g->Z1 : (uint64_t)g->taps;
-    const uint64_t n2 = g->b_batched ? (uint64_t)g->Z2 : 1;
-    rc = encode_map(&tmB, g->B, (uint64_t)g->N, (uint64_t)g->K, g->b_ld, n1, g->b_s1, n2, g->b_s2, split ? g->b_lo : 0, 64, BK, sb);
-  }
+  const uint64_t n1 = g->b_batched ? (uint64_t)g->Z1 : (uint64_t)g->taps;
+  const uint64_t n2 = g->b_batched ? (uint64_t)g->Z2 : 1;
+  if (g->b_major == 0)   // (k inner, n rows, z1|tap, z2)
+    rc = encode_map(&tmB, g->B, (uint64_t)g->K, (uint64_t)g->N, g->b_ld, n1, g->b_s1, n2, g->b_s2, g->b_lo, BK, BN / CG, sb);
+  else                   // (n inner, k rows, z1, z2)
+    rc = encode_map(&tmB, g->B, (uint64_t)g->N, (uint64_t)g->K, g->b_ld, n1, g->b_s1, n2, g->b_s2, g->b_lo, 64, BK, sb);
   if (rc) return rc;
   p.a_slot_row = sa[0]; p.a_slot_z1 = sa[1]; p.a_slot_z2 = sa[2];
   p.b_slot_row = sb[0]; p.b_slot_z1 = sb[1]; p.b_slot_z2 = sb[2];
 
-  if (split) {
-    switch (BN) {
-      case 32: return launch_tc<32, 4, true>(tmA, tmB, p, Z, st);
-      case 64: return launch_tc<64, 4, true>(tmA, tmB, p, Z, st);
-      default: return launch_tc<128, 3, true>(tmA, tmB, p, Z, st);
-    }
-  }
+  if (CG == 2) return BN == 256 ? launch_tc<256, 2>(tmA, tmB, p, Z, st) : launch_tc<128, 2>(tmA, tmB, p, Z, st);
   switch (BN) {
-    case 32: return launch_tc<32, 6, false>(tmA, tmB, p, Z, st);
-    case 64: return launch_tc<64, 6, false>(tmA, tmB, p, Z, st);
-    default: return launch_tc<128, 5, false>(tmA, tmB, p, Z, st);
+    case 32: return launch_tc<32, 1>(tmA, tmB, p, Z, st);
+    case 64: return launch_tc<64, 1>(tmA, tmB, p, Z, st);
+    default: return launch_tc<128, 1>(tmA, tmB, p, Z, st);
   }
 }
 
@@ -1011,6 +1103,7 @@ extern "C" int vilco_attention(const void* q, int64_t q_lo, const void* k, const
   p.v_slot_row = sv[0]; p.v_slot_z1 = sv[1]; p.v_slot_z2 = sv[2];
   p.Tq = Tq; p.Tk = Tk; p.H = H; p.scale = scale; p.kmask = kmask;
   p.O = static_cast<__nv_bfloat16*>(out); p.o_lo = out_lo; p.o_ld = C; p.o_sh = AT_D; p.o_sb = (long long)Tq * C;
+  p.fmt = act_fmt();
   const int PL = split ? 2 : 1;
   const int smem = PL * 16384 * (1 + 2 + 1 + 2) + AT_MAX_TK / 8 + 2 * 128 * 2 * 4 + 16 * 8 + 16 + 1024;
   dim3 grid((Tq + AT_BQ - 1) / AT_BQ, H, B);

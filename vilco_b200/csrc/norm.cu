@@ -8,7 +8,7 @@ namespace vilco {
 static constexpr int MAXCH = 8;  // float4 chunks per lane: C <= 8*128 = 1024
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {   // bf16 INPUT rows (x_dtype = VILCO_BF16), not operand planes
   uint2 u = *reinterpret_cast<const uint2*>(p);
   return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
 }
@@ -16,12 +16,17 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
-// bf16 store with optional lo plane (split precision: x ~= hi + lo)
-__device__ __forceinline__ void st4s(__nv_bfloat16* p, long long lo, float4 v) {
-  const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
-  *reinterpret_cast<uint2*>(p) = make_uint2(h0, h1);
-  if (lo) *reinterpret_cast<uint2*>(p + lo) = make_uint2(pack_bf16x2(v.x - bf16_lo(h0), v.y - bf16_hi(h0)),
-                                                          pack_bf16x2(v.z - bf16_lo(h1), v.w - bf16_hi(h1)));
+// operand-plane store (format fmt) with optional lo plane (split precision: x ~= hi + lo)
+__device__ __forceinline__ void st4s(__nv_bfloat16* p, long long lo, float4 v, int fmt) {
+  if (lo) {
+    uint32_t h0, h1, l0, l1;
+    split16x2(v.x, v.y, fmt, h0, l0);
+    split16x2(v.z, v.w, fmt, h1, l1);
+    *reinterpret_cast<uint2*>(p) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(p + lo) = make_uint2(l0, l1);
+  } else {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack16x2(v.x, v.y, fmt), pack16x2(v.z, v.w, fmt));
+  }
 }
 
 // two-pass statistics exactly like the reference (mean, then mean of squared residuals)
@@ -55,6 +60,7 @@ struct LnParams {
   float* y32; __nv_bfloat16* y16; long long y16_lo;
   long long y_ld, y_bs;               // output row stride / batch stride (elements)
   int rows, rows_per_batch, C;
+  int fmt;                            // element format of y16
 };
 
 template <typename TIn>
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
       }
       if (zero) o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.y32) st4(p.y32 + yoff + c, o);
-      if (p.y16) st4s(p.y16 + yoff + c, p.y16_lo, o);
+      if (p.y16) st4s(p.y16 + yoff + c, p.y16_lo, o, p.fmt);
     }
 }
 
@@ -114,6 +120,7 @@ struct DwParams {
   __nv_bfloat16* out[3];              // (B, T/s, C)
   long long out_lo;
   int B, T, C, stride; float eps;
+  int fmt;
 };
 
 template <typename TIn>
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const DwParams p) {
       const int c = (i * 32 + lane) * 4;
       const float4 w = ld4(lw + c), b = ld4(lb + c);
       st4s(o + c, p.out_lo, make_float4((v[i].x - mean) * rstd * w.x + b.x, (v[i].y - mean) * rstd * w.y + b.y,
-                                        (v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w));
+                                        (v[i].z - mean) * rstd * w.z + b.z, (v[i].w - mean) * rstd * w.w + b.w), p.fmt);
     }
 }
 
@@ -196,7 +203,7 @@ __global__ void maxpool3s2_kernel(const float* __restrict__ x, float* __restrict
 
 // out = a*x + b*y (fp32), optional bf16 copy
 __global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a, float b,
-                             float* __restrict__ o32, __nv_bfloat16* __restrict__ o16, long long o16_lo, long long n4) {
+                             float* __restrict__ o32, __nv_bfloat16* __restrict__ o16, long long o16_lo, long long n4, int fmt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 u = ld4(x + 4 * i);
     float4 o = make_float4(a * u.x, a * u.y, a * u.z, a * u.w);
@@ -205,7 +212,7 @@ __global__ void axpby_kernel(const float* __restrict__ x, const float* __restric
       o.x = fmaf(b, w.x, o.x); o.y = fmaf(b, w.y, o.y); o.z = fmaf(b, w.z, o.z); o.w = fmaf(b, w.w, o.w);
     }
     if (o32) st4(o32 + 4 * i, o);
-    if (o16) st4s(o16 + 4 * i, o16_lo, o);
+    if (o16) st4s(o16 + 4 * i, o16_lo, o, fmt);
   }
 }
 
@@ -226,7 +233,7 @@ __global__ void scale_add_kernel(const float* __restrict__ x, const float* __res
 
 // (B, C, T) fp32 channel-major (the reference layout) -> (B, T, C) bf16 token-major, zero padded to T_out rows
 __global__ void pack_feats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long y_lo, int C, int T,
-                                  int T_out) {
+                                  int T_out, int fmt) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -240,10 +247,7 @@ __global__ void pack_feats_kernel(const float* __restrict__ x, __nv_bfloat16* __
     const int t = t0 + j, c = c0 + tx;
     if (t < T_out && c < C) {
       const long long o = ((long long)b * T_out + t) * C + c;
-      const float v = tile[tx][j];
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      y[o] = h;
-      if (y_lo) y[y_lo + o] = __float2bfloat16_rn(v - __bfloat162float(h));
+      store16_split(reinterpret_cast<uint16_t*>(y), o, y_lo, tile[tx][j], fmt);
     }
   }
 }
@@ -255,7 +259,7 @@ __global__ void pack_feats_kernel(const float* __restrict__ x, __nv_bfloat16* __
 // planes.  One thread per 4 channels of an output row: both source rows are read with 16-byte loads that are contiguous
 // across the warp, every input byte is needed by at most ceil(T_out/T_in)+1 neighbouring output rows (L2 hits).
 __global__ void resize_feats_kernel(const float* __restrict__ x, const long long* __restrict__ row_start, float* __restrict__ o32,
-                                    __nv_bfloat16* __restrict__ o16, long long o16_lo, int C4, int T_out) {
+                                    __nv_bfloat16* __restrict__ o16, long long o16_lo, int C4, int T_out, int fmt) {
   const int b = blockIdx.y;
   const long long r0 = row_start[b];
   const int T_in = static_cast<int>(row_start[b + 1] - r0);
@@ -281,7 +285,7 @@ __global__ void resize_feats_kernel(const float* __restrict__ x, const long long
                                  __fadd_rn(__fmul_rn(l0, a.z), __fmul_rn(l1, d.z)), __fadd_rn(__fmul_rn(l0, a.w), __fmul_rn(l1, d.w)));
     const long long o = (static_cast<long long>(b) * T_out + t) * C + c;
     if (o32) st4(o32 + o, v);
-    if (o16) st4s(o16 + o, o16_lo, v);
+    if (o16) st4s(o16 + o, o16_lo, v, fmt);
   }
 }
 
@@ -325,6 +329,7 @@ extern "C" int vilco_layernorm(const void* x, int x_dtype, const float* add, con
   p.pe = pe; p.pe_T = pe_T; p.rowmul = rowmul; p.zero_rows = zero_rows;
   p.y32 = y32; p.y16 = static_cast<__nv_bfloat16*>(y16); p.y16_lo = y16_lo; p.y_ld = y_ld; p.y_bs = y_bs;
   p.rows = rows; p.rows_per_batch = rows_per_batch; p.C = C;
+  p.fmt = act_fmt();
   const int grid = (rows + 7) / 8;
   if (p.x_bf16) layernorm_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   else layernorm_kernel<float><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
@@ -346,6 +351,7 @@ extern "C" int vilco_dwconv_ln(const void* x, int x_dtype, const float* mask, co
   }
   p.out_lo = out_lo;
   p.B = B; p.T = T; p.C = C; p.stride = stride; p.eps = eps;
+  p.fmt = act_fmt();
   const int rows = B * (T / stride);
   dim3 grid((rows + 7) / 8, n_out);
   if (p.x_bf16) dwconv_ln_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
@@ -366,7 +372,7 @@ extern "C" int vilco_axpby(const float* x, const float* y, float a, float b, flo
                            int64_t n, void* stream) {
   VILCO_CHECK_ARG(x && (o32 || o16) && n % 4 == 0, "vilco_axpby: bad arguments");
   axpby_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, y, a, b, o32, static_cast<__nv_bfloat16*>(o16), o16_lo, n / 4);
+      x, y, a, b, o32, static_cast<__nv_bfloat16*>(o16), o16_lo, n / 4, act_fmt());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -374,7 +380,8 @@ extern "C" int vilco_axpby(const float* x, const float* y, float a, float b, flo
 extern "C" int vilco_pack_feats(const float* x, void* y, int64_t y_lo, int B, int C, int T, int T_out, void* stream) {
   VILCO_CHECK_ARG(x && y && B > 0 && C > 0 && T > 0 && T_out >= T, "vilco_pack_feats: bad arguments");
   dim3 grid((T_out + 31) / 32, (C + 31) / 32, B);
-  pack_feats_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y), y_lo, C, T, T_out);
+  pack_feats_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y), y_lo, C, T, T_out,
+                                                                            act_fmt());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -387,7 +394,8 @@ extern "C" int vilco_resize_feats(const float* x, const int64_t* row_start, int 
   const long long n = static_cast<long long>(T_out) * (C / 4);
   dim3 grid(grid_for(n, 256, 148 * 8 / (B < 8 ? B : 8)), B);
   resize_feats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, reinterpret_cast<const long long*>(row_start), out32, static_cast<__nv_bfloat16*>(out16), out16_lo, C / 4, T_out);
+      x, reinterpret_cast<const long long*>(row_start), out32, static_cast<__nv_bfloat16*>(out16), out16_lo, C / 4, T_out,
+      act_fmt());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

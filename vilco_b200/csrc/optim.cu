@@ -60,7 +60,7 @@ __device__ __forceinline__ float adamw_one(float& p, float g, float& m, float& v
 __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                     float4* __restrict__ v, long long n4, float lr, float b1, float b2, float eps,
                                                     float wd, float bc1, float bc2_sqrt, const float* __restrict__ gscale,
-                                                    __nv_bfloat16* __restrict__ planes, long long planes_lo) {
+                                                    __nv_bfloat16* __restrict__ planes, long long planes_lo, int fmt) {
   const float gs = gscale ? *gscale : 1.f;
   const float step = lr / bc1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -72,17 +72,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, cons
     adamw_one(pi.w, gi.w * gs, mi.w, vi.w, lr, b1, b2, eps, wd, step, bc2_sqrt);
     p[i] = pi; m[i] = mi; v[i] = vi;
     if (planes) {
-      const __nv_bfloat16 h0 = __float2bfloat16(pi.x), h1 = __float2bfloat16(pi.y), h2 = __float2bfloat16(pi.z),
-                          h3 = __float2bfloat16(pi.w);
-      uint2 hi;
-      hi.x = pack_bf16x2(h0, h1); hi.y = pack_bf16x2(h2, h3);
-      *reinterpret_cast<uint2*>(planes + 4 * i) = hi;
-      if (planes_lo) {
-        uint2 lo;
-        lo.x = pack_bf16x2(__float2bfloat16(pi.x - __bfloat162float(h0)), __float2bfloat16(pi.y - __bfloat162float(h1)));
-        lo.y = pack_bf16x2(__float2bfloat16(pi.z - __bfloat162float(h2)), __float2bfloat16(pi.w - __bfloat162float(h3)));
-        *reinterpret_cast<uint2*>(planes + planes_lo + 4 * i) = lo;
-      }
+      uint32_t h0, h1, l0, l1;
+      split16x2(pi.x, pi.y, fmt, h0, l0);
+      split16x2(pi.z, pi.w, fmt, h1, l1);
+      *reinterpret_cast<uint2*>(planes + 4 * i) = make_uint2(h0, h1);
+      if (planes_lo) *reinterpret_cast<uint2*>(planes + planes_lo + 4 * i) = make_uint2(l0, l1);
     }
   }
 }
@@ -123,7 +117,8 @@ extern "C" int vilco_adamw(float* p, const float* g, float* m, float* v, int64_t
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;   // seven 16-byte streams per thread: keep many warps in flight
   adamw_kernel<<<static_cast<unsigned>(blocks < 1 ? 1 : blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, static_cast<__nv_bfloat16*>(planes), planes_lo);
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n / 4, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, static_cast<__nv_bfloat16*>(planes), planes_lo,
+      act_fmt());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

@@ -52,7 +52,7 @@ def _concat_clips(clips):
 def _launch(clips, max_seq_len, want32, want16):
     x, row_start, B, C = _concat_clips(clips)
     o32 = torch.empty(B, max_seq_len, C, device=x.device, dtype=torch.float32) if want32 else None
-    o16 = ops.empty16(B, max_seq_len, C, device=x.device) if want16 else None
+    o16 = ops.empty16(B, max_seq_len, C, device=x.device, planes=ops.PLANES_HI) if want16 else None   # feeds the input projection
     L.check(L.lib().vilco_resize_feats(ops._p(x), ops._p(row_start), B, C, int(max_seq_len), ops._p(o32), ops._p(o16),
                                        ops._i64(ops.lo(o16) if want16 else 0), L.stream_ptr()), "vilco_resize_feats")
     return o32, o16

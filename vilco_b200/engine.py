@@ -1,5 +1,10 @@
-"""Forward engine of the Moment-Query model on hand-written sm_100a kernels (token-major, bf16 operands,
+"""Forward engine of the Moment-Query model on hand-written sm_100a kernels (token-major, 16-bit operand planes,
 fp32 accumulation / residual stream / statistics).
+
+Operand-format policy (ops.set_precision): in the default "mixed" mode every GEMM reads single fp16
+planes except the contractions upstream of the channel-attention softmax that the parity bar is sensitive to — the input
+projection, the embedding convolutions, the channel-attention qkv projection and core — whose operands carry two planes
+(`ops.PLANES_HI`; `sensitive_key` for the weights).
 
 `pack_weights` turns a reference-named state_dict into the operand formats the kernels want;
 the `*_fwd` functions are the B200 counterparts of the reference modules (file:line cited per function).  All
@@ -34,15 +39,24 @@ def _pack_kind(k, v):
     return "vec"
 
 
-def _pack_one(kind, v):
+def sensitive_key(k):
+    """weights of the contractions that keep split (two-plane) operands in the mixed mode"""
+    return k.startswith(("backbone.proj.", "backbone.embd.")) or k.endswith(".channel_attn.attn.qkv.weight")
+
+
+def _planes_for(k):
+    return ops.PLANES_HI if sensitive_key(k) else ops.PLANES
+
+
+def _pack_one(kind, v, planes=None):
     if kind == "xl_t":
-        return ops.split16(v.reshape(v.shape[0], -1).t().contiguous())
+        return ops.split16(v.reshape(v.shape[0], -1).t().contiguous(), planes)
     if kind == "gemm":
-        return ops.split16(v.reshape(v.shape[0], -1).contiguous())
+        return ops.split16(v.reshape(v.shape[0], -1).contiguous(), planes)
     if kind == "dw":                                   # depthwise (C,1,3) -> (3,C) fp32
         return v[:, 0, :].t().contiguous()
     if kind == "conv3":                                # dense k=3 conv -> tap-major (3, Cout, Cin)
-        return ops.split16(v.permute(2, 0, 1).contiguous())
+        return ops.split16(v.permute(2, 0, 1).contiguous(), planes)
     return v.reshape(-1).contiguous() if v.dim() != 2 else v.contiguous()
 
 
@@ -73,10 +87,10 @@ def pack_weights(sd, device, flat=None, params=None):
                 W[k] = prm.data.reshape(-1) if prm.dim() != 2 else prm.data
                 continue
             if kind == "gemm":
-                W[k] = flat.plane_view(prm, (prm.shape[0], prm.numel() // prm.shape[0]))
+                W[k] = flat.plane_view(prm, (prm.shape[0], prm.numel() // prm.shape[0]))[:_planes_for(k)]
                 continue
             repack.append((k, kind, prm))
-        W[k] = _pack_one(kind, v)
+        W[k] = _pack_one(kind, v, _planes_for(k))
     W["_repack"] = repack
     return W
 
@@ -84,7 +98,7 @@ def pack_weights(sd, device, flat=None, params=None):
 def refresh_packed(W):
     """Re-derive the permuted copies after an in-place parameter update and drop everything cached from the old weights."""
     for k, kind, prm in W.get("_repack", ()):
-        W[k] = _pack_one(kind, prm.data)
+        W[k] = _pack_one(kind, prm.data, _planes_for(k))
     W["_cache"] = {}
 
 
@@ -150,7 +164,7 @@ def cross_attn_fwd(W, pre, x16, y16, ymask, H):
 
 def channel_block_fwd(W, pre, ln1_32, ln1_16, H, tlen=None):
     """ChannelBlock.forward — blocks.py:423-466 on x = ln1(x) (no masking, norm1 unused).  Returns fp32 (B,T,C)."""
-    qkv = ops.linear(ln1_16, W[pre + "attn.qkv.weight"], bf16)
+    qkv = ops.linear(ln1_16, W[pre + "attn.qkv.weight"], bf16, planes=ops.PLANES_HI)
     y = ops.channel_attention(qkv, H, tlen)
     x1 = ops.linear(y, W[pre + "attn.proj.weight"], f32, bias=W[pre + "attn.proj.bias"], resid=ln1_32)
     _, n2 = ops.layernorm(x1, W[pre + "norm2.weight"], W[pre + "norm2.bias"], 1e-5)
@@ -174,7 +188,9 @@ def transformer_block_fwd(W, pre, x32, mask, H, stride, cross=None, t_c_alpha=0.
     """TransformerBlock.forward — blocks.py:561-593 (eval semantics).  x32 (B,T,C) fp32 residual stream.
     cross = (text32 (B,L,C), text_mask (B,L)) or None.  Returns (out32, out_mask[, out16])."""
     B, T, C = x32.shape
-    ln1_32, ln1_16 = ops.layernorm(x32, W[pre + "ln1.weight"], W[pre + "ln1.bias"], out32=True, out16=(stride == 1))
+    # ln1_16 only feeds the channel-attention qkv projection (stride-1 blocks): split operand
+    ln1_32, ln1_16 = ops.layernorm(x32, W[pre + "ln1.weight"], W[pre + "ln1.bias"], out32=True, out16=(stride == 1),
+                                   planes=ops.PLANES_HI)
     o, omask = mhca_fwd(W, pre + "attn.", ln1_32, mask, H, stride, window, tlen)
     om = omask.reshape(-1)
     skip = x32 if stride == 1 else ops.maxpool3s2(x32)
@@ -252,7 +268,8 @@ def backbone_fwd(W, cfg, x16, mask, text16=None, tmask=None, pe=None, pets_prefi
     _, B, T, _ = x16.shape
     C, H = cfg.embd_dim, cfg.n_head
     m = mask.reshape(-1)
-    x = ops.linear(x16, W[pre + "proj.0.conv.weight"], bf16, bias=W[pre + "proj.0.conv.bias"], rowmul=m)
+    # input projection and embedding convolutions: split operands (x16 comes in ops.PLANES_HI planes)
+    x = ops.linear(x16, W[pre + "proj.0.conv.weight"], bf16, bias=W[pre + "proj.0.conv.bias"], rowmul=m, planes=ops.PLANES_HI)
     x32 = None
     n_embd = cfg.arch[0]
     for i in range(n_embd):
@@ -260,7 +277,7 @@ def backbone_fwd(W, cfg, x16, mask, text16=None, tmask=None, pe=None, pets_prefi
         last = i == n_embd - 1
         x32, x = ops.layernorm(c, W[pre + f"embd_norm.{i}.weight"], W[pre + f"embd_norm.{i}.bias"], relu=True,
                                pe=pe if last else None, rowmul=m if last else None, out32=last, out16=not last,
-                               rows_per_batch=T)
+                               rows_per_batch=T, planes=ops.PLANES_HI)
     cross = None
     if cfg.use_cross_modal and text16 is not None:
         tm = tmask.reshape(-1)
@@ -356,11 +373,14 @@ def neck_heads_fwd(W, cfg, feats, masks, pyr=None):
     for head, final_w, final_b in (("cls_head.", "cls_head.cls_head.conv", None), ("reg_head.", "reg_head.offset_head.conv", None)):
         x = fpn
         for i in range(2):
-            c = ops.conv3(x, W[head + f"head.{i}.conv.weight"], f32, rowmul=pmask)
+            # flat=True: the pyramid rows of all clips as ONE sequence — every clip ends in an all-zero, masked gap row, so
+            # the k=3 taps never mix clips and no tile is cut at a clip boundary
+            c = ops.conv3(x, W[head + f"head.{i}.conv.weight"], f32, rowmul=pmask, flat=True)
             _, x = ops.layernorm(c, W[head + f"norm.{i}.weight"], W[head + f"norm.{i}.bias"], relu=True,
                                  zero_rows=zero_rows)
         if head == "cls_head.":
-            outs.append(ops.conv3(x, W[final_w + ".weight"], f32, bias=W[final_w + ".bias"], rowmul=pmask))
+            outs.append(ops.conv3(x, W[final_w + ".weight"], f32, bias=W[final_w + ".bias"], rowmul=pmask, flat=True))
         else:  # relu(scale_l * (conv + b) * mask)
-            outs.append(ops.conv3(x, W[final_w + ".weight"], f32, bias=W[final_w + ".bias"], rowmul=rowscale, act=ACT_RELU))
+            outs.append(ops.conv3(x, W[final_w + ".weight"], f32, bias=W[final_w + ".bias"], rowmul=rowscale, act=ACT_RELU,
+                                  flat=True))
     return outs[0], outs[1], pmask, pyr

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvilco_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 
 
 class VilcoError(RuntimeError):
@@ -35,6 +35,7 @@ class VilcoGemm(C.Structure):
         ("resid", C.c_void_p), ("resid_masked", C.c_int32),
         ("impl", C.c_int32),
         ("band_lo", C.c_int32), ("band_hi", C.c_int32), ("a_major", C.c_int32),
+        ("a_fmt", C.c_int32), ("b_fmt", C.c_int32),
     ]
 
 
@@ -54,6 +55,8 @@ def lib():
         _lib.vilco_launch_count.restype = C.c_uint64
         _lib.vilco_version.restype = C.c_int
         _lib.vilco_nms_workspace_bytes.restype = C.c_size_t
+        if _lib.vilco_version() < 2:
+            raise VilcoError(f"{LIB_PATH} is stale (ABI version {_lib.vilco_version()} < 2): rebuild it")
     return _lib
 
 
@@ -88,6 +91,8 @@ def default_gemm_impl():
     return 1 if os.environ.get("VILCO_GEMM", "tc") == "simt" else 0
 
 
+_FMT = {torch.bfloat16: BF16, torch.float16: F16}
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 _gemm_cache = {}     # descriptor without the pointers -> prepared VilcoGemm (a training step issues ~570 GEMMs from ~60 shapes)
 _gemm_fn = None
 
@@ -97,20 +102,20 @@ def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), 
          colscale=None, resid=None, resid_masked=False, impl=None, a_lo=0, b_lo=0, d_lo=0, band=(0, 0), a_major=0):
     """Raw descriptor-level call of ``vilco_gemm`` (see include/vilco_b200.h for the contract)."""
     global _gemm_fn
-    d32 = D.dtype == torch.float32
     key = (M, N, K, a_rows, a_ld, b_ld, d_ld, a_s, b_s, d_s, Z, taps, b_major, b_batched, alpha, rowmul_zs, act, resid_masked,
-           impl, a_lo, b_lo, d_lo, band, a_major, d32)
+           impl, a_lo, b_lo, d_lo, band, a_major, A.dtype, B.dtype, D.dtype)
     g = _gemm_cache.get(key)
     if g is None:
-        assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.is_cuda and B.is_cuda
-        assert D.dtype in (torch.float32, torch.bfloat16)
+        assert A.dtype in _FMT and B.dtype in _FMT and A.is_cuda and B.is_cuda, "operands must be fp16 / bf16 planes"
+        assert D.dtype in _DT
         g = VilcoGemm()
         g.a_ld, g.a_s1, g.a_s2, g.a_rows = a_ld, a_s[0], a_s[1], a_rows
         g.a_lo, g.b_lo, g.d_lo = a_lo, b_lo, d_lo
         g.b_ld, g.b_s1, g.b_s2 = b_ld, b_s[0], b_s[1]
         g.b_major, g.b_batched = b_major, int(b_batched)
         g.M, g.N, g.K, g.taps, g.Z1, g.Z2 = M, N, K, taps, Z[0], Z[1]
-        g.d_dtype, g.d_ld, g.d_s1, g.d_s2 = (F32 if d32 else BF16), d_ld, d_s[0], d_s[1]
+        g.d_dtype, g.d_ld, g.d_s1, g.d_s2 = _DT[D.dtype], d_ld, d_s[0], d_s[1]
+        g.a_fmt, g.b_fmt = _FMT[A.dtype], _FMT[B.dtype]
         g.alpha = alpha
         g.rowmul_zs = rowmul_zs
         g.act = act

@@ -487,7 +487,7 @@ class PtTransformer(nn.Module):
         """Everything that runs on the device between the padded input batch and the head outputs."""
         W = self.packed_weights()
         cfg = self.engine_cfg()
-        x16 = ops.pack_feats(batched)
+        x16 = ops.pack_feats(batched, planes=ops.PLANES_HI)      # the input projection reads split operands
         t16 = ops.pack_feats(text) if text is not None else None
         # evaluation: the reference runs one clip at a time, so its text is never padded; a batched evaluation must
         # therefore treat every text as un-padded (text_lens).  Training reproduces the reference's padded batch.
@@ -639,7 +639,7 @@ class PtTransformer(nn.Module):
             tp = TE.Tape(W, sinks=sinks)
         tp.after_node = getattr(self, "_after_backward_node", None)     # set by trainer.Trainer (bucketed all-reduce)
         with torch.no_grad():
-            x16 = ops.pack_feats(batched)
+            x16 = ops.pack_feats(batched, planes=ops.PLANES_HI)
             t16 = ops.pack_feats(text.detach()) if text is not None else None
             feats, masks, tin = TE.backbone(tp, cfg, x16, mask.contiguous(), t16, tmask, self._pe)
             if tin is not None and not text.requires_grad:
@@ -1066,7 +1066,7 @@ class PtTransformer(nn.Module):
             text, tmask, tlens = self.query_preprocessing(video_list)
             t16 = ops.pack_feats(text.contiguous())
         W, cfg = self.packed_weights(), self.engine_cfg()
-        trunk = E.backbone_fwd(W, cfg, ops.pack_feats(batched), mask.contiguous(), t16, tmask, self._pe, text_lens=tlens,
+        trunk = E.backbone_fwd(W, cfg, ops.pack_feats(batched, planes=ops.PLANES_HI), mask.contiguous(), t16, tmask, self._pe, text_lens=tlens,
                                trunk_only=True)
         feats, _ = E.branch_fwd(W, cfg, trunk, "pets.")
         out = []

@@ -2,10 +2,20 @@
 
 Every function here launches hand-written sm_100a kernels through ``libvilco_b200.so``; torch only owns the memory.
 
-Operand convention: every bf16 *operand* tensor carries a leading "plane" dimension of size ``PLANES``:
-  PLANES == 1  ("bf16")   : plain bf16 operands, one MMA per k-step (fast; ~3e-3 relative error per GEMM chain)
-  PLANES == 2  ("bf16x3") : x ~= hi + lo with lo = bf16(x - hi); GEMMs accumulate hi*hi + hi*lo + lo*hi in fp32
-                            (~1e-5 relative error) — the mode that meets the 1e-3 parity bar.
+Operand convention: every 16-bit *operand* tensor carries a leading "plane" dimension of size 1 or 2 (x ~= hi + lo, lo =
+round16(x - hi)); a GEMM issues hi*hi, + hi*lo when B has two planes, + lo*hi when A has two (fp32 accumulation).
+Precision modes (`set_precision`, env VILCO_PRECISION):
+
+  "mixed"   (default) fp16 planes.  One plane everywhere except the contractions the parity bar is sensitive to — the input
+            projection, the embedding convolutions and the channel-attention qkv / core, whose rounding noise the d x d
+            channel softmax amplifies (tools/precision_sweep.py) — which run on split operands.
+            Measured / emulated error of logits and offsets at the full MQ config: ~4e-4 (bar: 1e-3).
+  "fp16x3"  fp16 planes, every operand split: 3 MMAs per k-step, ~1e-6 relative error (exact mode)
+  "bf16x3"  bf16 planes, every operand split (round 1's parity mode, ~1e-5)
+  "fp16" / "bf16"  one plane everywhere (1.3e-3 / 1e-2 at the full config: above the bar, kept for comparison)
+
+Gradient planes (the 16-bit operands the backward kernels emit) are always bf16 — gradient magnitudes do not fit the fp16
+range — in two planes unless VILCO_BWD_PRECISION=bf16.
 """
 import ctypes as C
 import os
@@ -15,22 +25,34 @@ import torch
 from . import lib as L
 from .lib import ACT_GELU, ACT_NONE, ACT_RELU  # noqa: F401
 
-bf16 = torch.bfloat16
+bf16 = torch.bfloat16        # also the `out_dtype` marker meaning "operand planes in the activation format"
+f16 = torch.float16
 f32 = torch.float32
 
-PLANES = 1 if os.environ.get("VILCO_PRECISION", "bf16x3") == "bf16" else 2
+_MODES = {  # name -> (activation plane dtype, default planes, planes of the sensitive contractions)
+    "mixed": (f16, 1, 2), "fp16x3": (f16, 2, 2), "fp16": (f16, 1, 1), "bf16x3": (bf16, 2, 2), "bf16": (bf16, 1, 1),
+}
+_mode = None
+ACT_DTYPE, PLANES, PLANES_HI = bf16, 2, 2
 FUSED_ATTN = os.environ.get("VILCO_FUSED_ATTN", "1") == "1"  # 0: materialised QK^T -> softmax -> PV kernels
 
 
 def set_precision(name):
-    """'bf16x3' (default, parity mode) or 'bf16' (fast mode).  Weights must be re-packed after a change."""
-    global PLANES
-    assert name in ("bf16", "bf16x3")
-    PLANES = 1 if name == "bf16" else 2
+    """Select the operand-format policy (see the module docstring).  Weights must be re-packed after a change (the model
+    does so: its packed-weight cache is keyed on `precision()`)."""
+    global _mode, ACT_DTYPE, PLANES, PLANES_HI
+    assert name in _MODES, name
+    _mode = name
+    ACT_DTYPE, PLANES, PLANES_HI = _MODES[name]
+    if os.path.exists(L.LIB_PATH):   # the library holds the plane format the non-GEMM kernels read / write
+        L.check(L.lib().vilco_set_plane_format(L.F16 if ACT_DTYPE == f16 else L.BF16), "vilco_set_plane_format")
 
 
 def precision():
-    return "bf16" if PLANES == 1 else "bf16x3"
+    return _mode
+
+
+set_precision(os.environ.get("VILCO_PRECISION", "mixed"))
 
 
 def _p(t):
@@ -41,10 +63,10 @@ def _i64(v):
     return C.c_int64(int(v))
 
 
-# Optional fast training mode: the backward GEMMs read only the hi plane of every operand (one tcgen05.mma per k-step instead of
-# three).  Gradients then carry plain-bf16 operand rounding (~3e-3 relative, what bf16 autocast training has); the forward
-# pass, the losses and therefore every parity statement about outputs are unaffected.  Default: full split precision.
-BWD_PRECISION = os.environ.get("VILCO_BWD_PRECISION", "bf16x3")
+# Optional fast training mode: the backward GEMMs read only the hi plane of every operand.  Gradients then carry plain-bf16
+# operand rounding (~3e-3 relative, what bf16 autocast training has); the forward pass, the losses and therefore every parity
+# statement about outputs are unaffected.  Default: gradient planes split (hi + lo).
+BWD_PRECISION = os.environ.get("VILCO_BWD_PRECISION", "split")
 _single = False
 
 
@@ -65,29 +87,41 @@ def lo(t):
     return t.stride(0) if (t.shape[0] == 2 and not _single) else 0
 
 
-def empty16(*shape, device="cuda"):
-    return torch.empty(PLANES, *shape, device=device, dtype=bf16)
+def grad_planes():
+    return 1 if BWD_PRECISION == "bf16" else 2
 
 
-def zeros16(*shape, device="cuda"):
-    return torch.zeros(PLANES, *shape, device=device, dtype=bf16)
+def empty16(*shape, device="cuda", planes=None, grad=False):
+    """uninitialised operand tensor (planes, *shape): activation format, or bf16 when it will hold a gradient"""
+    if grad:
+        return torch.empty(grad_planes() if planes is None else planes, *shape, device=device, dtype=bf16)
+    return torch.empty(PLANES if planes is None else planes, *shape, device=device, dtype=ACT_DTYPE)
 
 
-def split16(x):
-    """fp32 tensor -> (PLANES, ...) bf16 operand (used for weights / constants at pack time)."""
-    hi = x.to(bf16)
-    if PLANES == 1:
+def zeros16(*shape, device="cuda", planes=None, grad=False):
+    if grad:
+        return torch.zeros(grad_planes() if planes is None else planes, *shape, device=device, dtype=bf16)
+    return torch.zeros(PLANES if planes is None else planes, *shape, device=device, dtype=ACT_DTYPE)
+
+
+def split16(x, planes=None, dtype=None):
+    """fp32 tensor -> (planes, ...) operand (used for weights / constants at pack time)."""
+    dtype = ACT_DTYPE if dtype is None else dtype
+    planes = PLANES if planes is None else planes
+    xc = x.clamp(-65504.0, 65504.0) if dtype == f16 else x
+    hi = xc.to(dtype)
+    if planes == 1:
         return hi.unsqueeze(0).contiguous()
-    return torch.stack([hi, (x - hi.float()).to(bf16)]).contiguous()
+    return torch.stack([hi, (xc - hi.float()).to(dtype)]).contiguous()
 
 
 def merge16(t):
-    """(PLANES, ...) bf16 operand -> fp32 value (tests / debugging)."""
+    """(planes, ...) operand -> fp32 value (tests / debugging)."""
     return t.float().sum(0)
 
 
 def linear(x, w, out_dtype=bf16, bias=None, rowmul=None, act=ACT_NONE, colscale=None, resid=None, resid_masked=False,
-           alpha=1.0, out=None):
+           alpha=1.0, out=None, planes=None):
     """y[r, n] = epi(sum_k x[r, k] w[n, k]).  x (NP, ..., K) bf16 operand, w (NP, N, K).  rowmul (rows,) fp32,
     resid (..., N) fp32.  Returns an operand tensor (NP, ..., N) for bf16 output, a plain fp32 tensor otherwise."""
     K = x.shape[-1]
@@ -95,24 +129,30 @@ def linear(x, w, out_dtype=bf16, bias=None, rowmul=None, act=ACT_NONE, colscale=
     assert w.shape[2] == K and K % 8 == 0
     rows = x[0].numel() // K
     if out is None:
-        out = empty16(*x.shape[1:-1], N, device=x.device) if out_dtype == bf16 else \
+        out = empty16(*x.shape[1:-1], N, device=x.device, planes=planes) if out_dtype == bf16 else \
             torch.empty(*x.shape[1:-1], N, device=x.device, dtype=f32)
     L.gemm(x, w, out, M=rows, N=N, K=K, a_rows=rows, a_ld=K, b_ld=K, d_ld=N, a_lo=lo(x), b_lo=lo(w),
-           d_lo=lo(out) if out.dtype == bf16 else 0,
+           d_lo=lo(out) if out.dtype != f32 else 0,
            bias=bias, rowmul=rowmul, act=act, colscale=colscale, resid=resid, resid_masked=resid_masked, alpha=alpha)
     return out
 
 
-def conv3(x, w3, out_dtype=bf16, bias=None, rowmul=None, act=ACT_NONE):
+def conv3(x, w3, out_dtype=bf16, bias=None, rowmul=None, act=ACT_NONE, flat=False):
     """k=3 stride-1 zero-padded conv over time.  x (NP, B, T, Cin), w3 (NP, 3, Cout, Cin) tap-major,
     rowmul (B, T) fp32 -> (B, T, Cout) fp32 or operand (NP, B, T, Cout)."""
     _, B, T, Cin = x.shape
     Cout = w3.shape[2]
     assert w3.shape[1] == 3 and w3.shape[3] == Cin and Cin % 8 == 0
     out = empty16(B, T, Cout, device=x.device) if out_dtype == bf16 else torch.empty(B, T, Cout, device=x.device, dtype=f32)
+    if flat:
+        # the caller guarantees that the last row of every clip is zero and masked (the pyramid's gap rows): the batch is then
+        # one long sequence, so tiles do not stop at clip boundaries (2056-row clips would waste 1/9 of every 256-row tile)
+        L.gemm(x, w3, out, M=B * T, N=Cout, K=Cin, a_rows=B * T, a_ld=Cin, taps=3, b_ld=Cin, b_s=(Cout * Cin, 0), d_ld=Cout,
+               a_lo=lo(x), b_lo=lo(w3), d_lo=lo(out) if out.dtype != f32 else 0, bias=bias, rowmul=rowmul, act=act)
+        return out
     L.gemm(x, w3, out, M=T, N=Cout, K=Cin, a_rows=T, a_ld=Cin, a_s=(0, T * Cin), Z=(1, B), taps=3, b_ld=Cin,
            b_s=(Cout * Cin, 0), d_ld=Cout, d_s=(0, T * Cout), a_lo=lo(x), b_lo=lo(w3),
-           d_lo=lo(out) if out.dtype == bf16 else 0, bias=bias, rowmul=rowmul, rowmul_zs=T, act=act)
+           d_lo=lo(out) if out.dtype != f32 else 0, bias=bias, rowmul=rowmul, rowmul_zs=T, act=act)
     return out
 
 
@@ -157,7 +197,7 @@ def attention(q, k, v, kmask, H, scale):
 
 
 def layernorm(x, w, b, eps=1e-5, add=None, relu=False, pe=None, rowmul=None, zero_rows=None, out32=False, out16=True,
-              y16=None, rows_per_batch=None, y_ld=None, y_bs=None, y16_lo=None):
+              y16=None, rows_per_batch=None, y_ld=None, y_bs=None, y16_lo=None, planes=None):
     """Channel LN over the last dim of token-major fp32 x.  Returns (y32 or None, y16 operand or None).
     `y16` may be a pre-allocated destination view (then pass y_ld / y_bs / y16_lo / rows_per_batch)."""
     assert x.dtype == f32 and x.is_contiguous()
@@ -165,7 +205,7 @@ def layernorm(x, w, b, eps=1e-5, add=None, relu=False, pe=None, rowmul=None, zer
     rows = x.numel() // Cc
     y32 = torch.empty(x.shape, device=x.device, dtype=f32) if out32 else None
     if out16 and y16 is None:
-        y16 = empty16(*x.shape, device=x.device)
+        y16 = empty16(*x.shape, device=x.device, planes=planes)
         y16_lo = lo(y16)
     rpb = rows if rows_per_batch is None else rows_per_batch
     L.check(L.lib().vilco_layernorm(
@@ -197,10 +237,10 @@ def maxpool3s2(x):
     return y
 
 
-def axpby(x, y=None, a=1.0, b=0.0, out32=True, out16=False):
+def axpby(x, y=None, a=1.0, b=0.0, out32=True, out16=False, planes=None):
     """a*x + b*y on fp32 tensors -> (fp32 or None, operand or None)."""
     o32 = torch.empty_like(x) if out32 else None
-    o16 = empty16(*x.shape, device=x.device) if out16 else None
+    o16 = empty16(*x.shape, device=x.device, planes=planes) if out16 else None
     L.check(L.lib().vilco_axpby(_p(x), _p(y), C.c_float(a), C.c_float(b), _p(o32), _p(o16),
                                 _i64(lo(o16) if out16 else 0), _i64(x.numel()), L.stream_ptr()), "vilco_axpby")
     return o32, o16
@@ -215,12 +255,12 @@ def scale_add(x, rowmul, y, scale):
     return out
 
 
-def pack_feats(x, T_out=None):
+def pack_feats(x, T_out=None, planes=None):
     """(B, C, T) fp32 (reference layout) -> operand (NP, B, T_out, C)."""
     assert x.dtype == f32 and x.is_contiguous()
     B, Cc, T = x.shape
     T_out = T if T_out is None else T_out
-    y = empty16(B, T_out, Cc, device=x.device)
+    y = empty16(B, T_out, Cc, device=x.device, planes=planes)
     L.check(L.lib().vilco_pack_feats(_p(x), _p(y), _i64(lo(y)), B, Cc, T, T_out, L.stream_ptr()), "vilco_pack_feats")
     return y
 
@@ -235,11 +275,11 @@ def unpack(x, out=None):
     return y
 
 
-def softmax_rows(S, kmask, mode=0, BD=None, scale=1.0, want32=False):
+def softmax_rows(S, kmask, mode=0, BD=None, scale=1.0, want32=False, planes=None):
     """S (B,H,Tq,Tk) fp32 -> P operand (NP,B,H,Tq,ldp) with ldp = roundup(Tk, 8) [, fp32 P (B,H,Tq,Tk) when want32]."""
     B, H, Tq, Tk = S.shape
     ldp = (Tk + 7) // 8 * 8
-    P = empty16(B, H, Tq, ldp, device=S.device)
+    P = empty16(B, H, Tq, ldp, device=S.device, planes=planes)
     P32 = torch.empty(B, H, Tq, Tk, device=S.device, dtype=f32) if want32 else None
     L.check(L.lib().vilco_softmax_rows(_p(S), _p(BD), _p(kmask), _p(P), _i64(lo(P)), _p(P32), B, H, Tq, Tk, _i64(ldp),
                                        C.c_float(scale), mode, L.stream_ptr()), "vilco_softmax_rows")
@@ -271,14 +311,15 @@ def channel_attention(qkv, H, tlen=None, return_A=False):
                                                 L.stream_ptr()), "vilco_channel_attention")
         if not return_A:
             return y
-        return y, softmax_rows(G.reshape(B, H, 64, 64), None, mode=0)
+        return y, softmax_rows(G.reshape(B, H, 64, 64), None, mode=0, planes=PLANES_HI)
     q = qkv[..., :Cc]
     G = torch.empty(B, H, 64, 64, device=qkv.device, dtype=f32)
-    # G[i, j] = (1/8) sum_t k[t, i] v[t, j]: sums of T products feed a softmax, so this stays on the SIMT kernel, which forms
-    # the full (hi + lo) x (hi + lo) products in fp32 (the three-MMA split drops lo x lo, visible in the detection scores)
+    # G[i, j] = (1/8) sum_t k[t, i] v[t, j]: sums of T products feed a d x d softmax, which turns their ABSOLUTE error into a
+    # relative error of A — the one place of the model that amplifies operand rounding.  So qkv arrives
+    # in two planes and this stays on the SIMT kernel, which forms the full (hi + lo) x (hi + lo) products in fp32.
     L.check(L.lib().vilco_channel_attention(_p(qkv), _i64(lo(qkv)), _p(G), None, _i64(0), None, B, T, Cc, H, L.stream_ptr()),
             "vilco_channel_attention")
-    A16 = softmax_rows(G, None, mode=0)                                   # (NP,B,H,64,64)
+    A16 = softmax_rows(G, None, mode=0, planes=PLANES_HI)                 # (NP,B,H,64,64): the core stays on split operands
     y = empty16(B, T, Cc, device=qkv.device)
     # y[t, i] = sum_j q[t, j] A[i, j]
     L.gemm(q, A16, y, M=T, N=64, K=64, a_rows=T, a_ld=C3, a_s=(64, T * C3), Z=(H, B), b_ld=64, b_s=(64 * 64, H * 64 * 64),

@@ -19,7 +19,7 @@ from .ops import _i64, _p, bf16, f32, lo
 
 
 class V:
-    """value + gradient; `p16` caches the bf16 (hi, lo) operand planes of `v`; const = no gradient wanted."""
+    """value + gradient; `p16` caches the 16-bit operand planes of `v`; const = no gradient wanted."""
     __slots__ = ("v", "g", "p16", "const")
 
     def __init__(self, v=None, p16=None, const=False):
@@ -61,9 +61,11 @@ class Tape:
             return
         self.G[key] = g if key not in self.G else _add(self.G[key], g)
 
-    def planes(self, x):
-        if x.p16 is None:
-            y, _ = BW.to_planes(x.v.reshape(-1, x.v.shape[-1]))
+    def planes(self, x, hi=False):
+        """operand planes of the activation x; hi: this consumer is one of the split-operand contractions (E.sensitive_key)"""
+        want = ops.PLANES_HI if hi else ops.PLANES
+        if x.p16 is None or (x.p16.shape[0] < want and x.v is not None):
+            y, _ = BW.to_planes(x.v.reshape(-1, x.v.shape[-1]), grad=False, planes=want)
             x.p16 = y.reshape(y.shape[0], *x.v.shape)
         return x.p16
 
@@ -93,10 +95,11 @@ class Tape:
         """y = (x w^T + b) * rowmul.  `bias` overrides W[bkey] (XLNet r_w / r_r).  out16: the result only feeds tensor-core
         kernels, so the GEMM epilogue writes the bf16 operand planes directly and no fp32 copy exists."""
         W = self.W
-        x16 = self.planes(x)
+        hi = E.sensitive_key(wkey)
+        x16 = self.planes(x, hi)
         b = bias if bias is not None else (W[bkey] if bkey else None)
         if out16:
-            y = V(p16=ops.linear(x16, W[wkey], bf16, bias=b, rowmul=rowmul))
+            y = V(p16=ops.linear(x16, W[wkey], bf16, bias=b, rowmul=rowmul, planes=ops.PLANES_HI if hi else None))
         else:
             y = V(ops.linear(x16, W[wkey], f32, bias=b, rowmul=rowmul))
 
@@ -116,7 +119,7 @@ class Tape:
 
     def conv3(self, x, wkey, bkey=None, rowmul=None):
         W = self.W
-        x16 = self.planes(x)
+        x16 = self.planes(x, E.sensitive_key(wkey))
         y = V(ops.conv3(x16, W[wkey], f32, bias=W[bkey] if bkey else None, rowmul=rowmul))
         cache = W.setdefault("_cache", {})       # derived from the current weights; dropped when they change
         N = W[wkey].shape[2]
@@ -125,7 +128,7 @@ class Tape:
         if fkey not in cache:                   # tap-reversed weights; rows padded to 8 so the dgrad K keeps 16-byte rows
             wf = W[wkey].flip(1)
             if N8 != N:
-                wp = torch.zeros(wf.shape[0], 3, N8, wf.shape[3], device=wf.device, dtype=bf16)
+                wp = torch.zeros(wf.shape[0], 3, N8, wf.shape[3], device=wf.device, dtype=wf.dtype)
                 wp[:, :, :N] = wf
                 wf = wp
             cache[fkey] = wf.contiguous()
@@ -158,16 +161,19 @@ class Tape:
         self.nodes.append(lambda: self.acc(x, ops.ew(3, y.g, y=y.v)) if y.g is not None else None)
         return y
 
-    def ln(self, x, wkey, bkey, eps=1e-5, relu=False, pe=None, rowmul=None, zero_rows=None, keep_rows=None, want16=True):
+    def ln(self, x, wkey, bkey, eps=1e-5, relu=False, pe=None, rowmul=None, zero_rows=None, keep_rows=None, want16=True,
+           hi=False):
         """channel LayerNorm (+ReLU, + pe*rowmul constant, rows flagged in zero_rows forced to 0).  want16: the kernel also
-        writes the operand planes the next GEMM reads."""
+        writes the operand planes the next GEMM reads (hi: for a split-operand contraction)."""
         W = self.W
+        np_ = ops.PLANES_HI if hi else None
         if pe is not None:   # constant positional term, no gradient
             y32, y16 = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, pe=pe, rowmul=rowmul, out32=True, out16=want16,
-                                     rows_per_batch=x.v.shape[1])
+                                     rows_per_batch=x.v.shape[1], planes=np_)
             yr, _ = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, out32=True, out16=False)
         else:
-            y32, y16 = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, out32=True, out16=want16, zero_rows=zero_rows)
+            y32, y16 = ops.layernorm(x.v, W[wkey], W[bkey], eps, relu=relu, out32=True, out16=want16, zero_rows=zero_rows,
+                                     planes=np_)
             yr = y32
         y = V(y32, p16=y16)
 
@@ -246,7 +252,7 @@ class Tape:
             if out.g is None:
                 return
             g = out.g.contiguous()
-            dz = ops.empty16(rows, N, device=g.device)
+            dz = ops.empty16(rows, N, device=g.device, grad=True)
             dres = torch.empty_like(g) if rm is not None else None
             sb = self.sink(bkey) if bkey else None
             ss = self.sink(skey) if sc is not None else None
@@ -361,7 +367,7 @@ def transformer_block(tp, pre, x, mask, H, stride, cross=None, t_c_alpha=0.8, ad
     W = tp.W
     C = x.shape[-1]
     scale = 1.0 / math.sqrt(C // H)
-    ln1 = tp.ln(x, pre + "ln1.weight", pre + "ln1.bias", want16=(stride == 1))
+    ln1 = tp.ln(x, pre + "ln1.weight", pre + "ln1.bias", want16=(stride == 1), hi=True)   # planes only feed the channel qkv
     qc, kc, vc = tp.dwconv_ln3(ln1, pre + "attn.", mask, stride)
     om = mask[:, ::stride].contiguous() if stride > 1 else mask
     omf = om.reshape(-1)
@@ -452,7 +458,7 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
             ops.dropout(dP, pd, seed, out=dP)
         dS, dS16 = BW.softmax_bwd(dP, scale, P32=P32, want32=True)
         del dP
-        dBD16 = ops.empty16(B, H, T, 2 * T, device=dS.device)
+        dBD16 = ops.empty16(B, H, T, 2 * T, device=dS.device, grad=True)
         L.check(L.lib().vilco_relshift_bwd(_p(dS), None, _p(dBD16), _i64(lo(dBD16)), _i64(B * H), T, L.stream_ptr()),
                 "vilco_relshift_bwd")
         del dS
@@ -487,7 +493,7 @@ def backbone(tp, cfg, x16, mask, text16, tmask, pe, pets_prefix="pets."):
         c = tp.conv3(x, pre + f"embd.{i}.conv.weight", None, rowmul=mask)
         last = i == n_embd - 1
         x = tp.ln(c, pre + f"embd_norm.{i}.weight", pre + f"embd_norm.{i}.bias", relu=True, pe=pe if last else None,
-                  rowmul=m if last else None, want16=not last)
+                  rowmul=m if last else None, want16=not last, hi=True)
     cross, tin = None, None
     if cfg.use_cross_modal and text16 is not None:
         tm = tmask.reshape(-1)

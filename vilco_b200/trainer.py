@@ -315,8 +315,8 @@ class FlatAdamW(torch.optim.Optimizer):
         optimizer step keeps them current by itself)."""
         from . import ops
         with torch.no_grad():
-            hi = self.flat_p.to(torch.bfloat16)
-            self.planes = torch.stack([hi, (self.flat_p - hi.float()).to(torch.bfloat16)]) if ops.PLANES == 2 else hi.unsqueeze(0).clone()
+            # two planes whenever any contraction reads split weights (ops.PLANES_HI); single-plane consumers use plane 0
+            self.planes = ops.split16(self.flat_p, planes=ops.PLANES_HI)
         self._planes_precision = ops.precision()
 
     def plane_view(self, p, shape):
