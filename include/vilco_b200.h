@@ -37,15 +37,17 @@ extern "C" {
 #define VILCO_BF16 1
 #define VILCO_F16 2
 
-/* Element format of the 16-bit ACTIVATION / WEIGHT operand planes every kernel of this library reads and writes
- * (VILCO_BF16, the initial value, or VILCO_F16).  It is process-wide state read at launch time (and therefore baked
- * into a captured CUDA graph): set it once per precision mode, before packing weights.  fp16 planes carry 11
- * significant bits (8x tighter than bf16) at the same tensor-core rate; the 16-bit GRADIENT planes the backward
- * kernels emit (vilco_to_planes with grad = 1, vilco_resid_branch_bwd, vilco_softmax_bwd, vilco_relshift_bwd) are
- * always bf16 because gradient magnitudes do not fit the fp16 range.  vilco_gemm takes the format of each operand
- * explicitly (a_fmt / b_fmt / d_dtype) since it mixes the two. */
+/* Element format of the 16-bit operand planes every kernel of this library reads and writes (VILCO_BF16, the initial
+ * value, or VILCO_F16).  It is process-wide state read at launch time (and therefore baked into a captured CUDA graph):
+ * set it once per precision mode, before packing weights.  fp16 planes carry 11 significant bits (8x tighter than bf16)
+ * at the same tensor-core rate.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands in one MMA, so the GRADIENT planes
+ * the backward kernels emit (vilco_to_planes with grad = 1, vilco_resid_branch_bwd, vilco_softmax_bwd,
+ * vilco_relshift_bwd) use the same format: they are stored multiplied by the gradient scale (vilco_set_grad_scale, a
+ * power of two, 1 for bf16) and the caller folds 1 / scale into the alpha of every vilco_gemm that consumes them.
+ * vilco_gemm takes the operand formats explicitly (a_fmt == b_fmt required by the hardware). */
 int vilco_set_plane_format(int fmt);
 int vilco_get_plane_format(void);
+int vilco_set_grad_scale(float scale);
 
 const char* vilco_last_error(void);
 int vilco_version(void);
@@ -243,8 +245,7 @@ int vilco_attention(const void* q, int64_t q_lo, const void* k, const void* v, i
  *   dW = dZ^T X    : A = dZ^T (vilco_to_planes writes the transposed planes), B = X as MN-major operand
  * ------------------------------------------------------------------------------------ */
 /* y16[r,c] = x[r,c]*rowmul[r]*colmul[c] as 16-bit (hi, lo) planes and / or its transpose yT16[c,r] with row stride ldT
- * (either output may be NULL).  grad != 0: x is a gradient, the planes are bf16; grad == 0: an activation, the planes use
- * the format of vilco_set_plane_format. */
+ * (either output may be NULL).  grad != 0: x is a gradient, the planes hold x * grad_scale (vilco_set_grad_scale). */
 int vilco_to_planes(const float* x, const float* rowmul, const float* colmul, void* y, int64_t y_lo, void* yT, int64_t yT_lo,
                     int R, int C, int ldT, int Z, int grad, void* stream);   /* Z independent (R,C) matrices */
 /* XLNet rel-shift backward (modeling_xlnet_x.py:256-268): dBD[z,i,p] = dS[z,i,p-T+i] inside the band, 0 elsewhere; every

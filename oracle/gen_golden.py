@@ -195,7 +195,7 @@ def gen_vilco_train_golden():
     out = {"loss_" + k: np.float32(v.detach().reshape(-1)[0].item()) for k, v in losses.items()}
     n = 0
     for k, p_ in model.named_parameters():
-        if p_.grad is not None and ".adapters." not in k:
+        if p_.grad is not None:      # incl. the temporal adapters, listed under backbone.branch.<b>.adapters.attn.*
             g = p_.grad.detach().reshape(-1).double()
             out["g:" + k] = np.concatenate([[g.norm().item(), g.sum().item()], g[:8].numpy()]).astype(np.float64)
             n += 1

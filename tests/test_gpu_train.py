@@ -278,14 +278,14 @@ def test_dropout_mask_statistics_and_fused_residual_branch():
     ref = resid * rm[:, None] + scale * ((y + bias) * keep) * ymul[:, None]
     assert rel_max(out, ref) < 1e-6
     dres = torch.empty_like(g)
-    dz = ops.empty16(R, Cc, device="cuda")
+    dz = ops.empty16(R, Cc, device="cuda", grad=True)
     db, ds = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
     L.check(L.lib().vilco_resid_branch_bwd(ops._p(g), ops._p(rm), ops._p(y), ops._p(bias), ops._p(scale), ops._p(ymul), ops._p(dres),
                                            ops._p(dz), ops._i64(ops.lo(dz)), ops._p(db), ops._p(ds), R, Cc, C.c_float(p),
                                            C.c_uint64(seed), st))
     t = g * ymul[:, None] * keep
     assert rel_max(dres, g * rm[:, None]) < 1e-6
-    assert rel_max(ops.merge16(dz), t * scale) < 2e-5
+    assert rel_max(ops.merge16(dz) * ops.ginv(), t * scale) < 2e-5        # gradient planes are stored times GRAD_SCALE
     assert rel_max(db, (t * scale).sum(0)) < 1e-5
     assert rel_max(ds, (t * (y + bias)).sum(0)) < 1e-5
 
@@ -431,6 +431,66 @@ def test_vilco_training_step_matches_reference_golden():
         assert np.abs(got[2:] - ref[2:]).max() <= tol * ref[0] + 1e-7, (key, got[2:4], ref[2:4])
         n += 1
     assert n > 250
+    # the temporal adapters are trained (the reference un-freezes them and EMA-averages them): their gradients reach the
+    # registered parameters although the engines address them as pets.<i>.*
+    assert sum(1 for k in g.files if ".adapters.attn." in k and g[k][0] >= 1e-6 * gmax) >= 10
+    for i in range(len(cfg.adapt_blocks)):
+        assert model.pets[i].layer[0].weight.grad is not None and float(model.pets[i].layer[0].weight.grad.abs().max()) > 0
+
+
+def test_flat_and_torch_optimizer_checkpoints_are_interchangeable():
+    """make_optimizer(flat=True).state_dict() loads into make_optimizer(flat=False) and back with every moment on the SAME
+    parameter: the state is indexed by the position in the (alphabetical) groups in both, whatever the flat layout order."""
+    from vilco_b200.trainer import make_optimizer
+    cfg = GG.small_cfg()
+    oc = {"type": "AdamW", "learning_rate": 1e-3, "weight_decay": 0.05}
+    m1, _ = build_pair(cfg, 0)
+    m2, _ = build_pair(cfg, 0)
+    o_flat, o_torch = make_optimizer(m1, oc, flat=True), make_optimizer(m2, oc, flat=False)
+    n1 = {id(p): k for k, p in m1.named_parameters()}
+    n2 = {id(p): k for k, p in m2.named_parameters()}
+    assert [[n1[id(p)] for p in g["params"]] for g in o_flat.param_groups] == \
+        [[n2[id(p)] for p in g["params"]] for g in o_torch.param_groups]
+    # give every parameter of the flat optimizer a recognisable state: exp_avg = hash of its name
+    o_flat.t = 3
+    tag = {k: float(sum(map(ord, k)) % 997) for k in n1.values()}
+    for pid, (o, k) in o_flat.slots.items():
+        o_flat.exp_avg[o:o + k] = tag[n1[pid]]
+        o_flat.exp_avg_sq[o:o + k] = 2 * tag[n1[pid]]
+    for p in m2.parameters():
+        p.grad = torch.zeros_like(p)
+    o_torch.step()                                       # creates torch's state entries
+    o_torch.load_state_dict(o_flat.state_dict())
+    for p, st in o_torch.state.items():
+        assert float(st["exp_avg"].flatten()[0]) == tag[n2[id(p)]] and float(st["exp_avg_sq"].flatten()[0]) == 2 * tag[n2[id(p)]]
+    m3, _ = build_pair(cfg, 0)
+    o3 = make_optimizer(m3, oc, flat=True)
+    o3.load_state_dict(o_torch.state_dict())
+    n3 = {id(p): k for k, p in m3.named_parameters()}
+    for pid, (o, k) in o3.slots.items():
+        assert float(o3.exp_avg[o]) == tag[n3[pid]], n3[pid]
+
+
+def test_eval_graph_applies_bic_bias_layers():
+    """BiC with n_known > 0: the captured evaluation graph corrects the logits like the eager forward (meta_archs.py:822-836)"""
+    from util import match_detections
+    from vilco_b200.modeling.meta_archs import BiasLayer
+    cfg = GG.small_cfg()
+    model, P = build_pair(cfg, 0)
+    videos = PR.synth_video_list(cfg, 2, seed=0, lens=[128, 100], text_lens=[40, 57], n_gt=[3, 2])
+    plain = model(videos, is_training=False)
+    model.cl_name, model.n_known, model.list_splits = "bic", 3, [3, 6]
+    model.list_bias_layers = [BiasLayer().cuda(), BiasLayer().cuda()]
+    for bl, (a, b) in zip(model.list_bias_layers, ((1.3, 0.2), (0.7, -0.3))):
+        bl.alpha.data.fill_(a)
+        bl.beta.data.fill_(b)
+    eager = model(videos, is_training=False)
+    out = model.make_eval_graph(2, text_len=64).run(videos)
+    assert float((eager[0]["scores"] - plain[0]["scores"]).abs().max()) > 1e-3          # the correction changes the result
+    for i in range(2):
+        ds, swaps, dseg, orphans = match_detections(out[i], eager[i]["segments"].numpy(), eager[i]["scores"].numpy(),
+                                                    eager[i]["labels"].numpy())
+        assert ds < 1e-5 and swaps <= 2 and orphans <= 1, (ds, swaps, orphans)
 
 
 @pytest.mark.parametrize("name", ["bic", "icarl"])

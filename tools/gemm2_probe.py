@@ -69,7 +69,7 @@ def case(M, N, K, fa, fb, pa, pb, impl, out=torch.float32, taps=1, epi=False, dp
     got = D.double().sum(0)
     # dropped lo*lo term: 2^-2p of the product magnitude; output rounding when the result is a single 16-bit plane
     eps = {F16: 2.0 ** -11, BF16: 2.0 ** -8}
-    tol = 3e-6 + (eps[fa] * eps[fb] * 4 if pa == 2 and pb == 2 else 0)
+    tol = (3e-6 if taps == 1 else 1e-5) + (eps[fa] * eps[fb] * 4 if pa == 2 and pb == 2 else 0)   # fp32 accumulation over K * taps
     if out != torch.float32:
         tol += eps[out] if dplanes == 1 else eps[out] ** 2 * 4
     name = (f"M{M} N{N} K{K} taps{taps} A:{str(fa)[6:]}x{pa} B:{str(fb)[6:]}x{pb} impl{impl} out:{str(out)[6:]}x{dplanes} epi{int(epi)}")
@@ -78,7 +78,7 @@ def case(M, N, K, fa, fb, pa, pb, impl, out=torch.float32, taps=1, epi=False, dp
 
 def check():
     for impl in (1, 2, 3):   # SIMT, one CTA per tile, CTA pair per tile
-        for fa, fb in ((F16, F16), (BF16, BF16), (BF16, F16)):
+        for fa, fb in ((F16, F16), (BF16, BF16)) + (((BF16, F16),) if impl == 1 else ()):   # the tensor core cannot mix formats
             for pa, pb in ((1, 1), (2, 2), (2, 1), (1, 2)):
                 case(512, 256, 256, fa, fb, pa, pb, impl)
         case(1000, 520, 328, F16, F16, 1, 1, impl, epi=True)                        # ragged M / N / K tails + epilogue

@@ -16,8 +16,8 @@ from .ops import _i64, _p, f32, lo
 def to_planes(x, rowmul=None, colmul=None, want=True, want_t=False, batch_dims=0, grad=True, planes=None):
     """x (..., R, C) fp32 -> (y16 (NP,...,R,C) or None, yT16 (NP,...,C,ldT) or None), y = x * rowmul[:,None] * colmul[None,:].
     The leading `batch_dims` dims index independent matrices (transposed separately); otherwise x is flattened to 2-D.
-    grad=True (the default here: this module handles gradients): bf16 planes; grad=False: an activation, planes in the
-    activation format."""
+    grad=True (the default here: this module handles gradients): the planes hold x * ops.GRAD_SCALE — every GEMM reading
+    them multiplies its alpha by ops.ginv(); grad=False: an activation, stored as is."""
     assert x.dtype == f32 and x.is_contiguous()
     Cc = x.shape[-1]
     if batch_dims:
@@ -53,6 +53,7 @@ def wgrad(dz, x2, Mo, No, R, alpha=1.0, out=None):
     rows while the output has few tiles, so K is split over batches (split-K) whenever the plain launch would leave most
     of the 148 SMs idle; partials are summed by vilco_colsum.  out: fp32 (Mo, No) buffer to ACCUMULATE into (the
     parameter's .grad view)."""
+    alpha = alpha * ops.ginv()        # dz is a gradient-plane operand
     tiles = ((Mo + 127) // 128) * ((No + 127) // 128)
     S = min(16, 148 // tiles) if tiles < 100 else 1
     while S > 1 and (R % (8 * S) != 0 or R // S < 512):
@@ -80,7 +81,8 @@ def linear_bwd(dy, x16, w16, rowmul=None, alpha=1.0, need_dx=True, need_dw=True,
     dx = dw = db = None
     if need_dx:
         dx = torch.empty(*dy.shape[:-1], K, device=dy.device, dtype=f32)
-        L.gemm(dz, w16, dx, M=R, N=K, K=N, a_rows=R, a_ld=N, b_ld=K, d_ld=K, b_major=1, alpha=alpha, a_lo=lo(dz), b_lo=lo(w16))
+        L.gemm(dz, w16, dx, M=R, N=K, K=N, a_rows=R, a_ld=N, b_ld=K, d_ld=K, b_major=1, alpha=alpha * ops.ginv(), a_lo=lo(dz),
+               b_lo=lo(w16))
     if need_dw:
         dw = wgrad(dz, x16.reshape(x16.shape[0], -1, K), N, K, R, alpha, out=dw_out)
     if need_db:
@@ -95,7 +97,7 @@ def linear_bwd16(dz, x16, w16, need_dx=True, dw_out=None):
     dx = None
     if need_dx:
         dx = torch.empty(R, K, device=dz.device, dtype=f32)
-        L.gemm(dz, w16, dx, M=R, N=K, K=N, a_rows=R, a_ld=N, b_ld=K, d_ld=K, b_major=1, a_lo=lo(dz), b_lo=lo(w16))
+        L.gemm(dz, w16, dx, M=R, N=K, K=N, a_rows=R, a_ld=N, b_ld=K, d_ld=K, b_major=1, alpha=ops.ginv(), a_lo=lo(dz), b_lo=lo(w16))
     dw = wgrad(dz, x16.reshape(x16.shape[0], -1, K), N, K, R, out=dw_out)
     return dx, dw
 
@@ -121,7 +123,7 @@ def conv3_bwd(dy, x16, w3, w3_flip, rowmul=None, need_dx=True):
         dx = torch.empty(B, T, K, device=dy.device, dtype=f32)
         dz4 = dz.reshape(dz.shape[0], B, T, N)
         L.gemm(dz4, w3_flip, dx, M=T, N=K, K=N, a_rows=T, a_ld=N, a_s=(0, T * N), Z=(1, B), taps=3, b_ld=K, b_s=(N * K, 0),
-               b_major=1, d_ld=K, d_s=(0, T * K), a_lo=lo(dz4), b_lo=lo(w3_flip))
+               b_major=1, d_ld=K, d_s=(0, T * K), alpha=ops.ginv(), a_lo=lo(dz4), b_lo=lo(w3_flip))
     R = B * T
     taps = []
     for tap in range(3):
@@ -213,12 +215,13 @@ def attention_bwd(dO, q16, k16, v16, kmask, H, scale):
     del S
     dO16, _ = to_planes(dO.reshape(-1, Cc))
     dO16 = dO16.reshape(dO16.shape[0], B, Tq, Cc)
-    dP = ops.attn_scores(dO16, v16, H, 1.0)                          # dP[b,h] = dO_h v_h^T
+    gi = ops.ginv()                                                  # dO16 / dS16 are gradient planes (times GRAD_SCALE)
+    dP = ops.attn_scores(dO16, v16, H, gi)                           # dP[b,h] = dO_h v_h^T
     _, dS16 = softmax_bwd(dP, scale, P16=P16)
     del dP
-    dq = ops.attn_pv(dS16, k16, H, Tk, out32=True)                   # dQ_h = dS K_h
-    dk = ops.attn_pv(dS16, q16, H, Tq, out32=True, a_trans=True, M=Tk)   # dK_h = dS^T Q_h
-    dv = ops.attn_pv(P16, dO16, H, Tq, out32=True, a_trans=True, M=Tk)   # dV_h = P^T dO_h
+    dq = ops.attn_pv(dS16, k16, H, Tk, out32=True, alpha=gi)                   # dQ_h = dS K_h
+    dk = ops.attn_pv(dS16, q16, H, Tq, out32=True, a_trans=True, M=Tk, alpha=gi)   # dK_h = dS^T Q_h
+    dv = ops.attn_pv(P16, dO16, H, Tq, out32=True, a_trans=True, M=Tk, alpha=gi)   # dV_h = P^T dO_h
     return dq, dk, dv
 
 

@@ -14,7 +14,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 static std::atomic<int> g_act_fmt{VILCO_BF16};
+static std::atomic<float> g_grad_scale{1.0f};
 int act_fmt() { return g_act_fmt.load(std::memory_order_relaxed); }
+float grad_scale() { return g_grad_scale.load(std::memory_order_relaxed); }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
 }  // namespace vilco
 
@@ -30,3 +32,11 @@ extern "C" int vilco_set_plane_format(int fmt) {
   return VILCO_OK;
 }
 extern "C" int vilco_get_plane_format(void) { return vilco::act_fmt(); }
+extern "C" int vilco_set_grad_scale(float s) {
+  if (!(s > 0.f)) {
+    vilco::set_error("vilco_set_grad_scale: scale must be positive");
+    return VILCO_E_ARG;
+  }
+  vilco::g_grad_scale.store(s, std::memory_order_relaxed);
+  return VILCO_OK;
+}

@@ -42,13 +42,14 @@ __device__ __forceinline__ float4 ld_planes4(const __nv_bfloat16* p, long long l
 // plain (no transpose) fp32 -> planes, 4 elements per thread; C % 4 == 0
 __global__ void __launch_bounds__(256) to_planes_vec_kernel(const float* __restrict__ x, const float* __restrict__ rowmul,
                                                             const float* __restrict__ colmul, __nv_bfloat16* __restrict__ y,
-                                                            long long y_lo, long long rows, int C, int fmt) {
+                                                            long long y_lo, long long rows, int C, int fmt, float mul) {
   const int C4 = C >> 2;
   const long long n4 = rows * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = ld4f(x + 4 * i);
     if (rowmul) { const float m = rowmul[i / C4]; v.x *= m; v.y *= m; v.z *= m; v.w *= m; }
     if (colmul) { const float4 m = ld4f(colmul + 4 * (i % C4)); v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w; }
+    v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
     st_planes4(y + 4 * i, y_lo, v, fmt);
   }
 }
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) to_planes_vec_kernel(const float* __restr
 // y16[r, c] = x[r, c] * rowmul[r] * colmul[c]  as bf16 planes; optional transposed copy yT16[c, r]
 __global__ void to_planes_kernel(const float* __restrict__ x, const float* __restrict__ rowmul, const float* __restrict__ colmul,
                                  __nv_bfloat16* __restrict__ y, long long y_lo, __nv_bfloat16* __restrict__ yT, long long yT_lo,
-                                 int R, int C, int ldT, int fmt) {
+                                 int R, int C, int ldT, int fmt, float mul) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -71,6 +72,7 @@ __global__ void to_planes_kernel(const float* __restrict__ x, const float* __res
       v = x[(long long)r * C + c];
       if (rowmul) v *= rowmul[r];
       if (colmul) v *= colmul[c];
+      v *= mul;
       if (y) st_planes(y + (long long)r * C + c, y_lo, v, fmt);
     }
     tile[j][tx] = v;
@@ -305,7 +307,8 @@ __global__ void dwconv_fwd32_kernel(const float* __restrict__ x, const float* __
 // XLNet rel-shift backward: dBD[z, i, p] = dS[z, i, p - T + i] where that index is inside [0, T), else 0 (gather form: every
 // output element is written once, fp32 and / or operand planes)
 __global__ void __launch_bounds__(256) relshift_bwd_kernel(const float* __restrict__ dS, float* __restrict__ dBD,
-                                                           __nv_bfloat16* __restrict__ dBD16, long long dbd_lo, long long Z, int T) {
+                                                           __nv_bfloat16* __restrict__ dBD16, long long dbd_lo, long long Z, int T,
+                                                           int fmt, float gs) {
   const int W4 = (2 * T) >> 2;   // T % 2 == 0 is checked by the host
   const long long total4 = Z * T * W4;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(256) relshift_bwd_kernel(const float* __restri
     }
     const float4 o = make_float4(v[0], v[1], v[2], v[3]);
     if (dBD) st4f(dBD + 4 * idx, o);
-    if (dBD16) st_planes4(dBD16 + 4 * idx, dbd_lo, o, VILCO_BF16);   // gradient planes are bf16
+    if (dBD16) st_planes4(dBD16 + 4 * idx, dbd_lo, make_float4(o.x * gs, o.y * gs, o.z * gs, o.w * gs), fmt);   // gradient planes: scaled
   }
 }
 
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(256) resid_branch_bwd_kernel(const float* __re
                                                                float* __restrict__ dresid, __nv_bfloat16* __restrict__ dy16,
                                                                long long dy_lo, float* __restrict__ dbias, float* __restrict__ dscale,
                                                                int R, int C, int rows_per_block, unsigned int thr, float inv_keep,
-                                                               unsigned long long seed) {
+                                                               unsigned long long seed, int fmt, float gs) {
   __shared__ float red[2][8][129];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + tx) * 4;   // C % 4 == 0 (host check)
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(256) resid_branch_bwd_kernel(const float* __re
         t.z *= keep_factor(seed, i + 2, thr, inv_keep); t.w *= keep_factor(seed, i + 3, thr, inv_keep);
       }
       const float4 dyi = make_float4(t.x * sc.x, t.y * sc.y, t.z * sc.z, t.w * sc.w);
-      st_planes4(dy16 + i, dy_lo, dyi, VILCO_BF16);   // gradient planes are bf16
+      st_planes4(dy16 + i, dy_lo, make_float4(dyi.x * gs, dyi.y * gs, dyi.z * gs, dyi.w * gs), fmt);   // gradient planes: scaled
       sb.x += dyi.x; sb.y += dyi.y; sb.z += dyi.z; sb.w += dyi.w;
       const float4 yi = ld4f(y + i);
       ss.x += t.x * (yi.x + bc.x); ss.y += t.y * (yi.y + bc.y); ss.z += t.z * (yi.z + bc.z); ss.w += t.w * (yi.w + bc.w);
@@ -527,8 +530,8 @@ __global__ void maxpool3s2_bwd_kernel(const float* __restrict__ x, const float* 
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ P32, const __nv_bfloat16* __restrict__ P16,
                                                           long long p_lo, long long p_ld, const float* __restrict__ dP,
                                                           float* __restrict__ dS, __nv_bfloat16* __restrict__ dS16, long long ds_lo,
-                                                          long long ds_ld, long long rows, int Tk, float scale, int pfmt) {
-  // P16 (forward probabilities) is in the activation format pfmt; the gradient planes dS16 are bf16
+                                                          long long ds_ld, long long rows, int Tk, float scale_in, int pfmt, float gs) {
+  // P16 (forward probabilities) and the gradient planes dS16 share the plane format pfmt; dS16 is stored times gs
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -549,18 +552,19 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     s = warp_sum(s);
     for (int j = lane * 4; j < Tk; j += 128) {
       const float4 pv = ld_planes4(p16 + j, p_lo, pfmt), dv = ld4f(d + j);
+      const float scale = scale_in * gs;
       st_planes4(dS16 + row * ds_ld + j, ds_lo, make_float4(scale * pv.x * (dv.x - s), scale * pv.y * (dv.y - s),
                                                             scale * pv.z * (dv.z - s), scale * pv.w * (dv.w - s)),
-                 VILCO_BF16);
+                 pfmt);
     }
     return;
   }
   for (int j = lane; j < Tk; j += 32) s += prob(j) * d[j];
   s = warp_sum(s);
   for (int j = lane; j < Tk; j += 32) {
-    const float v = scale * prob(j) * (d[j] - s);
+    const float v = scale_in * prob(j) * (d[j] - s);
     if (dS) dS[row * Tk + j] = v;
-    if (dS16) st_planes(dS16 + row * ds_ld + j, ds_lo, v, VILCO_BF16);
+    if (dS16) st_planes(dS16 + row * ds_ld + j, ds_lo, v * gs, pfmt);
   }
 }
 
@@ -578,7 +582,8 @@ static inline int bgrid(long long n, int block, int cap = 148 * 8) {
 extern "C" int vilco_to_planes(const float* x, const float* rowmul, const float* colmul, void* y, int64_t y_lo, void* yT,
                                int64_t yT_lo, int R, int C, int ldT, int Z, int grad, void* stream) {
   VILCO_CHECK_ARG(x && (y || yT) && R > 0 && C > 0 && Z > 0, "vilco_to_planes: bad arguments");
-  const int fmt = grad ? VILCO_BF16 : act_fmt();
+  const int fmt = act_fmt();
+  const float mul = grad ? grad_scale() : 1.0f;
   if (!yT && C % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 8 == 0 && y_lo % 4 == 0 &&
       (!colmul || reinterpret_cast<uintptr_t>(colmul) % 16 == 0)) {
     // Z independent matrices are contiguous: one flat pass (rowmul, when given, indexes z * R + r as well)
@@ -586,13 +591,13 @@ extern "C" int vilco_to_planes(const float* x, const float* rowmul, const float*
     long long g = (rows * (C / 4) + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
     to_planes_vec_kernel<<<static_cast<unsigned>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, rows, C, fmt);
+        x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, rows, C, fmt, mul);
     VILCO_LAUNCH_CHECK();
     return VILCO_OK;
   }
   dim3 grid((C + 31) / 32, (R + 31) / 32, Z);
   to_planes_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, static_cast<__nv_bfloat16*>(yT), yT_lo, R, C, ldT, fmt);
+      x, rowmul, colmul, static_cast<__nv_bfloat16*>(y), y_lo, static_cast<__nv_bfloat16*>(yT), yT_lo, R, C, ldT, fmt, mul);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -664,7 +669,7 @@ extern "C" int vilco_softmax_bwd(const float* P32, const void* P16, int64_t p_lo
   VILCO_CHECK_ARG((P32 || P16) && dP && (dS || dS16) && rows > 0 && Tk > 0, "vilco_softmax_bwd: bad arguments");
   softmax_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       P32, static_cast<const __nv_bfloat16*>(P16), p_lo, p_ld, dP, dS, static_cast<__nv_bfloat16*>(dS16), ds_lo, ds_ld, rows, Tk, scale,
-      act_fmt());
+      act_fmt(), grad_scale());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -690,7 +695,7 @@ extern "C" int vilco_dwconv_fwd32(const float* x, const float* mask, const float
 extern "C" int vilco_relshift_bwd(const float* dS, float* dBD, void* dBD16, int64_t dbd_lo, int64_t Z, int T, void* stream) {
   VILCO_CHECK_ARG(dS && (dBD || dBD16) && Z > 0 && T > 0 && T % 2 == 0 && dbd_lo % 4 == 0, "vilco_relshift_bwd: bad arguments");
   relshift_bwd_kernel<<<bgrid(Z * T * (T / 2LL), 256, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dS, dBD, static_cast<__nv_bfloat16*>(dBD16), dbd_lo, Z, T);
+      dS, dBD, static_cast<__nv_bfloat16*>(dBD16), dbd_lo, Z, T, act_fmt(), grad_scale());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -745,7 +750,8 @@ extern "C" int vilco_resid_branch_bwd(const float* g, const float* rm, const flo
   dim3 grid(cblocks, (R + rpb - 1) / rpb);
   resid_branch_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, rm, y, bias, scale, ymul, dresid,
                                                                              static_cast<__nv_bfloat16*>(dy16), dy_lo, dbias, dscale, R,
-                                                                             C, rpb, thr, 1.0f / (1.0f - p), seed);
+                                                                             C, rpb, thr, 1.0f / (1.0f - p), seed, act_fmt(),
+                                                                             grad_scale());
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

@@ -13,9 +13,12 @@ namespace vilco {
 // ---- host-side error plumbing -------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
-// element format of the ACTIVATION / WEIGHT operand planes (VILCO_BF16 or VILCO_F16; vilco_set_plane_format).  Gradient
-// planes (the backward kernels' 16-bit outputs) are always bf16: their range does not fit fp16.
+// element format of every 16-bit operand plane (VILCO_BF16 or VILCO_F16; vilco_set_plane_format).  tcgen05 kind::f16 cannot
+// mix fp16 and bf16 operands in one MMA, so the gradient planes the backward kernels emit use the same format; with fp16
+// they are stored pre-multiplied by grad_scale() (a power of two that centres gradient magnitudes in the fp16 range) and the
+// caller folds 1 / grad_scale into the alpha of every GEMM that consumes them.
 int act_fmt();
+float grad_scale();
 
 #define VILCO_CHECK_ARG(cond, ...)                         \
   do {                                                     \

@@ -425,6 +425,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = chalf; c < BN / 32; c += 2) {
         const int nb = n0 + c * 32;
         if (nb >= p.N || mrow0 >= p.M) break;  // warp-uniform
+        // fp32 output with a residual: issue this chunk's 8 residual loads (16 B per lane each) BEFORE the accumulator is
+        // fetched and transposed, so their L2 / HBM latency overlaps that work instead of serialising 8 dependent round trips
+        float4 rs[8];
+        const bool pre = is_f32 && resid != nullptr && p.vec_ok && (nb + 31 < p.N);
+        if (pre) {
+          const int rsub = lane >> 3, g = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int mm = mrow0 + 4 * i + rsub;
+            rs[i] = mm < p.M ? __ldg(reinterpret_cast<const float4*>(resid + zoff + (long long)mm * d_ld + nb + 4 * g))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t rr[32];
         __syncwarp();
         tmem_ld32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
@@ -448,9 +461,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (colscale) s4[u] = __ldg(colscale + n + u);
             }
           float* Df = static_cast<float*>(p.D);
-#pragma unroll 2
-          for (int r0 = 0; r0 < 32; r0 += 4) {
-            const int rloc = r0 + rsub;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rloc = 4 * i + rsub;
             const int mm = mrow0 + rloc;
             const float rmr = __shfl_sync(0xffffffffu, rm, rloc);
             if (mm < p.M && n < p.N) {
@@ -462,8 +475,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float f = resid_masked ? rmr : 1.0f;
               if (vec) {
                 if (resid) {
-                  const float4 rs = *reinterpret_cast<const float4*>(resid + o);
-                  v[0] += rs.x * f; v[1] += rs.y * f; v[2] += rs.z * f; v[3] += rs.w * f;
+                  const float4 rv = pre ? rs[i] : *reinterpret_cast<const float4*>(resid + o);
+                  v[0] += rv.x * f; v[1] += rv.y * f; v[2] += rv.z * f; v[3] += rv.w * f;
                 }
                 *reinterpret_cast<float4*>(Df + o) = make_float4(v[0], v[1], v[2], v[3]);
               } else {
@@ -995,6 +1008,8 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   const int a_fmt = g->a_fmt ? g->a_fmt : VILCO_BF16, b_fmt = g->b_fmt ? g->b_fmt : VILCO_BF16;   // 0 = legacy callers: bf16
   VILCO_CHECK_ARG((a_fmt == VILCO_BF16 || a_fmt == VILCO_F16) && (b_fmt == VILCO_BF16 || b_fmt == VILCO_F16),
                   "vilco_gemm: operand formats must be VILCO_BF16 or VILCO_F16");
+  // measured on B200: a kind::f16 MMA whose A and B formats differ raises "illegal instruction"
+  VILCO_CHECK_ARG(a_fmt == b_fmt || g->impl == 1, "vilco_gemm: A and B must have the same 16-bit format (tcgen05 kind::f16)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   GemmDev p{};

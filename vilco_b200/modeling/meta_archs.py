@@ -340,6 +340,22 @@ class PtTransformer(nn.Module):
             tab = self._ptab = ([k for k, _ in named], [p_ for _, p_ in named], len(named))
         return tab
 
+    def _canon_key(self, key):
+        """tape / packed-weight key -> the name `named_parameters()` lists the parameter under.  The temporal adapters are
+        registered twice (`pets.<i>.*` and `backbone.branch.<b>.adapters.attn.*`, like the reference); named_parameters()
+        de-duplicates and keeps the backbone name, while the engines address them as `pets.<i>.*`."""
+        if key.startswith("pets.") and self.use_adapt:
+            i, rest = key[5:].split(".", 1)
+            return f"backbone.branch.{self.adapt_blocks[int(i)]}.adapters.attn.{rest}"
+        return key
+
+    def _tape_key(self, name):
+        """inverse of `_canon_key`"""
+        if ".adapters.attn." in name and name.startswith("backbone.branch."):
+            b, rest = name[len("backbone.branch."):].split(".adapters.attn.", 1)
+            return f"pets.{self.adapt_blocks.index(int(b))}.{rest}"
+        return name
+
     def attach_pets(self, pets):
         """register the adapters under backbone.branch.<b>.adapters.attn like AdapterMixin.attach_adapter (blocks.py:28-33)"""
         for i, b in enumerate(self.adapt_blocks):
@@ -533,7 +549,7 @@ class PtTransformer(nn.Module):
             src = vl if is_training else video_list
             text, tmask, tlens = self.query_preprocessing(src)
             if hasattr(self, "prompt"):
-                if not is_training and len(src) > 1 and len(set(int(v) for v in tlens.tolist())) > 1:
+                if not is_training and len(src) > 1:
                     # batchwise prompt selection + zero-padded means depend on the batch composition: keep the
                     # reference's one-clip-at-a-time result by selecting prompts per clip
                     parts = [self._prompted_text(text[i:i + 1, :, :int(tlens[i])], tlens[i:i + 1], False, task_id)
@@ -565,12 +581,7 @@ class PtTransformer(nn.Module):
         if is_training and not get_emb and torch.is_grad_enabled():
             return self._train_forward(video_list, task_id, prev_out_cls_logits)
         vl, logits, offsets, pmask, pyr = self._network(video_list, is_training, task_id)
-        if self.n_known > 0 and self.cl_name == "bic":  # BiasLayer on class slices (meta_archs.py:823-836)
-            parts, lo_ = [], 0
-            for i, hi_ in enumerate(self.list_splits):
-                parts.append(self.list_bias_layers[i](logits[:, :, lo_:hi_]))
-                lo_ = hi_
-            logits = torch.cat(parts, dim=2).contiguous()
+        logits = self._apply_bias_layers(logits)
         if get_emb:
             cls_l = [logits[:, o:o + n] for o, n in zip(pyr.off, pyr.lens)]
             off_l = [offsets[:, o:o + n] for o, n in zip(pyr.off, pyr.lens)]
@@ -590,6 +601,16 @@ class PtTransformer(nn.Module):
             return video_list, points, msk_l, cls_l, off_l
         return results
 
+    def _apply_bias_layers(self, logits):
+        """BiC: BiasLayer on the class slices of the logits, at training AND inference (meta_archs.py:823-836)"""
+        if self.n_known > 0 and self.cl_name == "bic" and len(self.list_splits) > 0:
+            parts, lo_ = [], 0
+            for i, hi_ in enumerate(self.list_splits):
+                parts.append(self.list_bias_layers[i](logits[:, :, lo_:hi_]))
+                lo_ = hi_
+            return torch.cat(parts, dim=2).contiguous()
+        return logits
+
     def _grad_sinks(self):
         """key -> fp32 view of the parameter's existing .grad in the kernels' packed layout, for the parameters whose
         packed layout equals the parameter layout (vectors, 1x1 convs, nn.Linear, XLNet o).  With a trainer the .grad
@@ -599,9 +620,9 @@ class PtTransformer(nn.Module):
         if getattr(self, "_sinks_sig", None) != sig:
             sinks = {}
             for k, p in zip(names, plist):
-                if p.grad is None or not p.requires_grad or not p.grad.is_contiguous() or p.grad.dtype != torch.float32 \
-                        or ".adapters." in k:
+                if p.grad is None or not p.requires_grad or not p.grad.is_contiguous() or p.grad.dtype != torch.float32:
                     continue
+                k = self._tape_key(k)           # adapters: the tape addresses them as pets.<i>.*
                 kind = E._pack_kind(k, p)
                 if kind == "vec" and p.dim() != 2:
                     sinks[k] = p.grad.view(-1)
@@ -673,11 +694,13 @@ class PtTransformer(nn.Module):
             logits = lg_biased.detach().contiguous()
             extra.append(dist)
             extra_named["dist_loss"] = dist.detach()
+        if self.train_label_smoothing > 0:
+            # the fused loss kernels derive the positive set from the targets they are given; the reference takes it from the
+            # UN-smoothed targets (meta_archs.py:1400) and smooths a copy — not built (no MQ config smooths: default 0.0)
+            raise NotImplementedError("train_cfg.label_smoothing > 0 is not supported by the fused loss kernels")
         gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
         with torch.no_grad():
             gt_cls, gt_off = gt_cls.detach(), gt_off.detach()
-            if self.train_label_smoothing > 0:
-                gt_cls = gt_cls * (1 - self.train_label_smoothing) + self.train_label_smoothing / (K + 1)
             present = torch.zeros(B, K)
             for i, x in enumerate(vl):
                 present[i, x["labels"].cpu()] = 1
@@ -718,7 +741,7 @@ class PtTransformer(nn.Module):
             known = getattr(self, "_live_keys", None)
             owned_names = {k_ for k_, _ in owned}
             for k_, p_ in zip(names_, plist_):
-                if not p_.requires_grad or k_.startswith("pets_emas.") or ".adapters." in k_:
+                if not p_.requires_grad or k_.startswith("pets_emas."):
                     continue
                 if k_ in owned_names or known is None or k_ in known:
                     live.append((k_, p_))
@@ -772,8 +795,10 @@ class PtTransformer(nn.Module):
             returned = {}
             with torch.no_grad():
                 tp.backward()
-                model._last_touch = (tp.n_nodes, dict(tp.touch), set(tp.G.keys()))
+                model._last_touch = (tp.n_nodes, {model._canon_key(k_): v_ for k_, v_ in tp.touch.items()},
+                                     {model._canon_key(k_) for k_ in tp.G.keys()})
                 for key, g in tp.G.items():
+                    key = model._canon_key(key)          # pets.<i>.* -> the registered (de-duplicated) parameter name
                     prm = named.get(key)
                     if prm is None or not prm.requires_grad:
                         continue
@@ -789,7 +814,7 @@ class PtTransformer(nn.Module):
                         prm.grad = g.clone()
                     else:
                         prm.grad.add_(g)
-                model._live_keys = set(tp.G.keys())
+                model._live_keys = {model._canon_key(k_) for k_ in tp.G.keys()} | {model._canon_key(k_) for k_ in tp.touch}
             glue = [(t_, g_) for t_, g_ in ((wc, dwc), (wl, dwl), (wr, dwr)) if t_.requires_grad]
             if tin is not None and text.requires_grad and tin.g is not None:
                 glue.append((text, ops.unpack(tin.g)))
@@ -932,9 +957,9 @@ class PtTransformer(nn.Module):
         `_train_forward`, whose result carries the hand-written backward."""
         dev = self.device
         B, P, K = logits.shape
-        gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
         if self.train_label_smoothing > 0:
-            gt_cls = gt_cls * (1 - self.train_label_smoothing) + self.train_label_smoothing / (K + 1)
+            raise NotImplementedError("train_cfg.label_smoothing > 0 is not supported by the fused loss kernels")
+        gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
         present = torch.zeros(B, K)
         for i, x in enumerate(vl):
             present[i, x["labels"].cpu()] = 1
@@ -954,6 +979,8 @@ class PtTransformer(nn.Module):
         al_loss = sums[3] / self.loss_normalizer if K != 1 else torch.zeros((), device=dev)
         loss_weight = self.train_loss_weight if self.train_loss_weight > 0 else float(cls_loss) / max(float(reg_loss), 0.01)
         final = cls_loss + reg_loss * loss_weight + al_loss * self.al_loss_weight
+        if self.n_known > 0 and self.cl_name == "l2p" and getattr(self, "_reduce_sim", None) is not None:
+            final = final - 0.1 * self._reduce_sim.detach()       # L2P pull constraint (meta_archs.py:1478-1480)
         out = {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final}
         if self.n_known > 0 and self.cl_name in ("bic", "icarl"):
             # distillation against the previous task's outputs (meta_archs.py:1482-1519); forward() already applied the BiC
@@ -964,8 +991,10 @@ class PtTransformer(nn.Module):
 
     # ---- inference (reference: meta_archs.py:1527-1736) ---------------------------------------------
     @torch.no_grad()
-    def _decode_nms_device(self, pyr, pmask, logits, offsets):
-        """decode + NMS kernels; returns device tensors (segs (B,M,2), scores (B,M), labels (B,M) i64, count (B,) i32)."""
+    def _decode_device(self, pyr, pmask, logits, offsets):
+        """decode kernel (sigmoid * mask -> threshold -> top-k per level -> segments -> duration filter, meta_archs.py:1594-1692):
+        candidates per (clip, level) region of `pre_nms_topk` slots, sorted by score inside a region.
+        Returns (cand_segs (B, nl*topk, 2), cand_scores (B, nl*topk), cand_labels (B, nl*topk) i32, cand_count (B, nl) i32)."""
         B, P, K = logits.shape
         dev = logits.device
         nl, topk = len(pyr.lens), int(self.test_pre_nms_topk)
@@ -979,6 +1008,15 @@ class PtTransformer(nn.Module):
             FltArr(*[float(s) for s in self.fpn_strides]), C.c_float(self.test_pre_nms_thresh),
             C.c_float(self.test_duration_thresh), topk, ops._p(cand_segs), ops._p(cand_scores), ops._p(cand_labels),
             ops._p(cand_count), L.stream_ptr()), "vilco_decode")
+        return cand_segs, cand_scores, cand_labels, cand_count
+
+    @torch.no_grad()
+    def _decode_nms_device(self, pyr, pmask, logits, offsets):
+        """decode + NMS kernels; returns device tensors (segs (B,M,2), scores (B,M), labels (B,M) i64, count (B,) i32)."""
+        B, P, K = logits.shape
+        dev = logits.device
+        nl, topk = len(pyr.lens), int(self.test_pre_nms_topk)
+        cand_segs, cand_scores, cand_labels, cand_count = self._decode_device(pyr, pmask, logits, offsets)
         if self.test_nms_method == "none":   # no NMS: every decoded candidate, level-major (meta_archs.py:1711)
             cnt = cand_count.cpu()
             M = int(cnt.sum(1).max())
@@ -1147,7 +1185,8 @@ class EvalGraph:
     def _weights_sig(self):
         m = self.model
         W = m.packed_weights()
-        return (id(W), m._packed_key, getattr(m, "_packed_epoch", 0), getattr(m, "_packed_ema_key", None))
+        return (id(W), m._packed_key, getattr(m, "_packed_epoch", 0), getattr(m, "_packed_ema_key", None),
+                m.n_known, tuple(m.list_splits), tuple(id(b) for b in m.list_bias_layers))
 
     def _capture(self):
         """(Re)capture the graph against the model's current packed weights."""
@@ -1173,6 +1212,7 @@ class EvalGraph:
     def _step(self):
         m = self.model
         logits, offsets, pmask, pyr = m._device_forward(self.feats, self.mask, self.text, self.tmask, self.tlens, False)
+        logits = m._apply_bias_layers(logits)      # BiC (captured torch ops reading the live alpha / beta parameters)
         return m._decode_nms_device(pyr, pmask, logits, offsets)
 
     @staticmethod

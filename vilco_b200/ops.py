@@ -14,8 +14,10 @@ Precision modes (`set_precision`, env VILCO_PRECISION):
   "bf16x3"  bf16 planes, every operand split (round 1's parity mode, ~1e-5)
   "fp16" / "bf16"  one plane everywhere (1.3e-3 / 1e-2 at the full config: above the bar, kept for comparison)
 
-Gradient planes (the 16-bit operands the backward kernels emit) are always bf16 — gradient magnitudes do not fit the fp16
-range — in two planes unless VILCO_BWD_PRECISION=bf16.
+Gradient planes (the 16-bit operands the backward kernels emit) share the activation format — tcgen05 kind::f16 cannot mix
+fp16 and bf16 operands in one MMA (measured: illegal instruction).  In the fp16 modes they are stored multiplied by
+GRAD_SCALE = 2^10, which centres gradient magnitudes in the fp16 range (normal from 6e-8 / 2^10, saturating at 64), and every
+GEMM that consumes one folds 1 / GRAD_SCALE into its alpha (`ginv()`); two planes unless VILCO_BWD_PRECISION=bf16.
 """
 import ctypes as C
 import os
@@ -34,18 +36,21 @@ _MODES = {  # name -> (activation plane dtype, default planes, planes of the sen
 }
 _mode = None
 ACT_DTYPE, PLANES, PLANES_HI = bf16, 2, 2
+GRAD_SCALE = 1.0
 FUSED_ATTN = os.environ.get("VILCO_FUSED_ATTN", "1") == "1"  # 0: materialised QK^T -> softmax -> PV kernels
 
 
 def set_precision(name):
     """Select the operand-format policy (see the module docstring).  Weights must be re-packed after a change (the model
     does so: its packed-weight cache is keyed on `precision()`)."""
-    global _mode, ACT_DTYPE, PLANES, PLANES_HI
+    global _mode, ACT_DTYPE, PLANES, PLANES_HI, GRAD_SCALE
     assert name in _MODES, name
     _mode = name
     ACT_DTYPE, PLANES, PLANES_HI = _MODES[name]
-    if os.path.exists(L.LIB_PATH):   # the library holds the plane format the non-GEMM kernels read / write
+    GRAD_SCALE = float(2 ** int(os.environ.get("VILCO_GRAD_SCALE_LOG2", "10"))) if ACT_DTYPE == f16 else 1.0
+    if os.path.exists(L.LIB_PATH):   # the library holds the plane format / gradient scale the non-GEMM kernels use
         L.check(L.lib().vilco_set_plane_format(L.F16 if ACT_DTYPE == f16 else L.BF16), "vilco_set_plane_format")
+        L.check(L.lib().vilco_set_grad_scale(C.c_float(GRAD_SCALE)), "vilco_set_grad_scale")
 
 
 def precision():
@@ -91,16 +96,21 @@ def grad_planes():
     return 1 if BWD_PRECISION == "bf16" else 2
 
 
+def ginv():
+    """factor that undoes the scale of a gradient-plane operand: multiply the alpha of every GEMM reading one by it"""
+    return 1.0 / GRAD_SCALE
+
+
 def empty16(*shape, device="cuda", planes=None, grad=False):
-    """uninitialised operand tensor (planes, *shape): activation format, or bf16 when it will hold a gradient"""
+    """uninitialised operand tensor (planes, *shape); grad: it will hold a (scaled) gradient"""
     if grad:
-        return torch.empty(grad_planes() if planes is None else planes, *shape, device=device, dtype=bf16)
+        return torch.empty(grad_planes() if planes is None else planes, *shape, device=device, dtype=ACT_DTYPE)
     return torch.empty(PLANES if planes is None else planes, *shape, device=device, dtype=ACT_DTYPE)
 
 
 def zeros16(*shape, device="cuda", planes=None, grad=False):
     if grad:
-        return torch.zeros(grad_planes() if planes is None else planes, *shape, device=device, dtype=bf16)
+        return torch.zeros(grad_planes() if planes is None else planes, *shape, device=device, dtype=ACT_DTYPE)
     return torch.zeros(PLANES if planes is None else planes, *shape, device=device, dtype=ACT_DTYPE)
 
 
@@ -168,7 +178,7 @@ def attn_scores(q, k, H, alpha, band=(0, 0)):
     return out
 
 
-def attn_pv(P, v, H, Tk, out32=False, a_trans=False, M=None):
+def attn_pv(P, v, H, Tk, out32=False, a_trans=False, M=None, alpha=1.0):
     """O[b, :, h*d:(h+1)*d] = P[b,h] v_h.  P (NP,B,H,Tq,ldp), v (NP,B,Tk,C) -> operand (NP,B,Tq,C) (fp32 (B,Tq,C) if out32).
     a_trans: use P[b,h]^T instead — P is (NP,B,H,Tk,ldp) with M <= ldp valid columns, read as an MN-major A operand (no
     transposed copy), result (B,M,C)."""
@@ -180,7 +190,7 @@ def attn_pv(P, v, H, Tk, out32=False, a_trans=False, M=None):
     out = torch.empty(B, Tq, Cc, device=v.device, dtype=f32) if out32 else empty16(B, Tq, Cc, device=v.device)
     L.gemm(P, v, out, M=Tq, N=d, K=Tk, a_rows=Tq, a_ld=ldp, a_s=(R * ldp, H * R * ldp), Z=(H, B), b_ld=Cc,
            b_s=(d, Tk * Cc), b_batched=True, b_major=1, d_ld=Cc, d_s=(d, Tq * Cc), a_lo=lo(P), b_lo=lo(v),
-           d_lo=0 if out32 else lo(out), a_major=1 if a_trans else 0)
+           d_lo=0 if out32 else lo(out), a_major=1 if a_trans else 0, alpha=alpha)
     return out
 
 
@@ -339,19 +349,20 @@ def channel_attention_bwd(dy, qkv, A16, H):
     dy16 = dy16.reshape(dy16.shape[0], B, T, Cc)
     dqkv = torch.empty(B, T, C3, device=dy.device, dtype=f32)
     dA = torch.empty(B, H, 64, 64, device=dy.device, dtype=f32)
+    gi = ginv()     # dy16 / dG16 are gradient planes (stored times GRAD_SCALE)
     # dA[i, j] = sum_t dy[t, i] q[t, j]
     L.gemm(dy16, q, dA, M=64, N=64, K=T, a_rows=64, a_ld=Cc, a_s=(64, T * Cc), a_major=1, Z=(H, B), b_ld=C3, b_s=(64, T * C3),
-           b_batched=True, b_major=1, d_ld=64, d_s=(64 * 64, H * 64 * 64), a_lo=lo(dy16), b_lo=lo(qkv))
+           b_batched=True, b_major=1, d_ld=64, d_s=(64 * 64, H * 64 * 64), a_lo=lo(dy16), b_lo=lo(qkv), alpha=gi)
     # dq[t, j] = sum_i dy[t, i] A[i, j]
     L.gemm(dy16, A16, dqkv, M=T, N=64, K=64, a_rows=T, a_ld=Cc, a_s=(64, T * Cc), Z=(H, B), b_ld=64, b_s=(64 * 64, H * 64 * 64),
-           b_batched=True, b_major=1, d_ld=C3, d_s=(64, T * C3), a_lo=lo(dy16), b_lo=lo(A16))
+           b_batched=True, b_major=1, d_ld=C3, d_s=(64, T * C3), a_lo=lo(dy16), b_lo=lo(A16), alpha=gi)
     _, dG16 = BW.softmax_bwd(dA, 1.0, P16=A16)                            # dG = A * (dA - rowsum(dA * A)) as planes
     # dk[t, i] = (1/8) sum_j v[t, j] dG[i, j]
     L.gemm(v, dG16, dqkv[..., Cc:2 * Cc], M=T, N=64, K=64, a_rows=T, a_ld=C3, a_s=(64, T * C3), Z=(H, B), b_ld=64,
-           b_s=(64 * 64, H * 64 * 64), b_batched=True, d_ld=C3, d_s=(64, T * C3), alpha=0.125, a_lo=lo(qkv), b_lo=lo(dG16))
+           b_s=(64 * 64, H * 64 * 64), b_batched=True, d_ld=C3, d_s=(64, T * C3), alpha=0.125 * gi, a_lo=lo(qkv), b_lo=lo(dG16))
     # dv[t, j] = (1/8) sum_i k[t, i] dG[i, j]
     L.gemm(k, dG16, dqkv[..., 2 * Cc:], M=T, N=64, K=64, a_rows=T, a_ld=C3, a_s=(64, T * C3), Z=(H, B), b_ld=64,
-           b_s=(64 * 64, H * 64 * 64), b_batched=True, b_major=1, d_ld=C3, d_s=(64, T * C3), alpha=0.125, a_lo=lo(qkv),
+           b_s=(64 * 64, H * 64 * 64), b_batched=True, b_major=1, d_ld=C3, d_s=(64, T * C3), alpha=0.125 * gi, a_lo=lo(qkv),
            b_lo=lo(dG16))
     return dqkv
 

@@ -451,9 +451,10 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
     def bwd():
         if vec.g is None:
             return
+        gi = ops.ginv()                                        # gradient planes are stored times GRAD_SCALE
         dvec16, _ = BW.to_planes(vec.g.reshape(-1, C))
         dvec16 = dvec16.reshape(dvec16.shape[0], B, T, C)
-        dP = ops.attn_scores(dvec16, v16, H, 1.0)
+        dP = ops.attn_scores(dvec16, v16, H, gi)
         if seed is not None:
             ops.dropout(dP, pd, seed, out=dP)
         dS, dS16 = BW.softmax_bwd(dP, scale, P32=P32, want32=True)
@@ -462,12 +463,12 @@ def xlnet_layer(tp, pre, x, mask, H, eps=1e-12):
         L.check(L.lib().vilco_relshift_bwd(_p(dS), None, _p(dBD16), _i64(lo(dBD16)), _i64(B * H), T, L.stream_ptr()),
                 "vilco_relshift_bwd")
         del dS
-        tp.acc(qw, ops.attn_pv(dS16, k16, H, T, out32=True))
-        tp.acc(k, ops.attn_pv(dS16, qw16, H, T, out32=True, a_trans=True))        # dS^T qw: dS read as MN-major A
+        tp.acc(qw, ops.attn_pv(dS16, k16, H, T, out32=True, alpha=gi))
+        tp.acc(k, ops.attn_pv(dS16, qw16, H, T, out32=True, a_trans=True, alpha=gi))        # dS^T qw: dS read as MN-major A
         del dS16
-        tp.acc(v, ops.attn_pv(P16, dvec16, H, T, out32=True, a_trans=True))       # P^T dvec
-        tp.acc(qr, ops.attn_pv(dBD16, kr16, H, 2 * T, out32=True))
-        tp.acc(krel, ops.attn_pv(dBD16, qr16, H, T, out32=True, a_trans=True))    # dBD^T qr -> (B, 2T, C)
+        tp.acc(v, ops.attn_pv(P16, dvec16, H, T, out32=True, a_trans=True, alpha=gi))       # P^T dvec
+        tp.acc(qr, ops.attn_pv(dBD16, kr16, H, 2 * T, out32=True, alpha=gi))
+        tp.acc(krel, ops.attn_pv(dBD16, qr16, H, T, out32=True, a_trans=True, alpha=gi))    # dBD^T qr -> (B, 2T, C)
         if krel1 is not None:                                  # krel is the batch broadcast of krel1
             g1 = krel.g[0]
             for b in range(1, B):

@@ -217,16 +217,19 @@ def make_optimizer(model, optimizer_config, flat=False):
     late = lambda n: _pack_kind(n, pd[n]) in ("conv3", "dw", "xl_t") or pd[n].dim() == 0 or pd[n].dim() == 2 and pd[n].shape[1] == 1  # noqa: E731
     # (permuted layouts, Scale scalars and mu / sigma get their gradients at the very end of the backward pass: keep them
     # together behind the parameters whose gradients the kernels write in place)
-    order = (lambda names: sorted(names, key=lambda n: (late(n), -pos[n]))) if flat else sorted
-    groups = [{"params": [pd[n] for n in order(decay)], "weight_decay": wd},
-              {"params": [pd[n] for n in order(no_decay)], "weight_decay": 0.0},
-              {"params": [pd[n] for n in order(remain)], "weight_decay": wd}]
+    # the GROUPS list their parameters alphabetically in both paths — optimizer.state_dict() indexes the state by position in
+    # the groups, so checkpoints of FlatAdamW and torch.optim.AdamW are interchangeable; the flat path only uses the
+    # backward-completion order for where a parameter LIVES in the flat buffers (`layout_order`)
+    groups = [{"params": [pd[n] for n in sorted(decay)], "weight_decay": wd},
+              {"params": [pd[n] for n in sorted(no_decay)], "weight_decay": 0.0},
+              {"params": [pd[n] for n in sorted(remain)], "weight_decay": wd}]
     groups = [g for g in groups if g["params"]]
+    layout_order = {id(pd[n]): (late(n), -pos[n]) for n in pd}
     if optimizer_config["type"] == "SGD":
         return torch.optim.SGD(groups, lr=optimizer_config["learning_rate"], momentum=optimizer_config["momentum"])
     if optimizer_config["type"] == "AdamW":
         if flat:
-            return FlatAdamW(groups, lr=optimizer_config["learning_rate"])
+            return FlatAdamW(groups, lr=optimizer_config["learning_rate"], layout_order=layout_order)
         return torch.optim.AdamW(groups, lr=optimizer_config["learning_rate"])
     raise TypeError("Unsupported optimizer!")
 
@@ -241,8 +244,11 @@ class FlatAdamW(torch.optim.Optimizer):
     read (`self.planes`), so no per-tensor weight re-packing happens between iterations.
     """
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, layout_order=None):
+        """layout_order: id(param) -> sort key of its position inside its group's segment of the flat buffers (default: the
+        order of the group's list).  It never affects state_dict(): the state is indexed by the position in the groups."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._layout_order = layout_order or {}
         dev = next(p for g in self.param_groups for p in g["params"]).device
         assert dev.type == "cuda", "FlatAdamW runs on the CUDA kernels only"
         self.device = dev
@@ -272,6 +278,9 @@ class FlatAdamW(torch.optim.Optimizer):
                 if p.requires_grad and id(p) not in seen:
                     seen.add(id(p))
                     ps.append(p)
+            if self._layout_order:
+                rank = {id(p): i for i, p in enumerate(ps)}
+                ps.sort(key=lambda p: (self._layout_order.get(id(p), (True, 0)), rank[id(p)]))
             for p in ps:
                 if id(p) not in dead:
                     slots[id(p)] = (n, p.numel())
