@@ -3,7 +3,8 @@
 The headline `value` is inference; the training half of the metric is the `train` object of the same JSON line.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation of the same path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's OWN modules on the host cores (baseline/_ref)
+    python bench.py --metric train ...                       # same run, the training half reported as the headline value
 
 A step = one batch of `--batch` synthetic clips (features N(0,1) of shape (4096, 1024), CLIP-token text (768, L),
 mq_no_cl.yaml model, K=22 classes, random-init weights -> worst-case NMS load) through
@@ -114,98 +115,113 @@ def build_model(K=22):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU baseline = the oracle port of the reference's path (oracle/_ref NMS extension when loadable), all host threads
+# Baselines: the REFERENCE's own modules (un-modified MQ tree under baseline/_ref or /root/reference, imported through
+# oracle/ref_shim.py, soft-NMS = its own nms_cpu.cpp compiled into oracle/_ref) — "kind": "reference"; when that tree is not
+# there, the oracle port of the same path — "kind": "port".  Never on the product path.
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(state_dict, n_videos, seed=7):
-    from oracle import mq_oracle as O
-    from oracle import nms_c
-    torch.set_num_threads(os.cpu_count() or 1)
-    cfg = O.ModelCfg()
-    P = {k: v.detach().float().cpu() for k, v in state_dict.items() if torch.is_floating_point(v)}
-    vids = synth_videos(n_videos + 1, seed)
-    with torch.no_grad():
-        O.model_infer(P, cfg, vids[:1], softnms_fn=nms_c.softnms_1d)  # warm-up
-        t0 = time.perf_counter()
-        O.model_infer(P, cfg, vids[1:], softnms_fn=nms_c.softnms_1d)
-        dt = time.perf_counter() - t0
-    return n_videos / dt, dt
-
-
-def cpu_reference_train_rate(state_dict, n_videos, seed=11):
-    """One optimisation step of the oracle (torch CPU autograd + torch AdamW) on n_videos clips."""
-    from oracle import mq_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    cfg = O.ModelCfg()
-    spec_ok = lambda k, v: torch.is_floating_point(v) and not k.startswith("backbone.xlnet.word_embedding")  # noqa: E731
-    P = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in state_dict.items() if spec_ok(k, v)}
-    opt = torch.optim.AdamW(list(P.values()), lr=1e-4, weight_decay=0.05)
-    vids = synth_videos(n_videos, seed)
-    t0 = time.perf_counter()
-    opt.zero_grad()
-    lo, _ = O.model_train_losses(P, cfg, vids)
-    lo["final_loss"].backward()
-    torch.nn.utils.clip_grad_norm_([p for p in P.values() if p.grad is not None], 1.0)
-    opt.step()
-    dt = time.perf_counter() - t0
-    return n_videos / dt, dt
-
-
-def eager_gpu_rates(state_dict, tf32, n_inf=8, n_train=2):
-    """The same restatement run as eager PyTorch fp32 ON THE B200 (what running the reference's own modules on the GPU
-    amounts to: cuDNN / cuBLAS kernels behind torch ops, batch-1 evaluation, soft-NMS on the host like nms_cpu.cpp).
-    A reported baseline like cpu_baseline; the oracle is only executed here as the thing compared against."""
-    from oracle import mq_oracle as O
-    from oracle import nms_c
-    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
-    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
-    cfg = O.ModelCfg()
-    ok = lambda k, v: torch.is_floating_point(v) and not k.startswith("backbone.xlnet.word_embedding")  # noqa: E731
-    P = {k: v.detach().float().cuda().clone() for k, v in state_dict.items() if ok(k, v)}
-    orig_pe = O.sinusoid_pe
-    O.sinusoid_pe = lambda *a: orig_pe(*a).cuda()
+def reference_model(device="cpu"):
+    """(callable infer(video) -> result, callable train_step(videos) -> None, kind, description)"""
     try:
-        with torch.device("cuda"):
+        from oracle import ref_shim
+        if ref_shim.available():
+            torch.manual_seed(0)
+            model, _ = ref_shim.build_model(None, "mq_no_cl.yaml")
+            model = model.to(device).eval()
+            opt = [None]
+
             def infer(v):
-                x, mask, text, tmask = O.preprocess(cfg, [v], False)
                 with torch.no_grad():
-                    logits, offs, masks, _ = O.forward_heads(P, cfg, x, mask, text, tmask, training=False)
-                    pts = O.points(cfg, [m.shape[1] for m in masks])
-                    segs, scores, labels = O.decode_single_video(cfg, pts, [m[0] for m in masks], [l[0] for l in logits],
-                                                                 [o[0] for o in offs])
-                return O.postprocess(cfg, segs.cpu(), scores.cpu(), labels.cpu(), v["fps"], v["duration"], v["feat_stride"],
-                                     v["feat_num_frames"], nms_c.softnms_1d)
-            vids = synth_videos(n_inf + 1, 21)
-            infer(vids[0])
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for v in vids[1:]:
-                infer(v)
-            torch.cuda.synchronize()
-            inf_rate = n_inf / (time.perf_counter() - t0)
+                    return model([v], is_training=False)[0]
+
+            def train_step(vs):
+                if opt[0] is None:
+                    opt[0] = torch.optim.AdamW([q for q in model.parameters() if q.requires_grad], lr=1e-4, weight_decay=0.05)
+                model.train()
+                opt[0].zero_grad()
+                model(vs, is_training=True)["final_loss"].backward()
+                torch.nn.utils.clip_grad_norm_([q for q in model.parameters() if q.grad is not None], 1.0)
+                opt[0].step()
+                model.eval()
+            return infer, train_step, "reference", "the reference's PtTransformer (MQ/libs/modeling, mq_no_cl.yaml) + its nms_cpu.cpp"
+    except Exception as e:   # a baseline must never take the bench down
+        print(f"[bench] reference modules unavailable ({e!r}); using the oracle port", file=sys.stderr)
+    from oracle import mq_oracle as O
+    from oracle import nms_c
+    cfg = O.ModelCfg()
+    sd = build_model().state_dict()
+    P = {k: v.detach().float().to(device).clone() for k, v in sd.items()
+         if torch.is_floating_point(v) and not k.startswith("backbone.xlnet.word_embedding")}
+    opt = [None]
+    if device != "cpu":
+        orig_pe = O.sinusoid_pe
+        O.sinusoid_pe = lambda *a: orig_pe(*a).to(device)
+
+    def infer(v):
+        with torch.no_grad(), torch.device(device):
+            x, mask, text, tmask = O.preprocess(cfg, [v], False)
+            logits, offs, masks, _ = O.forward_heads(P, cfg, x.to(device), mask.to(device), text.to(device), tmask.to(device), training=False)
+            pts = [q.to(device) for q in O.points(cfg, [m.shape[1] for m in masks])]
+            segs, scores, labels = O.decode_single_video(cfg, pts, [m[0] for m in masks], [l[0] for l in logits], [o[0] for o in offs])
+        return O.postprocess(cfg, segs.cpu(), scores.cpu(), labels.cpu(), v["fps"], v["duration"], v["feat_stride"],
+                             v["feat_num_frames"], nms_c.softnms_1d)
+
+    def train_step(vs):
+        if opt[0] is None:
             for q in P.values():
                 q.requires_grad_(True)
-            opt = torch.optim.AdamW(list(P.values()), lr=1e-4, weight_decay=0.05)
-            tv = synth_videos(n_train, 22)
-            for v in tv:
-                v["segments"], v["labels"] = v["segments"].cuda(), v["labels"].cuda()
+            opt[0] = torch.optim.AdamW(list(P.values()), lr=1e-4, weight_decay=0.05)
+        opt[0].zero_grad()
+        with torch.device(device):
+            vv = [{**v, "feats": v["feats"].to(device), "prompt_feature": v["prompt_feature"].to(device),
+                   "segments": v["segments"].to(device), "labels": v["labels"].to(device)} for v in vs]
+            lo, _ = O.model_train_losses(P, cfg, vv)
+        lo["final_loss"].backward()
+        torch.nn.utils.clip_grad_norm_([q for q in P.values() if q.grad is not None], 1.0)
+        opt[0].step()
+    return infer, train_step, "port", "oracle/mq_oracle.py (torch restatement of the reference path) + oracle/softnms.c"
 
-            def train_step():
-                opt.zero_grad()
-                lo, _ = O.model_train_losses(P, cfg, tv)
-                lo["final_loss"].backward()
-                torch.nn.utils.clip_grad_norm_([q for q in P.values() if q.grad is not None], 1.0)
-                opt.step()
-            train_step()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                train_step()
-            torch.cuda.synchronize()
-            tr_rate = 3 * n_train / (time.perf_counter() - t0)
+
+def cpu_baseline_leg(n_videos, seed=7):
+    """bounded sample on the box's host cores: n_videos clips, one at a time like the reference's evaluation loop"""
+    torch.set_num_threads(os.cpu_count() or 1)
+    infer, _, kind, what = reference_model("cpu")
+    vids = synth_videos(n_videos + 1, seed)
+    infer(vids[0])                                  # warm-up
+    t0 = time.perf_counter()
+    for v in vids[1:]:
+        infer(v)
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    return {"value": n_videos / dt, "unit": "videos/s", "cores": cores, "kind": kind,
+            "sample": f"{n_videos} clips, one per call, through {what}; torch CPU fp32, {cores} threads, incl. soft-NMS; {dt:.1f} s"}
+
+
+def eager_gpu_rates(tf32, n_inf=6, n_train=2):
+    """The reference's own modules run as eager PyTorch fp32 ON THE B200 (cuDNN / cuBLAS kernels behind torch ops, batch-1
+    evaluation, soft-NMS on the host through its nms_cpu.cpp): the practical bar a GPU user of the reference has today."""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+    try:
+        infer, train_step, kind, _ = reference_model("cuda")
+        vids = synth_videos(n_inf + 1, 21)
+        infer(vids[0])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for v in vids[1:]:
+            infer(v)
+        torch.cuda.synchronize()
+        inf_rate = n_inf / (time.perf_counter() - t0)
+        tv = synth_videos(n_train, 22)
+        train_step(tv)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            train_step(tv)
+        torch.cuda.synchronize()
+        tr_rate = 3 * n_train / (time.perf_counter() - t0)
     finally:
-        O.sinusoid_pe = orig_pe
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
-    return inf_rate, tr_rate
+    return inf_rate, tr_rate, kind
 
 
 def next_rows():
@@ -277,30 +293,76 @@ def next_rows():
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, all threads.  EXACTLY
+    `--warmup` untimed + `--steps` timed steps are run; a step = a bounded sample (`--ref-videos` clips, evaluated one per call
+    as the reference's loop does) of our arm's step, so that the whole run ends within a few minutes.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    model = build_model()
-    n = max(1, args.ref_videos)
-    vals = []
-    for _ in range(args.warmup and 0):  # the oracle call itself contains one warm-up video
-        pass
-    for s in range(max(1, min(args.steps, 3))):
-        rate, dt = cpu_reference_rate(model.state_dict(), n, seed=7 + s)
-        vals.append(rate)
-    v = float(np.median(vals))
+    torch.set_num_threads(os.cpu_count() or 1)
     cores = os.cpu_count() or 1
-    tr_rate, tr_dt = cpu_reference_train_rate(model.state_dict(), 2)
+    n = max(1, args.ref_videos)
+    infer, train_step, kind, what = reference_model("cpu")
+    vids = synth_videos(n * 2, seed=7)
+    for i in range(args.warmup):
+        for v in vids[:n]:
+            infer(v)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        for v in vids[(i % 2) * n:(i % 2) * n + n]:
+            infer(v)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    t1 = time.perf_counter()
+    train_step(synth_videos(2, seed=11))
+    tr_dt = time.perf_counter() - t1
+    sample = (f"{n} clip(s) per step, one per call, through {what}; torch CPU fp32, {cores} threads, incl. soft-NMS; "
+              f"{args.warmup} warm-up + {args.steps} timed steps, {dt:.1f} s timed")
     line = {"impl": "reference", "metric": "mq_infer_videos_per_s", "value": v, "unit": "videos/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "videos_per_step": n},
-            "cpu_baseline": {"value": v, "unit": "videos/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} clip(s) per step through oracle/mq_oracle.py (torch CPU fp32, {cores} threads) incl. soft-NMS (oracle/softnms.c)"},
+            "config": bench_config(args, reference_sample=n),
+            "cpu_baseline": {"value": v, "unit": "videos/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "train": {"metric": "mq_train_videos_per_s", "value": tr_rate, "unit": "videos/s", "videos_per_step": 2,
-                      "sample": f"1 step (forward, loss, autograd backward, clip, AdamW) of 2 clips through the oracle on {cores} threads, {tr_dt:.1f} s"}}
+            "train_value": 2 / tr_dt,
+            "train": {"metric": "mq_train_videos_per_s", "value": 2 / tr_dt, "unit": "videos/s", "videos_per_step": 2,
+                      "sample": f"1 un-warmed step (forward, loss, autograd backward, clip, AdamW) of 2 clips, {tr_dt:.1f} s"}}
     print(json.dumps(line), flush=True)
+
+
+def bench_config(args, reference_sample=None):
+    """the `config` object: identical in both arms"""
+    from vilco_b200 import ops
+    modes = {"mixed": "fp16 operand planes, fp32 accumulate; one plane (1 tcgen05.mma per k-step) except the input projection, "
+                      "embedding convs and channel-attention qkv / core (split operands, 3 MMAs): logits / offsets within 1e-3",
+             "fp16x3": "fp16 hi+lo planes everywhere (3 MMAs per k-step, ~1e-5)", "bf16x3": "bf16 hi+lo planes everywhere (3 MMAs, ~1e-5)",
+             "fp16": "fp16 single planes everywhere", "bf16": "bf16 single planes everywhere"}
+    c = {"workload": WORKLOAD, "videos_per_step_per_gpu": args.batch, "precision": ops.precision() + ": " + modes[ops.precision()],
+         "l2": "working set per step (packed weights 0.9 GB + activations) exceeds the 126 MB L2; no explicit flush",
+         "train_videos_per_step_per_gpu": args.train_batch}
+    if reference_sample is not None:
+        c["reference_sample_videos_per_step"] = reference_sample
+    return c
+
+
+def verify_against_oracle(model, video):
+    """clip 0 of the bench batch, outside the timed region: head outputs vs the fp32 oracle, and the decode + soft-NMS kernels
+    vs the reference algorithm on the CUDA path's own head outputs (tests/util.kernel_parity_on_own_outputs)"""
+    from oracle import mq_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import kernel_parity_on_own_outputs, rel_max
+    cfg = O.ModelCfg()
+    P = {k: v.detach().float().cpu() for k, v in model.state_dict().items() if torch.is_floating_point(v)}
+    cls_l, off_l, _ = model([video], is_training=False, get_emb=True)
+    with torch.no_grad():
+        x, mask, text, tmask = O.preprocess(cfg, [video], False)
+        lg, of, _, _ = O.forward_heads(P, cfg, x, mask, text, tmask, training=False)
+    kp = kernel_parity_on_own_outputs(cfg, model, video)
+    return {"logits_rel_err": rel_max(torch.cat(cls_l, 1)[0].cpu(), torch.cat(lg, 1)[0]),
+            "offsets_rel_err": rel_max(torch.cat(off_l, 1)[0].cpu(), torch.cat(of, 1)[0]),
+            "decode_nms_vs_reference_algorithm": {k: kp[k] for k in ("cand_count", "cand_count_oracle", "score", "rank_swaps", "seg", "orphans")},
+            "against": "oracle/mq_oracle.py fp32 on the host (pinned to the reference's outputs by tests/golden/model_full.npz), "
+                       "random-init weights, clip 0 of the timed batch; bar 1e-3"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -425,13 +487,18 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="clips per step per GPU")
     ap.add_argument("--train-batch", type=int, default=32, help="clips per training step per GPU (0 = skip the training leg)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--metric", default="infer", choices=["infer", "train"], help="which half of the metric is the line's `value`")
     ap.add_argument("--precision", default=None, choices=[None, "mixed", "fp16x3", "fp16", "bf16x3", "bf16"])
-    ap.add_argument("--ref-videos", type=int, default=24, help="clips per CPU-baseline sample (about 10 s on 16 host threads)")
+    ap.add_argument("--ref-videos", type=int, default=None,
+                    help="clips per step of the reference arm (default 2) / of the cpu_baseline sample of our arm (default 12)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
+        args.ref_videos = args.ref_videos or 2
         return run_reference_arm(args)
+    args.ref_videos = args.ref_videos or 12
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -463,7 +530,6 @@ def main():
     sampler = ClockSampler(local, enabled=rank == 0)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n0 = L.launch_count()
     e0.record()
     for _ in range(args.steps):
         g.replay()
@@ -496,21 +562,17 @@ def main():
     fl, tg, nl = gemm_roofline(g, model, B)
     top = gemm_roofline.top
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         key = "x".join(str(top["shape"][k]) for k in ("M", "N", "K", "taps", "Z")) + ":" + ops.precision()
         traffic = tj.get(key)
-    roof = {"bound": "tensor", "kernel": "vilco::gemm_tc_kernel — the GEMM shape with the largest share of the step",
+    roof = {"bound": "tensor", "kernel": "vilco::gemm_tc_kernel<256,2> (CTA-pair tcgen05 GEMM): the shape with the largest share of the step",
             "shape": top["shape"], "launches_per_step": top["launches"], "us_per_launch": top["us_per_launch"],
             "achieved": top["tflops"], "peak": tf_sus, "unit": "TFLOP/s", "frac": top["tflops"] / tf_sus,
-            "traffic": traffic, "peak_source": f"bf16_tflops_sustained of {how}",
+            "traffic": traffic, "peak_source": f"bf16_tflops_sustained of {how} (cuBLAS bf16 = the same tensor rate as fp16)",
             "algorithmic_flop_per_launch": top["flop_per_launch"],
-            "mma_per_algorithmic_mac": 3 if ops.precision() == "bf16x3" else 1,
-            "tensor_pipe_frac": top["tflops"] * (3 if ops.precision() == "bf16x3" else 1) / tf_sus,
-            "all_gemm_launches": {"launches": nl, "achieved": fl / tg / 1e12, "share_of_step": tg / (t_dev / args.steps)},
-            "note": "algorithmic FLOPs (2*M*N*K*taps*Z); bf16x3 executes 3 tcgen05.mma per algorithmic MAC, so 1/3 of the "
-                    "tensor peak is the ceiling of this figure in the default precision"}
+            "all_gemm_launches": {"launches": nl, "achieved": fl / tg / 1e12, "share_of_step": tg / (t_dev / args.steps)}}
     # latency of the reference's own evaluation mode (one clip per call)
     g1 = model.make_eval_graph(1)
     g1.load_inputs(vids[:1])
@@ -525,6 +587,12 @@ def main():
     torch.cuda.synchronize()
     lat_b1 = l0.elapsed_time(l1) / 10
     launches_inf = int(g.launches * args.steps)
+    verify = None
+    if rank == 0 and not args.no_verify:
+        try:
+            verify = verify_against_oracle(model, vids[0])
+        except Exception as e:
+            verify = {"failed": repr(e)[:300]}
     del g, g1          # release the CUDA-graph memory pools before the training leg
     import gc
     gc.collect()
@@ -533,44 +601,53 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return
+    infer_value, infer_ms = world * B * args.steps / t_dev, 1e3 * t_dev / args.steps
+    e2e_inf = {"value": world * B * args.steps / t_e2e, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    head = {"metric": "mq_infer_videos_per_s", "value": infer_value, "unit": "videos/s", "ms_per_step": infer_ms, "e2e": e2e_inf,
+            "gpu_launches": launches_inf}
+    if args.metric == "train" and train is not None:
+        head = {"metric": "mq_train_videos_per_s", "value": train["value"], "unit": "videos/s", "ms_per_step": train["ms_per_step"],
+                "e2e": train["e2e"], "gpu_launches": int(train["gpu_launches_per_step"] * args.steps)}
     line = {
-        "metric": "mq_infer_videos_per_s", "value": world * B * args.steps / t_dev, "unit": "videos/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "videos_per_step_per_gpu": B,
-                   "precision": "bf16x3: bf16 hi+lo operand planes, 3 tcgen05.mma per k-step, fp32 accumulate (parity mode)" if ops.precision() == "bf16x3" else "bf16 single plane (fast mode, ~4e-3 rel. error)",
-                   "l2": "working set (packed weights > 0.9 GB per step) exceeds the 126 MB L2; no explicit flush",
-                   "train_videos_per_step_per_gpu": args.train_batch},
-        "e2e": {"value": world * B * args.steps / t_e2e, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches_inf,
+        "metric": head["metric"], "value": head["value"], "unit": head["unit"], "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16" if ops.ACT_DTYPE == torch.float16 else "bf16", "data": "synthetic",
+        # both halves of BASELINE.json's metric, compact and first (the verbose objects follow)
+        "infer_value": infer_value, "infer_ms_per_step": infer_ms, "infer_e2e_value": e2e_inf["value"],
+        "train_value": train["value"] if train else None, "train_ms_per_step": train["ms_per_step"] if train else None,
+        "train_e2e_value": train["e2e"]["value"] if train else None,
+        "train_batch2_value": train["batch2"]["value"] if train else None,
+        "train_batch2_ms_per_step": train["batch2"]["ms_per_step"] if train else None,
+        "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
         "clocks": sampler.summary(),
+        "config": bench_config(args),
         "roofline": roof,
+        "verify": verify,
         "latency_b1_ms": lat_b1,
-        "train": train,
     }
+    extras = {"train": train}
     if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(args.ref_videos)
         try:
             eg = {}
             for tf32 in (False, True):
-                i_r, t_r = eager_gpu_rates(model.state_dict(), tf32)
+                i_r, t_r, kind = eager_gpu_rates(tf32)
                 eg["tf32" if tf32 else "fp32"] = {"infer_videos_per_s": i_r, "train_videos_per_s": t_r}
-            eg["what"] = ("oracle/mq_oracle.py as eager PyTorch on this B200 (torch ops -> cuDNN/cuBLAS), evaluation one clip per "
-                          "call + host soft-NMS, training batch 2 with torch autograd + AdamW, no dropout")
+            eg["kind"] = kind
+            eg["what"] = ("the reference's own modules as eager PyTorch on this B200 (torch ops -> cuDNN / cuBLAS), evaluation one "
+                          "clip per call + its host soft-NMS, training batch 2 (forward, backward, clip, AdamW)")
             line["eager_gpu_baseline"] = eg
         except Exception as e:  # a baseline must never take the bench down
             line["eager_gpu_baseline"] = {"unavailable": repr(e)[:300]}
         torch.cuda.empty_cache()
         if world == 1:
             try:
-                line["next_rows"] = next_rows()
-                torch.cuda.empty_cache()
+                extras["next_rows"] = next_rows()
             except Exception as e:  # extras must never take the bench line down
-                line["next_rows"] = {"unavailable": repr(e)[:200]}
-        rate, dt = cpu_reference_rate(model.state_dict(), args.ref_videos)
-        cores = os.cpu_count() or 1
-        line["cpu_baseline"] = {"value": rate, "unit": "videos/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.ref_videos} clips through oracle/mq_oracle.py (torch CPU fp32, {cores} threads) incl. soft-NMS, {dt:.1f} s"}
+                extras["next_rows"] = {"unavailable": repr(e)[:200]}
+    line["train"] = train
+    if "next_rows" in extras:
+        line["next_rows"] = extras["next_rows"]
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

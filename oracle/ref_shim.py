@@ -14,9 +14,13 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("VILCO_REFERENCE", "/root/reference")
-REF_MQ = os.path.join(REF_ROOT, "MQ")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference's MQ tree: /root/reference in the authoring container; on the GPU box the un-modified copy that
+# baseline/vendor_ref.py placed under baseline/_ref (git-ignored, travels with the gpurun snapshot) — used there only by
+# bench.py's reference / baseline legs
+VENDORED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+REF_ROOT = os.environ.get("VILCO_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/MQ") else VENDORED)
+REF_MQ = os.path.join(REF_ROOT, "MQ")
 
 
 def available():
