@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | grep -v "^$" | tail -60
+timeout 2700 python -m pytest tests -q -m gpu 2>&1 | grep -v "^$" | grep -v "Warning\|warnings.warn\|^  " | tail -70

@@ -437,47 +437,50 @@ __global__ void __launch_bounds__(256) local_attn_bwd_kv_kernel(const LwBwdParam
 static constexpr int CA_D = 64;
 static constexpr int CA_TCHUNK = 64;
 
+// One CTA per (head, clip) walks all T chunks in order: the sum over tokens is formed in a FIXED order (no atomics), so the
+// result — which feeds a d x d softmax that amplifies its absolute error — is bit-reproducible from run to run.
 __global__ void __launch_bounds__(256) chan_attn_kv_kernel(const __nv_bfloat16* __restrict__ qkv, long long lo,
                                                            float* __restrict__ G, const int* __restrict__ tlen, int T,
                                                            int C, int H, float scale, int fmt) {
   __shared__ float sk[CA_TCHUNK][CA_D + 1];
   __shared__ float sv[CA_TCHUNK][CA_D + 1];
   const int h = blockIdx.y, b = blockIdx.z;
-  const int t0 = blockIdx.x * CA_TCHUNK;
   const int Tb = tlen ? min(T, tlen[b]) : T;  // tokens that take part in the k^T v sum
-  const int nt = min(CA_TCHUNK, Tb - t0);
-  if (nt <= 0) return;
   const long long ld = 3LL * C;
-  const __nv_bfloat16* kb = qkv + ((long long)b * T + t0) * ld + C + h * CA_D;
-  const __nv_bfloat16* vb = kb + C;
-  for (int idx = threadIdx.x; idx < CA_TCHUNK * (CA_D / 2); idx += blockDim.x) {
-    const int r = idx / (CA_D / 2), c = (idx % (CA_D / 2)) * 2;
-    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
-    if (r < nt) {
-      const float2 xk = ld2_split(kb + r * ld + c, lo, fmt);
-      const float2 xv = ld2_split(vb + r * ld + c, lo, fmt);
-      k0 = xk.x * scale; k1 = xk.y * scale; v0 = xv.x; v1 = xv.y;
-    }
-    sk[r][c] = k0; sk[r][c + 1] = k1; sv[r][c] = v0; sv[r][c + 1] = v1;
-  }
-  __syncthreads();
   // thread (i, j4): 4x4 sub-block of the 64x64 output
   const int ti = (threadIdx.x / 16) * 4, tj = (threadIdx.x % 16) * 4;
   float acc[4][4] = {};
-  for (int r = 0; r < CA_TCHUNK; ++r) {
-    float a[4], c[4];
+  for (int t0 = 0; t0 < Tb; t0 += CA_TCHUNK) {
+    const int nt = min(CA_TCHUNK, Tb - t0);
+    const __nv_bfloat16* kb = qkv + ((long long)b * T + t0) * ld + C + h * CA_D;
+    const __nv_bfloat16* vb = kb + C;
+    __syncthreads();   // the previous chunk has been consumed
+    for (int idx = threadIdx.x; idx < CA_TCHUNK * (CA_D / 2); idx += blockDim.x) {
+      const int r = idx / (CA_D / 2), c = (idx % (CA_D / 2)) * 2;
+      float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+      if (r < nt) {
+        const float2 xk = ld2_split(kb + r * ld + c, lo, fmt);
+        const float2 xv = ld2_split(vb + r * ld + c, lo, fmt);
+        k0 = xk.x * scale; k1 = xk.y * scale; v0 = xv.x; v1 = xv.y;
+      }
+      sk[r][c] = k0; sk[r][c + 1] = k1; sv[r][c] = v0; sv[r][c + 1] = v1;
+    }
+    __syncthreads();
+    for (int r = 0; r < CA_TCHUNK; ++r) {
+      float a[4], c[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { a[u] = sk[r][ti + u]; c[u] = sv[r][tj + u]; }
+      for (int u = 0; u < 4; ++u) { a[u] = sk[r][ti + u]; c[u] = sv[r][tj + u]; }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int w = 0; w < 4; ++w) acc[u][w] = fmaf(a[u], c[w], acc[u][w]);
+        for (int w = 0; w < 4; ++w) acc[u][w] = fmaf(a[u], c[w], acc[u][w]);
+    }
   }
   float* g = G + ((long long)b * H + h) * CA_D * CA_D;
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int w = 0; w < 4; ++w) atomicAdd(g + (ti + u) * CA_D + tj + w, acc[u][w]);
+    for (int w = 0; w < 4; ++w) g[(ti + u) * CA_D + tj + w] = acc[u][w];
 }
 
 __global__ void __launch_bounds__(256) chan_attn_apply_kernel(const __nv_bfloat16* __restrict__ qkv, long long lo,
@@ -745,9 +748,8 @@ extern "C" int vilco_channel_attention(const void* qkv, int64_t qkv_lo, float* G
   VILCO_CHECK_ARG(qkv && G, "vilco_channel_attention: null pointer");   // y == NULL: only G = (k / 8)^T v is wanted
   VILCO_CHECK_ARG(H > 0 && C == H * CA_D, "vilco_channel_attention: head dim must be 64 (C=%d H=%d)", C, H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  VILCO_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)B * H * CA_D * CA_D, st));
   dim3 grid((T + CA_TCHUNK - 1) / CA_TCHUNK, H, B);
-  chan_attn_kv_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, tlen, T, C, H, 1.0f / sqrtf((float)CA_D),
+  chan_attn_kv_kernel<<<dim3(1, H, B), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), qkv_lo, G, tlen, T, C, H, 1.0f / sqrtf((float)CA_D),
                                             act_fmt());
   VILCO_LAUNCH_CHECK();
   if (!y) return VILCO_OK;
