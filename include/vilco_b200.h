@@ -239,6 +239,15 @@ int vilco_mq_losses(const float* logits, const float* offsets, const float* pmas
 int vilco_attention(const void* q, int64_t q_lo, const void* k, const void* v, int64_t kv_lo, const float* kmask, void* out,
                     int64_t out_lo, int B, int H, int Tq, int Tk, int C, float scale, void* stream);
 
+/* Fused XLNet relative attention (XLNetRelativeAttention.rel_attn_core + rel_shift_bnij, MQ/libs/modeling/modeling_xlnet_x.py:
+ * 256-320) for single-plane operands, head dim 64, T a multiple of 128 (<= 2048):
+ *   out[b, i, h*64:(h+1)*64] = softmax_j( ((qw_i . k_j) + (qr_i . kr[T + j - i])) * scale | key j visible ) @ v
+ * qw = q + r_w_bias, qr = q + r_r_bias, k, v: (B, T, C) 16-bit planes; kr = pos_emb W_r: (2T, C) (no batch dim); a key j with
+ * kmask[b, j] == 0 is visible only to query j itself (the reference's -1e30 non-self padding mask).  Scores, relative
+ * shift and probabilities stay in TMEM / shared memory; out is one 16-bit plane (B, T, C). */
+int vilco_xl_attention(const void* qw, const void* qr, const void* k, const void* v, const void* kr, const float* kmask,
+                       void* out, int B, int H, int T, int C, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Backward-pass building blocks (training; token-major fp32 gradients).  The GEMM-shaped gradients reuse vilco_gemm:
  *   dX = dZ W      : A = dZ (K-major over the output channels), B = W as MN-major operand (b_major = 1)

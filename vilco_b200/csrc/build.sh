@@ -8,7 +8,7 @@ OBJS=""
 for f in *.cu; do
   o="build/${f%.cu}.o"
   mkdir -p build
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/vilco_b200.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ tc_common.cuh -nt "$o" ] || [ ../../include/vilco_b200.h -nt "$o" ]; then
     echo "nvcc $f"
     $NVCC $FLAGS -c "$f" -o "$o" &
   fi

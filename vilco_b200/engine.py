@@ -239,15 +239,22 @@ def xlnet_layer_fwd(W, pre, x32, x16, mask, H, eps=1e-12):
     # k_r = pos_emb @ W_r depends only on the weights and (T, B): cached with the packed weights (also keeps host->device
     # copies out of CUDA-graph capture)
     cache = W.setdefault("_cache", {})
-    krel = cache.get(("krel", T, B))
+    fused = ops.xl_attention_ok(qw, T, C, H)
+    krel = cache.get(("krel", T, 1 if fused else B))
     if krel is None:
         pos = xlnet_pos_emb(T, C, x32.device)                               # (2T, C)
-        krel = ops.linear(pos, W[kr], bf16).unsqueeze(1).expand(-1, B, 2 * T, C).contiguous()
-        cache[("krel", T, B)] = krel
-    ac = ops.attn_scores(qw, k, H, 1.0)                                     # (B,H,T,T)
-    bd = ops.attn_scores(qr, krel, H, 1.0, band=(T, 2 * T))                 # (B,H,T,2T); only T <= i + p < 2T is read
-    P = ops.softmax_rows(ac, mask, mode=1, BD=bd, scale=1.0 / math.sqrt(d))
-    vec = ops.attn_pv(P, v, H, T)
+        krel = ops.linear(pos, W[kr], bf16)                                 # (NP, 2T, C)
+        if not fused:
+            krel = krel.unsqueeze(1).expand(-1, B, 2 * T, C).contiguous()
+        cache[("krel", T, 1 if fused else B)] = krel
+    if fused:
+        # scores, relative shift, softmax and P V in one kernel: nothing of size T x T ever reaches HBM
+        vec = ops.xl_attention(qw, qr, k, v, krel, mask, H, 1.0 / math.sqrt(d))
+    else:
+        ac = ops.attn_scores(qw, k, H, 1.0)                                     # (B,H,T,T)
+        bd = ops.attn_scores(qr, krel, H, 1.0, band=(T, 2 * T))                 # (B,H,T,2T); only T <= i + p < 2T is read
+        P = ops.softmax_rows(ac, mask, mode=1, BD=bd, scale=1.0 / math.sqrt(d))
+        vec = ops.attn_pv(P, v, H, T)
     a = ops.linear(vec, W[ko], f32, resid=x32)                              # attn_out + h
     h1_32, h1_16 = ops.layernorm(a, W[pre + "rel_attn.layer_norm.weight"], W[pre + "rel_attn.layer_norm.bias"], eps,
                                  out32=True)

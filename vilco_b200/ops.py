@@ -206,6 +206,22 @@ def attention(q, k, v, kmask, H, scale):
     return out
 
 
+def xl_attention_ok(qw, T, C, H):
+    """the fused XLNet relative-attention kernel takes single-plane operands, head dim 64, T % 128 == 0"""
+    return FUSED_ATTN and qw.shape[0] == 1 and C // H == 64 and T % 128 == 0 and 128 <= T <= 2048
+
+
+def xl_attention(qw, qr, k, v, kr, kmask, H, scale):
+    """Fused XLNet relative attention: qw / qr / k / v (1,B,T,C), kr (1,2T,C), kmask (B,T) fp32 -> operand (1,B,T,C).
+    Scores, the relative shift and the probabilities never leave the SM (csrc/xlattn.cu)."""
+    _, B, T, Cc = qw.shape
+    assert kr.shape[-2] == 2 * T and kr.shape[0] == 1 and k.shape[0] == 1 and v.shape[0] == 1 and qr.shape[0] == 1
+    out = empty16(B, T, Cc, device=qw.device, planes=1)
+    L.check(L.lib().vilco_xl_attention(_p(qw), _p(qr), _p(k), _p(v), _p(kr), _p(kmask), _p(out), B, H, T, Cc, C.c_float(scale),
+                                       L.stream_ptr()), "vilco_xl_attention")
+    return out
+
+
 def layernorm(x, w, b, eps=1e-5, add=None, relu=False, pe=None, rowmul=None, zero_rows=None, out32=False, out16=True,
               y16=None, rows_per_batch=None, y_ld=None, y_bs=None, y16_lo=None, planes=None):
     """Channel LN over the last dim of token-major fp32 x.  Returns (y32 or None, y16 operand or None).
