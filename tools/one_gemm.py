@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vilco_b200 import ops  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "qk"
-ops.set_precision(sys.argv[2] if len(sys.argv) > 2 else "bf16x3")
+ops.set_precision(sys.argv[2] if len(sys.argv) > 2 else "mixed")
 dev = "cuda"
 B, T, C, H = 8, 1024, 1024, 16
 x = ops.split16(torch.randn(B, T, C, device=dev))
@@ -28,7 +28,13 @@ elif which == "heads":   # the dominant GEMM of bench.py's default step: head to
     xh = ops.split16(torch.randn(32, 2056, C, device=dev))
     w3 = ops.split16(torch.randn(3, C, C, device=dev) * 0.03)
     rm = torch.ones(32, 2056, device=dev)
-    fn = lambda: ops.conv3(xh, w3, ops.f32, rowmul=rm)
+    fn = lambda: ops.conv3(xh, w3, ops.f32, rowmul=rm, flat=True)
+elif which == "xl":      # fused XLNet relative attention at 32 clips
+    Bx = 32
+    mk = lambda *s_: ops.split16(torch.randn(*s_, device=dev), planes=1)
+    qw, qr, kk, vv, kr = mk(Bx, T, C), mk(Bx, T, C), mk(Bx, T, C), mk(Bx, T, C), mk(2 * T, C)
+    msk = torch.ones(Bx, T, device=dev)
+    fn = lambda: ops.xl_attention(qw, qr, kk, vv, kr, msk, H, 0.125)
 elif which == "wgrad":   # weight gradient dW = dZ^T X, both operands MN-major, split-K 2 (training step, 16 clips)
     from vilco_b200 import backward as BW
     dz = ops.split16(torch.randn(16 * T, C, device=dev))
