@@ -7,7 +7,7 @@ from vilco_b200.utils.nms import _run
 from vilco_b200 import lib as L
 L.lib()
 rs = np.random.RandomState(0)
-B, nl, topk, K = 8, 10, 5000, 22
+B, nl, topk, K = int(os.environ.get("NMS_B", 8)), 10, 5000, 22
 segs = torch.zeros(B, nl * topk, 2); scores = torch.zeros(B, nl * topk); labels = torch.zeros(B, nl * topk, dtype=torch.int32)
 cnt = torch.zeros(B, nl, dtype=torch.int32)
 per = [5000, 5000, 5000, 2816, 1408, 704, 352, 176, 88, 44]
