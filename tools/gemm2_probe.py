@@ -71,12 +71,33 @@ def case(M, N, K, fa, fb, pa, pb, impl, out=torch.float32, taps=1, epi=False, dp
     eps = {F16: 2.0 ** -11, BF16: 2.0 ** -8}
     tol = (3e-6 if taps == 1 else 1e-5) + (eps[fa] * eps[fb] * 4 if pa == 2 and pb == 2 else 0)   # fp32 accumulation over K * taps
     if out != torch.float32:
-        tol += eps[out] if dplanes == 1 else eps[out] ** 2 * 4
+        tol += eps[out] if dplanes == 1 else eps[out] ** 2 * 8
     name = (f"M{M} N{N} K{K} taps{taps} A:{str(fa)[6:]}x{pa} B:{str(fb)[6:]}x{pb} impl{impl} out:{str(out)[6:]}x{dplanes} epi{int(epi)}")
     report(name, got, ref, tol)
 
 
+def case_major(M, N, K, a_major, b_major, impl, pa=2, pb=1, Z=1):
+    """gradient-GEMM operand layouts: A stored (K, M) when a_major, B stored (K, N) when b_major (MN-major operands)"""
+    A32 = torch.randn(Z, M, K, device=dev)
+    B32 = torch.randn(Z, N, K, device=dev) * 0.1
+    A = planes(A32.transpose(1, 2).contiguous() if a_major else A32, F16, pa)      # (P, Z, K, M) or (P, Z, M, K)
+    Bt = planes(B32.transpose(1, 2).contiguous() if b_major else B32, F16, pb)
+    ref = torch.einsum("zmk,znk->zmn", (A.double().sum(0).transpose(1, 2) if a_major else A.double().sum(0)),
+                       (Bt.double().sum(0).transpose(1, 2) if b_major else Bt.double().sum(0)))
+    D = torch.zeros(Z, M, N, device=dev)
+    L.gemm(A, Bt, D, M=M, N=N, K=K, a_rows=M, a_ld=M if a_major else K, a_major=a_major, a_s=(M * K, 0), Z=(Z, 1),
+           b_ld=N if b_major else K, b_s=(N * K, 0), b_batched=True, b_major=b_major, d_ld=N, d_s=(M * N, 0), impl=impl,
+           a_lo=lo(A), b_lo=lo(Bt))
+    torch.cuda.synchronize()
+    report(f"M{M} N{N} K{K} Z{Z} a_major{a_major} b_major{b_major} planes {pa}/{pb} impl{impl}", D.double(), ref, 1e-5 if K < 2048 else 3e-5)
+
+
 def check():
+    for impl in (2, 3):
+        case_major(2048, 1024, 1024, 0, 1, impl)              # dgrad: dZ K-major, W as MN-major B
+        case_major(1024, 1024, 4096, 1, 1, impl, Z=4)         # wgrad: both MN-major, split-K batches
+        case_major(1000, 520, 328, 1, 1, impl)                # ragged
+        case_major(4096, 1024, 1024, 0, 1, impl, pa=1, pb=2)
     for impl in (1, 2, 3):   # SIMT, one CTA per tile, CTA pair per tile
         for fa, fb in ((F16, F16), (BF16, BF16)) + (((BF16, F16),) if impl == 1 else ()):   # the tensor core cannot mix formats
             for pa, pb in ((1, 1), (2, 2), (2, 1), (1, 2)):

@@ -47,7 +47,7 @@ def main():
             e0.record(); r = orig(A, Bm, D, **kw); e1.record()
             Z = kw.get("Z", (1, 1))
             rec.append((e0, e1, 2.0 * kw["M"] * kw["N"] * kw["K"] * kw.get("taps", 1) * Z[0] * Z[1],
-                        (kw["M"], kw["N"], kw["K"], kw.get("taps", 1), Z[0] * Z[1], kw.get("b_major", 0), str(D.dtype)[6:])))
+                        (kw["M"], kw["N"], kw["K"], kw.get("taps", 1), Z[0] * Z[1], f"{kw.get('a_major', 0)}{kw.get('b_major', 0)}p{A.shape[0]}{Bm.shape[0]}", str(D.dtype)[6:])))
             return r
         L.gemm = timed
         tr.step(vids)
@@ -81,10 +81,14 @@ def main():
             torch.cuda.synchronize()
         print(p.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
         return
+    cpu = 0.0
     for _ in range(steps):
+        c0 = time.perf_counter()
         lo = tr.step(vids)
+        cpu += time.perf_counter() - c0          # host time to ISSUE the step (no synchronisation inside tr.step except the loss sums)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
+    print(f"host issue time {cpu / steps * 1e3:.1f} ms/step")
     print(f"B={B}: {dt * 1e3:.1f} ms/step, {B / dt:.1f} train videos/s, our launches/step {(L.launch_count() - n0) / steps:.0f}")
 
 

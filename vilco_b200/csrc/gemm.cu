@@ -923,8 +923,9 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
     // would leave most of the 148 SMs idle
     BN = (t128 * 2 <= num_sms()) ? 64 : 128;
   }
-  // CTA pairs (cta_group::2, 256 x 256 or 256 x 128 tiles) for the big K-major problems: at least ~2 waves of 256 x 256 tiles
-  if (g->a_major == 0 && g->b_major == 0 && g->band_hi <= g->band_lo && force_cg != 1 && g->N >= 128) {
+  // CTA pairs (cta_group::2, 256 x 256 or 256 x 128 tiles) for the big problems (any operand majors: the gradient GEMMs read
+  // their operands MN-major): at least ~2 waves of 256 x 256 tiles
+  if (g->band_hi <= g->band_lo && force_cg != 1 && g->N >= 128) {
     const long long t256 = (long long)((g->N + 255) / 256) * ((g->M + 255) / 256) * Z;
     if (g->N >= 256 && (t256 >= 2 * (num_sms() / 2) || force_cg == 2)) { BN = 256; CG = 2; }
     else if (t128 / 2 >= 2 * (num_sms() / 2) || force_cg == 2) { BN = 128; CG = 2; }
