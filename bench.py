@@ -437,13 +437,17 @@ def run_train_leg(args, model, rank, world, dist, barrier, local):
     barrier()
     t_dev = e0.elapsed_time(e1) * 1e-3
     launches = (L.launch_count() - n0) // args.steps
+    # end to end: pinned host batches; the upload of batch i+1 is started (Trainer.stage, copy stream) before step i runs
+    nxt = tr.stage(host_sets[0])
     for i in range(args.warmup):
-        float(tr.step(host_sets[i % 2])["final_loss"].detach())
+        cur, nxt = nxt, tr.stage(host_sets[(i + 1) % 2])
+        float(tr.step(cur)["final_loss"].detach())
     barrier()
     t0 = time.perf_counter()
     last = 0.0
     for i in range(args.steps):
-        last = float(tr.step(host_sets[i % 2])["final_loss"].detach())      # D2H read of the loss every step
+        cur, nxt = nxt, tr.stage(host_sets[(i + 1) % 2])
+        last = float(tr.step(cur)["final_loss"].detach())      # D2H read of the loss every step
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
@@ -469,9 +473,9 @@ def run_train_leg(args, model, rank, world, dist, barrier, local):
             "ms_per_step": 1e3 * t_dev / args.steps, "videos_per_step_per_gpu": Bt, "gpu_launches_per_step": int(launches),
             "e2e": {"value": world * Bt * args.steps / t_e2e, "unit": "videos/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "step": "zero_grad, forward (dropout 0.1, drop-path 0.1, XLNet dropout 0.1), focal + DIoU + label-involved loss, "
-                    "hand-written backward, " + ("NCCL all-reduce of one flat fp32 gradient buffer, " if world > 1 else "") +
+                    "hand-written backward, " + (f"NCCL all-reduce of the flat gradient buffer ({tr.grad_comm} on the wire, fp32 master), " if world > 1 else "") +
                     "clip_grad_norm 1.0, fused flat AdamW (lr 1e-4, wd 0.05)",
-            "grad_bytes_allreduced_per_step": int(4 * sum(b - a for a, b in opt.live_ranges())) if world > 1 else 0,
+            "grad_bytes_allreduced_per_step": int((2 if tr.grad_comm == "bf16" else 4) * sum(b - a for a, b in opt.live_ranges())) if world > 1 else 0,
             "allreduce": ("bucketed (128 MB), launched as the backward completes each bucket" if tr.overlap else "one call after the backward") if world > 1 else None,
             "live_parameters": int(sum(b - a for a, b in opt.live_ranges())), "all_parameters": int(opt.n), "last_loss": last, "peak_mem_gib": mem,
             "batch2": {"value": world * 2 * 5 / t_small, "unit": "videos/s", "ms_per_step": 1e3 * t_small / 5,
