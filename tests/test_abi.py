@@ -154,3 +154,15 @@ def test_orchestration_facing_attributes_exist():
         assert hasattr(m, name), name
     assert m.cls_head.cls_head.conv.out_channels == c.num_classes
     assert isinstance(m.memory, dict) and isinstance(m.reg_params, dict) and m.list_bias_layers is not None
+
+
+def test_torch_custom_op_layer_is_registered_and_has_no_cpu_path():
+    """north_star: kernels are called through a thin torch custom-op layer — torch.ops.vilco.* (vilco_b200/torch_ops.py);
+    there is no CPU implementation behind it."""
+    import torch
+    import vilco_b200.torch_ops as T
+    for n in T.OPS:
+        assert hasattr(torch.ops.vilco, n), n
+        assert "vilco::" + n in str(getattr(torch.ops.vilco, n).default._schema)
+    with pytest.raises(NotImplementedError):
+        torch.ops.vilco.linear(torch.zeros(1, 4, 8, dtype=torch.float16), torch.zeros(1, 8, 8, dtype=torch.float16), None, None, 0, True)

@@ -182,3 +182,27 @@ def test_vilco_config_vs_reference_golden():
         a = model(v2, is_training=False, get_emb=True)
         b0 = model(v2[:1], is_training=False, get_emb=True)
     assert rel_max(torch.cat(a[0], 1)[0].cpu(), torch.cat(b0[0], 1)[0].cpu()) < 1e-4
+
+
+def test_torch_custom_ops_call_the_kernels():
+    """torch.ops.vilco.* (the torch.library layer) == the ops wrappers, which make the C-ABI calls"""
+    import vilco_b200.torch_ops  # noqa: F401
+    from vilco_b200 import ops
+    torch.manual_seed(0)
+    x32 = torch.randn(2, 128, 256, device="cuda")
+    w = ops.split16(torch.randn(512, 256, device="cuda") * 0.05)
+    lw, lb = torch.randn(256, device="cuda"), torch.randn(256, device="cuda")
+    y32, y16 = torch.ops.vilco.layernorm(x32, lw, lb, 1e-5, False)
+    ref = torch.nn.functional.layer_norm(x32, (256,), lw, lb, 1e-5)
+    assert rel_max(y32, ref) < 1e-5 and rel_max(ops.merge16(y16), ref) < 1e-3
+    bias = torch.randn(512, device="cuda")
+    z = torch.ops.vilco.linear(y16, w, bias, None, 0, True)
+    assert torch.equal(z, ops.linear(y16, w, ops.f32, bias=bias))
+    assert rel_max(z, ops.merge16(y16) @ ops.merge16(w).t() + bias) < 1e-4
+    q, k, v = (ops.split16(torch.randn(2, 256, 128, device="cuda"), planes=1) for _ in range(3))
+    o = torch.ops.vilco.attention(q, k, v, None, 2, 0.125)
+    assert torch.equal(o, ops.attention(q, k, v, None, 2, 0.125))
+    segs = torch.rand(300, 2, device="cuda").sort(dim=1)[0] * 100
+    sc, lb_ = torch.rand(300, device="cuda"), torch.randint(0, 5, (300,), device="cuda")
+    s1 = torch.ops.vilco.batched_nms(segs, sc, lb_, 0.1, 1e-4, 50, True, True, 0.99, 0.75)
+    assert s1[0].shape == (50, 2) and bool((s1[1][:-1] >= s1[1][1:]).all())
