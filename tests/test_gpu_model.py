@@ -113,6 +113,57 @@ def test_local_masked_mhca_vs_reference_golden(name, window):
     assert rel_max(y.cpu().numpy(), g[name + "_y"]) < TOL
 
 
+def _banded_attention_f64(q, k, v, valid, H, W, rel_pe):
+    """dense float64 restatement of the banded attention core (oracle/mq_oracle.py:local_masked_mhca, lines 96-110) on operands
+    already rounded to their planes"""
+    B, T, C = q.shape
+    d, w = C // H, W // 2
+    hd = lambda t: t.double().view(B, T, H, d).transpose(1, 2)     # noqa: E731
+    att = (hd(q) / d ** 0.5) @ hd(k).transpose(-2, -1)
+    idx = torch.arange(T, device=q.device)
+    rel = idx[None, :] - idx[:, None]
+    if rel_pe is not None:
+        att = att + rel_pe.double()[:, (rel.clamp(-w, w) + w)][None]
+    km = idx[None, :] < valid[:, None]
+    att = att + (~km[:, None, None, :]).double() * -1e4
+    att = att.masked_fill((rel.abs() > w)[None, None], float("-inf"))
+    att = torch.softmax(att, -1).masked_fill(~km[:, None, :, None], 0.0)
+    return (att @ hd(v)).transpose(1, 2).reshape(B, T, C)
+
+
+@pytest.mark.parametrize("B,T,H,d,W,valid,rel", [
+    (2, 100, 2, 16, 5, [100, 37], False),        # single partial tile, CTA narrower than 64 queries would be T < 64 only
+    (2, 40, 2, 32, 9, [40, 9], True),            # T < 64: 48-query CTA
+    (2, 1024, 16, 64, 9, [1024, 700], False),    # Moment-Query width
+    (1, 333, 4, 64, 17, [301], True),            # widest window of the two-chunk template
+    (2, 200, 4, 96, 9, [200, 130], True),        # NLQ head dim
+    (1, 130, 2, 128, 33, [130], False),          # three-chunk template, max head dim
+    (2, 77, 3, 32, 19, [77, 1], True),
+])
+@pytest.mark.parametrize("planes", [1, 2])
+def test_window_attention_kernel(B, T, H, d, W, valid, rel, planes):
+    """sliding-window attention kernel (tensor-core path, csrc/local_attn_tc.cu) against the dense float64 restatement on the
+    same rounded operands: two planes to 2e-5 (fp32 accumulation), one fp16 plane to 6e-4 (the probabilities are rounded to
+    fp16 for the P V product; the output is one fp16 plane)"""
+    from vilco_b200 import ops
+    with precision("fp16x3"):
+        rs = torch.Generator(device="cuda").manual_seed(T * 7 + W)
+        C = H * d
+        q, k, v = (ops.split16(torch.randn(B, T, C, device="cuda", generator=rs) * s, planes=planes) for s in (2.0, 1.0, 1.5))
+        vl = torch.tensor(valid, device="cuda")
+        mask = (torch.arange(T, device="cuda")[None, :] < vl[:, None]).float()
+        rel_pe = torch.randn(H, W, device="cuda", generator=rs) if rel else None
+        out = ops.local_attention(q, k, v, mask, H, W, rel_pe)
+        assert out.shape[0] == planes
+        ref = _banded_attention_f64(q.double().sum(0), k.double().sum(0), v.double().sum(0), vl, H, W, rel_pe)
+        got = out.double().sum(0)
+        assert torch.isfinite(got).all()
+        err = float((got - ref).abs().max() / ref.abs().max())
+        print(f"window attention T{T} d{d} W{W} planes{planes}: rel err {err:.2e}")
+        assert err < (2e-5 if planes == 2 else 6e-4)
+        assert float(got[~(mask > 0)].abs().max() if (mask == 0).any() else 0.0) == 0.0      # padded queries are zeroed
+
+
 def test_full_size_blocks_vs_oracle():
     """One stride-1 block, one stride-2 cross-attention block and the XLNet layer at the real MQ width
     (C=1024, H=16, T=1024) against the oracle on the same seeded weights."""

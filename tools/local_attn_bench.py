@@ -17,7 +17,7 @@ if os.path.exists(p):
     peak = json.load(open(p))["hbm_gbs"]
 out = {}
 for name, (B, T, C, H, W) in {"mq_w9": (32, 1024, 1024, 16, 9), "mq_w17": (32, 1024, 1024, 16, 17), "nlq_w9": (16, 2560, 384, 4, 9)}.items():
-    q, k, v = (ops.split16(torch.randn(B, T, C, device="cuda"), planes=1) for _ in range(3))
+    q, k, v = (ops.split16(torch.randn(B, T, C, device="cuda"), planes=ops.PLANES) for _ in range(3))
     mask = torch.ones(B, T, device="cuda")
     big = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)     # L2 flush between timed launches
     ts = []
@@ -31,7 +31,7 @@ for name, (B, T, C, H, W) in {"mq_w9": (32, 1024, 1024, 16, 9), "mq_w17": (32, 1
         if i >= 3:
             ts.append(e0.elapsed_time(e1) * 1e3)
     us = sorted(ts)[len(ts) // 2]
-    nbytes = 4 * T * C * 2 * B
+    nbytes = 4 * T * C * 2 * B * ops.PLANES
     out[name] = {"B": B, "T": T, "C": C, "H": H, "W": W, "us": us, "GBps": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / peak}
     print(name, out[name], flush=True)
 json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r2_local_attn_bench.json"), "w"), indent=1)

@@ -139,6 +139,9 @@ static constexpr int LW_TI = 32;      // queries per CTA
 static constexpr int LW_MAXW = 65;    // max window size
 static constexpr int LW_MAXD = 128;   // max head dim
 
+int local_attn_tc(const void* q, const void* k, const void* v, const float* mask, const float* rel_pe, void* out, long long lo,
+                  int B, int T, int C, int H, int W, float scale, int fmt, void* stream);   // local_attn_tc.cu
+
 struct LwParams {
   const __nv_bfloat16 *q, *k, *v; const float* mask;  // mask (B, T)
   const float* rel_pe;                                // (H, W) or null
@@ -699,6 +702,9 @@ extern "C" int vilco_local_attention(const void* q, const void* k, const void* v
   p.out = static_cast<__nv_bfloat16*>(out); p.lo = lo;
   p.B = B; p.T = T; p.C = C; p.H = H; p.d = d; p.W = W; p.scale = 1.0f / sqrtf(static_cast<float>(d));
   p.fmt = act_fmt();
+  // tensor-core kernel (local_attn_tc.cu) for the template set of head dims / windows; VILCO_LOCAL_ATTN=simt keeps the scalar one
+  static const bool force_simt = [] { const char* e = getenv("VILCO_LOCAL_ATTN"); return e && !strcmp(e, "simt"); }();
+  if (!force_simt && local_attn_tc(q, k, v, mask, rel_pe, out, lo, B, T, C, H, W, p.scale, p.fmt, stream) == VILCO_OK) return VILCO_OK;
   const size_t smem = (size_t)2 * (LW_TI + 2 * (W / 2)) * d * sizeof(float);
   static bool configured = false;
   if (!configured) {

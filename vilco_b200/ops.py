@@ -313,8 +313,9 @@ def softmax_rows(S, kmask, mode=0, BD=None, scale=1.0, want32=False, planes=None
 
 
 def local_attention(q, k, v, mask, H, W, rel_pe=None):
-    _, B, T, Cc = q.shape
-    out = empty16(B, T, Cc, device=q.device)
+    NP, B, T, Cc = q.shape
+    assert k.shape == q.shape and v.shape == q.shape
+    out = empty16(B, T, Cc, device=q.device, planes=NP)
     L.check(L.lib().vilco_local_attention(_p(q), _p(k), _p(v), _p(mask), _p(rel_pe), _p(out), _i64(lo(out)), B, T, Cc, H,
                                           W, L.stream_ptr()), "vilco_local_attention")
     return out
