@@ -113,18 +113,21 @@ def check():
     print("launches", L.launch_count(), "bad", bad)
 
 
-def timeit(fn, flops, name, n=20):
+def timeit(fn, flops, name, n=30):
+    """whole-sequence time of n back-to-back launches (what a step sees) and the per-launch durations inside it"""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
+    for i in range(n):
         fn()
-    e1.record()
+        ev[i + 1].record()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / n
-    print(f"{name:70s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s", flush=True)
+    us = ev[0].elapsed_time(ev[n]) * 1e3 / n
+    each = sorted(ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(n))
+    print(f"{name:70s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s   per launch min {each[0]:.1f} med {each[n // 2]:.1f} max {each[-1]:.1f}",
+          flush=True)
 
 
 def timing():
@@ -151,10 +154,33 @@ def timing():
             del A, W, D
 
 
+def sweep():
+    """per-tile cost model: time(K) at fixed N and time(N) at fixed K, plain epilogue, one fp16 plane"""
+    M = 32768
+    for (N, K, out, extra) in [(1024, 256, F16, ""), (1024, 512, F16, ""), (1024, 1024, F16, ""), (1024, 2048, F16, ""), (1024, 4096, F16, ""),
+                               (2048, 1024, F16, ""), (4096, 1024, F16, ""), (1024, 1024, torch.float32, ""), (4096, 1024, torch.float32, ""),
+                               (1024, 1024, F16, "bias+gelu"), (1024, 1024, torch.float32, "resid")]:
+        A = planes(torch.randn(M, K, device=dev), F16, 1)
+        W = planes(torch.randn(1, N, K, device=dev) * 0.05, F16, 1)
+        D = torch.empty(M, N, device=dev, dtype=out) if out == torch.float32 else torch.empty(1, M, N, device=dev, dtype=out)
+        kw = {}
+        if extra == "bias+gelu":
+            kw = dict(bias=torch.randn(N, device=dev), act=L.ACT_GELU)
+        if extra == "resid":
+            kw = dict(resid=torch.randn(M, N, device=dev))
+        fn = lambda: L.gemm(A, W, D, M=M, N=N, K=K, a_rows=M, a_ld=K, b_ld=K, b_s=(N * K, 0), d_ld=N, a_lo=0, b_lo=0, **kw)  # noqa: E731
+        tiles = (M // 256) * (N // 256)
+        waves = -(-tiles // 74)
+        timeit(fn, 2.0 * M * N * K, f"sweep M{M} N{N} K{K} out {str(out)[6:]} {extra} ({waves} waves)")
+        del A, W, D
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["check", "time"]
     if "check" in what:
         check()
     if "time" in what:
         timing()
+    if "sweep" in what:
+        sweep()
     sys.exit(1 if bad else 0)

@@ -24,6 +24,17 @@ elif which == "lin32":
     resid = torch.randn(B, T, C, device=dev)
     rm = torch.ones(B * T, device=dev)
     fn = lambda: ops.linear(x, w, ops.f32, rowmul=rm, resid=resid, resid_masked=True)
+elif which == "cxc32":   # C x C projection at 32 clips -> operand planes (q / k / v / proj shapes)
+    x32 = ops.split16(torch.randn(32, T, C, device=dev), planes=1)
+    w = ops.split16(torch.randn(C, C, device=dev) * 0.03, planes=1)
+    bb = torch.randn(C, device=dev)
+    fn = lambda: ops.linear(x32, w, ops.bf16, bias=bb, planes=1)
+elif which == "mlp2_32":  # FFN down projection at 32 clips: K = 4096, fp32 out + residual
+    x32 = ops.split16(torch.randn(32, T, 4 * C, device=dev), planes=1)
+    w = ops.split16(torch.randn(C, 4 * C, device=dev) * 0.03, planes=1)
+    resid = torch.randn(32, T, C, device=dev)
+    rm = torch.ones(32 * T, device=dev)
+    fn = lambda: ops.linear(x32, w, ops.f32, rowmul=rm, resid=resid, resid_masked=True)
 elif which == "heads":   # the dominant GEMM of bench.py's default step: head tower conv over the (32, 2056, 1024) pyramid
     xh = ops.split16(torch.randn(32, 2056, C, device=dev))
     w3 = ops.split16(torch.randn(3, C, C, device=dev) * 0.03)

@@ -80,9 +80,10 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 
 // ---- 16-bit operand planes in either format (fmt is warp-uniform: VILCO_BF16 or VILCO_F16) -------------------------------
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fmt) {
-  if (fmt == VILCO_F16) {   // saturate instead of producing inf (fp16 max = 65504)
-    __half2 h = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-    return *reinterpret_cast<uint32_t*>(&h);
+  if (fmt == VILCO_F16) {   // saturate instead of producing inf (fp16 max = 65504): one F2FP.SATFINITE, NaN stays NaN
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   }
   return pack_bf16x2(lo, hi);
 }

@@ -11,6 +11,7 @@
 // B has a lo plane, plus lo*hi when A has one.
 #include <mutex>
 #include "tc_common.cuh"
+#include <type_traits>
 
 namespace vilco {
 
@@ -141,6 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===== TMA producer =====
       int ca[4], cb[4];
       uint32_t it_g = 0;  // global k-iteration counter (continues across tiles)
+      uint32_t s = 0, ph = 0;   // ring position of it_g
       for (int t = worker; t < total_tiles; t += n_workers) {
         const int z = t / tiles_per_z, r = t - z * tiles_per_z;
         const int mt0 = (r / n_tiles) * BM * CG, n0 = (r % n_tiles) * BN;
@@ -150,12 +152,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nb0 = n0 + static_cast<int>(rank) * BNH;    // this CTA's share of the B tile
         ca[p.a_slot_z1] = z1; ca[p.a_slot_z2] = z2;
         cb[p.b_slot_z2] = p.b_batched ? z2 : 0;
+        int tap = 0, kb = 0;
         for (int it = 0; it < iters; ++it, ++it_g) {
-          const int s = it_g % STAGES;
-          const uint32_t ph = (it_g / STAGES) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
-          const int tap = it / kblocks;
-          const int kb = it - tap * kblocks;
           const uint32_t sa = smem_u32(ring + s * stage_bytes);
           const uint32_t sb = sa + A_BYTES * PA;
           uint32_t fb = full0 + 8 * s;
@@ -199,6 +198,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 load(sb + pl * B_BYTES + h * (BK * 128), &tmB, cb[0] + h * 64, cb[1], cb[2], cb[3], pl);
             }
           }
+          if (++s == static_cast<uint32_t>(STAGES)) { s = 0; ph ^= 1; }
+          if (++kb == kblocks) { kb = 0; ++tap; }
         }
       }
       // tail: wait until the MMAs have released every stage this CTA filled (no arrival may target an exited CTA)
@@ -208,10 +209,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread of the leader CTA) =====
+    // ===== MMA issuer (one elected lane of the leader CTA) =====
+    // The loop is latency-critical: it is ONE warp's instruction stream that has to stay ahead of the tensor pipe (a 256 x 256 x 16
+    // MMA retires in ~128 cycles).  Everything below is warp-uniform (descriptors are built by adding a stage offset to a
+    // constant, the ring position is a counter, the plane combinations are separate straight-line paths), so the compiler
+    // keeps it in uniform registers; only the tcgen05 instructions themselves sit under the elected-lane predicate.
     if (rank == 0) {
       const uint32_t idesc = make_idesc(BN, p.b_major, p.a_major, p.a_fmt, p.b_fmt, BM * CG);
-      uint32_t it_g = 0, tc = 0;
+      // K-major: advance 16 elements = 32 bytes inside the swizzle atom; MN-major: 16 k-rows of 128 bytes (descriptor units of 16 B)
+      const uint32_t a_k16 = (p.a_major == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;
+      const uint32_t b_k16 = (p.b_major == 0 ? UMMA_K * 2 : UMMA_K * 128) >> 4;
+      const uint64_t a_desc0 = make_smem_desc(0, p.a_major == 0 ? 16 : BK * 128, 1024);
+      const uint64_t b_desc0 = make_smem_desc(0, p.b_major == 0 ? 16 : BK * 128, 1024);   // MN-major: distance between 64-column swizzle atoms
+      const uint32_t ring16 = (smem_u32(ring) & 0x3FFFFu) >> 4, stage16 = stage_bytes >> 4;
+      const uint32_t a_pl16 = A_BYTES >> 4, b_pl16 = B_BYTES >> 4, b_off16 = (A_BYTES * PA) >> 4;
+      const bool leader_lane = elect_one();
+      uint32_t s = 0, ph = 0, tc = 0;
       for (int t = worker; t < total_tiles; t += n_workers) {
         {
           const int r = t % tiles_per_z;
@@ -222,30 +235,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(tempty0 + 8 * acc, ((tc_cur >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-        for (int it = 0; it < iters; ++it, ++it_g) {
-          const int s = it_g % STAGES;
-          const uint32_t ph = (it_g / STAGES) & 1;
+        for (int it = 0; it < iters; ++it) {
           mbar_wait(full0 + 8 * s, ph);
           tcgen05_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(ring + s * stage_bytes);
-            const uint32_t sb = sa + A_BYTES * PA;
-            auto mma = [&](uint64_t ad, uint64_t bd, uint32_t accum) {
-              if (CG == 2) tcgen05_mma_f16_2sm(tmem_d, ad, bd, idesc, accum);
-              else tcgen05_mma_f16(tmem_d, ad, bd, idesc, accum);
+          const uint64_t ad = a_desc0 + (ring16 + s * stage16);
+          const uint64_t bd = ad - a_desc0 + b_desc0 + b_off16;
+          const uint32_t first = it > 0 ? 1u : 0u;
+          if (leader_lane) {
+            auto mma = [&](uint64_t x, uint64_t y, uint32_t accum) {
+              if (CG == 2) tcgen05_mma_f16_2sm(tmem_d, x, y, idesc, accum);
+              else tcgen05_mma_f16(tmem_d, x, y, idesc, accum);
             };
+            if (PA == 1 && PB == 1) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // K-major: advance 16 elements = 32 bytes inside the swizzle atom; MN-major: 16 k-rows of 128 bytes.
-              const uint32_t aoff = p.a_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
-              const uint32_t a_lbo = p.a_major == 0 ? 16 : BK * 128;
-              const uint32_t boff = p.b_major == 0 ? k * UMMA_K * 2 : k * UMMA_K * 128;
-              const uint64_t a_hi = make_smem_desc(sa + aoff, a_lbo, 1024);
-              const uint32_t b_lbo = p.b_major == 0 ? 16 : BK * 128;   // MN-major: distance between 64-column swizzle atoms
-              const uint64_t b_hi = make_smem_desc(sb + boff, b_lbo, 1024);
-              mma(a_hi, b_hi, (it > 0 || k > 0) ? 1u : 0u);
-              if (PB == 2) mma(a_hi, make_smem_desc(sb + B_BYTES + boff, b_lbo, 1024), 1u);
-              if (PA == 2) mma(make_smem_desc(sa + A_BYTES + aoff, a_lbo, 1024), b_hi, 1u);
+              for (int k = 0; k < BK / UMMA_K; ++k) mma(ad + k * a_k16, bd + k * b_k16, k ? 1u : first);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t a_hi = ad + k * a_k16, b_hi = bd + k * b_k16;
+                mma(a_hi, b_hi, k ? 1u : first);
+                if (PB == 2) mma(a_hi, b_hi + b_pl16, 1u);
+                if (PA == 2) mma(a_hi + a_pl16, b_hi, 1u);
+              }
             }
             if (CG == 2) {
               tcgen05_commit_2sm(empty0 + 8 * s);                        // frees the stage in both CTAs when these MMAs retire
@@ -256,6 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           __syncwarp();
+          if (++s == static_cast<uint32_t>(STAGES)) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -273,6 +285,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const long long d_ld = p.d_ld, d_lo = p.d_lo;
     const bool is_f32 = p.d_dtype == VILCO_F32;
     const int d_fmt = p.d_dtype;
+    const bool has_rm = p.rowmul != nullptr;
+    // 16-byte vector loads of the per-column terms need aligned pointers; a 16-bit output with a residual takes the general path
+    const bool fast_ok = p.vec_ok && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
+                         (!colscale || (reinterpret_cast<uintptr_t>(colscale) & 15) == 0) && (is_f32 || resid == nullptr);
     uint32_t tc = 0;
     for (int t = worker; t < total_tiles; t += n_workers) {
       const int z = t / tiles_per_z, r = t - z * tiles_per_z;
@@ -288,121 +304,203 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float rm = 1.0f;                          // row multiplier of the accumulator row this lane owns
       if (p.rowmul && mrow0 + lane < p.M) rm = __ldg(p.rowmul + z2 * p.rowmul_zs + mrow0 + lane);
       const long long zoff = z1 * p.d_s1 + z2 * p.d_s2;
+      auto run_chunks = [&](auto act_c) {
+        constexpr int ACT = decltype(act_c)::value;   // -1: runtime `act` (slow path only)
       for (int c = chalf; c < BN / 32; c += 2) {
-        const int nb = n0 + c * 32;
-        if (nb >= p.N || mrow0 >= p.M) break;  // warp-uniform
-        // fp32 output with a residual: issue this chunk's 8 residual loads (16 B per lane each) BEFORE the accumulator is
-        // fetched and transposed, so their L2 / HBM latency overlaps that work instead of serialising 8 dependent round trips
-        float4 rs[8];
-        const bool pre = is_f32 && resid != nullptr && p.vec_ok && (nb + 31 < p.N);
-        if (pre) {
-          const int rsub = lane >> 3, g = lane & 7;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int mm = mrow0 + 4 * i + rsub;
-            rs[i] = mm < p.M ? __ldg(reinterpret_cast<const float4*>(resid + zoff + (long long)mm * d_ld + nb + 4 * g))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        uint32_t rr[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
-        // stage 1: raw accumulator row -> XOR-swizzled 32x32 transpose buffer (conflict-free 128-bit accesses)
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          *reinterpret_cast<uint4*>(sbuf + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
-              make_uint4(rr[4 * j4], rr[4 * j4 + 1], rr[4 * j4 + 2], rr[4 * j4 + 3]);
-        __syncwarp();
-        // stage 2: lanes own columns -> per-column vectors loaded once, wide fully coalesced stores
-        if (is_f32) {
-          // 8 lanes cover one 128-byte row segment, 4 rows per instruction
-          const int rsub = lane >> 3, g = lane & 7;
-          const int n = nb + 4 * g;
-          const bool vec = p.vec_ok && (n + 3 < p.N);
-          float b4[4] = {0.f, 0.f, 0.f, 0.f}, s4[4] = {1.f, 1.f, 1.f, 1.f};
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (n + u < p.N) {
-              if (bias) b4[u] = __ldg(bias + n + u);
-              if (colscale) s4[u] = __ldg(colscale + n + u);
-            }
-          float* Df = static_cast<float*>(p.D);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rloc = 4 * i + rsub;
-            const int mm = mrow0 + rloc;
-            const float rmr = __shfl_sync(0xffffffffu, rm, rloc);
-            if (mm < p.M && n < p.N) {
-              const float4 a = *reinterpret_cast<const float4*>(sbuf + rloc * 32 + ((g ^ (rloc & 7)) << 2));
-              float v[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) v[u] = apply_act((v[u] * alpha + b4[u]) * rmr, act) * s4[u];
-              const long long o = zoff + (long long)mm * d_ld + n;
-              const float f = resid_masked ? rmr : 1.0f;
-              if (vec) {
-                if (resid) {
-                  const float4 rv = pre ? rs[i] : *reinterpret_cast<const float4*>(resid + o);
-                  v[0] += rv.x * f; v[1] += rv.y * f; v[2] += rv.z * f; v[3] += rv.w * f;
-                }
-                *reinterpret_cast<float4*>(Df + o) = make_float4(v[0], v[1], v[2], v[3]);
-              } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (n + u < p.N) Df[o + u] = v[u] + (resid ? resid[o + u] * f : 0.0f);
-              }
-            }
-          }
-        } else {
-          // 4 lanes cover one 64-byte row segment (8 columns each), 8 rows per instruction
-          const int rsub = lane >> 2, g2 = (lane & 3) * 2;
-          const int n = nb + 4 * g2;
-          const bool vec = p.vec_ok && (n + 7 < p.N);
-          float b8[8], s8[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            b8[u] = (bias && n + u < p.N) ? __ldg(bias + n + u) : 0.f;
-            s8[u] = (colscale && n + u < p.N) ? __ldg(colscale + n + u) : 1.f;
-          }
-          uint16_t* Db = static_cast<uint16_t*>(p.D);
-#pragma unroll 2
-          for (int r0 = 0; r0 < 32; r0 += 8) {
-            const int rloc = r0 + rsub;
-            const int mm = mrow0 + rloc;
-            const float rmr = __shfl_sync(0xffffffffu, rm, rloc);
-            if (mm < p.M && n < p.N) {
-              const float4 a = *reinterpret_cast<const float4*>(sbuf + rloc * 32 + ((g2 ^ (rloc & 7)) << 2));
-              const float4 b = *reinterpret_cast<const float4*>(sbuf + rloc * 32 + (((g2 + 1) ^ (rloc & 7)) << 2));
-              float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] = apply_act((v[u] * alpha + b8[u]) * rmr, act) * s8[u];
-              const long long o = zoff + (long long)mm * d_ld + n;
+          const int nb = n0 + c * 32;
+          if (nb >= p.N || mrow0 >= p.M) break;  // warp-uniform
+          // ---- fast path: whole 32 x 32 chunk in range, 16-byte accesses allowed.  The epilogue is one of the two pipelines
+          // that bound a K = 1024 tile (8 warps x 4 chunks of it per 128 x 256 sub-tile), so this path has no bounds checks, no
+          // per-element branches, shared-space ld / st and vector loads of the per-column terms issued ahead of the TMEM read ----
+          if (fast_ok && (nb + 32 <= p.N) && (mrow0 + 32 <= p.M)) {
+            const uint32_t sb_u = smem_u32(sbuf);
+            if (is_f32) {
+              const int rsub = lane >> 3, g = lane & 7;
+              const int n = nb + 4 * g;
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+              if (colscale) s4 = __ldg(reinterpret_cast<const float4*>(colscale + n));
+              float* dptr = static_cast<float*>(p.D) + zoff + (long long)(mrow0 + rsub) * d_ld + n;
+              float4 rs[8];
               if (resid) {
-                const float f = resid_masked ? rmr : 1.0f;
+                const float* rptr = resid + zoff + (long long)(mrow0 + rsub) * d_ld + n;
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (n + u < p.N) v[u] += resid[o + u] * f;
+                for (int i = 0; i < 8; ++i) rs[i] = __ldg(reinterpret_cast<const float4*>(rptr + (long long)(4 * i) * d_ld));
               }
-              if (vec) {
+              uint32_t rr[32];
+              __syncwarp();
+              tmem_ld32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb_u + 4u * (lane * 32 + ((j4 ^ (lane & 7)) << 2))),
+                             "r"(rr[4 * j4]), "r"(rr[4 * j4 + 1]), "r"(rr[4 * j4 + 2]), "r"(rr[4 * j4 + 3]) : "memory");
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rloc = 4 * i + rsub;
+                const float rmr = has_rm ? __shfl_sync(0xffffffffu, rm, rloc) : 1.0f;
+                float4 a;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                             : "r"(sb_u + 4u * (rloc * 32 + ((g ^ (rloc & 7)) << 2))));
+                a.x = apply_act((a.x * alpha + b4.x) * rmr, ACT) * s4.x;
+                a.y = apply_act((a.y * alpha + b4.y) * rmr, ACT) * s4.y;
+                a.z = apply_act((a.z * alpha + b4.z) * rmr, ACT) * s4.z;
+                a.w = apply_act((a.w * alpha + b4.w) * rmr, ACT) * s4.w;
+                if (resid) {
+                  const float f = resid_masked ? rmr : 1.0f;
+                  a.x += rs[i].x * f; a.y += rs[i].y * f; a.z += rs[i].z * f; a.w += rs[i].w * f;
+                }
+                *reinterpret_cast<float4*>(dptr + (long long)(4 * i) * d_ld) = a;
+              }
+            } else {
+              const int rsub = lane >> 2, g2 = (lane & 3) * 2;
+              const int n = nb + 4 * g2;
+              float4 b8[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+              float4 s8[2] = {make_float4(1.f, 1.f, 1.f, 1.f), make_float4(1.f, 1.f, 1.f, 1.f)};
+              if (bias) { b8[0] = __ldg(reinterpret_cast<const float4*>(bias + n)); b8[1] = __ldg(reinterpret_cast<const float4*>(bias + n + 4)); }
+              if (colscale) { s8[0] = __ldg(reinterpret_cast<const float4*>(colscale + n)); s8[1] = __ldg(reinterpret_cast<const float4*>(colscale + n + 4)); }
+              uint16_t* dptr = static_cast<uint16_t*>(p.D) + zoff + (long long)(mrow0 + rsub) * d_ld + n;
+              uint32_t rr[32];
+              __syncwarp();
+              tmem_ld32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb_u + 4u * (lane * 32 + ((j4 ^ (lane & 7)) << 2))),
+                             "r"(rr[4 * j4]), "r"(rr[4 * j4 + 1]), "r"(rr[4 * j4 + 2]), "r"(rr[4 * j4 + 3]) : "memory");
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rloc = 8 * i + rsub;
+                const float rmr = has_rm ? __shfl_sync(0xffffffffu, rm, rloc) : 1.0f;
+                float v[8];
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                             : "r"(sb_u + 4u * (rloc * 32 + ((g2 ^ (rloc & 7)) << 2))));
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                             : "r"(sb_u + 4u * (rloc * 32 + (((g2 + 1) ^ (rloc & 7)) << 2))));
+                const float bb[8] = {b8[0].x, b8[0].y, b8[0].z, b8[0].w, b8[1].x, b8[1].y, b8[1].z, b8[1].w};
+                const float ss[8] = {s8[0].x, s8[0].y, s8[0].z, s8[0].w, s8[1].x, s8[1].y, s8[1].z, s8[1].w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = apply_act((v[u] * alpha + bb[u]) * rmr, ACT) * ss[u];
                 uint32_t h[4], l[4];
+                uint16_t* o = dptr + (long long)(8 * i) * d_ld;
                 if (d_lo) {
 #pragma unroll
                   for (int u = 0; u < 4; ++u) split16x2(v[2 * u], v[2 * u + 1], d_fmt, h[u], l[u]);
-                  *reinterpret_cast<uint4*>(Db + o) = make_uint4(h[0], h[1], h[2], h[3]);
-                  *reinterpret_cast<uint4*>(Db + d_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+                  *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(o + d_lo) = make_uint4(l[0], l[1], l[2], l[3]);
                 } else {
 #pragma unroll
                   for (int u = 0; u < 4; ++u) h[u] = pack16x2(v[2 * u], v[2 * u + 1], d_fmt);
-                  *reinterpret_cast<uint4*>(Db + o) = make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
                 }
-              } else {
+              }
+            }
+            continue;
+          }
+          // general path (tails, unaligned pointers, 16-bit output with a residual)
+          uint32_t rr[32];
+          __syncwarp();
+          tmem_ld32(tmem_base + acc * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16) + c * 32, rr);
+          // stage 1: raw accumulator row -> XOR-swizzled 32x32 transpose buffer (conflict-free 128-bit accesses)
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                  if (n + u < p.N) store16_split(Db, o + u, d_lo, v[u], d_fmt);
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<uint4*>(sbuf + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+                make_uint4(rr[4 * j4], rr[4 * j4 + 1], rr[4 * j4 + 2], rr[4 * j4 + 3]);
+          __syncwarp();
+          // stage 2: lanes own columns -> per-column vectors loaded once, wide fully coalesced stores
+          if (is_f32) {
+            // 8 lanes cover one 128-byte row segment, 4 rows per instruction
+            const int rsub = lane >> 3, g = lane & 7;
+            const int n = nb + 4 * g;
+            const bool vec = p.vec_ok && (n + 3 < p.N);
+            float b4[4] = {0.f, 0.f, 0.f, 0.f}, s4[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (n + u < p.N) {
+                if (bias) b4[u] = __ldg(bias + n + u);
+                if (colscale) s4[u] = __ldg(colscale + n + u);
+              }
+            float* Df = static_cast<float*>(p.D);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rloc = 4 * i + rsub;
+              const int mm = mrow0 + rloc;
+              const float rmr = __shfl_sync(0xffffffffu, rm, rloc);
+              if (mm < p.M && n < p.N) {
+                const float4 a = *reinterpret_cast<const float4*>(sbuf + rloc * 32 + ((g ^ (rloc & 7)) << 2));
+                float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = apply_act((v[u] * alpha + b4[u]) * rmr, act) * s4[u];
+                const long long o = zoff + (long long)mm * d_ld + n;
+                const float f = resid_masked ? rmr : 1.0f;
+                if (vec) {
+                  if (resid) {
+                    const float4 rv = *reinterpret_cast<const float4*>(resid + o);
+                    v[0] += rv.x * f; v[1] += rv.y * f; v[2] += rv.z * f; v[3] += rv.w * f;
+                  }
+                  *reinterpret_cast<float4*>(Df + o) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    if (n + u < p.N) Df[o + u] = v[u] + (resid ? resid[o + u] * f : 0.0f);
+                }
+              }
+            }
+          } else {
+            // 4 lanes cover one 64-byte row segment (8 columns each), 8 rows per instruction
+            const int rsub = lane >> 2, g2 = (lane & 3) * 2;
+            const int n = nb + 4 * g2;
+            const bool vec = p.vec_ok && (n + 7 < p.N);
+            float b8[8], s8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              b8[u] = (bias && n + u < p.N) ? __ldg(bias + n + u) : 0.f;
+              s8[u] = (colscale && n + u < p.N) ? __ldg(colscale + n + u) : 1.f;
+            }
+            uint16_t* Db = static_cast<uint16_t*>(p.D);
+#pragma unroll 2
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              const int rloc = r0 + rsub;
+              const int mm = mrow0 + rloc;
+              const float rmr = __shfl_sync(0xffffffffu, rm, rloc);
+              if (mm < p.M && n < p.N) {
+                const float4 a = *reinterpret_cast<const float4*>(sbuf + rloc * 32 + ((g2 ^ (rloc & 7)) << 2));
+                const float4 b = *reinterpret_cast<const float4*>(sbuf + rloc * 32 + (((g2 + 1) ^ (rloc & 7)) << 2));
+                float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = apply_act((v[u] * alpha + b8[u]) * rmr, act) * s8[u];
+                const long long o = zoff + (long long)mm * d_ld + n;
+                if (resid) {
+                  const float f = resid_masked ? rmr : 1.0f;
+#pragma unroll
+                  for (int u = 0; u < 8; ++u)
+                    if (n + u < p.N) v[u] += resid[o + u] * f;
+                }
+                if (vec) {
+                  uint32_t h[4], l[4];
+                  if (d_lo) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) split16x2(v[2 * u], v[2 * u + 1], d_fmt, h[u], l[u]);
+                    *reinterpret_cast<uint4*>(Db + o) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(Db + d_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+                  } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) h[u] = pack16x2(v[2 * u], v[2 * u + 1], d_fmt);
+                    *reinterpret_cast<uint4*>(Db + o) = make_uint4(h[0], h[1], h[2], h[3]);
+                  }
+                } else {
+#pragma unroll
+                  for (int u = 0; u < 8; ++u)
+                    if (n + u < p.N) store16_split(Db, o + u, d_lo, v[u], d_fmt);
+                }
               }
             }
           }
         }
-      }
+      };
+      if (act == VILCO_ACT_NONE) run_chunks(std::integral_constant<int, VILCO_ACT_NONE>{});
+      else if (act == VILCO_ACT_RELU) run_chunks(std::integral_constant<int, VILCO_ACT_RELU>{});
+      else run_chunks(std::integral_constant<int, VILCO_ACT_GELU>{});
       // this warp is done reading the accumulator stage
       tcgen05_fence_before();
       __syncwarp();
