@@ -154,6 +154,35 @@ def timing():
             del A, W, D
 
 
+def bwd_timing():
+    """gradient-GEMM shapes (MN-major operands): one CTA per 128-wide tile (impl 2) vs CTA pairs (impl 3) vs automatic"""
+    R = 32768
+    def dgrad(M, N, K, impl):
+        A = planes(torch.randn(M, K, device=dev), F16, 1)
+        Bt = planes(torch.randn(K, N, device=dev) * 0.05, F16, 1)          # W (K rows = out features, N cols): MN-major B
+        D = torch.empty(M, N, device=dev)
+        return lambda: L.gemm(A, Bt, D, M=M, N=N, K=K, a_rows=M, a_ld=K, b_ld=N, b_major=1, d_ld=N, impl=impl, a_lo=0, b_lo=0)
+    def wgradf(Mo, No, Rr, S, impl):
+        dz = planes(torch.randn(Rr, Mo, device=dev), F16, 1)
+        x = planes(torch.randn(Rr, No, device=dev), F16, 1)
+        part = torch.empty(S, Mo, No, device=dev)
+        ch = Rr // S
+        return lambda: L.gemm(dz, x, part, M=Mo, N=No, K=ch, a_rows=Mo, a_ld=Mo, a_major=1, a_s=(ch * Mo, 0), Z=(S, 1), b_ld=No,
+                              b_s=(ch * No, 0), b_batched=True, b_major=1, d_ld=No, d_s=(Mo * No, 0), impl=impl, a_lo=0, b_lo=0)
+    for M in (32768, 16384, 8192, 4096, 2048, 1024):
+        for impl in (2, 3, 0):
+            timeit(dgrad(M, 1024, 1024, impl), 2.0 * M * 1024 * 1024, f"dgrad M{M} N1024 K1024 impl{impl}")
+    for impl in (2, 3, 0):
+        timeit(dgrad(R, 4096, 1024, impl), 2.0 * R * 4096 * 1024, f"dgrad M{R} N4096 K1024 impl{impl}")
+        timeit(dgrad(R, 1024, 4096, impl), 2.0 * R * 4096 * 1024, f"dgrad M{R} N1024 K4096 impl{impl}")
+    for (Mo, No, Rr) in ((1024, 1024, R), (4096, 1024, R), (1024, 4096, R), (1024, 1024, 8192), (1024, 1024, 2048)):
+        for S in (1, 2, 4, 8, 16):
+            if Rr // S < 512:
+                continue
+            for impl in (2, 3):
+                timeit(wgradf(Mo, No, Rr, S, impl), 2.0 * Mo * No * Rr, f"wgrad {Mo}x{No} R{Rr} S{S} impl{impl}")
+
+
 def sweep():
     """per-tile cost model: time(K) at fixed N and time(N) at fixed K, plain epilogue, one fp16 plane"""
     M = 32768
@@ -181,6 +210,8 @@ if __name__ == "__main__":
         check()
     if "time" in what:
         timing()
+    if "bwd" in what:
+        bwd_timing()
     if "sweep" in what:
         sweep()
     sys.exit(1 if bad else 0)

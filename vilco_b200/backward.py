@@ -54,8 +54,14 @@ def wgrad(dz, x2, Mo, No, R, alpha=1.0, out=None):
     of the 148 SMs idle; partials are summed by vilco_colsum.  out: fp32 (Mo, No) buffer to ACCUMULATE into (the
     parameter's .grad view)."""
     alpha = alpha * ops.ginv()        # dz is a gradient-plane operand
-    tiles = ((Mo + 127) // 128) * ((No + 127) // 128)
-    S = min(16, 148 // tiles) if tiles < 100 else 1
+    # split-K so that the 256 x 256 pair tiles (vilco_gemm picks them from 37 tiles on) fill the 74 CTA pairs once: measured
+    # (tools/gemm2_probe.py bwd) C x C at 32768 rows 141 -> 81 us with S = 4 pair tiles instead of S = 2 single-CTA tiles
+    if Mo > 128 and No >= 256:
+        tiles = ((Mo + 255) // 256) * ((No + 255) // 256)
+        S = min(16, 74 // tiles) if tiles < 37 else 1
+    else:
+        tiles = ((Mo + 127) // 128) * ((No + 127) // 128)
+        S = min(16, 148 // tiles) if tiles < 100 else 1
     while S > 1 and (R % (8 * S) != 0 or R // S < 512):
         S -= 1
     if S <= 1:

@@ -1021,11 +1021,13 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
     // would leave most of the 148 SMs idle
     BN = (t128 * 2 <= num_sms()) ? 64 : 128;
   }
-  // CTA pairs (cta_group::2, 256 x 256 or 256 x 128 tiles) for the big problems (any operand majors: the gradient GEMMs read
-  // their operands MN-major): at least ~2 waves of 256 x 256 tiles
-  if (g->band_hi <= g->band_lo && force_cg != 1 && g->N >= 128) {
+  // CTA pairs (cta_group::2, 256 x 256 or 256 x 128 tiles), any operand majors (the gradient GEMMs read their operands MN-major).
+  // The main loop is bound by the L2 -> shared-memory stream, not by the MMA rate (ncu: the MMA warp waits on the full
+  // barriers), and a pair tile moves half the bytes per FLOP of a 128 x 128 tile: measured 1.5 - 1.9x faster per launch as soon
+  // as the 256 x 256 tiles fill half of the 74 CTA pairs (tools/gemm2_probe.py bwd), so that is the threshold.
+  if (g->band_hi <= g->band_lo && force_cg != 1 && g->N >= 128 && (g->M > 128 || force_cg == 2)) {
     const long long t256 = (long long)((g->N + 255) / 256) * ((g->M + 255) / 256) * Z;
-    if (g->N >= 256 && (t256 >= 2 * (num_sms() / 2) || force_cg == 2)) { BN = 256; CG = 2; }
+    if (g->N >= 256 && (t256 >= num_sms() / 4 || force_cg == 2)) { BN = 256; CG = 2; }
     else if (t128 / 2 >= 2 * (num_sms() / 2) || force_cg == 2) { BN = 128; CG = 2; }
   }
 
