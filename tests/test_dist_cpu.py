@@ -2,6 +2,7 @@
 ordered gather of results."""
 import os
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -60,7 +61,7 @@ class _Toy(torch.nn.Module):
         return {"final_loss": ((self.a(x) * self.b) ** 2).mean()}
 
 
-def _train_worker(rank, world, port, q):
+def _train_worker(rank, world, port, q, comm="fp32"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from vilco_b200.dist import shard_indices
@@ -70,7 +71,7 @@ def _train_worker(rank, world, port, q):
         model.b.add_(rank)            # deliberately different before the broadcast
     broadcast_parameters(model)
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
-    tr = Trainer(model, opt, clip_grad_l2norm=1.0)
+    tr = Trainer(model, opt, clip_grad_l2norm=1.0, grad_comm=comm)
     g = torch.Generator().manual_seed(5)
     videos = [{"feats": torch.randn(4, generator=g)} for _ in range(6)]
     for _ in range(3):
@@ -80,13 +81,15 @@ def _train_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_data_parallel_training_step_matches_single_process():
-    """2 ranks x 3 videos with gradient all-reduce == 1 process x 6 videos (equal shard sizes, mean loss)."""
+@pytest.mark.parametrize("comm,atol", [("fp32", 1e-6), ("bf16", 2e-3)])
+def test_data_parallel_training_step_matches_single_process(comm, atol):
+    """2 ranks x 3 videos with gradient all-reduce == 1 process x 6 videos (equal shard sizes, mean loss): exactly with fp32
+    buckets, to bf16 rounding of the exchanged gradients with the default bf16-on-the-wire buckets."""
     from vilco_b200.trainer import Trainer
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, comm)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
@@ -102,4 +105,4 @@ def test_data_parallel_training_step_matches_single_process():
     for rank, params, attached in out:
         assert attached
         for a, b in zip(params, model.parameters()):
-            assert torch.allclose(torch.tensor(a), b.detach().reshape(-1), atol=1e-6), rank
+            assert torch.allclose(torch.tensor(a), b.detach().reshape(-1), atol=atol), rank

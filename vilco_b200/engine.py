@@ -112,8 +112,20 @@ def sinusoid_pe_table(max_len, C, device):
     return (torch.from_numpy(tab.astype(np.float32)) / (C ** 0.5)).to(device).contiguous()
 
 
+_POS_EMB = {}
+
+
 def xlnet_pos_emb(T, C, device):
-    """relative_positional_encoding (bi, no clamp) — modeling_xlnet_x.py:1029-1066 -> (2T, C) operand."""
+    """relative_positional_encoding (bi, no clamp) — modeling_xlnet_x.py:1029-1066 -> (2T, C) operand.  Constant per
+    (T, C, device, operand mode): built and uploaded once (a per-step upload from pageable memory stalls the host until the
+    stream has drained)."""
+    key = (T, C, str(device), ops.precision())
+    if key not in _POS_EMB:
+        _POS_EMB[key] = _xlnet_pos_emb(T, C, device)
+    return _POS_EMB[key]
+
+
+def _xlnet_pos_emb(T, C, device):
     freq_seq = torch.arange(0, C, 2.0, dtype=torch.float)
     inv_freq = 1 / torch.pow(10000, (freq_seq / C))
     pos_seq = torch.arange(T, -T, -1.0)
@@ -351,6 +363,17 @@ class Pyramid:
         for o, n in zip(self.off, self.lens):
             gap[o:o + n] = 0
         self.gap_rows = gap.to(device)  # 1 = gap (always zero) row
+
+    _cache = {}
+
+    @classmethod
+    def cached(cls, lens, device):
+        """one instance per (level lengths, device): the training step reuses the gap-row mask, the point table and the
+        level one-hot instead of re-uploading them every step"""
+        key = (tuple(int(n) for n in lens), str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(lens, device)
+        return cls._cache[key]
 
 
 def neck_heads_fwd(W, cfg, feats, masks, pyr=None):

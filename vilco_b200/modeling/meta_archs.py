@@ -701,10 +701,10 @@ class PtTransformer(nn.Module):
         gt_cls, gt_off, wc, wl, wr = self._label_points(pyr, [x["segments"] for x in vl], [x["labels"] for x in vl])
         with torch.no_grad():
             gt_cls, gt_off = gt_cls.detach(), gt_off.detach()
-            present = torch.zeros(B, K)
+            present = torch.zeros(B, K, pin_memory=dev.type == "cuda")
             for i, x in enumerate(vl):
                 present[i, x["labels"].cpu()] = 1
-            present = present.to(dev)
+            present = present.to(dev, non_blocking=True)
             sums = torch.zeros(4, device=dev)
             scratch = torch.zeros(B * K, device=dev, dtype=torch.int32)
             wcd, wld, wrd = wc.detach().contiguous(), wl.detach().contiguous(), wr.detach().contiguous()
@@ -913,12 +913,15 @@ class PtTransformer(nn.Module):
                 pts[o:o + n] = list(self.point_generator.buffer_points)[l][:n].cpu()
             pts = pyr.pts = pts.to(dev)
         B, G = len(gt_segments), max(int(s.shape[0]) for s in gt_segments)
-        seg_h, lab_h, val_h = torch.zeros(B, G, 2), torch.zeros(B, G, dtype=torch.long), torch.zeros(B, G, dtype=torch.bool)
+        pin = dev.type == "cuda"      # pinned staging + non-blocking copies: a pageable upload would stall the host mid-step
+        seg_h = torch.zeros(B, G, 2, pin_memory=pin)
+        lab_h = torch.zeros(B, G, dtype=torch.long, pin_memory=pin)
+        val_h = torch.zeros(B, G, dtype=torch.bool, pin_memory=pin)
         for i, (sg, lb) in enumerate(zip(gt_segments, gt_labels)):
             n = sg.shape[0]
             seg_h[i, :n], lab_h[i, :n], val_h[i, :n] = sg.float().cpu(), lb.cpu(), True
             seg_h[i, n:, 1] = 1.0                      # padded segments get length 1 (never selected; avoids 0/0)
-        seg, lab, valid = seg_h.to(dev), lab_h.to(dev), val_h.to(dev)
+        seg, lab, valid = seg_h.to(dev, non_blocking=True), lab_h.to(dev, non_blocking=True), val_h.to(dev, non_blocking=True)
         t, stride = pts[None, :, 0, None], pts[None, :, 3, None].clamp(min=1e-9)          # (1,P,1)
         s0, s1 = seg[:, None, :, 0], seg[:, None, :, 1]                                    # (B,1,G)
         lens = (s1 - s0).expand(B, pyr.P, G)

@@ -31,11 +31,11 @@ bf16 = torch.bfloat16        # also the `out_dtype` marker meaning "operand plan
 f16 = torch.float16
 f32 = torch.float32
 
-_MODES = {  # name -> (activation plane dtype, default planes, planes of the sensitive contractions)
-    "mixed": (f16, 1, 2), "fp16x3": (f16, 2, 2), "fp16": (f16, 1, 1), "bf16x3": (bf16, 2, 2), "bf16": (bf16, 1, 1),
+_MODES = {  # name -> (activation plane dtype, default planes, planes of the sensitive contractions, gradient planes)
+    "mixed": (f16, 1, 2, 1), "fp16x3": (f16, 2, 2, 2), "fp16": (f16, 1, 1, 1), "bf16x3": (bf16, 2, 2, 2), "bf16": (bf16, 1, 1, 1),
 }
 _mode = None
-ACT_DTYPE, PLANES, PLANES_HI = bf16, 2, 2
+ACT_DTYPE, PLANES, PLANES_HI, GRAD_PLANES = bf16, 2, 2, 2
 GRAD_SCALE = 1.0
 FUSED_ATTN = os.environ.get("VILCO_FUSED_ATTN", "1") == "1"  # 0: materialised QK^T -> softmax -> PV kernels
 
@@ -43,10 +43,10 @@ FUSED_ATTN = os.environ.get("VILCO_FUSED_ATTN", "1") == "1"  # 0: materialised Q
 def set_precision(name):
     """Select the operand-format policy (see the module docstring).  Weights must be re-packed after a change (the model
     does so: its packed-weight cache is keyed on `precision()`)."""
-    global _mode, ACT_DTYPE, PLANES, PLANES_HI, GRAD_SCALE
+    global _mode, ACT_DTYPE, PLANES, PLANES_HI, GRAD_PLANES, GRAD_SCALE
     assert name in _MODES, name
     _mode = name
-    ACT_DTYPE, PLANES, PLANES_HI = _MODES[name]
+    ACT_DTYPE, PLANES, PLANES_HI, GRAD_PLANES = _MODES[name]
     GRAD_SCALE = float(2 ** int(os.environ.get("VILCO_GRAD_SCALE_LOG2", "10"))) if ACT_DTYPE == f16 else 1.0
     if os.path.exists(L.LIB_PATH):   # the library holds the plane format / gradient scale the non-GEMM kernels use
         L.check(L.lib().vilco_set_plane_format(L.F16 if ACT_DTYPE == f16 else L.BF16), "vilco_set_plane_format")
@@ -71,7 +71,7 @@ def _i64(v):
 # Optional fast training mode: the backward GEMMs read only the hi plane of every operand.  Gradients then carry plain-bf16
 # operand rounding (~3e-3 relative, what bf16 autocast training has); the forward pass, the losses and therefore every parity
 # statement about outputs are unaffected.  Default: gradient planes split (hi + lo).
-BWD_PRECISION = os.environ.get("VILCO_BWD_PRECISION", "split")
+BWD_PRECISION = os.environ.get("VILCO_BWD_PRECISION", "mode")
 _single = False
 
 
@@ -93,7 +93,13 @@ def lo(t):
 
 
 def grad_planes():
-    return 1 if BWD_PRECISION == "bf16" else 2
+    """planes of a gradient operand: the mode's (one fp16 plane x 2^10 in `mixed`, hi + lo in the exact modes) unless
+    VILCO_BWD_PRECISION forces `split` (2) or `single` / `bf16` (1)"""
+    if BWD_PRECISION == "split":
+        return 2
+    if BWD_PRECISION in ("single", "bf16"):
+        return 1
+    return GRAD_PLANES
 
 
 def ginv():

@@ -524,17 +524,22 @@ def neck_heads(tp, cfg, feats, masks):
     W = tp.W
     B, C = feats[0].shape[0], cfg.embd_dim
     dev = feats[0].v.device
-    pyr = E.Pyramid([f.shape[1] for f in feats], dev)
+    pyr = E.Pyramid.cached([f.shape[1] for f in feats], dev)
     P = pyr.P
     lv = [tp.ln(f, f"neck.fpn_norms.{l}.weight", f"neck.fpn_norms.{l}.bias", want16=False) for l, f in enumerate(feats)]
     fpn = V(torch.zeros(B, P, C, device=dev, dtype=f32))
     pmask = torch.zeros(B, P, device=dev, dtype=f32)
-    lvl_of_row = torch.full((P,), -1, device=dev, dtype=torch.long)
+    if getattr(pyr, "lvl_of_row", None) is None:
+        lvl = torch.full((P,), -1, dtype=torch.long)
+        for l in range(len(lv)):
+            lvl[pyr.off[l]:pyr.off[l] + pyr.lens[l]] = l
+        pyr.lvl_of_row = lvl.to(dev)
+        pyr.lvl_onehot = (pyr.lvl_of_row[None, :] == torch.arange(len(lv), device=dev)[:, None]).float()    # (levels, P)
+    lvl_of_row = pyr.lvl_of_row
     for l, (f, mk) in enumerate(zip(lv, masks)):
         o, n = pyr.off[l], pyr.lens[l]
         fpn.v[:, o:o + n] = f.v
         pmask[:, o:o + n] = mk
-        lvl_of_row[o:o + n] = l
 
     def cat_bwd():
         if fpn.g is None:
@@ -564,8 +569,9 @@ def neck_heads(tp, cfg, feats, masks):
                     return
                 tp.acc(z, ops.ew(0, s.g, rowmul=sv))
                 r = (s.g * z.v).sum(-1).sum(0)            # (P,) tiny glue reduction for the per-level Scale parameters
+                per_level = pyr.lvl_onehot @ r            # (levels,): no boolean indexing (it synchronises)
                 for l in range(len(feats)):
-                    tp.accp(f"reg_head.scale.{l}.scale", r[lvl_of_row == l].sum().reshape(1))
+                    tp.accp(f"reg_head.scale.{l}.scale", per_level[l:l + 1])
             tp.nodes.append(sc_bwd)
             outs.append(tp.relu(s))
     return outs[0], outs[1], pmask, pyr, lv
