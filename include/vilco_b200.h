@@ -248,6 +248,14 @@ int vilco_attention(const void* q, int64_t q_lo, const void* k, const void* v, i
 int vilco_xl_attention(const void* qw, const void* qr, const void* k, const void* v, const void* kr, const float* kmask,
                        void* out, int B, int H, int T, int C, float scale, void* stream);
 
+/* Single-pass masked self-attention (MaskedMHCA core, MQ/libs/modeling/blocks.py:351-410: att = softmax(q k^T * scale with
+ * masked_fill(~kv_mask, -inf)); out = att @ v) for single-plane operands, head dim 64, T a multiple of 128 (<= 2048) — the
+ * kernel of vilco_xl_attention without the position branch (online softmax with lazy rescale, one pass over the keys).
+ * q, k, v, out: (B, T, C) 16-bit planes; kmask (B, T) fp32, 0 = padded key, or NULL.  vilco_attention remains the general
+ * entry (Tq != Tk, tails, two planes). */
+int vilco_self_attention(const void* q, const void* k, const void* v, const float* kmask, void* out, int B, int H, int T, int C,
+                         float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Backward-pass building blocks (training; token-major fp32 gradients).  The GEMM-shaped gradients reuse vilco_gemm:
  *   dX = dZ W      : A = dZ (K-major over the output channels), B = W as MN-major operand (b_major = 1)

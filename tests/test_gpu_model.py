@@ -113,6 +113,29 @@ def test_local_masked_mhca_vs_reference_golden(name, window):
     assert rel_max(y.cpu().numpy(), g[name + "_y"]) < TOL
 
 
+@pytest.mark.parametrize("B,T,H,valid", [(2, 1024, 16, [1024, 700]), (3, 128, 2, [128, 1, 77]), (1, 512, 4, [333]), (2, 2048, 1, [2048, 1500])])
+def test_single_pass_self_attention_kernel(B, T, H, valid):
+    """single-pass masked self-attention (csrc/xlattn.cu, REL = false) against float64 softmax attention on the same fp16
+    operands (the un-normalised P is rounded to fp16 for the P V product: 8e-4 at T = 2048, 5e-4 at the MQ lengths) and against the two-pass kernel it replaces"""
+    from vilco_b200 import ops
+    with precision("mixed"):
+        gen = torch.Generator(device="cuda").manual_seed(T + H)
+        C = H * 64
+        q, k, v = (ops.split16(torch.randn(B, T, C, device="cuda", generator=gen) * s, planes=1) for s in (1.5, 1.5, 1.0))
+        vl = torch.tensor(valid, device="cuda")
+        mask = (torch.arange(T, device="cuda")[None, :] < vl[:, None]).float()
+        out = ops.self_attention(q, k, v, mask, H, 0.125)
+        two = ops.attention(q, k, v, mask, H, 0.125)
+        hd = lambda t: t[0].double().view(B, T, H, 64).transpose(1, 2)     # noqa: E731
+        att = (hd(q) @ hd(k).transpose(-2, -1)) * 0.125
+        att = att.masked_fill(~(mask > 0)[:, None, None, :], float("-inf"))
+        ref = (torch.softmax(att, -1) @ hd(v)).transpose(1, 2).reshape(B, T, C)
+        e1 = float((out[0].double() - ref).abs().max() / ref.abs().max())
+        e2 = float((two[0].double() - ref).abs().max() / ref.abs().max())
+        print(f"self-attention T{T} H{H}: single-pass {e1:.2e}, two-pass {e2:.2e}")
+        assert torch.isfinite(out.float()).all() and e1 < 8e-4
+
+
 def _banded_attention_f64(q, k, v, valid, H, W, rel_pe):
     """dense float64 restatement of the banded attention core (oracle/mq_oracle.py:local_masked_mhca, lines 96-110) on operands
     already rounded to their planes"""

@@ -55,6 +55,10 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// REL = true: XLNet relative attention as described above.  REL = false: plain masked self-attention (MaskedMHCA core,
+// blocks.py:351-410) with the same single-pass structure — no position branch, padded keys invisible to every query, 256 TMEM
+// columns and ~83 KB of shared memory, so two CTAs share an SM and one CTA's softmax overlaps the other's MMAs.
+template <bool REL>
 __global__ void __launch_bounds__(XL_THREADS, 1)
 xl_attn_kernel(const __grid_constant__ CUtensorMap tmQw, const __grid_constant__ CUtensorMap tmQr,
                const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -62,13 +66,13 @@ xl_attn_kernel(const __grid_constant__ CUtensorMap tmQw, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQw = smem;
-  uint8_t* sQr = sQw + XL_TILE;
-  uint8_t* sK = sQr + XL_TILE;
-  uint8_t* sR = sK + XL_TILE;                      // 256 k_r rows: 32 KB
-  uint8_t* sV = sR + 2 * XL_TILE;
+  uint8_t* sQr = sQw + XL_TILE;                    // (REL only)
+  uint8_t* sK = sQr + (REL ? XL_TILE : 0);
+  uint8_t* sR = sK + XL_TILE;                      // 256 k_r rows: 32 KB (REL only)
+  uint8_t* sV = sR + (REL ? 2 * XL_TILE : 0);
   uint8_t* sP = sV + XL_TILE;                      // 128 rows x 128 keys = two 64-key K-major blocks
   float* s_skew = reinterpret_cast<float*>(sP + 2 * XL_TILE);
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_skew) + XL_SKEW_BYTES);   // key validity bits
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_skew) + (REL ? XL_SKEW_BYTES : 0));   // key validity bits
   float* s_x = reinterpret_cast<float*>(s_bits + XL_MAX_T / 32);     // [2 tile parities][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_x + 2 * 2 * 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -97,7 +101,8 @@ xl_attn_kernel(const __grid_constant__ CUtensorMap tmQw, const __grid_constant__
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(REL ? 512 : 256)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -113,24 +118,26 @@ xl_attn_kernel(const __grid_constant__ CUtensorMap tmQw, const __grid_constant__
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tBD = tmem_base + 128, tO = tmem_base + 384;
+  const uint32_t tS = tmem_base, tBD = tmem_base + 128, tO = tmem_base + (REL ? 384 : 128);
 
   if (warp == 0) {
     if (lane == 0) {
       int c[4];
-      mbar_expect_tx(qfull, 2 * XL_TILE);
+      mbar_expect_tx(qfull, (REL ? 2 : 1) * XL_TILE);
       c[0] = 0; c[p.q_slot_row] = q0; c[p.q_slot_z1] = h; c[p.q_slot_z2] = b;
       tma_load_5d(smem_u32(sQw), &tmQw, qfull, c[0], c[1], c[2], c[3], 0);
-      tma_load_5d(smem_u32(sQr), &tmQr, qfull, c[0], c[1], c[2], c[3], 0);
+      if (REL) tma_load_5d(smem_u32(sQr), &tmQr, qfull, c[0], c[1], c[2], c[3], 0);
       for (int j = 0; j < nkv; ++j) {
         const uint32_t ph = j & 1;
         mbar_wait(kempty, ph ^ 1);
-        mbar_expect_tx(kfull, 3 * XL_TILE);
+        mbar_expect_tx(kfull, (REL ? 3 : 1) * XL_TILE);
         c[0] = 0; c[p.k_slot_row] = j * XL_BKV; c[p.k_slot_z1] = h; c[p.k_slot_z2] = b;
         tma_load_5d(smem_u32(sK), &tmK, kfull, c[0], c[1], c[2], c[3], 0);
-        int r[4];
-        r[0] = 0; r[p.r_slot_row] = p.T + j * XL_BKV - q0 - (XL_BQ - 1); r[p.r_slot_z1] = h; r[p.r_slot_z2] = 0;
-        tma_load_5d(smem_u32(sR), &tmR, kfull, r[0], r[1], r[2], r[3], 0);     // one 256-row box (row 2T reads as zero)
+        if (REL) {
+          int r[4];
+          r[0] = 0; r[p.r_slot_row] = p.T + j * XL_BKV - q0 - (XL_BQ - 1); r[p.r_slot_z1] = h; r[p.r_slot_z2] = 0;
+          tma_load_5d(smem_u32(sR), &tmR, kfull, r[0], r[1], r[2], r[3], 0);     // one 256-row box (row 2T reads as zero)
+        }
         mbar_wait(vempty, ph ^ 1);
         mbar_expect_tx(vfull, XL_TILE);
         tma_load_5d(smem_u32(sV), &tmV, vfull, c[0], c[1], c[2], c[3], 0);
@@ -168,10 +175,12 @@ xl_attn_kernel(const __grid_constant__ CUtensorMap tmQw, const __grid_constant__
         for (int k = 0; k < XL_D / UMMA_K; ++k)
           tcgen05_mma_f16(tS, make_smem_desc(smem_u32(sQw) + k * 32, 16, 1024), make_smem_desc(smem_u32(sK) + k * 32, 16, 1024),
                           idesc_s, k > 0 ? 1u : 0u);
+        if (REL) {
 #pragma unroll
-        for (int k = 0; k < XL_D / UMMA_K; ++k)
-          tcgen05_mma_f16(tBD, make_smem_desc(smem_u32(sQr) + k * 32, 16, 1024), make_smem_desc(smem_u32(sR) + k * 32, 16, 1024),
-                          idesc_r, k > 0 ? 1u : 0u);
+          for (int k = 0; k < XL_D / UMMA_K; ++k)
+            tcgen05_mma_f16(tBD, make_smem_desc(smem_u32(sQr) + k * 32, 16, 1024), make_smem_desc(smem_u32(sR) + k * 32, 16, 1024),
+                            idesc_r, k > 0 ? 1u : 0u);
+        }
         tcgen05_commit(kempty);
         tcgen05_commit(sfull);
       }
@@ -203,22 +212,28 @@ xl_attn_kernel(const __grid_constant__ CUtensorMap tmQw, const __grid_constant__
         // position scores: the 64-column window [base, base + 64) covers columns c + 127 - row for every lane of the warp
         const int base = c0 + 96 - 32 * q;
         __syncwarp();
-        tmem_ld32(tBD + lane_addr + base, r);
+        if (REL) {
+          tmem_ld32(tBD + lane_addr + base, r);
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          *reinterpret_cast<uint4*>(my_skew + 4 * t) = make_uint4(r[4 * t], r[4 * t + 1], r[4 * t + 2], r[4 * t + 3]);
-        tmem_ld32(tBD + lane_addr + base + 32, r);
+          for (int t = 0; t < 8; ++t)
+            *reinterpret_cast<uint4*>(my_skew + 4 * t) = make_uint4(r[4 * t], r[4 * t + 1], r[4 * t + 2], r[4 * t + 3]);
+          tmem_ld32(tBD + lane_addr + base + 32, r);
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          *reinterpret_cast<uint4*>(my_skew + 32 + 4 * t) = make_uint4(r[4 * t], r[4 * t + 1], r[4 * t + 2], r[4 * t + 3]);
+          for (int t = 0; t < 8; ++t)
+            *reinterpret_cast<uint4*>(my_skew + 32 + 4 * t) = make_uint4(r[4 * t], r[4 * t + 1], r[4 * t + 2], r[4 * t + 3]);
+        }
         tmem_ld32(tS + lane_addr + c0, r);             // content scores
         const uint32_t bits = s_bits[(j * XL_BKV + c0) >> 5];
         const int jj0 = j * XL_BKV + c0;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float v = (__uint_as_float(r[c]) + my_skew[sh + c]) * sc2;
-          const bool ok = ((bits >> c) & 1u) || (jj0 + c == gi);   // a padded key is only visible to itself
-          x[cc * 32 + c] = ok ? v : -INFINITY;
+          if (REL) {
+            const float v = (__uint_as_float(r[c]) + my_skew[sh + c]) * sc2;
+            const bool ok = ((bits >> c) & 1u) || (jj0 + c == gi);   // a padded key is only visible to itself
+            x[cc * 32 + c] = ok ? v : -INFINITY;
+          } else {
+            x[cc * 32 + c] = ((bits >> c) & 1u) ? __uint_as_float(r[c]) * sc2 : -INFINITY;   // padded keys: masked_fill(-inf)
+          }
         }
       }
       // the scores of this tile live in registers: the tensor core may overwrite S / BD with the next tile
@@ -294,7 +309,7 @@ xl_attn_kernel(const __grid_constant__ CUtensorMap tmQw, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(REL ? 512 : 256) : "memory");
   }
 }
 
@@ -331,9 +346,41 @@ extern "C" int vilco_xl_attention(const void* qw, const void* qr, const void* k,
   p.fmt = act_fmt();
   const int smem = 8 * XL_TILE + XL_SKEW_BYTES + XL_MAX_T / 8 + 2 * 2 * 128 * 4 + 16 * 8 + 16 + 1024;
   static bool cfg = false;
-  if (!cfg) { VILCO_CUDA(cudaFuncSetAttribute(xl_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cfg = true; }
+  if (!cfg) { VILCO_CUDA(cudaFuncSetAttribute(xl_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cfg = true; }
   dim3 grid(T / XL_BQ, H, B);
-  xl_attn_kernel<<<grid, XL_THREADS, smem, st>>>(tmQw, tmQr, tmK, tmV, tmR, p);
+  xl_attn_kernel<true><<<grid, XL_THREADS, smem, st>>>(tmQw, tmQr, tmK, tmV, tmR, p);
+  VILCO_LAUNCH_CHECK();
+  return VILCO_OK;
+}
+
+// Single-pass masked self-attention for single-plane operands (see include/vilco_b200.h)
+extern "C" int vilco_self_attention(const void* q, const void* k, const void* v, const float* kmask, void* out, int B, int H, int T,
+                                    int C, float scale, void* stream) {
+  VILCO_CHECK_ARG(q && k && v && out, "vilco_self_attention: null pointer");
+  VILCO_CHECK_ARG(H > 0 && C == H * XL_D, "vilco_self_attention: head dim must be 64 (C=%d, H=%d)", C, H);
+  VILCO_CHECK_ARG(T >= XL_BQ && T % XL_BQ == 0 && T <= XL_MAX_T, "vilco_self_attention: T=%d must be a multiple of %d, <= %d", T,
+                  XL_BQ, XL_MAX_T);
+  VILCO_CHECK_ARG(reinterpret_cast<uintptr_t>(out) % 16 == 0, "vilco_self_attention: out alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tmQ, tmK, tmV;
+  int sq[3], sk[3], tmp[3];
+  int rc = encode_map(&tmQ, q, XL_D, (uint64_t)T, C, (uint64_t)H, XL_D, (uint64_t)B, (int64_t)T * C, 0, XL_D, XL_BQ, sq);
+  if (rc) return rc;
+  rc = encode_map(&tmK, k, XL_D, (uint64_t)T, C, (uint64_t)H, XL_D, (uint64_t)B, (int64_t)T * C, 0, XL_D, XL_BKV, sk);
+  if (rc) return rc;
+  rc = encode_map(&tmV, v, XL_D, (uint64_t)T, C, (uint64_t)H, XL_D, (uint64_t)B, (int64_t)T * C, 0, XL_D, XL_BKV, tmp);
+  if (rc) return rc;
+  XlDev p{};
+  p.q_slot_row = sq[0]; p.q_slot_z1 = sq[1]; p.q_slot_z2 = sq[2];
+  p.k_slot_row = sk[0]; p.k_slot_z1 = sk[1]; p.k_slot_z2 = sk[2];
+  p.T = T; p.H = H; p.scale = scale; p.kmask = kmask;
+  p.O = static_cast<uint16_t*>(out); p.o_ld = C; p.o_sh = XL_D; p.o_sb = (long long)T * C;
+  p.fmt = act_fmt();
+  const int smem = 5 * XL_TILE + XL_MAX_T / 8 + 2 * 2 * 128 * 4 + 16 * 8 + 16 + 1024;
+  static bool cfg = false;
+  if (!cfg) { VILCO_CUDA(cudaFuncSetAttribute(xl_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); cfg = true; }
+  dim3 grid(T / XL_BQ, H, B);
+  xl_attn_kernel<false><<<grid, XL_THREADS, smem, st>>>(tmQ, tmQ, tmK, tmV, tmK, p);
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }

@@ -11,6 +11,7 @@ the `*_fwd` functions are the B200 counterparts of the reference modules (file:l
 tensors here are token-major: activations (B, T, C), masks (B, T) fp32 1/0.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -115,6 +116,9 @@ def sinusoid_pe_table(max_len, C, device):
 _POS_EMB = {}
 
 
+SELF_ATTN_SP = os.environ.get("VILCO_SELF_ATTN_SP", "1") == "1"   # 0: the two-pass attn_fused kernel for every shape
+
+
 def xlnet_pos_emb(T, C, device):
     """relative_positional_encoding (bi, no clamp) — modeling_xlnet_x.py:1029-1066 -> (2T, C) operand.  Constant per
     (T, C, device, operand mode): built and uploaded once (a per-step upload from pageable memory stalls the host until the
@@ -154,6 +158,8 @@ def mhca_fwd(W, pre, xin, mask, H, stride, window=-1, tlen=None):
     # v * kv_mask (blocks.py:394) fused as the row multiplier of the value projection
     v = ops.linear(vc, W[pre + "value.weight"], bf16, bias=W[pre + "value.bias"], rowmul=omask.reshape(-1))
     if ops.FUSED_ATTN and C // H == 64 and k.shape[2] <= 2048:
+        if SELF_ATTN_SP and q.shape == k.shape and v.shape[0] == 1 and ops.xl_attention_ok(q, q.shape[2], C, H):
+            return ops.self_attention(q, k, v, omask, H, 1.0 / math.sqrt(C // H)), omask     # single-pass kernel
         return ops.attention(q, k, v, omask, H, 1.0 / math.sqrt(C // H)), omask
     S = ops.attn_scores(q, k, H, 1.0 / math.sqrt(C // H))
     P = ops.softmax_rows(S, omask, mode=0)

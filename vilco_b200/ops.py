@@ -212,6 +212,16 @@ def attention(q, k, v, kmask, H, scale):
     return out
 
 
+def self_attention(q, k, v, kmask, H, scale):
+    """Single-pass masked self-attention (csrc/xlattn.cu, REL = false): q / k / v (1,B,T,C) -> operand (1,B,T,C)."""
+    _, B, T, Cc = q.shape
+    assert q.shape[0] == 1 and k.shape == q.shape and v.shape == q.shape
+    out = empty16(B, T, Cc, device=q.device, planes=1)
+    L.check(L.lib().vilco_self_attention(_p(q), _p(k), _p(v), _p(kmask), _p(out), B, H, T, Cc, C.c_float(scale), L.stream_ptr()),
+            "vilco_self_attention")
+    return out
+
+
 def xl_attention_ok(qw, T, C, H):
     """the fused XLNet relative-attention kernel takes single-plane operands, head dim 64, T % 128 == 0"""
     return FUSED_ATTN and qw.shape[0] == 1 and C // H == 64 and T % 128 == 0 and 128 <= T <= 2048
