@@ -214,7 +214,12 @@ class Tape:
 
     def attention(self, q, k, v, kmask, H, scale):
         q16, k16, v16 = self.planes(q), self.planes(k), self.planes(v)
-        o = V(p16=ops.attention(q16, k16, v16, kmask, H, scale))
+        C = q16.shape[-1]
+        if E.SELF_ATTN_SP and q16.shape == k16.shape and q16.shape[0] == 1 and v16.shape[0] == 1 and \
+                ops.xl_attention_ok(q16, q16.shape[2], C, H):
+            o = V(p16=ops.self_attention(q16, k16, v16, kmask, H, scale))       # single-pass kernel (csrc/xlattn.cu)
+        else:
+            o = V(p16=ops.attention(q16, k16, v16, kmask, H, scale))
 
         def bwd():
             if o.g is None:
