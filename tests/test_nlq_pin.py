@@ -116,3 +116,18 @@ def test_nlq_oracle_training_losses_match_reference_golden():
     for k in ("cls_loss", "reg_loss", "final_loss"):
         ref = float(g["loss_" + k])
         assert abs(float(losses[k]) - ref) <= 2e-5 * max(1.0, abs(ref)), (k, float(losses[k]), ref)
+
+
+def test_nlq_mirror_state_dict_equals_reference_layout():
+    """vilco_b200.modeling.nlq.NlqPtTransformer registers exactly the reference NLQ model's state_dict: names, order, shapes
+    (tests/golden/nlq_state_spec.json, written from the reference's own model) — a reference checkpoint loads strictly."""
+    from vilco_b200.modeling import make_meta_arch
+    spec = json.load(open(os.path.join(GOLDEN, "nlq_state_spec.json")))
+    m = make_meta_arch("NlqLocPointTransformer", regression_range=[[0, 4], [2, 8], [4, 16], [8, 32], [16, 64], [32, 128], [64, 10000]])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(spec["state_dict"].keys())
+    assert all(list(sd[k].shape) == spec["state_dict"][k] for k in sd)
+    assert sum(p.numel() for p in m.parameters()) == spec["n_parameters"]
+    assert m.fpn_strides == [1, 2, 4, 8, 16, 32, 64] and m.mha_win_size == [9] * 7 and m.max_div_factor == 512
+    with pytest.raises(NotImplementedError):
+        m([], is_training=True)

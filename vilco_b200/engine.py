@@ -42,7 +42,8 @@ def _pack_kind(k, v):
 
 def sensitive_key(k):
     """weights of the contractions that keep split (two-plane) operands in the mixed mode"""
-    return k.startswith(("backbone.proj.", "backbone.embd.")) or k.endswith(".channel_attn.attn.qkv.weight")
+    return k.startswith(("backbone.proj.", "backbone.embd.", "backbone.vid_embd.", "backbone.txt_embd.")) or \
+        k.endswith(".channel_attn.attn.qkv.weight")
 
 
 def _planes_for(k):

@@ -57,6 +57,21 @@ def precision():
     return _mode
 
 
+class use_precision:
+    """context manager: run a block in another operand-format policy (weights are re-packed by the models: their packed-weight
+    caches are keyed on `precision()`)"""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.prev = _mode
+        set_precision(self.name)
+
+    def __exit__(self, *a):
+        set_precision(self.prev)
+
+
 set_precision(os.environ.get("VILCO_PRECISION", "mixed"))
 
 
@@ -191,7 +206,7 @@ def attn_pv(P, v, H, Tk, out32=False, a_trans=False, M=None, alpha=1.0):
     _, B, _, R, ldp = P.shape
     Cc = v.shape[3]
     d = Cc // H
-    assert d == 64, "attn_pv: head dim must be 64"
+    assert d % 8 == 0 and d <= 128, "attn_pv: head dim must be a multiple of 8, <= 128"
     Tq = (M if M is not None else ldp) if a_trans else R
     out = torch.empty(B, Tq, Cc, device=v.device, dtype=f32) if out32 else empty16(B, Tq, Cc, device=v.device)
     L.gemm(P, v, out, M=Tq, N=d, K=Tk, a_rows=Tq, a_ld=ldp, a_s=(R * ldp, H * R * ldp), Z=(H, B), b_ld=Cc,
