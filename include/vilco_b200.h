@@ -248,6 +248,16 @@ int vilco_attention(const void* q, int64_t q_lo, const void* k, const void* v, i
 int vilco_xl_attention(const void* qw, const void* qr, const void* k, const void* v, const void* kr, const float* kmask,
                        void* out, int B, int H, int T, int C, float scale, void* stream);
 
+/* FPN1D building blocks (MQ/libs/modeling/necks.py:13-106; ACConv / DenseAPP, MQ/libs/modeling/utils.py:671-751).
+ * vilco_groupnorm: nn.GroupNorm(G, C) of a token-major fp32 (B, T, C) tensor — statistics per (clip, group) over all T rows and
+ * the C / G channels of the group, eps inside the square root, affine w / b (C,), optional ReLU; writes fp32 y32 and / or the
+ * 16-bit operand planes y16 (either may be NULL).
+ * vilco_upsample2_add: the top-down path, y (B, T2, C) += x (B, T2 / 2, C) repeated twice along time
+ * (F.interpolate(scale_factor=2, mode="nearest") + add, necks.py:88-93). */
+int vilco_groupnorm(const float* x, const float* w, const float* b, float* y32, void* y16, int64_t y16_lo, int B, int T, int C,
+                    int G, float eps, int relu, void* stream);
+int vilco_upsample2_add(const float* x, float* y, int B, int T2, int C, void* stream);
+
 /* Single-pass masked self-attention (MaskedMHCA core, MQ/libs/modeling/blocks.py:351-410: att = softmax(q k^T * scale with
  * masked_fill(~kv_mask, -inf)); out = att @ v) for single-plane operands, head dim 64, T a multiple of 128 (<= 2048) — the
  * kernel of vilco_xl_attention without the position branch (online softmax with lazy rescale, one pass over the keys).

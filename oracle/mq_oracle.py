@@ -256,6 +256,7 @@ class ModelCfg:
         self.use_cross_modal = True
         self.use_xl = True
         self.t_c_alpha = 0.8
+        self.fpn_type = "identity"      # "fpn": FPN1D + ACConv / DenseAPP (necks.py:13-106; no config selects it)
         self.regression_range = [[0, 4], [2, 8], [4, 16], [8, 32], [16, 64], [32, 128], [64, 256], [128, 512],
                                  [256, 1024], [512, 10000]]
         self.center_sample_radius = 1.5
@@ -329,6 +330,46 @@ def fpn_identity(P, feats, masks):
             for i, f in enumerate(feats)], masks
 
 
+DENSE_RATES = (3, 6, 12, 18, 24)
+
+
+def dense_app(P, pre, x):
+    """DenseAPP.forward — MQ/libs/modeling/utils.py:692-729 (evaluation: dropout off).  Five DenseBlocks (:671-689: 1x1 conv ->
+    GroupNorm(32) -> ReLU -> dilated k=3 conv, rate r -> ReLU), each fed the concatenation [newest, ..., oldest, input]; the five
+    outputs are concatenated, 1x1 conv, GroupNorm(32).  Plain (unmasked) convolutions, as in the reference."""
+    feature, outs = x, []
+    for r in DENSE_RATES:
+        b = f"{pre}aspp{r}."
+        h = F.conv1d(feature, P[b + "conv1x1.weight"], P[b + "conv1x1.bias"])
+        h = F.relu(F.group_norm(h, 32, P[b + "ConvGN.weight"], P[b + "ConvGN.bias"]))
+        h = F.relu(F.conv1d(h, P[b + "dilaconv.weight"], P[b + "dilaconv.bias"], padding=r, dilation=r))
+        outs.append(h)
+        feature = torch.cat([h, feature], dim=1)
+    y = F.conv1d(torch.cat(outs, dim=1), P[pre + "conv1x1.weight"], P[pre + "conv1x1.bias"])
+    return F.group_norm(y, 32, P[pre + "ConvGN.weight"], P[pre + "ConvGN.bias"])
+
+
+def fpn1d(P, feats, masks, pre="neck."):
+    """FPN1D.forward — MQ/libs/modeling/necks.py:64-106: 1x1 lateral convs (the LAST level goes through ACConv = DenseAPP x mask
+    instead, utils.py:732-751; its CxAM / CnAM branches are commented out in the reference), top-down nearest x2 upsample-add,
+    depthwise k=3 conv + channel LayerNorm per level.  feats [(B, C, T_l)], masks [(B, 1, T_l) bool]."""
+    n = len(feats)
+    lat = []
+    for i in range(n):
+        if i == n - 1:
+            lat.append(dense_app(P, pre + "ac_conv.denseapp.", feats[-1]) * masks[i].to(feats[-1].dtype))
+        else:
+            lat.append(masked_conv1d(feats[i], masks[i], P[pre + f"lateral_convs.{i}.conv.weight"], None)[0])
+    for i in range(n - 1, 0, -1):
+        lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], scale_factor=2.0, mode="nearest")
+    out = []
+    for i in range(n):
+        C = lat[i].shape[1]
+        x, _ = masked_conv1d(lat[i], masks[i], P[pre + f"fpn_convs.{i}.conv.weight"], None, groups=C)
+        out.append(channel_layernorm(x, P[pre + f"fpn_norms.{i}.weight"], P[pre + f"fpn_norms.{i}.bias"]))
+    return out, masks
+
+
 def _head_tower(P, pre, x, mask):
     for i in range(2):
         x, _ = masked_conv1d(x, mask, P[pre + f"head.{i}.conv.weight"], None)
@@ -396,7 +437,7 @@ def _forward_heads_once(P, cfg, feats_bct, mask_b1t, text=None, text_mask=None, 
     """backbone -> neck -> heads; returns lists permuted like meta_archs.py:848-852:
     logits (B,T_l,K), offsets (B,T_l,2), masks (B,T_l)."""
     feats, masks = backbone(P, cfg, feats_bct, mask_b1t, text, text_mask, training, pets_prefix)
-    fpn, masks = fpn_identity(P, feats, masks)
+    fpn, masks = fpn1d(P, feats, masks) if getattr(cfg, "fpn_type", "identity") == "fpn" else fpn_identity(P, feats, masks)
     offs = reg_head(P, fpn, masks)
     logits = cls_head(P, fpn, masks)
     return ([x.permute(0, 2, 1) for x in logits], [x.permute(0, 2, 1) for x in offs], [m.squeeze(1) for m in masks],

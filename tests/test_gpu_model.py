@@ -280,3 +280,66 @@ def test_torch_custom_ops_call_the_kernels():
     sc, lb_ = torch.rand(300, device="cuda"), torch.randint(0, 5, (300,), device="cuda")
     s1 = torch.ops.vilco.batched_nms(segs, sc, lb_, 0.1, 1e-4, 50, True, True, 0.99, 0.75)
     assert s1[0].shape == (50, 2) and bool((s1[1][:-1] >= s1[1][1:]).all())
+
+
+@pytest.mark.parametrize("mode,tol", [("fp16x3", 1e-4), ("mixed", 1e-3)])
+def test_fpn1d_vs_reference_golden(mode, tol):
+    """FPN1D (`fpn_type: fpn`: lateral 1x1 convs, ACConv / DenseAPP with GroupNorm and dilated convs on the last level, top-down
+    nearest upsample-add, depthwise conv + LN) through engine.fpn1d_fwd against the golden produced by the reference's own
+    module (tests/golden/fpn1d.npz, oracle/gen_golden_fpn.py)"""
+    from oracle.gen_golden_fpn import LEVELS, fpn_inputs, fpn_state
+    from vilco_b200 import engine as E
+    g = np.load(os.path.join(GOLDEN, "fpn1d.npz"))
+    feats, masks = fpn_inputs()
+    with precision(mode):
+        W = E.pack_weights(fpn_state(pre="neck."), "cuda")
+        out = E.fpn1d_fwd(W, [f.permute(0, 2, 1).contiguous().cuda() for f in feats], [m[:, 0].float().cuda() for m in masks])
+        torch.cuda.synchronize()
+        for l in range(LEVELS):
+            got = out[l].float().sum(0).permute(0, 2, 1).cpu().numpy()
+            e = rel_max(got, g[f"out_{l}"])
+            print(f"FPN1D {mode} level {l}: {e:.2e}")
+            assert e < tol
+
+
+def test_model_with_fpn1d_neck_vs_oracle():
+    """whole model with `fpn_type: fpn` (inference): logits / offsets / detections against the oracle, whose FPN1D restatement
+    is pinned to the reference's module by tests/test_fpn_cpu.py and whose other parts are pinned by the model goldens"""
+    from oracle import mq_oracle as O
+    from oracle import nms_c
+    from oracle import params as PR
+    from oracle.gen_golden import small_cfg
+    from oracle.gen_golden_fpn import fpn_spec
+    from vilco_b200.config import mq_model_kwargs
+    from vilco_b200.modeling import make_meta_arch
+    cfg = small_cfg()
+    cfg.fpn_type = "fpn"
+    n_levels = len(cfg.regression_range)
+    spec = {k: v for k, v in PR.param_spec(cfg).items() if not k.startswith("neck.")}
+    spec.update(fpn_spec(cfg.embd_dim, n_levels, pre="neck."))
+    P = PR.random_state(spec, 4)
+    for k in P:
+        if ".ConvGN." in k:
+            P[k] = (1.0 + 0.1 * P[k]) if k.endswith("weight") else 0.1 * P[k]
+    kw = mq_model_kwargs(cfg.input_dim, cfg.embd_dim, cfg.n_head, cfg.max_seq_len, cfg.arch, cfg.num_classes, cfg.n_txt_in,
+                         cfg.regression_range)
+    kw["fpn_type"] = "fpn"
+    model = make_meta_arch("LocPointTransformer", **kw)
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected and not [k for k in missing if k.startswith("neck.")]
+    model = model.cuda().eval()
+    videos = PR.synth_video_list(cfg, 2, seed=5, lens=[128, 77], text_lens=[20, 33], n_gt=[2, 1])
+    with precision("fp16x3"), torch.no_grad():
+        for v in videos:
+            cls_l, off_l, _ = model([v], is_training=False, get_emb=True)
+            res = model([v], is_training=False)[0]
+            ref, raw = O.model_infer(P, cfg, [v], softnms_fn=nms_c.softnms_1d, return_raw=True)
+            e1 = rel_max(torch.cat(cls_l, 1)[0], torch.cat(raw[0][0], 1)[0])
+            e2 = rel_max(torch.cat(off_l, 1)[0], torch.cat(raw[0][1], 1)[0])
+            print(f"model with FPN1D: logits {e1:.2e} offsets {e2:.2e}, {res['segments'].shape[0]} segments")
+            assert e1 < 1e-4 and e2 < 1e-4
+            assert res["segments"].shape == ref[0]["segments"].shape
+            assert float((res["scores"] - ref[0]["scores"]).abs().max()) < 1e-4
+    with pytest.raises(NotImplementedError):
+        model.train()
+        model(videos, is_training=True)

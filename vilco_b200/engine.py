@@ -29,8 +29,8 @@ def _pack_kind(k, v):
         return "xl_t"
     if ".rel_attn." in k and last == "o":
         return "gemm"
-    if k.endswith("_conv.conv.weight"):
-        return "dw"
+    if k.endswith("_conv.conv.weight") or (last == "weight" and v.dim() == 3 and v.shape[1] == 1 and v.shape[2] == 3 and v.shape[0] > 1):
+        return "dw"        # depthwise k=3 (attention q/k/v convs, FPN1D fpn_convs)
     if last == "weight" and v.dim() == 3 and v.shape[0] == 1 and v.shape[2] == 1:
         return "vec"
     if last == "weight" and v.dim() == 3 and v.shape[2] == 3:
@@ -43,7 +43,7 @@ def _pack_kind(k, v):
 def sensitive_key(k):
     """weights of the contractions that keep split (two-plane) operands in the mixed mode"""
     return k.startswith(("backbone.proj.", "backbone.embd.", "backbone.vid_embd.", "backbone.txt_embd.")) or \
-        k.endswith(".channel_attn.attn.qkv.weight")
+        k.endswith(".channel_attn.attn.qkv.weight") or ".ac_conv." in k      # FPN1D's DenseAPP stack: five GroupNorm blocks deep
 
 
 def _planes_for(k):
@@ -383,6 +383,59 @@ class Pyramid:
         return cls._cache[key]
 
 
+DENSE_RATES = (3, 6, 12, 18, 24)
+
+
+def _dilated_conv_relu(W, key, x16, rate):
+    """relu(dilated k=3 conv + bias) of the DenseAPP blocks on a token-major operand (NP, B, T, Cin): ONE GEMM over the three
+    row-shifted copies concatenated along channels (K = 3 Cin) against the taps concatenated the same way; taps that fall
+    entirely outside the sequence (rate >= T — every side tap at the MQ configuration, where the last level has T = 2)
+    are dropped."""
+    from . import backward as BW
+    T = x16.shape[2]
+    w3 = W[key + ".weight"]                                   # (NP, 3, Cout, Cin) tap-major
+    cache = W.setdefault("_cache", {})
+    if rate >= T:
+        return ops.linear(x16, w3[:, 1], bf16, bias=W[key + ".bias"], act=ACT_RELU, planes=ops.PLANES_HI)
+    ck = ("dil_cat", key)
+    if ck not in cache:
+        cache[ck] = w3.permute(0, 2, 1, 3).reshape(w3.shape[0], w3.shape[2], -1).contiguous()   # (NP, Cout, 3 Cin)
+    xcat = torch.cat([BW.shift_planes(x16, -rate), x16, BW.shift_planes(x16, rate)], dim=-1)
+    return ops.linear(xcat, cache[ck], bf16, bias=W[key + ".bias"], act=ACT_RELU, planes=ops.PLANES_HI)
+
+
+def fpn1d_fwd(W, feats, masks, pre="neck."):
+    """FPN1D.forward — MQ/libs/modeling/necks.py:64-106 (evaluation).  feats [(B, T_l, C) fp32], masks [(B, T_l) fp32]
+    -> per-level operand tensors (NP, B, T_l, C) = LN(depthwise conv(top-down sum)).  The last level's lateral is ACConv =
+    DenseAPP x mask (modeling/utils.py:692-751): 1x1 conv -> GroupNorm(32) -> ReLU -> dilated conv -> ReLU, five times over a
+    growing concatenation, then 1x1 conv -> GroupNorm(32)."""
+    n = len(feats)
+    lat = []
+    for i in range(n - 1):
+        _, f16 = ops.axpby(feats[i], None, 1.0, 0.0, out32=False, out16=True)
+        lat.append(ops.linear(f16, W[pre + f"lateral_convs.{i}.conv.weight"], f32, rowmul=masks[i].reshape(-1)))
+    d = pre + "ac_conv.denseapp."
+    # the DenseAPP stack keeps split operands in the mixed mode (sensitive_key: ".ac_conv."): it is five GroupNorm blocks deep
+    # and runs on the shortest level only (T = 2 at the MQ configuration), so this costs nothing
+    _, feature = ops.axpby(feats[-1], None, 1.0, 0.0, out32=False, out16=True, planes=ops.PLANES_HI)
+    outs = []
+    for r in DENSE_RATES:
+        b = f"{d}aspp{r}."
+        h32 = ops.linear(feature, W[b + "conv1x1.weight"], f32, bias=W[b + "conv1x1.bias"])
+        _, h16 = ops.groupnorm(h32, W[b + "ConvGN.weight"], W[b + "ConvGN.bias"], 32, relu=True, out32=False, out16=True,
+                               planes=ops.PLANES_HI)
+        o16 = _dilated_conv_relu(W, b + "dilaconv", h16, r)
+        outs.append(o16)
+        feature = torch.cat([o16, feature], dim=-1)
+    y32 = ops.linear(torch.cat(outs, dim=-1), W[d + "conv1x1.weight"], f32, bias=W[d + "conv1x1.bias"])
+    y32, _ = ops.groupnorm(y32, W[d + "ConvGN.weight"], W[d + "ConvGN.bias"], 32, out32=True, out16=False)
+    lat.append(y32 * masks[-1].unsqueeze(-1))
+    for i in range(n - 1, 0, -1):
+        ops.upsample2_add(lat[i], lat[i - 1])
+    return [ops.dwconv_ln(lat[i].contiguous(), masks[i], [W[pre + f"fpn_convs.{i}.conv.weight"]], [W[pre + f"fpn_norms.{i}.weight"]],
+                          [W[pre + f"fpn_norms.{i}.bias"]], 1)[0] for i in range(n)]
+
+
 def neck_heads_fwd(W, cfg, feats, masks, pyr=None):
     """FPNIdentity.forward (necks.py:173-198) + PtTransformerClsHead / RegHead (meta_archs.py:259-275, 334-349) over
     all levels at once.  Returns (logits (B,P,K) fp32, offsets (B,P,2) fp32, pmask (B,P) fp32, pyr)."""
@@ -399,10 +452,14 @@ def neck_heads_fwd(W, cfg, feats, masks, pyr=None):
     fpn = ops.zeros16(B, P, C, device=dev)
     pmask = torch.zeros(B, P, device=dev, dtype=f32)
     rowscale = torch.zeros(B, P, device=dev, dtype=f32)
+    lv = fpn1d_fwd(W, feats, masks) if getattr(cfg, "fpn_type", "identity") == "fpn" else None
     for l, (f, mk) in enumerate(zip(feats, masks)):
         o, n = pyr.off[l], pyr.lens[l]
-        ops.layernorm(f, W[f"neck.fpn_norms.{l}.weight"], W[f"neck.fpn_norms.{l}.bias"], out32=False,
-                      y16=fpn[:, :, o:o + n], y16_lo=ops.lo(fpn), rows_per_batch=n, y_ld=C, y_bs=P * C)
+        if lv is not None:
+            fpn[:, :, o:o + n] = lv[l]
+        else:
+            ops.layernorm(f, W[f"neck.fpn_norms.{l}.weight"], W[f"neck.fpn_norms.{l}.bias"], out32=False,
+                          y16=fpn[:, :, o:o + n], y16_lo=ops.lo(fpn), rows_per_batch=n, y_ld=C, y_bs=P * C)
         pmask[:, o:o + n] = mk
         rowscale[:, o:o + n] = mk * W[f"reg_head.scale.{l}.scale"]
     zero_rows = pyr.gap_rows.repeat(B)

@@ -270,9 +270,10 @@ class PtTransformer(nn.Module):
             embd_dim = sum(embd_dim)
         self.embd_dim, self.n_head, self.backbone_arch = embd_dim, n_head, tuple(backbone_arch)
         self.input_dim = input_dim[0] if isinstance(input_dim, (list, tuple)) else input_dim
-        assert fpn_type == "identity", "fpn_type 'fpn' (FPN1D + DenseAPP) is not selected by any MQ config"
+        assert fpn_type in ("identity", "fpn")       # 'fpn' = FPN1D + ACConv / DenseAPP (necks.py:13-106): evaluation path only
         assert embd_dim == fpn_dim == head_dim
-        self.neck = make_neck("identity", in_channels=[embd_dim] * n_levels, out_channel=fpn_dim,
+        self.fpn_type = fpn_type
+        self.neck = make_neck(fpn_type, in_channels=[embd_dim] * n_levels, out_channel=fpn_dim,
                               scale_factor=scale_factor, start_level=fpn_start_level, with_ln=fpn_with_ln)
         self.point_generator = make_generator("point", max_seq_len=max_seq_len * max_buffer_len_factor,
                                               fpn_strides=self.fpn_strides, regression_range=self.reg_range)
@@ -408,6 +409,7 @@ class PtTransformer(nn.Module):
         c.embd_dim, c.n_head, c.arch, c.scale_factor = self.embd_dim, self.n_head, self.backbone_arch, self.scale_factor
         c.use_cross_modal, c.use_xl, c.t_c_alpha, c.max_seq_len = self.use_cross_modal, self.use_xl, self.t_c_alpha, self.max_seq_len
         c.adapt_blocks = tuple(self.adapt_blocks)
+        c.fpn_type = self.fpn_type
         return c
 
     def use_flat_optimizer(self, opt):
@@ -637,6 +639,8 @@ class PtTransformer(nn.Module):
         CUDA backward pass (vilco_b200/train_engine.py) and accumulates into every parameter's .grad.  mu / sigma (and
         the L2P prompt pool) receive their gradients through torch autograd of the small target-assignment glue."""
         from .. import train_engine as TE
+        if self.fpn_type != "identity":
+            raise NotImplementedError("fpn_type 'fpn' (FPN1D) is built for evaluation only; no MQ config trains with it")
         dev = self.device
         vl, batched, mask = self.preprocessing(video_list, True)
         text = tmask = None

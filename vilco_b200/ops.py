@@ -322,6 +322,26 @@ def pack_feats(x, T_out=None, planes=None):
     return y
 
 
+def groupnorm(x, w, b, groups, eps=1e-5, relu=False, out32=True, out16=False, planes=None):
+    """nn.GroupNorm(groups, C) on token-major fp32 x (B, T, C) -> (y32 or None, y16 operand or None)"""
+    assert x.dtype == f32 and x.is_contiguous() and x.dim() == 3
+    B, T, Cc = x.shape
+    y32 = torch.empty_like(x) if out32 else None
+    y16 = empty16(B, T, Cc, device=x.device, planes=planes) if out16 else None
+    L.check(L.lib().vilco_groupnorm(_p(x), _p(w), _p(b), _p(y32), _p(y16), _i64(lo(y16) if out16 else 0), B, T, Cc, groups,
+                                    C.c_float(eps), int(relu), L.stream_ptr()), "vilco_groupnorm")
+    return y32, y16
+
+
+def upsample2_add(x, y):
+    """y (B, 2T, C) += nearest-upsampled x (B, T, C), in place"""
+    assert x.dtype == f32 and y.dtype == f32 and x.is_contiguous() and y.is_contiguous()
+    B, T2, Cc = y.shape
+    assert x.shape == (B, T2 // 2, Cc)
+    L.check(L.lib().vilco_upsample2_add(_p(x), _p(y), B, T2, Cc, L.stream_ptr()), "vilco_upsample2_add")
+    return y
+
+
 def unpack(x, out=None):
     """(B, T, C) fp32 -> (B, C, T) fp32 (into `out` when given)."""
     B, T, Cc = x.shape
