@@ -1,3 +1,5 @@
+"""Why a GEMM micro-benchmark depends on what ran before it: the same launch timed fresh, right after 4 s of dense tensor load
+(sw_power_cap engages near 880 W and the launch takes ~25 % longer), after a pause, with new allocations.  python tools/power_state_probe.py"""
 import os, sys, time, subprocess
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
