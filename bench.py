@@ -254,7 +254,7 @@ def next_rows():
             F.interpolate(xc.permute(1, 0).unsqueeze(0), size=T, mode="linear", align_corners=False)
         cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
         hbm = peaks()[0]
-        out["data_path"] = {"kernel": "vilco::resize_feats_kernel", "workload": "32 stored clips 512x4096 fp32 -> 1024 rows, bf16 hi/lo planes",
+        out["data_path"] = {"kernel": "vilco::resize_feats_kernel", "workload": "32 stored clips 512x4096 fp32 -> 1024 rows as the operand planes of the shipped mode (%d x 16 bit)" % o16.shape[0],
                             "us_per_launch": sec * 1e6, "bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": nbytes / sec / 1e9 / hbm, "clips_per_s": Bc / sec, "cpu_interpolate_ms_per_clip": cpu_ms}
         del x, o16
@@ -289,6 +289,35 @@ def next_rows():
                                   "reference": "the reference's evaluator on a table of this size: ~55 s in one process (tools/metrics_bench.py --reference)"}
     except Exception as e:
         out["evaluation_tail"] = {"unavailable": repr(e)[:200]}
+    try:      # §8f-1: the NLQ model (evaluation) on the same kernels, full size (T = 2560, C = 384, 4 heads of 96, window 9, 7 levels)
+        from vilco_b200 import lib as L
+        from vilco_b200.modeling import make_meta_arch
+        nlq = make_meta_arch("NlqLocPointTransformer", regression_range=[[0, 4], [2, 8], [4, 16], [8, 32], [16, 64], [32, 128], [64, 10000]],
+                             test_cfg=dict(voting_thresh=0.9, pre_nms_topk=2000, max_seg_num=5, min_score=0.001, nms_sigma=0.75,
+                                           duration_thresh=0.001)).cuda().eval()
+        g = torch.Generator().manual_seed(1)
+        Bq = 16
+        clips = [{"video_id": f"v{i}", "query_id": f"q{i}", "feats": torch.randn(256, 2560 - 17 * i, generator=g),
+                  "query_feats": torch.randn(512, 12, generator=g), "fps": 30.0, "duration": 1400.0, "feat_stride": 16.043,
+                  "feat_num_frames": 16.043} for i in range(Bq)]
+        for _ in range(3):
+            nlq(clips, is_training=False)
+        torch.cuda.synchronize()
+        n0 = L.launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(5):
+            res = nlq(clips, is_training=False)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 5
+        out["nlq_model"] = {"workload": "ego4d_nlq_v2_egovlp_1e-4.yaml evaluation, 16 queries per step, T = 2560, eager (host batching, upload, "
+                                        "decode + soft-NMS, result download inside the timed region)",
+                            "ms_per_step": ms, "queries_per_s": Bq / ms * 1e3, "gpu_launches_per_step": (L.launch_count() - n0) // 5,
+                            "operand_mode": nlq.operand_mode, "segments_per_query": int(res[0]["segments"].shape[0])}
+        del nlq
+    except Exception as e:
+        out["nlq_model"] = {"unavailable": repr(e)[:200]}
     return out
 
 
