@@ -31,6 +31,7 @@ extern "C" {
 #define VILCO_ACT_NONE 0
 #define VILCO_ACT_RELU 1
 #define VILCO_ACT_GELU 2   /* exact erf GELU (torch.nn.GELU default) */
+#define VILCO_ACT_EXP2 3   /* 2^x (softmax recompute in the attention gradients, see VilcoGemm.rowsub) */
 
 /* dtype codes */
 #define VILCO_F32 0
@@ -97,7 +98,17 @@ typedef struct VilcoGemm {
   int32_t band_lo, band_hi;   /* band_hi > band_lo: only outputs with band_lo <= m + n < band_hi are computed (others untouched) */
   int32_t a_major;            /* 0: A is (a_rows, K) K-major (row stride a_ld).  1: A is stored (K, M) MN-major — element (m, k) at
                                  A[k * a_ld + m] — the natural layout of a gradient matrix used as dZ^T in dW = dZ^T X; taps must be 1 */
-  int32_t a_fmt, b_fmt;       /* element format of A / B: VILCO_BF16 or VILCO_F16 (0 = VILCO_BF16); may differ (gradient x activation) */
+  int32_t a_fmt, b_fmt;       /* element format of A / B: VILCO_BF16 or VILCO_F16 (0 = VILCO_BF16); must be equal on the tensor core */
+  /* Fused softmax-recompute epilogues of the attention gradients (16-bit output, whole 32 x 32 chunks only; ABI version 3):
+   *   out = act((acc * alpha + bias[n] - rowsub[z, m]) * rowmul[m]) * colscale[z2, n] * emul[z, m, n]
+   * rowsub: fp32, element (z1, z2, m) at rowsub[z1 * rowsub_s1 + z2 * rowsub_s2 + m]; colscale gets the batch offset
+   * z2 * colscale_zs; emul: ONE 16-bit plane laid out like D (d_ld / d_s1 / d_s2).  With act = VILCO_ACT_EXP2 and rowsub = the
+   * row log-sum-exp (base 2) saved by vilco_self_attention, the QK^T GEMM writes the probabilities P directly; with emul = P and
+   * rowsub = delta = rowsum(dO * O), the dO V^T GEMM writes dS = P (dP - delta) directly — no (T x T) fp32 tensor and no softmax
+   * kernel in the backward pass. */
+  const float* rowsub; int64_t rowsub_s1, rowsub_s2;
+  int64_t colscale_zs;
+  const void* emul;
 } VilcoGemm;
 
 int vilco_gemm(const VilcoGemm* g, void* stream);
@@ -265,6 +276,10 @@ int vilco_upsample2_add(const float* x, float* y, int B, int T2, int C, void* st
  * entry (Tq != Tk, tails, two planes). */
 int vilco_self_attention(const void* q, const void* k, const void* v, const float* kmask, void* out, int B, int H, int T, int C,
                          float scale, void* stream);
+/* same, and lse2 (B, H, T) fp32 (may be NULL) receives log2(sum_j exp(score_ij)) = the row log-sum-exp in base 2 of the scaled,
+ * masked scores — what the fused gradient epilogues of vilco_gemm (rowsub) need to recompute P without a softmax pass */
+int vilco_self_attention_lse(const void* q, const void* k, const void* v, const float* kmask, void* out, float* lse2, int B, int H,
+                             int T, int C, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Backward-pass building blocks (training; token-major fp32 gradients).  The GEMM-shaped gradients reuse vilco_gemm:

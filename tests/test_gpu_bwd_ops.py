@@ -25,3 +25,4 @@ def test_backward_primitives_match_torch_autograd():
     bad = [l for l in out.splitlines() if l.startswith("BAD")]
     assert "bad 0" in out and not bad, "\n".join(bad[:10])
     assert out.count("OK ") >= 40
+

@@ -697,3 +697,37 @@ def test_class_incremental_flow():
         logits, _, _ = model(videos[:1], is_training=False, get_emb=True)
         r1 = model(videos[:1], is_training=False)
     assert logits[0].shape[-1] == 6 and len(r1[0]["scores"]) > 0
+
+
+@pytest.mark.parametrize("B,T,H,valid", [(2, 256, 2, [256, 100]), (1, 1024, 4, [777])])
+def test_attention_backward_with_fused_epilogues(B, T, H, valid):
+    """backward.attention_bwd_lse — probabilities recomputed in the QK^T GEMM epilogue from the forward kernel's row
+    log-sum-exp, softmax backward fused into the dO V^T GEMM epilogue — against torch autograd of the same attention on the same
+    fp16 operands (float64), and against the materialised chain it replaces"""
+    from util import precision
+    from vilco_b200 import backward as BW
+    from vilco_b200 import ops
+    with precision("mixed"):
+        gen = torch.Generator(device="cuda").manual_seed(B * T + H)
+        C = H * 64
+        q16, k16, v16 = (ops.split16(torch.randn(B, T, C, device="cuda", generator=gen) * s, planes=1) for s in (1.2, 1.2, 1.0))
+        vl = torch.tensor(valid, device="cuda")
+        kmask = (torch.arange(T, device="cuda")[None, :] < vl[:, None]).float()
+        v16 = v16 * kmask[None, :, :, None].to(v16.dtype)                 # the forward multiplies v by the key mask (blocks.py:394)
+        dO = torch.randn(B, T, C, device="cuda", generator=gen) * 1e-2
+        O16, lse = ops.self_attention(q16, k16, v16, kmask, H, 0.125, want_lse=True)
+        dq, dk, dv = BW.attention_bwd_lse(dO, O16, lse, q16, k16, v16, kmask, H, 0.125)
+        dq0, dk0, dv0 = BW.attention_bwd(dO, q16, k16, v16, kmask, H, 0.125)
+        q, k, v = (t[0].double().requires_grad_(True) for t in (q16, k16, v16))
+        hd = lambda t: t.view(B, T, H, 64).transpose(1, 2)     # noqa: E731
+        att = (hd(q) @ hd(k).transpose(-2, -1)) * 0.125
+        att = att.masked_fill(~(kmask > 0)[:, None, None, :], float("-inf"))
+        o = (torch.softmax(att, -1) @ hd(v)).transpose(1, 2).reshape(B, T, C)
+        lse_ref = torch.logsumexp(att, -1) * 1.4426950408889634
+        assert float((lse.double() - lse_ref).abs().max()) < 2e-3
+        gq, gk, gv = torch.autograd.grad(o, (q, k, v), dO.double())
+        for name, got, old, ref in (("dq", dq, dq0, gq), ("dk", dk, dk0, gk), ("dv", dv, dv0, gv)):
+            e_new = float((got.double() - ref).norm() / ref.norm())
+            e_old = float((old.double() - ref).norm() / ref.norm())
+            print(f"attention bwd T{T} {name}: fused epilogues {e_new:.2e}, materialised chain {e_old:.2e}")
+            assert e_new < 2e-3

@@ -231,6 +231,28 @@ def attention_bwd(dO, q16, k16, v16, kmask, H, scale):
     return dq, dk, dv
 
 
+def attention_bwd_lse(dO, O16, lse2, q16, k16, v16, kmask, H, scale):
+    """attention_bwd for the single-pass forward kernel, which saved the row log-sum-exp: no (T x T) tensor is ever written in
+    fp32 and no softmax kernel runs —
+        P  = exp2(scale log2e q k^T - lse) * kmask          in the epilogue of the QK^T GEMM      (one fp16 plane)
+        dS = P * (dO v^T - delta) * scale,  delta = rowsum(dO * O) per head   in the epilogue of the dO V^T GEMM
+    then dQ = dS K, dK = dS^T Q, dV = P^T dO as before.  dO (B,T,C) fp32, O16 / q16 / k16 / v16 single-plane operands."""
+    _, B, T, Cc = q16.shape
+    d = Cc // H
+    P16 = ops.attn_probs_from_lse(q16, k16, H, scale, lse2, kmask)
+    dO16, _ = to_planes(dO.reshape(-1, Cc), planes=1)
+    dO16 = dO16.reshape(1, B, T, Cc)
+    # delta[b,h,i] = sum_c dO[b,i,h,c] O[b,i,h,c]   (tiny glue reduction over the head dim)
+    delta = (dO.reshape(B, T, H, d) * O16[0].reshape(B, T, H, d).float()).sum(-1).permute(0, 2, 1).contiguous()
+    # dO16 carries GRAD_SCALE: (acc * scale - delta * scale * GS) = GS * scale * (dP - delta) -> dS as a gradient plane
+    dS16 = ops.attn_dscores_fused(dO16, v16, H, P16, delta * (scale * ops.GRAD_SCALE), scale)
+    gi = ops.ginv()
+    dq = ops.attn_pv(dS16, k16, H, T, out32=True, alpha=gi)
+    dk = ops.attn_pv(dS16, q16, H, T, out32=True, a_trans=True, M=T, alpha=gi)
+    dv = ops.attn_pv(P16, dO16, H, T, out32=True, a_trans=True, M=T, alpha=gi)
+    return dq, dk, dv
+
+
 def local_attention_bwd(dO, q16, k16, v16, mask, H, W, rel_pe=None):
     """forward: ops.local_attention (LocalMaskedMHCA core).  dO (B,T,C) fp32, q16 / k16 / v16 (NP,B,T,C) -> (dq, dk, dv) fp32."""
     _, B, T, Cc = q16.shape

@@ -21,7 +21,7 @@ void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::m
 }  // namespace vilco
 
 extern "C" const char* vilco_last_error(void) { return vilco::g_err; }
-extern "C" int vilco_version(void) { return 2; }
+extern "C" int vilco_version(void) { return 3; }
 extern "C" uint64_t vilco_launch_count(void) { return vilco::g_launches.load(std::memory_order_relaxed); }
 extern "C" int vilco_set_plane_format(int fmt) {
   if (fmt != VILCO_BF16 && fmt != VILCO_F16) {

@@ -88,6 +88,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == VILCO_ACT_RELU) return fmaxf(v, 0.0f);
   if (act == VILCO_ACT_GELU) return gelu_fast(v);
+  if (act == VILCO_ACT_EXP2) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v)); return e; }
   return v;
 }
 

@@ -40,6 +40,9 @@ struct GemmDev {
   const float* colscale;
   const float* resid; int resid_masked;
   int vec_ok;  // 16-byte aligned vector stores allowed
+  const float* rowsub; long long rowsub_s1, rowsub_s2;   // fused softmax-recompute epilogues (see VilcoGemm)
+  long long colscale_zs;
+  const uint16_t* emul;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -64,7 +67,9 @@ __device__ __forceinline__ float epi_value(const GemmDev& p, float acc, int n, f
 //                 epilogue of tile i overlaps the main loop of tile i+1 (tmem_full / tmem_empty mbarriers; tmem_empty lives in
 //                 the leader and counts the epilogue warps of both CTAs)
 //   warps 2..9  : epilogue of this CTA's 128 rows
-template <int BN, int CG>
+// GX = true: the instantiation that carries the fused attention-gradient epilogue terms (rowsub / emul / batched colscale);
+// they are compiled out of the common kernels, whose epilogue sits at the register cap
+template <int BN, int CG, bool GX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmDev p) {
@@ -278,7 +283,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* sbuf = stage_buf + (warp - 2) * (32 * 32);
     const float alpha = p.alpha;
     const float* __restrict__ bias = p.bias;
-    const float* __restrict__ colscale = p.colscale;
     const float* __restrict__ resid = p.resid;
     const int act = p.act;
     const bool resid_masked = p.resid_masked != 0;
@@ -288,7 +292,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_rm = p.rowmul != nullptr;
     // 16-byte vector loads of the per-column terms need aligned pointers; a 16-bit output with a residual takes the general path
     const bool fast_ok = p.vec_ok && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
-                         (!colscale || (reinterpret_cast<uintptr_t>(colscale) & 15) == 0) && (is_f32 || resid == nullptr);
+                         (!p.colscale || ((reinterpret_cast<uintptr_t>(p.colscale) & 15) == 0 && (p.colscale_zs & 3) == 0)) && (is_f32 || resid == nullptr);
     uint32_t tc = 0;
     for (int t = worker; t < total_tiles; t += n_workers) {
       const int z = t / tiles_per_z, r = t - z * tiles_per_z;
@@ -303,6 +307,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mrow0 = m0 + q * 32;            // first row of this warp's 32-row slab
       float rm = 1.0f;                          // row multiplier of the accumulator row this lane owns
       if (p.rowmul && mrow0 + lane < p.M) rm = __ldg(p.rowmul + z2 * p.rowmul_zs + mrow0 + lane);
+      float row_sub = 0.0f;                     // per-row subtrahend (row log-sum-exp / delta of the attention gradients)
+      if (GX && p.rowsub && mrow0 + lane < p.M) row_sub = __ldg(p.rowsub + z1 * p.rowsub_s1 + z2 * p.rowsub_s2 + mrow0 + lane);
+      const float* __restrict__ colscale = p.colscale ? p.colscale + (GX ? z2 * p.colscale_zs : 0) : nullptr;
       const long long zoff = z1 * p.d_s1 + z2 * p.d_s2;
       auto run_chunks = [&](auto act_c) {
         constexpr int ACT = decltype(act_c)::value;   // -1: runtime `act` (slow path only)
@@ -372,6 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < 4; ++i) {
                 const int rloc = 8 * i + rsub;
                 const float rmr = has_rm ? __shfl_sync(0xffffffffu, rm, rloc) : 1.0f;
+                const float rsr = (GX && p.rowsub) ? __shfl_sync(0xffffffffu, row_sub, rloc) : 0.0f;
                 float v[8];
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
                              : "r"(sb_u + 4u * (rloc * 32 + ((g2 ^ (rloc & 7)) << 2))));
@@ -380,9 +388,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float bb[8] = {b8[0].x, b8[0].y, b8[0].z, b8[0].w, b8[1].x, b8[1].y, b8[1].z, b8[1].w};
                 const float ss[8] = {s8[0].x, s8[0].y, s8[0].z, s8[0].w, s8[1].x, s8[1].y, s8[1].z, s8[1].w};
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = apply_act((v[u] * alpha + bb[u]) * rmr, ACT) * ss[u];
+                for (int u = 0; u < 8; ++u) v[u] = apply_act((v[u] * alpha + bb[u] - rsr) * rmr, ACT) * ss[u];
                 uint32_t h[4], l[4];
                 uint16_t* o = dptr + (long long)(8 * i) * d_ld;
+                if (GX && p.emul) {      // elementwise factor laid out like D (one 16-bit plane): dS = P * (dP - delta)
+                  const uint4 e = __ldg(reinterpret_cast<const uint4*>(p.emul + (o - static_cast<uint16_t*>(p.D))));
+                  const uint32_t ew[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float2 f = unpack16x2(ew[u], d_fmt);
+                    v[2 * u] *= f.x; v[2 * u + 1] *= f.y;
+                  }
+                }
                 if (d_lo) {
 #pragma unroll
                   for (int u = 0; u < 4; ++u) split16x2(v[2 * u], v[2 * u + 1], d_fmt, h[u], l[u]);
@@ -500,7 +517,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       if (act == VILCO_ACT_NONE) run_chunks(std::integral_constant<int, VILCO_ACT_NONE>{});
       else if (act == VILCO_ACT_RELU) run_chunks(std::integral_constant<int, VILCO_ACT_RELU>{});
-      else run_chunks(std::integral_constant<int, VILCO_ACT_GELU>{});
+      else if (GX && act == VILCO_ACT_EXP2) run_chunks(std::integral_constant<int, VILCO_ACT_EXP2>{});
+      else if (!GX) run_chunks(std::integral_constant<int, VILCO_ACT_GELU>{});
       // this warp is done reading the accumulator stage
       tcgen05_fence_before();
       __syncwarp();
@@ -639,7 +657,7 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool GX = false>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p, int Z, cudaStream_t st) {
   const int stage_bytes = p.pa * (BM * BK * 2) + p.pb * ((BN / CG) * BK * 2);
   int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - EPI_SMEM) / stage_bytes;
@@ -649,7 +667,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p,
   const int smem = 1024 + BAR_BYTES + EPI_SMEM + stages * stage_bytes;
   static bool configured = false;
   if (!configured) {
-    VILCO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    VILCO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, GX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
   const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM * CG - 1) / (BM * CG)) * Z;
@@ -665,7 +683,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmDev& p,
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  VILCO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, tmA, tmB, p));
+  VILCO_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, GX>, tmA, tmB, p));
   VILCO_LAUNCH_CHECK();
   return VILCO_OK;
 }
@@ -987,6 +1005,8 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   p.d_lo = g->d_dtype != VILCO_F32 ? g->d_lo : 0;
   p.alpha = g->alpha; p.bias = g->bias; p.rowmul = g->rowmul; p.rowmul_zs = g->rowmul_zs;
   p.act = g->act; p.colscale = g->colscale; p.resid = g->resid; p.resid_masked = g->resid_masked;
+  p.rowsub = g->rowsub; p.rowsub_s1 = g->rowsub_s1; p.rowsub_s2 = g->rowsub_s2; p.colscale_zs = g->colscale_zs;
+  p.emul = static_cast<const uint16_t*>(g->emul);
   const int esz = g->d_dtype == VILCO_F32 ? 4 : 2;
   // 16-byte vector stores / residual loads: every (row, column % vec == 0) element must be 16-byte aligned
   p.vec_ok = (reinterpret_cast<uintptr_t>(g->D) % 16 == 0) && ((g->d_ld * esz) % 16 == 0) &&
@@ -994,6 +1014,14 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
              (!g->resid || (reinterpret_cast<uintptr_t>(g->resid) % 16 == 0 && (g->d_ld * 4) % 16 == 0 &&
                             (g->d_s1 * 4) % 16 == 0 && (g->d_s2 * 4) % 16 == 0));
   const int Z = g->Z1 * g->Z2;
+  if (g->rowsub || g->emul || g->colscale_zs || g->act == VILCO_ACT_EXP2) {
+    // the fused gradient epilogues live in the bounds-free 16-bit path of the tensor-core kernel only
+    VILCO_CHECK_ARG(g->impl != 1 && g->d_dtype != VILCO_F32 && p.vec_ok && !g->resid && g->M % 32 == 0 && g->N % 32 == 0 &&
+                        (!g->bias || reinterpret_cast<uintptr_t>(g->bias) % 16 == 0) &&
+                        (!g->colscale || (reinterpret_cast<uintptr_t>(g->colscale) % 16 == 0 && g->colscale_zs % 4 == 0)) &&
+                        (!g->emul || reinterpret_cast<uintptr_t>(g->emul) % 16 == 0),
+                    "vilco_gemm: rowsub / emul / colscale_zs / ACT_EXP2 need a 16-bit output, M %% 32 == N %% 32 == 0 and 16-byte alignment");
+  }
 
   if (g->impl == 1) {
     SimtAddr q{};
@@ -1051,6 +1079,12 @@ extern "C" int vilco_gemm(const VilcoGemm* g, void* stream) {
   p.a_slot_row = sa[0]; p.a_slot_z1 = sa[1]; p.a_slot_z2 = sa[2];
   p.b_slot_row = sb[0]; p.b_slot_z1 = sb[1]; p.b_slot_z2 = sb[2];
 
+  if (g->rowsub || g->emul || g->colscale_zs || g->act == VILCO_ACT_EXP2) {      // fused attention-gradient epilogues
+    VILCO_CHECK_ARG(g->act == VILCO_ACT_NONE || g->act == VILCO_ACT_RELU || g->act == VILCO_ACT_EXP2, "vilco_gemm: act unsupported with rowsub / emul");
+    if (CG == 2) return BN == 256 ? launch_tc<256, 2, true>(tmA, tmB, p, Z, st) : launch_tc<128, 2, true>(tmA, tmB, p, Z, st);
+    VILCO_CHECK_ARG(BN >= 64, "vilco_gemm: N too small for the fused gradient epilogues");
+    return BN == 64 ? launch_tc<64, 1, true>(tmA, tmB, p, Z, st) : launch_tc<128, 1, true>(tmA, tmB, p, Z, st);
+  }
   if (CG == 2) return BN == 256 ? launch_tc<256, 2>(tmA, tmB, p, Z, st) : launch_tc<128, 2>(tmA, tmB, p, Z, st);
   switch (BN) {
     case 32: return launch_tc<32, 1>(tmA, tmB, p, Z, st);

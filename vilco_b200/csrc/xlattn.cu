@@ -39,6 +39,7 @@ struct XlDev {
   float scale;
   const float* kmask;                        // (B, T) 1 = valid key, or null
   uint16_t* O; long long o_ld, o_sh, o_sb;   // element strides: row, head, batch
+  float* lse2;                               // (B, H, T) row log-sum-exp in base 2, or null
   int fmt;
 };
 
@@ -291,7 +292,9 @@ xl_attn_kernel(const __grid_constant__ CUtensorMap tmQw, const __grid_constant__
     asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
     xs[half * 128 + row] = l;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    const float inv = 1.0f / (l + xs[(half ^ 1) * 128 + row]);
+    const float ltot = l + xs[(half ^ 1) * 128 + row];
+    const float inv = 1.0f / ltot;
+    if (p.lse2 && half == 0) p.lse2[((long long)b * p.H + h) * p.T + gi] = m_ref + log2f(ltot);
     uint32_t o[32];
     __syncwarp();
     tmem_ld32(tO + lane_addr + half * 32, o);
@@ -354,8 +357,15 @@ extern "C" int vilco_xl_attention(const void* qw, const void* qr, const void* k,
 }
 
 // Single-pass masked self-attention for single-plane operands (see include/vilco_b200.h)
+extern "C" int vilco_self_attention_lse(const void* q, const void* k, const void* v, const float* kmask, void* out, float* lse2, int B,
+                                        int H, int T, int C, float scale, void* stream);
 extern "C" int vilco_self_attention(const void* q, const void* k, const void* v, const float* kmask, void* out, int B, int H, int T,
                                     int C, float scale, void* stream) {
+  return vilco_self_attention_lse(q, k, v, kmask, out, nullptr, B, H, T, C, scale, stream);
+}
+
+extern "C" int vilco_self_attention_lse(const void* q, const void* k, const void* v, const float* kmask, void* out, float* lse2, int B,
+                                        int H, int T, int C, float scale, void* stream) {
   VILCO_CHECK_ARG(q && k && v && out, "vilco_self_attention: null pointer");
   VILCO_CHECK_ARG(H > 0 && C == H * XL_D, "vilco_self_attention: head dim must be 64 (C=%d, H=%d)", C, H);
   VILCO_CHECK_ARG(T >= XL_BQ && T % XL_BQ == 0 && T <= XL_MAX_T, "vilco_self_attention: T=%d must be a multiple of %d, <= %d", T,
@@ -375,6 +385,7 @@ extern "C" int vilco_self_attention(const void* q, const void* k, const void* v,
   p.k_slot_row = sk[0]; p.k_slot_z1 = sk[1]; p.k_slot_z2 = sk[2];
   p.T = T; p.H = H; p.scale = scale; p.kmask = kmask;
   p.O = static_cast<uint16_t*>(out); p.o_ld = C; p.o_sh = XL_D; p.o_sb = (long long)T * C;
+  p.lse2 = lse2;
   p.fmt = act_fmt();
   const int smem = 5 * XL_TILE + XL_MAX_T / 8 + 2 * 2 * 128 * 4 + 16 * 8 + 16 + 1024;
   static bool cfg = false;

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvilco_b200.so")
 
-ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_EXP2 = 0, 1, 2, 3
 F32, BF16, F16 = 0, 1, 2
 
 
@@ -36,6 +36,7 @@ class VilcoGemm(C.Structure):
         ("impl", C.c_int32),
         ("band_lo", C.c_int32), ("band_hi", C.c_int32), ("a_major", C.c_int32),
         ("a_fmt", C.c_int32), ("b_fmt", C.c_int32),
+        ("rowsub", C.c_void_p), ("rowsub_s1", C.c_int64), ("rowsub_s2", C.c_int64), ("colscale_zs", C.c_int64), ("emul", C.c_void_p),
     ]
 
 
@@ -55,8 +56,8 @@ def lib():
         _lib.vilco_launch_count.restype = C.c_uint64
         _lib.vilco_version.restype = C.c_int
         _lib.vilco_nms_workspace_bytes.restype = C.c_size_t
-        if _lib.vilco_version() < 2:
-            raise VilcoError(f"{LIB_PATH} is stale (ABI version {_lib.vilco_version()} < 2): rebuild it")
+        if _lib.vilco_version() < 3:
+            raise VilcoError(f"{LIB_PATH} is stale (ABI version {_lib.vilco_version()} < 3): rebuild it")
     return _lib
 
 
@@ -99,11 +100,12 @@ _gemm_fn = None
 
 def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), d_s=(0, 0), Z=(1, 1), taps=1,
          b_major=0, b_batched=False, alpha=1.0, bias=None, rowmul=None, rowmul_zs=0, act=ACT_NONE,
-         colscale=None, resid=None, resid_masked=False, impl=None, a_lo=0, b_lo=0, d_lo=0, band=(0, 0), a_major=0):
+         colscale=None, resid=None, resid_masked=False, impl=None, a_lo=0, b_lo=0, d_lo=0, band=(0, 0), a_major=0,
+         rowsub=None, rowsub_s=(0, 0), colscale_zs=0, emul=None):
     """Raw descriptor-level call of ``vilco_gemm`` (see include/vilco_b200.h for the contract)."""
     global _gemm_fn
     key = (M, N, K, a_rows, a_ld, b_ld, d_ld, a_s, b_s, d_s, Z, taps, b_major, b_batched, alpha, rowmul_zs, act, resid_masked,
-           impl, a_lo, b_lo, d_lo, band, a_major, A.dtype, B.dtype, D.dtype)
+           impl, a_lo, b_lo, d_lo, band, a_major, A.dtype, B.dtype, D.dtype, rowsub_s, colscale_zs)
     g = _gemm_cache.get(key)
     if g is None:
         assert A.dtype in _FMT and B.dtype in _FMT and A.is_cuda and B.is_cuda, "operands must be fp16 / bf16 planes"
@@ -123,6 +125,7 @@ def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), 
         g.impl = default_gemm_impl() if impl is None else impl
         g.band_lo, g.band_hi = band
         g.a_major = a_major
+        g.rowsub_s1, g.rowsub_s2, g.colscale_zs = rowsub_s[0], rowsub_s[1], colscale_zs
         _gemm_cache[key] = g
         if _gemm_fn is None:
             _gemm_fn = lib().vilco_gemm
@@ -131,6 +134,8 @@ def gemm(A, B, D, *, M, N, K, a_rows, a_ld, b_ld, d_ld, a_s=(0, 0), b_s=(0, 0), 
     g.rowmul = rowmul.data_ptr() if rowmul is not None else None
     g.colscale = colscale.data_ptr() if colscale is not None else None
     g.resid = resid.data_ptr() if resid is not None else None
+    g.rowsub = rowsub.data_ptr() if rowsub is not None else None
+    g.emul = emul.data_ptr() if emul is not None else None
     rc = _gemm_fn(C.byref(g), stream_ptr())
     if rc != 0:
         check(rc, "vilco_gemm")

@@ -6,6 +6,7 @@ of libvilco_b200.so.  No PyTorch compute fallback exists: without the CUDA libra
 """
 import ctypes as C
 import math
+import os
 
 import torch
 from torch import nn
@@ -18,6 +19,8 @@ from ..utils.nms import _run as _nms_run
 from .blocks import LayerNorm, MaskedConv1D, Scale
 from .models import make_backbone, make_generator, make_neck, register_meta_arch
 
+
+NOSYNC_STEP = os.environ.get("VILCO_NOSYNC_STEP", "1") == "1"   # 0: read the loss sums on the host between forward and backward
 
 class BiasLayer(nn.Module):
     """BiC bias-correction layer (reference: meta_archs.py:26-36)."""
@@ -157,11 +160,12 @@ class _TapeLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hook, value, run_backward, keys, *params):
         ctx.run_backward, ctx.keys, ctx.shapes = run_backward, keys, [(p.shape, p.dtype, p.device) for p in params]
+        ctx.nosync = bool(getattr(run_backward, "nosync", False))
         return value.detach().clone()
 
     @staticmethod
     def backward(ctx, g):
-        grads = ctx.run_backward(float(g)) or {}
+        grads = ctx.run_backward(g if ctx.nosync else float(g)) or {}
         outs = []
         for k, (shape, dtype, dev) in zip(ctx.keys, ctx.shapes):
             gk = grads.get(k)
@@ -289,6 +293,7 @@ class PtTransformer(nn.Module):
         self.sigma_reg_left = nn.Parameter(torch.ones(K, 1))
         self.mu_reg_right = nn.Parameter(torch.ones(K, 1) * 0.5)
         self.sigma_reg_right = nn.Parameter(torch.ones(K, 1))
+        self._ln_host, self._ln_dev = None, None
         self.loss_normalizer = tc["init_loss_norm"]
         self.loss_normalizer_momentum = 0.9
         self.reg_params = {}
@@ -404,6 +409,23 @@ class PtTransformer(nn.Module):
         self._ptab = None
 
     # ---- weights ---------------------------------------------------------------------------------
+    # ---- loss normaliser (EMA of the number of positives, meta_archs.py:1425-1431): a python float for the orchestration, a
+    # device scalar for the training step, synchronised lazily so that a step issues forward AND backward without waiting ----
+    @property
+    def loss_normalizer(self):
+        if self._ln_host is None:
+            self._ln_host = float(self._ln_dev)          # the one host read; happens when somebody asks (logging, checkpoints)
+        return self._ln_host
+
+    @loss_normalizer.setter
+    def loss_normalizer(self, v):
+        self._ln_host, self._ln_dev = float(v), None
+
+    def _ln_device(self, dev):
+        if self._ln_dev is None or self._ln_dev.device != dev:
+            self._ln_dev = torch.full((), float(self._ln_host), device=dev, dtype=torch.float32)
+        return self._ln_dev
+
     def engine_cfg(self):
         c = _Cfg()
         c.embd_dim, c.n_head, c.arch, c.scale_factor = self.embd_dim, self.n_head, self.backbone_arch, self.scale_factor
@@ -716,10 +738,20 @@ class PtTransformer(nn.Module):
                 ops._p(logits), ops._p(offsets), ops._p(pmask), ops._p(pyr.gap_rows), ops._p(gt_cls), ops._p(gt_off),
                 ops._p(wcd), ops._p(wld), ops._p(wrd), ops._p(present), B, P, K, C.c_float(0.25), C.c_float(2.0), ops._p(sums),
                 ops._p(scratch), L.stream_ptr()), "vilco_mq_losses")
-            s = sums.cpu()
-            self.loss_normalizer = self.loss_normalizer_momentum * self.loss_normalizer + \
-                (1 - self.loss_normalizer_momentum) * max(float(s[2]), 1)
-            norm = float(self.loss_normalizer)
+            # no host round trip between forward and backward (the deep pyramid levels at the start of the backward are
+            # launch-bound, so the host must already be ahead when the GPU gets there): the normaliser lives on the device.
+            # The reference's adaptive regression weight (train_loss_weight <= 0) needs the loss VALUES on the host.
+            nosync = self.train_loss_weight > 0 and dev.type == "cuda" and NOSYNC_STEP
+            if nosync:
+                norm = self.loss_normalizer_momentum * self._ln_device(dev) + \
+                    (1 - self.loss_normalizer_momentum) * sums[2].clamp(min=1.0)
+                self._ln_dev, self._ln_host = norm, None
+                s = None
+            else:
+                s = sums.cpu()
+                self.loss_normalizer = self.loss_normalizer_momentum * self.loss_normalizer + \
+                    (1 - self.loss_normalizer_momentum) * max(float(s[2]), 1)
+                norm = float(self.loss_normalizer)
             cls_loss, reg_loss = sums[0] / norm, sums[1] / norm
             al_loss = sums[3] / norm if K != 1 else torch.zeros((), device=dev)
             w_reg = self.train_loss_weight if self.train_loss_weight > 0 else float(s[0] / norm) / max(float(s[1] / norm), 0.01)
@@ -758,8 +790,12 @@ class PtTransformer(nn.Module):
                 L.check(L.lib().vilco_mq_losses_bwd(
                     ops._p(logits), ops._p(offsets), ops._p(pmask), ops._p(pyr.gap_rows), ops._p(gt_cls), ops._p(gt_off),
                     ops._p(wcd), ops._p(wld), ops._p(wrd), ops._p(present), ops._p(scratch), B, P, K, C.c_float(0.25),
-                    C.c_float(2.0), C.c_float(norm / gscale), C.c_float(w_reg), C.c_float(w_al), ops._p(dlogits),
+                    C.c_float(2.0), C.c_float(1.0 if nosync else norm / gscale), C.c_float(w_reg), C.c_float(w_al), ops._p(dlogits),
                     ops._p(doffsets), ops._p(dwc), ops._p(dwl), ops._p(dwr), L.stream_ptr()), "vilco_mq_losses_bwd")
+                if nosync:       # every output is linear in gscale / norm: applied from the device scalars
+                    fac = gscale / norm
+                    for t_ in (dlogits, doffsets, dwc, dwl, dwr):
+                        t_.mul_(fac)
                 logitsV.g, offsetsV.g = dlogits, doffsets
                 model._last_head_grads = (dlogits, doffsets, pyr)   # kept for the gradient parity tests
             owned_p = [p_ for _, p_ in owned]
@@ -778,7 +814,7 @@ class PtTransformer(nn.Module):
                         q_.grad = g_.clone() if q_.grad is None else q_.grad + g_
                 return out[:len(leaves)]
 
-            tensors, grads = list(extra), [torch.full_like(t_, gscale) for t_ in extra]
+            tensors, grads = list(extra), [torch.ones_like(t_) * gscale for t_ in extra]
             if lg_leaf is not None and lg_biased is not lg_leaf:
                 tensors.append(lg_biased)        # through the bias layers back to the raw logits
                 grads.append(dlogits)
@@ -838,6 +874,7 @@ class PtTransformer(nn.Module):
             return returned
 
         hook = torch.zeros((), device=dev, requires_grad=True)
+        run_backward.nosync = nosync
         final_t = _TapeLoss.apply(hook, final, run_backward, [k for k, _ in live], *[p_ for _, p_ in live])
         out = {"cls_loss": cls_loss, "reg_loss": reg_loss, "al_loss": al_loss, "final_loss": final_t}
         out.update(extra_named)

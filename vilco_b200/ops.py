@@ -227,13 +227,44 @@ def attention(q, k, v, kmask, H, scale):
     return out
 
 
-def self_attention(q, k, v, kmask, H, scale):
-    """Single-pass masked self-attention (csrc/xlattn.cu, REL = false): q / k / v (1,B,T,C) -> operand (1,B,T,C)."""
+def self_attention(q, k, v, kmask, H, scale, want_lse=False):
+    """Single-pass masked self-attention (csrc/xlattn.cu, REL = false): q / k / v (1,B,T,C) -> operand (1,B,T,C)
+    [, lse2 (B,H,T) fp32: the row log-sum-exp (base 2) of the scaled masked scores, for the fused gradient epilogues]."""
     _, B, T, Cc = q.shape
     assert q.shape[0] == 1 and k.shape == q.shape and v.shape == q.shape
     out = empty16(B, T, Cc, device=q.device, planes=1)
-    L.check(L.lib().vilco_self_attention(_p(q), _p(k), _p(v), _p(kmask), _p(out), B, H, T, Cc, C.c_float(scale), L.stream_ptr()),
-            "vilco_self_attention")
+    lse = torch.empty(B, H, T, device=q.device, dtype=f32) if want_lse else None
+    L.check(L.lib().vilco_self_attention_lse(_p(q), _p(k), _p(v), _p(kmask), _p(out), _p(lse), B, H, T, Cc, C.c_float(scale),
+                                             L.stream_ptr()), "vilco_self_attention_lse")
+    return (out, lse) if want_lse else out
+
+
+LOG2E = 1.4426950408889634
+
+
+def attn_probs_from_lse(q, k, H, scale, lse2, kmask):
+    """P[b,h] = exp2(scale * log2(e) * q_h k_h^T - lse2[b,h,:,None]) * kmask[b,None,:] as ONE 16-bit plane (1,B,H,Tq,Tk): the
+    QK^T GEMM with the softmax recompute fused into its epilogue (VilcoGemm.rowsub / ACT_EXP2 / colscale)."""
+    _, B, Tq, Cc = q.shape
+    Tk = k.shape[2]
+    d = Cc // H
+    out = empty16(B, H, Tq, Tk, device=q.device, planes=1)
+    L.gemm(q, k, out, M=Tq, N=Tk, K=d, a_rows=Tq, a_ld=Cc, a_s=(d, Tq * Cc), Z=(H, B), b_ld=Cc, b_s=(d, Tk * Cc), b_batched=True,
+           d_ld=Tk, d_s=(Tq * Tk, H * Tq * Tk), alpha=scale * LOG2E, a_lo=lo(q), b_lo=lo(k), act=L.ACT_EXP2,
+           rowsub=lse2, rowsub_s=(Tq, H * Tq), colscale=kmask, colscale_zs=Tk if kmask is not None else 0)
+    return out
+
+
+def attn_dscores_fused(dO16, v, H, P16, delta_scaled, alpha):
+    """dS[b,h] = P[b,h] * (alpha * dO_h v_h^T - delta_scaled[b,h,:,None]) as one 16-bit gradient plane (1,B,H,Tq,Tk): the dO V^T
+    GEMM with the softmax backward fused into its epilogue (VilcoGemm.rowsub / emul)."""
+    _, B, Tq, Cc = dO16.shape
+    Tk = v.shape[2]
+    d = Cc // H
+    out = empty16(B, H, Tq, Tk, device=v.device, planes=1)
+    L.gemm(dO16, v, out, M=Tq, N=Tk, K=d, a_rows=Tq, a_ld=Cc, a_s=(d, Tq * Cc), Z=(H, B), b_ld=Cc, b_s=(d, Tk * Cc), b_batched=True,
+           d_ld=Tk, d_s=(Tq * Tk, H * Tq * Tk), alpha=alpha, a_lo=lo(dO16), b_lo=lo(v), rowsub=delta_scaled, rowsub_s=(Tq, H * Tq),
+           emul=P16)
     return out
 
 

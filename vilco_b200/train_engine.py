@@ -9,6 +9,8 @@ Dropout / stochastic depth are not built yet: the training forward uses the eval
 import ctypes as CT
 import math
 
+import os
+
 import torch
 
 from . import backward as BW
@@ -32,6 +34,9 @@ class V:
 
 def _add(a, b):
     return ops.axpby(a, b, 1.0, 1.0)[0]
+
+
+FUSED_ATTN_BWD = os.environ.get("VILCO_FUSED_ATTN_BWD", "1") == "1"   # 0: materialised S / softmax / dP chain for every layer
 
 
 class Tape:
@@ -217,14 +222,20 @@ class Tape:
         C = q16.shape[-1]
         if E.SELF_ATTN_SP and q16.shape == k16.shape and q16.shape[0] == 1 and v16.shape[0] == 1 and \
                 ops.xl_attention_ok(q16, q16.shape[2], C, H):
-            o = V(p16=ops.self_attention(q16, k16, v16, kmask, H, scale))       # single-pass kernel (csrc/xlattn.cu)
+            r = ops.self_attention(q16, k16, v16, kmask, H, scale, want_lse=FUSED_ATTN_BWD)   # single-pass kernel
+            o16, lse = r if FUSED_ATTN_BWD else (r, None)
+            o = V(p16=o16)
         else:
+            lse = None
             o = V(p16=ops.attention(q16, k16, v16, kmask, H, scale))
 
         def bwd():
             if o.g is None:
                 return
-            dq, dk, dv = BW.attention_bwd(o.g, q16, k16, v16, kmask, H, scale)
+            if lse is not None:      # softmax recompute / backward fused into the GEMM epilogues (backward.attention_bwd_lse)
+                dq, dk, dv = BW.attention_bwd_lse(o.g, o.p16, lse, q16, k16, v16, kmask, H, scale)
+            else:
+                dq, dk, dv = BW.attention_bwd(o.g, q16, k16, v16, kmask, H, scale)
             self.acc(q, dq); self.acc(k, dk); self.acc(v, dv)
         self.nodes.append(bwd)
         return o
