@@ -133,3 +133,37 @@ def test_class_agnostic_nms_with_segment_voting(name, soft):
     tag = f"{name}_{'soft' if soft else 'hard'}"
     assert (sc.numpy() == g[tag + "_scores"]).all() and (lb.numpy() == g[tag + "_labels"]).all()
     assert np.abs(s.numpy() - g[tag + "_segs"]).max() <= 1e-5 * np.abs(g[tag + "_segs"]).max()
+
+
+@pytest.mark.parametrize("B,K", [(32, 22), (40, 22), (3, 22)])
+def test_many_clips_take_the_single_wave_cta_shapes(B, K):
+    """the NMS launch picks its CTA shape from the grid (512 / 384 / 256 threads; shared-memory capacity 2048 / 1024 candidates
+    per class, larger classes work in the global workspace): every shape must give what a clip evaluated alone gives — which the
+    tests above pin bit-exactly to the reference extension.  One clip carries a class with more than 1024 candidates."""
+    from vilco_b200.utils import batched_nms
+    from vilco_b200.utils.nms import _run
+    rs = np.random.RandomState(B)
+    n = 6000
+    segs = torch.zeros(B, n, 2)
+    scores = torch.zeros(B, n)
+    labels = torch.zeros(B, n, dtype=torch.int32)
+    cnt = torch.zeros(B, 1, dtype=torch.int32)
+    for b in range(B):
+        m = n if b == 1 else int(rs.randint(200, 3000))
+        c = rs.uniform(0, 1024, m).astype(np.float32)
+        ln = np.exp(rs.uniform(np.log(2.0), np.log(300.0), m)).astype(np.float32)
+        segs[b, :m] = torch.from_numpy(np.stack([c - ln / 2, c + ln / 2], 1))
+        scores[b, :m] = torch.from_numpy(np.sort(rs.beta(0.5, 8, m).astype(np.float32))[::-1].copy())
+        lab = rs.randint(0, K, m)
+        if b == 1:
+            lab[: m // 3] = 5                      # a 2000-candidate class: beyond the 1024-entry shared-memory shape
+        labels[b, :m] = torch.from_numpy(lab.astype(np.int32))
+        cnt[b, 0] = m
+    out = _run(segs.cuda(), scores.cuda(), labels.cuda(), cnt.cuda(), B, 1, n, K, True, 2, 0.1, 0.99, 1e-4, 200)
+    o_s, o_sc, o_lb, o_n = (t.cpu() for t in out)
+    for b in range(B):
+        m = int(cnt[b, 0])
+        s, sc, lb = batched_nms(segs[b, :m], scores[b, :m], labels[b, :m].long(), 0.1, 1e-4, 200, True, True, 0.99)
+        k = int(o_n[b])
+        assert k == s.shape[0]
+        assert (o_s[b, :k] == s).all() and (o_sc[b, :k] == sc).all() and (o_lb[b, :k] == lb).all(), b
