@@ -280,6 +280,31 @@ def test_torch_custom_ops_call_the_kernels():
     sc, lb_ = torch.rand(300, device="cuda"), torch.randint(0, 5, (300,), device="cuda")
     s1 = torch.ops.vilco.batched_nms(segs, sc, lb_, 0.1, 1e-4, 50, True, True, 0.99, 0.75)
     assert s1[0].shape == (50, 2) and bool((s1[1][:-1] >= s1[1][1:]).all())
+    o2 = torch.ops.vilco.self_attention(q, k, v, None, 2, 0.125)
+    assert torch.equal(o2, ops.self_attention(q, k, v, None, 2, 0.125)) and rel_max(o2.float(), o.float()) < 2e-3
+    gw, gb = torch.randn(256, device="cuda"), torch.randn(256, device="cuda")
+    gn = torch.ops.vilco.groupnorm(x32, gw, gb, 32, 1e-5, True)
+    ref = torch.relu(torch.nn.functional.group_norm(x32.transpose(1, 2), 32, gw, gb, 1e-5)).transpose(1, 2)
+    assert rel_max(gn, ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,C,G", [(2, 2, 512, 32), (3, 37, 128, 32), (1, 1024, 1024, 32), (2, 8, 64, 4)])
+def test_groupnorm_and_upsample_add_kernels(B, T, C, G):
+    """csrc/fpn.cu against torch: nn.GroupNorm on (B, C, T) (statistics over the group's channels and all T), with / without
+    ReLU, fp32 and operand-plane outputs; nearest x2 upsample-add"""
+    from vilco_b200 import ops
+    with precision("fp16x3"):
+        gen = torch.Generator(device="cuda").manual_seed(B * T + C)
+        x = torch.randn(B, T, C, device="cuda", generator=gen) * 3 + 0.5
+        w, b = torch.randn(C, device="cuda", generator=gen), torch.randn(C, device="cuda", generator=gen)
+        for relu in (False, True):
+            y32, y16 = ops.groupnorm(x, w, b, G, relu=relu, out32=True, out16=True)
+            ref = torch.nn.functional.group_norm(x.double().transpose(1, 2), G, w.double(), b.double(), 1e-5).transpose(1, 2)
+            ref = torch.relu(ref) if relu else ref
+            assert rel_max(y32.double(), ref) < 1e-5 and rel_max(ops.merge16(y16).double(), ref) < 1e-5
+        lo_, hi_ = torch.randn(B, T, C, device="cuda", generator=gen), torch.randn(B, 2 * T, C, device="cuda", generator=gen)
+        want = hi_ + lo_.repeat_interleave(2, dim=1)
+        assert torch.equal(ops.upsample2_add(lo_, hi_.clone()), want)
 
 
 @pytest.mark.parametrize("mode,tol", [("fp16x3", 1e-4), ("mixed", 1e-3)])

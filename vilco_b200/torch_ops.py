@@ -11,6 +11,8 @@ Moment-Query path.  Each op validates device / dtype, allocates its outputs with
 | vilco::linear, vilco::conv3 | vilco_gemm | MaskedConv1D / nn.Conv1d k=1, k=3 / nn.Linear (MQ/libs/modeling/blocks.py:106-130) |
 | vilco::layernorm | vilco_layernorm | LayerNorm.forward (blocks.py:160-175) |
 | vilco::attention | vilco_attention | MaskedMHCA / MaskedMHA core (blocks.py:228-269, 351-410) |
+| vilco::self_attention | vilco_self_attention | MaskedMHCA core, single-pass kernel (blocks.py:351-410) |
+| vilco::groupnorm | vilco_groupnorm | nn.GroupNorm of DenseAPP (MQ/libs/modeling/utils.py:671-729) |
 | vilco::xl_attention | vilco_xl_attention | XLNetRelativeAttention.rel_attn_core (modeling_xlnet_x.py:256-320) |
 | vilco::local_attention | vilco_local_attention | LocalMaskedMHCA core (blocks.py:1038-1207) |
 | vilco::batched_nms | vilco_batched_nms (+ vilco_seg_voting) | libs.utils.nms.batched_nms (MQ/libs/utils/nms.py:103-190) |
@@ -113,4 +115,27 @@ def _(segs, scores, cls_idxs, iou_threshold, min_score, max_seg_num, use_soft_nm
     return segs.new_empty((n, 2)), scores.new_empty((n,)), cls_idxs.new_empty((n,), dtype=torch.int64)
 
 
-OPS = ("linear", "conv3", "layernorm", "attention", "xl_attention", "local_attention", "batched_nms")
+@torch.library.custom_op("vilco::self_attention", mutates_args=(), device_types="cuda")
+def self_attention(q16: torch.Tensor, k16: torch.Tensor, v16: torch.Tensor, kmask: Optional[torch.Tensor], n_head: int,
+                   scale: float) -> torch.Tensor:
+    """single-pass masked self-attention: q16 / k16 / v16 (1,B,T,C) single-plane operands, T % 128 == 0, head dim 64"""
+    return ops.self_attention(q16, k16, v16, kmask, n_head, scale)
+
+
+@self_attention.register_fake
+def _(q16, k16, v16, kmask, n_head, scale):
+    return torch.empty_like(q16)
+
+
+@torch.library.custom_op("vilco::groupnorm", mutates_args=(), device_types="cuda")
+def groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, groups: int, eps: float, relu: bool) -> torch.Tensor:
+    """nn.GroupNorm(groups, C) (+ ReLU) of token-major fp32 x (B,T,C) -> fp32"""
+    return ops.groupnorm(x, weight, bias, groups, eps, relu=relu, out32=True, out16=False)[0]
+
+
+@groupnorm.register_fake
+def _(x, weight, bias, groups, eps, relu):
+    return torch.empty_like(x)
+
+
+OPS = ("linear", "conv3", "layernorm", "groupnorm", "attention", "self_attention", "xl_attention", "local_attention", "batched_nms")
