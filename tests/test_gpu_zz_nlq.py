@@ -61,3 +61,26 @@ def test_nlq_detections_vs_reference_golden():
         assert np.abs(sc[order] - g[f"det_scores_{i}"][ref_order]).max() < 1e-4
         assert np.abs(seg[order] - g[f"det_segments_{i}"][ref_order]).max() < 2e-3
         assert (r["labels"].numpy() == 0).all()
+
+
+def test_nlq_eval_graph_equals_eager():
+    """the captured NLQ evaluation step (NlqEvalGraph) returns exactly what the eager call returns, also after the weights change"""
+    from vilco_b200.modeling.nlq import NlqEvalGraph
+    model, clips = _build()
+    batch = [dict(clips[0]), dict(clips[0])]
+    batch[1]["feats"] = clips[1]["feats"]                      # two clips of different length, one query length
+    batch[1]["duration"], batch[1]["video_id"] = clips[1]["duration"], "second"
+    eager = model(batch, is_training=False)
+    g = NlqEvalGraph(model, batch_size=2, text_len=batch[0]["query_feats"].shape[-1])
+    for _ in range(2):
+        got = g.run(batch)
+        for a, b in zip(got, eager):
+            assert torch.equal(a["segments"], b["segments"]) and torch.equal(a["scores"], b["scores"])
+            assert torch.equal(a["labels"], b["labels"]) and a["video_id"] == b["video_id"]
+    with torch.no_grad():
+        model.cls_head.cls_head.conv.bias.add_(0.5)
+    eager2 = model(batch, is_training=False)
+    got2 = g.run(batch)
+    assert g.launches > 100
+    for a, b in zip(got2, eager2):
+        assert torch.equal(a["scores"], b["scores"]) and not torch.equal(a["scores"], eager[0]["scores"])

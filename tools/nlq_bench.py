@@ -38,6 +38,19 @@ ms = e0.elapsed_time(e1) / steps
 out = {"workload": "NLQ evaluation incl. host batching, upload, decode + soft-NMS and result download (eager, no CUDA graph)",
        "clips_per_step": B, "ms_per_step": ms, "queries_per_s": B / ms * 1e3, "launches_per_step": (L.launch_count() - n0) // steps,
        "operand_mode": model.operand_mode, "segments_per_query": int(res[0]["segments"].shape[0])}
+from vilco_b200.modeling.nlq import NlqEvalGraph  # noqa: E402
+g = NlqEvalGraph(model, B, 12)
+for _ in range(3):
+    g.run(clips)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(steps):
+    res2 = g.run(clips)
+e1.record()
+torch.cuda.synchronize()
+ms_g = e0.elapsed_time(e1) / steps
+out["graph_ms_per_step"], out["graph_queries_per_s"], out["graph_launches"] = ms_g, B / ms_g * 1e3, g.launches
+out["graph_equals_eager"] = all(torch.equal(a["scores"], b["scores"]) and torch.equal(a["segments"], b["segments"]) for a, b in zip(res, res2))
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/r2_nlq_bench.json", "w"), indent=1)

@@ -314,6 +314,19 @@ class NlqPtTransformer(nn.Module):
         tmask = (torch.arange(max(tl))[None, :] < torch.tensor(tl)[:, None]).float()
         return vid.to(dev), mask.to(dev), txt.to(dev), tmask.to(dev)
 
+    def _device_forward(self, vid, mask, txt, tmask):
+        """device tensors in the reference layout -> (logits (B,P,K), offsets (B,P,2), pmask (B,P), pyramid); every step a kernel"""
+        cfg = self.cfg
+        with self._sel("heads") as W:
+            key = ("nlq_pe", self.max_seq_len, cfg.embd_dim)
+            cache = W.setdefault("_cache", {})
+            if key not in cache:
+                cache[key] = E.sinusoid_pe_table(self.max_seq_len, cfg.embd_dim, self.device)
+            pe = cache[key]
+        feats, masks = nlq_backbone_fwd(self._sel, cfg, vid, mask, txt, tmask, pe)
+        with self._sel("heads") as W:
+            return E.neck_heads_fwd(W, cfg, feats, masks)
+
     @torch.no_grad()
     def forward(self, video_list, task_id=-1, ensemble=False, hidden_state=False, is_training=True, prev_out_cls_logits=None,
                 get_emb=False, val_qilDatasetList=None):
@@ -326,22 +339,86 @@ class NlqPtTransformer(nn.Module):
             if not get_emb:
                 return [o[0] for o in outs]
             return tuple([torch.cat([o[j][l] for o in outs]) for l in range(len(outs[0][j]))] for j in range(3))
-        cfg = self.cfg
         vid, mask, txt, tmask = self._batch(video_list)
-        with self._sel("heads") as W:
-            key = ("nlq_pe", self.max_seq_len, cfg.embd_dim)
-            cache = W.setdefault("_cache", {})
-            if key not in cache:
-                cache[key] = E.sinusoid_pe_table(self.max_seq_len, cfg.embd_dim, self.device)
-            pe = cache[key]
-        feats, masks = nlq_backbone_fwd(self._sel, cfg, vid, mask, txt, tmask, pe)
-        with self._sel("heads") as W:
-            logits, offsets, pmask, pyr = E.neck_heads_fwd(W, cfg, feats, masks)
+        logits, offsets, pmask, pyr = self._device_forward(vid, mask, txt, tmask)
         if get_emb:                                                       # meta_archs.py:744-745: per-level lists
             sl = [slice(o, o + n) for o, n in zip(pyr.off, pyr.lens)]
             return ([logits[:, s] for s in sl], [offsets[:, s] for s in sl], [pmask[:, s] > 0 for s in sl])
         segs, scores, labels, count = self._decode_nms_device(pyr, pmask, logits, offsets)
         res = self._to_results(video_list, segs.cpu(), scores.cpu(), labels.cpu(), count.cpu())
+        for r, v in zip(res, video_list):
+            if "query_id" in v:
+                r["query_id"] = v["query_id"]
+        return res
+
+
+class NlqEvalGraph:
+    """One captured CUDA graph of the NLQ evaluation step for a fixed number of queries per step and a fixed query length (the
+    reference evaluates one query at a time; a step of B queries with equal text length is B such evaluations).  Eager NLQ
+    evaluation is launch-bound (221 launches, ~4.8 ms for one query); the replay is not.
+
+        g = NlqEvalGraph(model, batch_size=16, text_len=12)
+        results = g.run(video_list)            # same dicts as model(video_list, is_training=False)
+    """
+
+    def __init__(self, model, batch_size, text_len):
+        self.model, self.B, self.L = model, batch_size, text_len
+        dev = model.device
+        T = model.max_seq_len
+        self.vid = torch.zeros(batch_size, model.input_vid_dim, T, device=dev)
+        self.mask = torch.ones(batch_size, T, device=dev)
+        self.txt = torch.zeros(batch_size, model.input_txt_dim, text_len, device=dev)
+        self.tmask = torch.ones(batch_size, text_len, device=dev)
+        self._stage_v = torch.zeros(batch_size, model.input_vid_dim, T).pin_memory()
+        self._stage_t = torch.zeros(batch_size, model.input_txt_dim, text_len).pin_memory()
+        self._stage_m = torch.zeros(batch_size, T).pin_memory()
+        self._ver = None
+        self._capture()
+
+    def _sig(self):
+        m = self.model
+        return (m.operand_mode, tuple(m.exact_stages), tuple(p._version for p in m.parameters()))
+
+    @torch.no_grad()
+    def _step(self):
+        m = self.model
+        logits, offsets, pmask, pyr = m._device_forward(self.vid, self.mask, self.txt, self.tmask)
+        return m._decode_nms_device(pyr, pmask, logits, offsets)
+
+    def _capture(self):
+        from .. import lib as L
+        self._ver = self._sig()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):           # warm-up outside capture (weight packing, lazy kernel attributes, allocator pools)
+            self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = self._step()
+        self.launches = L.launch_count() - n0
+
+    def run(self, video_list):
+        m = self.model
+        assert len(video_list) == self.B and all(v["query_feats"].shape[-1] == self.L for v in video_list)
+        if self._sig() != self._ver:              # parameters or the operand policy changed: the graph reads stale packed weights
+            self._capture()
+        self._stage_v.zero_()
+        self._stage_m.zero_()
+        for i, v in enumerate(video_list):
+            n = v["feats"].shape[-1]
+            assert n <= m.max_seq_len
+            self._stage_v[i, :, :n] = v["feats"]
+            self._stage_m[i, :n] = 1.0
+            self._stage_t[i] = v["query_feats"]
+        self.vid.copy_(self._stage_v, non_blocking=True)
+        self.mask.copy_(self._stage_m, non_blocking=True)
+        self.txt.copy_(self._stage_t, non_blocking=True)
+        self.graph.replay()
+        segs, scores, labels, count = (t.cpu() for t in self.out)
+        res = m._to_results(video_list, segs, scores, labels, count)
         for r, v in zip(res, video_list):
             if "query_id" in v:
                 r["query_id"] = v["query_id"]
