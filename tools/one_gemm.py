@@ -35,6 +35,11 @@ elif which == "mlp2_32":  # FFN down projection at 32 clips: K = 4096, fp32 out 
     resid = torch.randn(32, T, C, device=dev)
     rm = torch.ones(32 * T, device=dev)
     fn = lambda: ops.linear(x32, w, ops.f32, rowmul=rm, resid=resid, resid_masked=True)
+elif which == "heads64":  # the dominant GEMM of bench.py's default step (64 clips): head tower conv over the (64, 2056, 1024) pyramid
+    xh = ops.split16(torch.randn(64, 2056, C, device=dev))
+    w3 = ops.split16(torch.randn(3, C, C, device=dev) * 0.03)
+    rm = torch.ones(64, 2056, device=dev)
+    fn = lambda: ops.conv3(xh, w3, ops.f32, rowmul=rm, flat=True)
 elif which == "heads":   # the dominant GEMM of bench.py's default step: head tower conv over the (32, 2056, 1024) pyramid
     xh = ops.split16(torch.randn(32, 2056, C, device=dev))
     w3 = ops.split16(torch.randn(3, C, C, device=dev) * 0.03)
