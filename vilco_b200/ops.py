@@ -17,7 +17,8 @@ Precision modes (`set_precision`, env VILCO_PRECISION):
 Gradient planes (the 16-bit operands the backward kernels emit) share the activation format — tcgen05 kind::f16 cannot mix
 fp16 and bf16 operands in one MMA (measured: illegal instruction).  In the fp16 modes they are stored multiplied by
 GRAD_SCALE = 2^10, which centres gradient magnitudes in the fp16 range (normal from 6e-8 / 2^10, saturating at 64), and every
-GEMM that consumes one folds 1 / GRAD_SCALE into its alpha (`ginv()`); two planes unless VILCO_BWD_PRECISION=bf16.
+GEMM that consumes one folds 1 / GRAD_SCALE into its alpha (`ginv()`).  Their plane count follows the mode (`grad_planes()`):
+one plane in `mixed` / `fp16` / `bf16`, hi + lo in the exact modes; VILCO_BWD_PRECISION = split | single overrides it.
 """
 import ctypes as C
 import os
@@ -83,9 +84,9 @@ def _i64(v):
     return C.c_int64(int(v))
 
 
-# Optional fast training mode: the backward GEMMs read only the hi plane of every operand.  Gradients then carry plain-bf16
-# operand rounding (~3e-3 relative, what bf16 autocast training has); the forward pass, the losses and therefore every parity
-# statement about outputs are unaffected.  Default: gradient planes split (hi + lo).
+# Planes of the gradient operands: "mode" (default) = what the operand mode says (grad_planes()), "split" = hi + lo everywhere,
+# "single" = one plane everywhere; "bf16" (round 1) additionally makes the backward GEMMs read only the hi plane of every
+# operand.  The forward pass, the losses and therefore every parity statement about outputs are unaffected by this knob.
 BWD_PRECISION = os.environ.get("VILCO_BWD_PRECISION", "mode")
 _single = False
 
